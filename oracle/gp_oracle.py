@@ -1,0 +1,416 @@
+"""CPU oracle for the egobox-gp kriging hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This module is a numpy/scipy (fp64) restatement of the reference algorithm
+(relf/egobox @ be16128, crates/gp).  It is the *checker* for the CUDA path:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it.  The product package ``egobox_b200``
+never imports anything from ``oracle/``.
+
+Pinning: validated by ``tests/test_oracle_golden.py`` against every tight
+fixture the reference holds for this path (kernel known-answers
+``correlation_models.rs:597-641,718-726``; ``utils.rs:150-242``;
+``mean_models.rs:169-213``; 5-point kriging ``test_gpmix.py:37-53,137-142``;
+the 16-digit serialized model in ``doc/Gpx_Tutorial.ipynb:165-167,420-421``).
+Values at n > 300, predict_var beyond toy sizes and FITC/VFE likelihoods are
+NOT pinned by any reference fixture ("parity unpinned" there).
+
+The dense factorizations live in third-party crates that are not vendored in
+/root/reference (linfa-linalg 0.2.1 default / ndarray-linalg 0.17 + LAPACK
+with feature ``blas``); they are textbook Cholesky / triangular solve / thin
+QR / SVD and are restated with LAPACK through scipy.  QR sign convention
+follows linfa-linalg (diag(R) > 0), which is what the notebook fixture shows.
+
+Citations are file:line under /root/reference/crates/gp/src/.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.linalg as sla
+
+SQEXP, ABSEXP, MATERN32, MATERN52 = 0, 1, 2, 3
+CORR_NAMES = {SQEXP: "SquaredExponential", ABSEXP: "AbsoluteExponential",
+              MATERN32: "Matern32", MATERN52: "Matern52"}
+CONSTANT, LINEAR, QUADRATIC = 0, 1, 2
+MEAN_NAMES = {CONSTANT: "Constant", LINEAR: "Linear", QUADRATIC: "Quadratic"}
+
+DEFAULT_NUGGET = 100.0 * np.finfo(np.float64).eps      # parameters.rs:118
+THETA_DEFAULT_INIT = 1e-1                                # parameters.rs:49
+THETA_DEFAULT_BOUNDS = (1e-2, 1e1)                       # parameters.rs:51
+GP_OPTIM_N_START = 10                                    # algorithm.rs:33
+GP_COBYLA_MIN_EVAL = 25                                  # algorithm.rs:35
+GP_COBYLA_MAX_EVAL = 1000                                # algorithm.rs:37
+
+
+class LinalgError(Exception):
+    """GpError::LinalgError (errors.rs:19): Cholesky of a non-PD matrix."""
+
+
+class LikelihoodComputationError(Exception):
+    """GpError::LikelihoodComputationError (errors.rs:11)."""
+
+
+# --------------------------------------------------------------------------
+# utils.rs
+# --------------------------------------------------------------------------
+def normalize(x):
+    """utils.rs:45-54: column mean, std (ddof=1, 0 -> 1), (x - mean) / std."""
+    x = np.asarray(x, dtype=np.float64)
+    mean = x.mean(axis=0)
+    std = x.std(axis=0, ddof=1)
+    std = np.where(std == 0.0, 1.0, std)
+    return (x - mean) / std, mean, std
+
+
+def diff_matrix(x):
+    """utils.rs:80-104: |x_k - x_i| for all k < i, row order (0,1),(0,2)...,
+    plus the (k, i) index table."""
+    x = np.asarray(x, dtype=np.float64)
+    n, nx = x.shape
+    npairs = n * (n - 1) // 2
+    d = np.zeros((npairs, nx))
+    idx = np.zeros((npairs, 2), dtype=np.int64)
+    pos = 0
+    for k in range(n - 1):
+        cnt = n - k - 1
+        d[pos:pos + cnt] = x[k] - x[k + 1:]
+        idx[pos:pos + cnt, 0] = k
+        idx[pos:pos + cnt, 1] = np.arange(k + 1, n)
+        pos += cnt
+    return np.abs(d), idx
+
+
+def pairwise_differences(x, y):
+    """utils.rs:110-131: (nx*ny, d) array, row i*ny+j = x_i - y_j."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    assert x.shape[1] == y.shape[1]
+    return (x[:, None, :] - y[None, :, :]).reshape(-1, x.shape[1])
+
+
+# --------------------------------------------------------------------------
+# mean_models.rs
+# --------------------------------------------------------------------------
+def mean_value(kind, x):
+    """mean_models.rs:42-44 (constant), :68-71 (linear), :97-104 (quadratic:
+    [1, x_i, {x_k * x_j, j >= k} for k = 0..nx-1])."""
+    x = np.asarray(x, dtype=np.float64)
+    n, nx = x.shape
+    if kind == CONSTANT:
+        return np.ones((n, 1))
+    res = np.concatenate([np.ones((n, 1)), x], axis=1)
+    if kind == LINEAR:
+        return res
+    parts = [res]
+    for k in range(nx):
+        parts.append(x[:, k:] * x[:, k:k + 1])
+    return np.concatenate(parts, axis=1)
+
+
+def mean_nbasis(kind, nx):
+    return {CONSTANT: 1, LINEAR: nx + 1, QUADRATIC: (nx + 1) * (nx + 2) // 2}[kind]
+
+
+# --------------------------------------------------------------------------
+# correlation_models.rs  (value only)
+# --------------------------------------------------------------------------
+def corr_value(kind, d, theta, w):
+    """r(d; theta, W) for a (P, nx) array of component differences.
+
+    SqExp   correlation_models.rs:91-104
+    AbsExp  :185-196
+    Matern32 :277-286, 326-353
+    Matern52 :446-455, 497-523
+    Returns shape (P,)."""
+    d = np.asarray(d, dtype=np.float64)
+    theta = np.asarray(theta, dtype=np.float64).reshape(-1)
+    w = np.asarray(w, dtype=np.float64)
+    assert w.shape == (d.shape[1], theta.shape[0]), (w.shape, d.shape, theta.shape)
+    if kind == SQEXP:
+        theta_w = ((theta * w) ** 2).sum(axis=1)
+        r = (d ** 2).dot(theta_w)
+        return np.exp(-0.5 * r)
+    if kind == ABSEXP:
+        theta_w = np.abs(w).dot(theta)
+        r = np.abs(d).dot(theta_w)
+        return np.exp(-r)
+    theta_w = theta * np.abs(w)                       # (nx, h)
+    abs_d = np.abs(d)
+    a = np.ones(d.shape[0])
+    if kind == MATERN32:
+        s = math.sqrt(3.0)
+        for j in range(d.shape[1]):
+            for l in range(theta_w.shape[1]):
+                a *= 1.0 + s * theta_w[j, l] * abs_d[:, j]
+        b = np.exp(-s * abs_d.dot(theta_w).sum(axis=1))
+        return a * b
+    if kind == MATERN52:
+        s = math.sqrt(5.0)
+        c = 5.0 / 3.0
+        for j in range(d.shape[1]):
+            for l in range(theta_w.shape[1]):
+                v = theta_w[j, l]
+                a *= 1.0 + s * v * abs_d[:, j] + c * (v * v * d[:, j] * d[:, j])
+        b = np.exp(-s * abs_d.dot(theta_w).sum(axis=1))
+        return a * b
+    raise ValueError(kind)
+
+
+def corr_matrix(kind, xnorm, theta, w, nugget=DEFAULT_NUGGET, chunk=256):
+    """R = (1+nugget) I + symmetric scatter of r over pairs.
+
+    Same values as DiffMatrix + value + the scatter at algorithm.rs:997-1001
+    but built row-block by row-block so that the (P, nx) difference table
+    (2.68 GB at n=8192, d=10) is never materialised."""
+    x = np.asarray(xnorm, dtype=np.float64)
+    n = x.shape[0]
+    R = np.empty((n, n))
+    for i0 in range(0, n, chunk):
+        i1 = min(n, i0 + chunk)
+        dx = pairwise_differences(x[i0:i1], x)
+        R[i0:i1] = corr_value(kind, np.abs(dx), theta, w).reshape(i1 - i0, n)
+    R[np.diag_indices(n)] = 1.0 + nugget
+    return R
+
+
+# --------------------------------------------------------------------------
+# algorithm.rs: reduced likelihood
+# --------------------------------------------------------------------------
+@dataclass
+class InnerParams:
+    """GpInnerParams, algorithm.rs:47-60."""
+    sigma2: float
+    beta: np.ndarray      # (p, 1)
+    gamma: np.ndarray     # (n, 1)
+    r_chol: np.ndarray    # (n, n) lower
+    ft: np.ndarray        # (n, p)
+    ft_qr_r: np.ndarray   # (p, p) upper, diag > 0
+
+
+def _qr_pos(a):
+    """Thin QR with diag(R) > 0 (linfa-linalg / nalgebra convention)."""
+    q, r = np.linalg.qr(a, mode="reduced")
+    sgn = np.sign(np.diag(r))
+    sgn[sgn == 0] = 1.0
+    return q * sgn, (r.T * sgn).T
+
+
+def reduced_likelihood_from_R(fx, R, ynorm, y_std, copy=True):
+    """algorithm.rs:1002-1055 given the assembled correlation matrix R."""
+    n = R.shape[0]
+    try:
+        r_chol = sla.cholesky(R, lower=True, overwrite_a=not copy, check_finite=False)
+    except sla.LinAlgError as e:                               # :1004 `?`
+        raise LinalgError(str(e))
+    if not np.all(np.isfinite(np.diag(r_chol))):
+        raise LinalgError("non finite Cholesky factor")
+    ft = sla.solve_triangular(r_chol, fx, lower=True, check_finite=False)      # :1006
+    q, g = _qr_pos(ft)                                                          # :1007
+    sv = np.linalg.svd(g, compute_uv=False)                                     # :1010
+    cond_ft = sv[-1] / sv[0]
+    if cond_ft < 1e-10:                                                         # :1012
+        sv_f = np.linalg.svd(fx, compute_uv=False)
+        cond_fx = sv_f[0] / sv_f[-1]
+        if cond_fx > 1e15:
+            raise LikelihoodComputationError("F is too ill conditioned")
+        raise LikelihoodComputationError("ft is too ill conditioned")
+    yt = sla.solve_triangular(r_chol, ynorm, lower=True, check_finite=False)    # :1028
+    beta = sla.solve_triangular(g, q.T.dot(yt), lower=False, check_finite=False)  # :1030
+    rho = yt - ft.dot(beta)                                                     # :1031
+    rho_sqr = (rho * rho).sum(axis=0)
+    gamma = sla.solve_triangular(r_chol.T, rho, lower=False, check_finite=False)  # :1034
+    logdet = np.log10(np.diag(r_chol)).sum() * 2.0 / n                          # :1039
+    sigma2 = rho_sqr / n                                                        # :1042
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rlf = -n * (np.log10(sigma2.sum()) + logdet)                            # :1043
+    inner = InnerParams(sigma2=float(sigma2[0] * y_std * y_std), beta=beta, gamma=gamma,
+                        r_chol=np.tril(r_chol), ft=ft, ft_qr_r=g)
+    return float(rlf), inner
+
+
+def reduced_likelihood(kind, xnorm, fx, ynorm, y_std, theta, w, nugget=DEFAULT_NUGGET):
+    """objfn body (algorithm.rs:892-893) + reduced_likelihood (:989-1056)."""
+    R = corr_matrix(kind, xnorm, theta, w, nugget)
+    return reduced_likelihood_from_R(fx, R, np.asarray(ynorm).reshape(-1, 1), y_std, copy=False)
+
+
+def objective(kind, xnorm, fx, ynorm, y_std, theta, w, nugget=DEFAULT_NUGGET):
+    """-rlf with the Err -> +inf, NaN -> +inf mapping of algorithm.rs:880-897."""
+    theta = np.asarray(theta, dtype=np.float64)
+    if np.any(np.isnan(theta)):
+        return math.inf
+    try:
+        rlf, _ = reduced_likelihood(kind, xnorm, fx, ynorm, y_std, theta, w, nugget)
+    except (LinalgError, LikelihoodComputationError):
+        return math.inf
+    return -rlf
+
+
+# --------------------------------------------------------------------------
+# optimization.rs
+# --------------------------------------------------------------------------
+def lhs_classic(xlimits, ns, rng):
+    """LHS *construction* of crates/doe/src/lhs.rs (one uniform draw per
+    stratum, independent permutation per column).  The reference's maximin
+    optimisation and its Xoshiro256Plus stream are not reproduced."""
+    xlimits = np.asarray(xlimits, dtype=np.float64)
+    nx = xlimits.shape[0]
+    cut = np.linspace(0.0, 1.0, ns + 1)
+    u = rng.random((ns, nx))
+    pts = cut[:ns, None] + u * (cut[1:, None] - cut[:ns, None])
+    out = np.empty_like(pts)
+    for j in range(nx):
+        out[:, j] = pts[rng.permutation(ns), j]
+    return xlimits[:, 0] + out * (xlimits[:, 1] - xlimits[:, 0])
+
+
+def prepare_multistart(n_start, theta0, bounds, rng=None):
+    """optimization.rs:26-71: log10 bounds; row 0 = log10(theta0); rows 1.. =
+    LHS points in the log10 box (reference: maximin LHS, Xoshiro seed 42)."""
+    bounds = [(math.log10(lo), math.log10(hi)) for lo, hi in bounds]
+    theta0 = np.asarray(theta0, dtype=np.float64)
+    theta0s = np.zeros((n_start + 1, theta0.size))
+    theta0s[0] = np.log10(theta0)
+    rng = np.random.default_rng(42) if rng is None else rng
+    if n_start == 1:
+        theta0s[1] = [rng.uniform(a, b) for a, b in bounds]
+    elif n_start > 1:
+        theta0s[1:] = lhs_classic(np.array(bounds), n_start, rng)
+    return theta0s, bounds
+
+
+# --------------------------------------------------------------------------
+# algorithm.rs: GaussianProcess
+# --------------------------------------------------------------------------
+@dataclass
+class GaussianProcess:
+    """Trained state, algorithm.rs:174-192."""
+    corr: int
+    mean: int
+    theta: np.ndarray
+    likelihood: float
+    inner: InnerParams
+    w_star: np.ndarray
+    xt_norm: np.ndarray
+    x_mean: np.ndarray
+    x_std: np.ndarray
+    yt_norm: np.ndarray
+    y_mean: float
+    y_std: float
+    training_data: tuple = field(default=None, repr=False)
+
+    # algorithm.rs:372-380
+    def _compute_correlation(self, xnorm):
+        dx = pairwise_differences(xnorm, self.xt_norm)
+        r = corr_value(self.corr, dx, self.theta, self.w_star)
+        return r.reshape(xnorm.shape[0], self.xt_norm.shape[0])
+
+    # algorithm.rs:330-369
+    def _compute_rt_u(self, xnorm, corr):
+        rt = sla.solve_triangular(self.inner.r_chol, corr.T, lower=True, check_finite=False)
+        rhs = self.inner.ft.T.dot(rt) - mean_value(self.mean, xnorm).T
+        u = sla.solve_triangular(self.inner.ft_qr_r.T, rhs, lower=True, check_finite=False)
+        return rt, u
+
+    def _xnorm(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        return (x - self.x_mean) / self.x_std
+
+    # algorithm.rs:253-263
+    def predict(self, x, chunk=1024):
+        out = []
+        x = np.asarray(x, dtype=np.float64)
+        for i0 in range(0, x.shape[0], chunk):
+            xn = self._xnorm(x[i0:i0 + chunk])
+            f = mean_value(self.mean, xn)
+            corr = self._compute_correlation(xn)
+            y_ = f.dot(self.inner.beta) + corr.dot(self.inner.gamma)
+            out.append((y_ * self.y_std + self.y_mean)[:, 0])
+        return np.concatenate(out)
+
+    # algorithm.rs:267-279
+    def predict_var(self, x, chunk=1024):
+        return self.predict_valvar(x, chunk)[1]
+
+    # algorithm.rs:282-307
+    def predict_valvar(self, x, chunk=1024):
+        ys, vs = [], []
+        x = np.asarray(x, dtype=np.float64)
+        for i0 in range(0, x.shape[0], chunk):
+            xn = self._xnorm(x[i0:i0 + chunk])
+            f = mean_value(self.mean, xn)
+            corr = self._compute_correlation(xn)
+            y_ = f.dot(self.inner.beta) + corr.dot(self.inner.gamma)
+            ys.append((y_ * self.y_std + self.y_mean)[:, 0])
+            rt, u = self._compute_rt_u(xn, corr)
+            mse = 1.0 - (rt * rt).sum(axis=0) + (u * u).sum(axis=0)
+            mse = self.inner.sigma2 * mse
+            vs.append(np.where(mse < 0.0, 0.0, mse))
+        return np.concatenate(ys), np.concatenate(vs)
+
+
+def _theta0(theta_init, dim):
+    theta_init = np.atleast_1d(np.asarray(theta_init, dtype=np.float64))
+    if theta_init.size == 1:
+        return np.full(dim, theta_init[0])
+    assert theta_init.size == dim          # algorithm.rs:835 panics otherwise
+    return theta_init.copy()
+
+
+def fit(x, y, corr=SQEXP, mean=CONSTANT, theta_init=THETA_DEFAULT_INIT,
+        theta_bounds=THETA_DEFAULT_BOUNDS, fixed=False, n_start=GP_OPTIM_N_START,
+        max_eval=GP_COBYLA_MAX_EVAL, nugget=DEFAULT_NUGGET, w_star=None, rng=None,
+        trace=None):
+    """impl Fit for GpValidParams::fit, algorithm.rs:791-979 (no KPLS: the PLS
+    rotations come from linfa-pls; pass ``w_star`` explicitly to exercise the
+    weighted kernels).  Optimiser: scipy's COBYLA with rhobeg 0.5
+    (optimization.rs:16-24); the reference's cobyla 0.8 crate trajectory is
+    not reproduced, only its objective, bounds, multistart and reduction."""
+    from scipy.optimize import minimize
+
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    nx = x.shape[1]
+    w = np.eye(nx) if w_star is None else np.asarray(w_star, dtype=np.float64)
+    dim = w.shape[1]
+    theta0 = _theta0(theta_init, dim)
+    xn, xm, xs = normalize(x)
+    yn, ym, ys = normalize(y)
+    fx = mean_value(mean, xn)
+    y_std = float(ys[0])
+
+    if fixed:
+        theta = theta0
+    else:
+        b = np.atleast_2d(np.asarray(theta_bounds, dtype=np.float64))
+        bounds = [tuple(b[0])] * dim if b.shape[0] == 1 else [tuple(r) for r in b]
+        inits, lbounds = prepare_multistart(n_start, theta0, bounds, rng)
+        maxeval = min(max(10 * dim, GP_COBYLA_MIN_EVAL), max_eval)       # :936-937
+        lo = np.array([p[0] for p in lbounds])
+        hi = np.array([p[1] for p in lbounds])
+
+        def objfn(z):
+            th = 10.0 ** np.clip(z, lo, hi)
+            v = objective(corr, xn, fx, yn, y_std, th, w, nugget)
+            if trace is not None:
+                trace.append((th.copy(), v))
+            return v if np.isfinite(v) else 1e300
+
+        best = (math.inf, np.zeros(dim))
+        for i in range(inits.shape[0]):
+            res = minimize(objfn, inits[i], method="COBYLA", bounds=list(zip(lo, hi)),
+                           options=dict(rhobeg=0.5, maxiter=maxeval, tol=1e-4))
+            f = res.fun if np.isfinite(res.fun) and res.fun < 1e299 else math.inf
+            if f < best[0]:
+                best = (f, np.clip(res.x, lo, hi))
+        theta = 10.0 ** best[1]
+
+    rlf, inner = reduced_likelihood(corr, xn, fx, yn, y_std, theta, w, nugget)   # :966-968
+    return GaussianProcess(corr=corr, mean=mean, theta=np.asarray(theta), likelihood=rlf,
+                           inner=inner, w_star=w, xt_norm=xn, x_mean=xm, x_std=xs,
+                           yt_norm=yn, y_mean=float(ym[0]), y_std=y_std,
+                           training_data=(x, y[:, 0]))

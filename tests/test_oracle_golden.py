@@ -1,0 +1,181 @@
+"""Pins the CPU oracle against every tight fixture the reference holds for the path.
+
+Fixture values below are transcribed verbatim from the reference's own tests /
+stored notebook outputs (file:line cited per test)."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as O
+
+
+# ---- correlation_models.rs:597-641, 718-726 --------------------------------
+def test_squared_exponential_1d():
+    xt = np.array([[4.5], [1.2], [2.0], [3.0], [4.0]])
+    d, _ = O.diff_matrix(xt)
+    res = O.corr_value(O.SQEXP, d, [math.sqrt(0.2)], np.array([[1.0]]))
+    expected = [0.336552878364737, 0.5352614285189903, 0.7985162187593771, 0.9753099120283326,
+                0.9380049995307295, 0.7232502423798424, 0.4565760496233148, 0.9048374180359595,
+                0.6703200460356393, 0.9048374180359595]
+    np.testing.assert_allclose(res, expected, atol=1e-12)
+
+
+def test_squared_exponential_2d():
+    xt = np.array([[0.0, 1.0], [2.0, 3.0], [4.0, 5.0]])
+    d, _ = O.diff_matrix(xt)
+    res = O.corr_value(O.SQEXP, d, [math.sqrt(2.0), 2.0], np.eye(2))
+    np.testing.assert_allclose(res, [6.14421235e-06, 1.42516408e-21, 6.14421235e-06], atol=1e-6, rtol=1e-8)
+
+
+def test_matern32_2d():
+    xt = np.array([[0.0, 1.0], [2.0, 3.0], [4.0, 5.0]])
+    d, _ = O.diff_matrix(xt)
+    res = O.corr_value(O.MATERN32, d, [1.0, 2.0], np.eye(2))
+    np.testing.assert_allclose(res, [1.08539595e-03, 1.10776401e-07, 1.08539595e-03], atol=1e-6, rtol=1e-8)
+
+
+def test_matern52_2d():
+    xt = np.array([[0.0, 1.0], [2.0, 3.0], [4.0, 5.0]])
+    d, _ = O.diff_matrix(xt)
+    res = O.corr_value(O.MATERN52, d, [1.0, 2.0], np.eye(2))
+    np.testing.assert_allclose(res, [6.62391590e-04, 1.02117882e-08, 6.62391590e-04], atol=1e-6, rtol=1e-8)
+
+
+# ---- utils.rs:150-242 -------------------------------------------------------
+def test_pairwise_differences():
+    x = np.array([[-0.9486833], [-0.82219219]])
+    y = np.array([[-1.26491106], [-0.63245553], [0.0], [0.63245553], [1.26491106]])
+    exp = [0.31622777, -0.31622777, -0.9486833, -1.58113883, -2.21359436,
+           0.44271887, -0.18973666, -0.82219219, -1.45464772, -2.08710326]
+    np.testing.assert_allclose(O.pairwise_differences(x, y)[:, 0], exp, atol=1e-6)
+
+
+def test_normalized_matrix():
+    xn, mean, std = O.normalize(np.array([[1.0, 2.0], [3.0, 4.0]]))
+    assert list(mean) == [2.0, 3.0]
+    assert list(std) == [math.sqrt(2.0), math.sqrt(2.0)]
+
+
+def test_normalize_constant_column():
+    xn, mean, std = O.normalize(np.array([[1.0, 2.0], [1.0, 4.0]]))
+    assert std[0] == 1.0 and np.all(xn[:, 0] == 0.0)
+
+
+def test_diff_matrix():
+    xt = np.array([[0.5], [1.2], [2.0], [3.0], [4.0]])
+    d, idx = O.diff_matrix(xt)
+    np.testing.assert_allclose(d[:, 0], [0.7, 1.5, 2.5, 3.5, 0.8, 1.8, 2.8, 1.0, 2.0, 1.0], atol=1e-15)
+    assert idx.tolist() == [[0, 1], [0, 2], [0, 3], [0, 4], [1, 2], [1, 3], [1, 4], [2, 3], [2, 4], [3, 4]]
+
+
+# ---- mean_models.rs:169-213 -------------------------------------------------
+def test_quadratic_basis():
+    a = np.array([[1.0, 2.0, 3.0], [3.0, 4.0, 5.0]])
+    exp = np.array([[1.0, 1.0, 2.0, 3.0, 1.0, 2.0, 3.0, 4.0, 6.0, 9.0],
+                    [1.0, 3.0, 4.0, 5.0, 9.0, 12.0, 15.0, 16.0, 20.0, 25.0]])
+    np.testing.assert_array_equal(O.mean_value(O.QUADRATIC, a), exp)
+    assert O.mean_value(O.LINEAR, a).shape == (2, 4)
+    assert O.mean_value(O.CONSTANT, a).shape == (2, 1)
+    assert O.mean_nbasis(O.QUADRATIC, 3) == 10
+
+
+# ---- doc/Gpx_Tutorial.ipynb:420-421 : the 16-digit full model ----------------
+def _arr(o):
+    return np.array(o["data"], dtype=np.float64).reshape(o["dim"])
+
+
+@pytest.fixture(scope="module")
+def nb_model(golden_dir):
+    with open(os.path.join(golden_dir, "gpx_tutorial_linear_matern52.json")) as f:
+        return json.load(f)
+
+
+def test_notebook_full_model(nb_model):
+    m = nb_model
+    xt, yt = _arr(m["training_data"][0]), _arr(m["training_data"][1])
+    theta = _arr(m["theta"])
+    gp = O.fit(xt, yt, corr=O.MATERN52, mean=O.LINEAR, theta_init=theta, fixed=True,
+               nugget=m["params"]["nugget"])
+    ip = m["inner_params"]
+    np.testing.assert_allclose(gp.xt_norm, _arr(m["xt_norm"]["data"]), rtol=0, atol=5e-16)
+    np.testing.assert_allclose(gp.x_std, _arr(m["xt_norm"]["std"]), rtol=1e-15)
+    np.testing.assert_allclose(gp.yt_norm, _arr(m["yt_norm"]["data"]), rtol=0, atol=5e-16)
+    assert gp.likelihood == pytest.approx(m["likelihood"], rel=1e-13)
+    assert gp.inner.sigma2 == pytest.approx(ip["sigma2"], rel=1e-12)
+    np.testing.assert_allclose(gp.inner.r_chol, _arr(ip["r_chol"]), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(gp.inner.ft, _arr(ip["ft"]), rtol=0, atol=2e-15)
+    np.testing.assert_allclose(gp.inner.ft_qr_r, _arr(ip["ft_qr_r"]), rtol=0, atol=2e-15)
+    np.testing.assert_allclose(gp.inner.beta, _arr(ip["beta"]), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(gp.inner.gamma, _arr(ip["gamma"]), rtol=0, atol=1e-14)
+
+
+# ---- doc/Gpx_Tutorial.ipynb:165-167 + python/egobox/tests/test_gpmix.py:37-53 ----
+@pytest.fixture(scope="module")
+def krg5(golden_dir):
+    with open(os.path.join(golden_dir, "gpx_tutorial_kriging5.json")) as f:
+        return json.load(f)
+
+
+def test_kriging5_at_published_theta(krg5):
+    xt = np.array(krg5["xt"])[:, None]
+    gp = O.fit(xt, krg5["yt"], theta_init=[krg5["theta"]], fixed=True)
+    # printed theta has 9 significant digits: likelihood is flat at the optimum
+    assert gp.likelihood == pytest.approx(krg5["likelihood"], rel=1e-9)
+    assert gp.inner.sigma2 == pytest.approx(krg5["variance"], rel=2e-8)
+    # test_gpmix.py:37-46
+    assert gp.predict(np.array([[1.0]]))[0] == pytest.approx(1.0, abs=1e-7)
+    assert gp.predict_var(np.array([[1.0]]))[0] == pytest.approx(0.0, abs=1e-7)
+    assert gp.predict(np.array([[1.1]]))[0] == pytest.approx(1.1163, abs=1e-3)
+    assert gp.predict_var(np.array([[1.1]]))[0] == pytest.approx(0.0, abs=1e-3)
+
+
+def test_kriging5_optimised(krg5):
+    xt = np.array(krg5["xt"])[:, None]
+    gp = O.fit(xt, krg5["yt"])              # default multistart COBYLA
+    assert gp.theta[0] == pytest.approx(krg5["theta"], rel=2e-3)
+    assert gp.likelihood == pytest.approx(krg5["likelihood"], rel=1e-6)
+
+
+def test_fixed_theta_no_optim(krg5):
+    # test_gpmix.py:137-142
+    xt = np.array(krg5["xt"])[:, None]
+    gp = O.fit(xt, krg5["yt"], theta_init=[0.314], fixed=True)
+    assert gp.theta[0] == 0.314
+
+
+def test_valvar_matches_val_and_var(krg5):
+    # moe/src/algorithm.rs:1549-1552
+    xt = np.array(krg5["xt"])[:, None]
+    gp = O.fit(xt, krg5["yt"], theta_init=[1.0], fixed=True)
+    x = np.linspace(-1, 5, 17)[:, None]
+    y, v = gp.predict_valvar(x)
+    np.testing.assert_allclose(y, gp.predict(x), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(v, gp.predict_var(x), rtol=0, atol=1e-12)
+
+
+def test_non_pd_maps_to_inf():
+    # duplicated rows + nugget 0 -> singular R -> LinalgError -> +inf objective
+    x = np.array([[0.0], [0.0], [1.0], [2.0]])
+    y = np.array([0.0, 0.0, 1.0, 2.0])
+    xn, _, _ = O.normalize(x)
+    yn, _, ys = O.normalize(y.reshape(-1, 1))
+    fx = O.mean_value(O.CONSTANT, xn)
+    v = O.objective(O.SQEXP, xn, fx, yn, float(ys[0]), [1.0], np.eye(1), nugget=0.0)
+    assert v == math.inf
+    assert O.objective(O.SQEXP, xn, fx, yn, float(ys[0]), [float("nan")], np.eye(1)) == math.inf
+
+
+def test_corr_matrix_equals_scatter():
+    rng = np.random.default_rng(0)
+    x = rng.random((23, 3))
+    theta = np.array([0.3, 1.2, 2.0])
+    for kind in (O.SQEXP, O.ABSEXP, O.MATERN32, O.MATERN52):
+        d, idx = O.diff_matrix(x)
+        r = O.corr_value(kind, d, theta, np.eye(3))
+        R = np.eye(23) * (1.0 + O.DEFAULT_NUGGET)
+        R[idx[:, 0], idx[:, 1]] = r
+        R[idx[:, 1], idx[:, 0]] = r
+        np.testing.assert_allclose(O.corr_matrix(kind, x, theta, np.eye(3)), R, rtol=1e-14, atol=0)
