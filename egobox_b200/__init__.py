@@ -1,0 +1,7 @@
+"""egobox_b200 -- B200-native (sm_100a) kriging hot path of egobox-gp.
+
+Host-side mirror of the reference interface for this path; all arithmetic runs
+in hand-written CUDA kernels behind the C ABI of ``include/egobox_gpu.h``."""
+from ._lib import GpuError, device_count, load as load_library  # noqa: F401
+from .context import (GpContext, SQUARED_EXPONENTIAL, ABSOLUTE_EXPONENTIAL, MATERN32, MATERN52,  # noqa: F401
+                      CONSTANT, LINEAR, QUADRATIC, DEFAULT_NUGGET)

@@ -1,0 +1,85 @@
+"""ctypes binding of libegobox_gpu.so (the C ABI in include/egobox_gpu.h).
+
+There is no Python/CPU fallback: if the shared library is missing the import
+of any compute entry point raises, and if no CUDA device is visible every
+compute call returns EGX_CUDA_ERROR (surfaced as ``GpuError``)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libegobox_gpu.so")
+
+EGX_OK, EGX_NOT_POSITIVE_DEFINITE, EGX_ILL_CONDITIONED_FT, EGX_ILL_CONDITIONED_F, \
+    EGX_INVALID_VALUE, EGX_CUDA_ERROR = range(6)
+STATUS_NAMES = {0: "OK", 1: "NOT_POSITIVE_DEFINITE", 2: "ILL_CONDITIONED_FT", 3: "ILL_CONDITIONED_F",
+                4: "INVALID_VALUE", 5: "CUDA_ERROR"}
+NUM_STAGES = 9
+STAGE_NAMES = ["corr_build", "potrf_diag", "trsm_panel", "syrk_gemm", "gls", "backsolve",
+               "cross_corr", "var_finish", "small_batch"]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/egobox_gpu.h declares
+SIGNATURES = {
+    "egx_device_count": (C.c_int, []),
+    "egx_last_error": (C.c_char_p, []),
+    "egx_version": (C.c_char_p, []),
+    "egx_gp_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, _dp,
+                                C.c_double, C.c_double, _dp, C.c_int, C.c_double]),
+    "egx_gp_destroy": (None, [_vp]),
+    "egx_gp_dims": (C.c_int, [_vp, _ip, _ip, _ip, _ip]),
+    "egx_gp_reduced_likelihood": (C.c_int, [_vp, _dp, _dp]),
+    "egx_gp_reduced_likelihood_batch": (C.c_int, [_vp, _dp, C.c_int, _dp, _ip]),
+    "egx_gp_finalize": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "egx_gp_download_chol": (C.c_int, [_vp, _dp]),
+    "egx_gp_predict": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_gp_predict_var": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_gp_predict_valvar": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp]),
+    "egx_gp_predict_valvar_dev": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "egx_gp_correlation_matrix": (C.c_int, [_vp, _dp, _dp]),
+    "egx_gp_cross_correlation": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_gp_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "egx_gp_reset_profile": (C.c_int, [_vp]),
+    "egx_gp_get_profile": (C.c_int, [_vp, _dp, C.POINTER(C.c_longlong)]),
+    "egx_gp_set_force_blocked": (C.c_int, [_vp, C.c_int]),
+}
+
+_lib = None
+
+
+class GpuError(RuntimeError):
+    """A C-ABI call returned EGX_CUDA_ERROR / EGX_INVALID_VALUE."""
+
+    def __init__(self, status, msg):
+        super().__init__("%s: %s" % (STATUS_NAMES.get(status, status), msg))
+        self.status = status
+
+
+def load():
+    """Load the shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "egobox_b200: %s is missing -- build it with `python -m egobox_b200._build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().egx_last_error().decode("utf-8", "replace")
+
+
+def device_count():
+    return int(load().egx_device_count())

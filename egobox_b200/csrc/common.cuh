@@ -1,0 +1,80 @@
+// Internal definitions shared by the CUDA translation units of libegobox_gpu.so.
+// sm_100a only (compiled with -gencode arch=compute_100a,code=sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#define EGX_NB 128            // Cholesky / TRSM block size (rows and columns)
+#define EGX_CT 64             // correlation-kernel tile edge
+
+// One multiplicative / additive term of a correlation kernel: a (dimension j,
+// PLS component l) pair with theta_w[j,l] != 0 for the Matern models
+// (correlation_models.rs:333-351, 505-521), or a dimension j with its summed
+// weight for the exponential models (:97-100, :191-192).
+struct CorrTerm {
+    int dim;
+    int pad_;
+    double k1;   // SqExp: sum_l (theta_l W_jl)^2 | AbsExp: sum_l |W_jl| theta_l | Matern: tw = theta_l |W_jl|
+    double k2;   // Matern32: sqrt(3) tw | Matern52: sqrt(5) tw
+    double k3;   // Matern52: tw * tw
+};
+
+// Result block written by the GLS kernel (one per likelihood evaluation).
+struct EvalResult {
+    double rlf;        // reduced likelihood, algorithm.rs:1043
+    double sigma2;     // rho^T rho / n  (normalised units)
+    double logdet;     // (2/n) sum log10 L_ii
+    double rho_sqr;
+    int info;          // 0 ok, >0: 1-based index of the first non-positive pivot
+    int pad_;
+};
+
+struct GemmArgs {
+    double* C; long ldc;
+    const double* A; long lda;
+    const double* B; long ldb;
+    int Mt, Nt;      // tile counts (128 x 128 tiles)
+    int tri;         // tri > 0: lower-triangular tile set, first `tri` tile rows are
+                     // triangular (c <= r), rows tri..Mt-1 are full (c < tri).  tri == 0: full Mt x Nt
+};
+
+#define EGX_CUDA_TRY(expr)                                                         \
+    do {                                                                           \
+        cudaError_t e__ = (expr);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            egx_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                          __FILE__, __LINE__);                                     \
+            return EGX_CUDA_ERROR;                                                 \
+        }                                                                          \
+    } while (0)
+
+void egx_set_error(const char* fmt, ...);
+
+// ---- launchers (host) ------------------------------------------------------
+// kernels_corr.cu
+void launch_corr_build(int corr, const double* X, int n, int npad, int d, const CorrTerm* terms,
+                       int nterms, double* M, long ld, double diag_value, cudaStream_t s);
+void launch_cross_corr(int corr, const double* xraw, int m, int mpad, const double* x_mean,
+                       const double* x_std, const double* X, int n, int npad, int d,
+                       const CorrTerm* terms, int nterms, const double* gamma, const double* beta,
+                       const int* basis_i, const int* basis_j, int p, double y_mean, double y_std,
+                       double* Y, long ldy, double* yout, cudaStream_t s);
+void launch_mean_basis_rows(const double* X, int n, int npad, int d, const int* basis_i,
+                            const int* basis_j, int p, const double* ynorm_dev, double* FyT, long ld,
+                            cudaStream_t s);
+// kernels_chol.cu
+void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, cudaStream_t s);
+void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, double* P, int nblocks64,
+                      cudaStream_t s);
+void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s);
+int gemm_smem_bytes();
+// kernels_solve.cu
+void launch_gls(const double* M, long ld, int n, int npad, int p, double* work, double* G,
+                double* beta, double* rho, EvalResult* res, const int* info, cudaStream_t s);
+void launch_backsolve_diag(const double* Lkk, long ld, double* rho_k, cudaStream_t s);
+void launch_backsolve_update(const double* Lrow, long ld, const double* gamma_k, double* rho, int ncolblocks,
+                             cudaStream_t s);
+void launch_var_finish(const double* Y, long ldy, int m, int npad, const double* xraw, const double* x_mean,
+                       const double* x_std, int d, const double* FtT, long ldf, const double* G, int p,
+                       const int* basis_i, const int* basis_j, double sigma2, double* var, cudaStream_t s);

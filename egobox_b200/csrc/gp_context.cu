@@ -1,0 +1,763 @@
+// Device-resident GP context and the C ABI declared in include/egobox_gpu.h.
+//
+// One context = one training set on one GPU.  A likelihood evaluation is
+//   K1 corr_build -> [F|y]^T rows appended under R -> blocked Cholesky (the appended rows
+//   come out as (L^-1 [F|y])^T, i.e. the forward solves of algorithm.rs:1006,1028 are fused
+//   into the factorisation) -> GLS kernel -> one small D2H of (rlf, sigma2, info, G, beta).
+// Nothing here falls back to the CPU: the only host arithmetic is the O(p^3) condition
+// number test on the p x p factor G (algorithm.rs:1010-1027).
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/egobox_gpu.h"
+
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void egx_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* egx_last_error(void) { return g_err; }
+extern "C" const char* egx_version(void) { return "egobox_b200 0.1 (sm_100a)"; }
+extern "C" int egx_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return c;
+}
+
+namespace {
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// One-sided Jacobi (Hestenes) singular values of a (rows x cols) row-major matrix, rows >= cols.
+std::vector<double> singular_values(const double* a, int rows, int cols) {
+    std::vector<double> u(static_cast<size_t>(rows) * cols);
+    // column-major working copy
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) u[static_cast<size_t>(c) * rows + r] = a[static_cast<size_t>(r) * cols + c];
+    const double eps = 2.220446049250313e-16;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        bool rotated = false;
+        for (int i = 0; i < cols - 1; ++i) {
+            double* ui = &u[static_cast<size_t>(i) * rows];
+            for (int j = i + 1; j < cols; ++j) {
+                double* uj = &u[static_cast<size_t>(j) * rows];
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int k = 0; k < rows; ++k) {
+                    al += ui[k] * ui[k];
+                    be += uj[k] * uj[k];
+                    ga += ui[k] * uj[k];
+                }
+                if (ga == 0.0 || std::fabs(ga) <= eps * std::sqrt(al * be)) continue;
+                rotated = true;
+                const double zeta = (be - al) / (2.0 * ga);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+                for (int k = 0; k < rows; ++k) {
+                    const double x = ui[k], y = uj[k];
+                    ui[k] = c * x - s * y;
+                    uj[k] = s * x + c * y;
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+    std::vector<double> sv(cols);
+    for (int c = 0; c < cols; ++c) {
+        double s = 0.0;
+        for (int k = 0; k < rows; ++k) s += u[static_cast<size_t>(c) * rows + k] * u[static_cast<size_t>(c) * rows + k];
+        sv[c] = std::sqrt(s);
+    }
+    std::sort(sv.begin(), sv.end(), [](double x, double y) { return x > y; });
+    return sv;
+}
+
+struct ProfEvent {
+    cudaEvent_t a, b;
+    int stage;
+};
+
+}  // namespace
+
+struct egx_gp_ctx {
+    int device = 0, corr = 0, mean = 0;
+    int n = 0, d = 0, h = 0, p = 0, q = 0;
+    int npad = 0, qpad = 0, rows_total = 0;
+    long ld = 0;
+    double nugget = 0.0, y_mean = 0.0, y_std = 1.0;
+    std::vector<double> w_star, xnorm_h;
+    std::vector<int> basis_i_h, basis_j_h;
+
+    cudaStream_t stream = nullptr;
+    double *X = nullptr, *ynorm = nullptr, *x_mean = nullptr, *x_std = nullptr, *FyT = nullptr;
+    int *basis_i = nullptr, *basis_j = nullptr;
+    CorrTerm* terms = nullptr;
+    CorrTerm* terms_h = nullptr;   // pinned
+    int max_terms = 0, nterms = 0;
+
+    double *M = nullptr, *P = nullptr, *glswork = nullptr, *G = nullptr, *beta = nullptr, *rho = nullptr;
+    long p_rows = 0;
+    EvalResult* res = nullptr;
+    int* info = nullptr;
+    // pinned host mirrors
+    EvalResult* res_h = nullptr;
+    double *G_h = nullptr, *beta_h = nullptr;
+
+    // trained state (after finalize)
+    bool trained = false;
+    std::vector<double> theta;
+    double sigma2_scaled = 0.0;
+
+    // predict buffers
+    double *Y = nullptr, *xchunk = nullptr, *ychunk = nullptr, *vchunk = nullptr;
+    int mb_alloc = 0;
+
+    bool force_blocked = false;
+    bool profiling = false;
+    std::vector<ProfEvent> pending;
+    std::vector<cudaEvent_t> event_pool;
+    double stage_ms[EGX_NUM_STAGES] = {0};
+    long long stage_launches[EGX_NUM_STAGES] = {0};
+    std::mutex mu;
+};
+
+namespace {
+
+struct StageScope {
+    egx_gp_ctx* c;
+    ProfEvent ev;
+    bool on;
+    StageScope(egx_gp_ctx* ctx, int stage, int launches = 1) : c(ctx), on(ctx->profiling) {
+        c->stage_launches[stage] += launches;
+        if (on) {
+            ev.stage = stage;
+            for (cudaEvent_t* e : {&ev.a, &ev.b}) {
+                if (!c->event_pool.empty()) {
+                    *e = c->event_pool.back();
+                    c->event_pool.pop_back();
+                } else {
+                    cudaEventCreate(e);
+                }
+            }
+            cudaEventRecord(ev.a, c->stream);
+        }
+    }
+    ~StageScope() {
+        if (on) {
+            cudaEventRecord(ev.b, c->stream);
+            c->pending.push_back(ev);
+        }
+    }
+};
+
+void resolve_profile(egx_gp_ctx* c) {
+    for (auto& ev : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) c->stage_ms[ev.stage] += ms;
+        c->event_pool.push_back(ev.a);
+        c->event_pool.push_back(ev.b);
+    }
+    c->pending.clear();
+}
+
+int build_terms(egx_gp_ctx* c, const double* theta) {
+    const int d = c->d, h = c->h;
+    int nt = 0;
+    CorrTerm* t = c->terms_h;
+    const double* w = c->w_star.data();
+    if (c->corr == EGX_CORR_SQUARED_EXPONENTIAL || c->corr == EGX_CORR_ABSOLUTE_EXPONENTIAL) {
+        for (int j = 0; j < d; ++j) {
+            double s = 0.0;
+            for (int l = 0; l < h; ++l) {
+                if (c->corr == EGX_CORR_SQUARED_EXPONENTIAL) {
+                    const double v = theta[l] * w[j * h + l];
+                    s += v * v;
+                } else {
+                    s += std::fabs(w[j * h + l]) * theta[l];
+                }
+            }
+            if (s != 0.0) {
+                t[nt].dim = j;
+                t[nt].pad_ = 0;
+                t[nt].k1 = s;
+                t[nt].k2 = 0.0;
+                t[nt].k3 = 0.0;
+                ++nt;
+            }
+        }
+    } else {
+        const double sq = (c->corr == EGX_CORR_MATERN32) ? std::sqrt(3.0) : std::sqrt(5.0);
+        for (int j = 0; j < d; ++j)
+            for (int l = 0; l < h; ++l) {
+                const double tw = theta[l] * std::fabs(w[j * h + l]);
+                if (tw != 0.0) {
+                    t[nt].dim = j;
+                    t[nt].pad_ = 0;
+                    t[nt].k1 = tw;
+                    t[nt].k2 = sq * tw;
+                    t[nt].k3 = tw * tw;
+                    ++nt;
+                }
+            }
+    }
+    c->nterms = nt;
+    if (nt > 0)
+        EGX_CUDA_TRY(cudaMemcpyAsync(c->terms, c->terms_h, nt * sizeof(CorrTerm), cudaMemcpyHostToDevice, c->stream));
+    return EGX_OK;
+}
+
+// R(theta) lower block-triangle into M, then the RHS rows.
+int assemble(egx_gp_ctx* c, const double* theta) {
+    for (int l = 0; l < c->h; ++l)
+        if (std::isnan(theta[l])) {
+            egx_set_error("theta[%d] is NaN", l);
+            return EGX_INVALID_VALUE;
+        }
+    int st = build_terms(c, theta);
+    if (st != EGX_OK) return st;
+    EGX_CUDA_TRY(cudaMemsetAsync(c->info, 0, sizeof(int), c->stream));
+    {
+        StageScope sc(c, EGX_STAGE_CORR_BUILD);
+        launch_corr_build(c->corr, c->X, c->n, c->npad, c->d, c->terms, c->nterms, c->M, c->ld, 1.0 + c->nugget,
+                          c->stream);
+    }
+    EGX_CUDA_TRY(cudaMemcpyAsync(c->M + static_cast<long>(c->npad) * c->ld, c->FyT,
+                                 static_cast<size_t>(c->q) * c->ld * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 c->stream));
+    return EGX_OK;
+}
+
+void cholesky(egx_gp_ctx* c) {
+    const int T = c->npad / EGX_NB, Qt = c->qpad / EGX_NB;
+    const long ld = c->ld;
+    for (int k = 0; k < T; ++k) {
+        double* Akk = c->M + static_cast<long>(k) * EGX_NB * ld + static_cast<long>(k) * EGX_NB;
+        {
+            StageScope sc(c, EGX_STAGE_POTRF_DIAG);
+            launch_potrf_diag(Akk, ld, c->info, k * EGX_NB, c->stream);
+        }
+        const int rows_below = (T - k - 1) * EGX_NB + c->qpad;
+        if (rows_below > 0) {
+            StageScope sc(c, EGX_STAGE_TRSM_PANEL);
+            launch_trsm_rows(Akk + static_cast<long>(EGX_NB) * ld, ld, Akk, ld, c->P, rows_below / 64, c->stream);
+        }
+        const int tri = T - k - 1;
+        if (tri > 0) {
+            GemmArgs g;
+            g.C = Akk + static_cast<long>(EGX_NB) * ld + EGX_NB;
+            g.ldc = ld;
+            g.A = c->P;
+            g.lda = EGX_NB;
+            g.B = c->P;
+            g.ldb = EGX_NB;
+            g.tri = tri;
+            g.Mt = tri + Qt;
+            g.Nt = tri;
+            StageScope sc(c, EGX_STAGE_SYRK_GEMM);
+            launch_gemm_nt_sub(g, c->stream);
+        }
+    }
+}
+
+// Full likelihood evaluation; leaves L, (L^-1[F|y])^T, beta, G, rho on the device.
+int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
+    *rlf_out = NAN;
+    c->trained = false;
+    int st = assemble(c, theta);
+    if (st != EGX_OK) return st;
+    cholesky(c);
+    {
+        StageScope sc(c, EGX_STAGE_GLS);
+        launch_gls(c->M, c->ld, c->n, c->npad, c->p, c->glswork, c->G, c->beta, c->rho, c->res, c->info, c->stream);
+    }
+    EGX_CUDA_TRY(cudaMemcpyAsync(c->res_h, c->res, sizeof(EvalResult), cudaMemcpyDeviceToHost, c->stream));
+    EGX_CUDA_TRY(cudaMemcpyAsync(c->G_h, c->G, sizeof(double) * c->p * c->p, cudaMemcpyDeviceToHost, c->stream));
+    EGX_CUDA_TRY(cudaMemcpyAsync(c->beta_h, c->beta, sizeof(double) * c->p, cudaMemcpyDeviceToHost, c->stream));
+    EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EGX_CUDA_TRY(cudaGetLastError());
+    resolve_profile(c);
+    if (c->res_h->info != 0) {
+        egx_set_error("correlation matrix is not positive definite (pivot %d)", c->res_h->info);
+        return EGX_NOT_POSITIVE_DEFINITE;
+    }
+    // condition number test, algorithm.rs:1010-1027
+    std::vector<double> sv = singular_values(c->G_h, c->p, c->p);
+    const double cond_ft = sv.back() / sv.front();
+    if (!(cond_ft >= 1e-10)) {
+        // fx = mean.value(xnorm) rebuilt on the host for the (rare) diagnostic branch
+        std::vector<double> F(static_cast<size_t>(c->n) * c->p);
+        for (int i = 0; i < c->n; ++i)
+            for (int l = 0; l < c->p; ++l) {
+                const int bi = c->basis_i_h[l], bj = c->basis_j_h[l];
+                const double* x = &c->xnorm_h[static_cast<size_t>(i) * c->d];
+                F[static_cast<size_t>(i) * c->p + l] = (bi < 0 ? 1.0 : x[bi]) * (bj < 0 ? 1.0 : x[bj]);
+            }
+        std::vector<double> svf = singular_values(F.data(), c->n, c->p);
+        const double cond_fx = svf.front() / svf.back();
+        if (cond_fx > 1e15) {
+            egx_set_error("F is too ill conditioned. Poor combination of regression model and observations.");
+            return EGX_ILL_CONDITIONED_F;
+        }
+        egx_set_error("ft is too ill conditioned, try another theta again");
+        return EGX_ILL_CONDITIONED_FT;
+    }
+    *rlf_out = c->res_h->rlf;
+    return EGX_OK;
+}
+
+int ensure_predict_buffers(egx_gp_ctx* c, int mb) {
+    if (mb <= c->mb_alloc) return EGX_OK;
+    cudaFree(c->Y);
+    cudaFree(c->xchunk);
+    cudaFree(c->ychunk);
+    cudaFree(c->vchunk);
+    c->Y = c->xchunk = c->ychunk = c->vchunk = nullptr;
+    c->mb_alloc = 0;
+    EGX_CUDA_TRY(cudaMalloc(&c->Y, static_cast<size_t>(mb) * c->npad * sizeof(double)));
+    EGX_CUDA_TRY(cudaMalloc(&c->xchunk, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    EGX_CUDA_TRY(cudaMalloc(&c->ychunk, static_cast<size_t>(mb) * sizeof(double)));
+    EGX_CUDA_TRY(cudaMalloc(&c->vchunk, static_cast<size_t>(mb) * sizeof(double)));
+    if (static_cast<long>(mb) > c->p_rows) {
+        cudaFree(c->P);
+        c->P = nullptr;
+        EGX_CUDA_TRY(cudaMalloc(&c->P, static_cast<size_t>(mb) * EGX_NB * sizeof(double)));
+        c->p_rows = mb;
+    }
+    c->mb_alloc = mb;
+    return EGX_OK;
+}
+
+constexpr int PREDICT_CHUNK = 8192;
+
+// One chunk of <= mb_alloc points whose raw inputs are at x_dev (device).
+int predict_chunk_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, double* var_dev, double* c_out_dev) {
+    const int mpad = round_up(m, EGX_NB);
+    const bool want_var = (var_dev != nullptr);
+    double* Ybuf = (want_var || c_out_dev != nullptr) ? c->Y : nullptr;
+    {
+        StageScope sc(c, EGX_STAGE_CROSS_CORR);
+        launch_cross_corr(c->corr, x_dev, m, mpad, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d, c->terms,
+                          c->nterms, c->rho /* = gamma after finalize */, c->beta, c->basis_i, c->basis_j, c->p,
+                          c->y_mean, c->y_std, Ybuf, c->npad, y_dev, c->stream);
+    }
+    if (c_out_dev != nullptr)
+        EGX_CUDA_TRY(cudaMemcpy2DAsync(c_out_dev, static_cast<size_t>(c->n) * sizeof(double), c->Y,
+                                       static_cast<size_t>(c->npad) * sizeof(double),
+                                       static_cast<size_t>(c->n) * sizeof(double), m, cudaMemcpyDeviceToDevice,
+                                       c->stream));
+    if (!want_var) return EGX_OK;
+    const int T = c->npad / EGX_NB;
+    for (int k = 0; k < T; ++k) {
+        const double* Lkk = c->M + static_cast<long>(k) * EGX_NB * c->ld + static_cast<long>(k) * EGX_NB;
+        {
+            StageScope sc(c, EGX_STAGE_TRSM_PANEL);
+            launch_trsm_rows(c->Y + static_cast<long>(k) * EGX_NB, c->npad, Lkk, c->ld, c->P, mpad / 64, c->stream);
+        }
+        if (k < T - 1) {
+            GemmArgs g;
+            g.C = c->Y + static_cast<long>(k + 1) * EGX_NB;
+            g.ldc = c->npad;
+            g.A = c->P;
+            g.lda = EGX_NB;
+            g.B = Lkk + static_cast<long>(EGX_NB) * c->ld;
+            g.ldb = c->ld;
+            g.tri = 0;
+            g.Mt = mpad / EGX_NB;
+            g.Nt = T - k - 1;
+            StageScope sc(c, EGX_STAGE_SYRK_GEMM);
+            launch_gemm_nt_sub(g, c->stream);
+        }
+    }
+    {
+        StageScope sc(c, EGX_STAGE_VAR_FINISH);
+        launch_var_finish(c->Y, c->npad, m, c->npad, x_dev, c->x_mean, c->x_std, c->d,
+                          c->M + static_cast<long>(c->npad) * c->ld, c->ld, c->G, c->p, c->basis_i, c->basis_j,
+                          c->sigma2_scaled, var_dev, c->stream);
+    }
+    return EGX_OK;
+}
+
+int predict_impl(egx_gp_ctx* c, const double* x, int m, double* y, double* var, bool device_ptrs) {
+    if (!c->trained) {
+        egx_set_error("predict* called before a successful egx_gp_finalize");
+        return EGX_INVALID_VALUE;
+    }
+    if (m < 0 || (m > 0 && x == nullptr)) {
+        egx_set_error("bad prediction input");
+        return EGX_INVALID_VALUE;
+    }
+    if (m == 0) return EGX_OK;
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    const int mb = std::min(round_up(m, EGX_NB), PREDICT_CHUNK);
+    int st = ensure_predict_buffers(c, mb);
+    if (st != EGX_OK) return st;
+    for (int i0 = 0; i0 < m; i0 += mb) {
+        const int mc = std::min(mb, m - i0);
+        const double* xd;
+        double *yd = nullptr, *vd = nullptr;
+        if (device_ptrs) {
+            xd = x + static_cast<long>(i0) * c->d;
+            if (y) yd = y + i0;
+            if (var) vd = var + i0;
+        } else {
+            EGX_CUDA_TRY(cudaMemcpyAsync(c->xchunk, x + static_cast<long>(i0) * c->d,
+                                         static_cast<size_t>(mc) * c->d * sizeof(double), cudaMemcpyHostToDevice,
+                                         c->stream));
+            xd = c->xchunk;
+            if (y) yd = c->ychunk;
+            if (var) vd = c->vchunk;
+        }
+        st = predict_chunk_dev(c, xd, mc, yd, vd, nullptr);
+        if (st != EGX_OK) return st;
+        if (!device_ptrs) {
+            if (y) EGX_CUDA_TRY(cudaMemcpyAsync(y + i0, c->ychunk, mc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            if (var) EGX_CUDA_TRY(cudaMemcpyAsync(var + i0, c->vchunk, mc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            // the staging buffers are reused by the next chunk
+            EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+    }
+    EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EGX_CUDA_TRY(cudaGetLastError());
+    resolve_profile(c);
+    return EGX_OK;
+}
+
+void free_ctx(egx_gp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& ev : c->pending) {
+        cudaEventDestroy(ev.a);
+        cudaEventDestroy(ev.b);
+    }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    cudaFree(c->X);
+    cudaFree(c->ynorm);
+    cudaFree(c->x_mean);
+    cudaFree(c->x_std);
+    cudaFree(c->FyT);
+    cudaFree(c->basis_i);
+    cudaFree(c->basis_j);
+    cudaFree(c->terms);
+    cudaFree(c->M);
+    cudaFree(c->P);
+    cudaFree(c->glswork);
+    cudaFree(c->G);
+    cudaFree(c->beta);
+    cudaFree(c->rho);
+    cudaFree(c->res);
+    cudaFree(c->info);
+    cudaFree(c->Y);
+    cudaFree(c->xchunk);
+    cudaFree(c->ychunk);
+    cudaFree(c->vchunk);
+    cudaFreeHost(c->terms_h);
+    cudaFreeHost(c->res_h);
+    cudaFreeHost(c->G_h);
+    cudaFreeHost(c->beta_h);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, const double* xnorm, int n, int d,
+                             const double* ynorm, const double* x_mean, const double* x_std, double y_mean,
+                             double y_std, const double* w_star, int h, double nugget) {
+    if (!out) return EGX_INVALID_VALUE;
+    *out = nullptr;
+    if (n < 1 || d < 1 || h < 1 || h > d || !xnorm || !ynorm || !x_mean || !x_std || !w_star || corr < 0 ||
+        corr > 3 || mean < 0 || mean > 2) {
+        egx_set_error("egx_gp_create: invalid argument (n=%d d=%d h=%d corr=%d mean=%d)", n, d, h, corr, mean);
+        return EGX_INVALID_VALUE;
+    }
+    const int p = (mean == EGX_MEAN_CONSTANT) ? 1 : (mean == EGX_MEAN_LINEAR ? d + 1 : (d + 1) * (d + 2) / 2);
+    if (p > 255 || p > n) {
+        egx_set_error("egx_gp_create: regression basis size p=%d unsupported (need p <= min(255, n=%d))", p, n);
+        return EGX_INVALID_VALUE;
+    }
+    if (egx_device_count() <= device || device < 0) {
+        egx_set_error("egx_gp_create: CUDA device %d not available (no CPU fallback exists)", device);
+        return EGX_CUDA_ERROR;
+    }
+    EGX_CUDA_TRY(cudaSetDevice(device));
+    egx_gp_ctx* c = new egx_gp_ctx();
+    c->device = device;
+    c->corr = corr;
+    c->mean = mean;
+    c->n = n;
+    c->d = d;
+    c->h = h;
+    c->p = p;
+    c->q = p + 1;
+    c->npad = round_up(n, EGX_NB);
+    c->qpad = round_up(c->q, EGX_NB);
+    c->rows_total = c->npad + c->qpad;
+    c->ld = c->npad;
+    c->nugget = nugget;
+    c->y_mean = y_mean;
+    c->y_std = y_std;
+    c->w_star.assign(w_star, w_star + static_cast<size_t>(d) * h);
+    c->xnorm_h.assign(xnorm, xnorm + static_cast<size_t>(n) * d);
+    // regression basis f_l(x) = v(bi) * v(bj), v(-1) = 1  (mean_models.rs:42-44, 68-71, 97-104)
+    c->basis_i_h.push_back(-1);
+    c->basis_j_h.push_back(-1);
+    if (mean >= EGX_MEAN_LINEAR)
+        for (int j = 0; j < d; ++j) {
+            c->basis_i_h.push_back(j);
+            c->basis_j_h.push_back(-1);
+        }
+    if (mean == EGX_MEAN_QUADRATIC)
+        for (int k = 0; k < d; ++k)
+            for (int j = k; j < d; ++j) {
+                c->basis_i_h.push_back(j);
+                c->basis_j_h.push_back(k);
+            }
+
+#define EGX_CREATE_TRY(expr)                                                          \
+    do {                                                                              \
+        cudaError_t e__ = (expr);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            egx_set_error("%s failed: %s", #expr, cudaGetErrorString(e__));           \
+            free_ctx(c);                                                              \
+            return EGX_CUDA_ERROR;                                                    \
+        }                                                                             \
+    } while (0)
+
+    EGX_CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t xbytes = static_cast<size_t>(c->npad) * d * sizeof(double);
+    EGX_CREATE_TRY(cudaMalloc(&c->X, xbytes));
+    EGX_CREATE_TRY(cudaMemsetAsync(c->X, 0, xbytes, c->stream));
+    EGX_CREATE_TRY(cudaMemcpyAsync(c->X, xnorm, static_cast<size_t>(n) * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    EGX_CREATE_TRY(cudaMalloc(&c->ynorm, c->npad * sizeof(double)));
+    EGX_CREATE_TRY(cudaMemsetAsync(c->ynorm, 0, c->npad * sizeof(double), c->stream));
+    EGX_CREATE_TRY(cudaMemcpyAsync(c->ynorm, ynorm, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    EGX_CREATE_TRY(cudaMalloc(&c->x_mean, d * sizeof(double)));
+    EGX_CREATE_TRY(cudaMalloc(&c->x_std, d * sizeof(double)));
+    EGX_CREATE_TRY(cudaMemcpyAsync(c->x_mean, x_mean, d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    EGX_CREATE_TRY(cudaMemcpyAsync(c->x_std, x_std, d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    EGX_CREATE_TRY(cudaMalloc(&c->basis_i, p * sizeof(int)));
+    EGX_CREATE_TRY(cudaMalloc(&c->basis_j, p * sizeof(int)));
+    EGX_CREATE_TRY(cudaMemcpyAsync(c->basis_i, c->basis_i_h.data(), p * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    EGX_CREATE_TRY(cudaMemcpyAsync(c->basis_j, c->basis_j_h.data(), p * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->max_terms = d * h;
+    EGX_CREATE_TRY(cudaMalloc(&c->terms, c->max_terms * sizeof(CorrTerm)));
+    EGX_CREATE_TRY(cudaMallocHost(&c->terms_h, c->max_terms * sizeof(CorrTerm)));
+    EGX_CREATE_TRY(cudaMalloc(&c->FyT, static_cast<size_t>(c->q) * c->ld * sizeof(double)));
+    const size_t mbytes = static_cast<size_t>(c->rows_total) * c->ld * sizeof(double);
+    EGX_CREATE_TRY(cudaMalloc(&c->M, mbytes));
+    EGX_CREATE_TRY(cudaMemsetAsync(c->M, 0, mbytes, c->stream));
+    c->p_rows = c->rows_total;
+    EGX_CREATE_TRY(cudaMalloc(&c->P, static_cast<size_t>(c->p_rows) * EGX_NB * sizeof(double)));
+    EGX_CREATE_TRY(cudaMalloc(&c->glswork, static_cast<size_t>(c->q) * c->npad * sizeof(double)));
+    EGX_CREATE_TRY(cudaMalloc(&c->G, static_cast<size_t>(p) * p * sizeof(double)));
+    EGX_CREATE_TRY(cudaMalloc(&c->beta, p * sizeof(double)));
+    EGX_CREATE_TRY(cudaMalloc(&c->rho, c->npad * sizeof(double)));
+    EGX_CREATE_TRY(cudaMalloc(&c->res, sizeof(EvalResult)));
+    EGX_CREATE_TRY(cudaMalloc(&c->info, sizeof(int)));
+    EGX_CREATE_TRY(cudaMallocHost(&c->res_h, sizeof(EvalResult)));
+    EGX_CREATE_TRY(cudaMallocHost(&c->G_h, static_cast<size_t>(p) * p * sizeof(double)));
+    EGX_CREATE_TRY(cudaMallocHost(&c->beta_h, p * sizeof(double)));
+    launch_mean_basis_rows(c->X, n, c->npad, d, c->basis_i, c->basis_j, p, c->ynorm, c->FyT, c->ld, c->stream);
+    EGX_CREATE_TRY(cudaStreamSynchronize(c->stream));
+    EGX_CREATE_TRY(cudaGetLastError());
+#undef EGX_CREATE_TRY
+    *out = c;
+    return EGX_OK;
+}
+
+extern "C" void egx_gp_destroy(egx_gp_ctx* ctx) { free_ctx(ctx); }
+
+extern "C" int egx_gp_dims(const egx_gp_ctx* c, int* n, int* d, int* h, int* p) {
+    if (!c) return EGX_INVALID_VALUE;
+    if (n) *n = c->n;
+    if (d) *d = c->d;
+    if (h) *h = c->h;
+    if (p) *p = c->p;
+    return EGX_OK;
+}
+
+extern "C" int egx_gp_reduced_likelihood(egx_gp_ctx* c, const double* theta, double* rlf) {
+    if (!c || !theta || !rlf) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    return evaluate(c, theta, rlf);
+}
+
+extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thetas, int B, double* rlf, int* status) {
+    if (!c || !thetas || !rlf || !status || B < 0) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    for (int b = 0; b < B; ++b) {
+        status[b] = evaluate(c, thetas + static_cast<long>(b) * c->h, &rlf[b]);
+        if (status[b] == EGX_CUDA_ERROR) return EGX_CUDA_ERROR;
+    }
+    return EGX_OK;
+}
+
+extern "C" int egx_gp_finalize(egx_gp_ctx* c, const double* theta, double* rlf, double* sigma2, double* beta,
+                               double* gamma, double* ft, double* ft_qr_r) {
+    if (!c || !theta) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    double v = NAN;
+    int st = evaluate(c, theta, &v);
+    if (rlf) *rlf = v;
+    if (st != EGX_OK) return st;
+    // gamma = L^-T rho, blocked back substitution (algorithm.rs:1034)
+    const int T = c->npad / EGX_NB;
+    for (int k = T - 1; k >= 0; --k) {
+        const double* Lkk = c->M + static_cast<long>(k) * EGX_NB * c->ld + static_cast<long>(k) * EGX_NB;
+        StageScope sc(c, EGX_STAGE_BACKSOLVE, k > 0 ? 2 : 1);
+        launch_backsolve_diag(Lkk, c->ld, c->rho + k * EGX_NB, c->stream);
+        if (k > 0)
+            launch_backsolve_update(c->M + static_cast<long>(k) * EGX_NB * c->ld, c->ld, c->rho + k * EGX_NB, c->rho,
+                                    k, c->stream);
+    }
+    if (gamma) EGX_CUDA_TRY(cudaMemcpyAsync(gamma, c->rho, c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> ftT;
+    if (ft) {
+        ftT.resize(static_cast<size_t>(c->p) * c->n);
+        EGX_CUDA_TRY(cudaMemcpy2DAsync(ftT.data(), c->n * sizeof(double), c->M + static_cast<long>(c->npad) * c->ld,
+                                       c->ld * sizeof(double), c->n * sizeof(double), c->p, cudaMemcpyDeviceToHost,
+                                       c->stream));
+    }
+    EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EGX_CUDA_TRY(cudaGetLastError());
+    resolve_profile(c);
+    if (ft)
+        for (int i = 0; i < c->n; ++i)
+            for (int l = 0; l < c->p; ++l) ft[static_cast<size_t>(i) * c->p + l] = ftT[static_cast<size_t>(l) * c->n + i];
+    c->sigma2_scaled = c->res_h->sigma2 * c->y_std * c->y_std;   // algorithm.rs:1048
+    if (sigma2) *sigma2 = c->sigma2_scaled;
+    if (beta) std::memcpy(beta, c->beta_h, c->p * sizeof(double));
+    if (ft_qr_r) std::memcpy(ft_qr_r, c->G_h, sizeof(double) * c->p * c->p);
+    c->theta.assign(theta, theta + c->h);
+    c->trained = true;
+    return EGX_OK;
+}
+
+extern "C" int egx_gp_download_chol(egx_gp_ctx* c, double* r_chol) {
+    if (!c || !r_chol) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->trained) {
+        egx_set_error("egx_gp_download_chol before finalize");
+        return EGX_INVALID_VALUE;
+    }
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    EGX_CUDA_TRY(cudaMemcpy2D(r_chol, c->n * sizeof(double), c->M, c->ld * sizeof(double), c->n * sizeof(double), c->n,
+                              cudaMemcpyDeviceToHost));
+    for (int i = 0; i < c->n; ++i)
+        for (int j = i + 1; j < c->n; ++j) r_chol[static_cast<size_t>(i) * c->n + j] = 0.0;
+    return EGX_OK;
+}
+
+extern "C" int egx_gp_predict(egx_gp_ctx* c, const double* x, int m, double* y) {
+    if (!c || !y) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return predict_impl(c, x, m, y, nullptr, false);
+}
+extern "C" int egx_gp_predict_var(egx_gp_ctx* c, const double* x, int m, double* var) {
+    if (!c || !var) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return predict_impl(c, x, m, nullptr, var, false);
+}
+extern "C" int egx_gp_predict_valvar(egx_gp_ctx* c, const double* x, int m, double* y, double* var) {
+    if (!c || !y || !var) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return predict_impl(c, x, m, y, var, false);
+}
+extern "C" int egx_gp_predict_valvar_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, double* var_dev) {
+    if (!c) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return predict_impl(c, x_dev, m, y_dev, var_dev, true);
+}
+
+extern "C" int egx_gp_correlation_matrix(egx_gp_ctx* c, const double* theta, double* r) {
+    if (!c || !theta || !r) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    c->trained = false;
+    int st = assemble(c, theta);
+    if (st != EGX_OK) return st;
+    EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EGX_CUDA_TRY(cudaGetLastError());
+    resolve_profile(c);
+    EGX_CUDA_TRY(cudaMemcpy2D(r, c->n * sizeof(double), c->M, c->ld * sizeof(double), c->n * sizeof(double), c->n,
+                              cudaMemcpyDeviceToHost));
+    for (int i = 0; i < c->n; ++i)
+        for (int j = i + 1; j < c->n; ++j) r[static_cast<size_t>(i) * c->n + j] = r[static_cast<size_t>(j) * c->n + i];
+    return EGX_OK;
+}
+
+extern "C" int egx_gp_cross_correlation(egx_gp_ctx* c, const double* x, int m, double* out) {
+    if (!c || !x || !out || m < 1) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->trained) {
+        egx_set_error("egx_gp_cross_correlation before finalize");
+        return EGX_INVALID_VALUE;
+    }
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    const int mb = std::min(round_up(m, EGX_NB), PREDICT_CHUNK);
+    int st = ensure_predict_buffers(c, mb);
+    if (st != EGX_OK) return st;
+    double* cdev = nullptr;
+    EGX_CUDA_TRY(cudaMalloc(&cdev, static_cast<size_t>(mb) * c->n * sizeof(double)));
+    for (int i0 = 0; i0 < m; i0 += mb) {
+        const int mc = std::min(mb, m - i0);
+        cudaMemcpyAsync(c->xchunk, x + static_cast<long>(i0) * c->d, static_cast<size_t>(mc) * c->d * sizeof(double),
+                        cudaMemcpyHostToDevice, c->stream);
+        st = predict_chunk_dev(c, c->xchunk, mc, nullptr, nullptr, cdev);
+        if (st != EGX_OK) break;
+        cudaMemcpyAsync(out + static_cast<long>(i0) * c->n, cdev, static_cast<size_t>(mc) * c->n * sizeof(double),
+                        cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(cdev);
+    if (st != EGX_OK) return st;
+    EGX_CUDA_TRY(cudaGetLastError());
+    resolve_profile(c);
+    return EGX_OK;
+}
+
+extern "C" int egx_gp_set_profiling(egx_gp_ctx* c, int enabled) {
+    if (!c) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->profiling = enabled != 0;
+    return EGX_OK;
+}
+extern "C" int egx_gp_reset_profile(egx_gp_ctx* c) {
+    if (!c) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int i = 0; i < EGX_NUM_STAGES; ++i) {
+        c->stage_ms[i] = 0.0;
+        c->stage_launches[i] = 0;
+    }
+    return EGX_OK;
+}
+extern "C" int egx_gp_get_profile(egx_gp_ctx* c, double* ms, long long* launches) {
+    if (!c) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int i = 0; i < EGX_NUM_STAGES; ++i) {
+        if (ms) ms[i] = c->stage_ms[i];
+        if (launches) launches[i] = c->stage_launches[i];
+    }
+    return EGX_OK;
+}
+extern "C" int egx_gp_set_force_blocked(egx_gp_ctx* c, int enabled) {
+    if (!c) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->force_blocked = enabled != 0;
+    return EGX_OK;
+}

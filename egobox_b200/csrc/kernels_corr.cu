@@ -1,0 +1,343 @@
+// Fused pairwise-distance + correlation kernels (K1: R(theta) lower block-triangle,
+// K2: cross-correlation c(x*, X) fused with the mean / gamma GEMV of predict).
+//
+// Reference being replaced: DiffMatrix::new (gp/src/utils.rs:80-104) +
+// CorrelationModel::value (gp/src/correlation_models.rs:91-104, 185-196, 277-353,
+// 446-523) + the scatter into R (gp/src/algorithm.rs:997-1001), and for K2
+// pairwise_differences (utils.rs:110-131) + value + `.dot(gamma)`
+// (algorithm.rs:253-263, 372-380).  The (P x d) difference table is never formed.
+//
+// Row tiles of X are contiguous in HBM (row-major n x d), so they are staged
+// into shared memory with one 1-D TMA bulk copy each (cp.async.bulk ->
+// SASS UBLKCP) completing on an mbarrier; the column tile is then transposed
+// in shared memory so that the 16 lanes of a half-warp read 16 consecutive
+// double2 (conflict free), and results leave as coalesced 16-byte stores.
+#include "common.cuh"
+#include "../../include/egobox_gpu.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+template <int CORR>
+__device__ __forceinline__ void pair_term(const CorrTerm& t, double dx, double& acc, double& prod) {
+    if (CORR == EGX_CORR_SQUARED_EXPONENTIAL) {
+        acc += t.k1 * (dx * dx);
+    } else if (CORR == EGX_CORR_ABSOLUTE_EXPONENTIAL) {
+        acc += t.k1 * fabs(dx);
+    } else if (CORR == EGX_CORR_MATERN32) {
+        const double ad = fabs(dx);
+        prod *= 1.0 + t.k2 * ad;
+        acc += t.k1 * ad;
+    } else {
+        const double ad = fabs(dx);
+        prod *= (1.0 + t.k2 * ad) + (5.0 / 3.0) * ((t.k3 * dx) * dx);
+        acc += t.k1 * ad;
+    }
+}
+template <int CORR>
+__device__ __forceinline__ double pair_finish(double acc, double prod) {
+    if (CORR == EGX_CORR_SQUARED_EXPONENTIAL) return exp(-0.5 * acc);
+    if (CORR == EGX_CORR_ABSOLUTE_EXPONENTIAL) return exp(-acc);
+    if (CORR == EGX_CORR_MATERN32) return prod * exp(-1.7320508075688772 * acc);
+    return prod * exp(-2.23606797749979 * acc);
+}
+
+// Each of the 256 threads owns a 4 x 4 patch of the 64 x 64 tile:
+// rows ty + 16*ri, columns 2*tx + 32*cj + {0,1}.
+template <int CORR>
+__device__ __forceinline__ void tile_values(const double* __restrict__ Xi, const double* __restrict__ XjT,
+                                            const CorrTerm* __restrict__ terms, int nterms, int d, int ty,
+                                            int tx, double (&out)[4][4]) {
+    double acc[4][4], prod[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            acc[a][b] = 0.0;
+            prod[a][b] = 1.0;
+        }
+    for (int t = 0; t < nterms; ++t) {
+        const CorrTerm tm = terms[t];
+        double xi[4];
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) xi[ri] = Xi[(ty + 16 * ri) * d + tm.dim];
+        const double2 xa = *reinterpret_cast<const double2*>(&XjT[tm.dim * EGX_CT + 2 * tx]);
+        const double2 xb = *reinterpret_cast<const double2*>(&XjT[tm.dim * EGX_CT + 2 * tx + 32]);
+        const double xj[4] = {xa.x, xa.y, xb.x, xb.y};
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pair_term<CORR>(tm, xi[ri] - xj[c], acc[ri][c], prod[ri][c]);
+    }
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out[ri][c] = pair_finish<CORR>(acc[ri][c], prod[ri][c]);
+}
+
+__device__ __forceinline__ void tri_decode(int t, int& r, int& c) {
+    int rr = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
+    while ((rr + 1) * (rr + 2) / 2 <= t) ++rr;
+    while (rr * (rr + 1) / 2 > t) --rr;
+    r = rr;
+    c = t - rr * (rr + 1) / 2;
+}
+
+// ---------------------------------------------------------------------------
+// K1: R(theta), every 64 x 64 tile inside the lower 128-block triangle.
+// X is the zero-padded (npad x d) normalised training set.
+// ---------------------------------------------------------------------------
+template <int CORR>
+__global__ void __launch_bounds__(256)
+    corr_build_kernel(const double* __restrict__ X, int n, int d, const CorrTerm* __restrict__ gterms,
+                      int nterms, double* __restrict__ M, long ld, double diag_value) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Xi = reinterpret_cast<double*>(smem_raw + 16);
+    double* Xj = Xi + EGX_CT * d;
+    double* XjT = Xj + EGX_CT * d;
+    CorrTerm* terms = reinterpret_cast<CorrTerm*>(XjT + EGX_CT * d);
+
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.x >> 2, sub = blockIdx.x & 3;
+    int R, C;
+    tri_decode(pair, R, C);
+    const int i0 = (2 * R + (sub >> 1)) * EGX_CT;
+    const int j0 = (2 * C + (sub & 1)) * EGX_CT;
+    const uint32_t bytes = static_cast<uint32_t>(EGX_CT * d * sizeof(double));
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, 2 * bytes);
+        bulk_g2s(Xi, X + static_cast<long>(i0) * d, bytes, bar);
+        bulk_g2s(Xj, X + static_cast<long>(j0) * d, bytes, bar);
+    }
+    for (int t = tid; t < nterms; t += 256) terms[t] = gterms[t];
+    mbar_wait(bar, 0);
+    for (int e = tid; e < EGX_CT * d; e += 256) {
+        const int r = e / d, c = e - r * d;
+        XjT[c * EGX_CT + r] = Xj[e];
+    }
+    __syncthreads();
+
+    const int ty = tid >> 4, tx = tid & 15;
+    double v[4][4];
+    tile_values<CORR>(Xi, XjT, terms, nterms, d, ty, tx, v);
+
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+        const int i = i0 + ty + 16 * ri;
+#pragma unroll
+        for (int cj = 0; cj < 2; ++cj) {
+            const int j = j0 + 2 * tx + 32 * cj;
+            double a = v[ri][2 * cj], b = v[ri][2 * cj + 1];
+            if (i >= n || j >= n) a = 0.0;
+            if (i >= n || j + 1 >= n) b = 0.0;
+            if (i == j) a = (i < n) ? diag_value : 1.0;
+            if (i == j + 1) b = (i < n) ? diag_value : 1.0;
+            *reinterpret_cast<double2*>(&M[static_cast<long>(i) * ld + j]) = make_double2(a, b);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: cross-correlation of a block of 64 prediction points against all
+// training points, fused with yhat = f(x) beta + c(x, X) gamma.  Optionally
+// stores c into Y (row-major, ldy) for the variance TRSM.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double basis_value(const double* x, int bi, int bj) {
+    const double a = bi < 0 ? 1.0 : x[bi];
+    const double b = bj < 0 ? 1.0 : x[bj];
+    return a * b;
+}
+
+template <int CORR>
+__global__ void __launch_bounds__(256)
+    cross_corr_kernel(const double* __restrict__ xraw, int m, const double* __restrict__ x_mean,
+                      const double* __restrict__ x_std, const double* __restrict__ X, int n, int npad, int d,
+                      const CorrTerm* __restrict__ gterms, int nterms, const double* __restrict__ gamma,
+                      const double* __restrict__ beta, const int* __restrict__ basis_i,
+                      const int* __restrict__ basis_j, int p, double y_mean, double y_std,
+                      double* __restrict__ Y, long ldy, double* __restrict__ yout) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Xp = reinterpret_cast<double*>(smem_raw + 16);
+    double* Xj = Xp + EGX_CT * d;
+    double* XjT = Xj + EGX_CT * d;
+    double* gam = XjT + EGX_CT * d;
+    double* ysum = gam + EGX_CT;
+    CorrTerm* terms = reinterpret_cast<CorrTerm*>(ysum + EGX_CT);
+
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.x * EGX_CT;
+    const uint32_t bytes = static_cast<uint32_t>(EGX_CT * d * sizeof(double));
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    for (int e = tid; e < EGX_CT * d; e += 256) {
+        const int r = e / d, c = e - r * d;
+        const int i = i0 + r;
+        Xp[e] = (i < m) ? (xraw[static_cast<long>(i) * d + c] - x_mean[c]) / x_std[c] : 0.0;
+    }
+    for (int t = tid; t < nterms; t += 256) terms[t] = gterms[t];
+    __syncthreads();
+
+    const int ty = tid >> 4, tx = tid & 15;
+    double yacc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int ntiles = npad / EGX_CT;
+    for (int jt = 0; jt < ntiles; ++jt) {
+        const int j0 = jt * EGX_CT;
+        if (tid == 0) {
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(Xj, X + static_cast<long>(j0) * d, bytes, bar);
+        }
+        if (tid < EGX_CT) gam[tid] = (gamma != nullptr && j0 + tid < n) ? gamma[j0 + tid] : 0.0;
+        mbar_wait(bar, jt & 1);
+        for (int e = tid; e < EGX_CT * d; e += 256) {
+            const int r = e / d, c = e - r * d;
+            XjT[c * EGX_CT + r] = Xj[e];
+        }
+        __syncthreads();
+
+        double v[4][4];
+        tile_values<CORR>(Xp, XjT, terms, nterms, d, ty, tx, v);
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) {
+            const int i = i0 + ty + 16 * ri;
+#pragma unroll
+            for (int cj = 0; cj < 2; ++cj) {
+                const int jl = 2 * tx + 32 * cj;
+                double a = v[ri][2 * cj], b = v[ri][2 * cj + 1];
+                if (i >= m || j0 + jl >= n) a = 0.0;
+                if (i >= m || j0 + jl + 1 >= n) b = 0.0;
+                yacc[ri] += a * gam[jl] + b * gam[jl + 1];
+                if (Y != nullptr)
+                    *reinterpret_cast<double2*>(&Y[static_cast<long>(i) * ldy + j0 + jl]) = make_double2(a, b);
+            }
+        }
+        __syncthreads();   // Xj / XjT / gam are overwritten by the next tile
+    }
+
+    if (yout != nullptr) {
+        // reduce the 16 column-lanes of each row group (lanes tx = 0..15 of a half-warp)
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) {
+            double s = yacc[ri];
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (tx == 0) ysum[ty + 16 * ri] = s;
+        }
+        __syncthreads();
+        if (tid < EGX_CT && i0 + tid < m) {
+            const double* x = Xp + tid * d;
+            double f = 0.0;
+            for (int l = 0; l < p; ++l) f += basis_value(x, basis_i[l], basis_j[l]) * beta[l];
+            yout[i0 + tid] = (f + ysum[tid]) * y_std + y_mean;
+        }
+    }
+}
+
+// F^T rows (p x npad) followed by ynorm as row p: the right-hand sides that are
+// carried through the Cholesky as extra rows of the matrix (forward solves fused).
+__global__ void mean_basis_rows_kernel(const double* __restrict__ X, int n, int npad, int d,
+                                       const int* __restrict__ basis_i, const int* __restrict__ basis_j, int p,
+                                       const double* __restrict__ ynorm, double* __restrict__ FyT, long ld) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npad) return;
+    const double* x = X + static_cast<long>(j) * d;
+    for (int l = 0; l < p; ++l) FyT[static_cast<long>(l) * ld + j] = (j < n) ? basis_value(x, basis_i[l], basis_j[l]) : 0.0;
+    FyT[static_cast<long>(p) * ld + j] = (j < n) ? ynorm[j] : 0.0;
+}
+
+size_t corr_build_smem(int d, int nterms) { return 16 + 3 * EGX_CT * d * sizeof(double) + nterms * sizeof(CorrTerm); }
+size_t cross_corr_smem(int d, int nterms) {
+    return 16 + 3 * EGX_CT * d * sizeof(double) + 2 * EGX_CT * sizeof(double) + nterms * sizeof(CorrTerm);
+}
+
+template <typename K>
+void set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+}
+
+}  // namespace
+
+void launch_corr_build(int corr, const double* X, int n, int npad, int d, const CorrTerm* terms, int nterms,
+                       double* M, long ld, double diag_value, cudaStream_t s) {
+    const int T = npad / EGX_NB;
+    const int grid = 4 * (T * (T + 1) / 2);
+    const size_t smem = corr_build_smem(d, nterms);
+#define EGX_LAUNCH_K1(CK)                                                                         \
+    set_smem(corr_build_kernel<CK>, smem);                                                        \
+    corr_build_kernel<CK><<<grid, 256, smem, s>>>(X, n, d, terms, nterms, M, ld, diag_value);
+    switch (corr) {
+        case EGX_CORR_SQUARED_EXPONENTIAL: EGX_LAUNCH_K1(EGX_CORR_SQUARED_EXPONENTIAL) break;
+        case EGX_CORR_ABSOLUTE_EXPONENTIAL: EGX_LAUNCH_K1(EGX_CORR_ABSOLUTE_EXPONENTIAL) break;
+        case EGX_CORR_MATERN32: EGX_LAUNCH_K1(EGX_CORR_MATERN32) break;
+        default: EGX_LAUNCH_K1(EGX_CORR_MATERN52) break;
+    }
+#undef EGX_LAUNCH_K1
+}
+
+void launch_cross_corr(int corr, const double* xraw, int m, int mpad, const double* x_mean, const double* x_std,
+                       const double* X, int n, int npad, int d, const CorrTerm* terms, int nterms,
+                       const double* gamma, const double* beta, const int* basis_i, const int* basis_j, int p,
+                       double y_mean, double y_std, double* Y, long ldy, double* yout, cudaStream_t s) {
+    const int grid = mpad / EGX_CT;
+    const size_t smem = cross_corr_smem(d, nterms);
+#define EGX_LAUNCH_K2(CK)                                                                               \
+    set_smem(cross_corr_kernel<CK>, smem);                                                              \
+    cross_corr_kernel<CK><<<grid, 256, smem, s>>>(xraw, m, x_mean, x_std, X, n, npad, d, terms, nterms, \
+                                                  gamma, beta, basis_i, basis_j, p, y_mean, y_std, Y, ldy, yout);
+    switch (corr) {
+        case EGX_CORR_SQUARED_EXPONENTIAL: EGX_LAUNCH_K2(EGX_CORR_SQUARED_EXPONENTIAL) break;
+        case EGX_CORR_ABSOLUTE_EXPONENTIAL: EGX_LAUNCH_K2(EGX_CORR_ABSOLUTE_EXPONENTIAL) break;
+        case EGX_CORR_MATERN32: EGX_LAUNCH_K2(EGX_CORR_MATERN32) break;
+        default: EGX_LAUNCH_K2(EGX_CORR_MATERN52) break;
+    }
+#undef EGX_LAUNCH_K2
+}
+
+void launch_mean_basis_rows(const double* X, int n, int npad, int d, const int* basis_i, const int* basis_j, int p,
+                            const double* ynorm_dev, double* FyT, long ld, cudaStream_t s) {
+    mean_basis_rows_kernel<<<(npad + 255) / 256, 256, 0, s>>>(X, n, npad, d, basis_i, basis_j, p, ynorm_dev, FyT, ld);
+}

@@ -1,0 +1,156 @@
+/* egobox_gpu.h -- C ABI of the B200-native kriging hot path (libegobox_gpu.so).
+ *
+ * This is the drop-in boundary for egobox-gp's kriging training / prediction
+ * path.  The reference (relf/egobox @ be16128) has no FFI for this path; its
+ * seams are Rust traits and one free function, and each entry point below
+ * names the reference interface it replaces (file:line under
+ * /root/reference/crates/).  INTEGRATION.md shows the Rust `extern "C"`
+ * binding a maintainer would add under `cfg(feature = "cuda")`.
+ *
+ * Conventions
+ *  - f64 everywhere, arrays row-major (ndarray C order), caller owns every
+ *    host buffer, the opaque handle owns all device state.
+ *  - Every function returns an `int` status (EGX_*).  Numerical failures are
+ *    statuses, never aborts, so a caller can map them to `+inf` exactly like
+ *    gp/src/algorithm.rs:893-896 does with `Err(_)`.
+ *  - Calls on one handle are serialised by a handle-level mutex (the
+ *    reference calls `reduced_likelihood` from rayon workers,
+ *    gp/src/algorithm.rs:928-945); different handles are independent.
+ *  - There is no CPU fallback: without a CUDA device every call that needs
+ *    one returns EGX_CUDA_ERROR.
+ */
+#ifndef EGOBOX_GPU_H
+#define EGOBOX_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes --------------------------------------------------------
+ * 1 <-> GpError::LinalgError (gp/src/errors.rs:19, Cholesky of a non-PD R,
+ *       gp/src/algorithm.rs:1004)
+ * 2,3 <-> GpError::LikelihoodComputationError (gp/src/algorithm.rs:1012-1026)
+ * 4 <-> GpError::InvalidValueError (gp/src/errors.rs:38)                     */
+#define EGX_OK                    0
+#define EGX_NOT_POSITIVE_DEFINITE 1
+#define EGX_ILL_CONDITIONED_FT    2
+#define EGX_ILL_CONDITIONED_F     3
+#define EGX_INVALID_VALUE         4
+#define EGX_CUDA_ERROR            5
+
+/* correlation models, gp/src/correlation_models.rs:87,181,273,442 */
+#define EGX_CORR_SQUARED_EXPONENTIAL  0
+#define EGX_CORR_ABSOLUTE_EXPONENTIAL 1
+#define EGX_CORR_MATERN32             2
+#define EGX_CORR_MATERN52             3
+
+/* regression (mean) models, gp/src/mean_models.rs:39,65,94 */
+#define EGX_MEAN_CONSTANT  0
+#define EGX_MEAN_LINEAR    1
+#define EGX_MEAN_QUADRATIC 2
+
+typedef struct egx_gp_ctx egx_gp_ctx;
+
+/* Library / device probe.  Returns the number of visible CUDA devices (0 if
+ * none); never fails. */
+int egx_device_count(void);
+/* Thread-local description of the last non-OK status on this thread. */
+const char* egx_last_error(void);
+const char* egx_version(void);
+
+/* ---- model context --------------------------------------------------------
+ * Holds the device-resident training set of one GP: normalised inputs,
+ * normalised output, the regression basis F = mean.value(xnorm), PLS weights.
+ * Replaces the state captured by the `objfn` closure in
+ * gp/src/algorithm.rs:856-897 (xtrain, ytrain, x_distances, fx, w_star) --
+ * the DiffMatrix (gp/src/utils.rs:58-105) is never materialised.
+ *
+ *   xnorm  n x d   normalised training inputs   (NormalizedData, utils.rs:28-54)
+ *   ynorm  n       normalised training output
+ *   x_mean,x_std d ; y_mean,y_std  -- kept to (de)normalise in predict*
+ *   w_star d x h   identity (h == d) or PLS rotations (algorithm.rs:843-855)
+ *   nugget         (1+nugget) on the diagonal of R (algorithm.rs:997)
+ */
+int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean,
+                  const double* xnorm, int n, int d, const double* ynorm,
+                  const double* x_mean, const double* x_std,
+                  double y_mean, double y_std,
+                  const double* w_star, int h, double nugget);
+void egx_gp_destroy(egx_gp_ctx* ctx);
+
+/* sizes: n, d, h (theta length), p (regression basis size) */
+int egx_gp_dims(const egx_gp_ctx* ctx, int* n, int* d, int* h, int* p);
+
+/* Reduced likelihood at theta (length h).
+ * Replaces `corr.value(D, theta, W)` + `reduced_likelihood(..)`:
+ * gp/src/algorithm.rs:892-893 and :989-1056 (value `.0` only).
+ * On status != EGX_OK, *rlf is NaN and the caller maps it to +inf. */
+int egx_gp_reduced_likelihood(egx_gp_ctx* ctx, const double* theta, double* rlf);
+
+/* Batched form of the above for B candidate thetas (row-major B x h):
+ * multistart chains advanced in lock step (gp/src/algorithm.rs:928-945) and
+ * theta sweeps.  status[b] holds the per-candidate status; the return value
+ * is EGX_OK unless the call itself failed (bad argument, CUDA error). */
+int egx_gp_reduced_likelihood_batch(egx_gp_ctx* ctx, const double* thetas, int B,
+                                    double* rlf, int* status);
+
+/* Final evaluation at the selected theta (gp/src/algorithm.rs:966-968): keeps
+ * the Cholesky factor, gamma, beta, Ft, G on the device for predict*, and
+ * optionally returns GpInnerParams (algorithm.rs:47-60) -- any output pointer
+ * may be NULL.  sigma2 is already multiplied by y_std^2 (algorithm.rs:1048).
+ *   beta p ; gamma n ; ft n x p ; ft_qr_r p x p (upper, diag > 0)            */
+int egx_gp_finalize(egx_gp_ctx* ctx, const double* theta, double* rlf, double* sigma2,
+                    double* beta, double* gamma, double* ft, double* ft_qr_r);
+
+/* r_chol (n x n, lower, upper part zeroed) for serde save
+ * (GpInnerParams.r_chol, gp/src/algorithm.rs:54-55). */
+int egx_gp_download_chol(egx_gp_ctx* ctx, double* r_chol);
+
+/* Prediction at m raw (un-normalised) points x (m x d).  Require a prior
+ * successful egx_gp_finalize.
+ *   predict        gp/src/algorithm.rs:253-263
+ *   predict_var    gp/src/algorithm.rs:267-279  (+ _compute_rt_u :330-369)
+ *   predict_valvar gp/src/algorithm.rs:282-307                               */
+int egx_gp_predict(egx_gp_ctx* ctx, const double* x, int m, double* y);
+int egx_gp_predict_var(egx_gp_ctx* ctx, const double* x, int m, double* var);
+int egx_gp_predict_valvar(egx_gp_ctx* ctx, const double* x, int m, double* y, double* var);
+
+/* Same, with x / y / var already resident on the context's device (device
+ * pointers).  Used to time the kernels without the PCIe copies. */
+int egx_gp_predict_valvar_dev(egx_gp_ctx* ctx, const double* x_dev, int m,
+                              double* y_dev, double* var_dev);
+
+/* ---- building blocks exposed for parity tests ------------------------------
+ * R(theta) as assembled at gp/src/algorithm.rs:997-1001 (full symmetric n x n,
+ * (1+nugget) on the diagonal), computed by the fused pairwise-distance +
+ * correlation kernel. */
+int egx_gp_correlation_matrix(egx_gp_ctx* ctx, const double* theta, double* r);
+/* c(x*, X) as in `_compute_correlation`, gp/src/algorithm.rs:372-380 (m x n),
+ * for the theta of the last finalize. */
+int egx_gp_cross_correlation(egx_gp_ctx* ctx, const double* x, int m, double* c);
+
+/* ---- instrumentation --------------------------------------------------------
+ * Per-stage device timings (CUDA events on the context's stream) accumulated
+ * since the last reset, for bench.py's roofline block.  Stage ids: */
+#define EGX_STAGE_CORR_BUILD   0  /* fused distance + correlation, R lower tiles */
+#define EGX_STAGE_POTRF_DIAG   1  /* diagonal-panel Cholesky                    */
+#define EGX_STAGE_TRSM_PANEL   2  /* panel / row triangular solves               */
+#define EGX_STAGE_SYRK_GEMM    3  /* trailing SYRK / GEMM updates (DMMA)         */
+#define EGX_STAGE_GLS          4  /* thin QR, beta, rho, sigma2, logdet          */
+#define EGX_STAGE_BACKSOLVE    5  /* gamma = L^-T rho                            */
+#define EGX_STAGE_CROSS_CORR   6  /* c(x*, X) (+ fused mean / gamma GEMV)        */
+#define EGX_STAGE_VAR_FINISH   7  /* row norms, u, variance                      */
+#define EGX_STAGE_SMALL_BATCH  8  /* one-CTA-per-theta small-n likelihood        */
+#define EGX_NUM_STAGES         9
+int egx_gp_set_profiling(egx_gp_ctx* ctx, int enabled);
+int egx_gp_reset_profile(egx_gp_ctx* ctx);
+/* ms[EGX_NUM_STAGES], launches[EGX_NUM_STAGES] */
+int egx_gp_get_profile(egx_gp_ctx* ctx, double* ms, long long* launches);
+/* Force the blocked large-n path even when n is small enough for the
+ * one-CTA-per-theta kernel (tests exercise both on the same inputs). */
+int egx_gp_set_force_blocked(egx_gp_ctx* ctx, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOBOX_GPU_H */

@@ -1,0 +1,43 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads and exports every
+symbol include/egobox_gpu.h declares; without a GPU the product path fails loudly."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "egobox_gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(egx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from egobox_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), name
+        assert name in _lib.SIGNATURES, "ctypes signature missing for %s" % name
+    assert set(_lib.SIGNATURES) <= set(declared)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import egobox_b200 as eg
+    if eg.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(eg.GpuError):
+        eg.GpContext(np.zeros((5, 1)), np.zeros(5), [0.0], [1.0], 0.0, 1.0, eg.SQUARED_EXPONENTIAL, eg.CONSTANT)
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "egobox_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,208 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances: the north-star asks for 1e-6 relative (fp64) on log-likelihood, predict and
+predict_var; the tests below hold the path to much tighter bounds where conditioning allows
+and state the bound used next to each assert."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as O
+from tests.gpu_util import make_problem, make_context, oracle_gp
+
+pytestmark = pytest.mark.gpu
+
+CORRS = [O.SQEXP, O.ABSEXP, O.MATERN32, O.MATERN52]
+
+
+def _arr(o):
+    return np.array(o["data"], dtype=np.float64).reshape(o["dim"])
+
+
+# ---------------------------------------------------------------- K1 ---------
+@pytest.mark.parametrize("corr", CORRS)
+@pytest.mark.parametrize("n,d", [(5, 1), (130, 3), (333, 10)])
+def test_correlation_matrix(corr, n, d):
+    x, y = make_problem(n, d, seed=n)
+    ctx, (xn, *_rest) = make_context(x, y, corr, O.CONSTANT)
+    theta = np.linspace(0.3, 1.7, d)
+    R = ctx.correlation_matrix(theta)
+    Ro = O.corr_matrix(corr, xn, theta, np.eye(d))
+    np.testing.assert_allclose(R, Ro, rtol=1e-13, atol=1e-300)
+    ctx.close()
+
+
+@pytest.mark.parametrize("corr", CORRS)
+def test_correlation_matrix_kpls_weights(corr):
+    n, d, h = 150, 6, 2
+    x, y = make_problem(n, d, seed=3)
+    rng = np.random.default_rng(5)
+    w = rng.normal(size=(d, h))
+    w[2, 0] = 0.0
+    ctx, (xn, *_rest) = make_context(x, y, corr, O.CONSTANT, w_star=w)
+    theta = np.array([0.4, 1.3])
+    R = ctx.correlation_matrix(theta)
+    Ro = O.corr_matrix(corr, xn, theta, w)
+    np.testing.assert_allclose(R, Ro, rtol=1e-13, atol=1e-300)
+    ctx.close()
+
+
+def test_reference_kernel_known_answers():
+    # correlation_models.rs:597-641 / 718-726 through the GPU kernel (n=3, d=2, no normalisation)
+    import egobox_b200 as eg
+    xt = np.array([[0.0, 1.0], [2.0, 3.0], [4.0, 5.0]])
+    for corr, theta, exp in [(O.SQEXP, [np.sqrt(2.0), 2.0], [6.14421235e-06, 1.42516408e-21, 6.14421235e-06]),
+                             (O.MATERN32, [1.0, 2.0], [1.08539595e-03, 1.10776401e-07, 1.08539595e-03]),
+                             (O.MATERN52, [1.0, 2.0], [6.62391590e-04, 1.02117882e-08, 6.62391590e-04])]:
+        ctx = eg.GpContext(xt, np.zeros(3), [0, 0], [1, 1], 0.0, 1.0, corr, O.CONSTANT)
+        R = ctx.correlation_matrix(theta)
+        np.testing.assert_allclose([R[0, 1], R[0, 2], R[1, 2]], exp, rtol=1e-8, atol=1e-6)
+        ctx.close()
+
+
+# ------------------------------------------------- reduced likelihood --------
+def test_notebook_model_through_gpu(golden_dir):
+    """doc/Gpx_Tutorial.ipynb:420-421: the 16-digit Linear+Matern52 model."""
+    with open(os.path.join(golden_dir, "gpx_tutorial_linear_matern52.json")) as f:
+        m = json.load(f)
+    xt, yt = _arr(m["training_data"][0]), _arr(m["training_data"][1])
+    theta = _arr(m["theta"])
+    ctx, _ = make_context(xt, yt, O.MATERN52, O.LINEAR, nugget=m["params"]["nugget"])
+    st, res = ctx.finalize(theta)
+    ip = m["inner_params"]
+    assert st == 0
+    assert res["rlf"] == pytest.approx(m["likelihood"], rel=1e-12)
+    assert res["sigma2"] == pytest.approx(ip["sigma2"], rel=1e-11)
+    np.testing.assert_allclose(res["beta"], _arr(ip["beta"])[:, 0], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(res["gamma"], _arr(ip["gamma"])[:, 0], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(res["ft"], _arr(ip["ft"]), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(res["ft_qr_r"], _arr(ip["ft_qr_r"]), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(ctx.download_chol(), _arr(ip["r_chol"]), rtol=0, atol=1e-15)
+    ctx.close()
+
+
+def test_kriging5_through_gpu(golden_dir):
+    """doc/Gpx_Tutorial.ipynb:165-167 + python/egobox/tests/test_gpmix.py:37-46."""
+    with open(os.path.join(golden_dir, "gpx_tutorial_kriging5.json")) as f:
+        k = json.load(f)
+    xt = np.array(k["xt"])[:, None]
+    yt = np.array(k["yt"])
+    ctx, _ = make_context(xt, yt, O.SQEXP, O.CONSTANT)
+    st, res = ctx.finalize([k["theta"]])
+    assert st == 0
+    assert res["rlf"] == pytest.approx(k["likelihood"], rel=1e-9)
+    assert res["sigma2"] == pytest.approx(k["variance"], rel=2e-8)
+    assert ctx.predict(np.array([[1.0]]))[0] == pytest.approx(1.0, abs=1e-7)
+    assert ctx.predict_var(np.array([[1.0]]))[0] == pytest.approx(0.0, abs=1e-7)
+    assert ctx.predict(np.array([[1.1]]))[0] == pytest.approx(1.1163, abs=1e-3)
+    assert ctx.predict_var(np.array([[1.1]]))[0] == pytest.approx(0.0, abs=1e-3)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,d,corr,mean", [
+    (200, 1, O.SQEXP, O.CONSTANT),        # BASELINE config C1 shape
+    (257, 4, O.ABSEXP, O.LINEAR),
+    (500, 10, O.MATERN52, O.CONSTANT),
+    (384, 5, O.MATERN32, O.QUADRATIC),
+    (1000, 10, O.MATERN52, O.LINEAR),
+])
+def test_reduced_likelihood_and_state(n, d, corr, mean):
+    x, y = make_problem(n, d, seed=7)
+    theta = np.full(d, 2.0) if corr != O.SQEXP else np.full(d, 5.0)
+    ctx, _ = make_context(x, y, corr, mean)
+    gp = oracle_gp(x, y, corr, mean, theta)
+    st, rlf = ctx.reduced_likelihood(theta)
+    assert st == 0
+    assert rlf == pytest.approx(gp.likelihood, rel=1e-9)          # north-star bound: 1e-6
+    st, res = ctx.finalize(theta)
+    assert st == 0
+    assert res["rlf"] == pytest.approx(gp.likelihood, rel=1e-9)
+    assert res["sigma2"] == pytest.approx(gp.inner.sigma2, rel=1e-8)
+    L = ctx.download_chol()
+    np.testing.assert_allclose(L, gp.inner.r_chol, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(res["ft"], gp.inner.ft, rtol=0, atol=1e-8 * max(1.0, np.abs(gp.inner.ft).max()))
+    np.testing.assert_allclose(res["ft_qr_r"], gp.inner.ft_qr_r, rtol=1e-8, atol=1e-8 * np.abs(gp.inner.ft_qr_r).max())
+    gs = np.abs(gp.inner.gamma).max()
+    np.testing.assert_allclose(res["gamma"], gp.inner.gamma[:, 0], rtol=0, atol=1e-7 * gs)
+    np.testing.assert_allclose(res["beta"], gp.inner.beta[:, 0], rtol=1e-7, atol=1e-9)
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,d,corr,mean", [
+    (200, 1, O.SQEXP, O.CONSTANT),
+    (500, 10, O.MATERN52, O.CONSTANT),
+    (300, 3, O.MATERN32, O.LINEAR),
+    (260, 2, O.ABSEXP, O.QUADRATIC),
+])
+def test_predict_valvar(n, d, corr, mean):
+    x, y = make_problem(n, d, seed=11)
+    theta = np.full(d, 1.5) if corr != O.SQEXP else np.full(d, 4.0)
+    ctx, _ = make_context(x, y, corr, mean)
+    gp = oracle_gp(x, y, corr, mean, theta)
+    st, _res = ctx.finalize(theta)
+    assert st == 0
+    rng = np.random.default_rng(43)
+    xs = rng.random((777, d))
+    yo, vo = gp.predict_valvar(xs)
+    yg, vg = ctx.predict_valvar(xs)
+    scale = np.abs(yo).max()
+    np.testing.assert_allclose(yg, yo, rtol=1e-7, atol=1e-8 * scale)      # bound: 1e-6 relative
+    np.testing.assert_allclose(vg, vo, rtol=1e-6, atol=1e-8 * gp.inner.sigma2)
+    np.testing.assert_allclose(ctx.predict(xs), yg, rtol=0, atol=1e-12 * scale)   # moe/src/algorithm.rs:1549-1552
+    np.testing.assert_allclose(ctx.predict_var(xs), vg, rtol=0, atol=1e-12 * gp.inner.sigma2)
+    c = ctx.cross_correlation(xs[:70])
+    co = gp._compute_correlation(gp._xnorm(xs[:70]))
+    np.testing.assert_allclose(c, co, rtol=1e-12, atol=1e-300)
+    ctx.close()
+
+
+def test_batch_equals_single():
+    x, y = make_problem(300, 4, seed=5)
+    ctx, _ = make_context(x, y, O.MATERN52, O.CONSTANT)
+    rng = np.random.default_rng(1)
+    thetas = 10.0 ** rng.uniform(-1.5, 0.8, size=(6, 4))
+    status, rlf = ctx.reduced_likelihood_batch(thetas)
+    for b in range(6):
+        st, v = ctx.reduced_likelihood(thetas[b])
+        assert st == status[b]
+        if st == 0:
+            assert v == rlf[b]
+    ctx.close()
+
+
+# -------------------------------------------------- failure signalling -------
+def test_not_positive_definite_status():
+    # duplicated rows + zero nugget -> singular R -> status 1 (GpError::LinalgError -> +inf objective)
+    x = np.array([[0.0], [0.0], [1.0], [2.0]])
+    y = np.array([0.0, 0.0, 1.0, 2.0])
+    ctx, _ = make_context(x, y, O.SQEXP, O.CONSTANT, nugget=0.0)
+    st, rlf = ctx.reduced_likelihood([1.0])
+    assert st == 1 and np.isnan(rlf)
+    ctx.close()
+
+
+def test_nan_theta_is_invalid_value():
+    import egobox_b200 as eg
+    x, y = make_problem(50, 2, seed=1)
+    ctx, _ = make_context(x, y, O.SQEXP, O.CONSTANT)
+    with pytest.raises(eg.GpuError):
+        ctx.finalize([np.nan, 1.0])
+    ctx.close()
+
+
+def test_ill_conditioned_ft_status():
+    # quadratic trend on points that only span a line in 2-D: F has dependent columns
+    t = np.linspace(0.0, 1.0, 40)
+    x = np.stack([t, 2.0 * t], axis=1)
+    y = np.sin(3 * t)
+    ctx, _ = make_context(x, y, O.SQEXP, O.QUADRATIC)
+    st, _ = ctx.reduced_likelihood([1.0, 1.0])
+    assert st in (2, 3)
+    from oracle.gp_oracle import LikelihoodComputationError
+    xn, _, _ = O.normalize(x)
+    yn, _, ys = O.normalize(y.reshape(-1, 1))
+    with pytest.raises(LikelihoodComputationError):
+        O.reduced_likelihood(O.SQEXP, xn, O.mean_value(O.QUADRATIC, xn), yn, float(ys[0]), [1.0, 1.0], np.eye(2))
+    ctx.close()

@@ -1,0 +1,57 @@
+"""First-light probe: per-stage device timings of one likelihood evaluation and a
+predict_valvar chunk at a few sizes (not a bench; prints JSON lines to stdout)."""
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from oracle import gp_oracle as O          # noqa: E402  (probe = test infrastructure)
+from tests.gpu_util import make_problem, make_context   # noqa: E402
+
+
+def main():
+    sizes = [int(a) for a in sys.argv[1:]] or [1024, 4096, 8192]
+    for n in sizes:
+        d = 10
+        x, y = make_problem(n, d, seed=42)
+        ctx, _ = make_context(x, y, O.MATERN52, O.CONSTANT)
+        theta = np.full(d, 1.0)
+        for _ in range(2):
+            ctx.reduced_likelihood(theta)
+        ctx.set_profiling(True)
+        ctx.reset_profile()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            st, rlf = ctx.reduced_likelihood(theta)
+        t1 = time.perf_counter()
+        prof = ctx.profile()
+        print(json.dumps({"n": n, "status": st, "rlf": rlf, "wall_ms_per_eval": (t1 - t0) / reps * 1e3,
+                          "stage_ms_per_eval": {k: round(v[0] / reps, 4) for k, v in prof.items()},
+                          "launches_per_eval": {k: v[1] // reps for k, v in prof.items()}}), flush=True)
+        ctx.set_profiling(False)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.reduced_likelihood(theta)
+        t1 = time.perf_counter()
+        print(json.dumps({"n": n, "wall_ms_per_eval_noprof": (t1 - t0) / reps * 1e3}), flush=True)
+        st, res = ctx.finalize(theta)
+        m = 8192
+        xs = np.random.default_rng(43).random((m, d))
+        ctx.predict_valvar(xs[:256])
+        ctx.set_profiling(True)
+        ctx.reset_profile()
+        t0 = time.perf_counter()
+        yv = ctx.predict_valvar(xs)
+        t1 = time.perf_counter()
+        prof = ctx.profile()
+        print(json.dumps({"n": n, "m": m, "predict_valvar_wall_ms": (t1 - t0) * 1e3,
+                          "stage_ms": {k: round(v[0], 4) for k, v in prof.items()},
+                          "var_min": float(yv[1].min()), "var_max": float(yv[1].max())}), flush=True)
+        ctx.close()
+
+
+if __name__ == "__main__":
+    main()
