@@ -5,3 +5,8 @@ in hand-written CUDA kernels behind the C ABI of ``include/egobox_gpu.h``."""
 from ._lib import GpuError, device_count, load as load_library  # noqa: F401
 from .context import (GpContext, SQUARED_EXPONENTIAL, ABSOLUTE_EXPONENTIAL, MATERN32, MATERN52,  # noqa: F401
                       CONSTANT, LINEAR, QUADRATIC, DEFAULT_NUGGET)
+from .gp import (GaussianProcess, GpParams, Kriging, ThetaTuning, GpError, LinalgError,  # noqa: F401
+                 LikelihoodComputationError, InvalidValueError,
+                 SquaredExponentialCorr, AbsoluteExponentialCorr, Matern32Corr, Matern52Corr,
+                 ConstantMean, LinearMean, QuadraticMean)
+from .gpx import Gpx, GpMix, RegressionSpec, CorrelationSpec, Recombination  # noqa: F401

@@ -48,6 +48,41 @@ SIGNATURES = {
     "egx_gp_set_force_blocked": (C.c_int, [_vp, C.c_int]),
 }
 
+
+
+class GpParamsStruct(C.Structure):
+    """egx_gp_params (include/egobox_gpu.h)."""
+    _fields_ = [("corr", C.c_int), ("mean", C.c_int), ("theta_tuning", C.c_int),
+                ("theta_init", _dp), ("n_theta_init", C.c_int),
+                ("theta_bounds", _dp), ("n_theta_bounds", C.c_int),
+                ("active", _ip), ("n_active", C.c_int),
+                ("n_start", C.c_int), ("max_eval", C.c_int), ("nugget", C.c_double),
+                ("w_star", _dp), ("kpls_dim", C.c_int), ("device", C.c_int),
+                ("seed", C.c_ulonglong), ("cobyla_rhobeg", C.c_double), ("cobyla_ftol_rel", C.c_double)]
+
+
+OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, _dp, C.c_int, C.c_void_p)
+_pp = C.POINTER(GpParamsStruct)
+SIGNATURES.update({
+    "egx_gp_params_default": (None, [_pp]),
+    "egx_gp_fit": (C.c_int, [_pp, _dp, C.c_int, C.c_int, _dp, C.POINTER(_vp)]),
+    "egx_gp_model_destroy": (None, [_vp]),
+    "egx_gp_model_dims": (C.c_int, [_vp, _ip, _ip, _ip, _ip]),
+    "egx_gp_model_theta": (C.c_int, [_vp, _dp]),
+    "egx_gp_model_variance": (C.c_double, [_vp]),
+    "egx_gp_model_likelihood": (C.c_double, [_vp]),
+    "egx_gp_model_n_evals": (C.c_longlong, [_vp]),
+    "egx_gp_model_inner_params": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "egx_gp_model_normalization": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp]),
+    "egx_gp_model_context": (_vp, [_vp]),
+    "egx_gp_model_predict": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_gp_model_predict_var": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_gp_model_predict_valvar": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp]),
+    "egx_bound_cobyla_minimize": (C.c_int, [OBJECTIVE_FN, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_double,
+                                            C.c_double, C.c_int, _dp, _dp, _ip]),
+    "egx_prepare_multistart": (C.c_int, [C.c_int, _dp, _dp, C.c_int, C.c_ulonglong, _dp]),
+})
+
 _lib = None
 
 

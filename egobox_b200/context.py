@@ -64,9 +64,7 @@ class GpContext:
         th = _f64(theta).reshape(-1)
         assert th.size == self.h
         out = C.c_double()
-        st = self._lib.egx_gp_reduced_likelihood(self._h, _ptr(th), C.byref(out))
-        if st == EGX_CUDA_ERROR:
-            raise GpuError(st, _lib.last_error())
+        st = self._check(self._lib.egx_gp_reduced_likelihood(self._h, _ptr(th), C.byref(out)))
         return st, out.value
 
     def reduced_likelihood_batch(self, thetas):
@@ -85,10 +83,8 @@ class GpContext:
         gamma = np.empty(self.n)
         ft = np.empty((self.n, self.p)) if want_ft else None
         g = np.empty((self.p, self.p))
-        st = self._lib.egx_gp_finalize(self._h, _ptr(th), C.byref(rlf), C.byref(s2), _ptr(beta), _ptr(gamma),
-                                       _ptr(ft) if want_ft else None, _ptr(g))
-        if st == EGX_CUDA_ERROR:
-            raise GpuError(st, _lib.last_error())
+        st = self._check(self._lib.egx_gp_finalize(self._h, _ptr(th), C.byref(rlf), C.byref(s2), _ptr(beta),
+                                                   _ptr(gamma), _ptr(ft) if want_ft else None, _ptr(g)))
         return st, dict(rlf=rlf.value, sigma2=s2.value, beta=beta, gamma=gamma, ft=ft, ft_qr_r=g)
 
     def download_chol(self):

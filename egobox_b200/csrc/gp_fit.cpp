@@ -1,0 +1,754 @@
+// Host-side GP model: the fit driver of gp/src/algorithm.rs:791-979 above the device seam.
+//
+//   normalise (utils.rs:45-54) -> device context -> theta0 / bounds / multistart seeds
+//   (algorithm.rs:815-838, 899-925; optimization.rs:26-71) -> n_start+1 derivative-free
+//   chains advanced in LOCK STEP, one egx_gp_reduced_likelihood_batch call per optimiser
+//   iteration (replaces the rayon `into_par_iter` at algorithm.rs:928-945) -> min reduction
+//   -> final evaluation (algorithm.rs:966-968).
+//
+// The optimiser is a linear-interpolation trust-region method in the COBYLA family
+// (Powell 1994: simplex of n+1 points, linear model, trust radius rho halved when the
+// model stops paying, geometry-improvement steps with alpha = 1/4, beta = 2.1, gamma = 1/2),
+// specialised to the only constraints this path has -- simple bounds in log10(theta) -- so
+// the trust-region subproblem is solved exactly (clipped steepest descent) instead of
+// through COBYLA's general LP.  It keeps the reference's settings (rhobeg 0.5, ftol_rel
+// 1e-4, maxeval = clamp(10 dim, 25, max_eval)); the trajectory of the third-party
+// `cobyla 0.8.0` crate is not reproduced (it is not in /root/reference, and the reference
+// pins only the optimum, test_gpmix.py:37-53).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "../../include/egobox_gpu.h"
+
+void egx_set_error(const char* fmt, ...);
+
+namespace {
+
+constexpr double kInf = std::numeric_limits<double>::infinity();
+constexpr int GP_COBYLA_MIN_EVAL = 25;   // gp/src/algorithm.rs:35
+
+// ---- xoshiro256+ (the generator family the reference seeds its LHS with) -------------
+struct Xoshiro256Plus {
+    uint64_t s[4];
+    explicit Xoshiro256Plus(uint64_t seed) {
+        uint64_t z = seed;
+        for (auto& v : s) {   // splitmix64 seeding
+            z += 0x9e3779b97f4a7c15ULL;
+            uint64_t x = z;
+            x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+            x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+            v = x ^ (x >> 31);
+        }
+    }
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next() {
+        const uint64_t r = s[0] + s[3];
+        const uint64_t t = s[1] << 17;
+        s[2] ^= s[0];
+        s[3] ^= s[1];
+        s[1] ^= s[2];
+        s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return r;
+    }
+    double uniform() { return static_cast<double>(next() >> 11) * (1.0 / 9007199254740992.0); }
+    uint64_t below(uint64_t n) { return next() % n; }
+};
+
+// crates/doe/src/lhs.rs:247-268 (classic) and :283-304 (maximin = best of 5 by min pair distance)
+std::vector<double> lhs_classic(int ns, int nx, Xoshiro256Plus& rng) {
+    std::vector<double> pts(static_cast<size_t>(ns) * nx);
+    for (int j = 0; j < nx; ++j) {
+        std::vector<double> col(ns);
+        for (int i = 0; i < ns; ++i) col[i] = (i + rng.uniform()) / ns;
+        for (int i = ns - 1; i > 0; --i) std::swap(col[i], col[rng.below(i + 1)]);
+        for (int i = 0; i < ns; ++i) pts[static_cast<size_t>(i) * nx + j] = col[i];
+    }
+    return pts;
+}
+double min_pdist(const std::vector<double>& p, int ns, int nx) {
+    double best = kInf;
+    for (int a = 0; a < ns; ++a)
+        for (int b = a + 1; b < ns; ++b) {
+            double s = 0.0;
+            for (int j = 0; j < nx; ++j) {
+                const double t = p[static_cast<size_t>(a) * nx + j] - p[static_cast<size_t>(b) * nx + j];
+                s += t * t;
+            }
+            best = std::min(best, std::sqrt(s));
+        }
+    return best;
+}
+std::vector<double> lhs_maximin(int ns, int nx, Xoshiro256Plus& rng) {
+    std::vector<double> best = lhs_classic(ns, nx, rng);
+    double dbest = min_pdist(best, ns, nx);
+    for (int it = 0; it < 4; ++it) {
+        std::vector<double> cand = lhs_classic(ns, nx, rng);
+        const double dm = min_pdist(cand, ns, nx);
+        if (dbest < dm) {
+            dbest = dm;
+            best.swap(cand);
+        }
+    }
+    return best;
+}
+
+// ---- bound-constrained linear-model trust-region optimiser (ask / tell) ---------------
+class BoundCobyla {
+   public:
+    BoundCobyla(const std::vector<double>& x0, const std::vector<double>& lo, const std::vector<double>& hi,
+                double rhobeg, double ftol_rel, int maxfun)
+        : n_(static_cast<int>(x0.size())), lo_(lo), hi_(hi), rho_(rhobeg), ftol_rel_(ftol_rel), maxfun_(maxfun) {
+        V_.assign(n_ + 1, std::vector<double>(n_));
+        F_.assign(n_ + 1, kInf);
+        for (int i = 0; i < n_; ++i) V_[0][i] = std::min(std::max(x0[i], lo_[i]), hi_[i]);
+        pending_ = V_[0];
+        phase_ = INIT;
+        init_idx_ = 0;
+        if (maxfun_ < 1) phase_ = DONE;
+    }
+    bool done() const { return phase_ == DONE; }
+    const std::vector<double>& ask() const { return pending_; }
+    double best_f() const { return fbest_; }
+    const std::vector<double>& best_x() const { return xbest_; }
+    int nfev() const { return nfev_; }
+
+    void tell(double f_raw) {
+        // failed evaluations come back as +inf (algorithm.rs:893-896); keep the linear algebra finite
+        const double f = std::isnan(f_raw) ? kBig : std::min(f_raw, kBig);
+        ++nfev_;
+        bool ftol_hit = false;
+        if (f_raw < fbest_) {   // NaN compares false
+            if (ftol_rel_ > 0.0 && std::isfinite(fbest_) &&
+                std::fabs(f_raw - fbest_) < ftol_rel_ * (std::fabs(f_raw) + std::fabs(fbest_)) * 0.5)
+                ftol_hit = true;
+            fbest_ = f_raw;
+            xbest_ = pending_;
+        } else if (xbest_.empty()) {
+            xbest_ = pending_;
+        }
+        if (phase_ == INIT) {
+            V_[init_idx_] = pending_;
+            F_[init_idx_] = f;
+            ++init_idx_;
+            if (nfev_ >= maxfun_) {
+                phase_ = DONE;
+                return;
+            }
+            if (init_idx_ <= n_) {
+                const int j = init_idx_ - 1;
+                pending_ = V_[0];
+                double step = rho_;
+                if (pending_[j] + step > hi_[j]) step = -step;
+                pending_[j] = std::min(std::max(pending_[j] + step, lo_[j]), hi_[j]);
+                return;
+            }
+            iterate(false);
+            return;
+        }
+        if (ftol_hit || nfev_ >= maxfun_) {
+            phase_ = DONE;
+            return;
+        }
+        if (phase_ == TRUST) {
+            const double actual = F_[0] - f;
+            insert_after_trust(f);
+            if (actual > 0.0 && actual >= 0.1 * predicted_) iterate(false);
+            else after_failure();
+            return;
+        }
+        if (phase_ == GEOM) {
+            V_[jdrop_] = pending_;
+            F_[jdrop_] = f;
+            iterate(true);
+            return;
+        }
+    }
+
+   private:
+    enum Phase { INIT, TRUST, GEOM, DONE };
+    static constexpr double kBig = 1e100;
+    static constexpr double kAlpha = 0.25, kBeta = 2.1, kGamma = 0.5;
+
+    void best_to_front() {
+        int jb = 0;
+        for (int j = 1; j <= n_; ++j)
+            if (F_[j] < F_[jb]) jb = j;
+        if (jb != 0) {
+            std::swap(V_[0], V_[jb]);
+            std::swap(F_[0], F_[jb]);
+        }
+    }
+
+    // simi = inverse of the edge matrix S (columns s_j = V_j - V_0); false if singular
+    bool compute_simi() {
+        const int n = n_;
+        std::vector<double> a(static_cast<size_t>(n) * 2 * n, 0.0);
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < n; ++j) a[static_cast<size_t>(i) * 2 * n + j] = V_[j + 1][i] - V_[0][i];
+            a[static_cast<size_t>(i) * 2 * n + n + i] = 1.0;
+        }
+        for (int c = 0; c < n; ++c) {
+            int piv = c;
+            for (int r = c + 1; r < n; ++r)
+                if (std::fabs(a[static_cast<size_t>(r) * 2 * n + c]) > std::fabs(a[static_cast<size_t>(piv) * 2 * n + c])) piv = r;
+            if (std::fabs(a[static_cast<size_t>(piv) * 2 * n + c]) < 1e-300) return false;
+            if (piv != c)
+                for (int k = 0; k < 2 * n; ++k) std::swap(a[static_cast<size_t>(piv) * 2 * n + k], a[static_cast<size_t>(c) * 2 * n + k]);
+            const double inv = 1.0 / a[static_cast<size_t>(c) * 2 * n + c];
+            for (int k = 0; k < 2 * n; ++k) a[static_cast<size_t>(c) * 2 * n + k] *= inv;
+            for (int r = 0; r < n; ++r) {
+                if (r == c) continue;
+                const double f = a[static_cast<size_t>(r) * 2 * n + c];
+                if (f == 0.0) continue;
+                for (int k = 0; k < 2 * n; ++k) a[static_cast<size_t>(r) * 2 * n + k] -= f * a[static_cast<size_t>(c) * 2 * n + k];
+            }
+        }
+        simi_.assign(static_cast<size_t>(n) * n, 0.0);
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) simi_[static_cast<size_t>(j) * n + i] = a[static_cast<size_t>(j) * 2 * n + n + i];
+        sigma_.assign(n, 0.0);
+        eta_.assign(n, 0.0);
+        acceptable_ = true;
+        for (int j = 0; j < n; ++j) {
+            double rs = 0.0, es = 0.0;
+            for (int i = 0; i < n; ++i) {
+                rs += simi_[static_cast<size_t>(j) * n + i] * simi_[static_cast<size_t>(j) * n + i];
+                const double e = V_[j + 1][i] - V_[0][i];
+                es += e * e;
+            }
+            sigma_[j] = 1.0 / std::sqrt(rs);
+            eta_[j] = std::sqrt(es);
+            if (sigma_[j] < kAlpha * rho_ || eta_[j] > kBeta * rho_) acceptable_ = false;
+        }
+        return true;
+    }
+
+    void gradient() {
+        g_.assign(n_, 0.0);
+        for (int j = 0; j < n_; ++j) {
+            const double df = F_[j + 1] - F_[0];
+            for (int i = 0; i < n_; ++i) g_[i] += simi_[static_cast<size_t>(j) * n_ + i] * df;
+        }
+    }
+
+    // argmin g.d  s.t. |d| <= rho, lo <= V0 + d <= hi  : d = clip(-t g) with |d| = rho
+    double trust_step(std::vector<double>& d) const {
+        const int n = n_;
+        std::vector<double> a(n), b(n);
+        for (int i = 0; i < n; ++i) {
+            a[i] = lo_[i] - V_[0][i];
+            b[i] = hi_[i] - V_[0][i];
+        }
+        auto eval = [&](double t, std::vector<double>& out) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) {
+                double v = -t * g_[i];
+                v = std::min(std::max(v, a[i]), b[i]);
+                out[i] = v;
+                s += v * v;
+            }
+            return std::sqrt(s);
+        };
+        d.assign(n, 0.0);
+        double gmax = 0.0;
+        for (int i = 0; i < n; ++i) gmax = std::max(gmax, std::fabs(g_[i]));
+        if (gmax == 0.0 || !std::isfinite(gmax)) return 0.0;
+        // corner reached when t -> inf
+        std::vector<double> dinf(n);
+        for (int i = 0; i < n; ++i) dinf[i] = g_[i] < 0.0 ? b[i] : (g_[i] > 0.0 ? a[i] : 0.0);
+        double ninf = 0.0;
+        for (double v : dinf) ninf += v * v;
+        ninf = std::sqrt(ninf);
+        if (ninf <= rho_) {
+            d = dinf;
+            return ninf;
+        }
+        double tlo = 0.0, thi = rho_ / gmax;
+        while (eval(thi, d) < rho_) thi *= 2.0;
+        for (int it = 0; it < 200; ++it) {
+            const double tm = 0.5 * (tlo + thi);
+            if (eval(tm, d) < rho_) tlo = tm;
+            else thi = tm;
+            if (thi - tlo <= 1e-15 * thi) break;
+        }
+        return eval(thi, d);
+    }
+
+    void reinit_simplex() {
+        // degenerate simplex: rebuild around the best vertex with the current radius
+        best_to_front();
+        phase_ = INIT;
+        init_idx_ = 1;
+        pending_ = V_[0];
+        double step = rho_;
+        if (pending_[0] + step > hi_[0]) step = -step;
+        pending_[0] = std::min(std::max(pending_[0] + step, lo_[0]), hi_[0]);
+    }
+
+    void iterate(bool force_trust) {
+        for (;;) {
+            best_to_front();
+            if (!compute_simi()) {
+                reinit_simplex();
+                return;
+            }
+            if (force_trust || acceptable_) {
+                gradient();
+                std::vector<double> d;
+                const double dn = trust_step(d);
+                if (dn >= 0.5 * rho_) {
+                    predicted_ = 0.0;
+                    for (int i = 0; i < n_; ++i) predicted_ -= g_[i] * d[i];
+                    d_ = d;
+                    pending_ = V_[0];
+                    for (int i = 0; i < n_; ++i) pending_[i] = std::min(std::max(pending_[i] + d[i], lo_[i]), hi_[i]);
+                    phase_ = TRUST;
+                    return;
+                }
+                // step too short to be worth an evaluation
+                if (!acceptable_) {
+                    geometry_step();
+                    return;
+                }
+                if (!reduce_rho()) return;
+                force_trust = false;
+                continue;
+            }
+            geometry_step();
+            return;
+        }
+    }
+
+    void after_failure() {
+        best_to_front();
+        if (!compute_simi()) {
+            reinit_simplex();
+            return;
+        }
+        if (!acceptable_) {
+            geometry_step();
+            return;
+        }
+        if (!reduce_rho()) return;
+        iterate(false);
+    }
+
+    bool reduce_rho() {
+        if (rho_ <= rhoend_) {
+            phase_ = DONE;
+            return false;
+        }
+        rho_ *= 0.5;
+        if (rho_ <= 1.5 * rhoend_) rho_ = rhoend_;
+        return true;
+    }
+
+    // V_/F_ are ordered (best first) and simi_ is current
+    void geometry_step() {
+        int jd = -1;
+        double worst = kBeta * rho_;
+        for (int j = 0; j < n_; ++j)
+            if (eta_[j] > worst) {
+                worst = eta_[j];
+                jd = j;
+            }
+        if (jd < 0) {
+            double smin = kInf;
+            for (int j = 0; j < n_; ++j)
+                if (sigma_[j] < smin) {
+                    smin = sigma_[j];
+                    jd = j;
+                }
+        }
+        gradient();
+        std::vector<double> u(n_);
+        for (int i = 0; i < n_; ++i) u[i] = simi_[static_cast<size_t>(jd) * n_ + i] * sigma_[jd];   // unit normal
+        double gu = 0.0;
+        for (int i = 0; i < n_; ++i) gu += g_[i] * u[i];
+        double sgn = (gu > 0.0) ? -1.0 : 1.0;
+        auto make = [&](double s, std::vector<double>& out) {
+            double len = 0.0;
+            out = V_[0];
+            for (int i = 0; i < n_; ++i) {
+                const double t = std::min(std::max(out[i] + s * kGamma * rho_ * u[i], lo_[i]), hi_[i]);
+                len += (t - out[i]) * (t - out[i]);
+                out[i] = t;
+            }
+            return std::sqrt(len);
+        };
+        std::vector<double> c1, c2;
+        const double l1 = make(sgn, c1);
+        if (l1 < 0.5 * kGamma * rho_) {
+            const double l2 = make(-sgn, c2);
+            if (l2 > l1) c1 = c2;
+        }
+        pending_ = c1;
+        jdrop_ = jd + 1;
+        phase_ = GEOM;
+    }
+
+    // replace one vertex by the trust-region point (Powell's volume / distance rule)
+    void insert_after_trust(double f) {
+        const int n = n_;
+        const bool improved = f < F_[0];
+        int jd = -1;
+        double best = improved ? 1.0 : 0.0;   // ratio threshold: keep the simplex volume from collapsing
+        for (int j = 0; j < n; ++j) {
+            double t = 0.0;
+            for (int i = 0; i < n; ++i) t += simi_[static_cast<size_t>(j) * n + i] * d_[i];
+            t = std::fabs(t);
+            if (eta_[j] > kBeta * rho_) t *= eta_[j] / rho_;
+            if (t > best) {
+                best = t;
+                jd = j;
+            }
+        }
+        if (jd < 0) {
+            if (!improved) return;      // the point would flatten the simplex and is not better: drop it
+            // better point but every replacement shrinks the volume: drop the worst vertex
+            double fw = -kInf;
+            for (int j = 0; j < n; ++j)
+                if (F_[j + 1] > fw) {
+                    fw = F_[j + 1];
+                    jd = j;
+                }
+        }
+        V_[jd + 1] = pending_;
+        F_[jd + 1] = f;
+    }
+
+    int n_;
+    std::vector<double> lo_, hi_;
+    double rho_, rhoend_ = 1e-8, ftol_rel_;
+    int maxfun_, nfev_ = 0;
+    std::vector<std::vector<double>> V_;
+    std::vector<double> F_, simi_, sigma_, eta_, g_, d_, pending_, xbest_;
+    bool acceptable_ = false;
+    double predicted_ = 0.0, fbest_ = kInf;
+    int init_idx_ = 0, jdrop_ = 0;
+    Phase phase_;
+};
+
+void normalize_cols(const double* x, int n, int d, std::vector<double>& xn, std::vector<double>& mean,
+                    std::vector<double>& sd) {
+    // gp/src/utils.rs:45-54: mean, std with ddof = 1, zero std -> 1
+    xn.assign(static_cast<size_t>(n) * d, 0.0);
+    mean.assign(d, 0.0);
+    sd.assign(d, 1.0);
+    for (int j = 0; j < d; ++j) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += x[static_cast<size_t>(i) * d + j];
+        const double m = s / n;
+        double v = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double t = x[static_cast<size_t>(i) * d + j] - m;
+            v += t * t;
+        }
+        double st = (n > 1) ? std::sqrt(v / (n - 1)) : 0.0;
+        if (st == 0.0 || std::isnan(st)) st = 1.0;
+        mean[j] = m;
+        sd[j] = st;
+        for (int i = 0; i < n; ++i) xn[static_cast<size_t>(i) * d + j] = (x[static_cast<size_t>(i) * d + j] - m) / st;
+    }
+}
+
+}  // namespace
+
+struct egx_gp_model {
+    egx_gp_ctx* ctx = nullptr;
+    int n = 0, d = 0, h = 0, p = 0;
+    std::vector<double> theta, x_mean, x_std, w_star;
+    double y_mean = 0.0, y_std = 1.0, likelihood = NAN, sigma2 = NAN;
+    long long n_evals = 0;
+};
+
+// Stand-alone access to the optimiser (host only, no GPU): used by the CPU tests and by
+// callers that want the reference's `optimize_params` (optimization.rs:122-169) semantics.
+extern "C" int egx_bound_cobyla_minimize(egx_objective_fn f, void* user, int n, const double* x0, const double* lo,
+                                         const double* hi, double rhobeg, double ftol_rel, int maxeval,
+                                         double* x_opt, double* f_opt, int* n_evals) {
+    if (!f || !x0 || !lo || !hi || n < 1 || !x_opt || !f_opt) return EGX_INVALID_VALUE;
+    BoundCobyla opt(std::vector<double>(x0, x0 + n), std::vector<double>(lo, lo + n), std::vector<double>(hi, hi + n),
+                    rhobeg, ftol_rel, maxeval);
+    while (!opt.done()) {
+        const std::vector<double>& z = opt.ask();
+        double v = f(z.data(), n, user);
+        if (std::isnan(v)) v = kInf;
+        opt.tell(v);
+    }
+    *f_opt = opt.best_f();
+    if (opt.best_x().empty()) std::memcpy(x_opt, x0, sizeof(double) * n);
+    else std::memcpy(x_opt, opt.best_x().data(), sizeof(double) * n);
+    if (n_evals) *n_evals = opt.nfev();
+    return EGX_OK;
+}
+
+// prepare_multistart seeds (optimization.rs:26-71): (n_start + 1) x dim log10 starts
+extern "C" int egx_prepare_multistart(int n_start, const double* theta0, const double* bounds, int dim,
+                                      unsigned long long seed, double* starts_out) {
+    if (!theta0 || !bounds || dim < 1 || n_start < 0 || !starts_out) return EGX_INVALID_VALUE;
+    for (int i = 0; i < dim; ++i) starts_out[i] = std::log10(theta0[i]);
+    Xoshiro256Plus rng(seed);
+    if (n_start == 1) {
+        for (int i = 0; i < dim; ++i) {
+            const double a = std::log10(bounds[2 * i]), b = std::log10(bounds[2 * i + 1]);
+            starts_out[dim + i] = a + (b - a) * rng.uniform();
+        }
+    } else if (n_start > 1) {
+        std::vector<double> pts = lhs_maximin(n_start, dim, rng);
+        for (int s = 0; s < n_start; ++s)
+            for (int i = 0; i < dim; ++i) {
+                const double a = std::log10(bounds[2 * i]), b = std::log10(bounds[2 * i + 1]);
+                starts_out[static_cast<size_t>(s + 1) * dim + i] = a + (b - a) * pts[static_cast<size_t>(s) * dim + i];
+            }
+    }
+    return EGX_OK;
+}
+
+extern "C" void egx_gp_params_default(egx_gp_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->corr = EGX_CORR_SQUARED_EXPONENTIAL;
+    p->mean = EGX_MEAN_CONSTANT;
+    p->theta_tuning = EGX_THETA_FULL;
+    p->n_start = 10;                       // GP_OPTIM_N_START
+    p->max_eval = 1000;                    // GP_COBYLA_MAX_EVAL
+    p->nugget = 100.0 * 2.220446049250313e-16;
+    p->seed = 42;
+    p->cobyla_rhobeg = 0.5;
+    p->cobyla_ftol_rel = 1e-4;
+}
+
+extern "C" void egx_gp_model_destroy(egx_gp_model* m) {
+    if (!m) return;
+    if (m->ctx) egx_gp_destroy(m->ctx);
+    delete m;
+}
+
+extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int d, const double* y,
+                          egx_gp_model** out) {
+    if (!out) return EGX_INVALID_VALUE;
+    *out = nullptr;
+    if (!prm || !x || !y || n < 1 || d < 1) {
+        egx_set_error("egx_gp_fit: invalid argument");
+        return EGX_INVALID_VALUE;
+    }
+    const bool kpls = prm->w_star != nullptr;
+    if (kpls && (prm->kpls_dim < 1 || prm->kpls_dim > d)) {
+        // algorithm.rs:798-807
+        egx_set_error("Dimension reduction %d should be smaller than actual training input dimensions %d",
+                      prm->kpls_dim, d);
+        return EGX_INVALID_VALUE;
+    }
+    const int h = kpls ? prm->kpls_dim : d;
+
+    // theta0 (algorithm.rs:828-838)
+    static const double kDefaultInit = 0.1;
+    std::vector<double> theta0(h);
+    if (prm->theta_init == nullptr || prm->n_theta_init == 0) {
+        std::fill(theta0.begin(), theta0.end(), kDefaultInit);
+    } else if (prm->n_theta_init == 1) {
+        std::fill(theta0.begin(), theta0.end(), prm->theta_init[0]);
+    } else if (prm->n_theta_init == h) {
+        theta0.assign(prm->theta_init, prm->theta_init + h);
+    } else {
+        egx_set_error("Initial guess for theta should be either 1-dim or dim of xtrain (w_star.ncols()), got %d",
+                      prm->n_theta_init);
+        return EGX_INVALID_VALUE;
+    }
+
+    std::unique_ptr<egx_gp_model, void (*)(egx_gp_model*)> m(new egx_gp_model(), egx_gp_model_destroy);
+    m->n = n;
+    m->d = d;
+    m->h = h;
+    std::vector<double> xn, yn, ym, ys;
+    normalize_cols(x, n, d, xn, m->x_mean, m->x_std);
+    normalize_cols(y, n, 1, yn, ym, ys);
+    m->y_mean = ym[0];
+    m->y_std = ys[0];
+    if (kpls) m->w_star.assign(prm->w_star, prm->w_star + static_cast<size_t>(d) * h);
+    else {
+        m->w_star.assign(static_cast<size_t>(d) * d, 0.0);
+        for (int j = 0; j < d; ++j) m->w_star[static_cast<size_t>(j) * d + j] = 1.0;
+    }
+    int st = egx_gp_create(&m->ctx, prm->device, prm->corr, prm->mean, xn.data(), n, d, yn.data(), m->x_mean.data(),
+                           m->x_std.data(), m->y_mean, m->y_std, m->w_star.data(), h, prm->nugget);
+    if (st != EGX_OK) return st;
+    egx_gp_dims(m->ctx, nullptr, nullptr, nullptr, &m->p);
+
+    std::vector<double> theta_opt = theta0;
+    if (prm->theta_tuning != EGX_THETA_FIXED) {
+        // active set and bounds (algorithm.rs:815-827, 899-920)
+        std::vector<int> active;
+        if (prm->theta_tuning == EGX_THETA_PARTIAL) {
+            for (int i = 0; i < prm->n_active; ++i) {
+                if (prm->active[i] < 0 || prm->active[i] >= h) {
+                    egx_set_error("active theta component %d out of range", prm->active[i]);
+                    return EGX_INVALID_VALUE;
+                }
+                active.push_back(prm->active[i]);
+            }
+        } else {
+            for (int i = 0; i < h; ++i) active.push_back(i);
+        }
+        std::vector<double> blo(h, 1e-2), bhi(h, 1e1);     // ThetaTuning::DEFAULT_BOUNDS
+        if (prm->theta_bounds != nullptr && prm->n_theta_bounds > 0) {
+            if (prm->n_theta_bounds == 1) {
+                std::fill(blo.begin(), blo.end(), prm->theta_bounds[0]);
+                std::fill(bhi.begin(), bhi.end(), prm->theta_bounds[1]);
+            } else if (prm->n_theta_bounds == h) {
+                for (int i = 0; i < h; ++i) {
+                    blo[i] = prm->theta_bounds[2 * i];
+                    bhi[i] = prm->theta_bounds[2 * i + 1];
+                }
+            } else {
+                egx_set_error("Bounds for theta should be either 1-dim or dim of xtrain (%d), got %d", h,
+                              prm->n_theta_bounds);
+                return EGX_INVALID_VALUE;
+            }
+        }
+        const int na = static_cast<int>(active.size());
+        if (na > 0) {
+            std::vector<double> lo(na), hi(na), z0(na);
+            for (int i = 0; i < na; ++i) {
+                lo[i] = std::log10(blo[active[i]]);
+                hi[i] = std::log10(bhi[active[i]]);
+                z0[i] = std::log10(theta0[active[i]]);
+            }
+            // prepare_multistart (optimization.rs:26-71)
+            const int n_start = std::max(prm->n_start, 0);
+            std::vector<std::vector<double>> starts;
+            starts.push_back(z0);
+            Xoshiro256Plus rng(prm->seed);
+            if (n_start == 1) {
+                std::vector<double> v(na);
+                for (int i = 0; i < na; ++i) v[i] = lo[i] + (hi[i] - lo[i]) * rng.uniform();
+                starts.push_back(v);
+            } else if (n_start > 1) {
+                std::vector<double> pts = lhs_maximin(n_start, na, rng);
+                for (int s = 0; s < n_start; ++s) {
+                    std::vector<double> v(na);
+                    for (int i = 0; i < na; ++i) v[i] = lo[i] + (hi[i] - lo[i]) * pts[static_cast<size_t>(s) * na + i];
+                    starts.push_back(v);
+                }
+            }
+            const int maxeval = std::min(std::max(10 * na, GP_COBYLA_MIN_EVAL), std::max(prm->max_eval, 1));
+            std::vector<BoundCobyla> chains;
+            chains.reserve(starts.size());
+            for (auto& s0 : starts) chains.emplace_back(s0, lo, hi, prm->cobyla_rhobeg, prm->cobyla_ftol_rel, maxeval);
+
+            std::vector<double> thetas, rlf;
+            std::vector<int> status, who;
+            for (;;) {
+                thetas.clear();
+                who.clear();
+                for (size_t c = 0; c < chains.size(); ++c) {
+                    if (chains[c].done()) continue;
+                    const std::vector<double>& z = chains[c].ask();
+                    std::vector<double> th = theta0;
+                    for (int i = 0; i < na; ++i) th[active[i]] = std::pow(10.0, z[i]);
+                    thetas.insert(thetas.end(), th.begin(), th.end());
+                    who.push_back(static_cast<int>(c));
+                }
+                if (who.empty()) break;
+                const int B = static_cast<int>(who.size());
+                rlf.assign(B, NAN);
+                status.assign(B, 0);
+                st = egx_gp_reduced_likelihood_batch(m->ctx, thetas.data(), B, rlf.data(), status.data());
+                if (st != EGX_OK) return st;
+                m->n_evals += B;
+                for (int b = 0; b < B; ++b) {
+                    // Err(_) -> +inf, algorithm.rs:893-896 ; NaN -> +inf, optimization.rs:157-161
+                    double f = (status[b] == EGX_OK) ? -rlf[b] : kInf;
+                    if (std::isnan(f)) f = kInf;
+                    chains[who[b]].tell(f);
+                }
+            }
+            // reduce (algorithm.rs:942-945): first strictly smaller wins, default theta = 1 (log10 = 0)
+            double fbest = kInf;
+            std::vector<double> zbest(na, 0.0);
+            for (auto& ch : chains)
+                if (ch.best_f() < fbest) {
+                    fbest = ch.best_f();
+                    zbest = ch.best_x();
+                }
+            // algorithm.rs:947-964
+            if (prm->theta_tuning == EGX_THETA_PARTIAL) {
+                theta_opt = theta0;
+                for (int i = 0; i < na; ++i) theta_opt[active[i]] = std::pow(10.0, zbest[i]);
+            } else {
+                for (int i = 0; i < na; ++i) theta_opt[i] = std::pow(10.0, zbest[i]);
+            }
+        }
+    }
+
+    double rlf = NAN, s2 = NAN;
+    st = egx_gp_finalize(m->ctx, theta_opt.data(), &rlf, &s2, nullptr, nullptr, nullptr, nullptr);
+    m->n_evals += 1;
+    if (st != EGX_OK) return st;        // `?` at algorithm.rs:967-968
+    m->theta = theta_opt;
+    m->likelihood = rlf;
+    m->sigma2 = s2;
+    *out = m.release();
+    return EGX_OK;
+}
+
+extern "C" int egx_gp_model_dims(const egx_gp_model* m, int* n, int* d, int* h, int* p) {
+    if (!m) return EGX_INVALID_VALUE;
+    if (n) *n = m->n;
+    if (d) *d = m->d;
+    if (h) *h = m->h;
+    if (p) *p = m->p;
+    return EGX_OK;
+}
+extern "C" int egx_gp_model_theta(const egx_gp_model* m, double* theta) {
+    if (!m || !theta) return EGX_INVALID_VALUE;
+    std::memcpy(theta, m->theta.data(), sizeof(double) * m->h);
+    return EGX_OK;
+}
+extern "C" double egx_gp_model_variance(const egx_gp_model* m) { return m ? m->sigma2 : NAN; }
+extern "C" double egx_gp_model_likelihood(const egx_gp_model* m) { return m ? m->likelihood : NAN; }
+extern "C" long long egx_gp_model_n_evals(const egx_gp_model* m) { return m ? m->n_evals : 0; }
+extern "C" egx_gp_ctx* egx_gp_model_context(egx_gp_model* m) { return m ? m->ctx : nullptr; }
+
+extern "C" int egx_gp_model_inner_params(egx_gp_model* m, double* beta, double* gamma, double* r_chol, double* ft,
+                                         double* ft_qr_r) {
+    if (!m) return EGX_INVALID_VALUE;
+    // re-run the final evaluation to fetch the requested pieces (the factor stays on the device)
+    double rlf, s2;
+    int st = egx_gp_finalize(m->ctx, m->theta.data(), &rlf, &s2, beta, gamma, ft, ft_qr_r);
+    if (st != EGX_OK) return st;
+    if (r_chol) st = egx_gp_download_chol(m->ctx, r_chol);
+    return st;
+}
+
+extern "C" int egx_gp_model_normalization(const egx_gp_model* m, double* x_mean, double* x_std, double* y_mean,
+                                          double* y_std, double* w_star) {
+    if (!m) return EGX_INVALID_VALUE;
+    if (x_mean) std::memcpy(x_mean, m->x_mean.data(), sizeof(double) * m->d);
+    if (x_std) std::memcpy(x_std, m->x_std.data(), sizeof(double) * m->d);
+    if (y_mean) *y_mean = m->y_mean;
+    if (y_std) *y_std = m->y_std;
+    if (w_star) std::memcpy(w_star, m->w_star.data(), sizeof(double) * m->d * m->h);
+    return EGX_OK;
+}
+
+extern "C" int egx_gp_model_predict(egx_gp_model* m, const double* x, int npts, double* y) {
+    if (!m) return EGX_INVALID_VALUE;
+    return egx_gp_predict(m->ctx, x, npts, y);
+}
+extern "C" int egx_gp_model_predict_var(egx_gp_model* m, const double* x, int npts, double* var) {
+    if (!m) return EGX_INVALID_VALUE;
+    return egx_gp_predict_var(m->ctx, x, npts, var);
+}
+extern "C" int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int npts, double* y, double* var) {
+    if (!m) return EGX_INVALID_VALUE;
+    return egx_gp_predict_valvar(m->ctx, x, npts, y, var);
+}

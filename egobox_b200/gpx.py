@@ -1,0 +1,146 @@
+"""`Gpx` / `GpMix`: the Python surface of python/src/gp_mix.rs:31-496 for the kriging path.
+
+Same builder signature, defaults and return shapes as the PyO3 classes; the model behind
+it is the B200-resident GaussianProcess of ``egobox_b200.gp``.  The mixture-of-experts
+control plane of egobox-moe (GMM clustering, multi-spec cross-validated model selection,
+smooth recombination) is the CALLER of this path and is out of scope (SURVEY.md section 8,
+rows (f)-2): ``n_clusters`` other than 1 and multi-bit ``regr_spec`` / ``corr_spec`` raise
+``NotImplementedError`` instead of silently doing something else."""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+
+from . import gp as _gp
+
+
+class RegressionSpec:            # python/src/types.rs
+    CONSTANT, LINEAR, QUADRATIC, ALL = 1, 2, 4, 7
+
+
+class CorrelationSpec:
+    SQUARED_EXPONENTIAL, ABSOLUTE_EXPONENTIAL, MATERN32, MATERN52, ALL = 1, 2, 4, 8, 15
+
+
+class Recombination:
+    HARD, SMOOTH = 0, 1
+    Hard, Smooth = 0, 1
+
+
+_REGR = {1: _gp.ConstantMean, 2: _gp.LinearMean, 4: _gp.QuadraticMean}
+_CORR = {1: _gp.SquaredExponentialCorr, 2: _gp.AbsoluteExponentialCorr, 4: _gp.Matern32Corr, 8: _gp.Matern52Corr}
+EGO_GP_OPTIM_N_START = 10      # ego/src/solver/egor_config.rs:13
+EGO_GP_OPTIM_MAX_EVAL = 50     # ego/src/solver/egor_config.rs:15
+MOE_GP_MAX_EVAL = 1000         # moe/src/parameters.rs:153 -- what GpMix.fit really runs with (gp_mix.rs:222-231)
+
+
+class GpMix:
+    """Gaussian processes mixture builder (python/src/gp_mix.rs:31-236)."""
+
+    def __init__(self, regr_spec=RegressionSpec.CONSTANT, corr_spec=CorrelationSpec.SQUARED_EXPONENTIAL,
+                 kpls_dim=None, n_clusters=1, recombination=Recombination.HARD, theta_init=None,
+                 theta_bounds=None, n_start=EGO_GP_OPTIM_N_START, max_eval=EGO_GP_OPTIM_MAX_EVAL, seed=None,
+                 w_star=None, device=0):
+        self.regr_spec, self.corr_spec, self.kpls_dim = regr_spec, corr_spec, kpls_dim
+        self.n_clusters, self.recombination = n_clusters, recombination
+        self.theta_init, self.theta_bounds = theta_init, theta_bounds
+        self.n_start, self.max_eval, self.seed = n_start, max_eval, seed
+        self.w_star, self.device = w_star, device
+
+    def fit(self, xt, yt):
+        """gp_mix.rs:140-236: accepts 1-D or 2-D xt, yt must be single-output."""
+        xt = np.asarray(xt, dtype=np.float64)
+        if xt.ndim == 1:
+            xt = xt[:, None]
+        elif xt.ndim != 2:
+            raise ValueError("Bad training input data")           # gp_mix.rs:147-150
+        yt = np.asarray(yt, dtype=np.float64)
+        if yt.ndim == 2:
+            if yt.shape[1] != 1:
+                raise ValueError("Bad training output data")      # gp_mix.rs:157-160
+            yt = yt[:, 0]
+        elif yt.ndim != 1:
+            raise ValueError("Bad training output data")
+        if self.n_clusters != 1:
+            raise NotImplementedError("n_clusters != 1: GMM clustering is egobox-moe's control plane (out of scope)")
+        if self.regr_spec not in _REGR or self.corr_spec not in _CORR:
+            raise NotImplementedError("multi-model selection by cross-validation (moe/src/algorithm.rs:209-347) "
+                                      "is out of scope: pass a single regr_spec / corr_spec")
+        tuning = _gp.ThetaTuning.Full()
+        if self.theta_init is not None:
+            tuning = _gp.ThetaTuning.Full(list(self.theta_init), [_gp.ThetaTuning.DEFAULT_BOUNDS])
+        if self.theta_bounds is not None:
+            tuning = _gp.ThetaTuning.Full(tuning.init, [tuple(b) for b in self.theta_bounds])
+        n_start = self.n_start
+        if n_start < 0:                                            # gp_mix.rs:200-206
+            tuning = _gp.ThetaTuning.Fixed(tuning.init)
+            n_start = 0
+        params = (_gp.GaussianProcess.params(_REGR[self.regr_spec], _CORR[self.corr_spec])
+                  .theta_tuning(tuning).n_start(n_start).max_eval(MOE_GP_MAX_EVAL).device(self.device))
+        if self.kpls_dim is not None:
+            params = params.kpls_dim(self.kpls_dim, self.w_star)
+        return Gpx(params.fit(xt, yt), self)
+
+
+class Gpx:
+    """A trained Gaussian processes mixture with one expert (python/src/gp_mix.rs:242-496)."""
+
+    def __init__(self, model, builder):
+        self._gp = model
+        self._builder = builder
+
+    @staticmethod
+    def builder(regr_spec=RegressionSpec.CONSTANT, corr_spec=CorrelationSpec.SQUARED_EXPONENTIAL, kpls_dim=None,
+                n_clusters=1, recombination=Recombination.HARD, theta_init=None, theta_bounds=None,
+                n_start=EGO_GP_OPTIM_N_START, max_eval=EGO_GP_OPTIM_MAX_EVAL, seed=None, **kw):
+        return GpMix(regr_spec, corr_spec, kpls_dim, n_clusters, recombination, theta_init, theta_bounds,
+                     n_start, max_eval, seed, **kw)
+
+    def predict(self, x):
+        return self._gp.predict(np.asarray(x, dtype=np.float64))
+
+    def predict_var(self, x):
+        return self._gp.predict_var(np.asarray(x, dtype=np.float64))
+
+    def predict_valvar(self, x):
+        return self._gp.predict_valvar(np.asarray(x, dtype=np.float64))
+
+    def predict_gradients(self, x):
+        raise NotImplementedError("batched prediction gradients: SURVEY.md 8(f)-1 (next)")
+
+    def predict_var_gradients(self, x):
+        raise NotImplementedError("batched prediction gradients: SURVEY.md 8(f)-1 (next)")
+
+    def sample(self, x, n_traj):
+        raise NotImplementedError("conditional sampling: SURVEY.md 8(f)-4 (next)")
+
+    def dims(self):
+        return self._gp.dims()
+
+    def training_data(self):
+        x, y = self._gp.training_data
+        return x.copy(), y.copy()
+
+    def thetas(self):
+        return self._gp.theta()[None, :]
+
+    def variances(self):
+        return np.array([self._gp.variance()])
+
+    def likelihoods(self):
+        return np.array([self._gp.likelihood()])
+
+    def gp(self):
+        return self._gp
+
+    def __str__(self):
+        p = self._gp.params_
+        return "Mixture[Hard](%s_%sGP(mean=%s, corr=%s, theta=%s, variance=%s, likelihood=%s))" % (
+            _gp.MEAN_NAMES[p._mean].replace("Mean", ""), _gp.CORR_NAMES[p._corr], _gp.MEAN_NAMES[p._mean],
+            _gp.CORR_NAMES[p._corr], self._gp.theta().tolist(), self._gp.variance(), self._gp.likelihood())
+
+    def __repr__(self):
+        return json.dumps({"recombination": "Hard", "experts": [{
+            "theta": self._gp.theta().tolist(), "likelihood": self._gp.likelihood(),
+            "variance": self._gp.variance()}]})

@@ -150,6 +150,86 @@ int egx_gp_get_profile(egx_gp_ctx* ctx, double* ms, long long* launches);
  * one-CTA-per-theta kernel (tests exercise both on the same inputs). */
 int egx_gp_set_force_blocked(egx_gp_ctx* ctx, int enabled);
 
+
+/* ============================================================================
+ * Host-level model API (C++ host code above the device seam, same library).
+ * Mirrors `GpParams::fit(&Dataset) -> GaussianProcess` and the inherent
+ * accessors / predict* of gp/src/algorithm.rs:242-439, 785-979 so that the
+ * moe `GpSurrogate` wrappers (moe/src/surrogates.rs:147-155) and the PyO3
+ * `Gpx` class (python/src/gp_mix.rs:242-496) can bind it one to one.
+ * ========================================================================== */
+#define EGX_THETA_FIXED   0   /* ThetaTuning::Fixed   gp/src/parameters.rs:17 */
+#define EGX_THETA_FULL    1   /* ThetaTuning::Full    gp/src/parameters.rs:19 */
+#define EGX_THETA_PARTIAL 2   /* ThetaTuning::Partial gp/src/parameters.rs:26 */
+
+/* GpValidParams, gp/src/parameters.rs:90-120.  Use egx_gp_params_default() to
+ * get the reference defaults (theta init 0.1, bounds [1e-2, 10], n_start 10,
+ * max_eval 1000, nugget 100*eps, constant mean, squared exponential). */
+typedef struct egx_gp_params {
+    int corr;                    /* EGX_CORR_*  */
+    int mean;                    /* EGX_MEAN_*  */
+    int theta_tuning;            /* EGX_THETA_* */
+    const double* theta_init;    /* n_theta_init values: 1 (broadcast) or theta dimension */
+    int n_theta_init;
+    const double* theta_bounds;  /* n_theta_bounds (lo, hi) pairs: 1 (broadcast) or theta dimension */
+    int n_theta_bounds;
+    const int* active;           /* EGX_THETA_PARTIAL: optimised component indices */
+    int n_active;
+    int n_start;                 /* multistart count (n_start + 1 chains), algorithm.rs:33 */
+    int max_eval;                /* per-chain budget = clamp(10*dim, 25, max_eval), algorithm.rs:936-937 */
+    double nugget;
+    const double* w_star;        /* optional d x kpls_dim PLS rotations (algorithm.rs:843-855); NULL = identity */
+    int kpls_dim;                /* columns of w_star; ignored when w_star is NULL */
+    int device;                  /* CUDA device ordinal */
+    unsigned long long seed;     /* multistart LHS seed (reference: 42, optimization.rs:60-63) */
+    double cobyla_rhobeg;        /* 0.5   optimization.rs:19 */
+    double cobyla_ftol_rel;      /* 1e-4  optimization.rs:20; <= 0 disables the early stop */
+} egx_gp_params;
+
+typedef struct egx_gp_model egx_gp_model;
+
+void egx_gp_params_default(egx_gp_params* p);
+
+/* impl Fit for GpValidParams::fit, gp/src/algorithm.rs:791-979.
+ * x: n x d raw inputs, y: n raw outputs.  The n_start+1 COBYLA chains are
+ * advanced in lock step so that every optimiser iteration is one
+ * egx_gp_reduced_likelihood_batch call (the rayon fan-out of :928-945). */
+int egx_gp_fit(const egx_gp_params* params, const double* x, int n, int d, const double* y,
+               egx_gp_model** out);
+void egx_gp_model_destroy(egx_gp_model* m);
+
+/* accessors: theta() :413, variance() :418, likelihood() :423, dims() :437 */
+int egx_gp_model_dims(const egx_gp_model* m, int* n, int* d, int* h, int* p);
+int egx_gp_model_theta(const egx_gp_model* m, double* theta /* h */);
+double egx_gp_model_variance(const egx_gp_model* m);
+double egx_gp_model_likelihood(const egx_gp_model* m);
+long long egx_gp_model_n_evals(const egx_gp_model* m);   /* likelihood evaluations spent by fit */
+/* GpInnerParams (algorithm.rs:47-60) and normalisation data for serialisation; any pointer may be NULL */
+int egx_gp_model_inner_params(egx_gp_model* m, double* beta, double* gamma, double* r_chol, double* ft,
+                              double* ft_qr_r);
+int egx_gp_model_normalization(const egx_gp_model* m, double* x_mean, double* x_std, double* y_mean,
+                               double* y_std, double* w_star /* d x h */);
+/* the device context of a fitted model (owned by the model) */
+egx_gp_ctx* egx_gp_model_context(egx_gp_model* m);
+
+/* Host-only utilities (no GPU needed).
+ * egx_bound_cobyla_minimize: the derivative-free optimiser `optimize_params` runs per
+ * chain (gp/src/optimization.rs:122-169): minimise f over the box [lo, hi] from x0 with
+ * initial trust radius rhobeg, NLopt-style ftol_rel stop and an evaluation budget.
+ * egx_prepare_multistart: gp/src/optimization.rs:26-71, (n_start+1) x dim log10 starts
+ * (row 0 = log10 theta0, rows 1.. = maximin LHS in the log10 box, bounds = dim (lo,hi) pairs). */
+typedef double (*egx_objective_fn)(const double* x, int n, void* user);
+int egx_bound_cobyla_minimize(egx_objective_fn f, void* user, int n, const double* x0, const double* lo,
+                              const double* hi, double rhobeg, double ftol_rel, int maxeval,
+                              double* x_opt, double* f_opt, int* n_evals);
+int egx_prepare_multistart(int n_start, const double* theta0, const double* bounds, int dim,
+                           unsigned long long seed, double* starts_out);
+
+/* predict :253, predict_var :267, predict_valvar :282 (raw x, m x d) */
+int egx_gp_model_predict(egx_gp_model* m, const double* x, int npts, double* y);
+int egx_gp_model_predict_var(egx_gp_model* m, const double* x, int npts, double* var);
+int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int npts, double* y, double* var);
+
 #ifdef __cplusplus
 }
 #endif

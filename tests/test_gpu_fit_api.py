@@ -1,0 +1,94 @@
+"""-m gpu: the reference-facing API (Gpx / GaussianProcess) end to end on the GPU, with the
+known answers of python/egobox/tests/test_gpmix.py and doc/Gpx_Tutorial.ipynb."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def krg5(golden_dir):
+    with open(os.path.join(golden_dir, "gpx_tutorial_kriging5.json")) as f:
+        return json.load(f)
+
+
+def test_gpx_kriging(krg5):
+    """test_gpmix.py:30-53 + Gpx_Tutorial.ipynb:165-167 (optimised theta, variance, likelihood)."""
+    import egobox_b200 as egx
+    xt = np.array([[0.0, 1.0, 2.0, 3.0, 4.0]]).T
+    yt = np.array([[0.0, 1.0, 1.5, 0.9, 1.0]]).T
+    gpx = egx.Gpx.builder().fit(xt, yt)
+    assert gpx.predict(np.array([[1.0]])).item() == pytest.approx(1.0, abs=1e-7)
+    assert gpx.predict_var(np.array([[1.0]])).item() == pytest.approx(0.0, abs=1e-7)
+    assert gpx.predict(np.array([[1.1]])).item() == pytest.approx(1.1163, abs=1e-3)
+    assert gpx.predict_var(np.array([[1.1]])).item() == pytest.approx(0.0, abs=1e-3)
+    assert gpx.thetas().shape == (1, 1)
+    assert gpx.thetas().item() == pytest.approx(krg5["theta"], rel=5e-3)
+    assert gpx.likelihoods().item() == pytest.approx(krg5["likelihood"], rel=1e-6)
+    assert gpx.variances().item() == pytest.approx(krg5["variance"], rel=5e-3)
+    # test_training_params
+    assert gpx.dims() == (1, 1)
+    xd, yd = gpx.training_data()
+    np.testing.assert_array_equal(xd, xt)
+    np.testing.assert_array_equal(yd, yt[:, 0])
+
+
+def test_gpx_1d_training_data_and_fixed_theta():
+    """test_gpmix.py:130-142."""
+    import egobox_b200 as egx
+    xt1 = np.array([0.0, 1.0, 2.0, 3.0, 4.0])
+    yt1 = np.array([0.0, 1.0, 1.5, 0.9, 1.0])
+    gpx = egx.Gpx.builder().fit(xt1, yt1)
+    assert gpx.thetas().item() != 0.314
+    gpx = egx.Gpx.builder(n_start=-1, theta_init=[0.314]).fit(xt1, yt1)
+    assert gpx.thetas().item() == 0.314
+
+
+def test_gpx_multi_outputs_exception():
+    """test_gpmix.py:122-128."""
+    import egobox_b200 as egx
+    xt = np.array([[0.0, 1.0, 2.0, 3.0, 4.0]]).T
+    yt = np.array([[0.0, 10.0], [1.0, -3.0], [1.5, 1.5], [0.9, 1.0], [1.0, 0.0]])
+    with pytest.raises(BaseException):
+        egx.Gpx.builder().fit(xt, yt)
+
+
+def test_fit_matches_oracle_at_found_theta():
+    """Whatever theta the multistart finds, the fitted state must be the oracle's at that theta,
+    and the found likelihood must not be worse than the oracle's own multistart optimum."""
+    import egobox_b200 as egx
+    rng = np.random.default_rng(3)
+    x = rng.random((120, 3))
+    y = np.sum(np.sin(4 * x) * np.array([1.0, 0.5, 2.0]), axis=1)
+    gp = egx.GaussianProcess.params(egx.ConstantMean, egx.Matern52Corr).fit(x, y)
+    th = gp.theta()
+    ogp = O.fit(x, y, corr=O.MATERN52, mean=O.CONSTANT, theta_init=th, fixed=True)
+    assert gp.likelihood() == pytest.approx(ogp.likelihood, rel=1e-9)
+    assert gp.variance() == pytest.approx(ogp.inner.sigma2, rel=1e-8)
+    xs = rng.random((50, 3))
+    np.testing.assert_allclose(gp.predict(xs), ogp.predict(xs), rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(gp.predict_var(xs), ogp.predict_var(xs), rtol=1e-6, atol=1e-9 * ogp.inner.sigma2)
+    ofull = O.fit(x, y, corr=O.MATERN52, mean=O.CONSTANT)
+    assert gp.likelihood() >= ofull.likelihood - 1e-3 * abs(ofull.likelihood)
+    assert 30 <= gp.n_evals() <= 11 * 30 + 1       # maxeval = clamp(10*3, 25, 1000) per chain
+    ip = gp.inner_params()
+    np.testing.assert_allclose(ip["r_chol"], ogp.inner.r_chol, rtol=0, atol=1e-11)
+
+
+def test_kriging_alias_and_errors():
+    import egobox_b200 as egx
+    x = np.linspace(0, 1, 9)[:, None]
+    y = np.sin(5 * x[:, 0])
+    gp = egx.Kriging.params().fit(x, y)
+    assert "SquaredExponential" in str(gp)
+    with pytest.raises(egx.InvalidValueError):
+        egx.GaussianProcess.params().kpls_dim(3, w_star=np.ones((1, 3))).fit(x, y)
+    # duplicated points + zero nugget: the final evaluation propagates LinalgError (algorithm.rs:967-968)
+    xd = np.array([[0.0], [0.0], [1.0]])
+    with pytest.raises(egx.LinalgError):
+        egx.GaussianProcess.params().theta_tuning(egx.ThetaTuning.Fixed([1.0])).nugget(0.0).fit(xd, [0.0, 0.0, 1.0])

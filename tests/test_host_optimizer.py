@@ -1,0 +1,87 @@
+"""CPU tests of the host-side fit machinery (C++ in libegobox_gpu.so, no GPU needed):
+the bound-constrained COBYLA-family optimiser and the multistart seeds
+(gp/src/optimization.rs:26-71, 122-169).  The kriging objective here is the ORACLE's
+(checker), so these tests also pin the optimiser on the reference's published optimum."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from egobox_b200 import gp as G
+from oracle import gp_oracle as O
+
+
+def test_quadratic_in_box():
+    f = lambda z: (z[0] - 0.3) ** 2 + 2.0 * (z[1] + 0.2) ** 2 + 1.0
+    x, fv, nev = G.bound_cobyla_minimize(f, [-0.9, 0.9], [(-1, 1), (-1, 1)], ftol_rel=0.0, maxeval=200)
+    assert fv == pytest.approx(1.0, abs=1e-8)
+    np.testing.assert_allclose(x, [0.3, -0.2], atol=1e-4)
+    assert nev <= 200
+
+
+def test_active_bound():
+    f = lambda z: (z[0] - 2.0) ** 2 + (z[1] - 0.5) ** 2
+    x, fv, _ = G.bound_cobyla_minimize(f, [0.0, 0.0], [(-1, 1), (-1, 1)], ftol_rel=0.0, maxeval=150)
+    np.testing.assert_allclose(x, [1.0, 0.5], atol=1e-4)
+    assert fv == pytest.approx(1.0, abs=1e-6)
+
+
+def test_budget_and_inf_values():
+    calls = []
+
+    def f(z):
+        calls.append(z.copy())
+        return math.inf if z[0] < -0.5 else (z[0] - 0.1) ** 2 + (z[1] + 0.4) ** 2 + (z[2] - 0.2) ** 2
+
+    x, fv, nev = G.bound_cobyla_minimize(f, [-0.9, 0.0, 0.0], [(-1, 1)] * 3, ftol_rel=0.0, maxeval=60)
+    assert nev == len(calls) <= 60
+    assert all(np.all(np.abs(c) <= 1.0 + 1e-15) for c in calls)     # never leaves the box
+    assert fv < 1e-3
+
+
+def test_rosenbrock_5d_budget():
+    def f(z):
+        return float(np.sum(100.0 * (z[1:] - z[:-1] ** 2) ** 2 + (1 - z[:-1]) ** 2))
+    # linear-model methods crawl along the Rosenbrock valley: hold ours to the same league as
+    # scipy's COBYLA (PRIMA) with the same radius and budget
+    from scipy.optimize import minimize
+    x, fv, nev = G.bound_cobyla_minimize(f, np.zeros(5), [(-2, 2)] * 5, ftol_rel=0.0, maxeval=500)
+    ref = minimize(f, np.zeros(5), method="COBYLA", bounds=[(-2, 2)] * 5,
+                   options=dict(rhobeg=0.5, maxiter=500, tol=1e-10))
+    assert nev == 500
+    assert fv < 2.5 * ref.fun
+
+
+def test_prepare_multistart_layout():
+    s = G.prepare_multistart(10, [0.1, 0.1, 0.1], [(1e-2, 10.0)])
+    assert s.shape == (11, 3)
+    np.testing.assert_allclose(s[0], -1.0)
+    assert np.all(s[1:] >= -2.0) and np.all(s[1:] <= 1.0)
+    # LHS: exactly one point per stratum in every column
+    for j in range(3):
+        strata = np.floor((s[1:, j] + 2.0) / 3.0 * 10).astype(int)
+        assert sorted(strata) == list(range(10))
+    np.testing.assert_array_equal(s, G.prepare_multistart(10, [0.1, 0.1, 0.1], [(1e-2, 10.0)]))   # seeded
+
+
+def test_kriging5_optimum_with_reference_settings(golden_dir):
+    """doc/Gpx_Tutorial.ipynb:165-167: theta* = 1.83209405, rlf = 0.5781740714613353."""
+    with open(os.path.join(golden_dir, "gpx_tutorial_kriging5.json")) as f:
+        k = json.load(f)
+    x = np.array(k["xt"])[:, None]
+    y = np.array(k["yt"])
+    xn, _, _ = O.normalize(x)
+    yn, _, ys = O.normalize(y.reshape(-1, 1))
+    fx = O.mean_value(O.CONSTANT, xn)
+    obj = lambda z: O.objective(O.SQEXP, xn, fx, yn, float(ys[0]), 10.0 ** z, np.eye(1))
+    starts = G.prepare_multistart(10, [0.1], [(1e-2, 10.0)])
+    best = (math.inf, None)
+    for s in starts:
+        z, fv, nev = G.bound_cobyla_minimize(obj, s, [(-2.0, 1.0)], rhobeg=0.5, ftol_rel=1e-4, maxeval=25)
+        assert nev <= 25
+        if fv < best[0]:
+            best = (fv, z)
+    assert -best[0] == pytest.approx(k["likelihood"], rel=1e-6)
+    assert 10.0 ** best[1][0] == pytest.approx(k["theta"], rel=5e-3)
