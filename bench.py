@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native kriging hot path.
+
+Metric (BASELINE.json): GP fit+predict throughput in points/s at n=8192, d=10.
+Workload (BASELINE.json configs[1]): Kriging Matern-5/2, n=8192, d=10, fp64, constant mean;
+one STEP = one fit with the reference's default optimisation budget (n_start=10 ->
+11 chains x clamp(10*d, 25, max_eval)=100 likelihood evaluations + 1 final = 1101
+evaluations, gp/src/algorithm.rs:33-37, 936-937) followed by predict_var on m=100000 points.
+    points/s = m / (t_fit + t_predict_var)
+
+ value : the same work with the training set, the theta sequence and x* already resident
+         in HBM (C ABI device-pointer entry points), CUDA-event timed.
+ e2e   : the reference-facing call a user makes -- GaussianProcess.params(..).fit(x, y)
+         then predict_var(x*) -- with host buffers (x* pinned), H2D/D2H inside the region.
+ N > 1 : one process per GPU (torchrun), weak scaling: every rank fits and predicts its own
+         n=8192 expert (the MoE expert loop moe/src/algorithm.rs:167-177 sharded over GPUs);
+         the only collective is the final NCCL all-gather of (likelihood, theta) per expert.
+ --impl reference : the CPU path (oracle restatement: C/OpenMP correlation + LAPACK through
+         scipy, all host threads) on a bounded sample of the same step, extrapolated.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CORR_MATERN52, MEAN_CONSTANT = 3, 0
+
+
+# ----------------------------------------------------------------------------- workload
+def lhs(n, d, seed):
+    rng = np.random.default_rng(seed)
+    u = rng.random((n, d))
+    pts = (np.arange(n)[:, None] + u) / n
+    for j in range(d):
+        pts[:, j] = pts[rng.permutation(n), j]
+    return pts
+
+
+def rosenbrock(x):
+    z = 4.0 * x - 2.0
+    return np.sum(100.0 * (z[:, 1:] - z[:, :-1] ** 2) ** 2 + (1.0 - z[:, :-1]) ** 2, axis=1)
+
+
+def make_workload(n, d, m, evals, rank):
+    x = lhs(n, d, 42 + 1000 * rank)
+    y = rosenbrock(x)
+    xs = np.random.default_rng(43 + 1000 * rank).random((m, d))
+    # theta sequence: log10-uniform LHS in the default bounds [1e-2, 10] (parameters.rs:51)
+    thetas = 10.0 ** (-2.0 + 3.0 * lhs(evals, d, 44))
+    return x, y, xs, thetas
+
+
+def normalize(a):
+    mean = a.mean(axis=0)
+    std = a.std(axis=0, ddof=1)
+    std = np.where(std == 0.0, 1.0, std)
+    return (a - mean) / std, mean, std
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.3:
+                continue
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smmax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smmax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample(n, d, m, evals, sample_pts=1024):
+    """Bounded sample of one step on the host cores: ONE likelihood evaluation at full n plus
+    predict_valvar on `sample_pts` points, extrapolated to `evals` evaluations and m points."""
+    from oracle import fast, gp_oracle as O
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        blas_threads = None
+    cores = len(os.sched_getaffinity(0))
+    x, y, xs, thetas = make_workload(n, d, sample_pts, 4, 0)
+    xn, xm, xsd = normalize(x)
+    yn, ym, ysd = normalize(y.reshape(-1, 1))
+    fx = O.mean_value(O.CONSTANT, xn)
+    theta = np.full(d, 1.0)
+    t0 = time.perf_counter()
+    rlf, inner = fast.reduced_likelihood(O.MATERN52, xn, fx, yn, float(ysd[0]), theta, np.eye(d))
+    t_eval = time.perf_counter() - t0
+    gp = O.GaussianProcess(corr=O.MATERN52, mean=O.CONSTANT, theta=theta, likelihood=rlf, inner=inner,
+                           w_star=np.eye(d), xt_norm=xn, x_mean=xm, x_std=xsd, yt_norm=yn,
+                           y_mean=float(ym[0]), y_std=float(ysd[0]))
+    t0 = time.perf_counter()
+    fast.predict_valvar(gp, xs, chunk=sample_pts)
+    t_chunk = time.perf_counter() - t0
+    t_fit = evals * t_eval
+    t_pred = (m / sample_pts) * t_chunk
+    return {"value": m / (t_fit + t_pred), "unit": "points/s", "cores": cores, "blas_threads": blas_threads,
+            "kind": "port",
+            "sample": "1 likelihood eval at n=%d (%.2f s, x%d) + predict_var on %d points (%.2f s, x%.1f); "
+                      "oracle port: C/OpenMP correlation + scipy LAPACK" % (n, t_eval, evals, sample_pts, t_chunk,
+                                                                            m / sample_pts),
+            "t_eval_s": t_eval, "t_predict_chunk_s": t_chunk, "rlf": rlf}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, last = [], None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        last = cpu_sample(args.n, args.d, args.m, args.evals)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    val = last["value"]
+    out = {"impl": "reference", "metric": "GP fit+predict throughput (points/s) at n=%d d=%d" % (args.n, args.d),
+           "value": val, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * args.m / val, "sample_wall_ms_per_step": 1e3 * float(np.mean(times)),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args), "cpu_baseline": last,
+           "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "Kriging Matern52 n=%d d=%d fp64 constant mean: fit (%d likelihood evals = 11 chains x 100 "
+                        "+ final) + predict_var on m=%d points" % (args.n, args.d, args.evals, args.m),
+            "n": args.n, "d": args.d, "m": args.m, "likelihood_evals_per_fit": args.evals,
+            "l2": "inputs larger than L2 (R/L workspace %.0f MB, predict chunk %.0f MB vs 126 MB L2)" % (
+                8e-6 * args.n * args.n, 8e-6 * min(args.m, 8192) * args.n),
+            "parallelism": "1 expert per GPU, no data-path collective"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def gemm_algorithmic_flops(n, evals, m, chunk=8192, nb=128, q=2):
+    """Useful flops executed by the K4 GEMM launches of one step (SURVEY 8d figures restated per launch)."""
+    T = -(-n // nb)
+    fl = 0.0
+    for k in range(T - 1):
+        r = max(n - (k + 1) * nb, 0)
+        fl += 2.0 * nb * (r * (r + 1) / 2.0 + q * r)
+    chol = fl * (evals + 1)
+    pred = 0.0
+    for i0 in range(0, m, chunk):
+        mc = min(chunk, m - i0)
+        for k in range(T - 1):
+            pred += 2.0 * nb * mc * max(n - (k + 1) * nb, 0)
+    return chol + pred
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import egobox_b200 as eg
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if eg.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, d, m, E = args.n, args.d, args.m, args.evals
+    x, y, xs, thetas = make_workload(n, d, m, E - 1, rank)
+    xn, xm, xsd = normalize(x)
+    yn, ym, ysd = normalize(y.reshape(-1, 1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value leg: everything resident in HBM --------------------------------
+    ctx = eg.GpContext(xn, yn[:, 0], xm, xsd, float(ym[0]), float(ysd[0]), eg.MATERN52, eg.CONSTANT,
+                       device=local_rank)
+    xs_dev = torch.from_numpy(xs).cuda()
+    y_dev = torch.empty(m, dtype=torch.float64, device="cuda")
+    v_dev = torch.empty(m, dtype=torch.float64, device="cuda")
+    theta_fin = np.full(d, 1.0)
+
+    split = {"fit_ms": 0.0, "predict_ms": 0.0}
+
+    def device_step():
+        ctx.timer_start()
+        status, rlf = ctx.reduced_likelihood_batch(thetas)
+        st, _ = ctx.finalize(theta_fin, want_ft=False)
+        assert st == 0
+        split["fit_ms"] += ctx.timer_stop()
+        ctx.timer_start()
+        ctx.predict_valvar_dev(xs_dev.data_ptr(), m, y_dev.data_ptr(), v_dev.data_ptr())
+        split["predict_ms"] += ctx.timer_stop()
+        return status, rlf
+
+    for _ in range(args.warmup):
+        device_step()
+    ctx.set_profiling(True)
+    ctx.reset_profile()
+    split["fit_ms"] = split["predict_ms"] = 0.0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        status, rlf = device_step()
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    # The kernels run on the context's own stream, which torch events do not see: the step time is
+    # the CUDA-event time measured on THAT stream (egx_gp_timer_*: fit + predict regions, GPU idle
+    # gaps while the host prepares the next launch included).  Host wall time is kept as a check.
+    dev_ms = split["fit_ms"] + split["predict_ms"]
+    wall_ms = (t_wall1 - t_wall0) * 1e3
+    step_ms = dev_ms / args.steps
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    n_fail = int(np.sum(status != 0))
+    launches = sum(v[1] for v in prof.values())
+
+    # ---------------- e2e leg: public API, host buffers ------------------------------------
+    xs_pinned = torch.from_numpy(xs).pin_memory().numpy()
+    x_h, y_h = np.ascontiguousarray(x), np.ascontiguousarray(y)
+
+    def e2e_step():
+        gp = (eg.GaussianProcess.params(eg.ConstantMean, eg.Matern52Corr).n_start(10).max_eval(1000)
+              .cobyla_ftol_rel(0.0).device(local_rank).fit(x_h, y_h))
+        var = gp.predict_var(xs_pinned)
+        nev = gp.n_evals()
+        lik, th = gp.likelihood(), gp.theta()
+        gp.close()
+        return var, nev, lik, th
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(min(args.warmup, 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        var, nev, lik, th = e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    # ---------------- reductions over ranks -------------------------------------------------
+    step_ms_all, e2e_ms_all = step_ms, e2e_ms
+    if world > 1:
+        t = torch.tensor([step_ms, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms_all, e2e_ms_all = float(t[0]), float(t[1])
+        # the one collective of the design: gather (likelihood, theta) of every expert
+        pack = torch.tensor([lik] + list(th), dtype=torch.float64, device="cuda")
+        gathered = [torch.empty_like(pack) for _ in range(world)]
+        dist.all_gather(gathered, pack)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (sustained 1400)"
+        gemm_ms, gemm_launches = prof["syrk_gemm"]
+        flops = gemm_algorithmic_flops(n, E - 1, m) * args.steps
+        achieved = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        sm_clock = clocks.get("sm_mhz") or 1965.0
+        fp64_peak_at_clock = 148 * 64 * 2 * sm_clock * 1e6 / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(
+                "gemm_nt_sub_kernel", {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {"bound": "tensor", "kernel": "gemm_nt_sub_kernel (DMMA fp64 SYRK / TRSM update)",
+                    "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": (achieved / bf16_peak) if achieved else None, "peak_source": peak_src,
+                    "traffic": traffic,
+                    "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
+                    "share_of_step": gemm_ms / (step_ms * args.steps),
+                    "fp64_pipe_peak_tflops_at_sampled_clock": fp64_peak_at_clock,
+                    "frac_of_fp64_pipe": (achieved / fp64_peak_at_clock) if achieved else None,
+                    "note": "fp64 contraction on the DMMA pipe (tcgen05 has no f64 kind); the bf16 figure is the "
+                            "mandated denominator, the fp64-pipe line (148 SM x 64 FMA/clk) is the physical bound"}
+        value = world * m / (step_ms_all * 1e-3)
+        e2e_value = world * m / (e2e_ms_all * 1e-3)
+        out = {"metric": "GP fit+predict throughput (points/s) at n=%d d=%d" % (n, d),
+               "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": step_ms_all, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+               "clocks": clocks,
+               "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": e2e_ms_all, "steps": e2e_steps,
+                       "likelihood_evals": nev,
+                       "h2d_bytes_per_step": int(x_h.nbytes + y_h.nbytes + xs_pinned.nbytes + nev * d * 8),
+                       "d2h_bytes_per_step": int(var.nbytes + nev * 64)},
+               "gpu_launches": int(launches),
+               "stage_ms_per_step": {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
+               "fit_ms_per_step": split["fit_ms"] / args.steps, "predict_ms_per_step": split["predict_ms"] / args.steps,
+               "likelihood_evals_per_s": world * E / (split["fit_ms"] / args.steps * 1e-3),
+               "predict_var_points_per_s": world * m / (split["predict_ms"] / args.steps * 1e-3),
+               "host_wall_ms_per_step": wall_ms / args.steps,
+               "failed_theta_in_sweep": n_fail,
+               "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_sample(n, d, m, E)
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=8192)
+    ap.add_argument("--d", type=int, default=10)
+    ap.add_argument("--m", type=int, default=100000)
+    ap.add_argument("--evals", type=int, default=1101)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,8 @@ SIGNATURES = {
     "egx_gp_reset_profile": (C.c_int, [_vp]),
     "egx_gp_get_profile": (C.c_int, [_vp, _dp, C.POINTER(C.c_longlong)]),
     "egx_gp_set_force_blocked": (C.c_int, [_vp, C.c_int]),
+    "egx_gp_timer_start": (C.c_int, [_vp]),
+    "egx_gp_timer_stop": (C.c_int, [_vp, _dp]),
 }
 
 

@@ -141,5 +141,14 @@ class GpContext:
         self._lib.egx_gp_get_profile(self._h, _ptr(ms), ln.ctypes.data_as(C.POINTER(C.c_longlong)))
         return {STAGE_NAMES[i]: (float(ms[i]), int(ln[i])) for i in range(NUM_STAGES)}
 
+    def timer_start(self):
+        self._check(self._lib.egx_gp_timer_start(self._h))
+
+    def timer_stop(self):
+        """Elapsed device milliseconds on the context's stream since timer_start()."""
+        ms = C.c_double()
+        self._check(self._lib.egx_gp_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def set_force_blocked(self, on=True):
         self._lib.egx_gp_set_force_blocked(self._h, int(bool(on)))

@@ -64,9 +64,9 @@ void launch_mean_basis_rows(const double* X, int n, int npad, int d, const int* 
                             const int* basis_j, int p, const double* ynorm_dev, double* FyT, long ld,
                             cudaStream_t s);
 // kernels_chol.cu
-void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, cudaStream_t s);
-void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, double* P, int nblocks64,
-                      cudaStream_t s);
+void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* Dinv, cudaStream_t s);
+void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P,
+                      int nblocks64, cudaStream_t s);
 void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s);
 int gemm_smem_bytes();
 // kernels_solve.cu

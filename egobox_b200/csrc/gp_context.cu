@@ -105,6 +105,7 @@ struct egx_gp_ctx {
     CorrTerm* terms_h = nullptr;   // pinned
     int max_terms = 0, nterms = 0;
 
+    double* Dinv = nullptr;   // [npad/128][4][32][32] inverted diagonal sub-blocks of L
     double *M = nullptr, *P = nullptr, *glswork = nullptr, *G = nullptr, *beta = nullptr, *rho = nullptr;
     long p_rows = 0;
     EvalResult* res = nullptr;
@@ -122,6 +123,7 @@ struct egx_gp_ctx {
     double *Y = nullptr, *xchunk = nullptr, *ychunk = nullptr, *vchunk = nullptr;
     int mb_alloc = 0;
 
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     bool force_blocked = false;
     bool profiling = false;
     std::vector<ProfEvent> pending;
@@ -244,12 +246,13 @@ void cholesky(egx_gp_ctx* c) {
         double* Akk = c->M + static_cast<long>(k) * EGX_NB * ld + static_cast<long>(k) * EGX_NB;
         {
             StageScope sc(c, EGX_STAGE_POTRF_DIAG);
-            launch_potrf_diag(Akk, ld, c->info, k * EGX_NB, c->stream);
+            launch_potrf_diag(Akk, ld, c->info, k * EGX_NB, c->Dinv + static_cast<long>(k) * 4096, c->stream);
         }
         const int rows_below = (T - k - 1) * EGX_NB + c->qpad;
         if (rows_below > 0) {
             StageScope sc(c, EGX_STAGE_TRSM_PANEL);
-            launch_trsm_rows(Akk + static_cast<long>(EGX_NB) * ld, ld, Akk, ld, c->P, rows_below / 64, c->stream);
+            launch_trsm_rows(Akk + static_cast<long>(EGX_NB) * ld, ld, Akk, ld, c->Dinv + static_cast<long>(k) * 4096, c->P,
+                             rows_below / 64, c->stream);
         }
         const int tri = T - k - 1;
         if (tri > 0) {
@@ -361,7 +364,8 @@ int predict_chunk_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, 
         const double* Lkk = c->M + static_cast<long>(k) * EGX_NB * c->ld + static_cast<long>(k) * EGX_NB;
         {
             StageScope sc(c, EGX_STAGE_TRSM_PANEL);
-            launch_trsm_rows(c->Y + static_cast<long>(k) * EGX_NB, c->npad, Lkk, c->ld, c->P, mpad / 64, c->stream);
+            launch_trsm_rows(c->Y + static_cast<long>(k) * EGX_NB, c->npad, Lkk, c->ld, c->Dinv + static_cast<long>(k) * 4096,
+                             c->P, mpad / 64, c->stream);
         }
         if (k < T - 1) {
             GemmArgs g;
@@ -441,6 +445,8 @@ void free_ctx(egx_gp_ctx* c) {
         cudaEventDestroy(ev.b);
     }
     for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->timer_a) cudaEventDestroy(c->timer_a);
+    if (c->timer_b) cudaEventDestroy(c->timer_b);
     cudaFree(c->X);
     cudaFree(c->ynorm);
     cudaFree(c->x_mean);
@@ -450,6 +456,7 @@ void free_ctx(egx_gp_ctx* c) {
     cudaFree(c->basis_j);
     cudaFree(c->terms);
     cudaFree(c->M);
+    cudaFree(c->Dinv);
     cudaFree(c->P);
     cudaFree(c->glswork);
     cudaFree(c->G);
@@ -558,6 +565,7 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
     const size_t mbytes = static_cast<size_t>(c->rows_total) * c->ld * sizeof(double);
     EGX_CREATE_TRY(cudaMalloc(&c->M, mbytes));
     EGX_CREATE_TRY(cudaMemsetAsync(c->M, 0, mbytes, c->stream));
+    EGX_CREATE_TRY(cudaMalloc(&c->Dinv, static_cast<size_t>(c->npad / EGX_NB) * 4096 * sizeof(double)));
     c->p_rows = c->rows_total;
     EGX_CREATE_TRY(cudaMalloc(&c->P, static_cast<size_t>(c->p_rows) * EGX_NB * sizeof(double)));
     EGX_CREATE_TRY(cudaMalloc(&c->glswork, static_cast<size_t>(c->q) * c->npad * sizeof(double)));
@@ -753,6 +761,28 @@ extern "C" int egx_gp_get_profile(egx_gp_ctx* c, double* ms, long long* launches
         if (ms) ms[i] = c->stage_ms[i];
         if (launches) launches[i] = c->stage_launches[i];
     }
+    return EGX_OK;
+}
+extern "C" int egx_gp_timer_start(egx_gp_ctx* c) {
+    if (!c) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->timer_a) {
+        EGX_CUDA_TRY(cudaEventCreate(&c->timer_a));
+        EGX_CUDA_TRY(cudaEventCreate(&c->timer_b));
+    }
+    EGX_CUDA_TRY(cudaEventRecord(c->timer_a, c->stream));
+    return EGX_OK;
+}
+extern "C" int egx_gp_timer_stop(egx_gp_ctx* c, double* elapsed_ms) {
+    if (!c || !elapsed_ms || !c->timer_a) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    EGX_CUDA_TRY(cudaEventRecord(c->timer_b, c->stream));
+    EGX_CUDA_TRY(cudaEventSynchronize(c->timer_b));
+    float ms = 0.f;
+    EGX_CUDA_TRY(cudaEventElapsedTime(&ms, c->timer_a, c->timer_b));
+    *elapsed_ms = ms;
     return EGX_OK;
 }
 extern "C" int egx_gp_set_force_blocked(egx_gp_ctx* c, int enabled) {

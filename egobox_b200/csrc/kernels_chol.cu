@@ -18,90 +18,221 @@
 namespace {
 
 // ---------------------------------------------------------------------------
-// K3: diagonal block.  512 threads, S[128][129] in shared memory.
+// K3: diagonal block, register-resident right-looking Cholesky.
+// 256 threads = 16 x 16 grid; thread (ty, tx) owns S[ty + 16 a][tx + 16 b], a, b = 0..7
+// (2-D cyclic, so the shrinking trailing matrix stays balanced).  Per column j the owners of
+// column j publish it through a double-buffered 128-entry shared vector (ONE barrier per
+// column), every thread scales with rsqrt(pivot) and applies the rank-1 update to its
+// registers.  Afterwards the four 32 x 32 diagonal sub-blocks are inverted (one warp each,
+// one lane per column) for the blocked triangular solves of K5.
 // ---------------------------------------------------------------------------
-constexpr int PD_LD = 129;
+constexpr int PD_DLD = 33;   // smem leading dimension of the 32x32 diagonal sub-blocks
 
-__global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A, long ld, int* __restrict__ info,
-                                                         int base_index) {
-    extern __shared__ double S[];
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    // load the lower triangle (rows are contiguous in HBM)
-    for (int r = warp; r < EGX_NB; r += 16)
-        for (int c = lane; c <= r; c += 32) S[r * PD_LD + c] = A[static_cast<long>(r) * ld + c];
-    __syncthreads();
-
-    for (int j = 0; j < EGX_NB; ++j) {
-        const double dj = S[j * PD_LD + j];
-        // LAPACK dpotrf semantics: fail on a non-positive or NaN pivot
-        if (!(dj > 0.0)) {
-            if (tid == 0) atomicCAS(info, 0, base_index + j + 1);
+template <int JA>
+__device__ __forceinline__ void potrf_block_columns(double (&a)[8][8], double (*colbuf)[EGX_NB], int ty, int tx,
+                                                    int* info, int base_index, bool& failed) {
+#pragma unroll 1
+    for (int jr = 0; jr < 16; ++jr) {
+        const int j = JA * 16 + jr;
+        double* cb = colbuf[j & 1];
+        if (tx == jr) {
+#pragma unroll
+            for (int ai = JA; ai < 8; ++ai) cb[ty + 16 * ai] = a[ai][JA];
         }
-        const double ljj = sqrt(dj);
-        __syncthreads();   // everyone has read the pivot before it is overwritten
-        if (tid == 0) S[j * PD_LD + j] = ljj;
-        for (int i = j + 1 + tid; i < EGX_NB; i += 512) S[i * PD_LD + j] /= ljj;
         __syncthreads();
-        // trailing update of the lower triangle: S[i][c] -= S[i][j] * S[c][j],  j < c <= i
-        for (int i = j + 1 + warp; i < EGX_NB; i += 16) {
-            const double lij = S[i * PD_LD + j];
-            for (int c = j + 1 + lane; c <= i; c += 32) S[i * PD_LD + c] -= lij * S[c * PD_LD + j];
+        const double dj = cb[j];
+        if (!(dj > 0.0)) {                       // LAPACK dpotrf: non-positive or NaN pivot
+            if (ty == 0 && tx == 0 && !failed) atomicCAS(info, 0, base_index + j + 1);
+            failed = true;
         }
-        // the next iteration's pivot read happens after this barrier
-        __syncthreads();
+        const double rs = rsqrt(dj);
+        double lr[8], lc[8];
+#pragma unroll
+        for (int ai = JA; ai < 8; ++ai) lr[ai] = cb[ty + 16 * ai] * rs;
+#pragma unroll
+        for (int bi = JA; bi < 8; ++bi) lc[bi] = cb[tx + 16 * bi] * rs;
+        // final values of column j (owners only): L[i][j] = S[i][j] / sqrt(d), L[j][j] = sqrt(d)
+        if (tx == jr) {
+#pragma unroll
+            for (int ai = JA; ai < 8; ++ai) {
+                const int i = ty + 16 * ai;
+                if (i > j) a[ai][JA] = lr[ai];
+                else if (i == j) a[ai][JA] = dj * rs;
+            }
+        }
+        // rank-1 update of the trailing lower triangle: rows i > j, columns j < c <= i
+#pragma unroll
+        for (int ai = JA; ai < 8; ++ai) {
+            const bool row_ok = (ai > JA) || (ty > jr);
+#pragma unroll
+            for (int bi = JA; bi <= ai; ++bi) {
+                const bool col_ok = (bi > JA) || (tx > jr);
+                const bool tri_ok = (bi < ai) || (tx <= ty);
+                if (row_ok && col_ok && tri_ok) a[ai][bi] -= lr[ai] * lc[bi];
+            }
+        }
     }
-    for (int r = warp; r < EGX_NB; r += 16)
-        for (int c = lane; c <= r; c += 32) A[static_cast<long>(r) * ld + c] = S[r * PD_LD + c];
+}
+
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, long ld, int* __restrict__ info,
+                                                         int base_index, double* __restrict__ Dinv) {
+    __shared__ double colbuf[2][EGX_NB];
+    __shared__ double Dg[4][32 * PD_DLD];
+    __shared__ double rdiag[4][32];
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    double a[8][8];
+#pragma unroll
+    for (int ai = 0; ai < 8; ++ai)
+#pragma unroll
+        for (int bi = 0; bi < 8; ++bi) {
+            const int r = ty + 16 * ai, c = tx + 16 * bi;
+            a[ai][bi] = (c <= r) ? A[static_cast<long>(r) * ld + c] : 0.0;
+        }
+    bool failed = false;
+    potrf_block_columns<0>(a, colbuf, ty, tx, info, base_index, failed);
+    potrf_block_columns<1>(a, colbuf, ty, tx, info, base_index, failed);
+    potrf_block_columns<2>(a, colbuf, ty, tx, info, base_index, failed);
+    potrf_block_columns<3>(a, colbuf, ty, tx, info, base_index, failed);
+    potrf_block_columns<4>(a, colbuf, ty, tx, info, base_index, failed);
+    potrf_block_columns<5>(a, colbuf, ty, tx, info, base_index, failed);
+    potrf_block_columns<6>(a, colbuf, ty, tx, info, base_index, failed);
+    potrf_block_columns<7>(a, colbuf, ty, tx, info, base_index, failed);
+
+#pragma unroll
+    for (int ai = 0; ai < 8; ++ai)
+#pragma unroll
+        for (int bi = 0; bi < 8; ++bi) {
+            const int r = ty + 16 * ai, c = tx + 16 * bi;
+            if (c <= r) {
+                A[static_cast<long>(r) * ld + c] = a[ai][bi];
+                if ((r >> 5) == (c >> 5)) Dg[r >> 5][(r & 31) * PD_DLD + (c & 31)] = a[ai][bi];
+            }
+        }
+    __syncthreads();
+    // inverse of each 32 x 32 diagonal sub-block: lane c solves L x = e_c by forward substitution
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < 4) {
+        const double* Lb = Dg[warp];
+        rdiag[warp][lane] = 1.0 / Lb[lane * PD_DLD + lane];
+        __syncwarp();
+        double x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            double sacc = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int j = 0; j < i; ++j) sacc -= Lb[i * PD_DLD + j] * x[j];
+            x[i] = sacc * rdiag[warp][i];
+        }
+        double* Do = Dinv + warp * 1024;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Do[i * 32 + lane] = x[i];
+    }
 }
 
 // ---------------------------------------------------------------------------
-// K5: X (64 x 128 slab, in place) <- X * L^-T,  L = 128 x 128 lower block.
-//   x[r][c] = (a[r][c] - sum_{j<c} x[r][j] L[c][j]) / L[c][c]
-// 256 threads: 4 lanes per row (same warp), columns processed in order, the
-// j-sum is split over the 4 lanes (j = q mod 4) and combined with two shuffles.
+// K5: X (64 x 128 slab, in place) <- X * L^-T with L = 128 x 128 lower block, blocked by
+// 32 columns on the FP64 tensor pipe:
+//   for b = 0..3:  T   = X_b - sum_{b' < b} X_b' * L[b, b']^T      (DMMA, K = 32 b)
+//                  X_b = T * Dinv_b^T                               (DMMA, K = 32)
+// Dinv_b are the inverted 32 x 32 diagonal sub-blocks produced by K3 (the standard blocked
+// TRSM of GPU BLAS libraries).  Also emits the contiguous panel copy P used by K4.
+// 256 threads = 8 warps as 4 (rows) x 2 (cols), warp tile 16 x 16 of the 64 x 32 output.
 // ---------------------------------------------------------------------------
 constexpr int TR_ROWS = 64;
-constexpr int TR_LDX = 132;
+constexpr int TR_LDX = 132;   // (4 g + t) mod 16 distinct -> conflict-free fragment loads
+constexpr int TR_LDL = 100;   // columns 0..95 of L (+4 pad)
+constexpr int TR_LDD = 36;
+
+__device__ __forceinline__ void dmma884_t(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
 
 __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, long ldx,
                                                         const double* __restrict__ L, long ldl,
+                                                        const double* __restrict__ Dinv,
                                                         double* __restrict__ P) {
     extern __shared__ double sm[];
-    double* Ls = sm;                       // [128][128]
-    double* Xs = sm + EGX_NB * EGX_NB;     // [64][132]
+    double* Ls = sm;                              // [128][100]
+    double* Ds = Ls + EGX_NB * TR_LDL;            // [4][32][36]
+    double* Xs = Ds + 4 * 32 * TR_LDD;            // [64][132]
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     double* Xg = X + static_cast<long>(blockIdx.x) * TR_ROWS * ldx;
 
-    for (int r = warp; r < EGX_NB; r += 8) {
-        for (int c = lane; c < EGX_NB; c += 32) Ls[r * EGX_NB + c] = (c <= r) ? L[static_cast<long>(r) * ldl + c] : 0.0;
+    for (int r = 32 + warp; r < EGX_NB; r += 8)
+        for (int c = lane; c < 96; c += 32) Ls[r * TR_LDL + c] = L[static_cast<long>(r) * ldl + c];
+    for (int e = tid; e < 4 * 1024; e += 256) {
+        const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
+        Ds[(b * 32 + r) * TR_LDD + c] = Dinv[e];
     }
-    for (int r = warp; r < TR_ROWS; r += 8) {
+    for (int r = warp; r < TR_ROWS; r += 8)
         for (int c = lane; c < EGX_NB; c += 32) Xs[r * TR_LDX + c] = Xg[static_cast<long>(r) * ldx + c];
-    }
     __syncthreads();
 
-    const int r = tid >> 2, q = tid & 3;
-    double* xr = Xs + r * TR_LDX;
-    for (int c = 0; c < EGX_NB; ++c) {
-        const double* lc = Ls + c * EGX_NB;
-        double s0 = 0.0, s1 = 0.0;
-        int j = q;
-        for (; j + 4 < c; j += 8) {
-            s0 += xr[j] * lc[j];
-            s1 += xr[j + 4] * lc[j + 4];
+    const int wm = warp >> 1, wn = warp & 1;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int row0 = wm * 16;        // rows of this warp inside the slab
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        const int col0 = b * 32 + wn * 16;          // output columns of this warp
+        double acc[2][2][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                const double2 v = *reinterpret_cast<const double2*>(&Xs[(row0 + mi * 8 + gid) * TR_LDX + col0 + ni * 8 + 2 * tig]);
+                acc[mi][ni][0] = v.x;
+                acc[mi][ni][1] = v.y;
+            }
+        // T = X_b - X[:, 0:32b] * L[b-block rows, 0:32b]^T
+        for (int k0 = 0; k0 < 32 * b; k0 += 4) {
+            double af[2], bf[2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) af[mi] = -Xs[(row0 + mi * 8 + gid) * TR_LDX + k0 + tig];
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) bf[ni] = Ls[(col0 + ni * 8 + gid) * TR_LDL + k0 + tig];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
-        if (j < c) s0 += xr[j] * lc[j];
-        double s = s0 + s1;
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        const double x = (xr[c] - s) / lc[c];
-        __syncwarp();
-        if (q == 0) xr[c] = x;
-        __syncwarp();
+        __syncthreads();        // every warp has finished reading X_b as an accumulator seed
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+                *reinterpret_cast<double2*>(&Xs[(row0 + mi * 8 + gid) * TR_LDX + col0 + ni * 8 + 2 * tig]) =
+                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        __syncthreads();        // T is visible
+        // X_b = T * Dinv_b^T
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll
+        for (int k0 = 0; k0 < 32; k0 += 4) {
+            double af[2], bf[2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) af[mi] = Xs[(row0 + mi * 8 + gid) * TR_LDX + b * 32 + k0 + tig];
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) bf[ni] = Ds[(b * 32 + wn * 16 + ni * 8 + gid) * TR_LDD + k0 + tig];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+        }
+        __syncthreads();        // all reads of T done before it is overwritten by X_b
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+                *reinterpret_cast<double2*>(&Xs[(row0 + mi * 8 + gid) * TR_LDX + col0 + ni * 8 + 2 * tig]) =
+                    make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        __syncthreads();        // X_b visible to the next block step
     }
-    __syncthreads();
     double* Pg = (P != nullptr) ? P + static_cast<long>(blockIdx.x) * TR_ROWS * EGX_NB : nullptr;
     for (int rr = warp; rr < TR_ROWS; rr += 8) {
         for (int c = lane; c < EGX_NB; c += 32) {
@@ -245,25 +376,20 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_sub_kernel(const GemmArgs g) {
 
 int gemm_smem_bytes() { return 2 * GM_STAGES * GM_TILE_ELEMS * static_cast<int>(sizeof(double)); }
 
-void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, cudaStream_t s) {
-    static bool configured = false;
-    const int smem = EGX_NB * PD_LD * sizeof(double);
-    if (!configured) {
-        cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
-    }
-    potrf_diag_kernel<<<1, 512, smem, s>>>(Akk, ld, info, base_index);
+void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* Dinv, cudaStream_t s) {
+    potrf_diag_kernel<<<1, 256, 0, s>>>(Akk, ld, info, base_index, Dinv);
 }
 
-void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, double* P, int nblocks64, cudaStream_t s) {
+void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, int nblocks64,
+                      cudaStream_t s) {
     static bool configured = false;
-    const int smem = (EGX_NB * EGX_NB + TR_ROWS * TR_LDX) * sizeof(double);
+    const int smem = (EGX_NB * TR_LDL + 4 * 32 * TR_LDD + TR_ROWS * TR_LDX) * sizeof(double);
     if (!configured) {
         cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
     if (nblocks64 <= 0) return;
-    trsm_rows_kernel<<<nblocks64, 256, smem, s>>>(X, ldx, Lkk, ldl, P);
+    trsm_rows_kernel<<<nblocks64, 256, smem, s>>>(X, ldx, Lkk, ldl, Dinv, P);
 }
 
 void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s) {

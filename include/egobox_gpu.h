@@ -146,6 +146,11 @@ int egx_gp_set_profiling(egx_gp_ctx* ctx, int enabled);
 int egx_gp_reset_profile(egx_gp_ctx* ctx);
 /* ms[EGX_NUM_STAGES], launches[EGX_NUM_STAGES] */
 int egx_gp_get_profile(egx_gp_ctx* ctx, double* ms, long long* launches);
+/* Device timer on the context's own stream (CUDA events): start records an event, stop
+ * records a second one, waits for it and returns the elapsed milliseconds in between
+ * (includes any GPU idle time while the host prepares the next launch). */
+int egx_gp_timer_start(egx_gp_ctx* ctx);
+int egx_gp_timer_stop(egx_gp_ctx* ctx, double* elapsed_ms);
 /* Force the blocked large-n path even when n is small enough for the
  * one-CTA-per-theta kernel (tests exercise both on the same inputs). */
 int egx_gp_set_force_blocked(egx_gp_ctx* ctx, int enabled);

@@ -178,4 +178,19 @@ def test_corr_matrix_equals_scatter():
         R = np.eye(23) * (1.0 + O.DEFAULT_NUGGET)
         R[idx[:, 0], idx[:, 1]] = r
         R[idx[:, 1], idx[:, 0]] = r
-        np.testing.assert_allclose(O.corr_matrix(kind, x, theta, np.eye(3)), R, rtol=1e-14, atol=0)
+        np.testing.assert_allclose(O.corr_matrix(kind, x, theta, np.eye(3)), R, rtol=1e-12, atol=0)
+
+
+def test_c_restatement_matches_numpy():
+    """oracle/corr_oracle.c (OpenMP, the CPU-baseline kernel) against the numpy restatement."""
+    from oracle import fast
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(57, 4))
+    xs = rng.normal(size=(13, 4))
+    for w in (np.eye(4), rng.normal(size=(4, 2))):
+        theta = np.array([0.4, 1.1, 0.7, 2.0])[: w.shape[1]]
+        for kind in (O.SQEXP, O.ABSEXP, O.MATERN32, O.MATERN52):
+            np.testing.assert_allclose(fast.corr_matrix(kind, x, theta, w), O.corr_matrix(kind, x, theta, w),
+                                       rtol=1e-12, atol=0)
+            ref = O.corr_value(kind, O.pairwise_differences(xs, x), theta, w).reshape(13, 57)
+            np.testing.assert_allclose(fast.cross_corr(kind, xs, x, theta, w), ref, rtol=1e-12, atol=0)
