@@ -8,6 +8,7 @@
 // number test on the p x p factor G (algorithm.rs:1010-1027).
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <mutex>
@@ -98,7 +99,12 @@ struct egx_gp_ctx {
     std::vector<double> w_star, xnorm_h;
     std::vector<int> basis_i_h, basis_j_h;
 
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // bulk stream (everything except the look-ahead panel work)
+    cudaStream_t stream_panel = nullptr;  // high-priority stream: diagonal block + panel solves one step ahead
+    std::vector<cudaEvent_t> ev_panel, ev_bulk;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    double* P2[2] = {nullptr, nullptr};   // double-buffered contiguous panel copies
+    bool lookahead = true;
     double *X = nullptr, *ynorm = nullptr, *x_mean = nullptr, *x_std = nullptr, *FyT = nullptr;
     int *basis_i = nullptr, *basis_j = nullptr;
     CorrTerm* terms = nullptr;
@@ -106,7 +112,7 @@ struct egx_gp_ctx {
     int max_terms = 0, nterms = 0;
 
     double* Dinv = nullptr;   // [npad/128][4][32][32] inverted diagonal sub-blocks of L
-    double *M = nullptr, *P = nullptr, *glswork = nullptr, *G = nullptr, *beta = nullptr, *rho = nullptr;
+    double *M = nullptr, *glswork = nullptr, *G = nullptr, *beta = nullptr, *rho = nullptr;
     long p_rows = 0;
     EvalResult* res = nullptr;
     int* info = nullptr;
@@ -139,7 +145,9 @@ struct StageScope {
     egx_gp_ctx* c;
     ProfEvent ev;
     bool on;
-    StageScope(egx_gp_ctx* ctx, int stage, int launches = 1) : c(ctx), on(ctx->profiling) {
+    cudaStream_t st;
+    StageScope(egx_gp_ctx* ctx, int stage, int launches = 1, cudaStream_t stream = nullptr)
+        : c(ctx), on(ctx->profiling), st(stream ? stream : ctx->stream) {
         c->stage_launches[stage] += launches;
         if (on) {
             ev.stage = stage;
@@ -151,12 +159,12 @@ struct StageScope {
                     cudaEventCreate(e);
                 }
             }
-            cudaEventRecord(ev.a, c->stream);
+            cudaEventRecord(ev.a, st);
         }
     }
     ~StageScope() {
         if (on) {
-            cudaEventRecord(ev.b, c->stream);
+            cudaEventRecord(ev.b, st);
             c->pending.push_back(ev);
         }
     }
@@ -239,37 +247,121 @@ int assemble(egx_gp_ctx* c, const double* theta) {
     return EGX_OK;
 }
 
-void cholesky(egx_gp_ctx* c) {
+// Generic blocked "solve block column k, update the trailing columns" sweep shared by the
+// Cholesky factorisation (factor = true: rows are the rows of the matrix below the diagonal
+// plus the appended RHS rows) and by the multi-RHS solve Y L^T = C of predict_var
+// (factor = false: rows are prediction points).  With look-ahead the diagonal block, the panel
+// solve and the update of the NEXT block column run on a high-priority stream while the bulk
+// of the trailing update of the current step is still in flight on the main stream.
+struct SweepArgs {
+    bool factor;
+    double* rows;      // factor: M ; solve: Y
+    long ld_rows;
+    int row_tiles;     // solve: number of 128-row tiles of Y ; factor: unused
+    int slabs64;       // solve: number of 64-row slabs
+};
+
+void blocked_sweep(egx_gp_ctx* c, const SweepArgs& a) {
     const int T = c->npad / EGX_NB, Qt = c->qpad / EGX_NB;
     const long ld = c->ld;
-    for (int k = 0; k < T; ++k) {
-        double* Akk = c->M + static_cast<long>(k) * EGX_NB * ld + static_cast<long>(k) * EGX_NB;
-        {
-            StageScope sc(c, EGX_STAGE_POTRF_DIAG);
-            launch_potrf_diag(Akk, ld, c->info, k * EGX_NB, c->Dinv + static_cast<long>(k) * 4096, c->stream);
-        }
-        const int rows_below = (T - k - 1) * EGX_NB + c->qpad;
-        if (rows_below > 0) {
-            StageScope sc(c, EGX_STAGE_TRSM_PANEL);
-            launch_trsm_rows(Akk + static_cast<long>(EGX_NB) * ld, ld, Akk, ld, c->Dinv + static_cast<long>(k) * 4096, c->P,
-                             rows_below / 64, c->stream);
-        }
-        const int tri = T - k - 1;
-        if (tri > 0) {
-            GemmArgs g;
-            g.C = Akk + static_cast<long>(EGX_NB) * ld + EGX_NB;
-            g.ldc = ld;
-            g.A = c->P;
-            g.lda = EGX_NB;
-            g.B = c->P;
-            g.ldb = EGX_NB;
-            g.tri = tri;
-            g.Mt = tri + Qt;
-            g.Nt = tri;
-            StageScope sc(c, EGX_STAGE_SYRK_GEMM);
-            launch_gemm_nt_sub(g, c->stream);
-        }
+    const bool la = c->lookahead && T > 2;
+    cudaStream_t sb = c->stream, sp = la ? c->stream_panel : c->stream;
+    if (la) {
+        cudaEventRecord(c->ev_fork, sb);
+        cudaStreamWaitEvent(sp, c->ev_fork, 0);
     }
+    for (int k = 0; k < T; ++k) {
+        double* Pk = c->P2[k & 1];
+        const double* Lkk = c->M + static_cast<long>(k) * EGX_NB * ld + static_cast<long>(k) * EGX_NB;
+        const int tri = T - k - 1;
+        // ---- panel (k) -------------------------------------------------------------
+        if (a.factor) {
+            double* Akk = c->M + static_cast<long>(k) * EGX_NB * ld + static_cast<long>(k) * EGX_NB;
+            {
+                StageScope sc(c, EGX_STAGE_POTRF_DIAG, 1, sp);
+                launch_potrf_diag(Akk, ld, c->info, k * EGX_NB, c->Dinv + static_cast<long>(k) * 4096, sp);
+            }
+            const int rows_below = tri * EGX_NB + c->qpad;
+            StageScope sc(c, EGX_STAGE_TRSM_PANEL, 1, sp);
+            launch_trsm_rows(Akk + static_cast<long>(EGX_NB) * ld, ld, Akk, ld, c->Dinv + static_cast<long>(k) * 4096, Pk,
+                             rows_below / 64, sp);
+        } else {
+            StageScope sc(c, EGX_STAGE_TRSM_PANEL, 1, sp);
+            launch_trsm_rows(a.rows + static_cast<long>(k) * EGX_NB, a.ld_rows, Lkk, ld,
+                             c->Dinv + static_cast<long>(k) * 4096, Pk, a.slabs64, sp);
+        }
+        if (tri == 0) break;
+        if (la) cudaEventRecord(c->ev_panel[k], sp);
+        // ---- trailing update (k) ---------------------------------------------------
+        GemmArgs g;
+        g.A = Pk;
+        g.lda = EGX_NB;
+        if (a.factor) {
+            g.C = c->M + static_cast<long>(k + 1) * EGX_NB * ld + static_cast<long>(k + 1) * EGX_NB;
+            g.ldc = ld;
+            g.B = Pk;
+            g.ldb = EGX_NB;
+        } else {
+            g.C = a.rows + static_cast<long>(k + 1) * EGX_NB;
+            g.ldc = a.ld_rows;
+            g.B = Lkk + static_cast<long>(EGX_NB) * ld;
+            g.ldb = ld;
+        }
+        if (!la) {
+            g.tri = a.factor ? tri : 0;
+            g.Mt = a.factor ? tri + Qt : a.row_tiles;
+            g.Nt = tri;
+            StageScope sc(c, EGX_STAGE_SYRK_GEMM, 1, sb);
+            launch_gemm_nt_sub(g, sb);
+            continue;
+        }
+        // part A: block column k+1 only (what panel k+1 needs), on the panel stream
+        if (k > 0) cudaStreamWaitEvent(sp, c->ev_bulk[k - 1], 0);
+        {
+            GemmArgs ga = g;
+            ga.tri = 0;
+            ga.Mt = a.factor ? tri + Qt : a.row_tiles;
+            ga.Nt = 1;
+            StageScope sc(c, EGX_STAGE_GEMM_LOOKAHEAD, 1, sp);
+            launch_gemm_nt_sub(ga, sp);
+        }
+        // part B: block columns k+2.., on the bulk stream
+        cudaStreamWaitEvent(sb, c->ev_panel[k], 0);
+        if (tri > 1) {
+            GemmArgs gb = g;
+            if (a.factor) {
+                gb.C = g.C + static_cast<long>(EGX_NB) * ld + EGX_NB;
+                gb.A = Pk + static_cast<long>(EGX_NB) * EGX_NB;
+                gb.B = Pk + static_cast<long>(EGX_NB) * EGX_NB;
+                gb.tri = tri - 1;
+                gb.Mt = tri - 1 + Qt;
+                gb.Nt = tri - 1;
+            } else {
+                gb.C = g.C + EGX_NB;
+                gb.B = g.B + static_cast<long>(EGX_NB) * ld;
+                gb.tri = 0;
+                gb.Mt = a.row_tiles;
+                gb.Nt = tri - 1;
+            }
+            StageScope sc(c, EGX_STAGE_SYRK_GEMM, 1, sb);
+            launch_gemm_nt_sub(gb, sb);
+        }
+        cudaEventRecord(c->ev_bulk[k], sb);
+    }
+    if (la) {
+        cudaEventRecord(c->ev_join, sp);
+        cudaStreamWaitEvent(sb, c->ev_join, 0);
+    }
+}
+
+void cholesky(egx_gp_ctx* c) {
+    SweepArgs a;
+    a.factor = true;
+    a.rows = c->M;
+    a.ld_rows = c->ld;
+    a.row_tiles = 0;
+    a.slabs64 = 0;
+    blocked_sweep(c, a);
 }
 
 // Full likelihood evaluation; leaves L, (L^-1[F|y])^T, beta, G, rho on the device.
@@ -331,9 +423,11 @@ int ensure_predict_buffers(egx_gp_ctx* c, int mb) {
     EGX_CUDA_TRY(cudaMalloc(&c->ychunk, static_cast<size_t>(mb) * sizeof(double)));
     EGX_CUDA_TRY(cudaMalloc(&c->vchunk, static_cast<size_t>(mb) * sizeof(double)));
     if (static_cast<long>(mb) > c->p_rows) {
-        cudaFree(c->P);
-        c->P = nullptr;
-        EGX_CUDA_TRY(cudaMalloc(&c->P, static_cast<size_t>(mb) * EGX_NB * sizeof(double)));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(c->P2[i]);
+            c->P2[i] = nullptr;
+            EGX_CUDA_TRY(cudaMalloc(&c->P2[i], static_cast<size_t>(mb) * EGX_NB * sizeof(double)));
+        }
         c->p_rows = mb;
     }
     c->mb_alloc = mb;
@@ -359,28 +453,14 @@ int predict_chunk_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, 
                                        static_cast<size_t>(c->n) * sizeof(double), m, cudaMemcpyDeviceToDevice,
                                        c->stream));
     if (!want_var) return EGX_OK;
-    const int T = c->npad / EGX_NB;
-    for (int k = 0; k < T; ++k) {
-        const double* Lkk = c->M + static_cast<long>(k) * EGX_NB * c->ld + static_cast<long>(k) * EGX_NB;
-        {
-            StageScope sc(c, EGX_STAGE_TRSM_PANEL);
-            launch_trsm_rows(c->Y + static_cast<long>(k) * EGX_NB, c->npad, Lkk, c->ld, c->Dinv + static_cast<long>(k) * 4096,
-                             c->P, mpad / 64, c->stream);
-        }
-        if (k < T - 1) {
-            GemmArgs g;
-            g.C = c->Y + static_cast<long>(k + 1) * EGX_NB;
-            g.ldc = c->npad;
-            g.A = c->P;
-            g.lda = EGX_NB;
-            g.B = Lkk + static_cast<long>(EGX_NB) * c->ld;
-            g.ldb = c->ld;
-            g.tri = 0;
-            g.Mt = mpad / EGX_NB;
-            g.Nt = T - k - 1;
-            StageScope sc(c, EGX_STAGE_SYRK_GEMM);
-            launch_gemm_nt_sub(g, c->stream);
-        }
+    {
+        SweepArgs a;
+        a.factor = false;
+        a.rows = c->Y;
+        a.ld_rows = c->npad;
+        a.row_tiles = mpad / EGX_NB;
+        a.slabs64 = mpad / 64;
+        blocked_sweep(c, a);
     }
     {
         StageScope sc(c, EGX_STAGE_VAR_FINISH);
@@ -457,7 +537,13 @@ void free_ctx(egx_gp_ctx* c) {
     cudaFree(c->terms);
     cudaFree(c->M);
     cudaFree(c->Dinv);
-    cudaFree(c->P);
+    cudaFree(c->P2[0]);
+    cudaFree(c->P2[1]);
+    for (auto e : c->ev_panel) cudaEventDestroy(e);
+    for (auto e : c->ev_bulk) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream_panel) cudaStreamDestroy(c->stream_panel);
     cudaFree(c->glswork);
     cudaFree(c->G);
     cudaFree(c->beta);
@@ -567,7 +653,24 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
     EGX_CREATE_TRY(cudaMemsetAsync(c->M, 0, mbytes, c->stream));
     EGX_CREATE_TRY(cudaMalloc(&c->Dinv, static_cast<size_t>(c->npad / EGX_NB) * 4096 * sizeof(double)));
     c->p_rows = c->rows_total;
-    EGX_CREATE_TRY(cudaMalloc(&c->P, static_cast<size_t>(c->p_rows) * EGX_NB * sizeof(double)));
+    for (int i = 0; i < 2; ++i)
+        EGX_CREATE_TRY(cudaMalloc(&c->P2[i], static_cast<size_t>(c->p_rows) * EGX_NB * sizeof(double)));
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        EGX_CREATE_TRY(cudaStreamCreateWithPriority(&c->stream_panel, cudaStreamNonBlocking, hi));
+        const int T = c->npad / EGX_NB;
+        c->ev_panel.resize(T);
+        c->ev_bulk.resize(T);
+        for (int k = 0; k < T; ++k) {
+            EGX_CREATE_TRY(cudaEventCreateWithFlags(&c->ev_panel[k], cudaEventDisableTiming));
+            EGX_CREATE_TRY(cudaEventCreateWithFlags(&c->ev_bulk[k], cudaEventDisableTiming));
+        }
+        EGX_CREATE_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        EGX_CREATE_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        const char* e = getenv("EGX_LOOKAHEAD");
+        c->lookahead = !(e != nullptr && atoi(e) == 0);
+    }
     EGX_CREATE_TRY(cudaMalloc(&c->glswork, static_cast<size_t>(c->q) * c->npad * sizeof(double)));
     EGX_CREATE_TRY(cudaMalloc(&c->G, static_cast<size_t>(p) * p * sizeof(double)));
     EGX_CREATE_TRY(cudaMalloc(&c->beta, p * sizeof(double)));

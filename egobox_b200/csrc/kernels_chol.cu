@@ -12,6 +12,8 @@
 // tcgen05 has no f64 kind (kinds: f16, tf32, f8f6f4, i8, mxf8f6f4, mxf4, mxf4nvf4), so the
 // fp64-exact contraction runs on the DMMA pipe; see DESIGN.md for the int8-sliced tcgen05
 // variant and which one each profile measures.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/egobox_gpu.h"
 
@@ -150,11 +152,16 @@ __device__ __forceinline__ void dmma884_t(double& c0, double& c1, double a, doub
                  : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void tr_cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, long ldx,
                                                         const double* __restrict__ L, long ldl,
                                                         const double* __restrict__ Dinv,
                                                         double* __restrict__ P) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     double* Ls = sm;                              // [128][100]
     double* Ds = Ls + EGX_NB * TR_LDL;            // [4][32][36]
     double* Xs = Ds + 4 * 32 * TR_LDD;            // [64][132]
@@ -162,14 +169,22 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
     const int warp = tid >> 5, lane = tid & 31;
     double* Xg = X + static_cast<long>(blockIdx.x) * TR_ROWS * ldx;
 
-    for (int r = 32 + warp; r < EGX_NB; r += 8)
-        for (int c = lane; c < 96; c += 32) Ls[r * TR_LDL + c] = L[static_cast<long>(r) * ldl + c];
-    for (int e = tid; e < 4 * 1024; e += 256) {
-        const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
-        Ds[(b * 32 + r) * TR_LDD + c] = Dinv[e];
+    // stage L (rows 32..127, cols 0..95), the four Dinv blocks and the X slab with 16-byte cp.async
+    // (all requests in flight at once; plain load/store loops expose one L2 round trip per iteration)
+    for (int e = tid; e < 96 * 48; e += 256) {
+        const int r = 32 + e / 48, ch = e % 48;
+        tr_cp_async16(&Ls[r * TR_LDL + ch * 2], L + static_cast<long>(r) * ldl + ch * 2);
     }
-    for (int r = warp; r < TR_ROWS; r += 8)
-        for (int c = lane; c < EGX_NB; c += 32) Xs[r * TR_LDX + c] = Xg[static_cast<long>(r) * ldx + c];
+    for (int e = tid; e < 2048; e += 256) {
+        const int b = e >> 9, r = (e >> 4) & 31, ch = e & 15;
+        tr_cp_async16(&Ds[(b * 32 + r) * TR_LDD + ch * 2], Dinv + e * 2);
+    }
+    for (int e = tid; e < TR_ROWS * 64; e += 256) {
+        const int r = e >> 6, ch = e & 63;
+        tr_cp_async16(&Xs[r * TR_LDX + ch * 2], Xg + static_cast<long>(r) * ldx + ch * 2);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int wm = warp >> 1, wn = warp & 1;
@@ -234,12 +249,11 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
         __syncthreads();        // X_b visible to the next block step
     }
     double* Pg = (P != nullptr) ? P + static_cast<long>(blockIdx.x) * TR_ROWS * EGX_NB : nullptr;
-    for (int rr = warp; rr < TR_ROWS; rr += 8) {
-        for (int c = lane; c < EGX_NB; c += 32) {
-            const double v = Xs[rr * TR_LDX + c];
-            Xg[static_cast<long>(rr) * ldx + c] = v;
-            if (Pg != nullptr) Pg[rr * EGX_NB + c] = v;
-        }
+    for (int e = tid; e < TR_ROWS * 64; e += 256) {
+        const int r = e >> 6, ch = e & 63;
+        const double2 v = *reinterpret_cast<const double2*>(&Xs[r * TR_LDX + ch * 2]);
+        *reinterpret_cast<double2*>(Xg + static_cast<long>(r) * ldx + ch * 2) = v;
+        if (Pg != nullptr) *reinterpret_cast<double2*>(Pg + r * EGX_NB + ch * 2) = v;
     }
 }
 
@@ -270,50 +284,66 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// tile t -> (row tile r of 128 rows, column tile c of BN columns)
+template <int BN>
 __device__ __forceinline__ void gemm_tile_decode(const GemmArgs& g, int t, int& r, int& c) {
+    constexpr int S = EGX_NB / BN;          // column tiles per 128-block (1 or 2)
     if (g.tri > 0) {
-        const int ntri = g.tri * (g.tri + 1) / 2;
+        const int ntri = S * g.tri * (g.tri + 1) / 2;
         if (t < ntri) {
-            int rr = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
-            while ((rr + 1) * (rr + 2) / 2 <= t) ++rr;
-            while (rr * (rr + 1) / 2 > t) --rr;
+            // rows r = 0..tri-1 hold S*(r+1) tiles each; prefix(r) = S r (r+1) / 2
+            int rr = static_cast<int>((sqrt(8.0 * static_cast<double>(t) / S + 1.0) - 1.0) * 0.5);
+            while (S * (rr + 1) * (rr + 2) / 2 <= t) ++rr;
+            while (S * rr * (rr + 1) / 2 > t) --rr;
             r = rr;
-            c = t - rr * (rr + 1) / 2;
+            c = t - S * rr * (rr + 1) / 2;
         } else {
-            const int u = t - ntri;
-            r = g.tri + u / g.tri;
-            c = u % g.tri;
+            const int u = t - ntri, w = S * g.tri;
+            r = g.tri + u / w;
+            c = u % w;
         }
     } else {
-        r = t / g.Nt;
-        c = t % g.Nt;
+        const int w = S * g.Nt;
+        r = t / w;
+        c = t % w;
     }
 }
 
-__global__ void __launch_bounds__(256, 1) gemm_nt_sub_kernel(const GemmArgs g) {
+template <int BN>
+__global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(const GemmArgs g) {
+    constexpr int WARPS_N = (BN == 128) ? 4 : 2;
+    constexpr int WARPS_M = 8 / WARPS_N;
+    constexpr int MI = EGX_NB / WARPS_M / 8;      // m8 tiles per warp
+    constexpr int NI = BN / WARPS_N / 8;          // n8 tiles per warp
+    constexpr int A_ELEMS = EGX_NB * GM_LDS, B_ELEMS = BN * GM_LDS;
     extern __shared__ __align__(16) double gsm[];
-    double* As = gsm;                                   // [STAGES][128][20]
-    double* Bs = gsm + GM_STAGES * GM_TILE_ELEMS;       // [STAGES][128][20]
+    double* As = gsm;                               // [STAGES][128][20]
+    double* Bs = gsm + GM_STAGES * A_ELEMS;         // [STAGES][BN][20]
 
     int tr, tc;
-    gemm_tile_decode(g, blockIdx.x, tr, tc);
+    gemm_tile_decode<BN>(g, blockIdx.x, tr, tc);
     const double* Ag = g.A + static_cast<long>(tr) * EGX_NB * g.lda;
-    const double* Bg = g.B + static_cast<long>(tc) * EGX_NB * g.ldb;
-    double* Cg = g.C + static_cast<long>(tr) * EGX_NB * g.ldc + static_cast<long>(tc) * EGX_NB;
+    const double* Bg = g.B + static_cast<long>(tc) * BN * g.ldb;
+    double* Cg = g.C + static_cast<long>(tr) * EGX_NB * g.ldc + static_cast<long>(tc) * BN;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
     const int gid = lane >> 2, tig = lane & 3;
 
     auto load_stage = [&](int stage, int kb) {
-        double* as = As + stage * GM_TILE_ELEMS;
-        double* bs = Bs + stage * GM_TILE_ELEMS;
+        double* as = As + stage * A_ELEMS;
+        double* bs = Bs + stage * B_ELEMS;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int idx = tid + i * 256;          // 1024 16-byte chunks per operand
+            const int idx = tid + i * 256;          // 1024 16-byte chunks of A
             const int row = idx >> 3, ch = idx & 7;
             cp_async16(as + row * GM_LDS + ch * 2, Ag + static_cast<long>(row) * g.lda + kb * GM_BK + ch * 2);
+        }
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+            const int idx = tid + i * 256;
+            const int row = idx >> 3, ch = idx & 7;
             cp_async16(bs + row * GM_LDS + ch * 2, Bg + static_cast<long>(row) * g.ldb + kb * GM_BK + ch * 2);
         }
     };
@@ -326,13 +356,13 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_sub_kernel(const GemmArgs g) {
     }
 
     // accumulators start as the C tile
-    double acc[8][4][2];
+    double acc[MI][NI][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int row = wm * 64 + mi * 8 + gid;
-            const int col = wn * 32 + ni * 8 + 2 * tig;
+        for (int ni = 0; ni < NI; ++ni) {
+            const int row = wm * (MI * 8) + mi * 8 + gid;
+            const int col = wn * (NI * 8) + ni * 8 + 2 * tig;
             const double2 c = *reinterpret_cast<const double2*>(Cg + static_cast<long>(row) * g.ldc + col);
             acc[mi][ni][0] = c.x;
             acc[mi][ni][1] = c.y;
@@ -344,29 +374,29 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_sub_kernel(const GemmArgs g) {
         __syncthreads();
         if (kb + GM_STAGES - 1 < KB) load_stage((kb + GM_STAGES - 1) % GM_STAGES, kb + GM_STAGES - 1);
         cp_async_commit();
-        const double* as = As + (kb % GM_STAGES) * GM_TILE_ELEMS + (wm * 64 + gid) * GM_LDS + tig;
-        const double* bs = Bs + (kb % GM_STAGES) * GM_TILE_ELEMS + (wn * 32 + gid) * GM_LDS + tig;
+        const double* as = As + (kb % GM_STAGES) * A_ELEMS + (wm * (MI * 8) + gid) * GM_LDS + tig;
+        const double* bs = Bs + (kb % GM_STAGES) * B_ELEMS + (wn * (NI * 8) + gid) * GM_LDS + tig;
 #pragma unroll
         for (int kk = 0; kk < GM_BK / 4; ++kk) {
-            double a[8], b[4];
+            double a[MI], b[NI];
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi) a[mi] = -as[mi * 8 * GM_LDS + kk * 4];
+            for (int mi = 0; mi < MI; ++mi) a[mi] = -as[mi * 8 * GM_LDS + kk * 4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = bs[ni * 8 * GM_LDS + kk * 4];
+            for (int ni = 0; ni < NI; ++ni) b[ni] = bs[ni * 8 * GM_LDS + kk * 4];
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi)
+            for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
     }
     cp_async_wait<0>();
 
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int row = wm * 64 + mi * 8 + gid;
-            const int col = wn * 32 + ni * 8 + 2 * tig;
+        for (int ni = 0; ni < NI; ++ni) {
+            const int row = wm * (MI * 8) + mi * 8 + gid;
+            const int col = wn * (NI * 8) + ni * 8 + 2 * tig;
             *reinterpret_cast<double2*>(Cg + static_cast<long>(row) * g.ldc + col) =
                 make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
@@ -374,7 +404,7 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_sub_kernel(const GemmArgs g) {
 
 }  // namespace
 
-int gemm_smem_bytes() { return 2 * GM_STAGES * GM_TILE_ELEMS * static_cast<int>(sizeof(double)); }
+int gemm_smem_bytes() { return GM_STAGES * (EGX_NB + 128) * GM_LDS * static_cast<int>(sizeof(double)); }
 
 void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* Dinv, cudaStream_t s) {
     potrf_diag_kernel<<<1, 256, 0, s>>>(Akk, ld, info, base_index, Dinv);
@@ -392,16 +422,29 @@ void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const do
     trsm_rows_kernel<<<nblocks64, 256, smem, s>>>(X, ldx, Lkk, ldl, Dinv, P);
 }
 
+static int gemm_bn() {
+    static int bn = 0;
+    if (bn == 0) {
+        const char* e = getenv("EGX_GEMM_BN");
+        bn = (e != nullptr && atoi(e) == 128) ? 128 : 64;
+    }
+    return bn;
+}
+
 void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s) {
     static bool configured = false;
-    const int smem = gemm_smem_bytes();
+    const int smem128 = GM_STAGES * (EGX_NB + 128) * GM_LDS * static_cast<int>(sizeof(double));
+    const int smem64 = GM_STAGES * (EGX_NB + 64) * GM_LDS * static_cast<int>(sizeof(double));
     if (!configured) {
-        cudaFuncSetAttribute(gemm_nt_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(gemm_nt_sub_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128);
+        cudaFuncSetAttribute(gemm_nt_sub_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
         configured = true;
     }
+    const int S = (gemm_bn() == 128) ? 1 : 2;
     int tiles;
-    if (g.tri > 0) tiles = g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri;
-    else tiles = g.Mt * g.Nt;
+    if (g.tri > 0) tiles = S * g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * S * g.tri;
+    else tiles = g.Mt * S * g.Nt;
     if (tiles <= 0) return;
-    gemm_nt_sub_kernel<<<tiles, 256, smem, s>>>(g);
+    if (S == 1) gemm_nt_sub_kernel<128><<<tiles, 256, smem128, s>>>(g);
+    else gemm_nt_sub_kernel<64><<<tiles, 256, smem64, s>>>(g);
 }

@@ -68,16 +68,21 @@ def test_fit_matches_oracle_at_found_theta():
     gp = egx.GaussianProcess.params(egx.ConstantMean, egx.Matern52Corr).fit(x, y)
     th = gp.theta()
     ogp = O.fit(x, y, corr=O.MATERN52, mean=O.CONSTANT, theta_init=th, fixed=True)
-    assert gp.likelihood() == pytest.approx(ogp.likelihood, rel=1e-9)
-    assert gp.variance() == pytest.approx(ogp.inner.sigma2, rel=1e-8)
+    # the optimum of a smooth function sits at small theta where R is ill conditioned: sigma2 (hence
+    # rlf) carries a relative error ~ cond(R) * eps on the CPU and on the GPU alike (hard part 2)
+    cond = np.linalg.cond(O.corr_matrix(O.MATERN52, ogp.xt_norm, th, np.eye(3)))
+    tol = max(1e-9, cond * 2.3e-16)
+    assert gp.likelihood() == pytest.approx(ogp.likelihood, rel=tol)
+    assert gp.variance() == pytest.approx(ogp.inner.sigma2, rel=10 * tol)
     xs = rng.random((50, 3))
-    np.testing.assert_allclose(gp.predict(xs), ogp.predict(xs), rtol=1e-7, atol=1e-9)
-    np.testing.assert_allclose(gp.predict_var(xs), ogp.predict_var(xs), rtol=1e-6, atol=1e-9 * ogp.inner.sigma2)
+    np.testing.assert_allclose(gp.predict(xs), ogp.predict(xs), rtol=max(1e-7, 10 * tol), atol=1e-9)
+    np.testing.assert_allclose(gp.predict_var(xs), ogp.predict_var(xs), rtol=max(1e-6, 10 * tol),
+                               atol=max(1e-9, 10 * tol) * ogp.inner.sigma2)
     ofull = O.fit(x, y, corr=O.MATERN52, mean=O.CONSTANT)
     assert gp.likelihood() >= ofull.likelihood - 1e-3 * abs(ofull.likelihood)
     assert 30 <= gp.n_evals() <= 11 * 30 + 1       # maxeval = clamp(10*3, 25, 1000) per chain
     ip = gp.inner_params()
-    np.testing.assert_allclose(ip["r_chol"], ogp.inner.r_chol, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(ip["r_chol"], ogp.inner.r_chol, rtol=0, atol=max(1e-11, tol))
 
 
 def test_kriging_alias_and_errors():

@@ -221,3 +221,55 @@ def test_ill_conditioned_ft_status():
     with pytest.raises(LikelihoodComputationError):
         O.reduced_likelihood(O.SQEXP, xn, O.mean_value(O.QUADRATIC, xn), yn, float(ys[0]), [1.0, 1.0], np.eye(2))
     ctx.close()
+
+
+# ------------------------------------------- accuracy against exact arithmetic -----------
+def _rlf_extended(R, fx, yn):
+    """Reduced likelihood in x87 extended precision (eps 1.1e-19): plain Cholesky-Banachiewicz,
+    forward solves, GLS by normal equations on the (tiny, well conditioned) p x p system."""
+    ld = np.longdouble
+    n = R.shape[0]
+    A = R.astype(ld)
+    L = np.zeros((n, n), dtype=ld)
+    for i in range(n):
+        for j in range(i):
+            L[i, j] = (A[i, j] - np.dot(L[i, :j], L[j, :j])) / L[j, j]
+        L[i, i] = np.sqrt(A[i, i] - np.dot(L[i, :i], L[i, :i]))
+    B = np.concatenate([fx, yn.reshape(-1, 1)], axis=1).astype(ld)
+    Z = np.zeros_like(B)
+    for i in range(n):
+        Z[i] = (B[i] - L[i, :i] @ Z[:i]) / L[i, i]
+    Ft, yt = Z[:, :-1], Z[:, -1]
+    G = Ft.T @ Ft
+    beta = np.linalg.solve(G.astype(np.float64), (Ft.T @ yt).astype(np.float64)).astype(ld)
+    beta = beta + np.linalg.solve(G.astype(np.float64), (Ft.T @ (yt - Ft @ beta)).astype(np.float64)).astype(ld)
+    rho = yt - Ft @ beta
+    sigma2 = np.dot(rho, rho) / n
+    logdet = np.sum(np.log10(np.diag(L))) * 2 / n
+    return float(-n * (np.log10(sigma2) + logdet))
+
+
+@pytest.mark.parametrize("theta0,label", [(0.35, "cond~1e12"), (1.0, "cond~1e8")])
+def test_accuracy_against_extended_precision(theta0, label):
+    """Who is closer to exact arithmetic?  The GPU path must be as accurate as the CPU LAPACK path:
+    both within cond(R)*eps of the extended-precision value, and within the north-star 1e-6 whenever
+    cond(R) <= 1e10."""
+    n, d = 220, 2
+    x, y = make_problem(n, d, seed=21)
+    theta = np.full(d, theta0)
+    ctx, (xn, xm, xs, yn, ym, ys) = make_context(x, y, O.MATERN52, O.CONSTANT)
+    R = O.corr_matrix(O.MATERN52, xn, theta, np.eye(d))
+    cond = np.linalg.cond(R)
+    fx = O.mean_value(O.CONSTANT, xn)
+    ext = _rlf_extended(R, fx, yn[:, 0])
+    cpu, _ = O.reduced_likelihood(O.MATERN52, xn, fx, yn, ys, theta, np.eye(d))
+    st, gpu = ctx.reduced_likelihood(theta)
+    assert st == 0
+    err_cpu, err_gpu = abs(cpu - ext) / abs(ext), abs(gpu - ext) / abs(ext)
+    print("%s cond=%.2e  rel.err cpu=%.2e gpu=%.2e" % (label, cond, err_cpu, err_gpu))
+    bound = cond * 2.3e-16
+    assert err_gpu <= max(bound, 1e-13)
+    assert err_cpu <= max(bound, 1e-13)
+    if cond <= 1e10:
+        assert err_gpu <= 1e-6
+    ctx.close()
