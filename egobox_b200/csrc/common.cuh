@@ -78,3 +78,12 @@ void launch_backsolve_update(const double* Lrow, long ld, const double* gamma_k,
 void launch_var_finish(const double* Y, long ldy, int m, int npad, const double* xraw, const double* x_mean,
                        const double* x_std, int d, const double* FtT, long ldf, const double* G, int p,
                        const int* basis_i, const int* basis_j, double sigma2, double* var, cudaStream_t s);
+// small_batch.cu
+size_t small_batch_smem_bytes(int n, int d, int h, int p);
+void launch_small_batch(int corr, const double* X, int n, int d, const double* W, int h, const double* thetas, int B,
+                        const double* FyT, long ldf, int p, double diag_value, void* out, double* out_G,
+                        cudaStream_t s);
+struct SmallOutHost {
+    double rlf, sigma2;
+    int info, pad_;
+};

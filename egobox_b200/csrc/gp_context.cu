@@ -120,6 +120,13 @@ struct egx_gp_ctx {
     EvalResult* res_h = nullptr;
     double *G_h = nullptr, *beta_h = nullptr;
 
+    // small-n batched path (K8)
+    double *W_dev = nullptr, *sb_thetas = nullptr, *sb_G = nullptr;
+    void* sb_out = nullptr;
+    SmallOutHost* sb_out_h = nullptr;   // pinned
+    double *sb_G_h = nullptr, *sb_thetas_h = nullptr;
+    int sb_cap = 0;
+
     // trained state (after finalize)
     bool trained = false;
     std::vector<double> theta;
@@ -264,7 +271,9 @@ struct SweepArgs {
 void blocked_sweep(egx_gp_ctx* c, const SweepArgs& a) {
     const int T = c->npad / EGX_NB, Qt = c->qpad / EGX_NB;
     const long ld = c->ld;
-    const bool la = c->lookahead && T > 2;
+    // look-ahead pays for the factorisation (a serial 1-CTA diagonal block per step); the multi-RHS solve
+    // has no serial part and is faster as plain back-to-back launches (measured: 22.9 vs 28.8 ms / chunk)
+    const bool la = c->lookahead && a.factor && T > 2;
     cudaStream_t sb = c->stream, sp = la ? c->stream_panel : c->stream;
     if (la) {
         cudaEventRecord(c->ev_fork, sb);
@@ -364,6 +373,95 @@ void cholesky(egx_gp_ctx* c) {
     blocked_sweep(c, a);
 }
 
+// Condition-number test of gp/src/algorithm.rs:1010-1027 on the p x p factor G (host, O(p^3)).
+int cond_status(egx_gp_ctx* c, const double* G) {
+    std::vector<double> sv = singular_values(G, c->p, c->p);
+    const double cond_ft = sv.back() / sv.front();
+    if (!(cond_ft >= 1e-10)) {
+        // fx = mean.value(xnorm) rebuilt on the host for the (rare) diagnostic branch
+        std::vector<double> F(static_cast<size_t>(c->n) * c->p);
+        for (int i = 0; i < c->n; ++i)
+            for (int l = 0; l < c->p; ++l) {
+                const int bi = c->basis_i_h[l], bj = c->basis_j_h[l];
+                const double* x = &c->xnorm_h[static_cast<size_t>(i) * c->d];
+                F[static_cast<size_t>(i) * c->p + l] = (bi < 0 ? 1.0 : x[bi]) * (bj < 0 ? 1.0 : x[bj]);
+            }
+        std::vector<double> svf = singular_values(F.data(), c->n, c->p);
+        const double cond_fx = svf.front() / svf.back();
+        if (cond_fx > 1e15) {
+            egx_set_error("F is too ill conditioned. Poor combination of regression model and observations.");
+            return EGX_ILL_CONDITIONED_F;
+        }
+        egx_set_error("ft is too ill conditioned, try another theta again");
+        return EGX_ILL_CONDITIONED_FT;
+    }
+    return EGX_OK;
+}
+
+bool small_path_ok(const egx_gp_ctx* c) {
+    return !c->force_blocked && small_batch_smem_bytes(c->n, c->d, c->h, c->p) <= 225 * 1024;
+}
+
+// B candidate thetas, one CTA each (K8).  thetas: host, B x h.
+int evaluate_small_batch(egx_gp_ctx* c, const double* thetas, int B, double* rlf, int* status) {
+    if (B <= 0) return EGX_OK;
+    c->trained = false;
+    if (B > c->sb_cap) {
+        cudaFree(c->sb_thetas);
+        cudaFree(c->sb_G);
+        cudaFree(c->sb_out);
+        cudaFreeHost(c->sb_out_h);
+        cudaFreeHost(c->sb_G_h);
+        cudaFreeHost(c->sb_thetas_h);
+        c->sb_cap = 0;
+        const int cap = std::max(B, 64);
+        EGX_CUDA_TRY(cudaMalloc(&c->sb_thetas, static_cast<size_t>(cap) * c->h * sizeof(double)));
+        EGX_CUDA_TRY(cudaMalloc(&c->sb_G, static_cast<size_t>(cap) * c->p * c->p * sizeof(double)));
+        EGX_CUDA_TRY(cudaMalloc(&c->sb_out, static_cast<size_t>(cap) * sizeof(SmallOutHost)));
+        EGX_CUDA_TRY(cudaMallocHost(&c->sb_out_h, static_cast<size_t>(cap) * sizeof(SmallOutHost)));
+        EGX_CUDA_TRY(cudaMallocHost(&c->sb_G_h, static_cast<size_t>(cap) * c->p * c->p * sizeof(double)));
+        EGX_CUDA_TRY(cudaMallocHost(&c->sb_thetas_h, static_cast<size_t>(cap) * c->h * sizeof(double)));
+        c->sb_cap = cap;
+    }
+    std::vector<char> bad(B, 0);
+    for (int b = 0; b < B; ++b)
+        for (int l = 0; l < c->h; ++l) {
+            const double v = thetas[static_cast<long>(b) * c->h + l];
+            if (std::isnan(v)) bad[b] = 1;
+            c->sb_thetas_h[static_cast<long>(b) * c->h + l] = std::isnan(v) ? 1.0 : v;
+        }
+    EGX_CUDA_TRY(cudaMemcpyAsync(c->sb_thetas, c->sb_thetas_h, static_cast<size_t>(B) * c->h * sizeof(double),
+                                 cudaMemcpyHostToDevice, c->stream));
+    {
+        StageScope sc(c, EGX_STAGE_SMALL_BATCH);
+        launch_small_batch(c->corr, c->X, c->n, c->d, c->W_dev, c->h, c->sb_thetas, B, c->FyT, c->ld, c->p,
+                           1.0 + c->nugget, c->sb_out, c->sb_G, c->stream);
+    }
+    EGX_CUDA_TRY(cudaMemcpyAsync(c->sb_out_h, c->sb_out, static_cast<size_t>(B) * sizeof(SmallOutHost),
+                                 cudaMemcpyDeviceToHost, c->stream));
+    EGX_CUDA_TRY(cudaMemcpyAsync(c->sb_G_h, c->sb_G, static_cast<size_t>(B) * c->p * c->p * sizeof(double),
+                                 cudaMemcpyDeviceToHost, c->stream));
+    EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EGX_CUDA_TRY(cudaGetLastError());
+    resolve_profile(c);
+    for (int b = 0; b < B; ++b) {
+        rlf[b] = NAN;
+        if (bad[b]) {
+            egx_set_error("theta is NaN");
+            status[b] = EGX_INVALID_VALUE;
+            continue;
+        }
+        if (c->sb_out_h[b].info != 0) {
+            egx_set_error("correlation matrix is not positive definite (pivot %d)", c->sb_out_h[b].info);
+            status[b] = EGX_NOT_POSITIVE_DEFINITE;
+            continue;
+        }
+        status[b] = cond_status(c, c->sb_G_h + static_cast<long>(b) * c->p * c->p);
+        if (status[b] == EGX_OK) rlf[b] = c->sb_out_h[b].rlf;
+    }
+    return EGX_OK;
+}
+
 // Full likelihood evaluation; leaves L, (L^-1[F|y])^T, beta, G, rho on the device.
 int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
     *rlf_out = NAN;
@@ -385,26 +483,9 @@ int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
         egx_set_error("correlation matrix is not positive definite (pivot %d)", c->res_h->info);
         return EGX_NOT_POSITIVE_DEFINITE;
     }
-    // condition number test, algorithm.rs:1010-1027
-    std::vector<double> sv = singular_values(c->G_h, c->p, c->p);
-    const double cond_ft = sv.back() / sv.front();
-    if (!(cond_ft >= 1e-10)) {
-        // fx = mean.value(xnorm) rebuilt on the host for the (rare) diagnostic branch
-        std::vector<double> F(static_cast<size_t>(c->n) * c->p);
-        for (int i = 0; i < c->n; ++i)
-            for (int l = 0; l < c->p; ++l) {
-                const int bi = c->basis_i_h[l], bj = c->basis_j_h[l];
-                const double* x = &c->xnorm_h[static_cast<size_t>(i) * c->d];
-                F[static_cast<size_t>(i) * c->p + l] = (bi < 0 ? 1.0 : x[bi]) * (bj < 0 ? 1.0 : x[bj]);
-            }
-        std::vector<double> svf = singular_values(F.data(), c->n, c->p);
-        const double cond_fx = svf.front() / svf.back();
-        if (cond_fx > 1e15) {
-            egx_set_error("F is too ill conditioned. Poor combination of regression model and observations.");
-            return EGX_ILL_CONDITIONED_F;
-        }
-        egx_set_error("ft is too ill conditioned, try another theta again");
-        return EGX_ILL_CONDITIONED_FT;
+    {
+        const int cst = cond_status(c, c->G_h);
+        if (cst != EGX_OK) return cst;
     }
     *rlf_out = c->res_h->rlf;
     return EGX_OK;
@@ -536,6 +617,13 @@ void free_ctx(egx_gp_ctx* c) {
     cudaFree(c->basis_j);
     cudaFree(c->terms);
     cudaFree(c->M);
+    cudaFree(c->W_dev);
+    cudaFree(c->sb_thetas);
+    cudaFree(c->sb_G);
+    cudaFree(c->sb_out);
+    cudaFreeHost(c->sb_out_h);
+    cudaFreeHost(c->sb_G_h);
+    cudaFreeHost(c->sb_thetas_h);
     cudaFree(c->Dinv);
     cudaFree(c->P2[0]);
     cudaFree(c->P2[1]);
@@ -644,6 +732,8 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
     EGX_CREATE_TRY(cudaMalloc(&c->basis_j, p * sizeof(int)));
     EGX_CREATE_TRY(cudaMemcpyAsync(c->basis_i, c->basis_i_h.data(), p * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     EGX_CREATE_TRY(cudaMemcpyAsync(c->basis_j, c->basis_j_h.data(), p * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    EGX_CREATE_TRY(cudaMalloc(&c->W_dev, static_cast<size_t>(d) * h * sizeof(double)));
+    EGX_CREATE_TRY(cudaMemcpyAsync(c->W_dev, w_star, static_cast<size_t>(d) * h * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->max_terms = d * h;
     EGX_CREATE_TRY(cudaMalloc(&c->terms, c->max_terms * sizeof(CorrTerm)));
     EGX_CREATE_TRY(cudaMallocHost(&c->terms_h, c->max_terms * sizeof(CorrTerm)));
@@ -703,6 +793,11 @@ extern "C" int egx_gp_reduced_likelihood(egx_gp_ctx* c, const double* theta, dou
     if (!c || !theta || !rlf) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
+    if (small_path_ok(c)) {
+        int st = EGX_OK;
+        const int rc = evaluate_small_batch(c, theta, 1, rlf, &st);
+        return rc != EGX_OK ? rc : st;
+    }
     return evaluate(c, theta, rlf);
 }
 
@@ -710,6 +805,7 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
     if (!c || !thetas || !rlf || !status || B < 0) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
+    if (small_path_ok(c)) return evaluate_small_batch(c, thetas, B, rlf, status);
     for (int b = 0; b < B; ++b) {
         status[b] = evaluate(c, thetas + static_cast<long>(b) * c->h, &rlf[b]);
         if (status[b] == EGX_CUDA_ERROR) return EGX_CUDA_ERROR;

@@ -159,7 +159,9 @@ class BoundCobyla {
         if (phase_ == TRUST) {
             const double actual = F_[0] - f;
             insert_after_trust(f);
-            if (actual > 0.0 && actual >= 0.1 * predicted_) iterate(false);
+            // Powell: a step that earns >= 10 % of the predicted reduction is followed by another
+            // trust-region step straight away (no geometry check in between)
+            if (replaced_ && actual > 0.0 && actual >= 0.1 * predicted_) iterate(true);
             else after_failure();
             return;
         }
@@ -394,32 +396,50 @@ class BoundCobyla {
         phase_ = GEOM;
     }
 
-    // replace one vertex by the trust-region point (Powell's volume / distance rule)
+    // Decide whether the trust-region point replaces a vertex (Powell 1994, COBYLA "L440"):
+    //   temp_j = |simi_j . d| is the ratio new/old simplex volume if vertex j is replaced; the change is
+    //   mandatory when the point improves on the best vertex, otherwise the volume must grow (temp_j > 1).
+    //   Among replacements that keep the simplex acceptable, prefer dropping the vertex farthest from the
+    //   new point when it lies beyond 1.1 rho.
     void insert_after_trust(double f) {
         const int n = n_;
         const bool improved = f < F_[0];
+        double ratio = improved ? 0.0 : 1.0;
         int jd = -1;
-        double best = improved ? 1.0 : 0.0;   // ratio threshold: keep the simplex volume from collapsing
+        std::vector<double> sigbar(n);
         for (int j = 0; j < n; ++j) {
             double t = 0.0;
             for (int i = 0; i < n; ++i) t += simi_[static_cast<size_t>(j) * n + i] * d_[i];
             t = std::fabs(t);
-            if (eta_[j] > kBeta * rho_) t *= eta_[j] / rho_;
-            if (t > best) {
-                best = t;
+            if (t > ratio) {
                 jd = j;
+                ratio = t;
+            }
+            sigbar[j] = t * sigma_[j];
+        }
+        double edgmax = 1.1 * rho_;
+        int l = -1;
+        const double parsig = kAlpha * rho_;
+        for (int j = 0; j < n; ++j) {
+            if (sigbar[j] >= parsig || sigbar[j] >= sigma_[j]) {
+                double t = eta_[j];
+                if (predicted_ > 0.0) {
+                    t = 0.0;
+                    for (int i = 0; i < n; ++i) {
+                        const double e = d_[i] - (V_[j + 1][i] - V_[0][i]);
+                        t += e * e;
+                    }
+                    t = std::sqrt(t);
+                }
+                if (t > edgmax) {
+                    l = j;
+                    edgmax = t;
+                }
             }
         }
-        if (jd < 0) {
-            if (!improved) return;      // the point would flatten the simplex and is not better: drop it
-            // better point but every replacement shrinks the volume: drop the worst vertex
-            double fw = -kInf;
-            for (int j = 0; j < n; ++j)
-                if (F_[j + 1] > fw) {
-                    fw = F_[j + 1];
-                    jd = j;
-                }
-        }
+        if (l >= 0) jd = l;
+        replaced_ = jd >= 0;
+        if (!replaced_) return;
         V_[jd + 1] = pending_;
         F_[jd + 1] = f;
     }
@@ -430,7 +450,7 @@ class BoundCobyla {
     int maxfun_, nfev_ = 0;
     std::vector<std::vector<double>> V_;
     std::vector<double> F_, simi_, sigma_, eta_, g_, d_, pending_, xbest_;
-    bool acceptable_ = false;
+    bool acceptable_ = false, replaced_ = false;
     double predicted_ = 0.0, fbest_ = kInf;
     int init_idx_ = 0, jdrop_ = 0;
     Phase phase_;

@@ -30,8 +30,12 @@ namespace {
 // ---------------------------------------------------------------------------
 constexpr int PD_DLD = 33;   // smem leading dimension of the 32x32 diagonal sub-blocks
 
+// The column owners publish column j with ZEROS in rows <= j (and the pivot in slot 128), so that
+// every thread can apply the rank-1 update unconditionally: rows / columns that are already final
+// see a zero multiplier.  This keeps the per-column instruction count (the kernel is issue bound,
+// not latency bound: ~8 warps x 128 columns on ONE SM) close to the 36 DFMA it needs.
 template <int JA>
-__device__ __forceinline__ void potrf_block_columns(double (&a)[8][8], double (*colbuf)[EGX_NB], int ty, int tx,
+__device__ __forceinline__ void potrf_block_columns(double (&a)[8][8], double (*colbuf)[EGX_NB + 8], int ty, int tx,
                                                     int* info, int base_index, bool& failed) {
 #pragma unroll 1
     for (int jr = 0; jr < 16; ++jr) {
@@ -39,10 +43,14 @@ __device__ __forceinline__ void potrf_block_columns(double (&a)[8][8], double (*
         double* cb = colbuf[j & 1];
         if (tx == jr) {
 #pragma unroll
-            for (int ai = JA; ai < 8; ++ai) cb[ty + 16 * ai] = a[ai][JA];
+            for (int ai = JA; ai < 8; ++ai) {
+                const int i = ty + 16 * ai;
+                cb[i] = (i > j) ? a[ai][JA] : 0.0;
+                if (i == j) cb[EGX_NB] = a[ai][JA];
+            }
         }
         __syncthreads();
-        const double dj = cb[j];
+        const double dj = cb[EGX_NB];
         if (!(dj > 0.0)) {                       // LAPACK dpotrf: non-positive or NaN pivot
             if (ty == 0 && tx == 0 && !failed) atomicCAS(info, 0, base_index + j + 1);
             failed = true;
@@ -53,6 +61,12 @@ __device__ __forceinline__ void potrf_block_columns(double (&a)[8][8], double (*
         for (int ai = JA; ai < 8; ++ai) lr[ai] = cb[ty + 16 * ai] * rs;
 #pragma unroll
         for (int bi = JA; bi < 8; ++bi) lc[bi] = cb[tx + 16 * bi] * rs;
+        // rank-1 update of the trailing block (upper halves of diagonal 16x16 register blocks are
+        // updated too: they are never read)
+#pragma unroll
+        for (int ai = JA; ai < 8; ++ai)
+#pragma unroll
+            for (int bi = JA; bi <= ai; ++bi) a[ai][bi] -= lr[ai] * lc[bi];
         // final values of column j (owners only): L[i][j] = S[i][j] / sqrt(d), L[j][j] = sqrt(d)
         if (tx == jr) {
 #pragma unroll
@@ -62,23 +76,12 @@ __device__ __forceinline__ void potrf_block_columns(double (&a)[8][8], double (*
                 else if (i == j) a[ai][JA] = dj * rs;
             }
         }
-        // rank-1 update of the trailing lower triangle: rows i > j, columns j < c <= i
-#pragma unroll
-        for (int ai = JA; ai < 8; ++ai) {
-            const bool row_ok = (ai > JA) || (ty > jr);
-#pragma unroll
-            for (int bi = JA; bi <= ai; ++bi) {
-                const bool col_ok = (bi > JA) || (tx > jr);
-                const bool tri_ok = (bi < ai) || (tx <= ty);
-                if (row_ok && col_ok && tri_ok) a[ai][bi] -= lr[ai] * lc[bi];
-            }
-        }
     }
 }
 
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, long ld, int* __restrict__ info,
                                                          int base_index, double* __restrict__ Dinv) {
-    __shared__ double colbuf[2][EGX_NB];
+    __shared__ double colbuf[2][EGX_NB + 8];
     __shared__ double Dg[4][32 * PD_DLD];
     __shared__ double rdiag[4][32];
     const int tid = threadIdx.x;

@@ -273,3 +273,63 @@ def test_accuracy_against_extended_precision(theta0, label):
     if cond <= 1e10:
         assert err_gpu <= 1e-6
     ctx.close()
+
+
+# ------------------------------------------------- K8: one CTA per theta -----------------
+@pytest.mark.parametrize("n,d,corr,mean", [
+    (5, 1, O.SQEXP, O.CONSTANT),
+    (21, 20, O.MATERN52, O.CONSTANT),       # BASELINE config 5: EGO Rosenbrock d=20, n_doe = d+1
+    (100, 20, O.MATERN52, O.CONSTANT),      # ... and the end of its budget
+    (64, 3, O.MATERN32, O.LINEAR),
+    (150, 2, O.ABSEXP, O.QUADRATIC),
+    (97, 4, O.SQEXP, O.LINEAR),
+])
+def test_small_batch_path(n, d, corr, mean):
+    x, y = make_problem(n, d, seed=100 + n)
+    ctx, (xn, xm, xs, yn, ym, ys) = make_context(x, y, corr, mean)
+    rng = np.random.default_rng(n)
+    B = 24
+    thetas = 10.0 ** rng.uniform(-0.3, 1.0, size=(B, d))
+    fx = O.mean_value(mean, xn)
+    status, rlf = ctx.reduced_likelihood_batch(thetas)              # one CTA per theta
+    ctx.set_force_blocked(True)
+    status_b, rlf_b = ctx.reduced_likelihood_batch(thetas)          # blocked path, same inputs
+    ctx.set_force_blocked(False)
+    n_ok = 0
+    for b in range(B):
+        try:
+            ref, _ = O.reduced_likelihood(corr, xn, fx, yn, ys, thetas[b], np.eye(d))
+            ost = 0
+        except O.LinalgError:
+            ost = 1
+        except O.LikelihoodComputationError:
+            ost = 2
+        assert (status[b] == 0) == (ost == 0), (b, status[b], ost)
+        assert status[b] == status_b[b]
+        if ost == 0:
+            n_ok += 1
+            assert rlf[b] == pytest.approx(ref, rel=1e-8)          # bound: 1e-6
+            assert rlf_b[b] == pytest.approx(ref, rel=1e-8)
+    assert n_ok >= B // 2
+    st1, v1 = ctx.reduced_likelihood(thetas[0])
+    assert st1 == status[0] and (st1 != 0 or v1 == rlf[0])
+    ctx.close()
+
+
+def test_theta_sweep_512_candidates():
+    """BASELINE config 5 shape: 512 candidate thetas, d=20, n=21 training points."""
+    n, d, B = 21, 20, 512
+    x, y = make_problem(n, d, seed=5)
+    ctx, (xn, xm, xs, yn, ym, ys) = make_context(x, y, O.MATERN52, O.CONSTANT)
+    thetas = 10.0 ** np.random.default_rng(42).uniform(-2.0, 1.0, size=(B, d))
+    status, rlf = ctx.reduced_likelihood_batch(thetas)
+    fx = O.mean_value(O.CONSTANT, xn)
+    for b in range(0, B, 17):
+        ref = -O.objective(O.MATERN52, xn, fx, yn, ys, thetas[b], np.eye(d))
+        if np.isfinite(ref):
+            assert status[b] == 0 and rlf[b] == pytest.approx(ref, rel=1e-8)
+        else:
+            assert status[b] != 0
+    best = int(np.nanargmax(np.where(status == 0, rlf, -np.inf)))
+    assert status[best] == 0
+    ctx.close()
