@@ -281,7 +281,10 @@ def run_ours(args):
     x_h, y_h = np.ascontiguousarray(x), np.ascontiguousarray(y)
 
     def e2e_step():
-        gp = (eg.GaussianProcess.params(eg.ConstantMean, eg.Matern52Corr).n_start(10).max_eval(1000)
+        # same evaluation budget as the value leg: (n_start + 1) chains x clamp(10 d, 25, 1000) + 1 final
+        per_chain = min(max(10 * d, 25), 1000)
+        gp = (eg.GaussianProcess.params(eg.ConstantMean, eg.Matern52Corr)
+              .n_start(max((E - 1) // per_chain - 1, 0)).max_eval(1000)
               .cobyla_ftol_rel(0.0).device(local_rank).fit(x_h, y_h))
         var = gp.predict_var(xs_pinned)
         nev = gp.n_evals()

@@ -37,6 +37,10 @@ struct GemmArgs {
     int Mt, Nt;      // tile counts (128 x 128 tiles)
     int tri;         // tri > 0: lower-triangular tile set, first `tri` tile rows are
                      // triangular (c <= r), rows tri..Mt-1 are full (c < tri).  tri == 0: full Mt x Nt
+    int K = 128;     // contraction length (multiple of 16)
+    int add = 0;     // 0: C -= A B^T (factorisation / solve updates) ; 1: C += A B^T
+    int splits = 1;  // split-K: blockIdx.y = s works on K-range [s*K, (s+1)*K) of A/B and on C + s*split_c_stride
+    long split_c_stride = 0;
 };
 
 #define EGX_CUDA_TRY(expr)                                                         \
@@ -54,12 +58,12 @@ void egx_set_error(const char* fmt, ...);
 // ---- launchers (host) ------------------------------------------------------
 // kernels_corr.cu
 void launch_corr_build(int corr, const double* X, int n, int npad, int d, const CorrTerm* terms,
-                       int nterms, double* M, long ld, double diag_value, cudaStream_t s);
+                       int nterms, double* M, long ld, double diag_value, cudaStream_t s, double scale = 1.0);
 void launch_cross_corr(int corr, const double* xraw, int m, int mpad, const double* x_mean,
                        const double* x_std, const double* X, int n, int npad, int d,
                        const CorrTerm* terms, int nterms, const double* gamma, const double* beta,
                        const int* basis_i, const int* basis_j, int p, double y_mean, double y_std,
-                       double* Y, long ldy, double* yout, cudaStream_t s);
+                       double* Y, long ldy, double* yout, cudaStream_t s, double scale = 1.0);
 void launch_mean_basis_rows(const double* X, int n, int npad, int d, const int* basis_i,
                             const int* basis_j, int p, const double* ynorm_dev, double* FyT, long ld,
                             cudaStream_t s);

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "sweep.cuh"
 #include "../../include/egobox_gpu.h"
 
 // ---------------------------------------------------------------------------
@@ -83,11 +84,6 @@ std::vector<double> singular_values(const double* a, int rows, int cols) {
     return sv;
 }
 
-struct ProfEvent {
-    cudaEvent_t a, b;
-    int stage;
-};
-
 }  // namespace
 
 struct egx_gp_ctx {
@@ -99,12 +95,8 @@ struct egx_gp_ctx {
     std::vector<double> w_star, xnorm_h;
     std::vector<int> basis_i_h, basis_j_h;
 
-    cudaStream_t stream = nullptr;        // bulk stream (everything except the look-ahead panel work)
-    cudaStream_t stream_panel = nullptr;  // high-priority stream: diagonal block + panel solves one step ahead
-    std::vector<cudaEvent_t> ev_panel, ev_bulk;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    double* P2[2] = {nullptr, nullptr};   // double-buffered contiguous panel copies
-    bool lookahead = true;
+    SweepEnv env;                         // streams, look-ahead events, panel buffers, profiler
+    cudaStream_t stream = nullptr;        // alias of env.sb
     double *X = nullptr, *ynorm = nullptr, *x_mean = nullptr, *x_std = nullptr, *FyT = nullptr;
     int *basis_i = nullptr, *basis_j = nullptr;
     CorrTerm* terms = nullptr;
@@ -113,7 +105,6 @@ struct egx_gp_ctx {
 
     double* Dinv = nullptr;   // [npad/128][4][32][32] inverted diagonal sub-blocks of L
     double *M = nullptr, *glswork = nullptr, *G = nullptr, *beta = nullptr, *rho = nullptr;
-    long p_rows = 0;
     EvalResult* res = nullptr;
     int* info = nullptr;
     // pinned host mirrors
@@ -138,54 +129,12 @@ struct egx_gp_ctx {
 
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     bool force_blocked = false;
-    bool profiling = false;
-    std::vector<ProfEvent> pending;
-    std::vector<cudaEvent_t> event_pool;
-    double stage_ms[EGX_NUM_STAGES] = {0};
-    long long stage_launches[EGX_NUM_STAGES] = {0};
     std::mutex mu;
 };
 
 namespace {
 
-struct StageScope {
-    egx_gp_ctx* c;
-    ProfEvent ev;
-    bool on;
-    cudaStream_t st;
-    StageScope(egx_gp_ctx* ctx, int stage, int launches = 1, cudaStream_t stream = nullptr)
-        : c(ctx), on(ctx->profiling), st(stream ? stream : ctx->stream) {
-        c->stage_launches[stage] += launches;
-        if (on) {
-            ev.stage = stage;
-            for (cudaEvent_t* e : {&ev.a, &ev.b}) {
-                if (!c->event_pool.empty()) {
-                    *e = c->event_pool.back();
-                    c->event_pool.pop_back();
-                } else {
-                    cudaEventCreate(e);
-                }
-            }
-            cudaEventRecord(ev.a, st);
-        }
-    }
-    ~StageScope() {
-        if (on) {
-            cudaEventRecord(ev.b, st);
-            c->pending.push_back(ev);
-        }
-    }
-};
-
-void resolve_profile(egx_gp_ctx* c) {
-    for (auto& ev : c->pending) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) c->stage_ms[ev.stage] += ms;
-        c->event_pool.push_back(ev.a);
-        c->event_pool.push_back(ev.b);
-    }
-    c->pending.clear();
-}
+void resolve_profile(egx_gp_ctx* c) { c->env.prof.resolve(); }
 
 int build_terms(egx_gp_ctx* c, const double* theta) {
     const int d = c->d, h = c->h;
@@ -244,7 +193,7 @@ int assemble(egx_gp_ctx* c, const double* theta) {
     if (st != EGX_OK) return st;
     EGX_CUDA_TRY(cudaMemsetAsync(c->info, 0, sizeof(int), c->stream));
     {
-        StageScope sc(c, EGX_STAGE_CORR_BUILD);
+        StageScope sc(c->env.prof, EGX_STAGE_CORR_BUILD, 1, c->stream);
         launch_corr_build(c->corr, c->X, c->n, c->npad, c->d, c->terms, c->nterms, c->M, c->ld, 1.0 + c->nugget,
                           c->stream);
     }
@@ -254,124 +203,18 @@ int assemble(egx_gp_ctx* c, const double* theta) {
     return EGX_OK;
 }
 
-// Generic blocked "solve block column k, update the trailing columns" sweep shared by the
-// Cholesky factorisation (factor = true: rows are the rows of the matrix below the diagonal
-// plus the appended RHS rows) and by the multi-RHS solve Y L^T = C of predict_var
-// (factor = false: rows are prediction points).  With look-ahead the diagonal block, the panel
-// solve and the update of the NEXT block column run on a high-priority stream while the bulk
-// of the trailing update of the current step is still in flight on the main stream.
-struct SweepArgs {
-    bool factor;
-    double* rows;      // factor: M ; solve: Y
-    long ld_rows;
-    int row_tiles;     // solve: number of 128-row tiles of Y ; factor: unused
-    int slabs64;       // solve: number of 64-row slabs
-};
-
-void blocked_sweep(egx_gp_ctx* c, const SweepArgs& a) {
-    const int T = c->npad / EGX_NB, Qt = c->qpad / EGX_NB;
-    const long ld = c->ld;
-    // look-ahead pays for the factorisation (a serial 1-CTA diagonal block per step); the multi-RHS solve
-    // has no serial part and is faster as plain back-to-back launches (measured: 22.9 vs 28.8 ms / chunk)
-    const bool la = c->lookahead && a.factor && T > 2;
-    cudaStream_t sb = c->stream, sp = la ? c->stream_panel : c->stream;
-    if (la) {
-        cudaEventRecord(c->ev_fork, sb);
-        cudaStreamWaitEvent(sp, c->ev_fork, 0);
-    }
-    for (int k = 0; k < T; ++k) {
-        double* Pk = c->P2[k & 1];
-        const double* Lkk = c->M + static_cast<long>(k) * EGX_NB * ld + static_cast<long>(k) * EGX_NB;
-        const int tri = T - k - 1;
-        // ---- panel (k) -------------------------------------------------------------
-        if (a.factor) {
-            double* Akk = c->M + static_cast<long>(k) * EGX_NB * ld + static_cast<long>(k) * EGX_NB;
-            {
-                StageScope sc(c, EGX_STAGE_POTRF_DIAG, 1, sp);
-                launch_potrf_diag(Akk, ld, c->info, k * EGX_NB, c->Dinv + static_cast<long>(k) * 4096, sp);
-            }
-            const int rows_below = tri * EGX_NB + c->qpad;
-            StageScope sc(c, EGX_STAGE_TRSM_PANEL, 1, sp);
-            launch_trsm_rows(Akk + static_cast<long>(EGX_NB) * ld, ld, Akk, ld, c->Dinv + static_cast<long>(k) * 4096, Pk,
-                             rows_below / 64, sp);
-        } else {
-            StageScope sc(c, EGX_STAGE_TRSM_PANEL, 1, sp);
-            launch_trsm_rows(a.rows + static_cast<long>(k) * EGX_NB, a.ld_rows, Lkk, ld,
-                             c->Dinv + static_cast<long>(k) * 4096, Pk, a.slabs64, sp);
-        }
-        if (tri == 0) break;
-        if (la) cudaEventRecord(c->ev_panel[k], sp);
-        // ---- trailing update (k) ---------------------------------------------------
-        GemmArgs g;
-        g.A = Pk;
-        g.lda = EGX_NB;
-        if (a.factor) {
-            g.C = c->M + static_cast<long>(k + 1) * EGX_NB * ld + static_cast<long>(k + 1) * EGX_NB;
-            g.ldc = ld;
-            g.B = Pk;
-            g.ldb = EGX_NB;
-        } else {
-            g.C = a.rows + static_cast<long>(k + 1) * EGX_NB;
-            g.ldc = a.ld_rows;
-            g.B = Lkk + static_cast<long>(EGX_NB) * ld;
-            g.ldb = ld;
-        }
-        if (!la) {
-            g.tri = a.factor ? tri : 0;
-            g.Mt = a.factor ? tri + Qt : a.row_tiles;
-            g.Nt = tri;
-            StageScope sc(c, EGX_STAGE_SYRK_GEMM, 1, sb);
-            launch_gemm_nt_sub(g, sb);
-            continue;
-        }
-        // part A: block column k+1 only (what panel k+1 needs), on the panel stream
-        if (k > 0) cudaStreamWaitEvent(sp, c->ev_bulk[k - 1], 0);
-        {
-            GemmArgs ga = g;
-            ga.tri = 0;
-            ga.Mt = a.factor ? tri + Qt : a.row_tiles;
-            ga.Nt = 1;
-            StageScope sc(c, EGX_STAGE_GEMM_LOOKAHEAD, 1, sp);
-            launch_gemm_nt_sub(ga, sp);
-        }
-        // part B: block columns k+2.., on the bulk stream
-        cudaStreamWaitEvent(sb, c->ev_panel[k], 0);
-        if (tri > 1) {
-            GemmArgs gb = g;
-            if (a.factor) {
-                gb.C = g.C + static_cast<long>(EGX_NB) * ld + EGX_NB;
-                gb.A = Pk + static_cast<long>(EGX_NB) * EGX_NB;
-                gb.B = Pk + static_cast<long>(EGX_NB) * EGX_NB;
-                gb.tri = tri - 1;
-                gb.Mt = tri - 1 + Qt;
-                gb.Nt = tri - 1;
-            } else {
-                gb.C = g.C + EGX_NB;
-                gb.B = g.B + static_cast<long>(EGX_NB) * ld;
-                gb.tri = 0;
-                gb.Mt = a.row_tiles;
-                gb.Nt = tri - 1;
-            }
-            StageScope sc(c, EGX_STAGE_SYRK_GEMM, 1, sb);
-            launch_gemm_nt_sub(gb, sb);
-        }
-        cudaEventRecord(c->ev_bulk[k], sb);
-    }
-    if (la) {
-        cudaEventRecord(c->ev_join, sp);
-        cudaStreamWaitEvent(sb, c->ev_join, 0);
-    }
+FactorRef factor_ref(egx_gp_ctx* c) {
+    FactorRef f;
+    f.M = c->M;
+    f.ld = c->ld;
+    f.T = c->npad / EGX_NB;
+    f.qpad = c->qpad;
+    f.Dinv = c->Dinv;
+    f.info = c->info;
+    return f;
 }
 
-void cholesky(egx_gp_ctx* c) {
-    SweepArgs a;
-    a.factor = true;
-    a.rows = c->M;
-    a.ld_rows = c->ld;
-    a.row_tiles = 0;
-    a.slabs64 = 0;
-    blocked_sweep(c, a);
-}
+void cholesky(egx_gp_ctx* c) { blocked_sweep(c->env, factor_ref(c), true, nullptr, 0, 0, 0); }
 
 // Condition-number test of gp/src/algorithm.rs:1010-1027 on the p x p factor G (host, O(p^3)).
 int cond_status(egx_gp_ctx* c, const double* G) {
@@ -433,7 +276,7 @@ int evaluate_small_batch(egx_gp_ctx* c, const double* thetas, int B, double* rlf
     EGX_CUDA_TRY(cudaMemcpyAsync(c->sb_thetas, c->sb_thetas_h, static_cast<size_t>(B) * c->h * sizeof(double),
                                  cudaMemcpyHostToDevice, c->stream));
     {
-        StageScope sc(c, EGX_STAGE_SMALL_BATCH);
+        StageScope sc(c->env.prof, EGX_STAGE_SMALL_BATCH, 1, c->stream);
         launch_small_batch(c->corr, c->X, c->n, c->d, c->W_dev, c->h, c->sb_thetas, B, c->FyT, c->ld, c->p,
                            1.0 + c->nugget, c->sb_out, c->sb_G, c->stream);
     }
@@ -470,7 +313,7 @@ int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
     if (st != EGX_OK) return st;
     cholesky(c);
     {
-        StageScope sc(c, EGX_STAGE_GLS);
+        StageScope sc(c->env.prof, EGX_STAGE_GLS, 1, c->stream);
         launch_gls(c->M, c->ld, c->n, c->npad, c->p, c->glswork, c->G, c->beta, c->rho, c->res, c->info, c->stream);
     }
     EGX_CUDA_TRY(cudaMemcpyAsync(c->res_h, c->res, sizeof(EvalResult), cudaMemcpyDeviceToHost, c->stream));
@@ -503,14 +346,7 @@ int ensure_predict_buffers(egx_gp_ctx* c, int mb) {
     EGX_CUDA_TRY(cudaMalloc(&c->xchunk, static_cast<size_t>(mb) * c->d * sizeof(double)));
     EGX_CUDA_TRY(cudaMalloc(&c->ychunk, static_cast<size_t>(mb) * sizeof(double)));
     EGX_CUDA_TRY(cudaMalloc(&c->vchunk, static_cast<size_t>(mb) * sizeof(double)));
-    if (static_cast<long>(mb) > c->p_rows) {
-        for (int i = 0; i < 2; ++i) {
-            cudaFree(c->P2[i]);
-            c->P2[i] = nullptr;
-            EGX_CUDA_TRY(cudaMalloc(&c->P2[i], static_cast<size_t>(mb) * EGX_NB * sizeof(double)));
-        }
-        c->p_rows = mb;
-    }
+    if (c->env.ensure_panel_rows(mb) != EGX_OK) return EGX_CUDA_ERROR;
     c->mb_alloc = mb;
     return EGX_OK;
 }
@@ -523,7 +359,7 @@ int predict_chunk_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, 
     const bool want_var = (var_dev != nullptr);
     double* Ybuf = (want_var || c_out_dev != nullptr) ? c->Y : nullptr;
     {
-        StageScope sc(c, EGX_STAGE_CROSS_CORR);
+        StageScope sc(c->env.prof, EGX_STAGE_CROSS_CORR, 1, c->stream);
         launch_cross_corr(c->corr, x_dev, m, mpad, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d, c->terms,
                           c->nterms, c->rho /* = gamma after finalize */, c->beta, c->basis_i, c->basis_j, c->p,
                           c->y_mean, c->y_std, Ybuf, c->npad, y_dev, c->stream);
@@ -534,17 +370,9 @@ int predict_chunk_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, 
                                        static_cast<size_t>(c->n) * sizeof(double), m, cudaMemcpyDeviceToDevice,
                                        c->stream));
     if (!want_var) return EGX_OK;
+    blocked_sweep(c->env, factor_ref(c), false, c->Y, c->npad, mpad / EGX_NB, mpad / 64);
     {
-        SweepArgs a;
-        a.factor = false;
-        a.rows = c->Y;
-        a.ld_rows = c->npad;
-        a.row_tiles = mpad / EGX_NB;
-        a.slabs64 = mpad / 64;
-        blocked_sweep(c, a);
-    }
-    {
-        StageScope sc(c, EGX_STAGE_VAR_FINISH);
+        StageScope sc(c->env.prof, EGX_STAGE_VAR_FINISH, 1, c->stream);
         launch_var_finish(c->Y, c->npad, m, c->npad, x_dev, c->x_mean, c->x_std, c->d,
                           c->M + static_cast<long>(c->npad) * c->ld, c->ld, c->G, c->p, c->basis_i, c->basis_j,
                           c->sigma2_scaled, var_dev, c->stream);
@@ -601,11 +429,6 @@ void free_ctx(egx_gp_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (auto& ev : c->pending) {
-        cudaEventDestroy(ev.a);
-        cudaEventDestroy(ev.b);
-    }
-    for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->timer_a) cudaEventDestroy(c->timer_a);
     if (c->timer_b) cudaEventDestroy(c->timer_b);
     cudaFree(c->X);
@@ -625,13 +448,6 @@ void free_ctx(egx_gp_ctx* c) {
     cudaFreeHost(c->sb_G_h);
     cudaFreeHost(c->sb_thetas_h);
     cudaFree(c->Dinv);
-    cudaFree(c->P2[0]);
-    cudaFree(c->P2[1]);
-    for (auto e : c->ev_panel) cudaEventDestroy(e);
-    for (auto e : c->ev_bulk) cudaEventDestroy(e);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->stream_panel) cudaStreamDestroy(c->stream_panel);
     cudaFree(c->glswork);
     cudaFree(c->G);
     cudaFree(c->beta);
@@ -646,7 +462,7 @@ void free_ctx(egx_gp_ctx* c) {
     cudaFreeHost(c->res_h);
     cudaFreeHost(c->G_h);
     cudaFreeHost(c->beta_h);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    c->env.destroy();
     delete c;
 }
 
@@ -716,7 +532,11 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
         }                                                                             \
     } while (0)
 
-    EGX_CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (c->env.init(c->npad / EGX_NB) != EGX_OK) {
+        free_ctx(c);
+        return EGX_CUDA_ERROR;
+    }
+    c->stream = c->env.sb;
     const size_t xbytes = static_cast<size_t>(c->npad) * d * sizeof(double);
     EGX_CREATE_TRY(cudaMalloc(&c->X, xbytes));
     EGX_CREATE_TRY(cudaMemsetAsync(c->X, 0, xbytes, c->stream));
@@ -742,24 +562,9 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
     EGX_CREATE_TRY(cudaMalloc(&c->M, mbytes));
     EGX_CREATE_TRY(cudaMemsetAsync(c->M, 0, mbytes, c->stream));
     EGX_CREATE_TRY(cudaMalloc(&c->Dinv, static_cast<size_t>(c->npad / EGX_NB) * 4096 * sizeof(double)));
-    c->p_rows = c->rows_total;
-    for (int i = 0; i < 2; ++i)
-        EGX_CREATE_TRY(cudaMalloc(&c->P2[i], static_cast<size_t>(c->p_rows) * EGX_NB * sizeof(double)));
-    {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        EGX_CREATE_TRY(cudaStreamCreateWithPriority(&c->stream_panel, cudaStreamNonBlocking, hi));
-        const int T = c->npad / EGX_NB;
-        c->ev_panel.resize(T);
-        c->ev_bulk.resize(T);
-        for (int k = 0; k < T; ++k) {
-            EGX_CREATE_TRY(cudaEventCreateWithFlags(&c->ev_panel[k], cudaEventDisableTiming));
-            EGX_CREATE_TRY(cudaEventCreateWithFlags(&c->ev_bulk[k], cudaEventDisableTiming));
-        }
-        EGX_CREATE_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        EGX_CREATE_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-        const char* e = getenv("EGX_LOOKAHEAD");
-        c->lookahead = !(e != nullptr && atoi(e) == 0);
+    if (c->env.ensure_panel_rows(c->rows_total) != EGX_OK) {
+        free_ctx(c);
+        return EGX_CUDA_ERROR;
     }
     EGX_CREATE_TRY(cudaMalloc(&c->glswork, static_cast<size_t>(c->q) * c->npad * sizeof(double)));
     EGX_CREATE_TRY(cudaMalloc(&c->G, static_cast<size_t>(p) * p * sizeof(double)));
@@ -826,7 +631,7 @@ extern "C" int egx_gp_finalize(egx_gp_ctx* c, const double* theta, double* rlf, 
     const int T = c->npad / EGX_NB;
     for (int k = T - 1; k >= 0; --k) {
         const double* Lkk = c->M + static_cast<long>(k) * EGX_NB * c->ld + static_cast<long>(k) * EGX_NB;
-        StageScope sc(c, EGX_STAGE_BACKSOLVE, k > 0 ? 2 : 1);
+        StageScope sc(c->env.prof, EGX_STAGE_BACKSOLVE, k > 0 ? 2 : 1, c->stream);
         launch_backsolve_diag(Lkk, c->ld, c->rho + k * EGX_NB, c->stream);
         if (k > 0)
             launch_backsolve_update(c->M + static_cast<long>(k) * EGX_NB * c->ld, c->ld, c->rho + k * EGX_NB, c->rho,
@@ -941,24 +746,21 @@ extern "C" int egx_gp_cross_correlation(egx_gp_ctx* c, const double* x, int m, d
 extern "C" int egx_gp_set_profiling(egx_gp_ctx* c, int enabled) {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
-    c->profiling = enabled != 0;
+    c->env.prof.on = enabled != 0;
     return EGX_OK;
 }
 extern "C" int egx_gp_reset_profile(egx_gp_ctx* c) {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
-    for (int i = 0; i < EGX_NUM_STAGES; ++i) {
-        c->stage_ms[i] = 0.0;
-        c->stage_launches[i] = 0;
-    }
+    c->env.prof.reset();
     return EGX_OK;
 }
 extern "C" int egx_gp_get_profile(egx_gp_ctx* c, double* ms, long long* launches) {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     for (int i = 0; i < EGX_NUM_STAGES; ++i) {
-        if (ms) ms[i] = c->stage_ms[i];
-        if (launches) launches[i] = c->stage_launches[i];
+        if (ms) ms[i] = c->env.prof.ms[i];
+        if (launches) launches[i] = c->env.prof.launches[i];
     }
     return EGX_OK;
 }

@@ -325,9 +325,11 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
 
     int tr, tc;
     gemm_tile_decode<BN>(g, blockIdx.x, tr, tc);
-    const double* Ag = g.A + static_cast<long>(tr) * EGX_NB * g.lda;
-    const double* Bg = g.B + static_cast<long>(tc) * BN * g.ldb;
-    double* Cg = g.C + static_cast<long>(tr) * EGX_NB * g.ldc + static_cast<long>(tc) * BN;
+    const long koff = static_cast<long>(blockIdx.y) * g.K;      // split-K slice
+    const double* Ag = g.A + static_cast<long>(tr) * EGX_NB * g.lda + koff;
+    const double* Bg = g.B + static_cast<long>(tc) * BN * g.ldb + koff;
+    double* Cg = g.C + static_cast<long>(blockIdx.y) * g.split_c_stride + static_cast<long>(tr) * EGX_NB * g.ldc +
+                 static_cast<long>(tc) * BN;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -351,10 +353,11 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
         }
     };
 
-    constexpr int KB = GM_K / GM_BK;   // 8
+    const int KB = g.K / GM_BK;
+    const double sgn = g.add ? 1.0 : -1.0;
 #pragma unroll
     for (int s = 0; s < GM_STAGES - 1; ++s) {
-        load_stage(s, s);
+        if (s < KB) load_stage(s, s);
         cp_async_commit();
     }
 
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
         for (int kk = 0; kk < GM_BK / 4; ++kk) {
             double a[MI], b[NI];
 #pragma unroll
-            for (int mi = 0; mi < MI; ++mi) a[mi] = -as[mi * 8 * GM_LDS + kk * 4];
+            for (int mi = 0; mi < MI; ++mi) a[mi] = sgn * as[mi * 8 * GM_LDS + kk * 4];
 #pragma unroll
             for (int ni = 0; ni < NI; ++ni) b[ni] = bs[ni * 8 * GM_LDS + kk * 4];
 #pragma unroll
@@ -448,6 +451,7 @@ void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s) {
     if (g.tri > 0) tiles = S * g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * S * g.tri;
     else tiles = g.Mt * S * g.Nt;
     if (tiles <= 0) return;
-    if (S == 1) gemm_nt_sub_kernel<128><<<tiles, 256, smem128, s>>>(g);
-    else gemm_nt_sub_kernel<64><<<tiles, 256, smem64, s>>>(g);
+    const dim3 grid(tiles, g.splits > 1 ? g.splits : 1);
+    if (S == 1) gemm_nt_sub_kernel<128><<<grid, 256, smem128, s>>>(g);
+    else gemm_nt_sub_kernel<64><<<grid, 256, smem64, s>>>(g);
 }

@@ -122,7 +122,7 @@ __device__ __forceinline__ void tri_decode(int t, int& r, int& c) {
 template <int CORR>
 __global__ void __launch_bounds__(256)
     corr_build_kernel(const double* __restrict__ X, int n, int d, const CorrTerm* __restrict__ gterms,
-                      int nterms, double* __restrict__ M, long ld, double diag_value) {
+                      int nterms, double* __restrict__ M, long ld, double diag_value, double scale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* Xi = reinterpret_cast<double*>(smem_raw + 16);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int cj = 0; cj < 2; ++cj) {
             const int j = j0 + 2 * tx + 32 * cj;
-            double a = v[ri][2 * cj], b = v[ri][2 * cj + 1];
+            double a = scale * v[ri][2 * cj], b = scale * v[ri][2 * cj + 1];
             if (i >= n || j >= n) a = 0.0;
             if (i >= n || j + 1 >= n) b = 0.0;
             if (i == j) a = (i < n) ? diag_value : 1.0;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256)
                       const CorrTerm* __restrict__ gterms, int nterms, const double* __restrict__ gamma,
                       const double* __restrict__ beta, const int* __restrict__ basis_i,
                       const int* __restrict__ basis_j, int p, double y_mean, double y_std,
-                      double* __restrict__ Y, long ldy, double* __restrict__ yout) {
+                      double* __restrict__ Y, long ldy, double* __restrict__ yout, double scale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* Xp = reinterpret_cast<double*>(smem_raw + 16);
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
             for (int cj = 0; cj < 2; ++cj) {
                 const int jl = 2 * tx + 32 * cj;
-                double a = v[ri][2 * cj], b = v[ri][2 * cj + 1];
+                double a = scale * v[ri][2 * cj], b = scale * v[ri][2 * cj + 1];
                 if (i >= m || j0 + jl >= n) a = 0.0;
                 if (i >= m || j0 + jl + 1 >= n) b = 0.0;
                 yacc[ri] += a * gam[jl] + b * gam[jl + 1];
@@ -302,13 +302,13 @@ void set_smem(K kernel, size_t bytes) {
 }  // namespace
 
 void launch_corr_build(int corr, const double* X, int n, int npad, int d, const CorrTerm* terms, int nterms,
-                       double* M, long ld, double diag_value, cudaStream_t s) {
+                       double* M, long ld, double diag_value, cudaStream_t s, double scale) {
     const int T = npad / EGX_NB;
     const int grid = 4 * (T * (T + 1) / 2);
     const size_t smem = corr_build_smem(d, nterms);
 #define EGX_LAUNCH_K1(CK)                                                                         \
     set_smem(corr_build_kernel<CK>, smem);                                                        \
-    corr_build_kernel<CK><<<grid, 256, smem, s>>>(X, n, d, terms, nterms, M, ld, diag_value);
+    corr_build_kernel<CK><<<grid, 256, smem, s>>>(X, n, d, terms, nterms, M, ld, diag_value, scale);
     switch (corr) {
         case EGX_CORR_SQUARED_EXPONENTIAL: EGX_LAUNCH_K1(EGX_CORR_SQUARED_EXPONENTIAL) break;
         case EGX_CORR_ABSOLUTE_EXPONENTIAL: EGX_LAUNCH_K1(EGX_CORR_ABSOLUTE_EXPONENTIAL) break;
@@ -321,13 +321,13 @@ void launch_corr_build(int corr, const double* X, int n, int npad, int d, const 
 void launch_cross_corr(int corr, const double* xraw, int m, int mpad, const double* x_mean, const double* x_std,
                        const double* X, int n, int npad, int d, const CorrTerm* terms, int nterms,
                        const double* gamma, const double* beta, const int* basis_i, const int* basis_j, int p,
-                       double y_mean, double y_std, double* Y, long ldy, double* yout, cudaStream_t s) {
+                       double y_mean, double y_std, double* Y, long ldy, double* yout, cudaStream_t s, double scale) {
     const int grid = mpad / EGX_CT;
     const size_t smem = cross_corr_smem(d, nterms);
 #define EGX_LAUNCH_K2(CK)                                                                               \
     set_smem(cross_corr_kernel<CK>, smem);                                                              \
     cross_corr_kernel<CK><<<grid, 256, smem, s>>>(xraw, m, x_mean, x_std, X, n, npad, d, terms, nterms, \
-                                                  gamma, beta, basis_i, basis_j, p, y_mean, y_std, Y, ldy, yout);
+                                                  gamma, beta, basis_i, basis_j, p, y_mean, y_std, Y, ldy, yout, scale);
     switch (corr) {
         case EGX_CORR_SQUARED_EXPONENTIAL: EGX_LAUNCH_K2(EGX_CORR_SQUARED_EXPONENTIAL) break;
         case EGX_CORR_ABSOLUTE_EXPONENTIAL: EGX_LAUNCH_K2(EGX_CORR_ABSOLUTE_EXPONENTIAL) break;

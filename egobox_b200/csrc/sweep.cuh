@@ -1,0 +1,64 @@
+// Host-side execution helpers shared by the dense-GP and sparse-GP contexts:
+// stage profiler (CUDA events on the launching stream), the two-stream sweep environment and the
+// blocked "solve block column k, update the trailing columns" sweep (Cholesky factorisation and
+// multi-RHS triangular solve).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/egobox_gpu.h"
+
+struct ProfEvent {
+    cudaEvent_t a, b;
+    int stage;
+};
+
+struct Profiler {
+    bool on = false;
+    std::vector<ProfEvent> pending;
+    std::vector<cudaEvent_t> pool;
+    double ms[EGX_NUM_STAGES] = {0};
+    long long launches[EGX_NUM_STAGES] = {0};
+    void resolve();
+    void reset();
+    void destroy();
+};
+
+struct StageScope {
+    Profiler* p;
+    ProfEvent ev;
+    bool on;
+    cudaStream_t st;
+    StageScope(Profiler& prof, int stage, int launches, cudaStream_t stream);
+    ~StageScope();
+};
+
+struct SweepEnv {
+    cudaStream_t sb = nullptr;   // bulk stream
+    cudaStream_t sp = nullptr;   // high-priority panel / look-ahead stream
+    bool lookahead = true;
+    std::vector<cudaEvent_t> ev_panel, ev_bulk;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    double* P2[2] = {nullptr, nullptr};   // double-buffered contiguous panel copies (rows x 128)
+    long p_rows = 0;
+    Profiler prof;
+    int init(int max_block_cols);
+    int ensure_panel_rows(long rows);
+    void destroy();
+};
+
+// A lower-triangular factor stored as 128-blocks in a row-major matrix (ld), T block columns,
+// optionally followed by `qpad` appended right-hand-side rows (factor sweeps only).
+struct FactorRef {
+    double* M;
+    long ld;
+    int T;
+    int qpad;
+    double* Dinv;   // [T][4][32][32]
+    int* info;
+};
+
+// factor = true : in-place Cholesky of f.M (+ appended rows become (L^-1 B)^T)
+// factor = false: rows (row_tiles*128 x T*128, ld_rows) <- rows * L^-T using the factor f
+void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows, long ld_rows, int row_tiles,
+                   int slabs64);
