@@ -10,3 +10,5 @@ from .gp import (GaussianProcess, GpParams, Kriging, ThetaTuning, GpError, Linal
                  SquaredExponentialCorr, AbsoluteExponentialCorr, Matern32Corr, Matern52Corr,
                  ConstantMean, LinearMean, QuadraticMean)
 from .gpx import Gpx, GpMix, RegressionSpec, CorrelationSpec, Recombination  # noqa: F401
+from .sgp import (SparseGaussianProcess, SgpParams, SparseKriging, SgpContext, ParamTuning, Inducings,  # noqa: F401
+                  SparseMethod, SparseGpx, SparseGpMix)

@@ -85,6 +85,48 @@ SIGNATURES.update({
     "egx_prepare_multistart": (C.c_int, [C.c_int, _dp, _dp, C.c_int, C.c_ulonglong, _dp]),
 })
 
+
+
+class SgpParamsStruct(C.Structure):
+    """egx_sgp_params (include/egobox_gpu.h)."""
+    _fields_ = [("corr", C.c_int), ("method", C.c_int), ("theta_fixed", C.c_int),
+                ("theta_init", _dp), ("n_theta_init", C.c_int),
+                ("theta_bounds", _dp), ("n_theta_bounds", C.c_int),
+                ("noise_fixed", C.c_int), ("noise_init", C.c_double), ("noise_lo", C.c_double),
+                ("noise_hi", C.c_double), ("z", _dp), ("n_inducings", C.c_int),
+                ("n_start", C.c_int), ("max_eval", C.c_int), ("nugget", C.c_double),
+                ("w_star", _dp), ("kpls_dim", C.c_int), ("device", C.c_int), ("seed", C.c_ulonglong),
+                ("cobyla_rhobeg", C.c_double), ("cobyla_ftol_rel", C.c_double)]
+
+
+_sp = C.POINTER(SgpParamsStruct)
+_llp = C.POINTER(C.c_longlong)
+SIGNATURES.update({
+    "egx_sgp_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp, _dp, C.c_int,
+                                 _dp, C.c_int, C.c_double]),
+    "egx_sgp_destroy": (None, [_vp]),
+    "egx_sgp_reduced_likelihood": (C.c_int, [_vp, _dp, C.c_double, C.c_double, _dp]),
+    "egx_sgp_finalize": (C.c_int, [_vp, _dp, C.c_double, C.c_double, _dp, _dp, _dp]),
+    "egx_sgp_predict": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_sgp_predict_var": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_sgp_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "egx_sgp_get_profile": (C.c_int, [_vp, _dp, _llp]),
+    "egx_sgp_params_default": (None, [_sp]),
+    "egx_sgp_fit": (C.c_int, [_sp, _dp, C.c_int, C.c_int, _dp, C.POINTER(_vp)]),
+    "egx_sgp_model_destroy": (None, [_vp]),
+    "egx_sgp_model_dims": (C.c_int, [_vp, _ip, _ip, _ip, _ip]),
+    "egx_sgp_model_theta": (C.c_int, [_vp, _dp]),
+    "egx_sgp_model_variance": (C.c_double, [_vp]),
+    "egx_sgp_model_noise_variance": (C.c_double, [_vp]),
+    "egx_sgp_model_likelihood": (C.c_double, [_vp]),
+    "egx_sgp_model_n_evals": (C.c_longlong, [_vp]),
+    "egx_sgp_model_inducings": (C.c_int, [_vp, _dp]),
+    "egx_sgp_model_woodbury": (C.c_int, [_vp, _dp, _dp]),
+    "egx_sgp_model_context": (_vp, [_vp]),
+    "egx_sgp_model_predict": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_sgp_model_predict_var": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+})
+
 _lib = None
 
 

@@ -137,48 +137,10 @@ namespace {
 void resolve_profile(egx_gp_ctx* c) { c->env.prof.resolve(); }
 
 int build_terms(egx_gp_ctx* c, const double* theta) {
-    const int d = c->d, h = c->h;
-    int nt = 0;
-    CorrTerm* t = c->terms_h;
-    const double* w = c->w_star.data();
-    if (c->corr == EGX_CORR_SQUARED_EXPONENTIAL || c->corr == EGX_CORR_ABSOLUTE_EXPONENTIAL) {
-        for (int j = 0; j < d; ++j) {
-            double s = 0.0;
-            for (int l = 0; l < h; ++l) {
-                if (c->corr == EGX_CORR_SQUARED_EXPONENTIAL) {
-                    const double v = theta[l] * w[j * h + l];
-                    s += v * v;
-                } else {
-                    s += std::fabs(w[j * h + l]) * theta[l];
-                }
-            }
-            if (s != 0.0) {
-                t[nt].dim = j;
-                t[nt].pad_ = 0;
-                t[nt].k1 = s;
-                t[nt].k2 = 0.0;
-                t[nt].k3 = 0.0;
-                ++nt;
-            }
-        }
-    } else {
-        const double sq = (c->corr == EGX_CORR_MATERN32) ? std::sqrt(3.0) : std::sqrt(5.0);
-        for (int j = 0; j < d; ++j)
-            for (int l = 0; l < h; ++l) {
-                const double tw = theta[l] * std::fabs(w[j * h + l]);
-                if (tw != 0.0) {
-                    t[nt].dim = j;
-                    t[nt].pad_ = 0;
-                    t[nt].k1 = tw;
-                    t[nt].k2 = sq * tw;
-                    t[nt].k3 = tw * tw;
-                    ++nt;
-                }
-            }
-    }
-    c->nterms = nt;
-    if (nt > 0)
-        EGX_CUDA_TRY(cudaMemcpyAsync(c->terms, c->terms_h, nt * sizeof(CorrTerm), cudaMemcpyHostToDevice, c->stream));
+    c->nterms = egx_fill_terms(c->corr, c->d, c->h, c->w_star.data(), theta, c->terms_h);
+    if (c->nterms > 0)
+        EGX_CUDA_TRY(cudaMemcpyAsync(c->terms, c->terms_h, c->nterms * sizeof(CorrTerm), cudaMemcpyHostToDevice,
+                                     c->stream));
     return EGX_OK;
 }
 
@@ -628,15 +590,7 @@ extern "C" int egx_gp_finalize(egx_gp_ctx* c, const double* theta, double* rlf, 
     if (rlf) *rlf = v;
     if (st != EGX_OK) return st;
     // gamma = L^-T rho, blocked back substitution (algorithm.rs:1034)
-    const int T = c->npad / EGX_NB;
-    for (int k = T - 1; k >= 0; --k) {
-        const double* Lkk = c->M + static_cast<long>(k) * EGX_NB * c->ld + static_cast<long>(k) * EGX_NB;
-        StageScope sc(c->env.prof, EGX_STAGE_BACKSOLVE, k > 0 ? 2 : 1, c->stream);
-        launch_backsolve_diag(Lkk, c->ld, c->rho + k * EGX_NB, c->stream);
-        if (k > 0)
-            launch_backsolve_update(c->M + static_cast<long>(k) * EGX_NB * c->ld, c->ld, c->rho + k * EGX_NB, c->rho,
-                                    k, c->stream);
-    }
+    backsolve_vector(c->env, factor_ref(c), c->rho);
     if (gamma) EGX_CUDA_TRY(cudaMemcpyAsync(gamma, c->rho, c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     std::vector<double> ftT;
     if (ft) {

@@ -772,3 +772,246 @@ extern "C" int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_predict_valvar(m->ctx, x, npts, y, var);
 }
+
+
+// ============================================================================================
+// Sparse GP fit driver: impl Fit for SgpValidParams, sparse_algorithm.rs:416-648.
+// Optimisation variables = log10 of [theta_1..theta_h, sigma2, (noise)].
+// ============================================================================================
+struct egx_sgp_model {
+    egx_sgp_ctx* ctx = nullptr;
+    int n = 0, d = 0, h = 0, m = 0;
+    std::vector<double> theta, z;
+    double sigma2 = NAN, noise = NAN, likelihood = NAN;
+    long long n_evals = 0;
+};
+
+extern "C" void egx_sgp_params_default(egx_sgp_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->corr = EGX_CORR_SQUARED_EXPONENTIAL;
+    p->method = EGX_SGP_FITC;
+    p->noise_init = 1e-2;                                   // sparse_parameters.rs:25-32
+    p->noise_lo = 100.0 * 2.220446049250313e-16;
+    p->noise_hi = 1e10;
+    p->n_inducings = 10;                                    // Inducings::Randomized(10), :44-48
+    p->n_start = 10;
+    p->max_eval = 1000;
+    p->nugget = 100.0 * 2.220446049250313e-16;
+    p->seed = 42;
+    p->cobyla_rhobeg = 0.5;
+    p->cobyla_ftol_rel = 1e-4;
+}
+
+extern "C" void egx_sgp_model_destroy(egx_sgp_model* m) {
+    if (!m) return;
+    if (m->ctx) egx_sgp_destroy(m->ctx);
+    delete m;
+}
+
+extern "C" int egx_sgp_fit(const egx_sgp_params* prm, const double* x, int n, int d, const double* y,
+                           egx_sgp_model** out) {
+    if (!out) return EGX_INVALID_VALUE;
+    *out = nullptr;
+    if (!prm || !x || !y || n < 2 || d < 1) {
+        egx_set_error("egx_sgp_fit: invalid argument");
+        return EGX_INVALID_VALUE;
+    }
+    const bool kpls = prm->w_star != nullptr;
+    if (kpls && (prm->kpls_dim < 1 || prm->kpls_dim > d)) {
+        egx_set_error("Dimension reduction %d should be smaller than actual training input dimensions %d",
+                      prm->kpls_dim, d);
+        return EGX_INVALID_VALUE;
+    }
+    const int h = kpls ? prm->kpls_dim : d;
+    std::unique_ptr<egx_sgp_model, void (*)(egx_sgp_model*)> m(new egx_sgp_model(), egx_sgp_model_destroy);
+    m->n = n;
+    m->d = d;
+    m->h = h;
+    std::vector<double> w;
+    if (kpls) w.assign(prm->w_star, prm->w_star + static_cast<size_t>(d) * h);
+    else {
+        w.assign(static_cast<size_t>(d) * d, 0.0);
+        for (int j = 0; j < d; ++j) w[static_cast<size_t>(j) * d + j] = 1.0;
+    }
+    Xoshiro256Plus rng(prm->seed);
+    // inducing points (:455-458, make_inducings :833-847)
+    if (prm->z != nullptr) {
+        m->m = prm->n_inducings;
+        m->z.assign(prm->z, prm->z + static_cast<size_t>(m->m) * d);
+    } else {
+        std::vector<int> idx(n);
+        for (int i = 0; i < n; ++i) idx[i] = i;
+        for (int i = n - 1; i > 0; --i) std::swap(idx[i], idx[rng.below(i + 1)]);
+        m->m = std::min(prm->n_inducings, n);
+        m->z.resize(static_cast<size_t>(m->m) * d);
+        for (int r = 0; r < m->m; ++r)
+            for (int j = 0; j < d; ++j) m->z[static_cast<size_t>(r) * d + j] = x[static_cast<size_t>(idx[r]) * d + j];
+    }
+    if (m->m < 1) {
+        egx_set_error("egx_sgp_fit: no inducing points");
+        return EGX_INVALID_VALUE;
+    }
+    int st = egx_sgp_create(&m->ctx, prm->device, prm->corr, prm->method, x, n, d, y, m->z.data(), m->m, w.data(), h,
+                            prm->nugget);
+    if (st != EGX_OK) return st;
+
+    const bool noise_est = !prm->noise_fixed;
+    // theta0 (:476-488)
+    std::vector<double> theta0(h);
+    const int n_init = (prm->theta_init != nullptr) ? prm->n_theta_init : 0;
+    if (n_init == 0) std::fill(theta0.begin(), theta0.end(), 0.1);
+    else if (n_init == 1) std::fill(theta0.begin(), theta0.end(), prm->theta_init[0]);
+    else if (n_init == h) theta0.assign(prm->theta_init, prm->theta_init + h);
+    else {
+        egx_set_error("Initial guess for theta should be either 1-dim or dim of xtrain (w_star.ncols()), got %d", n_init);
+        return EGX_INVALID_VALUE;
+    }
+    // sigma2_0 = var(y, ddof = 1)  (:491-492)
+    double mean = 0.0;
+    for (int i = 0; i < n; ++i) mean += y[i];
+    mean /= n;
+    double var = 0.0;
+    for (int i = 0; i < n; ++i) var += (y[i] - mean) * (y[i] - mean);
+    const double sigma2_0 = var / (n - 1);
+    const int np = h + 1 + (noise_est ? 1 : 0);
+    std::vector<double> p0(np);
+    for (int i = 0; i < h; ++i) p0[i] = theta0[i];
+    p0[h] = sigma2_0;
+    if (noise_est) p0[np - 1] = prm->noise_init;
+    // bounds (:544-577): theta bounds broadcast to every parameter, then variance and noise overrides
+    std::vector<double> lo(np), hi(np);
+    {
+        double blo = 1e-2, bhi = 1e2;                       // sparse_parameters.rs:160-163
+        const int nb = (prm->theta_bounds != nullptr) ? prm->n_theta_bounds : 0;
+        if (prm->theta_fixed) {
+            for (int i = 0; i < np; ++i) {
+                const double v = (i < h) ? theta0[i] : theta0[0];
+                lo[i] = hi[i] = std::log10(v);
+            }
+        } else if (nb <= 1) {
+            if (nb == 1) {
+                blo = prm->theta_bounds[0];
+                bhi = prm->theta_bounds[1];
+            }
+            for (int i = 0; i < np; ++i) {
+                lo[i] = std::log10(blo);
+                hi[i] = std::log10(bhi);
+            }
+        } else if (nb == np) {
+            for (int i = 0; i < np; ++i) {
+                lo[i] = std::log10(prm->theta_bounds[2 * i]);
+                hi[i] = std::log10(prm->theta_bounds[2 * i + 1]);
+            }
+        } else {
+            egx_set_error("Bounds for theta should be either 1-dim or dim of the parameter vector (%d), got %d", np, nb);
+            return EGX_INVALID_VALUE;
+        }
+        lo[h] = std::log10(1e-12);
+        hi[h] = std::log10(9.0 * sigma2_0);
+        if (noise_est) {
+            lo[np - 1] = std::log10(prm->noise_lo);
+            hi[np - 1] = std::log10(prm->noise_hi);
+        }
+    }
+    // multistart seeds in the (pre-override) log10 box, row 0 = log10(p0)  (:566)
+    const int n_start = std::max(prm->n_start, 0);
+    std::vector<std::vector<double>> starts;
+    {
+        std::vector<double> z0(np);
+        for (int i = 0; i < np; ++i) z0[i] = std::log10(p0[i]);
+        starts.push_back(z0);
+        if (n_start == 1) {
+            std::vector<double> v(np);
+            for (int i = 0; i < np; ++i) v[i] = lo[i] + (hi[i] - lo[i]) * rng.uniform();
+            starts.push_back(v);
+        } else if (n_start > 1) {
+            std::vector<double> pts = lhs_maximin(n_start, np, rng);
+            for (int s = 0; s < n_start; ++s) {
+                std::vector<double> v(np);
+                for (int i = 0; i < np; ++i) v[i] = lo[i] + (hi[i] - lo[i]) * pts[static_cast<size_t>(s) * np + i];
+                starts.push_back(v);
+            }
+        }
+    }
+    const int maxeval = std::min(std::max(10 * std::max(n_init, 1), GP_COBYLA_MIN_EVAL), std::max(prm->max_eval, 1));  // :598-600
+    std::vector<BoundCobyla> chains;
+    for (auto& s0 : starts) chains.emplace_back(s0, lo, hi, prm->cobyla_rhobeg, prm->cobyla_ftol_rel, maxeval);
+    std::vector<double> th(h);
+    auto eval = [&](const std::vector<double>& z, double* lik) {
+        for (int i = 0; i < h; ++i) th[i] = std::pow(10.0, z[i]);
+        const double s2 = std::pow(10.0, z[h]);
+        const double nz = noise_est ? std::pow(10.0, z[np - 1]) : prm->noise_init;
+        return egx_sgp_reduced_likelihood(m->ctx, th.data(), s2, nz, lik);
+    };
+    for (;;) {
+        bool any = false;
+        for (auto& ch : chains) {
+            if (ch.done()) continue;
+            any = true;
+            double lik = NAN;
+            st = eval(ch.ask(), &lik);
+            if (st == EGX_CUDA_ERROR) return st;
+            m->n_evals += 1;
+            double f = (st == EGX_OK) ? -lik : kInf;
+            if (std::isnan(f)) f = kInf;
+            ch.tell(f);
+        }
+        if (!any) break;
+    }
+    double fbest = kInf;
+    std::vector<double> zbest(np, 0.0);
+    for (auto& ch : chains)
+        if (ch.best_f() < fbest) {
+            fbest = ch.best_f();
+            zbest = ch.best_x();
+        }
+    m->theta.resize(h);
+    for (int i = 0; i < h; ++i) m->theta[i] = std::pow(10.0, zbest[i]);
+    m->sigma2 = std::pow(10.0, zbest[h]);
+    m->noise = noise_est ? std::pow(10.0, zbest[np - 1]) : prm->noise_init;
+    double lik = NAN;
+    st = egx_sgp_finalize(m->ctx, m->theta.data(), m->sigma2, m->noise, &lik, nullptr, nullptr);
+    m->n_evals += 1;
+    if (st != EGX_OK) return st;
+    m->likelihood = lik;
+    *out = m.release();
+    return EGX_OK;
+}
+
+extern "C" int egx_sgp_model_dims(const egx_sgp_model* m, int* n, int* d, int* h, int* nz) {
+    if (!m) return EGX_INVALID_VALUE;
+    if (n) *n = m->n;
+    if (d) *d = m->d;
+    if (h) *h = m->h;
+    if (nz) *nz = m->m;
+    return EGX_OK;
+}
+extern "C" int egx_sgp_model_theta(const egx_sgp_model* m, double* theta) {
+    if (!m || !theta) return EGX_INVALID_VALUE;
+    std::memcpy(theta, m->theta.data(), sizeof(double) * m->h);
+    return EGX_OK;
+}
+extern "C" double egx_sgp_model_variance(const egx_sgp_model* m) { return m ? m->sigma2 : NAN; }
+extern "C" double egx_sgp_model_noise_variance(const egx_sgp_model* m) { return m ? m->noise : NAN; }
+extern "C" double egx_sgp_model_likelihood(const egx_sgp_model* m) { return m ? m->likelihood : NAN; }
+extern "C" long long egx_sgp_model_n_evals(const egx_sgp_model* m) { return m ? m->n_evals : 0; }
+extern "C" int egx_sgp_model_inducings(const egx_sgp_model* m, double* z) {
+    if (!m || !z) return EGX_INVALID_VALUE;
+    std::memcpy(z, m->z.data(), sizeof(double) * m->z.size());
+    return EGX_OK;
+}
+extern "C" int egx_sgp_model_woodbury(egx_sgp_model* m, double* w_vec, double* w_inv) {
+    if (!m) return EGX_INVALID_VALUE;
+    double lik;
+    return egx_sgp_finalize(m->ctx, m->theta.data(), m->sigma2, m->noise, &lik, w_vec, w_inv);
+}
+extern "C" egx_sgp_ctx* egx_sgp_model_context(egx_sgp_model* m) { return m ? m->ctx : nullptr; }
+extern "C" int egx_sgp_model_predict(egx_sgp_model* m, const double* x, int npts, double* y) {
+    if (!m) return EGX_INVALID_VALUE;
+    return egx_sgp_predict(m->ctx, x, npts, y);
+}
+extern "C" int egx_sgp_model_predict_var(egx_sgp_model* m, const double* x, int npts, double* var) {
+    if (!m) return EGX_INVALID_VALUE;
+    return egx_sgp_predict_var(m->ctx, x, npts, var);
+}

@@ -1,4 +1,5 @@
 // Implementation of the shared sweep environment (see sweep.cuh).
+#include <cmath>
 #include <cstdlib>
 
 #include "sweep.cuh"
@@ -185,5 +186,54 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
     if (la) {
         cudaEventRecord(env.ev_join, sp);
         cudaStreamWaitEvent(sb, env.ev_join, 0);
+    }
+}
+
+int egx_fill_terms(int corr, int d, int h, const double* w, const double* theta, CorrTerm* t) {
+    int nt = 0;
+    if (corr == EGX_CORR_SQUARED_EXPONENTIAL || corr == EGX_CORR_ABSOLUTE_EXPONENTIAL) {
+        for (int j = 0; j < d; ++j) {
+            double s = 0.0;
+            for (int l = 0; l < h; ++l) {
+                if (corr == EGX_CORR_SQUARED_EXPONENTIAL) {
+                    const double v = theta[l] * w[j * h + l];
+                    s += v * v;
+                } else {
+                    s += std::fabs(w[j * h + l]) * theta[l];
+                }
+            }
+            if (s != 0.0) {
+                t[nt].dim = j;
+                t[nt].pad_ = 0;
+                t[nt].k1 = s;
+                t[nt].k2 = 0.0;
+                t[nt].k3 = 0.0;
+                ++nt;
+            }
+        }
+    } else {
+        const double sq = (corr == EGX_CORR_MATERN32) ? std::sqrt(3.0) : std::sqrt(5.0);
+        for (int j = 0; j < d; ++j)
+            for (int l = 0; l < h; ++l) {
+                const double tw = theta[l] * std::fabs(w[j * h + l]);
+                if (tw != 0.0) {
+                    t[nt].dim = j;
+                    t[nt].pad_ = 0;
+                    t[nt].k1 = tw;
+                    t[nt].k2 = sq * tw;
+                    t[nt].k3 = tw * tw;
+                    ++nt;
+                }
+            }
+    }
+    return nt;
+}
+
+void backsolve_vector(SweepEnv& env, const FactorRef& f, double* v) {
+    for (int k = f.T - 1; k >= 0; --k) {
+        const double* Lkk = f.M + static_cast<long>(k) * EGX_NB * f.ld + static_cast<long>(k) * EGX_NB;
+        StageScope sc(env.prof, EGX_STAGE_BACKSOLVE, k > 0 ? 2 : 1, env.sb);
+        launch_backsolve_diag(Lkk, f.ld, v + k * EGX_NB, env.sb);
+        if (k > 0) launch_backsolve_update(f.M + static_cast<long>(k) * EGX_NB * f.ld, f.ld, v + k * EGX_NB, v, k, env.sb);
     }
 }

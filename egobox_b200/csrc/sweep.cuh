@@ -62,3 +62,10 @@ struct FactorRef {
 // factor = false: rows (row_tiles*128 x T*128, ld_rows) <- rows * L^-T using the factor f
 void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows, long ld_rows, int row_tiles,
                    int slabs64);
+
+// Per-theta kernel weights: (dimension, component) term list consumed by K1/K2 (correlation_models.rs
+// :97-100, 191, 333, 505).  Returns the number of terms written (<= d*h).
+int egx_fill_terms(int corr, int d, int h, const double* w_star, const double* theta, CorrTerm* out);
+
+// gamma-style single-vector back substitution  v <- L^-T v  with the blocked factor f (algorithm.rs:1034)
+void backsolve_vector(SweepEnv& env, const FactorRef& f, double* v);

@@ -236,6 +236,69 @@ int egx_gp_model_predict(egx_gp_model* m, const double* x, int npts, double* y);
 int egx_gp_model_predict_var(egx_gp_model* m, const double* x, int npts, double* var);
 int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int npts, double* y, double* var);
 
+/* ============================================================================
+ * Sparse GP (FITC / VFE) -- crates/gp/src/sparse_algorithm.rs.
+ * No input normalisation, zero mean (as in the reference).  x: N x d raw, y: N,
+ * z: M x d inducing points (Inducings::Located, or drawn by egx_sgp_fit for
+ * Inducings::Randomized :833-847), w_star d x h (identity when h == d).
+ * ========================================================================== */
+#define EGX_SGP_FITC 0   /* SparseMethod::Fitc, sparse_parameters.rs:56 */
+#define EGX_SGP_VFE  1   /* SparseMethod::Vfe */
+typedef struct egx_sgp_ctx egx_sgp_ctx;
+int egx_sgp_create(egx_sgp_ctx** out, int device, int corr, int method, const double* x, int n, int d,
+                   const double* y, const double* z, int m, const double* w_star, int h, double nugget);
+void egx_sgp_destroy(egx_sgp_ctx* ctx);
+/* SgpValidParams::reduced_likelihood (sparse_algorithm.rs:654-673 -> fitc :695-765 / vfe :769-830),
+ * value only.  A failed Cholesky (where the reference `.unwrap()`s) is status EGX_NOT_POSITIVE_DEFINITE. */
+int egx_sgp_reduced_likelihood(egx_sgp_ctx* ctx, const double* theta, double sigma2, double noise, double* lik);
+/* Final evaluation: keeps U = chol(Kmm), L = chol(A) and the Woodbury vector on the device;
+ * w_vec (M) and w_inv (M x M, WoodburyData.inv -- computed only when non-NULL) may be NULL. */
+int egx_sgp_finalize(egx_sgp_ctx* ctx, const double* theta, double sigma2, double noise, double* lik,
+                     double* w_vec, double* w_inv);
+/* predict :237-241, predict_var :245-257 (k^T inv k evaluated by two triangular sweeps, inv never formed) */
+int egx_sgp_predict(egx_sgp_ctx* ctx, const double* x, int m, double* y);
+int egx_sgp_predict_var(egx_sgp_ctx* ctx, const double* x, int m, double* var);
+int egx_sgp_set_profiling(egx_sgp_ctx* ctx, int enabled);
+int egx_sgp_get_profile(egx_sgp_ctx* ctx, double* ms, long long* launches);
+
+/* SgpValidParams (sparse_parameters.rs:71-82, 151-293) + impl Fit (sparse_algorithm.rs:416-648). */
+typedef struct egx_sgp_params {
+    int corr;
+    int method;                  /* EGX_SGP_FITC | EGX_SGP_VFE */
+    int theta_fixed;             /* ThetaTuning::Fixed -> bounds collapse onto init (:470) */
+    const double* theta_init;    /* 1 or theta-dimension values (default 0.1) */
+    int n_theta_init;
+    const double* theta_bounds;  /* 1 (broadcast) or n_params (lo, hi) pairs; default (1e-2, 1e2) */
+    int n_theta_bounds;
+    int noise_fixed;             /* ParamTuning::Fixed(noise_init) vs Optimized{init, bounds} */
+    double noise_init;           /* default 1e-2 */
+    double noise_lo, noise_hi;   /* default (100 eps, 1e10) */
+    const double* z;             /* Inducings::Located (n_inducings x d) or NULL */
+    int n_inducings;             /* Inducings::Randomized(n) when z == NULL (default 10) */
+    int n_start, max_eval;
+    double nugget;
+    const double* w_star;
+    int kpls_dim;
+    int device;
+    unsigned long long seed;
+    double cobyla_rhobeg, cobyla_ftol_rel;
+} egx_sgp_params;
+typedef struct egx_sgp_model egx_sgp_model;
+void egx_sgp_params_default(egx_sgp_params* p);
+int egx_sgp_fit(const egx_sgp_params* params, const double* x, int n, int d, const double* y, egx_sgp_model** out);
+void egx_sgp_model_destroy(egx_sgp_model* m);
+int egx_sgp_model_dims(const egx_sgp_model* m, int* n, int* d, int* h, int* n_inducings);
+int egx_sgp_model_theta(const egx_sgp_model* m, double* theta);
+double egx_sgp_model_variance(const egx_sgp_model* m);        /* sigma2        :262 */
+double egx_sgp_model_noise_variance(const egx_sgp_model* m);  /* noise         :267 */
+double egx_sgp_model_likelihood(const egx_sgp_model* m);
+long long egx_sgp_model_n_evals(const egx_sgp_model* m);
+int egx_sgp_model_inducings(const egx_sgp_model* m, double* z /* n_inducings x d */);
+int egx_sgp_model_woodbury(egx_sgp_model* m, double* w_vec, double* w_inv);
+egx_sgp_ctx* egx_sgp_model_context(egx_sgp_model* m);
+int egx_sgp_model_predict(egx_sgp_model* m, const double* x, int npts, double* y);
+int egx_sgp_model_predict_var(egx_sgp_model* m, const double* x, int npts, double* var);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,92 @@
+"""-m gpu: sparse GP (FITC / VFE) through the C ABI against the oracle (sparse_algorithm.rs)."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as O
+from oracle import sgp_oracle as S
+
+pytestmark = pytest.mark.gpu
+
+
+def f_obj(x):
+    # sparse_algorithm.rs:864-866
+    return np.sin(3 * np.pi * x) + 0.3 * np.cos(9 * np.pi * x) + 0.5 * np.sin(7 * np.pi * x)
+
+
+def make_1d(nt=200, eta2=0.01, seed=42):
+    rng = np.random.default_rng(seed)
+    xt = 2 * rng.random((nt, 1)) - 1
+    yt = f_obj(xt)[:, 0] + rng.normal(0, np.sqrt(eta2), nt)
+    return xt, yt, rng
+
+
+@pytest.mark.parametrize("method", [S.FITC, S.VFE])
+@pytest.mark.parametrize("corr,n,d,m", [(O.SQEXP, 200, 1, 30), (O.MATERN52, 700, 3, 150), (O.MATERN32, 333, 2, 129)])
+def test_sgp_likelihood_and_predict(method, corr, n, d, m):
+    import egobox_b200 as eg
+    rng = np.random.default_rng(n + m)
+    x = 2 * rng.random((n, d)) - 1
+    y = np.sum(np.sin(3 * x), axis=1) + rng.normal(0, 0.1, n)
+    z = S.make_inducings(m, x, rng)
+    theta = np.full(d, 2.0 if corr != O.SQEXP else 4.0)
+    sigma2, noise, nug = 0.8, 0.02, 1e-8
+    ctx = eg.SgpContext(x, y, z, corr=corr, method=method, nugget=nug)
+    ref = S.build(method, corr, theta, sigma2, noise, x, y, z, nugget=nug)
+    st, lik = ctx.reduced_likelihood(theta, sigma2, noise)
+    assert st == 0
+    assert lik == pytest.approx(ref.likelihood, rel=1e-8)                 # bar: 1e-6
+    st, res = ctx.finalize(theta, sigma2, noise, want_inv=True)
+    assert st == 0 and res["likelihood"] == pytest.approx(ref.likelihood, rel=1e-8)
+    scale_v = np.abs(ref.w_data.vec).max()
+    np.testing.assert_allclose(res["w_vec"], ref.w_data.vec[:, 0], rtol=0, atol=1e-6 * scale_v)
+    scale_i = np.abs(ref.w_data.inv).max()
+    np.testing.assert_allclose(res["w_inv"], ref.w_data.inv, rtol=0, atol=1e-6 * scale_i)
+    xs = 2 * rng.random((500, d)) - 1
+    np.testing.assert_allclose(ctx.predict(xs), ref.predict(xs), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(ctx.predict_var(xs), ref.predict_var(xs), rtol=1e-6, atol=1e-9)
+    ctx.close()
+
+
+def test_sgp_non_pd_status():
+    import egobox_b200 as eg
+    x = np.linspace(-1, 1, 50)[:, None]
+    y = np.sin(x[:, 0])
+    z = np.array([[0.0], [0.0], [0.5]])                 # duplicated inducing point, zero nugget
+    ctx = eg.SgpContext(x, y, z, nugget=0.0)
+    st, lik = ctx.reduced_likelihood([1.0], 1.0, 0.01)
+    assert st == 1 and np.isnan(lik)
+    ctx.close()
+
+
+def test_sparse_kriging_fit_like_reference_test():
+    """sparse_algorithm.rs:906-945 (test_sgp_default): 200 noisy 1-D points, 30 random inducing points,
+    prediction error < 0.5, variance error < 0.3; and :1005-1044 noise estimated within 0.015."""
+    import egobox_b200 as eg
+    xt, yt, rng = make_1d()
+    sgp = eg.SparseKriging.params(eg.Inducings.Randomized(30)).seed(42).fit(xt, yt)
+    xplot = np.linspace(-1, 1, 100)[:, None]
+    err = np.abs(f_obj(xplot)[:, 0] - sgp.predict(xplot))
+    assert err.max() < 0.5
+    assert np.abs(sgp.predict_var(xplot) - 0.01).max() < 0.3
+    assert sgp.noise_variance() == pytest.approx(0.01, abs=0.015)
+    assert sgp.inducings().shape == (30, 1)
+    # the fitted state equals the oracle's at the found hyper-parameters
+    ref = S.build(S.FITC, O.SQEXP, sgp.theta(), sgp.variance(), sgp.noise_variance(), xt, yt, sgp.inducings())
+    assert sgp.likelihood() == pytest.approx(ref.likelihood, rel=1e-7)
+    np.testing.assert_allclose(sgp.predict(xplot), ref.predict(xplot), rtol=1e-5, atol=1e-7)
+    wd = sgp.woodbury()
+    np.testing.assert_allclose(wd["vec"], ref.w_data.vec, rtol=0, atol=1e-5 * np.abs(ref.w_data.vec).max())
+
+
+def test_sparse_vfe_fixed_noise():
+    """sparse_algorithm.rs:957-989 (test_sgp_vfe): Located inducings, VFE, fixed noise."""
+    import egobox_b200 as eg
+    xt, yt, rng = make_1d()
+    z = S.make_inducings(30, xt, rng)
+    sgp = (eg.SparseGaussianProcess.params(eg.SquaredExponentialCorr, eg.Inducings.Located(z))
+           .sparse_method(eg.SparseMethod.VFE).noise_variance(eg.ParamTuning.Fixed(0.01)).seed(0).fit(xt, yt))
+    assert sgp.noise_variance() == 0.01
+    xplot = np.linspace(-1, 1, 100)[:, None]
+    assert np.abs(f_obj(xplot)[:, 0] - sgp.predict(xplot)).max() < 0.5
+    gpx = eg.SparseGpx.builder(nz=20, seed=1).fit(xt, yt)
+    assert gpx.thetas().shape == (1, 1) and gpx.predict(xplot).shape == (100,)
