@@ -142,8 +142,13 @@ class BoundCobyla {
                 return;
             }
             if (init_idx_ <= n_) {
+                // Powell's initial simplex is greedy: the next coordinate step starts from the best
+                // point found so far (the better vertex becomes the base), not from x0
                 const int j = init_idx_ - 1;
-                pending_ = V_[0];
+                int jb = 0;
+                for (int k = 1; k < init_idx_; ++k)
+                    if (F_[k] < F_[jb]) jb = k;
+                pending_ = V_[jb];
                 double step = rho_;
                 if (pending_[j] + step > hi_[j]) step = -step;
                 pending_[j] = std::min(std::max(pending_[j] + step, lo_[j]), hi_[j]);
@@ -907,14 +912,10 @@ extern "C" int egx_sgp_fit(const egx_sgp_params* prm, const double* x, int n, in
             egx_set_error("Bounds for theta should be either 1-dim or dim of the parameter vector (%d), got %d", np, nb);
             return EGX_INVALID_VALUE;
         }
-        lo[h] = std::log10(1e-12);
-        hi[h] = std::log10(9.0 * sigma2_0);
-        if (noise_est) {
-            lo[np - 1] = std::log10(prm->noise_lo);
-            hi[np - 1] = std::log10(prm->noise_hi);
-        }
     }
-    // multistart seeds in the (pre-override) log10 box, row 0 = log10(p0)  (:566)
+    // multistart seeds (:566) are drawn in the box BEFORE the variance / noise overrides below, i.e. every
+    // parameter (theta, sigma2, noise) starts inside the theta bounds -- exactly like the reference, which calls
+    // prepare_multistart first and only then rewrites bounds[sigma2] and bounds[noise] (:568-584)
     const int n_start = std::max(prm->n_start, 0);
     std::vector<std::vector<double>> starts;
     {
@@ -932,6 +933,14 @@ extern "C" int egx_sgp_fit(const egx_sgp_params* prm, const double* x, int n, in
                 for (int i = 0; i < np; ++i) v[i] = lo[i] + (hi[i] - lo[i]) * pts[static_cast<size_t>(s) * np + i];
                 starts.push_back(v);
             }
+        }
+    }
+    {
+        lo[h] = std::log10(1e-12);
+        hi[h] = std::log10(9.0 * sigma2_0);
+        if (noise_est) {
+            lo[np - 1] = std::log10(prm->noise_lo);
+            hi[np - 1] = std::log10(prm->noise_hi);
         }
     }
     const int maxeval = std::min(std::max(10 * std::max(n_init, 1), GP_COBYLA_MIN_EVAL), std::max(prm->max_eval, 1));  // :598-600

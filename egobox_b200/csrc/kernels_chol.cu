@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
 // ---------------------------------------------------------------------------
 constexpr int TR_ROWS = 64;
 constexpr int TR_LDX = 132;   // (4 g + t) mod 16 distinct -> conflict-free fragment loads
-constexpr int TR_LDL = 100;   // columns 0..95 of L (+4 pad)
+constexpr int TR_LDL = 100;   // 96 columns of one 32-row block of L (+4 pad)
 constexpr int TR_LDD = 36;
 
 __device__ __forceinline__ void dmma884_t(double& c0, double& c1, double a, double b) {
@@ -160,41 +160,44 @@ __device__ __forceinline__ void tr_cp_async16(void* smem_dst, const void* gsrc) 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
+// Shared memory: X slab 64 x 132 (67.6 KB) + the four Dinv blocks (36.9 KB) + ONE 32-row block of L
+// (32 x 100, 25.6 KB, re-staged per block step) = 130 KB, so that a solve CTA can share an SM with a
+// CTA of the trailing-update kernel (92 KB) instead of waiting for the whole SM to drain.
 __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, long ldx,
                                                         const double* __restrict__ L, long ldl,
                                                         const double* __restrict__ Dinv,
                                                         double* __restrict__ P) {
     extern __shared__ __align__(16) double sm[];
-    double* Ls = sm;                              // [128][100]
-    double* Ds = Ls + EGX_NB * TR_LDL;            // [4][32][36]
-    double* Xs = Ds + 4 * 32 * TR_LDD;            // [64][132]
+    double* Xs = sm;                              // [64][132]
+    double* Ds = Xs + TR_ROWS * TR_LDX;           // [4][32][36]
+    double* Lb = Ds + 4 * 32 * TR_LDD;            // [32][100] rows of block b, columns 0..32b-1
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     double* Xg = X + static_cast<long>(blockIdx.x) * TR_ROWS * ldx;
 
-    // stage L (rows 32..127, cols 0..95), the four Dinv blocks and the X slab with 16-byte cp.async
-    // (all requests in flight at once; plain load/store loops expose one L2 round trip per iteration)
-    for (int e = tid; e < 96 * 48; e += 256) {
-        const int r = 32 + e / 48, ch = e % 48;
-        tr_cp_async16(&Ls[r * TR_LDL + ch * 2], L + static_cast<long>(r) * ldl + ch * 2);
+    for (int e = tid; e < TR_ROWS * 64; e += 256) {
+        const int r = e >> 6, ch = e & 63;
+        tr_cp_async16(&Xs[r * TR_LDX + ch * 2], Xg + static_cast<long>(r) * ldx + ch * 2);
     }
     for (int e = tid; e < 2048; e += 256) {
         const int b = e >> 9, r = (e >> 4) & 31, ch = e & 15;
         tr_cp_async16(&Ds[(b * 32 + r) * TR_LDD + ch * 2], Dinv + e * 2);
     }
-    for (int e = tid; e < TR_ROWS * 64; e += 256) {
-        const int r = e >> 6, ch = e & 63;
-        tr_cp_async16(&Xs[r * TR_LDX + ch * 2], Xg + static_cast<long>(r) * ldx + ch * 2);
-    }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
 
     const int wm = warp >> 1, wn = warp & 1;
     const int gid = lane >> 2, tig = lane & 3;
     const int row0 = wm * 16;        // rows of this warp inside the slab
 #pragma unroll 1
     for (int b = 0; b < 4; ++b) {
+        // stage L[32b .. 32b+31][0 .. 32b-1] (16 b chunks of 16 bytes per row)
+        for (int e = tid; e < 32 * 16 * b; e += 256) {
+            const int r = e / (16 * b), ch = e - r * (16 * b);
+            tr_cp_async16(&Lb[r * TR_LDL + ch * 2], L + static_cast<long>(32 * b + r) * ldl + ch * 2);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
         const int col0 = b * 32 + wn * 16;          // output columns of this warp
         double acc[2][2][2];
 #pragma unroll
@@ -211,20 +214,19 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) af[mi] = -Xs[(row0 + mi * 8 + gid) * TR_LDX + k0 + tig];
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) bf[ni] = Ls[(col0 + ni * 8 + gid) * TR_LDL + k0 + tig];
+            for (int ni = 0; ni < 2; ++ni) bf[ni] = Lb[(wn * 16 + ni * 8 + gid) * TR_LDL + k0 + tig];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
-        __syncthreads();        // every warp has finished reading X_b as an accumulator seed
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni)
                 *reinterpret_cast<double2*>(&Xs[(row0 + mi * 8 + gid) * TR_LDX + col0 + ni * 8 + 2 * tig]) =
                     make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-        __syncthreads();        // T is visible
+        __syncthreads();        // T is visible; every warp is done with Lb
         // X_b = T * Dinv_b^T
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
@@ -419,7 +421,7 @@ void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* 
 void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, int nblocks64,
                       cudaStream_t s) {
     static bool configured = false;
-    const int smem = (EGX_NB * TR_LDL + 4 * 32 * TR_LDD + TR_ROWS * TR_LDX) * sizeof(double);
+    const int smem = (TR_ROWS * TR_LDX + 4 * 32 * TR_LDD + 32 * TR_LDL) * sizeof(double);
     if (!configured) {
         cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
