@@ -92,7 +92,12 @@ struct egx_gp_ctx {
     int npad = 0, qpad = 0, rows_total = 0;
     long ld = 0;
     double nugget = 0.0, y_mean = 0.0, y_std = 1.0;
-    std::vector<double> w_star, xnorm_h;
+    std::vector<double> w_star, xnorm_h, ynorm_h, x_mean_h, x_std_h;
+    // replicas of this context (own R/L workspace, streams, events) used to keep several independent
+    // likelihood evaluations of a batch in flight: one evaluation's serial panel chain overlaps the
+    // bulk trailing updates of another
+    std::vector<egx_gp_ctx*> replicas;
+    bool pending_eval = false;
     std::vector<int> basis_i_h, basis_j_h;
 
     SweepEnv env;                         // streams, look-ahead events, panel buffers, profiler
@@ -268,9 +273,11 @@ int evaluate_small_batch(egx_gp_ctx* c, const double* thetas, int B, double* rlf
 }
 
 // Full likelihood evaluation; leaves L, (L^-1[F|y])^T, beta, G, rho on the device.
-int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
-    *rlf_out = NAN;
+// evaluate_launch enqueues everything (no host synchronisation); evaluate_collect waits for the
+// result block and applies the host-side status logic.
+int evaluate_launch(egx_gp_ctx* c, const double* theta) {
     c->trained = false;
+    c->pending_eval = false;
     int st = assemble(c, theta);
     if (st != EGX_OK) return st;
     cholesky(c);
@@ -281,6 +288,13 @@ int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
     EGX_CUDA_TRY(cudaMemcpyAsync(c->res_h, c->res, sizeof(EvalResult), cudaMemcpyDeviceToHost, c->stream));
     EGX_CUDA_TRY(cudaMemcpyAsync(c->G_h, c->G, sizeof(double) * c->p * c->p, cudaMemcpyDeviceToHost, c->stream));
     EGX_CUDA_TRY(cudaMemcpyAsync(c->beta_h, c->beta, sizeof(double) * c->p, cudaMemcpyDeviceToHost, c->stream));
+    c->pending_eval = true;
+    return EGX_OK;
+}
+
+int evaluate_collect(egx_gp_ctx* c, double* rlf_out) {
+    *rlf_out = NAN;
+    c->pending_eval = false;
     EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
     EGX_CUDA_TRY(cudaGetLastError());
     resolve_profile(c);
@@ -294,6 +308,13 @@ int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
     }
     *rlf_out = c->res_h->rlf;
     return EGX_OK;
+}
+
+int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
+    *rlf_out = NAN;
+    int st = evaluate_launch(c, theta);
+    if (st != EGX_OK) return st;
+    return evaluate_collect(c, rlf_out);
 }
 
 int ensure_predict_buffers(egx_gp_ctx* c, int mb) {
@@ -389,6 +410,8 @@ int predict_impl(egx_gp_ctx* c, const double* x, int m, double* y, double* var, 
 
 void free_ctx(egx_gp_ctx* c) {
     if (!c) return;
+    for (egx_gp_ctx* r : c->replicas) free_ctx(r);
+    c->replicas.clear();
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->timer_a) cudaEventDestroy(c->timer_a);
@@ -469,6 +492,9 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
     c->y_std = y_std;
     c->w_star.assign(w_star, w_star + static_cast<size_t>(d) * h);
     c->xnorm_h.assign(xnorm, xnorm + static_cast<size_t>(n) * d);
+    c->ynorm_h.assign(ynorm, ynorm + n);
+    c->x_mean_h.assign(x_mean, x_mean + d);
+    c->x_std_h.assign(x_std, x_std + d);
     // regression basis f_l(x) = v(bi) * v(bj), v(-1) = 1  (mean_models.rs:42-44, 68-71, 97-104)
     c->basis_i_h.push_back(-1);
     c->basis_j_h.push_back(-1);
@@ -573,9 +599,38 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
     if (small_path_ok(c)) return evaluate_small_batch(c, thetas, B, rlf, status);
-    for (int b = 0; b < B; ++b) {
-        status[b] = evaluate(c, thetas + static_cast<long>(b) * c->h, &rlf[b]);
-        if (status[b] == EGX_CUDA_ERROR) return EGX_CUDA_ERROR;
+    // Large n: keep `W` independent evaluations in flight on W replicas of the workspace (own streams):
+    // the serial diagonal-block / panel chain of one factorisation overlaps the bulk updates of the others.
+    int W = 3;
+    if (const char* e = getenv("EGX_BATCH_STREAMS")) W = std::max(1, atoi(e));
+    W = std::min(W, B);
+    while (static_cast<int>(c->replicas.size()) < W - 1) {
+        egx_gp_ctx* r = nullptr;
+        const int st = egx_gp_create(&r, c->device, c->corr, c->mean, c->xnorm_h.data(), c->n, c->d, c->ynorm_h.data(),
+                                     c->x_mean_h.data(), c->x_std_h.data(), c->y_mean, c->y_std, c->w_star.data(),
+                                     c->h, c->nugget);
+        if (st != EGX_OK) return st;
+        r->env.prof.on = c->env.prof.on;
+        c->replicas.push_back(r);
+    }
+    std::vector<egx_gp_ctx*> ws;
+    ws.push_back(c);
+    for (int i = 0; i < W - 1; ++i) ws.push_back(c->replicas[i]);
+    std::vector<int> owner(W, -1);     // which candidate each workspace is working on
+    for (int b = 0; b < B + W; ++b) {
+        egx_gp_ctx* w = ws[b % W];
+        const int prev = owner[b % W];
+        if (prev >= 0) {
+            if (status[prev] == EGX_OK) status[prev] = evaluate_collect(w, &rlf[prev]);
+            if (status[prev] == EGX_CUDA_ERROR) return EGX_CUDA_ERROR;
+            owner[b % W] = -1;
+        }
+        if (b < B) {
+            rlf[b] = NAN;
+            status[b] = evaluate_launch(w, thetas + static_cast<long>(b) * c->h);
+            if (status[b] == EGX_CUDA_ERROR) return EGX_CUDA_ERROR;
+            owner[b % W] = b;
+        }
     }
     return EGX_OK;
 }
@@ -701,12 +756,14 @@ extern "C" int egx_gp_set_profiling(egx_gp_ctx* c, int enabled) {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     c->env.prof.on = enabled != 0;
+    for (egx_gp_ctx* r : c->replicas) r->env.prof.on = c->env.prof.on;
     return EGX_OK;
 }
 extern "C" int egx_gp_reset_profile(egx_gp_ctx* c) {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     c->env.prof.reset();
+    for (egx_gp_ctx* r : c->replicas) r->env.prof.reset();
     return EGX_OK;
 }
 extern "C" int egx_gp_get_profile(egx_gp_ctx* c, double* ms, long long* launches) {
@@ -715,6 +772,10 @@ extern "C" int egx_gp_get_profile(egx_gp_ctx* c, double* ms, long long* launches
     for (int i = 0; i < EGX_NUM_STAGES; ++i) {
         if (ms) ms[i] = c->env.prof.ms[i];
         if (launches) launches[i] = c->env.prof.launches[i];
+        for (egx_gp_ctx* r : c->replicas) {
+            if (ms) ms[i] += r->env.prof.ms[i];
+            if (launches) launches[i] += r->env.prof.launches[i];
+        }
     }
     return EGX_OK;
 }
@@ -733,6 +794,10 @@ extern "C" int egx_gp_timer_stop(egx_gp_ctx* c, double* elapsed_ms) {
     if (!c || !elapsed_ms || !c->timer_a) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
+    for (egx_gp_ctx* r : c->replicas) {   // the replicas' streams end before the stop event
+        EGX_CUDA_TRY(cudaEventRecord(r->env.ev_join, r->stream));
+        EGX_CUDA_TRY(cudaStreamWaitEvent(c->stream, r->env.ev_join, 0));
+    }
     EGX_CUDA_TRY(cudaEventRecord(c->timer_b, c->stream));
     EGX_CUDA_TRY(cudaEventSynchronize(c->timer_b));
     float ms = 0.f;

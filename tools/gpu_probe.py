@@ -37,6 +37,13 @@ def main():
             ctx.reduced_likelihood(theta)
         t1 = time.perf_counter()
         print(json.dumps({"n": n, "wall_ms_per_eval_noprof": (t1 - t0) / reps * 1e3}), flush=True)
+        thetas = np.tile(theta, (12, 1)) * np.linspace(0.8, 1.2, 12)[:, None]
+        ctx.reduced_likelihood_batch(thetas[:4])
+        t0 = time.perf_counter()
+        stb, rlfb = ctx.reduced_likelihood_batch(thetas)
+        t1 = time.perf_counter()
+        print(json.dumps({"n": n, "batch12_ms_per_eval": (t1 - t0) / 12 * 1e3, "batch_status_ok": int((stb == 0).sum()),
+                          "batch_streams": __import__("os").environ.get("EGX_BATCH_STREAMS", "3")}), flush=True)
         st, res = ctx.finalize(theta)
         m = 8192
         xs = np.random.default_rng(43).random((m, d))
