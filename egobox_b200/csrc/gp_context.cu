@@ -601,7 +601,7 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
     if (small_path_ok(c)) return evaluate_small_batch(c, thetas, B, rlf, status);
     // Large n: keep `W` independent evaluations in flight on W replicas of the workspace (own streams):
     // the serial diagonal-block / panel chain of one factorisation overlaps the bulk updates of the others.
-    int W = 3;
+    int W = 4;
     if (const char* e = getenv("EGX_BATCH_STREAMS")) W = std::max(1, atoi(e));
     W = std::min(W, B);
     while (static_cast<int>(c->replicas.size()) < W - 1) {
