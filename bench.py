@@ -375,9 +375,9 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=8192)
-    ap.add_argument("--d", type=int, default=10)
-    ap.add_argument("--m", type=int, default=100000)
+    ap.add_argument("--ntrain", dest="n", type=int, default=8192)
+    ap.add_argument("--dim", dest="d", type=int, default=10)
+    ap.add_argument("--npred", dest="m", type=int, default=100000)
     ap.add_argument("--evals", type=int, default=1101)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

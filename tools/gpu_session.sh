@@ -12,4 +12,4 @@ echo "== ncu launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --cl
 echo "== ncu full"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_nt_sub|potrf_diag|trsm_rows|corr_build|cross_corr|gls_kernel|var_finish" -c 14 -f -o gpurun_out/prof_r01 python tools/ncu_target.py 8192 2048 > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out/*.ncu-rep
 fi
-echo "== short bench"; timeout 600 python bench.py --steps 2 --warmup 3 --evals 101 --m 20000 2>&1 | tee gpurun_out/bench_short.log | cut -c1-3000
+echo "== short bench"; timeout 600 python bench.py --steps 2 --warmup 3 --evals 101 --npred 20000 2>&1 | tee gpurun_out/bench_short.log | cut -c1-3000
