@@ -111,6 +111,12 @@ class GpContext:
         self._check(self._lib.egx_gp_predict_valvar(self._h, _ptr(x), x.shape[0], _ptr(y), _ptr(v)))
         return y, v
 
+    def predict_gradients(self, x):
+        x = _f64(x).reshape(-1, self.d)
+        g = np.empty((x.shape[0], self.d))
+        self._check(self._lib.egx_gp_predict_gradients(self._h, _ptr(x), x.shape[0], _ptr(g)))
+        return g
+
     def predict_valvar_dev(self, x_ptr, m, y_ptr, v_ptr):
         """x/y/var are raw device addresses (ints) on this context's GPU."""
         self._check(self._lib.egx_gp_predict_valvar_dev(self._h, C.c_void_p(x_ptr), m,
@@ -149,6 +155,9 @@ class GpContext:
         ms = C.c_double()
         self._check(self._lib.egx_gp_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+    def set_lookahead(self, on=True):
+        self._lib.egx_gp_set_lookahead(self._h, int(bool(on)))
 
     def set_force_blocked(self, on=True):
         self._lib.egx_gp_set_force_blocked(self._h, int(bool(on)))

@@ -64,6 +64,10 @@ void launch_cross_corr(int corr, const double* xraw, int m, int mpad, const doub
                        const CorrTerm* terms, int nterms, const double* gamma, const double* beta,
                        const int* basis_i, const int* basis_j, int p, double y_mean, double y_std,
                        double* Y, long ldy, double* yout, cudaStream_t s, double scale = 1.0);
+void launch_predict_grad(int corr, const double* xraw, int m, const double* x_mean, const double* x_std, const double* X,
+                         int n, int npad, int d, const CorrTerm* terms, int nterms, const double* gamma,
+                         const double* beta, const int* basis_i, const int* basis_j, int p, double y_std, double* out,
+                         cudaStream_t s);
 void launch_mean_basis_rows(const double* X, int n, int npad, int d, const int* basis_i,
                             const int* basis_j, int p, const double* ynorm_dev, double* FyT, long ld,
                             cudaStream_t s);

@@ -699,6 +699,46 @@ extern "C" int egx_gp_predict_valvar(egx_gp_ctx* c, const double* x, int m, doub
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_impl(c, x, m, y, var, false);
 }
+extern "C" int egx_gp_predict_gradients(egx_gp_ctx* c, const double* x, int m, double* grad) {
+    if (!c || !x || !grad || m < 0) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->trained) {
+        egx_set_error("predict_gradients called before a successful egx_gp_finalize");
+        return EGX_INVALID_VALUE;
+    }
+    if (c->d > 32) {
+        egx_set_error("predict_gradients supports input dimension <= 32 (got %d)", c->d);
+        return EGX_INVALID_VALUE;
+    }
+    if (m == 0) return EGX_OK;
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    const int mb = std::min(round_up(m, EGX_NB), PREDICT_CHUNK);
+    double *xd = nullptr, *gd = nullptr;
+    EGX_CUDA_TRY(cudaMalloc(&xd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    EGX_CUDA_TRY(cudaMalloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    int st = EGX_OK;
+    for (int i0 = 0; i0 < m && st == EGX_OK; i0 += mb) {
+        const int mc = std::min(mb, m - i0);
+        cudaMemcpyAsync(xd, x + static_cast<long>(i0) * c->d, static_cast<size_t>(mc) * c->d * sizeof(double),
+                        cudaMemcpyHostToDevice, c->stream);
+        {
+            StageScope sc(c->env.prof, EGX_STAGE_CROSS_CORR, 1, c->stream);
+            launch_predict_grad(c->corr, xd, mc, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d, c->terms, c->nterms,
+                                c->rho, c->beta, c->basis_i, c->basis_j, c->p, c->y_std, gd, c->stream);
+        }
+        cudaMemcpyAsync(grad + static_cast<long>(i0) * c->d, gd, static_cast<size_t>(mc) * c->d * sizeof(double),
+                        cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = EGX_CUDA_ERROR;
+    }
+    cudaFree(xd);
+    cudaFree(gd);
+    if (st != EGX_OK || cudaGetLastError() != cudaSuccess) {
+        egx_set_error("predict_gradients: CUDA failure");
+        return EGX_CUDA_ERROR;
+    }
+    resolve_profile(c);
+    return EGX_OK;
+}
 extern "C" int egx_gp_predict_valvar_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, double* var_dev) {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -803,6 +843,13 @@ extern "C" int egx_gp_timer_stop(egx_gp_ctx* c, double* elapsed_ms) {
     float ms = 0.f;
     EGX_CUDA_TRY(cudaEventElapsedTime(&ms, c->timer_a, c->timer_b));
     *elapsed_ms = ms;
+    return EGX_OK;
+}
+extern "C" int egx_gp_set_lookahead(egx_gp_ctx* c, int enabled) {
+    if (!c) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->env.lookahead = enabled != 0;
+    for (egx_gp_ctx* r : c->replicas) r->env.lookahead = c->env.lookahead;
     return EGX_OK;
 }
 extern "C" int egx_gp_set_force_blocked(egx_gp_ctx* c, int enabled) {

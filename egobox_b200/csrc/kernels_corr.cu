@@ -277,6 +277,113 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Batched prediction gradients  d yhat / d x  (gp/src/algorithm.rs:510-550 `predict_gradients` via
+// `predict_jacobian`; kernels' jacobians correlation_models.rs:106-122, 198-214, 288-298+355-412,
+// 457-468+525-586).  One warp per prediction point, lanes over training points; per pair the kernel
+// value r and, per input dimension k, the logarithmic derivative  s_k = (dr/dx_k) / r  are formed in
+// one pass over the term list (for the Matern models: sum_l f'_kl / f_kl - sqrt(nu') tw_k sign, every
+// factor f >= 1 so the division is safe), and  g_k += gamma_j r s_k  is accumulated in registers.
+// ---------------------------------------------------------------------------
+template <int CORR, int DMAX>
+__global__ void __launch_bounds__(256)
+    predict_grad_kernel(const double* __restrict__ xraw, int m, const double* __restrict__ x_mean,
+                        const double* __restrict__ x_std, const double* __restrict__ X, int n, int npad, int d,
+                        const CorrTerm* __restrict__ gterms, int nterms, const double* __restrict__ gamma,
+                        const double* __restrict__ beta, const int* __restrict__ basis_i,
+                        const int* __restrict__ basis_j, int p, double y_std, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* XjT = reinterpret_cast<double*>(smem_raw);          // [d][64]
+    double* gam = XjT + EGX_CT * d;                               // [64]
+    double* xp = gam + EGX_CT;                                    // [8][d] normalised prediction points
+    CorrTerm* terms = reinterpret_cast<CorrTerm*>(xp + 8 * d);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * 8 + warp;
+    for (int t = tid; t < nterms; t += 256) terms[t] = gterms[t];
+    for (int e = tid; e < 8 * d; e += 256) {
+        const int w = e / d, c = e - w * d;
+        const int ii = blockIdx.x * 8 + w;
+        xp[e] = (ii < m) ? (xraw[static_cast<long>(ii) * d + c] - x_mean[c]) / x_std[c] : 0.0;
+    }
+    double g[DMAX];
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) g[k] = 0.0;
+    const double* xi = xp + warp * d;
+    const double sq = (CORR == EGX_CORR_MATERN32) ? 1.7320508075688772 : 2.23606797749979;
+    for (int j0 = 0; j0 < npad; j0 += EGX_CT) {
+        __syncthreads();     // previous tile fully consumed (also covers the terms / xp staging the first time)
+        for (int e = tid; e < EGX_CT * d; e += 256) {
+            const int r = e / d, c = e - r * d;
+            XjT[c * EGX_CT + r] = X[static_cast<long>(j0 + r) * d + c];
+        }
+        if (tid < EGX_CT) gam[tid] = (j0 + tid < n) ? gamma[j0 + tid] : 0.0;
+        __syncthreads();
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int jl = lane + 32 * h;
+            const double gj = gam[jl];
+            double s[DMAX];
+#pragma unroll
+            for (int k = 0; k < DMAX; ++k) s[k] = 0.0;
+            double acc = 0.0, prod = 1.0;
+            for (int t = 0; t < nterms; ++t) {
+                const CorrTerm tm = terms[t];
+                const double dx = xi[tm.dim] - XjT[tm.dim * EGX_CT + jl];
+                const double ad = fabs(dx), sg = copysign(1.0, dx);
+                double sk;
+                if (CORR == EGX_CORR_SQUARED_EXPONENTIAL) {
+                    acc += tm.k1 * (dx * dx);
+                    sk = -tm.k1 * dx;
+                } else if (CORR == EGX_CORR_ABSOLUTE_EXPONENTIAL) {
+                    acc += tm.k1 * ad;
+                    sk = -tm.k1 * sg;
+                } else if (CORR == EGX_CORR_MATERN32) {
+                    const double f = 1.0 + tm.k2 * ad;
+                    prod *= f;
+                    acc += tm.k1 * ad;
+                    sk = sg * (tm.k2 / f - sq * tm.k1);
+                } else {
+                    const double f = (1.0 + tm.k2 * ad) + (5.0 / 3.0) * ((tm.k3 * dx) * dx);
+                    prod *= f;
+                    acc += tm.k1 * ad;
+                    sk = sg * ((tm.k2 + (10.0 / 3.0) * tm.k3 * ad) / f - sq * tm.k1);
+                }
+#pragma unroll
+                for (int k = 0; k < DMAX; ++k)
+                    if (k == tm.dim) s[k] += sk;
+            }
+            const double r = gj * pair_finish<CORR>(acc, prod);
+#pragma unroll
+            for (int k = 0; k < DMAX; ++k) g[k] += r * s[k];
+        }
+    }
+    if (i >= m) return;
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k) {
+        double v = g[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        g[k] = v;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k) {
+            if (k < d) {
+                // (d f / d x_k)^T beta with f_l = v(bi) v(bj)  (mean_models.rs jacobians)
+                double df = 0.0;
+                for (int l = 0; l < p; ++l) {
+                    const int bi = basis_i[l], bj = basis_j[l];
+                    double t = 0.0;
+                    if (bi == k) t += (bj < 0) ? 1.0 : xi[bj];
+                    if (bj == k) t += (bi < 0) ? 1.0 : xi[bi];
+                    df += t * beta[l];
+                }
+                out[static_cast<long>(i) * d + k] = (df + g[k]) * y_std / x_std[k];
+            }
+        }
+    }
+}
+
 // F^T rows (p x npad) followed by ynorm as row p: the right-hand sides that are
 // carried through the Cholesky as extra rows of the matrix (forward solves fused).
 __global__ void mean_basis_rows_kernel(const double* __restrict__ X, int n, int npad, int d,
@@ -340,4 +447,51 @@ void launch_cross_corr(int corr, const double* xraw, int m, int mpad, const doub
 void launch_mean_basis_rows(const double* X, int n, int npad, int d, const int* basis_i, const int* basis_j, int p,
                             const double* ynorm_dev, double* FyT, long ld, cudaStream_t s) {
     mean_basis_rows_kernel<<<(npad + 255) / 256, 256, 0, s>>>(X, n, npad, d, basis_i, basis_j, p, ynorm_dev, FyT, ld);
+}
+
+template <int CORR>
+static void launch_pg(int dmax, int grid, size_t smem, cudaStream_t s, const double* xraw, int m, const double* x_mean,
+                      const double* x_std, const double* X, int n, int npad, int d, const CorrTerm* terms, int nterms,
+                      const double* gamma, const double* beta, const int* bi, const int* bj, int p, double y_std,
+                      double* out) {
+    if (dmax <= 8) {
+        set_smem(predict_grad_kernel<CORR, 8>, smem);
+        predict_grad_kernel<CORR, 8><<<grid, 256, smem, s>>>(xraw, m, x_mean, x_std, X, n, npad, d, terms, nterms, gamma,
+                                                            beta, bi, bj, p, y_std, out);
+    } else if (dmax <= 16) {
+        set_smem(predict_grad_kernel<CORR, 16>, smem);
+        predict_grad_kernel<CORR, 16><<<grid, 256, smem, s>>>(xraw, m, x_mean, x_std, X, n, npad, d, terms, nterms, gamma,
+                                                             beta, bi, bj, p, y_std, out);
+    } else {
+        set_smem(predict_grad_kernel<CORR, 32>, smem);
+        predict_grad_kernel<CORR, 32><<<grid, 256, smem, s>>>(xraw, m, x_mean, x_std, X, n, npad, d, terms, nterms, gamma,
+                                                             beta, bi, bj, p, y_std, out);
+    }
+}
+
+// d <= 32 (caller checks)
+void launch_predict_grad(int corr, const double* xraw, int m, const double* x_mean, const double* x_std, const double* X,
+                         int n, int npad, int d, const CorrTerm* terms, int nterms, const double* gamma,
+                         const double* beta, const int* basis_i, const int* basis_j, int p, double y_std, double* out,
+                         cudaStream_t s) {
+    const int grid = (m + 7) / 8;
+    const size_t smem = (static_cast<size_t>(EGX_CT) * d + EGX_CT + 8 * d) * sizeof(double) + nterms * sizeof(CorrTerm);
+    switch (corr) {
+        case EGX_CORR_SQUARED_EXPONENTIAL:
+            launch_pg<EGX_CORR_SQUARED_EXPONENTIAL>(d, grid, smem, s, xraw, m, x_mean, x_std, X, n, npad, d, terms, nterms,
+                                                    gamma, beta, basis_i, basis_j, p, y_std, out);
+            break;
+        case EGX_CORR_ABSOLUTE_EXPONENTIAL:
+            launch_pg<EGX_CORR_ABSOLUTE_EXPONENTIAL>(d, grid, smem, s, xraw, m, x_mean, x_std, X, n, npad, d, terms, nterms,
+                                                     gamma, beta, basis_i, basis_j, p, y_std, out);
+            break;
+        case EGX_CORR_MATERN32:
+            launch_pg<EGX_CORR_MATERN32>(d, grid, smem, s, xraw, m, x_mean, x_std, X, n, npad, d, terms, nterms, gamma,
+                                         beta, basis_i, basis_j, p, y_std, out);
+            break;
+        default:
+            launch_pg<EGX_CORR_MATERN52>(d, grid, smem, s, xraw, m, x_mean, x_std, X, n, npad, d, terms, nterms, gamma,
+                                         beta, basis_i, basis_j, p, y_std, out);
+            break;
+    }
 }

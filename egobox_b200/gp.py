@@ -268,6 +268,16 @@ class GaussianProcess:
             _raise_status(st)
         return y, v
 
+    def predict_gradients(self, x):
+        """algorithm.rs:518-529: (n, nx) matrix of output derivatives."""
+        x = self._x(x)
+        g = np.empty((x.shape[0], self._d))
+        st = self._lib.egx_gp_model_predict_gradients(self._h, x.ctypes.data_as(C.POINTER(C.c_double)), x.shape[0],
+                                                      g.ctypes.data_as(C.POINTER(C.c_double)))
+        if st != EGX_OK:
+            _raise_status(st)
+        return g
+
     def theta(self):
         th = np.empty(self._hdim)
         self._lib.egx_gp_model_theta(self._h, th.ctypes.data_as(C.POINTER(C.c_double)))

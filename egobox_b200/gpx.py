@@ -107,10 +107,11 @@ class Gpx:
         return self._gp.predict_valvar(np.asarray(x, dtype=np.float64))
 
     def predict_gradients(self, x):
-        raise NotImplementedError("batched prediction gradients: SURVEY.md 8(f)-1 (next)")
+        """gp_mix.rs:373-383: (nsamples, nx) output derivatives."""
+        return self._gp.predict_gradients(np.asarray(x, dtype=np.float64))
 
     def predict_var_gradients(self, x):
-        raise NotImplementedError("batched prediction gradients: SURVEY.md 8(f)-1 (next)")
+        raise NotImplementedError("batched variance gradients: SURVEY.md 8(f)-1 (next)")
 
     def sample(self, x, n_traj):
         raise NotImplementedError("conditional sampling: SURVEY.md 8(f)-4 (next)")

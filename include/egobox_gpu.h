@@ -115,6 +115,11 @@ int egx_gp_predict(egx_gp_ctx* ctx, const double* x, int m, double* y);
 int egx_gp_predict_var(egx_gp_ctx* ctx, const double* x, int m, double* var);
 int egx_gp_predict_valvar(egx_gp_ctx* ctx, const double* x, int m, double* y, double* var);
 
+/* Batched prediction gradients d yhat / d x at m raw points: grad is m x d (row-major).
+ *   predict_gradients gp/src/algorithm.rs:518-529 (one `predict_jacobian` :533-566 per point in the
+ *   reference; one warp per point here).  Supports d <= 32. */
+int egx_gp_predict_gradients(egx_gp_ctx* ctx, const double* x, int m, double* grad);
+
 /* Same, with x / y / var already resident on the context's device (device
  * pointers).  Used to time the kernels without the PCIe copies. */
 int egx_gp_predict_valvar_dev(egx_gp_ctx* ctx, const double* x_dev, int m,
@@ -152,6 +157,10 @@ int egx_gp_get_profile(egx_gp_ctx* ctx, double* ms, long long* launches);
  * (includes any GPU idle time while the host prepares the next launch). */
 int egx_gp_timer_start(egx_gp_ctx* ctx);
 int egx_gp_timer_stop(egx_gp_ctx* ctx, double* elapsed_ms);
+/* Enable / disable the two-stream look-ahead of the factorisation (default on; EGX_LOOKAHEAD=0 also disables).
+ * With look-ahead off every kernel of an evaluation runs back to back on one stream, which is what the
+ * per-kernel roofline pass of bench.py times. */
+int egx_gp_set_lookahead(egx_gp_ctx* ctx, int enabled);
 /* Force the blocked large-n path even when n is small enough for the
  * one-CTA-per-theta kernel (tests exercise both on the same inputs). */
 int egx_gp_set_force_blocked(egx_gp_ctx* ctx, int enabled);
@@ -235,6 +244,7 @@ int egx_prepare_multistart(int n_start, const double* theta0, const double* boun
 int egx_gp_model_predict(egx_gp_model* m, const double* x, int npts, double* y);
 int egx_gp_model_predict_var(egx_gp_model* m, const double* x, int npts, double* var);
 int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int npts, double* y, double* var);
+int egx_gp_model_predict_gradients(egx_gp_model* m, const double* x, int npts, double* grad /* npts x d */);
 
 /* ============================================================================
  * Sparse GP (FITC / VFE) -- crates/gp/src/sparse_algorithm.rs.

@@ -158,6 +158,75 @@ def corr_value(kind, d, theta, w):
     raise ValueError(kind)
 
 
+def mean_jacobian(kind, x):
+    """mean_models.rs:50-53 (constant), :75-82 (linear), :110-128 (quadratic): (p, nx) at one point x."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    nx = x.size
+    if kind == CONSTANT:
+        return np.zeros((1, nx))
+    if kind == LINEAR:
+        jac = np.zeros((nx + 1, nx))
+        jac[1:, :] = np.eye(nx)
+        return jac
+    jac = np.zeros((1 + nx + nx * (nx + 1) // 2, nx))
+    jac[1:nx + 1, :] = np.eye(nx)
+    o, p = 1 + nx, nx
+    for i in range(nx):
+        part = np.zeros((p, p))
+        part[:, 0] = x[i:]
+        part = part + np.eye(p) * x[i]
+        jac[o:o + nx - i, i:nx] = part
+        o += p
+        p -= 1
+    return jac
+
+
+def corr_jacobian(kind, x, xtrain, theta, w):
+    """d r(x, xtrain_j) / d x_k as an (n, nx) array.
+    SqExp correlation_models.rs:106-122, AbsExp :198-214, Matern32 :288-298 + 355-412,
+    Matern52 :457-468 + 525-586."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    xtrain = np.asarray(xtrain, dtype=np.float64)
+    theta = np.asarray(theta, dtype=np.float64).reshape(-1)
+    w = np.asarray(w, dtype=np.float64)
+    d = x[None, :] - xtrain                                  # utils.rs:136-142 `differences`
+    if kind == SQEXP:
+        r = corr_value(kind, d, theta, w)
+        dtheta_w = -((theta * w) ** 2).sum(axis=1)
+        return d * dtheta_w * r[:, None]
+    if kind == ABSEXP:
+        r = corr_value(kind, d, theta, w)
+        dtheta_w = np.copysign(1.0, d) * (-(theta * np.abs(w)).sum(axis=1))    # Rust f64::signum(+0.0) = 1
+        return dtheta_w * r[:, None]
+    s = math.sqrt(3.0) if kind == MATERN32 else math.sqrt(5.0)
+    theta_w = theta * np.abs(w)                              # (nx, h)
+    abs_d, sign_d = np.abs(d), np.copysign(1.0, d)
+    a = np.ones(d.shape[0])
+    fac = np.empty((d.shape[0],) + theta_w.shape)            # f_jl per pair
+    for j in range(theta_w.shape[0]):
+        for l in range(theta_w.shape[1]):
+            v = theta_w[j, l] * abs_d[:, j]
+            fac[:, j, l] = 1.0 + s * v if kind == MATERN32 else 1.0 + s * v + (5.0 / 3.0) * v * v
+            a *= fac[:, j, l]
+    b = np.exp(-s * abs_d.dot(theta_w).sum(axis=1))
+    tw = np.abs(w).dot(theta)                                # (nx,)
+    db = -s * tw[None, :] * sign_d * (a * b)[:, None]
+    da = np.zeros_like(d)
+    for j in range(theta_w.shape[0]):
+        for k in range(theta_w.shape[1]):
+            if kind == MATERN32:
+                deriv = s * theta_w[j, k] * sign_d[:, j]
+            else:
+                deriv = s * theta_w[j, k] * sign_d[:, j] + (10.0 / 3.0) * theta_w[j, k] ** 2 * sign_d[:, j] * abs_d[:, j]
+            term = np.ones(d.shape[0])
+            for p_ in range(theta_w.shape[0]):
+                for l in range(theta_w.shape[1]):
+                    if l != k or p_ != j:
+                        term = term * fac[:, p_, l]
+            da[:, j] += deriv * term
+    return db + b[:, None] * da
+
+
 def corr_matrix(kind, xnorm, theta, w, nugget=DEFAULT_NUGGET, chunk=256):
     """R = (1+nugget) I + symmetric scatter of r over pairs.
 
@@ -329,6 +398,18 @@ class GaussianProcess:
             y_ = f.dot(self.inner.beta) + corr.dot(self.inner.gamma)
             out.append((y_ * self.y_std + self.y_mean)[:, 0])
         return np.concatenate(out)
+
+    # algorithm.rs:518-550 (predict_gradients via predict_jacobian)
+    def predict_gradients(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        out = np.zeros((x.shape[0], self.xt_norm.shape[1]))
+        for i in range(x.shape[0]):
+            xn = (x[i] - self.x_mean) / self.x_std
+            df_dx = mean_jacobian(self.mean, xn).T.dot(self.inner.beta)            # (nx, 1)
+            dr = corr_jacobian(self.corr, xn, self.xt_norm, self.theta, self.w_star)
+            dr_dx = df_dx + dr.T.dot(self.inner.gamma)
+            out[i] = dr_dx[:, 0] * self.y_std / self.x_std
+        return out
 
     # algorithm.rs:267-279
     def predict_var(self, x, chunk=1024):

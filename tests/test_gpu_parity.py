@@ -333,3 +333,49 @@ def test_theta_sweep_512_candidates():
     best = int(np.nanargmax(np.where(status == 0, rlf, -np.inf)))
     assert status[best] == 0
     ctx.close()
+
+
+# ------------------------------------------------- batched prediction gradients ----------
+@pytest.mark.parametrize("n,d,corr,mean", [
+    (120, 1, O.SQEXP, O.CONSTANT),
+    (300, 3, O.MATERN32, O.LINEAR),
+    (260, 4, O.MATERN52, O.QUADRATIC),
+    (200, 10, O.MATERN52, O.CONSTANT),
+    (150, 20, O.ABSEXP, O.CONSTANT),
+])
+def test_predict_gradients(n, d, corr, mean):
+    x, y = make_problem(n, d, seed=31)
+    theta = np.full(d, 1.2) if corr != O.SQEXP else np.full(d, 40.0)
+    ctx, _ = make_context(x, y, corr, mean)
+    gp = oracle_gp(x, y, corr, mean, theta)
+    st, _res = ctx.finalize(theta)
+    assert st == 0
+    xs = np.random.default_rng(7).random((37, d))
+    g_ref = gp.predict_gradients(xs)
+    g = ctx.predict_gradients(xs)
+    np.testing.assert_allclose(g, g_ref, rtol=1e-7, atol=1e-8 * np.abs(g_ref).max())
+    # and against central finite differences of the GPU's own predict
+    e = 1e-6
+    for k in range(min(d, 3)):
+        xp, xm = xs.copy(), xs.copy()
+        xp[:, k] += e
+        xm[:, k] -= e
+        fd = (ctx.predict(xp) - ctx.predict(xm)) / (2 * e)
+        np.testing.assert_allclose(g[:, k], fd, rtol=2e-4, atol=1e-5 * np.abs(g_ref).max())
+    ctx.close()
+
+
+def test_predict_gradients_kpls_weights():
+    n, d, h = 140, 5, 2
+    x, y = make_problem(n, d, seed=8)
+    w = np.random.default_rng(2).normal(size=(d, h))
+    theta = np.array([0.6, 1.1])
+    for corr in (O.SQEXP, O.MATERN52):
+        ctx, _ = make_context(x, y, corr, O.CONSTANT, w_star=w)
+        gp = oracle_gp(x, y, corr, O.CONSTANT, theta, w_star=w)
+        st, _res = ctx.finalize(theta)
+        assert st == 0
+        xs = np.random.default_rng(3).random((20, d))
+        g_ref = gp.predict_gradients(xs)
+        np.testing.assert_allclose(ctx.predict_gradients(xs), g_ref, rtol=1e-7, atol=1e-8 * np.abs(g_ref).max())
+        ctx.close()

@@ -194,3 +194,54 @@ def test_c_restatement_matches_numpy():
                                        rtol=1e-12, atol=0)
             ref = O.corr_value(kind, O.pairwise_differences(xs, x), theta, w).reshape(13, 57)
             np.testing.assert_allclose(fast.cross_corr(kind, xs, x, theta, w), ref, rtol=1e-12, atol=0)
+
+
+# ---- correlation_models.rs:643-716: analytic jacobians vs central finite differences -------
+XT16 = np.array([[-9.375, -5.625], [-5.625, -4.375], [9.375, 1.875], [8.125, 5.625], [-4.375, -0.625],
+                 [6.875, -3.125], [4.375, 9.375], [3.125, 4.375], [5.625, -8.125], [-8.125, 3.125],
+                 [1.875, -6.875], [-0.625, 8.125], [-1.875, -1.875], [0.625, 0.625], [-6.875, -9.375],
+                 [-3.125, 6.875]])
+
+
+@pytest.mark.parametrize("kpls", [False, True])
+@pytest.mark.parametrize("kind", [O.SQEXP, O.ABSEXP, O.MATERN32, O.MATERN52])
+def test_corr_jacobian_vs_finite_differences(kind, kpls):
+    x = np.array([3.0, 5.0])
+    xn_t, mean, std = O.normalize(XT16)
+    if kpls:
+        theta, w = np.array([0.31059002]), np.array([[-0.02701716], [-0.99963497]])
+    else:
+        theta, w = np.array([0.34599115925909146, 0.32083374253611624]), np.eye(2)
+    jac = O.corr_jacobian(kind, (x - mean) / std, xn_t, theta, w) / std
+    e = 1e-5
+    for k in range(2):
+        xp, xm = x.copy(), x.copy()
+        xp[k] += e
+        xm[k] -= e
+        rp = O.corr_value(kind, (xp - mean) / std - xn_t, theta, w)
+        rm = O.corr_value(kind, (xm - mean) / std - xn_t, theta, w)
+        np.testing.assert_allclose((rp - rm) / (2 * e), jac[:, k], atol=1e-6)
+
+
+def test_kriging5_predict_gradients(krg5):
+    # python/egobox/tests/test_gpmix.py:48-50: predict_gradients(1.1) = 1.1204 (+- 1e-3)
+    xt = np.array(krg5["xt"])[:, None]
+    gp = O.fit(xt, krg5["yt"], theta_init=[krg5["theta"]], fixed=True)
+    g = gp.predict_gradients(np.array([[1.1]]))
+    assert g.shape == (1, 1) and g[0, 0] == pytest.approx(1.1204, abs=1e-3)
+    e = 1e-6
+    fd = (gp.predict(np.array([[1.1 + e]])) - gp.predict(np.array([[1.1 - e]]))) / (2 * e)
+    assert g[0, 0] == pytest.approx(fd[0], rel=1e-6)
+
+
+def test_quadratic_mean_jacobian():
+    # mean_models.rs:188-213
+    x = np.array([1.0, 2.0, 3.0])
+    jac = O.mean_jacobian(O.QUADRATIC, x)
+    e = 1e-6
+    for k in range(3):
+        xp, xm = x.copy(), x.copy()
+        xp[k] += e
+        xm[k] -= e
+        fd = (O.mean_value(O.QUADRATIC, xp[None])[0] - O.mean_value(O.QUADRATIC, xm[None])[0]) / (2 * e)
+        np.testing.assert_allclose(jac[:, k], fd, atol=1e-8)
