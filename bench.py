@@ -126,17 +126,24 @@ def cpu_sample(n, d, m, evals, sample_pts=1024):
     """Bounded sample of one step on the host cores: ONE likelihood evaluation at full n plus
     predict_valvar on `sample_pts` points, extrapolated to `evals` evaluations and m points."""
     from oracle import fast, gp_oracle as O
+    cores = len(os.sched_getaffinity(0))
+    # all host threads, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+    omp_threads = fast.set_threads(cores)
+    blas_threads = None
     try:
-        from threadpoolctl import threadpool_info
+        import scipy.linalg  # noqa: F401  (loads OpenBLAS before the pool is resized)
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=cores)
         blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
-        blas_threads = None
-    cores = len(os.sched_getaffinity(0))
+        pass
     x, y, xs, thetas = make_workload(n, d, sample_pts, 4, 0)
     xn, xm, xsd = normalize(x)
     yn, ym, ysd = normalize(y.reshape(-1, 1))
     fx = O.mean_value(O.CONSTANT, xn)
     theta = np.full(d, 1.0)
+    nw = min(n, 1024)       # warm the OpenMP / BLAS thread pools outside the timed sample
+    fast.reduced_likelihood(O.MATERN52, xn[:nw], fx[:nw], yn[:nw], float(ysd[0]), theta, np.eye(d))
     t0 = time.perf_counter()
     rlf, inner = fast.reduced_likelihood(O.MATERN52, xn, fx, yn, float(ysd[0]), theta, np.eye(d))
     t_eval = time.perf_counter() - t0
@@ -149,11 +156,26 @@ def cpu_sample(n, d, m, evals, sample_pts=1024):
     t_fit = evals * t_eval
     t_pred = (m / sample_pts) * t_chunk
     return {"value": m / (t_fit + t_pred), "unit": "points/s", "cores": cores, "blas_threads": blas_threads,
+            "omp_threads": omp_threads,
             "kind": "port",
             "sample": "1 likelihood eval at n=%d (%.2f s, x%d) + predict_var on %d points (%.2f s, x%.1f); "
                       "oracle port: C/OpenMP correlation + scipy LAPACK" % (n, t_eval, evals, sample_pts, t_chunk,
                                                                             m / sample_pts),
             "t_eval_s": t_eval, "t_predict_chunk_s": t_chunk, "rlf": rlf}
+
+
+def cpu_sample_clean_env(n, d, m, evals):
+    """Run cpu_sample in a child process whose environment does not pin the thread pools to one thread
+    (torchrun exports OMP_NUM_THREADS=1 and OpenBLAS sizes its pool from it at load time)."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "GOTO_NUM_THREADS")}
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-sample-only", "--ntrain", str(n), "--dim", str(d),
+           "--npred", str(m), "--evals", str(evals)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("cpu sample failed: %s" % r.stderr[-2000:])
 
 
 def run_reference(args):
@@ -163,7 +185,7 @@ def run_reference(args):
     times, last = [], None
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        last = cpu_sample(args.n, args.d, args.m, args.evals)
+        last = cpu_sample_clean_env(args.n, args.d, args.m, args.evals)
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     val = last["value"]
@@ -380,7 +402,7 @@ def run_ours(args):
                "failed_theta_in_sweep": n_fail,
                "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_sample(n, d, m, E)
+            out["cpu_baseline"] = cpu_sample_clean_env(n, d, m, E)
         print(json.dumps(out), flush=True)
     ctx.close()
     if world > 1:
@@ -399,7 +421,11 @@ def main():
     ap.add_argument("--evals", type=int, default=1101)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_sample_only:
+        print(json.dumps(cpu_sample(args.n, args.d, args.m, args.evals)), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

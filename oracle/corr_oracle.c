@@ -13,6 +13,25 @@
  */
 #include <math.h>
 #include <stddef.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline sets its thread count explicitly */
+void egx_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int egx_oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 static double pair_value(int kind, const double* a, const double* b, int d, int h, const double* theta,
                          const double* w) {

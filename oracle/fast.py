@@ -23,8 +23,17 @@ def _lib():
         lib.egx_oracle_corr_matrix.restype = None
         lib.egx_oracle_cross_corr.argtypes = [C.c_int, dp, C.c_int, dp, C.c_int, C.c_int, dp, dp, C.c_int, dp]
         lib.egx_oracle_cross_corr.restype = None
+        lib.egx_oracle_set_threads.argtypes = [C.c_int]
+        lib.egx_oracle_set_threads.restype = None
+        lib.egx_oracle_max_threads.restype = C.c_int
         _LIB = lib
     return _LIB
+
+
+def set_threads(n):
+    """Use n OpenMP threads in the C kernels (torchrun exports OMP_NUM_THREADS=1)."""
+    _lib().egx_oracle_set_threads(int(n))
+    return int(_lib().egx_oracle_max_threads())
 
 
 def _p(a):
