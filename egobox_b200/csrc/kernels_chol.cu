@@ -268,11 +268,6 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
 // cp.async pipeline over K in steps of 16.  The accumulators are initialised
 // with the C tile and A fragments are negated, so the epilogue is a pure store.
 // ---------------------------------------------------------------------------
-constexpr int GM_BK = 16;
-constexpr int GM_LDS = 20;                        // 16 + 4 pad doubles: conflict-free fragment loads
-constexpr int GM_STAGES = 3;
-constexpr int GM_TILE_ELEMS = EGX_NB * GM_LDS;    // per operand per stage
-constexpr int GM_K = EGX_NB;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
@@ -314,16 +309,20 @@ __device__ __forceinline__ void gemm_tile_decode(const GemmArgs& g, int t, int& 
     }
 }
 
-template <int BN>
+// ADD = false: C -= A B^T (the negation folds into the DMMA operand, SASS `DMMA R, -R, R, R`); ADD = true: C += A B^T
+// BK x STAGES: 16 x 3 (default) or 32 x 2 (half the barriers per tile, same shared-memory footprint class).
+template <int BN, bool ADD, int BK, int STAGES>
 __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(const GemmArgs g) {
     constexpr int WARPS_N = (BN == 128) ? 4 : 2;
     constexpr int WARPS_M = 8 / WARPS_N;
     constexpr int MI = EGX_NB / WARPS_M / 8;      // m8 tiles per warp
     constexpr int NI = BN / WARPS_N / 8;          // n8 tiles per warp
-    constexpr int A_ELEMS = EGX_NB * GM_LDS, B_ELEMS = BN * GM_LDS;
+    constexpr int LDS = BK + 4;                   // (4 g + t) mod 16 distinct: conflict-free fragment loads
+    constexpr int A_ELEMS = EGX_NB * LDS, B_ELEMS = BN * LDS;
+    constexpr int CH = BK / 2;                    // 16-byte chunks per row
     extern __shared__ __align__(16) double gsm[];
-    double* As = gsm;                               // [STAGES][128][20]
-    double* Bs = gsm + GM_STAGES * A_ELEMS;         // [STAGES][BN][20]
+    double* As = gsm;                               // [STAGES][128][LDS]
+    double* Bs = gsm + STAGES * A_ELEMS;            // [STAGES][BN][LDS]
 
     int tr, tc;
     gemm_tile_decode<BN>(g, blockIdx.x, tr, tc);
@@ -342,23 +341,22 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
         double* as = As + stage * A_ELEMS;
         double* bs = Bs + stage * B_ELEMS;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + i * 256;          // 1024 16-byte chunks of A
-            const int row = idx >> 3, ch = idx & 7;
-            cp_async16(as + row * GM_LDS + ch * 2, Ag + static_cast<long>(row) * g.lda + kb * GM_BK + ch * 2);
+        for (int i = 0; i < EGX_NB * CH / 256; ++i) {
+            const int idx = tid + i * 256;
+            const int row = idx / CH, ch = idx % CH;
+            cp_async16(as + row * LDS + ch * 2, Ag + static_cast<long>(row) * g.lda + kb * BK + ch * 2);
         }
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i) {
+        for (int i = 0; i < BN * CH / 256; ++i) {
             const int idx = tid + i * 256;
-            const int row = idx >> 3, ch = idx & 7;
-            cp_async16(bs + row * GM_LDS + ch * 2, Bg + static_cast<long>(row) * g.ldb + kb * GM_BK + ch * 2);
+            const int row = idx / CH, ch = idx % CH;
+            cp_async16(bs + row * LDS + ch * 2, Bg + static_cast<long>(row) * g.ldb + kb * BK + ch * 2);
         }
     };
 
-    const int KB = g.K / GM_BK;
-    const double sgn = g.add ? 1.0 : -1.0;
+    const int KB = g.K / BK;
 #pragma unroll
-    for (int s = 0; s < GM_STAGES - 1; ++s) {
+    for (int s = 0; s < STAGES - 1; ++s) {
         if (s < KB) load_stage(s, s);
         cp_async_commit();
     }
@@ -378,19 +376,19 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
 
 #pragma unroll 1
     for (int kb = 0; kb < KB; ++kb) {
-        cp_async_wait<GM_STAGES - 2>();
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (kb + GM_STAGES - 1 < KB) load_stage((kb + GM_STAGES - 1) % GM_STAGES, kb + GM_STAGES - 1);
+        if (kb + STAGES - 1 < KB) load_stage((kb + STAGES - 1) % STAGES, kb + STAGES - 1);
         cp_async_commit();
-        const double* as = As + (kb % GM_STAGES) * A_ELEMS + (wm * (MI * 8) + gid) * GM_LDS + tig;
-        const double* bs = Bs + (kb % GM_STAGES) * B_ELEMS + (wn * (NI * 8) + gid) * GM_LDS + tig;
+        const double* as = As + (kb % STAGES) * A_ELEMS + (wm * (MI * 8) + gid) * LDS + tig;
+        const double* bs = Bs + (kb % STAGES) * B_ELEMS + (wn * (NI * 8) + gid) * LDS + tig;
 #pragma unroll
-        for (int kk = 0; kk < GM_BK / 4; ++kk) {
+        for (int kk = 0; kk < BK / 4; ++kk) {
             double a[MI], b[NI];
 #pragma unroll
-            for (int mi = 0; mi < MI; ++mi) a[mi] = sgn * as[mi * 8 * GM_LDS + kk * 4];
+            for (int mi = 0; mi < MI; ++mi) a[mi] = ADD ? as[mi * 8 * LDS + kk * 4] : -as[mi * 8 * LDS + kk * 4];
 #pragma unroll
-            for (int ni = 0; ni < NI; ++ni) b[ni] = bs[ni * 8 * GM_LDS + kk * 4];
+            for (int ni = 0; ni < NI; ++ni) b[ni] = bs[ni * 8 * LDS + kk * 4];
 #pragma unroll
             for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
@@ -412,7 +410,7 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
 
 }  // namespace
 
-int gemm_smem_bytes() { return GM_STAGES * (EGX_NB + 128) * GM_LDS * static_cast<int>(sizeof(double)); }
+int gemm_smem_bytes() { return 3 * (EGX_NB + 128) * 20 * static_cast<int>(sizeof(double)); }
 
 void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* Dinv, cudaStream_t s) {
     potrf_diag_kernel<<<1, 256, 0, s>>>(Akk, ld, info, base_index, Dinv);
@@ -420,7 +418,10 @@ void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* 
 
 void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, int nblocks64,
                       cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& configured = configured_dev[dev_ & 63];   // the attribute is per device (one process may drive several)
     const int smem = (TR_ROWS * TR_LDX + 4 * 32 * TR_LDD + 32 * TR_LDL) * sizeof(double);
     if (!configured) {
         cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -430,30 +431,50 @@ void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const do
     trsm_rows_kernel<<<nblocks64, 256, smem, s>>>(X, ldx, Lkk, ldl, Dinv, P);
 }
 
+static int gemm_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e != nullptr ? atoi(e) : dflt;
+}
 static int gemm_bn() {
     static int bn = 0;
-    if (bn == 0) {
-        const char* e = getenv("EGX_GEMM_BN");
-        bn = (e != nullptr && atoi(e) == 128) ? 128 : 64;
-    }
+    if (bn == 0) bn = (gemm_env("EGX_GEMM_BN", 64) == 128) ? 128 : 64;
     return bn;
+}
+static int gemm_bk() {
+    static int bk = 0;
+    if (bk == 0) bk = (gemm_env("EGX_GEMM_BK", 16) == 32) ? 32 : 16;
+    return bk;
+}
+
+template <int BN, int BK, int STAGES>
+static void gemm_launch_variant(const GemmArgs& g, dim3 grid, cudaStream_t s) {
+    constexpr int smem = STAGES * (EGX_NB + BN) * (BK + 4) * static_cast<int>(sizeof(double));
+    static bool configured_dev[64] = {false};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& configured = configured_dev[dev_ & 63];   // the attribute is per device (one process may drive several)
+    if (!configured) {
+        cudaFuncSetAttribute(gemm_nt_sub_kernel<BN, false, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(gemm_nt_sub_kernel<BN, true, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    if (g.add) gemm_nt_sub_kernel<BN, true, BK, STAGES><<<grid, 256, smem, s>>>(g);
+    else gemm_nt_sub_kernel<BN, false, BK, STAGES><<<grid, 256, smem, s>>>(g);
 }
 
 void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s) {
-    static bool configured = false;
-    const int smem128 = GM_STAGES * (EGX_NB + 128) * GM_LDS * static_cast<int>(sizeof(double));
-    const int smem64 = GM_STAGES * (EGX_NB + 64) * GM_LDS * static_cast<int>(sizeof(double));
-    if (!configured) {
-        cudaFuncSetAttribute(gemm_nt_sub_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem128);
-        cudaFuncSetAttribute(gemm_nt_sub_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
-        configured = true;
-    }
     const int S = (gemm_bn() == 128) ? 1 : 2;
     int tiles;
     if (g.tri > 0) tiles = S * g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * S * g.tri;
     else tiles = g.Mt * S * g.Nt;
     if (tiles <= 0) return;
     const dim3 grid(tiles, g.splits > 1 ? g.splits : 1);
-    if (S == 1) gemm_nt_sub_kernel<128><<<grid, 256, smem128, s>>>(g);
-    else gemm_nt_sub_kernel<64><<<grid, 256, smem64, s>>>(g);
+    const bool bk32 = gemm_bk() == 32 && (g.K % 32 == 0);
+    if (S == 1) {
+        if (bk32) gemm_launch_variant<128, 32, 2>(g, grid, s);
+        else gemm_launch_variant<128, 16, 3>(g, grid, s);
+    } else {
+        if (bk32) gemm_launch_variant<64, 32, 2>(g, grid, s);
+        else gemm_launch_variant<64, 16, 3>(g, grid, s);
+    }
 }

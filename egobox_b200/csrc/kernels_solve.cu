@@ -254,7 +254,10 @@ void launch_gls(const double* M, long ld, int n, int npad, int p, double* work, 
 }
 
 void launch_backsolve_diag(const double* Lkk, long ld, double* rho_k, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_dev[64] = {false};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& configured = configured_dev[dev_ & 63];   // the attribute is per device (one process may drive several)
     const int smem = EGX_NB * EGX_NB * sizeof(double);
     if (!configured) {
         cudaFuncSetAttribute(backsolve_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

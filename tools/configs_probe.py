@@ -10,8 +10,7 @@ import numpy as np
 
 sys.path.insert(0, ".")
 import egobox_b200 as eg                                   # noqa: E402
-from tests.gpu_util import make_problem, make_context      # noqa: E402
-from oracle import gp_oracle as O                          # noqa: E402  (input generation / normalisation only)
+from tools._util import make_problem, make_context         # noqa: E402
 
 
 def c1():
@@ -43,7 +42,7 @@ def c5():
     d, B = 20, 512
     for n in (21, 100, 2048):
         x, y = make_problem(n, d, seed=5)
-        ctx, _ = make_context(x, y, O.MATERN52, O.CONSTANT)
+        ctx = make_context(x, y, eg.MATERN52, eg.CONSTANT)
         thetas = 10.0 ** np.random.default_rng(42).uniform(-2.0, 1.0, size=(B, d))
         ctx.reduced_likelihood_batch(thetas[:32])
         t0 = time.perf_counter()

@@ -7,8 +7,8 @@ import time
 import numpy as np
 
 sys.path.insert(0, ".")
-from oracle import gp_oracle as O          # noqa: E402  (probe = test infrastructure)
-from tests.gpu_util import make_problem, make_context   # noqa: E402
+import egobox_b200 as eg                                  # noqa: E402
+from tools._util import make_problem, make_context        # noqa: E402
 
 
 def main():
@@ -16,7 +16,7 @@ def main():
     for n in sizes:
         d = 10
         x, y = make_problem(n, d, seed=42)
-        ctx, _ = make_context(x, y, O.MATERN52, O.CONSTANT)
+        ctx = make_context(x, y, eg.MATERN52, eg.CONSTANT)
         theta = np.full(d, 1.0)
         for _ in range(2):
             ctx.reduced_likelihood(theta)

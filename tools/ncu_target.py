@@ -5,13 +5,13 @@ import sys
 import numpy as np
 
 sys.path.insert(0, ".")
-from tests.gpu_util import make_problem, make_context   # noqa: E402
-from oracle import gp_oracle as O                       # noqa: E402  (input generation only)
+import egobox_b200 as eg                                # noqa: E402
+from tools._util import make_problem, make_context      # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 x, y = make_problem(n, 10, seed=42)
-ctx, _ = make_context(x, y, O.MATERN52, O.CONSTANT)
+ctx = make_context(x, y, eg.MATERN52, eg.CONSTANT)
 theta = np.full(10, 1.0)
 st, rlf = ctx.reduced_likelihood(theta)
 st, res = ctx.finalize(theta, want_ft=False)

@@ -33,8 +33,4 @@ t0 = time.perf_counter()
 v = ctx.predict_var(xs)
 t1 = time.perf_counter()
 print(json.dumps({"predict_var_100k_ms": (t1 - t0) * 1e3, "var_mean": float(v.mean())}))
-if N <= 20000:
-    from oracle import sgp_oracle as S, gp_oracle as O
-    ref = S.build(S.FITC, O.MATERN52, theta, 1.0, 0.01, x, y, z)
-    print(json.dumps({"oracle_lik": ref.likelihood, "rel_err": abs(lik - ref.likelihood) / abs(ref.likelihood)}))
 ctx.close()
