@@ -76,6 +76,14 @@ class GpContext:
             self._h, _ptr(th), B, _ptr(rlf), status.ctypes.data_as(C.POINTER(C.c_int))))
         return status, rlf
 
+    def reduced_likelihood_grad(self, theta, rel_step=1e-6):
+        """-> (status, rlf, d rlf / d theta) by one batch of 2h+1 evaluations (central differences)."""
+        th = _f64(theta).reshape(-1)
+        out = C.c_double()
+        g = np.empty(self.h)
+        st = self._check(self._lib.egx_gp_reduced_likelihood_grad(self._h, _ptr(th), float(rel_step), C.byref(out), _ptr(g)))
+        return st, out.value, g
+
     def finalize(self, theta, want_ft=True):
         th = _f64(theta).reshape(-1)
         rlf, s2 = C.c_double(), C.c_double()

@@ -635,6 +635,29 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
     return EGX_OK;
 }
 
+extern "C" int egx_gp_reduced_likelihood_grad(egx_gp_ctx* c, const double* theta, double rel_step, double* rlf,
+                                              double* grad) {
+    if (!c || !theta || !rlf || !grad || !(rel_step > 0.0)) return EGX_INVALID_VALUE;
+    const int h = c->h, B = 2 * h + 1;
+    std::vector<double> th(static_cast<size_t>(B) * h), val(B);
+    std::vector<int> st(B);
+    for (int b = 0; b < B; ++b)
+        for (int l = 0; l < h; ++l) th[static_cast<size_t>(b) * h + l] = theta[l];
+    for (int k = 0; k < h; ++k) {
+        const double dk = rel_step * theta[k];
+        th[static_cast<size_t>(1 + 2 * k) * h + k] = theta[k] + dk;
+        th[static_cast<size_t>(2 + 2 * k) * h + k] = theta[k] - dk;
+    }
+    const int rc = egx_gp_reduced_likelihood_batch(c, th.data(), B, val.data(), st.data());
+    if (rc != EGX_OK) return rc;
+    *rlf = val[0];
+    for (int k = 0; k < h; ++k) {
+        const double hi = th[static_cast<size_t>(1 + 2 * k) * h + k], lo = th[static_cast<size_t>(2 + 2 * k) * h + k];
+        grad[k] = (st[1 + 2 * k] == EGX_OK && st[2 + 2 * k] == EGX_OK) ? (val[1 + 2 * k] - val[2 + 2 * k]) / (hi - lo) : NAN;
+    }
+    return st[0];
+}
+
 extern "C" int egx_gp_finalize(egx_gp_ctx* c, const double* theta, double* rlf, double* sigma2, double* beta,
                                double* gamma, double* ft, double* ft_qr_r) {
     if (!c || !theta) return EGX_INVALID_VALUE;

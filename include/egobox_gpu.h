@@ -94,6 +94,14 @@ int egx_gp_reduced_likelihood(egx_gp_ctx* ctx, const double* theta, double* rlf)
 int egx_gp_reduced_likelihood_batch(egx_gp_ctx* ctx, const double* thetas, int B,
                                     double* rlf, int* status);
 
+/* Reduced likelihood and its theta-gradient by central differences, d rlf / d theta_k ~
+ * (rlf(theta + delta_k e_k) - rlf(theta - delta_k e_k)) / (2 delta_k), delta_k = rel_step * theta_k, evaluated as ONE
+ * batch of 2h+1 likelihoods (kept in flight together).  The reference has no theta-gradient
+ * (gp/src/algorithm.rs:880 ignores `_gradient`; COBYLA is derivative free); this is the batched building block
+ * for gradient-based callers.  Returns the status of the centre point; grad[k] is NaN where a side point failed. */
+int egx_gp_reduced_likelihood_grad(egx_gp_ctx* ctx, const double* theta, double rel_step, double* rlf,
+                                   double* grad);
+
 /* Final evaluation at the selected theta (gp/src/algorithm.rs:966-968): keeps
  * the Cholesky factor, gamma, beta, Ft, G on the device for predict*, and
  * optionally returns GpInnerParams (algorithm.rs:47-60) -- any output pointer

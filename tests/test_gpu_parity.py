@@ -382,3 +382,24 @@ def test_predict_gradients_kpls_weights():
         g_ref = gp.predict_gradients(xs)
         np.testing.assert_allclose(ctx.predict_gradients(xs), g_ref, rtol=1e-7, atol=1e-8 * np.abs(g_ref).max())
         ctx.close()
+
+
+def test_theta_gradient_central_differences():
+    """SURVEY 7 (hard part 7): the reference has no theta-gradient; the oracle for ours is the central finite
+    difference of the ORACLE's rlf with the same step."""
+    n, d = 150, 3
+    x, y = make_problem(n, d, seed=77)
+    ctx, (xn, xm, xs, yn, ym, ys) = make_context(x, y, O.MATERN52, O.CONSTANT)
+    theta = np.array([1.5, 0.9, 2.2])
+    st, rlf, g = ctx.reduced_likelihood_grad(theta, rel_step=1e-5)
+    assert st == 0
+    fx = O.mean_value(O.CONSTANT, xn)
+    f = lambda t: O.reduced_likelihood(O.MATERN52, xn, fx, yn, ys, t, np.eye(d))[0]
+    assert rlf == pytest.approx(f(theta), rel=1e-9)
+    for k in range(d):
+        tp, tm = theta.copy(), theta.copy()
+        tp[k] += 1e-5 * theta[k]
+        tm[k] -= 1e-5 * theta[k]
+        ref = (f(tp) - f(tm)) / (tp[k] - tm[k])
+        assert g[k] == pytest.approx(ref, rel=1e-4, abs=1e-6)
+    ctx.close()
