@@ -125,6 +125,12 @@ class GpContext:
         self._check(self._lib.egx_gp_predict_gradients(self._h, _ptr(x), x.shape[0], _ptr(g)))
         return g
 
+    def predict_var_gradients(self, x):
+        x = _f64(x).reshape(-1, self.d)
+        g = np.empty((x.shape[0], self.d))
+        self._check(self._lib.egx_gp_predict_var_gradients(self._h, _ptr(x), x.shape[0], _ptr(g)))
+        return g
+
     def predict_valvar_dev(self, x_ptr, m, y_ptr, v_ptr):
         """x/y/var are raw device addresses (ints) on this context's GPU."""
         self._check(self._lib.egx_gp_predict_valvar_dev(self._h, C.c_void_p(x_ptr), m,

@@ -95,3 +95,12 @@ struct SmallOutHost {
     double rlf, sigma2;
     int info, pad_;
 };
+// kernels_grad.cu
+void launch_transpose_lower(const double* L, long ld, double* LT, int T, cudaStream_t s);
+void launch_trsm_rows_upper(double* X, long ldx, const double* LTkk, long ldl, const double* Dinv, double* P,
+                            int nblocks64, cudaStream_t s);
+size_t var_grad_smem_bytes(int d, int p, int nterms);
+void launch_var_grad(int corr, const double* W, long ldw, const double* xraw, int m, const double* x_mean,
+                     const double* x_std, const double* X, int n, int npad, int d, const CorrTerm* terms, int nterms,
+                     const double* KF, long ldk, const double* G, int p, const int* basis_i, const int* basis_j,
+                     double sigma2, double* out, cudaStream_t s);

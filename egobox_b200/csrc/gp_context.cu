@@ -128,6 +128,10 @@ struct egx_gp_ctx {
     std::vector<double> theta;
     double sigma2_scaled = 0.0;
 
+    // variance-gradient state (built lazily after a finalize): transposed factor and K_F = R^-1 F
+    double *LT = nullptr, *KF = nullptr;
+    bool grad_ready = false;
+
     // predict buffers
     double *Y = nullptr, *xchunk = nullptr, *ychunk = nullptr, *vchunk = nullptr;
     int mb_alloc = 0;
@@ -277,6 +281,7 @@ int evaluate_small_batch(egx_gp_ctx* c, const double* thetas, int B, double* rlf
 // result block and applies the host-side status logic.
 int evaluate_launch(egx_gp_ctx* c, const double* theta) {
     c->trained = false;
+    c->grad_ready = false;
     c->pending_eval = false;
     int st = assemble(c, theta);
     if (st != EGX_OK) return st;
@@ -425,6 +430,8 @@ void free_ctx(egx_gp_ctx* c) {
     cudaFree(c->basis_j);
     cudaFree(c->terms);
     cudaFree(c->M);
+    cudaFree(c->LT);
+    cudaFree(c->KF);
     cudaFree(c->W_dev);
     cudaFree(c->sb_thetas);
     cudaFree(c->sb_G);
@@ -757,6 +764,91 @@ extern "C" int egx_gp_predict_gradients(egx_gp_ctx* c, const double* x, int m, d
     cudaFree(gd);
     if (st != EGX_OK || cudaGetLastError() != cudaSuccess) {
         egx_set_error("predict_gradients: CUDA failure");
+        return EGX_CUDA_ERROR;
+    }
+    resolve_profile(c);
+    return EGX_OK;
+}
+extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int m, double* grad) {
+    if (!c || !x || !grad || m < 0) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->trained) {
+        egx_set_error("predict_var_gradients called before a successful egx_gp_finalize");
+        return EGX_INVALID_VALUE;
+    }
+    if (c->d > 32 || static_cast<long>(c->d) * c->p > 2048) {
+        egx_set_error("predict_var_gradients supports d <= 32 and d * p <= 2048 (got d=%d, p=%d)", c->d, c->p);
+        return EGX_INVALID_VALUE;
+    }
+    if (m == 0) return EGX_OK;
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    const int T = c->npad / EGX_NB;
+    const long ld = c->ld;
+    if (!c->grad_ready) {
+        if (!c->LT) EGX_CUDA_TRY(cudaMalloc(&c->LT, static_cast<size_t>(c->npad) * ld * sizeof(double)));
+        if (!c->KF) EGX_CUDA_TRY(cudaMalloc(&c->KF, static_cast<size_t>(c->p) * c->npad * sizeof(double)));
+        launch_transpose_lower(c->M, ld, c->LT, T, c->stream);
+        // K_F = R^-1 F = L^-T (L^-1 F): rows npad.. of M hold (L^-1 F)^T, one back substitution per basis function
+        EGX_CUDA_TRY(cudaMemcpy2DAsync(c->KF, c->npad * sizeof(double), c->M + static_cast<long>(c->npad) * ld,
+                                       ld * sizeof(double), c->npad * sizeof(double), c->p, cudaMemcpyDeviceToDevice,
+                                       c->stream));
+        for (int l = 0; l < c->p; ++l) backsolve_vector(c->env, factor_ref(c), c->KF + static_cast<long>(l) * c->npad);
+        c->grad_ready = true;
+    }
+    const int mb = std::min(round_up(m, EGX_NB), PREDICT_CHUNK);
+    int st = ensure_predict_buffers(c, mb);
+    if (st != EGX_OK) return st;
+    double* gd = nullptr;
+    EGX_CUDA_TRY(cudaMalloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    for (int i0 = 0; i0 < m && st == EGX_OK; i0 += mb) {
+        const int mc = std::min(mb, m - i0);
+        const int mpad = round_up(mc, EGX_NB);
+        cudaMemcpyAsync(c->xchunk, x + static_cast<long>(i0) * c->d, static_cast<size_t>(mc) * c->d * sizeof(double),
+                        cudaMemcpyHostToDevice, c->stream);
+        {
+            StageScope sc(c->env.prof, EGX_STAGE_CROSS_CORR, 1, c->stream);
+            launch_cross_corr(c->corr, c->xchunk, mc, mpad, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d, c->terms,
+                              c->nterms, nullptr, nullptr, c->basis_i, c->basis_j, 0, 0.0, 1.0, c->Y, c->npad, nullptr,
+                              c->stream);
+        }
+        blocked_sweep(c->env, factor_ref(c), false, c->Y, c->npad, mpad / EGX_NB, mpad / 64);     // Y <- C L^-T
+        // backward sweep Y <- Y L^-1 on the transposed factor (W = C R^-1)
+        for (int k = T - 1; k >= 0; --k) {
+            double* Pk = c->env.P2[k & 1];
+            {
+                StageScope sc(c->env.prof, EGX_STAGE_TRSM_PANEL, 1, c->stream);
+                launch_trsm_rows_upper(c->Y + static_cast<long>(k) * EGX_NB, c->npad,
+                                       c->LT + static_cast<long>(k) * EGX_NB * ld + static_cast<long>(k) * EGX_NB, ld,
+                                       c->Dinv + static_cast<long>(k) * 4096, Pk, mpad / 64, c->stream);
+            }
+            if (k > 0) {
+                GemmArgs g;
+                g.C = c->Y;
+                g.ldc = c->npad;
+                g.A = Pk;
+                g.lda = EGX_NB;
+                g.B = c->LT + static_cast<long>(k) * EGX_NB;      // rows 0 .. k*128-1 of LT, columns of block k
+                g.ldb = ld;
+                g.tri = 0;
+                g.Mt = mpad / EGX_NB;
+                g.Nt = k;
+                StageScope sc(c->env.prof, EGX_STAGE_SYRK_GEMM, 1, c->stream);
+                launch_gemm_nt_sub(g, c->stream);
+            }
+        }
+        {
+            StageScope sc(c->env.prof, EGX_STAGE_VAR_FINISH, 1, c->stream);
+            launch_var_grad(c->corr, c->Y, c->npad, c->xchunk, mc, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d,
+                            c->terms, c->nterms, c->KF, c->npad, c->G, c->p, c->basis_i, c->basis_j, c->sigma2_scaled,
+                            gd, c->stream);
+        }
+        cudaMemcpyAsync(grad + static_cast<long>(i0) * c->d, gd, static_cast<size_t>(mc) * c->d * sizeof(double),
+                        cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = EGX_CUDA_ERROR;
+    }
+    cudaFree(gd);
+    if (st != EGX_OK || cudaGetLastError() != cudaSuccess) {
+        egx_set_error("predict_var_gradients: CUDA failure (%s)", cudaGetErrorString(cudaGetLastError()));
         return EGX_CUDA_ERROR;
     }
     resolve_profile(c);

@@ -778,6 +778,10 @@ extern "C" int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int
     return egx_gp_predict_valvar(m->ctx, x, npts, y, var);
 }
 
+extern "C" int egx_gp_model_predict_var_gradients(egx_gp_model* m, const double* x, int npts, double* grad) {
+    if (!m) return EGX_INVALID_VALUE;
+    return egx_gp_predict_var_gradients(m->ctx, x, npts, grad);
+}
 extern "C" int egx_gp_model_predict_gradients(egx_gp_model* m, const double* x, int npts, double* grad) {
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_predict_gradients(m->ctx, x, npts, grad);

@@ -278,6 +278,20 @@ class GaussianProcess:
             _raise_status(st)
         return g
 
+    def predict_var_gradients(self, x):
+        """algorithm.rs:697-704: (n, nx) matrix of variance derivatives."""
+        x = self._x(x)
+        g = np.empty((x.shape[0], self._d))
+        st = self._lib.egx_gp_model_predict_var_gradients(self._h, x.ctypes.data_as(C.POINTER(C.c_double)), x.shape[0],
+                                                          g.ctypes.data_as(C.POINTER(C.c_double)))
+        if st != EGX_OK:
+            _raise_status(st)
+        return g
+
+    def predict_valvar_gradients(self, x):
+        """algorithm.rs:708-727."""
+        return self.predict_gradients(x), self.predict_var_gradients(x)
+
     def theta(self):
         th = np.empty(self._hdim)
         self._lib.egx_gp_model_theta(self._h, th.ctypes.data_as(C.POINTER(C.c_double)))

@@ -111,7 +111,8 @@ class Gpx:
         return self._gp.predict_gradients(np.asarray(x, dtype=np.float64))
 
     def predict_var_gradients(self, x):
-        raise NotImplementedError("batched variance gradients: SURVEY.md 8(f)-1 (next)")
+        """gp_mix.rs:394-404: (nsamples, nx) variance derivatives."""
+        return self._gp.predict_var_gradients(np.asarray(x, dtype=np.float64))
 
     def sample(self, x, n_traj):
         raise NotImplementedError("conditional sampling: SURVEY.md 8(f)-4 (next)")

@@ -127,6 +127,10 @@ int egx_gp_predict_valvar(egx_gp_ctx* ctx, const double* x, int m, double* y, do
  *   predict_gradients gp/src/algorithm.rs:518-529 (one `predict_jacobian` :533-566 per point in the
  *   reference; one warp per point here).  Supports d <= 32. */
 int egx_gp_predict_gradients(egx_gp_ctx* ctx, const double* x, int m, double* grad);
+/* Batched variance gradients d var / d x (m x d): predict_var_gradients gp/src/algorithm.rs:697-704, one
+ * `predict_var_gradients_single` :554-616 (four n x n triangular solves) per point in the reference; here one
+ * forward and one backward multi-RHS sweep per chunk of points.  Supports d <= 32 and d * p <= 2048. */
+int egx_gp_predict_var_gradients(egx_gp_ctx* ctx, const double* x, int m, double* grad);
 
 /* Same, with x / y / var already resident on the context's device (device
  * pointers).  Used to time the kernels without the PCIe copies. */
@@ -253,6 +257,7 @@ int egx_gp_model_predict(egx_gp_model* m, const double* x, int npts, double* y);
 int egx_gp_model_predict_var(egx_gp_model* m, const double* x, int npts, double* var);
 int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int npts, double* y, double* var);
 int egx_gp_model_predict_gradients(egx_gp_model* m, const double* x, int npts, double* grad /* npts x d */);
+int egx_gp_model_predict_var_gradients(egx_gp_model* m, const double* x, int npts, double* grad /* npts x d */);
 
 /* ============================================================================
  * Sparse GP (FITC / VFE) -- crates/gp/src/sparse_algorithm.rs.

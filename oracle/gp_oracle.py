@@ -411,6 +411,34 @@ class GaussianProcess:
             out[i] = dr_dx[:, 0] * self.y_std / self.x_std
         return out
 
+    # algorithm.rs:554-616 predict_var_gradients_single, :697-704 predict_var_gradients
+    def predict_var_gradients(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        out = np.zeros((x.shape[0], self.xt_norm.shape[1]))
+        L = self.inner.r_chol
+        f_mean = mean_value(self.mean, self.xt_norm)
+        rho2 = sla.solve_triangular(L, f_mean, lower=True, check_finite=False)
+        inv_kf = sla.solve_triangular(L.T, rho2, lower=False, check_finite=False)            # R^-1 F
+        b_mat = f_mean.T.dot(inv_kf)
+        rho3 = sla.cholesky(b_mat, lower=True, check_finite=False)
+        for i in range(x.shape[0]):
+            xn = ((x[i] - self.x_mean) / self.x_std)[None, :]
+            r = corr_value(self.corr, xn - self.xt_norm, self.theta, self.w_star)[:, None]   # (n, 1)
+            dr = corr_jacobian(self.corr, xn[0], self.xt_norm, self.theta, self.w_star)      # (n, nx)
+            rho1 = sla.solve_triangular(L, r, lower=True, check_finite=False)
+            inv_kr = sla.solve_triangular(L.T, rho1, lower=False, check_finite=False)        # R^-1 r
+            p2 = inv_kr.T.dot(dr)                                                            # (1, nx)
+            f_x = mean_value(self.mean, xn).T                                                # (p, 1)
+            a_mat = f_x.T - r.T.dot(inv_kf)                                                  # (1, p)
+            inv_bat = sla.solve_triangular(rho3, a_mat.T, lower=True, check_finite=False)
+            d_mat = sla.solve_triangular(rho3.T, inv_bat, lower=False, check_finite=False)   # B^-1 A^T
+            df = mean_jacobian(self.mean, xn[0])                                             # (p, nx)
+            d_a = df.T - dr.T.dot(inv_kf)                                                    # (nx, p)
+            p4 = d_mat.T.dot(d_a.T)                                                          # (1, nx)
+            prime = 2.0 * (p4 - p2)
+            out[i] = (prime / self.x_std * self.inner.sigma2)[0]
+        return out
+
     # algorithm.rs:267-279
     def predict_var(self, x, chunk=1024):
         return self.predict_valvar(x, chunk)[1]

@@ -29,6 +29,8 @@ def test_gpx_kriging(krg5):
     assert gpx.predict_var(np.array([[1.1]])).item() == pytest.approx(0.0, abs=1e-3)
     # test_gpmix.py:48-50
     assert gpx.predict_gradients(np.array([[1.1]])).item() == pytest.approx(1.1204, abs=1e-3)
+    # test_gpmix.py:51-53
+    assert gpx.predict_var_gradients(np.array([[1.1]])).item() == pytest.approx(0.0145, abs=1e-3)
     assert gpx.thetas().shape == (1, 1)
     assert gpx.thetas().item() == pytest.approx(krg5["theta"], rel=5e-3)
     assert gpx.likelihoods().item() == pytest.approx(krg5["likelihood"], rel=1e-6)

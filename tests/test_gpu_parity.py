@@ -403,3 +403,45 @@ def test_theta_gradient_central_differences():
         ref = (f(tp) - f(tm)) / (tp[k] - tm[k])
         assert g[k] == pytest.approx(ref, rel=1e-4, abs=1e-6)
     ctx.close()
+
+
+# ------------------------------------------------- batched variance gradients ------------
+@pytest.mark.parametrize("n,d,corr,mean", [
+    (12, 2, O.SQEXP, O.CONSTANT),
+    (140, 1, O.SQEXP, O.CONSTANT),
+    (300, 3, O.MATERN52, O.CONSTANT),
+    (260, 2, O.MATERN32, O.LINEAR),
+    (200, 3, O.MATERN52, O.QUADRATIC),
+    (180, 10, O.MATERN52, O.CONSTANT),
+])
+def test_predict_var_gradients(n, d, corr, mean):
+    x, y = make_problem(n, d, seed=41)
+    theta = np.full(d, 1.3) if corr != O.SQEXP else np.full(d, 30.0 if n > 20 else 0.4)
+    ctx, _ = make_context(x, y, corr, mean)
+    gp = oracle_gp(x, y, corr, mean, theta)
+    st, _res = ctx.finalize(theta)
+    assert st == 0
+    xs = np.random.default_rng(9).random((29, d))
+    g_ref = gp.predict_var_gradients(xs)
+    g = ctx.predict_var_gradients(xs)
+    np.testing.assert_allclose(g, g_ref, rtol=1e-6, atol=1e-7 * np.abs(g_ref).max())
+    ctx.close()
+
+
+def test_bug_var_derivatives_through_gpu():
+    """gp/src/algorithm.rs:1723-1786 on the GPU path: analytic variance gradient vs central FD of predict_var."""
+    xt = np.array([[6.875, -4.375], [-3.125, 1.875], [1.875, -1.875], [-4.375, 3.125], [8.125, 9.375],
+                   [4.375, 4.375], [0.625, 0.625], [9.375, 6.875], [5.625, 8.125], [-0.625, -3.125],
+                   [3.125, 5.625], [-1.875, -0.625]])
+    yt = np.array([2.43286801, 13.10840811, 5.32908578, 17.81862219, 74.08849877, 39.68137781, 14.96009727,
+                   63.17475741, 61.26331775, -7.46009727, 44.39159189, 2.17091422])
+    theta = np.array([np.sqrt(2 * 0.0437386), np.sqrt(2 * 0.00697978)])
+    ctx, _ = make_context(xt, yt, O.SQEXP, O.CONSTANT)
+    st, _res = ctx.finalize(theta)
+    assert st == 0
+    e, xa, xb = 5e-6, -1.3, 2.5
+    v = ctx.predict_var(np.array([[xa, xb], [xa + e, xb], [xa - e, xb], [xa, xb + e], [xa, xb - e]]))
+    g = ctx.predict_var_gradients(np.array([[xa, xb]]))
+    assert g[0, 0] == pytest.approx((v[1] - v[2]) / (2 * e), abs=1e-5)
+    assert g[0, 1] == pytest.approx((v[3] - v[4]) / (2 * e), abs=1e-5)
+    ctx.close()

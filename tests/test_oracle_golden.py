@@ -245,3 +245,46 @@ def test_quadratic_mean_jacobian():
         xm[k] -= e
         fd = (O.mean_value(O.QUADRATIC, xp[None])[0] - O.mean_value(O.QUADRATIC, xm[None])[0]) / (2 * e)
         np.testing.assert_allclose(jac[:, k], fd, atol=1e-8)
+
+
+def test_bug_var_derivatives_fixture():
+    """gp/src/algorithm.rs:1723-1786: fixed theta, fixed 12-point data, analytic variance gradient vs
+    central finite differences of predict_var to 1e-5."""
+    xt = np.array([[6.875, -4.375], [-3.125, 1.875], [1.875, -1.875], [-4.375, 3.125], [8.125, 9.375],
+                   [4.375, 4.375], [0.625, 0.625], [9.375, 6.875], [5.625, 8.125], [-0.625, -3.125],
+                   [3.125, 5.625], [-1.875, -0.625]])
+    yt = np.array([2.43286801, 13.10840811, 5.32908578, 17.81862219, 74.08849877, 39.68137781, 14.96009727,
+                   63.17475741, 61.26331775, -7.46009727, 44.39159189, 2.17091422])
+    theta = [np.sqrt(2 * 0.0437386), np.sqrt(2 * 0.00697978)]
+    gp = O.fit(xt, yt, corr=O.SQEXP, mean=O.CONSTANT, theta_init=theta, fixed=True)
+    e, xa, xb = 5e-6, -1.3, 2.5
+    xq = np.array([[xa, xb], [xa + e, xb], [xa - e, xb], [xa, xb + e], [xa, xb - e]])
+    v = gp.predict_var(xq)
+    g = gp.predict_var_gradients(np.array([[xa, xb]]))
+    assert g[0, 0] == pytest.approx((v[1] - v[2]) / (2 * e), abs=1e-5)
+    assert g[0, 1] == pytest.approx((v[3] - v[4]) / (2 * e), abs=1e-5)
+
+
+def test_kriging5_predict_var_gradients(krg5):
+    # python/egobox/tests/test_gpmix.py:51-53: predict_var_gradients(1.1) = 0.0145 (+- 1e-3)
+    xt = np.array(krg5["xt"])[:, None]
+    gp = O.fit(xt, krg5["yt"], theta_init=[krg5["theta"]], fixed=True)
+    g = gp.predict_var_gradients(np.array([[1.1]]))
+    assert g[0, 0] == pytest.approx(0.0145, abs=1e-3)
+
+
+@pytest.mark.parametrize("corr,mean", [(O.MATERN52, O.LINEAR), (O.MATERN32, O.QUADRATIC), (O.ABSEXP, O.CONSTANT)])
+def test_var_gradients_vs_fd_general(corr, mean):
+    rng = np.random.default_rng(4)
+    x = rng.random((40, 2)) * 3
+    y = np.sin(x[:, 0]) + x[:, 1] ** 2
+    gp = O.fit(x, y, corr=corr, mean=mean, theta_init=[0.8, 1.3], fixed=True)
+    xq = np.array([[1.234, 0.777]])
+    g = gp.predict_var_gradients(xq)
+    e = 1e-6
+    for k in range(2):
+        xp, xm = xq.copy(), xq.copy()
+        xp[0, k] += e
+        xm[0, k] -= e
+        fd = (gp.predict_var(xp)[0] - gp.predict_var(xm)[0]) / (2 * e)
+        assert g[0, k] == pytest.approx(fd, rel=1e-4, abs=1e-7)
