@@ -136,6 +136,76 @@ class Gpx:
     def gp(self):
         return self._gp
 
+    # ---- persistence (gp_mix.rs:310-337; moe/src/algorithm.rs:510-524, 1096-1106) -----------------
+    def _expert_dict(self):
+        """The `experts[0]` object in the reference's serde-JSON layout (ndarray = {"v":1,"dim":[..],"data":[..]}),
+        as printed in doc/Gpx_Tutorial.ipynb:421 (GpInnerParams gp/src/algorithm.rs:41-60, GaussianProcess :165-192)."""
+        gp = self._gp
+        p = gp.params_
+        ip = gp.inner_params()
+        nz = gp.normalization()
+        x, y = gp.training_data
+        xn = (x - nz["x_mean"]) / nz["x_std"]
+        yn = ((y - nz["y_mean"]) / nz["y_std"])[:, None]
+
+        def arr(a):
+            a = np.asarray(a, dtype=np.float64)
+            return {"v": 1, "dim": list(a.shape), "data": a.reshape(-1).tolist()}
+        t = p._theta_tuning
+        if t.kind == 0:
+            tuning = {"Fixed": arr(t.init)}
+        else:
+            b = [list(map(float, bb)) for bb in (t.bounds or [_gp.ThetaTuning.DEFAULT_BOUNDS])]
+            tuning = {"Full": {"init": arr(t.init), "bounds": {"v": 1, "dim": [len(b)], "data": b}}}
+            if t.kind == 2:
+                tuning = {"Partial": {"init": arr(t.init), "bounds": {"v": 1, "dim": [len(b)], "data": b},
+                                      "active": list(t.active)}}
+        mean_name = _gp.MEAN_NAMES[p._mean]
+        return {
+            "type_fullgp": "Gp%s%sSurrogate" % (mean_name.replace("Mean", ""), _gp.CORR_NAMES[p._corr]),
+            "theta": arr(gp.theta()), "likelihood": gp.likelihood(),
+            "inner_params": {"sigma2": ip["sigma2"], "beta": arr(ip["beta"]), "gamma": arr(ip["gamma"]),
+                             "r_chol": arr(ip["r_chol"]), "ft": arr(ip["ft"]), "ft_qr_r": arr(ip["ft_qr_r"])},
+            "w_star": arr(nz["w_star"]),
+            "xt_norm": {"data": arr(xn), "mean": arr(nz["x_mean"]), "std": arr(nz["x_std"])},
+            "yt_norm": {"data": arr(yn), "mean": arr([nz["y_mean"]]), "std": arr([nz["y_std"]])},
+            "training_data": [arr(x), arr(y)],
+            "params": {"theta_tuning": tuning, "mean": mean_name, "corr": _gp.CORR_NAMES[p._corr],
+                       "kpls_dim": p._kpls_dim, "n_start": p._n_start, "max_eval": p._max_eval, "nugget": p._nugget},
+        }
+
+    def save(self, filename):
+        """JSON only: {"recombination": "Hard", "experts": [<expert in the reference layout>]}.  The mixture-level
+        blocks of the reference file (gmx, gp_type, params with the RNG state) belong to egobox-moe's control plane
+        and are not written, so stock egobox cannot load this file as a GpMixture."""
+        if not str(filename).endswith(".json"):
+            raise NotImplementedError("bincode persistence is out of scope; use a .json filename")
+        with open(filename, "w") as f:
+            json.dump({"recombination": "Hard", "experts": [self._expert_dict()]}, f)
+        return True
+
+    @staticmethod
+    def load(filename, device=0):
+        """Rebuild the device-resident model from a file written by save() -- or from the `experts[0]` block of a
+        stock egobox JSON -- by one final evaluation at the stored theta (Fixed tuning)."""
+        with open(filename) as f:
+            obj = json.load(f)
+        e = obj["experts"][0] if "experts" in obj else obj
+
+        def arr(o):
+            return np.array(o["data"], dtype=np.float64).reshape(o["dim"])
+        prm = e["params"]
+        mean = _gp.MEAN_NAMES.index(prm["mean"])
+        corr = _gp.CORR_NAMES.index(prm["corr"])
+        x, y = arr(e["training_data"][0]), arr(e["training_data"][1])
+        params = (_gp.GaussianProcess.params(mean, corr).theta_tuning(_gp.ThetaTuning.Fixed(arr(e["theta"])))
+                  .nugget(prm.get("nugget", _gp.DEFAULT_NUGGET)).device(device))
+        w = arr(e["w_star"])
+        if w.shape[1] < w.shape[0]:
+            params = params.kpls_dim(w.shape[1], w)
+        builder = GpMix(regr_spec=1 << mean, corr_spec=1 << corr, n_start=-1, theta_init=arr(e["theta"]).tolist())
+        return Gpx(params.fit(x, y), builder)
+
     def __str__(self):
         p = self._gp.params_
         return "Mixture[Hard](%s_%sGP(mean=%s, corr=%s, theta=%s, variance=%s, likelihood=%s))" % (

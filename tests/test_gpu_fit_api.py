@@ -103,3 +103,38 @@ def test_kriging_alias_and_errors():
     xd = np.array([[0.0], [0.0], [1.0]])
     with pytest.raises(egx.LinalgError):
         egx.GaussianProcess.params().theta_tuning(egx.ThetaTuning.Fixed([1.0])).nugget(0.0).fit(xd, [0.0, 0.0, 1.0])
+
+
+def test_gpx_save_load_reference_expert_layout(tmp_path, golden_dir):
+    """test_gpmix.py:55-82 (save / load round trip) + the serde layout of doc/Gpx_Tutorial.ipynb:421: the expert
+    block we write must match the reference's stored JSON key by key and number by number."""
+    import egobox_b200 as egx
+    with open(os.path.join(golden_dir, "gpx_tutorial_linear_matern52.json")) as f:
+        ref = json.load(f)
+    arr = lambda o: np.array(o["data"], dtype=np.float64).reshape(o["dim"])
+    xt, yt = arr(ref["training_data"][0]), arr(ref["training_data"][1])
+    gpx = egx.Gpx.builder(regr_spec=egx.RegressionSpec.LINEAR, corr_spec=egx.CorrelationSpec.MATERN52,
+                          n_start=-1, theta_init=arr(ref["theta"]).tolist()).fit(xt, yt)
+    fn = str(tmp_path / "gpdump.json")
+    assert gpx.save(fn)
+    ours = json.load(open(fn))["experts"][0]
+    assert ours["type_fullgp"] == ref["type_fullgp"]
+    assert set(ours) == set(k for k in ref if k != "source")
+    assert ours["likelihood"] == pytest.approx(ref["likelihood"], rel=1e-12)
+    for k in ("beta", "gamma", "r_chol", "ft", "ft_qr_r"):
+        assert ours["inner_params"][k]["dim"] == ref["inner_params"][k]["dim"]
+        np.testing.assert_allclose(arr(ours["inner_params"][k]), arr(ref["inner_params"][k]), rtol=0, atol=1e-12)
+    assert ours["inner_params"]["sigma2"] == pytest.approx(ref["inner_params"]["sigma2"], rel=1e-10)
+    for k in ("xt_norm", "yt_norm"):
+        for kk in ("data", "mean", "std"):
+            np.testing.assert_allclose(arr(ours[k][kk]), arr(ref[k][kk]), rtol=1e-14, atol=1e-15)
+    assert ours["params"]["mean"] == ref["params"]["mean"] and ours["params"]["corr"] == ref["params"]["corr"]
+    gpx2 = egx.Gpx.load(fn)
+    xq = np.linspace(-8, 8, 33)[:, None]
+    np.testing.assert_allclose(gpx2.predict(xq), gpx.predict(xq), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(gpx2.predict_var(xq), gpx.predict_var(xq), rtol=1e-9, atol=1e-9)
+    # a stock egobox expert block loads too (the golden fixture IS one)
+    gpx3 = egx.Gpx.load(os.path.join(golden_dir, "gpx_tutorial_linear_matern52.json"))
+    np.testing.assert_allclose(gpx3.predict(xq), gpx.predict(xq), rtol=1e-10, atol=1e-10)
+    with pytest.raises(NotImplementedError):
+        gpx.save(str(tmp_path / "gpdump.bin"))
