@@ -608,7 +608,9 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
     if (small_path_ok(c)) return evaluate_small_batch(c, thetas, B, rlf, status);
     // Large n: keep `W` independent evaluations in flight on W replicas of the workspace (own streams):
     // the serial diagonal-block / panel chain of one factorisation overlaps the bulk updates of the others.
-    int W = 4;
+    // how many: the smaller the matrix, the more an evaluation is a latency chain (block columns x ~80 us)
+    // rather than throughput work, and the cheaper a replica is (npad^2 x 8 bytes)
+    int W = (c->npad <= 2048) ? 12 : (c->npad <= 4096 ? 6 : 4);
     if (const char* e = getenv("EGX_BATCH_STREAMS")) W = std::max(1, atoi(e));
     W = std::min(W, B);
     while (static_cast<int>(c->replicas.size()) < W - 1) {
