@@ -73,7 +73,7 @@ void launch_mean_basis_rows(const double* X, int n, int npad, int d, const int* 
                             cudaStream_t s);
 // kernels_chol.cu
 void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* Dinv, cudaStream_t s);
-void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P,
+void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, long ldp,
                       int nblocks64, cudaStream_t s);
 void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s);
 int gemm_smem_bytes();

@@ -166,7 +166,7 @@ __device__ __forceinline__ void tr_cp_async16(void* smem_dst, const void* gsrc) 
 __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, long ldx,
                                                         const double* __restrict__ L, long ldl,
                                                         const double* __restrict__ Dinv,
-                                                        double* __restrict__ P) {
+                                                        double* __restrict__ P, long ldp) {
     extern __shared__ __align__(16) double sm[];
     double* Xs = sm;                              // [64][132]
     double* Ds = Xs + TR_ROWS * TR_LDX;           // [4][32][36]
@@ -253,12 +253,13 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
                     make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         __syncthreads();        // X_b visible to the next block step
     }
-    double* Pg = (P != nullptr) ? P + static_cast<long>(blockIdx.x) * TR_ROWS * EGX_NB : nullptr;
+    // panel copy for the trailing update: 128 columns of a (rows x ldp) buffer (ldp = 256: two panels side by side)
+    double* Pg = (P != nullptr) ? P + static_cast<long>(blockIdx.x) * TR_ROWS * ldp : nullptr;
     for (int e = tid; e < TR_ROWS * 64; e += 256) {
         const int r = e >> 6, ch = e & 63;
         const double2 v = *reinterpret_cast<const double2*>(&Xs[r * TR_LDX + ch * 2]);
         *reinterpret_cast<double2*>(Xg + static_cast<long>(r) * ldx + ch * 2) = v;
-        if (Pg != nullptr) *reinterpret_cast<double2*>(Pg + r * EGX_NB + ch * 2) = v;
+        if (Pg != nullptr) *reinterpret_cast<double2*>(Pg + static_cast<long>(r) * ldp + ch * 2) = v;
     }
 }
 
@@ -416,8 +417,8 @@ void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* 
     potrf_diag_kernel<<<1, 256, 0, s>>>(Akk, ld, info, base_index, Dinv);
 }
 
-void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, int nblocks64,
-                      cudaStream_t s) {
+void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, long ldp,
+                      int nblocks64, cudaStream_t s) {
     static bool configured_dev[64] = {false};
     int dev_ = 0;
     cudaGetDevice(&dev_);
@@ -428,7 +429,7 @@ void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const do
         configured = true;
     }
     if (nblocks64 <= 0) return;
-    trsm_rows_kernel<<<nblocks64, 256, smem, s>>>(X, ldx, Lkk, ldl, Dinv, P);
+    trsm_rows_kernel<<<nblocks64, 256, smem, s>>>(X, ldx, Lkk, ldl, Dinv, P, ldp);
 }
 
 static int gemm_env(const char* name, int dflt) {

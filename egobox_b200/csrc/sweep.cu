@@ -75,7 +75,7 @@ int SweepEnv::ensure_panel_rows(long rows) {
     for (int i = 0; i < 2; ++i) {
         cudaFree(P2[i]);
         P2[i] = nullptr;
-        EGX_CUDA_TRY(cudaMalloc(&P2[i], static_cast<size_t>(rows) * EGX_NB * sizeof(double)));
+        EGX_CUDA_TRY(cudaMalloc(&P2[i], static_cast<size_t>(rows) * 2 * EGX_NB * sizeof(double)));
     }
     p_rows = rows;
     return EGX_OK;
@@ -98,90 +98,144 @@ void SweepEnv::destroy() {
     sb = sp = nullptr;
 }
 
-// With look-ahead the diagonal block, the panel solve and the update of the NEXT block column
-// run on the high-priority stream while the bulk of the trailing update of the current step is
-// still in flight on the bulk stream.  Look-ahead pays for the factorisation (a serial 1-CTA
-// diagonal block per step); the multi-RHS solve has no serial part and is faster as plain
-// back-to-back launches (measured 22.9 vs 28.8 ms per 8192-point chunk at n = 8192).
+// Two-level blocking: block columns are processed in PAIRS (outer block 256 = two 128-panels).  Panel A, the
+// K=128 update of the partner column, panel B, then ONE trailing update with K = 256 over both panels
+// (side by side in a rows x 256 buffer): half as many passes over the trailing matrix and half as many tile
+// prologues/epilogues as a K = 128 update per panel.
+// With look-ahead (factorisation only) the panel chain and the update of the NEXT pair's two block columns run
+// on the high-priority stream while the bulk of the trailing update is still in flight on the bulk stream.
+// The multi-RHS solve has no serial part and runs as plain back-to-back launches (measured 22.9 vs 28.8 ms
+// per 8192-point chunk at n = 8192 with / without stream splitting).
 void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows, long ld_rows, int row_tiles,
                    int slabs64) {
     const int T = f.T, Qt = f.qpad / EGX_NB;
     const long ld = f.ld;
-    const bool la = env.lookahead && factor && T > 2 && static_cast<int>(env.ev_panel.size()) >= T;
+    const long LDP = 2 * EGX_NB;
+    const bool la = env.lookahead && factor && T > 4 && static_cast<int>(env.ev_panel.size()) >= (T + 1) / 2;
     cudaStream_t sb = env.sb, sp = la ? env.sp : env.sb;
     if (la) {
         cudaEventRecord(env.ev_fork, sb);
         cudaStreamWaitEvent(sp, env.ev_fork, 0);
     }
-    for (int k = 0; k < T; ++k) {
-        double* Pk = env.P2[k & 1];
-        double* Akk = f.M + static_cast<long>(k) * EGX_NB * ld + static_cast<long>(k) * EGX_NB;
-        double* Dk = f.Dinv + static_cast<long>(k) * 4096;
-        const int tri = T - k - 1;
-        // ---- panel (k) -------------------------------------------------------------
+    auto blk = [&](int r, int c) { return f.M + static_cast<long>(r) * EGX_NB * ld + static_cast<long>(c) * EGX_NB; };
+    for (int k = 0; k < T; k += 2) {
+        const int pair = k >> 1;
+        double* Pw = env.P2[pair & 1];                 // rows x 256; factor: row 0 = first row of block k+1
+        const bool two = (k + 1 < T);
+        // ---- panel A (block column k) -----------------------------------------------------------------
         if (factor) {
             {
                 StageScope sc(env.prof, EGX_STAGE_POTRF_DIAG, 1, sp);
-                launch_potrf_diag(Akk, ld, f.info, k * EGX_NB, Dk, sp);
+                launch_potrf_diag(blk(k, k), ld, f.info, k * EGX_NB, f.Dinv + static_cast<long>(k) * 4096, sp);
             }
-            const int rows_below = tri * EGX_NB + f.qpad;
+            const int rows_below = (T - k - 1) * EGX_NB + f.qpad;
             if (rows_below > 0) {
                 StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
-                launch_trsm_rows(Akk + static_cast<long>(EGX_NB) * ld, ld, Akk, ld, Dk, Pk, rows_below / 64, sp);
+                launch_trsm_rows(blk(k + 1, k), ld, blk(k, k), ld, f.Dinv + static_cast<long>(k) * 4096, Pw, LDP,
+                                 rows_below / 64, sp);
             }
         } else {
             StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
-            launch_trsm_rows(rows + static_cast<long>(k) * EGX_NB, ld_rows, Akk, ld, Dk, Pk, slabs64, sp);
+            launch_trsm_rows(rows + static_cast<long>(k) * EGX_NB, ld_rows, blk(k, k), ld,
+                             f.Dinv + static_cast<long>(k) * 4096, Pw, LDP, slabs64, sp);
         }
-        if (tri == 0) break;
-        if (la) cudaEventRecord(env.ev_panel[k], sp);
-        // ---- trailing update (k) ---------------------------------------------------
-        GemmArgs g;
-        g.A = Pk;
-        g.lda = EGX_NB;
+        if (!two) break;
+        const int tri1 = T - k - 1;                    // block columns right of k
+        // ---- partner column k+1: K = 128 update with panel A ------------------------------------------
+        {
+            GemmArgs g;
+            g.A = Pw;
+            g.lda = LDP;
+            g.K = EGX_NB;
+            g.tri = 0;
+            g.Nt = 1;
+            if (factor) {
+                g.C = blk(k + 1, k + 1);
+                g.ldc = ld;
+                g.B = Pw;
+                g.ldb = LDP;
+                g.Mt = tri1 + Qt;
+            } else {
+                g.C = rows + static_cast<long>(k + 1) * EGX_NB;
+                g.ldc = ld_rows;
+                g.B = blk(k + 1, k);
+                g.ldb = ld;
+                g.Mt = row_tiles;
+            }
+            StageScope sc(env.prof, EGX_STAGE_GEMM_LOOKAHEAD, 1, sp);
+            launch_gemm_nt_sub(g, sp);
+        }
+        // ---- panel B (block column k+1) -> columns 128..255 of Pw ---------------------------------------
         if (factor) {
-            g.C = Akk + static_cast<long>(EGX_NB) * ld + EGX_NB;
-            g.ldc = ld;
-            g.B = Pk;
-            g.ldb = EGX_NB;
+            {
+                StageScope sc(env.prof, EGX_STAGE_POTRF_DIAG, 1, sp);
+                launch_potrf_diag(blk(k + 1, k + 1), ld, f.info, (k + 1) * EGX_NB, f.Dinv + static_cast<long>(k + 1) * 4096,
+                                  sp);
+            }
+            const int rows_below = (T - k - 2) * EGX_NB + f.qpad;
+            if (rows_below > 0) {
+                StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
+                launch_trsm_rows(blk(k + 2, k + 1), ld, blk(k + 1, k + 1), ld, f.Dinv + static_cast<long>(k + 1) * 4096,
+                                 Pw + static_cast<long>(EGX_NB) * LDP + EGX_NB, LDP, rows_below / 64, sp);
+            }
         } else {
-            g.C = rows + static_cast<long>(k + 1) * EGX_NB;
-            g.ldc = ld_rows;
-            g.B = Akk + static_cast<long>(EGX_NB) * ld;
+            StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
+            launch_trsm_rows(rows + static_cast<long>(k + 1) * EGX_NB, ld_rows, blk(k + 1, k + 1), ld,
+                             f.Dinv + static_cast<long>(k + 1) * 4096, Pw + EGX_NB, LDP, slabs64, sp);
+        }
+        const int tri2 = T - k - 2;                    // block columns right of the pair
+        if (la) cudaEventRecord(env.ev_panel[pair], sp);
+        if (tri2 <= 0) continue;                       // nothing right of the pair (appended rows only touch existing columns)
+        // ---- trailing update with K = 256 ---------------------------------------------------------------
+        GemmArgs g;
+        g.K = 2 * EGX_NB;
+        g.lda = LDP;
+        if (factor) {
+            g.A = Pw + static_cast<long>(EGX_NB) * LDP;      // rows from block k+2
+            g.B = g.A;
+            g.ldb = LDP;
+            g.C = blk(k + 2, k + 2);
+            g.ldc = ld;
+        } else {
+            g.A = Pw;
+            g.B = blk(k + 2, k);                            // L[(k+2).., 256 columns of the pair]
             g.ldb = ld;
+            g.C = rows + static_cast<long>(k + 2) * EGX_NB;
+            g.ldc = ld_rows;
         }
         if (!la) {
-            g.tri = factor ? tri : 0;
-            g.Mt = factor ? tri + Qt : row_tiles;
-            g.Nt = tri;
+            g.tri = factor ? tri2 : 0;
+            g.Mt = factor ? tri2 + Qt : row_tiles;
+            g.Nt = tri2;
             StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, sb);
             launch_gemm_nt_sub(g, sb);
             continue;
         }
-        // part A: block column k+1 only (what panel k+1 needs), on the panel stream
-        if (k > 0) cudaStreamWaitEvent(sp, env.ev_bulk[k - 1], 0);
+        // look-ahead part: the next pair's two block columns, on the panel stream
+        if (pair > 0) cudaStreamWaitEvent(sp, env.ev_bulk[pair - 1], 0);
+        const int nla = tri2 < 2 ? tri2 : 2;
         {
             GemmArgs ga = g;
             ga.tri = 0;
-            ga.Mt = tri + Qt;
-            ga.Nt = 1;
+            ga.Mt = tri2 + Qt;
+            ga.Nt = nla;
             StageScope sc(env.prof, EGX_STAGE_GEMM_LOOKAHEAD, 1, sp);
             launch_gemm_nt_sub(ga, sp);
         }
-        // part B: block columns k+2.., on the bulk stream
-        cudaStreamWaitEvent(sb, env.ev_panel[k], 0);
-        if (tri > 1) {
+        // bulk: block columns k+4 .., on the bulk stream
+        cudaStreamWaitEvent(sb, env.ev_panel[pair], 0);
+        if (tri2 > 2) {
             GemmArgs gb = g;
-            gb.C = g.C + static_cast<long>(EGX_NB) * ld + EGX_NB;
-            gb.A = Pk + static_cast<long>(EGX_NB) * EGX_NB;
-            gb.B = Pk + static_cast<long>(EGX_NB) * EGX_NB;
-            gb.tri = tri - 1;
-            gb.Mt = tri - 1 + Qt;
-            gb.Nt = tri - 1;
+            gb.C = g.C + static_cast<long>(2 * EGX_NB) * ld + 2 * EGX_NB;
+            gb.A = g.A + static_cast<long>(2 * EGX_NB) * LDP;
+            gb.B = gb.A;
+            gb.tri = tri2 - 2;
+            gb.Mt = tri2 - 2 + Qt;
+            gb.Nt = tri2 - 2;
             StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, sb);
             launch_gemm_nt_sub(gb, sb);
         }
-        cudaEventRecord(env.ev_bulk[k], sb);
+        cudaEventRecord(env.ev_bulk[pair], sb);
     }
     if (la) {
         cudaEventRecord(env.ev_join, sp);
