@@ -41,6 +41,7 @@ struct GemmArgs {
     int add = 0;     // 0: C -= A B^T (factorisation / solve updates) ; 1: C += A B^T
     int splits = 1;  // split-K: blockIdx.y = s works on K-range [s*K, (s+1)*K) of A/B and on C + s*split_c_stride
     long split_c_stride = 0;
+    int late_c = 0;  // set by the launcher: accumulate from zero, fold C in at the end (hides the C-tile load)
 };
 
 #define EGX_CUDA_TRY(expr)                                                         \

@@ -138,6 +138,15 @@ struct egx_gp_ctx {
 
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     bool force_blocked = false;
+
+    // One likelihood evaluation captured as a CUDA graph (both streams of the look-ahead schedule): a blocked
+    // evaluation is 5-7 launches per block column, host launch-bound below n ~ 4096.  Re-captured when the
+    // number of kernel terms, the look-ahead setting or a captured buffer changes; bypassed while profiling.
+    cudaGraphExec_t eval_graph = nullptr;
+    int graph_nterms = -1, graph_generation = -1;
+    bool graph_lookahead = false, use_graphs = true;
+    long long graph_launches[EGX_NUM_STAGES] = {0};
+    long long direct_evals = 0;
     std::mutex mu;
 };
 
@@ -145,22 +154,32 @@ namespace {
 
 void resolve_profile(egx_gp_ctx* c) { c->env.prof.resolve(); }
 
-int build_terms(egx_gp_ctx* c, const double* theta) {
+// host half of the per-theta setup: kernel weights into the pinned staging buffer
+int build_terms_host(egx_gp_ctx* c, const double* theta) {
+    for (int l = 0; l < c->h; ++l)
+        if (std::isnan(theta[l])) {
+            egx_set_error("theta[%d] is NaN", l);
+            return EGX_INVALID_VALUE;
+        }
     c->nterms = egx_fill_terms(c->corr, c->d, c->h, c->w_star.data(), theta, c->terms_h);
+    return EGX_OK;
+}
+
+int upload_terms(egx_gp_ctx* c) {
     if (c->nterms > 0)
         EGX_CUDA_TRY(cudaMemcpyAsync(c->terms, c->terms_h, c->nterms * sizeof(CorrTerm), cudaMemcpyHostToDevice,
                                      c->stream));
     return EGX_OK;
 }
 
-// R(theta) lower block-triangle into M, then the RHS rows.
-int assemble(egx_gp_ctx* c, const double* theta) {
-    for (int l = 0; l < c->h; ++l)
-        if (std::isnan(theta[l])) {
-            egx_set_error("theta[%d] is NaN", l);
-            return EGX_INVALID_VALUE;
-        }
-    int st = build_terms(c, theta);
+int build_terms(egx_gp_ctx* c, const double* theta) {
+    c->nterms = egx_fill_terms(c->corr, c->d, c->h, c->w_star.data(), theta, c->terms_h);
+    return upload_terms(c);
+}
+
+// R(theta) lower block-triangle into M, then the RHS rows (terms already in the pinned staging buffer).
+int assemble_staged(egx_gp_ctx* c) {
+    int st = upload_terms(c);
     if (st != EGX_OK) return st;
     EGX_CUDA_TRY(cudaMemsetAsync(c->info, 0, sizeof(int), c->stream));
     {
@@ -172,6 +191,12 @@ int assemble(egx_gp_ctx* c, const double* theta) {
                                  static_cast<size_t>(c->q) * c->ld * sizeof(double), cudaMemcpyDeviceToDevice,
                                  c->stream));
     return EGX_OK;
+}
+
+int assemble(egx_gp_ctx* c, const double* theta) {
+    int st = build_terms_host(c, theta);
+    if (st != EGX_OK) return st;
+    return assemble_staged(c);
 }
 
 FactorRef factor_ref(egx_gp_ctx* c) {
@@ -279,11 +304,8 @@ int evaluate_small_batch(egx_gp_ctx* c, const double* thetas, int B, double* rlf
 // Full likelihood evaluation; leaves L, (L^-1[F|y])^T, beta, G, rho on the device.
 // evaluate_launch enqueues everything (no host synchronisation); evaluate_collect waits for the
 // result block and applies the host-side status logic.
-int evaluate_launch(egx_gp_ctx* c, const double* theta) {
-    c->trained = false;
-    c->grad_ready = false;
-    c->pending_eval = false;
-    int st = assemble(c, theta);
+int enqueue_eval(egx_gp_ctx* c) {
+    int st = assemble_staged(c);
     if (st != EGX_OK) return st;
     cholesky(c);
     {
@@ -293,6 +315,66 @@ int evaluate_launch(egx_gp_ctx* c, const double* theta) {
     EGX_CUDA_TRY(cudaMemcpyAsync(c->res_h, c->res, sizeof(EvalResult), cudaMemcpyDeviceToHost, c->stream));
     EGX_CUDA_TRY(cudaMemcpyAsync(c->G_h, c->G, sizeof(double) * c->p * c->p, cudaMemcpyDeviceToHost, c->stream));
     EGX_CUDA_TRY(cudaMemcpyAsync(c->beta_h, c->beta, sizeof(double) * c->p, cudaMemcpyDeviceToHost, c->stream));
+    return EGX_OK;
+}
+
+void drop_graph(egx_gp_ctx* c) {
+    if (c->eval_graph) cudaGraphExecDestroy(c->eval_graph);
+    c->eval_graph = nullptr;
+}
+
+// Capture one evaluation (terms upload ... result download) on the context's streams.
+int capture_eval_graph(egx_gp_ctx* c) {
+    drop_graph(c);
+    long long before[EGX_NUM_STAGES];
+    for (int i = 0; i < EGX_NUM_STAGES; ++i) before[i] = c->env.prof.launches[i];
+    EGX_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int st = enqueue_eval(c);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    for (int i = 0; i < EGX_NUM_STAGES; ++i) {
+        c->graph_launches[i] = c->env.prof.launches[i] - before[i];
+        c->env.prof.launches[i] = before[i];
+    }
+    if (st != EGX_OK || e != cudaSuccess || g == nullptr) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        egx_set_error("CUDA graph capture of the likelihood evaluation failed: %s", cudaGetErrorString(e));
+        return EGX_CUDA_ERROR;
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&c->eval_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) {
+        c->eval_graph = nullptr;
+        egx_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+        return EGX_CUDA_ERROR;
+    }
+    c->graph_nterms = c->nterms;
+    c->graph_lookahead = c->env.lookahead;
+    c->graph_generation = c->env.generation;
+    return EGX_OK;
+}
+
+int evaluate_launch(egx_gp_ctx* c, const double* theta) {
+    c->trained = false;
+    c->grad_ready = false;
+    c->pending_eval = false;
+    int st = build_terms_host(c, theta);
+    if (st != EGX_OK) return st;
+    // the first evaluation of a context always launches directly (lazy module loading, function attributes)
+    if (c->use_graphs && !c->env.prof.on && c->direct_evals > 0) {
+        if (c->eval_graph == nullptr || c->graph_nterms != c->nterms || c->graph_lookahead != c->env.lookahead ||
+            c->graph_generation != c->env.generation) {
+            st = capture_eval_graph(c);
+            if (st != EGX_OK) return st;
+        }
+        for (int i = 0; i < EGX_NUM_STAGES; ++i) c->env.prof.launches[i] += c->graph_launches[i];
+        EGX_CUDA_TRY(cudaGraphLaunch(c->eval_graph, c->stream));
+    } else {
+        st = enqueue_eval(c);
+        if (st != EGX_OK) return st;
+        ++c->direct_evals;
+    }
     c->pending_eval = true;
     return EGX_OK;
 }
@@ -419,6 +501,8 @@ void free_ctx(egx_gp_ctx* c) {
     c->replicas.clear();
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->eval_graph) cudaGraphExecDestroy(c->eval_graph);
+    c->eval_graph = nullptr;
     if (c->timer_a) cudaEventDestroy(c->timer_a);
     if (c->timer_b) cudaEventDestroy(c->timer_b);
     cudaFree(c->X);
@@ -532,6 +616,10 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
         return EGX_CUDA_ERROR;
     }
     c->stream = c->env.sb;
+    // measured (tools/midsize_probe.py, configs_probe.py): replay wins 1.5-2.7x for n <= 2048 and 6 % at n = 4096,
+    // and loses 2.5 % at n = 8192 where the evaluation is throughput- not launch-bound
+    c->use_graphs = c->npad <= 4096;
+    if (const char* e = getenv("EGX_GRAPHS")) c->use_graphs = atoi(e) != 0;
     const size_t xbytes = static_cast<size_t>(c->npad) * d * sizeof(double);
     EGX_CREATE_TRY(cudaMalloc(&c->X, xbytes));
     EGX_CREATE_TRY(cudaMemsetAsync(c->X, 0, xbytes, c->stream));

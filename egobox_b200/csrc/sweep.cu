@@ -78,6 +78,7 @@ int SweepEnv::ensure_panel_rows(long rows) {
         EGX_CUDA_TRY(cudaMalloc(&P2[i], static_cast<size_t>(rows) * 2 * EGX_NB * sizeof(double)));
     }
     p_rows = rows;
+    ++generation;
     return EGX_OK;
 }
 
@@ -162,7 +163,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
                 g.ldb = ld;
                 g.Mt = row_tiles;
             }
-            StageScope sc(env.prof, EGX_STAGE_GEMM_LOOKAHEAD, 1, sp);
+            StageScope sc(env.prof, la ? EGX_STAGE_GEMM_LOOKAHEAD : EGX_STAGE_SYRK_GEMM, 1, sp);
             launch_gemm_nt_sub(g, sp);
         }
         // ---- panel B (block column k+1) -> columns 128..255 of Pw ---------------------------------------

@@ -41,6 +41,7 @@ struct SweepEnv {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double* P2[2] = {nullptr, nullptr};   // double-buffered contiguous panel copies (rows x 128)
     long p_rows = 0;
+    int generation = 0;                   // bumped when a buffer captured in a CUDA graph is reallocated
     Profiler prof;
     int init(int max_block_cols);
     int ensure_panel_rows(long rows);

@@ -158,7 +158,7 @@ int egx_gp_cross_correlation(egx_gp_ctx* ctx, const double* x, int m, double* c)
 #define EGX_STAGE_CROSS_CORR   6  /* c(x*, X) (+ fused mean / gamma GEMV)        */
 #define EGX_STAGE_VAR_FINISH   7  /* row norms, u, variance                      */
 #define EGX_STAGE_SMALL_BATCH  8  /* one-CTA-per-theta small-n likelihood        */
-#define EGX_STAGE_GEMM_LOOKAHEAD 9 /* block-column k+1 update issued ahead on the panel stream */
+#define EGX_STAGE_GEMM_LOOKAHEAD 9 /* updates issued ahead on the panel stream (partner column, next pair's two columns) */
 #define EGX_NUM_STAGES         10
 int egx_gp_set_profiling(egx_gp_ctx* ctx, int enabled);
 int egx_gp_reset_profile(egx_gp_ctx* ctx);

@@ -16,6 +16,7 @@ from tools._util import make_problem, make_context         # noqa: E402
 def c1():
     x = np.sort(np.random.default_rng(42).random((200, 1)) * 25.0, axis=0)
     y = (x[:, 0] - 3.5) * np.sin((x[:, 0] - 3.5) / np.pi)
+    eg.Kriging.params().fit(x[:50], y[:50]).predict_var(x[:10])     # CUDA context / module load outside the timing
     t0 = time.perf_counter()
     gp = eg.Kriging.params().fit(x, y)
     t1 = time.perf_counter()
