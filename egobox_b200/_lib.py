@@ -43,6 +43,10 @@ SIGNATURES = {
     "egx_gp_predict_valvar_dev": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "egx_gp_predict_gradients": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_gp_predict_var_gradients": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_symmetric_eig": (C.c_int, [C.c_int, _dp, _dp]),
+    "egx_release_cached_memory": (None, []),
+    "egx_gp_covariance": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_gp_sample": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp]),
     "egx_gp_correlation_matrix": (C.c_int, [_vp, _dp, _dp]),
     "egx_gp_cross_correlation": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_gp_set_profiling": (C.c_int, [_vp, C.c_int]),
@@ -86,6 +90,8 @@ SIGNATURES.update({
     "egx_gp_model_predict_valvar": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp]),
     "egx_gp_model_predict_gradients": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_gp_model_predict_var_gradients": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_gp_model_covariance": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_gp_model_sample": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp]),
     "egx_bound_cobyla_minimize": (C.c_int, [OBJECTIVE_FN, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_double,
                                             C.c_double, C.c_int, _dp, _dp, _ip]),
     "egx_prepare_multistart": (C.c_int, [C.c_int, _dp, _dp, C.c_int, C.c_ulonglong, _dp]),

@@ -59,6 +59,11 @@ class GpContext:
             raise GpuError(st, _lib.last_error())
         return st
 
+    def _check_all(self, st):
+        if st != 0:
+            raise GpuError(st, _lib.last_error())
+        return st
+
     def reduced_likelihood(self, theta):
         """-> (status, rlf); numerical failures are statuses (rlf = NaN)."""
         th = _f64(theta).reshape(-1)
@@ -130,6 +135,23 @@ class GpContext:
         g = np.empty((x.shape[0], self.d))
         self._check(self._lib.egx_gp_predict_var_gradients(self._h, _ptr(x), x.shape[0], _ptr(g)))
         return g
+
+    def covariance(self, x):
+        """Conditional covariance at the rows of x (algorithm.rs:310-326), (m, m)."""
+        x = _f64(x).reshape(-1, self.d)
+        cov = np.empty((x.shape[0], x.shape[0]))
+        self._check_all(self._lib.egx_gp_covariance(self._h, _ptr(x), x.shape[0], _ptr(cov)))
+        return cov
+
+    def sample(self, x, z, method=0):
+        """mean + C z with C C^T the conditional covariance (algorithm.rs:1153-1194); z is (m, n_traj)
+        standard-normal draws, method 0 = Cholesky, 1 = eigenvalues."""
+        x = _f64(x).reshape(-1, self.d)
+        z = _f64(z).reshape(x.shape[0], -1)
+        out = np.empty_like(z)
+        self._check_all(self._lib.egx_gp_sample(self._h, _ptr(x), x.shape[0], _ptr(z), z.shape[1], int(method),
+                                                _ptr(out)))
+        return out
 
     def predict_valvar_dev(self, x_ptr, m, y_ptr, v_ptr):
         """x/y/var are raw device addresses (ints) on this context's GPU."""

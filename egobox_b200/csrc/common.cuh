@@ -86,7 +86,29 @@ void launch_backsolve_update(const double* Lrow, long ld, const double* gamma_k,
                              cudaStream_t s);
 void launch_var_finish(const double* Y, long ldy, int m, int npad, const double* xraw, const double* x_mean,
                        const double* x_std, int d, const double* FtT, long ldf, const double* G, int p,
-                       const int* basis_i, const int* basis_j, double sigma2, double* var, cudaStream_t s);
+                       const int* basis_i, const int* basis_j, double sigma2, double* var, cudaStream_t s,
+                       double* U = nullptr /* optional m x p: u_i = G^-T (Ft^T rt_i - f(x_i)) */);
+void launch_cov_finish(double* C, long ld, int m, int mpad, const double* U, int p, double sigma2, cudaStream_t s);
+void launch_normalize_rows(const double* x, int m, int mpad, int d, const double* mean, const double* sd, double* out,
+                           cudaStream_t s);
+void launch_zero_upper(double* A, long ld, int npad, cudaStream_t s);
+void launch_bcast_rows(double* out, long ld, int m, int mpad, int cols, const double* mean, cudaStream_t s);
+int egx_host_symmetric_eig(int n, double* a, double* w);
+
+// cached allocators (devmem.cu): same contract as cudaMalloc / cudaFree / cudaMallocHost / cudaFreeHost
+cudaError_t egx_dev_malloc_bytes(void** p, size_t bytes);
+void egx_dev_free(void* p);
+cudaError_t egx_host_malloc_bytes(void** p, size_t bytes);
+void egx_host_free(void* p);
+void egx_mem_trim();
+template <typename T>
+inline cudaError_t egx_dev_malloc(T** p, size_t bytes) {
+    return egx_dev_malloc_bytes(reinterpret_cast<void**>(p), bytes);
+}
+template <typename T>
+inline cudaError_t egx_host_malloc(T** p, size_t bytes) {
+    return egx_host_malloc_bytes(reinterpret_cast<void**>(p), bytes);
+}
 // small_batch.cu
 size_t small_batch_smem_bytes(int n, int d, int h, int p);
 void launch_small_batch(int corr, const double* X, int n, int d, const double* W, int h, const double* thetas, int B,

@@ -1,0 +1,129 @@
+// Size-keyed cache of device and pinned-host blocks.  A fit builds one context plus up to 11 workspace replicas
+// (about 25 device and 4 pinned allocations each) and tears them down again; the EGO loop refits at every
+// iteration.  cudaMalloc / cudaFree / cudaMallocHost cost 0.1 - 1 ms apiece and cudaFree synchronises the device,
+// which at n ~ 1000 is more than the 90 likelihood rounds of the fit itself.  Blocks are reused by exact size
+// (buffer sizes are functions of n padded to 128, so they repeat from fit to fit); every context synchronises its
+// streams before releasing memory, so a cached block has no work in flight.
+// EGX_CACHE_MB caps the cached (idle) bytes per kind, default 4096; 0 disables the cache.
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/egobox_gpu.h"
+
+namespace {
+
+struct BlockCache {
+    bool host;
+    std::mutex mu;
+    std::map<std::pair<int, size_t>, std::vector<void*>> idle;      // (device, bytes) -> blocks
+    std::unordered_map<void*, std::pair<int, size_t>> live;
+    size_t idle_bytes = 0;
+
+    explicit BlockCache(bool h) : host(h) {}
+
+    static size_t cap() {
+        static const size_t c = [] {
+            const char* e = getenv("EGX_CACHE_MB");
+            return static_cast<size_t>(e ? std::max(0, atoi(e)) : 4096) << 20;
+        }();
+        return c;
+    }
+    cudaError_t raw_alloc(void** p, size_t bytes) { return host ? cudaMallocHost(p, bytes) : cudaMalloc(p, bytes); }
+    void raw_free(void* p) {
+        if (host) cudaFreeHost(p);
+        else cudaFree(p);
+    }
+    cudaError_t alloc(void** p, size_t bytes) {
+        *p = nullptr;
+        if (bytes == 0) bytes = 8;
+        int dev = 0;
+        if (!host) cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = idle.find({dev, bytes});
+            if (it != idle.end() && !it->second.empty()) {
+                *p = it->second.back();
+                it->second.pop_back();
+                idle_bytes -= bytes;
+                live[*p] = {dev, bytes};
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = raw_alloc(p, bytes);
+        if (e != cudaSuccess) {
+            // out of memory with idle blocks around: give them back and retry once
+            trim();
+            cudaGetLastError();
+            e = raw_alloc(p, bytes);
+            if (e != cudaSuccess) return e;
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        live[*p] = {dev, bytes};
+        return cudaSuccess;
+    }
+    void release(void* p) {
+        if (p == nullptr) return;
+        std::pair<int, size_t> key;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = live.find(p);
+            if (it == live.end()) {             // not ours
+                raw_free(p);
+                return;
+            }
+            key = it->second;
+            live.erase(it);
+            if (idle_bytes + key.second <= cap()) {
+                idle[key].push_back(p);
+                idle_bytes += key.second;
+                return;
+            }
+        }
+        raw_free(p);
+    }
+    void trim() {
+        std::vector<std::pair<int, void*>> blocks;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (auto& kv : idle)
+                for (void* b : kv.second) blocks.push_back({kv.first.first, b});
+            idle.clear();
+            idle_bytes = 0;
+        }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto& b : blocks) {
+            if (!host) cudaSetDevice(b.first);
+            raw_free(b.second);
+        }
+        if (!host) cudaSetDevice(cur);
+    }
+};
+
+BlockCache& dev_cache() {
+    static BlockCache* c = new BlockCache(false);     // leaked on purpose: no CUDA calls during static destruction
+    return *c;
+}
+BlockCache& host_cache() {
+    static BlockCache* c = new BlockCache(true);
+    return *c;
+}
+
+}  // namespace
+
+cudaError_t egx_dev_malloc_bytes(void** p, size_t bytes) { return dev_cache().alloc(p, bytes); }
+void egx_dev_free(void* p) { dev_cache().release(p); }
+cudaError_t egx_host_malloc_bytes(void** p, size_t bytes) { return host_cache().alloc(p, bytes); }
+void egx_host_free(void* p) { host_cache().release(p); }
+void egx_mem_trim() {
+    dev_cache().trim();
+    host_cache().trim();
+}
+
+extern "C" void egx_release_cached_memory(void) { egx_mem_trim(); }

@@ -246,20 +246,20 @@ int evaluate_small_batch(egx_gp_ctx* c, const double* thetas, int B, double* rlf
     if (B <= 0) return EGX_OK;
     c->trained = false;
     if (B > c->sb_cap) {
-        cudaFree(c->sb_thetas);
-        cudaFree(c->sb_G);
-        cudaFree(c->sb_out);
-        cudaFreeHost(c->sb_out_h);
-        cudaFreeHost(c->sb_G_h);
-        cudaFreeHost(c->sb_thetas_h);
+        egx_dev_free(c->sb_thetas);
+        egx_dev_free(c->sb_G);
+        egx_dev_free(c->sb_out);
+        egx_host_free(c->sb_out_h);
+        egx_host_free(c->sb_G_h);
+        egx_host_free(c->sb_thetas_h);
         c->sb_cap = 0;
         const int cap = std::max(B, 64);
-        EGX_CUDA_TRY(cudaMalloc(&c->sb_thetas, static_cast<size_t>(cap) * c->h * sizeof(double)));
-        EGX_CUDA_TRY(cudaMalloc(&c->sb_G, static_cast<size_t>(cap) * c->p * c->p * sizeof(double)));
-        EGX_CUDA_TRY(cudaMalloc(&c->sb_out, static_cast<size_t>(cap) * sizeof(SmallOutHost)));
-        EGX_CUDA_TRY(cudaMallocHost(&c->sb_out_h, static_cast<size_t>(cap) * sizeof(SmallOutHost)));
-        EGX_CUDA_TRY(cudaMallocHost(&c->sb_G_h, static_cast<size_t>(cap) * c->p * c->p * sizeof(double)));
-        EGX_CUDA_TRY(cudaMallocHost(&c->sb_thetas_h, static_cast<size_t>(cap) * c->h * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&c->sb_thetas, static_cast<size_t>(cap) * c->h * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&c->sb_G, static_cast<size_t>(cap) * c->p * c->p * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&c->sb_out, static_cast<size_t>(cap) * sizeof(SmallOutHost)));
+        EGX_CUDA_TRY(egx_host_malloc(&c->sb_out_h, static_cast<size_t>(cap) * sizeof(SmallOutHost)));
+        EGX_CUDA_TRY(egx_host_malloc(&c->sb_G_h, static_cast<size_t>(cap) * c->p * c->p * sizeof(double)));
+        EGX_CUDA_TRY(egx_host_malloc(&c->sb_thetas_h, static_cast<size_t>(cap) * c->h * sizeof(double)));
         c->sb_cap = cap;
     }
     std::vector<char> bad(B, 0);
@@ -406,16 +406,16 @@ int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
 
 int ensure_predict_buffers(egx_gp_ctx* c, int mb) {
     if (mb <= c->mb_alloc) return EGX_OK;
-    cudaFree(c->Y);
-    cudaFree(c->xchunk);
-    cudaFree(c->ychunk);
-    cudaFree(c->vchunk);
+    egx_dev_free(c->Y);
+    egx_dev_free(c->xchunk);
+    egx_dev_free(c->ychunk);
+    egx_dev_free(c->vchunk);
     c->Y = c->xchunk = c->ychunk = c->vchunk = nullptr;
     c->mb_alloc = 0;
-    EGX_CUDA_TRY(cudaMalloc(&c->Y, static_cast<size_t>(mb) * c->npad * sizeof(double)));
-    EGX_CUDA_TRY(cudaMalloc(&c->xchunk, static_cast<size_t>(mb) * c->d * sizeof(double)));
-    EGX_CUDA_TRY(cudaMalloc(&c->ychunk, static_cast<size_t>(mb) * sizeof(double)));
-    EGX_CUDA_TRY(cudaMalloc(&c->vchunk, static_cast<size_t>(mb) * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&c->Y, static_cast<size_t>(mb) * c->npad * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&c->xchunk, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&c->ychunk, static_cast<size_t>(mb) * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&c->vchunk, static_cast<size_t>(mb) * sizeof(double)));
     if (c->env.ensure_panel_rows(mb) != EGX_OK) return EGX_CUDA_ERROR;
     c->mb_alloc = mb;
     return EGX_OK;
@@ -505,39 +505,39 @@ void free_ctx(egx_gp_ctx* c) {
     c->eval_graph = nullptr;
     if (c->timer_a) cudaEventDestroy(c->timer_a);
     if (c->timer_b) cudaEventDestroy(c->timer_b);
-    cudaFree(c->X);
-    cudaFree(c->ynorm);
-    cudaFree(c->x_mean);
-    cudaFree(c->x_std);
-    cudaFree(c->FyT);
-    cudaFree(c->basis_i);
-    cudaFree(c->basis_j);
-    cudaFree(c->terms);
-    cudaFree(c->M);
-    cudaFree(c->LT);
-    cudaFree(c->KF);
-    cudaFree(c->W_dev);
-    cudaFree(c->sb_thetas);
-    cudaFree(c->sb_G);
-    cudaFree(c->sb_out);
-    cudaFreeHost(c->sb_out_h);
-    cudaFreeHost(c->sb_G_h);
-    cudaFreeHost(c->sb_thetas_h);
-    cudaFree(c->Dinv);
-    cudaFree(c->glswork);
-    cudaFree(c->G);
-    cudaFree(c->beta);
-    cudaFree(c->rho);
-    cudaFree(c->res);
-    cudaFree(c->info);
-    cudaFree(c->Y);
-    cudaFree(c->xchunk);
-    cudaFree(c->ychunk);
-    cudaFree(c->vchunk);
-    cudaFreeHost(c->terms_h);
-    cudaFreeHost(c->res_h);
-    cudaFreeHost(c->G_h);
-    cudaFreeHost(c->beta_h);
+    egx_dev_free(c->X);
+    egx_dev_free(c->ynorm);
+    egx_dev_free(c->x_mean);
+    egx_dev_free(c->x_std);
+    egx_dev_free(c->FyT);
+    egx_dev_free(c->basis_i);
+    egx_dev_free(c->basis_j);
+    egx_dev_free(c->terms);
+    egx_dev_free(c->M);
+    egx_dev_free(c->LT);
+    egx_dev_free(c->KF);
+    egx_dev_free(c->W_dev);
+    egx_dev_free(c->sb_thetas);
+    egx_dev_free(c->sb_G);
+    egx_dev_free(c->sb_out);
+    egx_host_free(c->sb_out_h);
+    egx_host_free(c->sb_G_h);
+    egx_host_free(c->sb_thetas_h);
+    egx_dev_free(c->Dinv);
+    egx_dev_free(c->glswork);
+    egx_dev_free(c->G);
+    egx_dev_free(c->beta);
+    egx_dev_free(c->rho);
+    egx_dev_free(c->res);
+    egx_dev_free(c->info);
+    egx_dev_free(c->Y);
+    egx_dev_free(c->xchunk);
+    egx_dev_free(c->ychunk);
+    egx_dev_free(c->vchunk);
+    egx_host_free(c->terms_h);
+    egx_host_free(c->res_h);
+    egx_host_free(c->G_h);
+    egx_host_free(c->beta_h);
     c->env.destroy();
     delete c;
 }
@@ -621,43 +621,43 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
     c->use_graphs = c->npad <= 4096;
     if (const char* e = getenv("EGX_GRAPHS")) c->use_graphs = atoi(e) != 0;
     const size_t xbytes = static_cast<size_t>(c->npad) * d * sizeof(double);
-    EGX_CREATE_TRY(cudaMalloc(&c->X, xbytes));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->X, xbytes));
     EGX_CREATE_TRY(cudaMemsetAsync(c->X, 0, xbytes, c->stream));
     EGX_CREATE_TRY(cudaMemcpyAsync(c->X, xnorm, static_cast<size_t>(n) * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    EGX_CREATE_TRY(cudaMalloc(&c->ynorm, c->npad * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->ynorm, c->npad * sizeof(double)));
     EGX_CREATE_TRY(cudaMemsetAsync(c->ynorm, 0, c->npad * sizeof(double), c->stream));
     EGX_CREATE_TRY(cudaMemcpyAsync(c->ynorm, ynorm, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    EGX_CREATE_TRY(cudaMalloc(&c->x_mean, d * sizeof(double)));
-    EGX_CREATE_TRY(cudaMalloc(&c->x_std, d * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->x_mean, d * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->x_std, d * sizeof(double)));
     EGX_CREATE_TRY(cudaMemcpyAsync(c->x_mean, x_mean, d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     EGX_CREATE_TRY(cudaMemcpyAsync(c->x_std, x_std, d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    EGX_CREATE_TRY(cudaMalloc(&c->basis_i, p * sizeof(int)));
-    EGX_CREATE_TRY(cudaMalloc(&c->basis_j, p * sizeof(int)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->basis_i, p * sizeof(int)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->basis_j, p * sizeof(int)));
     EGX_CREATE_TRY(cudaMemcpyAsync(c->basis_i, c->basis_i_h.data(), p * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     EGX_CREATE_TRY(cudaMemcpyAsync(c->basis_j, c->basis_j_h.data(), p * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    EGX_CREATE_TRY(cudaMalloc(&c->W_dev, static_cast<size_t>(d) * h * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->W_dev, static_cast<size_t>(d) * h * sizeof(double)));
     EGX_CREATE_TRY(cudaMemcpyAsync(c->W_dev, w_star, static_cast<size_t>(d) * h * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->max_terms = d * h;
-    EGX_CREATE_TRY(cudaMalloc(&c->terms, c->max_terms * sizeof(CorrTerm)));
-    EGX_CREATE_TRY(cudaMallocHost(&c->terms_h, c->max_terms * sizeof(CorrTerm)));
-    EGX_CREATE_TRY(cudaMalloc(&c->FyT, static_cast<size_t>(c->q) * c->ld * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->terms, c->max_terms * sizeof(CorrTerm)));
+    EGX_CREATE_TRY(egx_host_malloc(&c->terms_h, c->max_terms * sizeof(CorrTerm)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->FyT, static_cast<size_t>(c->q) * c->ld * sizeof(double)));
     const size_t mbytes = static_cast<size_t>(c->rows_total) * c->ld * sizeof(double);
-    EGX_CREATE_TRY(cudaMalloc(&c->M, mbytes));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->M, mbytes));
     EGX_CREATE_TRY(cudaMemsetAsync(c->M, 0, mbytes, c->stream));
-    EGX_CREATE_TRY(cudaMalloc(&c->Dinv, static_cast<size_t>(c->npad / EGX_NB) * 4096 * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->Dinv, static_cast<size_t>(c->npad / EGX_NB) * 4096 * sizeof(double)));
     if (c->env.ensure_panel_rows(c->rows_total) != EGX_OK) {
         free_ctx(c);
         return EGX_CUDA_ERROR;
     }
-    EGX_CREATE_TRY(cudaMalloc(&c->glswork, static_cast<size_t>(c->q) * c->npad * sizeof(double)));
-    EGX_CREATE_TRY(cudaMalloc(&c->G, static_cast<size_t>(p) * p * sizeof(double)));
-    EGX_CREATE_TRY(cudaMalloc(&c->beta, p * sizeof(double)));
-    EGX_CREATE_TRY(cudaMalloc(&c->rho, c->npad * sizeof(double)));
-    EGX_CREATE_TRY(cudaMalloc(&c->res, sizeof(EvalResult)));
-    EGX_CREATE_TRY(cudaMalloc(&c->info, sizeof(int)));
-    EGX_CREATE_TRY(cudaMallocHost(&c->res_h, sizeof(EvalResult)));
-    EGX_CREATE_TRY(cudaMallocHost(&c->G_h, static_cast<size_t>(p) * p * sizeof(double)));
-    EGX_CREATE_TRY(cudaMallocHost(&c->beta_h, p * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->glswork, static_cast<size_t>(c->q) * c->npad * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->G, static_cast<size_t>(p) * p * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->beta, p * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->rho, c->npad * sizeof(double)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->res, sizeof(EvalResult)));
+    EGX_CREATE_TRY(egx_dev_malloc(&c->info, sizeof(int)));
+    EGX_CREATE_TRY(egx_host_malloc(&c->res_h, sizeof(EvalResult)));
+    EGX_CREATE_TRY(egx_host_malloc(&c->G_h, static_cast<size_t>(p) * p * sizeof(double)));
+    EGX_CREATE_TRY(egx_host_malloc(&c->beta_h, p * sizeof(double)));
     launch_mean_basis_rows(c->X, n, c->npad, d, c->basis_i, c->basis_j, p, c->ynorm, c->FyT, c->ld, c->stream);
     EGX_CREATE_TRY(cudaStreamSynchronize(c->stream));
     EGX_CREATE_TRY(cudaGetLastError());
@@ -834,8 +834,8 @@ extern "C" int egx_gp_predict_gradients(egx_gp_ctx* c, const double* x, int m, d
     EGX_CUDA_TRY(cudaSetDevice(c->device));
     const int mb = std::min(round_up(m, EGX_NB), PREDICT_CHUNK);
     double *xd = nullptr, *gd = nullptr;
-    EGX_CUDA_TRY(cudaMalloc(&xd, static_cast<size_t>(mb) * c->d * sizeof(double)));
-    EGX_CUDA_TRY(cudaMalloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&xd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
     int st = EGX_OK;
     for (int i0 = 0; i0 < m && st == EGX_OK; i0 += mb) {
         const int mc = std::min(mb, m - i0);
@@ -850,8 +850,8 @@ extern "C" int egx_gp_predict_gradients(egx_gp_ctx* c, const double* x, int m, d
                         cudaMemcpyDeviceToHost, c->stream);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = EGX_CUDA_ERROR;
     }
-    cudaFree(xd);
-    cudaFree(gd);
+    egx_dev_free(xd);
+    egx_dev_free(gd);
     if (st != EGX_OK || cudaGetLastError() != cudaSuccess) {
         egx_set_error("predict_gradients: CUDA failure");
         return EGX_CUDA_ERROR;
@@ -875,8 +875,8 @@ extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int 
     const int T = c->npad / EGX_NB;
     const long ld = c->ld;
     if (!c->grad_ready) {
-        if (!c->LT) EGX_CUDA_TRY(cudaMalloc(&c->LT, static_cast<size_t>(c->npad) * ld * sizeof(double)));
-        if (!c->KF) EGX_CUDA_TRY(cudaMalloc(&c->KF, static_cast<size_t>(c->p) * c->npad * sizeof(double)));
+        if (!c->LT) EGX_CUDA_TRY(egx_dev_malloc(&c->LT, static_cast<size_t>(c->npad) * ld * sizeof(double)));
+        if (!c->KF) EGX_CUDA_TRY(egx_dev_malloc(&c->KF, static_cast<size_t>(c->p) * c->npad * sizeof(double)));
         launch_transpose_lower(c->M, ld, c->LT, T, c->stream);
         // K_F = R^-1 F = L^-T (L^-1 F): rows npad.. of M hold (L^-1 F)^T, one back substitution per basis function
         EGX_CUDA_TRY(cudaMemcpy2DAsync(c->KF, c->npad * sizeof(double), c->M + static_cast<long>(c->npad) * ld,
@@ -889,7 +889,7 @@ extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int 
     int st = ensure_predict_buffers(c, mb);
     if (st != EGX_OK) return st;
     double* gd = nullptr;
-    EGX_CUDA_TRY(cudaMalloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
     for (int i0 = 0; i0 < m && st == EGX_OK; i0 += mb) {
         const int mc = std::min(mb, m - i0);
         const int mpad = round_up(mc, EGX_NB);
@@ -936,7 +936,7 @@ extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int 
                         cudaMemcpyDeviceToHost, c->stream);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = EGX_CUDA_ERROR;
     }
-    cudaFree(gd);
+    egx_dev_free(gd);
     if (st != EGX_OK || cudaGetLastError() != cudaSuccess) {
         egx_set_error("predict_var_gradients: CUDA failure (%s)", cudaGetErrorString(cudaGetLastError()));
         return EGX_CUDA_ERROR;
@@ -944,6 +944,203 @@ extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int 
     resolve_profile(c);
     return EGX_OK;
 }
+// ---------------------------------------------------------------------------------------------
+// Conditional covariance and trajectory sampling (gp/src/algorithm.rs:310-326, 383-410, 1153-1194).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct CovWork {
+    double *K = nullptr, *xn = nullptr, *U = nullptr, *xraw = nullptr, *mean = nullptr;
+    int mpad = 0;
+    ~CovWork() {
+        egx_dev_free(K);
+        egx_dev_free(xn);
+        egx_dev_free(U);
+        egx_dev_free(xraw);
+        egx_dev_free(mean);
+    }
+};
+
+constexpr int COV_MAX_POINTS = 8192;
+
+// w.K <- sigma2 (K(x, x) - rt^T rt + u^T u), padded with the identity to mpad x mpad ; w.mean <- predict(x)
+int conditional_cov_dev(egx_gp_ctx* c, const double* x, int m, CovWork& w) {
+    if (!c->trained) {
+        egx_set_error("covariance / sample called before a successful egx_gp_finalize");
+        return EGX_INVALID_VALUE;
+    }
+    if (m < 1 || m > COV_MAX_POINTS) {
+        egx_set_error("covariance / sample: number of locations must be in 1..%d (got %d)", COV_MAX_POINTS, m);
+        return EGX_INVALID_VALUE;
+    }
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    const int mpad = round_up(m, EGX_NB);
+    w.mpad = mpad;
+    int st = ensure_predict_buffers(c, mpad);
+    if (st != EGX_OK) return st;
+    EGX_CUDA_TRY(egx_dev_malloc(&w.K, static_cast<size_t>(mpad) * mpad * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&w.xn, static_cast<size_t>(mpad) * c->d * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&w.U, static_cast<size_t>(m) * c->p * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&w.xraw, static_cast<size_t>(m) * c->d * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&w.mean, static_cast<size_t>(m) * sizeof(double)));
+    EGX_CUDA_TRY(cudaMemcpyAsync(w.xraw, x, static_cast<size_t>(m) * c->d * sizeof(double), cudaMemcpyHostToDevice,
+                                 c->stream));
+    // c(x, X) rows + the predicted mean, then rt = L^-1 c^T as rows of Y
+    {
+        StageScope sc(c->env.prof, EGX_STAGE_CROSS_CORR, 1, c->stream);
+        launch_cross_corr(c->corr, w.xraw, m, mpad, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d, c->terms, c->nterms,
+                          c->rho, c->beta, c->basis_i, c->basis_j, c->p, c->y_mean, c->y_std, c->Y, c->npad, w.mean,
+                          c->stream);
+    }
+    blocked_sweep(c->env, factor_ref(c), false, c->Y, c->npad, mpad / EGX_NB, mpad / 64);
+    {
+        StageScope sc(c->env.prof, EGX_STAGE_VAR_FINISH, 1, c->stream);
+        launch_var_finish(c->Y, c->npad, m, c->npad, w.xraw, c->x_mean, c->x_std, c->d,
+                          c->M + static_cast<long>(c->npad) * c->ld, c->ld, c->G, c->p, c->basis_i, c->basis_j,
+                          c->sigma2_scaled, nullptr, c->stream, w.U);
+    }
+    // K(x, x): the cross-correlation kernel with the (normalised) locations as the "training" set
+    launch_normalize_rows(w.xraw, m, mpad, c->d, c->x_mean, c->x_std, w.xn, c->stream);
+    {
+        StageScope sc(c->env.prof, EGX_STAGE_CROSS_CORR, 1, c->stream);
+        launch_cross_corr(c->corr, w.xraw, m, mpad, c->x_mean, c->x_std, w.xn, m, mpad, c->d, c->terms, c->nterms, nullptr,
+                          nullptr, c->basis_i, c->basis_j, 0, 0.0, 1.0, w.K, mpad, nullptr, c->stream);
+    }
+    {
+        GemmArgs g;                       // K -= rt^T rt  (rows of Y are the columns of rt)
+        g.C = w.K;
+        g.ldc = mpad;
+        g.A = c->Y;
+        g.lda = c->npad;
+        g.B = c->Y;
+        g.ldb = c->npad;
+        g.K = c->npad;
+        g.tri = 0;
+        g.Mt = g.Nt = mpad / EGX_NB;
+        StageScope sc(c->env.prof, EGX_STAGE_SYRK_GEMM, 1, c->stream);
+        launch_gemm_nt_sub(g, c->stream);
+    }
+    launch_cov_finish(w.K, mpad, m, mpad, w.U, c->p, c->sigma2_scaled, c->stream);
+    return EGX_OK;
+}
+
+}  // namespace
+
+extern "C" int egx_gp_covariance(egx_gp_ctx* c, const double* x, int m, double* cov) {
+    if (!c || !x || !cov) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CovWork w;
+    int st = conditional_cov_dev(c, x, m, w);
+    if (st != EGX_OK) return st;
+    EGX_CUDA_TRY(cudaMemcpy2DAsync(cov, static_cast<size_t>(m) * sizeof(double), w.K,
+                                   static_cast<size_t>(w.mpad) * sizeof(double), static_cast<size_t>(m) * sizeof(double), m,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EGX_CUDA_TRY(cudaGetLastError());
+    resolve_profile(c);
+    return EGX_OK;
+}
+
+extern "C" int egx_gp_sample(egx_gp_ctx* c, const double* x, int m, const double* z, int n_traj, int method,
+                             double* out) {
+    if (!c || !x || !z || !out || n_traj < 1) return EGX_INVALID_VALUE;
+    if (method != EGX_SAMPLE_CHOLESKY && method != EGX_SAMPLE_EIGENVALUES) {
+        egx_set_error("unknown sampling method %d", method);
+        return EGX_INVALID_VALUE;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CovWork w;
+    int st = conditional_cov_dev(c, x, m, w);
+    if (st != EGX_OK) return st;
+    const int mpad = w.mpad, tpad = round_up(n_traj, EGX_NB);
+    struct Tmp {
+        double *ZT = nullptr, *OUT = nullptr, *Dinv = nullptr;
+        int* info = nullptr;
+        ~Tmp() {
+            egx_dev_free(ZT);
+            egx_dev_free(OUT);
+            egx_dev_free(Dinv);
+            egx_dev_free(info);
+        }
+    } t;
+    EGX_CUDA_TRY(egx_dev_malloc(&t.ZT, static_cast<size_t>(tpad) * mpad * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&t.OUT, static_cast<size_t>(mpad) * tpad * sizeof(double)));
+    // the normal draws, one trajectory per row (the B operand of the NT product)
+    std::vector<double> zt(static_cast<size_t>(tpad) * mpad, 0.0);
+    for (int i = 0; i < m; ++i)
+        for (int k = 0; k < n_traj; ++k) zt[static_cast<size_t>(k) * mpad + i] = z[static_cast<size_t>(i) * n_traj + k];
+    EGX_CUDA_TRY(cudaMemcpyAsync(t.ZT, zt.data(), zt.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+
+    if (method == EGX_SAMPLE_CHOLESKY) {
+        // cov = C C^T with the same blocked factorisation as the likelihood (algorithm.rs:1162-1168)
+        EGX_CUDA_TRY(egx_dev_malloc(&t.Dinv, static_cast<size_t>(mpad / EGX_NB) * 4096 * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&t.info, sizeof(int)));
+        EGX_CUDA_TRY(cudaMemsetAsync(t.info, 0, sizeof(int), c->stream));
+        FactorRef f;
+        f.M = w.K;
+        f.ld = mpad;
+        f.T = mpad / EGX_NB;
+        f.qpad = 0;
+        f.Dinv = t.Dinv;
+        f.info = t.info;
+        blocked_sweep(c->env, f, true, nullptr, 0, 0, 0);
+        int info_h = 0;
+        EGX_CUDA_TRY(cudaMemcpyAsync(&info_h, t.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (info_h != 0) {
+            egx_set_error("conditional covariance is not positive definite (pivot %d); use the eigenvalue method",
+                          info_h);
+            return EGX_NOT_POSITIVE_DEFINITE;
+        }
+        launch_zero_upper(w.K, mpad, mpad, c->stream);
+    } else {
+        // C = W diag(sqrt(max(v, 0))) with eigenvalues below 1e-9 dropped (algorithm.rs:1169-1187); the m x m
+        // eigen-decomposition runs on the host, as in the reference
+        std::vector<double> a(static_cast<size_t>(m) * m), ev(m);
+        EGX_CUDA_TRY(cudaMemcpy2DAsync(a.data(), static_cast<size_t>(m) * sizeof(double), w.K,
+                                       static_cast<size_t>(mpad) * sizeof(double), static_cast<size_t>(m) * sizeof(double),
+                                       m, cudaMemcpyDeviceToHost, c->stream));
+        EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (egx_host_symmetric_eig(m, a.data(), ev.data()) != 0) {
+            egx_set_error("eigen-decomposition of the conditional covariance did not converge");
+            return EGX_INVALID_VALUE;
+        }
+        for (int j = 0; j < m; ++j) ev[j] = (ev[j] < 1e-9) ? 0.0 : std::sqrt(ev[j]);
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) a[static_cast<size_t>(i) * m + j] *= ev[j];
+        EGX_CUDA_TRY(cudaMemsetAsync(w.K, 0, static_cast<size_t>(mpad) * mpad * sizeof(double), c->stream));
+        EGX_CUDA_TRY(cudaMemcpy2DAsync(w.K, static_cast<size_t>(mpad) * sizeof(double), a.data(),
+                                       static_cast<size_t>(m) * sizeof(double), static_cast<size_t>(m) * sizeof(double), m,
+                                       cudaMemcpyHostToDevice, c->stream));
+        EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));      // `a` goes out of scope
+    }
+    // trajectories = mean + C Z   (algorithm.rs:1191-1193)
+    launch_bcast_rows(t.OUT, tpad, m, mpad, tpad, w.mean, c->stream);
+    {
+        GemmArgs g;
+        g.C = t.OUT;
+        g.ldc = tpad;
+        g.A = w.K;
+        g.lda = mpad;
+        g.B = t.ZT;
+        g.ldb = mpad;
+        g.K = mpad;
+        g.add = 1;
+        g.tri = 0;
+        g.Mt = mpad / EGX_NB;
+        g.Nt = tpad / EGX_NB;
+        StageScope sc(c->env.prof, EGX_STAGE_SYRK_GEMM, 1, c->stream);
+        launch_gemm_nt_sub(g, c->stream);
+    }
+    EGX_CUDA_TRY(cudaMemcpy2DAsync(out, static_cast<size_t>(n_traj) * sizeof(double), t.OUT,
+                                   static_cast<size_t>(tpad) * sizeof(double), static_cast<size_t>(n_traj) * sizeof(double),
+                                   m, cudaMemcpyDeviceToHost, c->stream));
+    EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EGX_CUDA_TRY(cudaGetLastError());
+    resolve_profile(c);
+    return EGX_OK;
+}
+
 extern "C" int egx_gp_predict_valvar_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, double* var_dev) {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -979,7 +1176,7 @@ extern "C" int egx_gp_cross_correlation(egx_gp_ctx* c, const double* x, int m, d
     int st = ensure_predict_buffers(c, mb);
     if (st != EGX_OK) return st;
     double* cdev = nullptr;
-    EGX_CUDA_TRY(cudaMalloc(&cdev, static_cast<size_t>(mb) * c->n * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&cdev, static_cast<size_t>(mb) * c->n * sizeof(double)));
     for (int i0 = 0; i0 < m; i0 += mb) {
         const int mc = std::min(mb, m - i0);
         cudaMemcpyAsync(c->xchunk, x + static_cast<long>(i0) * c->d, static_cast<size_t>(mc) * c->d * sizeof(double),
@@ -990,7 +1187,7 @@ extern "C" int egx_gp_cross_correlation(egx_gp_ctx* c, const double* x, int m, d
                         cudaMemcpyDeviceToHost, c->stream);
         cudaStreamSynchronize(c->stream);
     }
-    cudaFree(cdev);
+    egx_dev_free(cdev);
     if (st != EGX_OK) return st;
     EGX_CUDA_TRY(cudaGetLastError());
     resolve_profile(c);

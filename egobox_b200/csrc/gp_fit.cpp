@@ -782,6 +782,15 @@ extern "C" int egx_gp_model_predict_var_gradients(egx_gp_model* m, const double*
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_predict_var_gradients(m->ctx, x, npts, grad);
 }
+extern "C" int egx_gp_model_covariance(egx_gp_model* m, const double* x, int npts, double* cov) {
+    if (!m) return EGX_INVALID_VALUE;
+    return egx_gp_covariance(m->ctx, x, npts, cov);
+}
+extern "C" int egx_gp_model_sample(egx_gp_model* m, const double* x, int npts, const double* z, int n_traj, int method,
+                                   double* out) {
+    if (!m) return EGX_INVALID_VALUE;
+    return egx_gp_sample(m->ctx, x, npts, z, n_traj, method, out);
+}
 extern "C" int egx_gp_model_predict_gradients(egx_gp_model* m, const double* x, int npts, double* grad) {
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_predict_gradients(m->ctx, x, npts, grad);

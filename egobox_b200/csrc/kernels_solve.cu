@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256)
                       const double* __restrict__ x_mean, const double* __restrict__ x_std, int d,
                       const double* __restrict__ FtT, long ldf, const double* __restrict__ G, int p,
                       const int* __restrict__ basis_i, const int* __restrict__ basis_j, double sigma2,
-                      double* __restrict__ var) {
+                      double* __restrict__ var, double* __restrict__ U) {
     extern __shared__ double vsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* xs = vsm + warp * (d + p);
@@ -235,18 +235,83 @@ __global__ void __launch_bounds__(256)
         s = warp_sum(s);
         const double u = (z[a] - s) / G[a * p + a];
         __syncwarp();
-        if (lane == 0) z[a] = u;
+        if (lane == 0) {
+            z[a] = u;
+            if (U != nullptr) U[static_cast<long>(i) * p + a] = u;
+        }
         __syncwarp();
         su += u * u;
     }
-    if (lane == 0) {
+    if (lane == 0 && var != nullptr) {
         double mse = (1.0 - s1) + su;
         mse = sigma2 * mse;
         var[i] = (mse < 0.0) ? 0.0 : mse;
     }
 }
 
+// Conditional covariance epilogue (gp/src/algorithm.rs:323-324): C holds K(x, x) - rt^T rt on entry;
+//   cov[i][j] = sigma2 * (C[i][j] + u_i . u_j)   for i, j < m ;  identity on the padding (so that the padded
+// matrix can be factorised as it is).
+__global__ void __launch_bounds__(256)
+    cov_finish_kernel(double* __restrict__ C, long ld, int m, int mpad, const double* __restrict__ U, int p,
+                      double sigma2) {
+    const int j = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int i = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i >= mpad || j >= mpad) return;
+    double v;
+    if (i < m && j < m) {
+        double s = C[static_cast<long>(i) * ld + j];
+        for (int l = 0; l < p; ++l) s += U[static_cast<long>(i) * p + l] * U[static_cast<long>(j) * p + l];
+        v = sigma2 * s;
+    } else {
+        v = (i == j) ? 1.0 : 0.0;
+    }
+    C[static_cast<long>(i) * ld + j] = v;
+}
+
+// out[i][:] = (x[i][:] - mean) / std for i < m, zero rows up to mpad
+__global__ void normalize_rows_kernel(const double* __restrict__ x, int m, int mpad, int d,
+                                      const double* __restrict__ mean, const double* __restrict__ sd,
+                                      double* __restrict__ out) {
+    const long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<long>(mpad) * d) return;
+    const int i = static_cast<int>(e / d), c = static_cast<int>(e - static_cast<long>(i) * d);
+    out[e] = (i < m) ? (x[e] - mean[c]) / sd[c] : 0.0;
+}
+
+// strictly-upper part of an (npad x npad) matrix <- 0 (a factor used as a dense GEMM operand)
+__global__ void zero_upper_kernel(double* __restrict__ A, long ld, int npad) {
+    const int j = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int i = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i < npad && j < npad && j > i) A[static_cast<long>(i) * ld + j] = 0.0;
+}
+
+// out[i][c] = mean[i] for i < m (else 0): the trajectories start from the predicted mean
+__global__ void bcast_rows_kernel(double* __restrict__ out, long ld, int m, int mpad, int cols,
+                                  const double* __restrict__ mean) {
+    const long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<long>(mpad) * cols) return;
+    const int i = static_cast<int>(e / cols), c = static_cast<int>(e - static_cast<long>(i) * cols);
+    out[static_cast<long>(i) * ld + c] = (i < m) ? mean[i] : 0.0;
+}
+
 }  // namespace
+
+void launch_cov_finish(double* C, long ld, int m, int mpad, const double* U, int p, double sigma2, cudaStream_t s) {
+    cov_finish_kernel<<<dim3((mpad + 63) / 64, (mpad + 3) / 4), 256, 0, s>>>(C, ld, m, mpad, U, p, sigma2);
+}
+void launch_normalize_rows(const double* x, int m, int mpad, int d, const double* mean, const double* sd, double* out,
+                           cudaStream_t s) {
+    const long tot = static_cast<long>(mpad) * d;
+    normalize_rows_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(x, m, mpad, d, mean, sd, out);
+}
+void launch_zero_upper(double* A, long ld, int npad, cudaStream_t s) {
+    zero_upper_kernel<<<dim3((npad + 63) / 64, (npad + 3) / 4), 256, 0, s>>>(A, ld, npad);
+}
+void launch_bcast_rows(double* out, long ld, int m, int mpad, int cols, const double* mean, cudaStream_t s) {
+    const long tot = static_cast<long>(mpad) * cols;
+    bcast_rows_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, s>>>(out, ld, m, mpad, cols, mean);
+}
 
 void launch_gls(const double* M, long ld, int n, int npad, int p, double* work, double* G, double* beta, double* rho,
                 EvalResult* res, const int* info, cudaStream_t s) {
@@ -274,8 +339,9 @@ void launch_backsolve_update(const double* Lrow, long ld, const double* gamma_k,
 
 void launch_var_finish(const double* Y, long ldy, int m, int npad, const double* xraw, const double* x_mean,
                        const double* x_std, int d, const double* FtT, long ldf, const double* G, int p,
-                       const int* basis_i, const int* basis_j, double sigma2, double* var, cudaStream_t s) {
+                       const int* basis_i, const int* basis_j, double sigma2, double* var, cudaStream_t s,
+                       double* U) {
     const size_t smem = 8 * static_cast<size_t>(d + p) * sizeof(double);
     var_finish_kernel<<<(m + 7) / 8, 256, smem, s>>>(Y, ldy, m, npad, xraw, x_mean, x_std, d, FtT, ldf, G, p, basis_i,
-                                                     basis_j, sigma2, var);
+                                                     basis_j, sigma2, var, U);
 }

@@ -73,9 +73,9 @@ int SweepEnv::init(int max_block_cols) {
 int SweepEnv::ensure_panel_rows(long rows) {
     if (rows <= p_rows) return EGX_OK;
     for (int i = 0; i < 2; ++i) {
-        cudaFree(P2[i]);
+        egx_dev_free(P2[i]);
         P2[i] = nullptr;
-        EGX_CUDA_TRY(cudaMalloc(&P2[i], static_cast<size_t>(rows) * 2 * EGX_NB * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&P2[i], static_cast<size_t>(rows) * 2 * EGX_NB * sizeof(double)));
     }
     p_rows = rows;
     ++generation;
@@ -92,8 +92,8 @@ void SweepEnv::destroy() {
         if (e) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
-    cudaFree(P2[0]);
-    cudaFree(P2[1]);
+    egx_dev_free(P2[0]);
+    egx_dev_free(P2[1]);
     if (sp) cudaStreamDestroy(sp);
     if (sb) cudaStreamDestroy(sb);
     sb = sp = nullptr;

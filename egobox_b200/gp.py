@@ -292,6 +292,42 @@ class GaussianProcess:
         """algorithm.rs:708-727."""
         return self.predict_gradients(x), self.predict_var_gradients(x)
 
+    def covariance(self, x):
+        """algorithm.rs:310-326 `_compute_covariance`: (n, n) conditional covariance at the rows of x."""
+        x = self._x(x)
+        cov = np.empty((x.shape[0], x.shape[0]))
+        st = self._lib.egx_gp_model_covariance(self._h, x.ctypes.data_as(C.POINTER(C.c_double)), x.shape[0],
+                                               cov.ctypes.data_as(C.POINTER(C.c_double)))
+        if st != EGX_OK:
+            _raise_status(st)
+        return cov
+
+    def _sample(self, x, n_traj, method, seed=None, z=None):
+        x = self._x(x)
+        if z is None:
+            # the reference draws from an unseeded generator (algorithm.rs:1191-1192)
+            z = np.random.default_rng(seed).standard_normal((x.shape[0], int(n_traj)))
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(x.shape[0], -1)
+        out = np.empty_like(z)
+        st = self._lib.egx_gp_model_sample(self._h, x.ctypes.data_as(C.POINTER(C.c_double)), x.shape[0],
+                                           z.ctypes.data_as(C.POINTER(C.c_double)), z.shape[1], int(method),
+                                           out.ctypes.data_as(C.POINTER(C.c_double)))
+        if st != EGX_OK:
+            _raise_status(st)
+        return out
+
+    def sample_chol(self, x, n_traj, seed=None, z=None):
+        """algorithm.rs:383-385: (n, n_traj) trajectories, Cholesky of the conditional covariance."""
+        return self._sample(x, n_traj, 0, seed, z)
+
+    def sample_eig(self, x, n_traj, seed=None, z=None):
+        """algorithm.rs:388-390: eigen-decomposition of the conditional covariance (eigenvalues < 1e-9 dropped)."""
+        return self._sample(x, n_traj, 1, seed, z)
+
+    def sample(self, x, n_traj, seed=None, z=None):
+        """algorithm.rs:393-395: alias of sample_eig."""
+        return self.sample_eig(x, n_traj, seed, z)
+
     def theta(self):
         th = np.empty(self._hdim)
         self._lib.egx_gp_model_theta(self._h, th.ctypes.data_as(C.POINTER(C.c_double)))
@@ -396,3 +432,17 @@ def prepare_multistart(n_start, theta0, bounds, seed=42):
     if st != EGX_OK:
         _raise_status(st)
     return out
+
+
+def symmetric_eig(a):
+    """Host eigen-decomposition used by the eigenvalue sampler (`cov_x.eigh()`, algorithm.rs:1171-1173):
+    returns (w, v) with the eigenvectors as the columns of v (unsorted)."""
+    lib = _lib.load()
+    v = np.array(a, dtype=np.float64, order="C")
+    n = v.shape[0]
+    w = np.empty(n)
+    dp = C.POINTER(C.c_double)
+    st = lib.egx_symmetric_eig(n, v.ctypes.data_as(dp), w.ctypes.data_as(dp))
+    if st != EGX_OK:
+        _raise_status(st)
+    return w, v

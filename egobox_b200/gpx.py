@@ -114,8 +114,10 @@ class Gpx:
         """gp_mix.rs:394-404: (nsamples, nx) variance derivatives."""
         return self._gp.predict_var_gradients(np.asarray(x, dtype=np.float64))
 
-    def sample(self, x, n_traj):
-        raise NotImplementedError("conditional sampling: SURVEY.md 8(f)-4 (next)")
+    def sample(self, x, n_traj, seed=None):
+        """gp_mix.rs:415-425: (nsamples, n_traj) trajectories of the (single-cluster) surrogate;
+        moe/src/algorithm.rs:550-558 -> GaussianProcess::sample (eigenvalue variant)."""
+        return self._gp.sample(np.asarray(x, dtype=np.float64), int(n_traj), seed=seed)
 
     def dims(self):
         return self._gp.dims()

@@ -132,6 +132,22 @@ int egx_gp_predict_gradients(egx_gp_ctx* ctx, const double* x, int m, double* gr
  * forward and one backward multi-RHS sweep per chunk of points.  Supports d <= 32 and d * p <= 2048. */
 int egx_gp_predict_var_gradients(egx_gp_ctx* ctx, const double* x, int m, double* grad);
 
+/* Conditional covariance of the trained GP at m locations, cov (m x m, row-major) =
+ *   sigma2 * (K(x, x) - rt^T rt + u^T u)
+ * `_compute_covariance` gp/src/algorithm.rs:310-326 (rt, u as in predict_var, :330-369).  1 <= m <= 8192. */
+int egx_gp_covariance(egx_gp_ctx* ctx, const double* x, int m, double* cov);
+
+/* Trajectory sampling, `sample_chol` / `sample_eig` / `sample` gp/src/algorithm.rs:383-410 and the free function
+ * `sample` :1153-1194:  out (m x n_traj) = predict(x) 1^T + C z, where C C^T is the conditional covariance, factored
+ * by Cholesky (on the device, same blocked factorisation as the likelihood) or by eigen-decomposition with
+ * eigenvalues below 1e-9 dropped (:1175-1181; m x m symmetric eigenproblem on the host, as in the reference).
+ * The reference draws z ~ N(0, 1) itself (ndarray-rand, :1191-1192); here z (m x n_traj, row-major) is an argument
+ * so that callers own the random stream and results are reproducible.
+ * EGX_NOT_POSITIVE_DEFINITE when the Cholesky variant meets a non-positive pivot (the reference panics, :1164). */
+#define EGX_SAMPLE_CHOLESKY 0
+#define EGX_SAMPLE_EIGENVALUES 1
+int egx_gp_sample(egx_gp_ctx* ctx, const double* x, int m, const double* z, int n_traj, int method, double* out);
+
 /* Same, with x / y / var already resident on the context's device (device
  * pointers).  Used to time the kernels without the PCIe copies. */
 int egx_gp_predict_valvar_dev(egx_gp_ctx* ctx, const double* x_dev, int m,
@@ -239,6 +255,12 @@ int egx_gp_model_normalization(const egx_gp_model* m, double* x_mean, double* x_
 /* the device context of a fitted model (owned by the model) */
 egx_gp_ctx* egx_gp_model_context(egx_gp_model* m);
 
+/* Contexts draw device / pinned memory from a size-keyed cache (a fit creates and destroys ~12 workspaces and the
+ * EGO loop refits every iteration -- the reference allocates its ndarray temporaries per call likewise, through the
+ * system allocator).  Idle blocks are capped by EGX_CACHE_MB (default 4096 per kind); this returns them to the
+ * driver. */
+void egx_release_cached_memory(void);
+
 /* Host-only utilities (no GPU needed).
  * egx_bound_cobyla_minimize: the derivative-free optimiser `optimize_params` runs per
  * chain (gp/src/optimization.rs:122-169): minimise f over the box [lo, hi] from x0 with
@@ -251,6 +273,10 @@ int egx_bound_cobyla_minimize(egx_objective_fn f, void* user, int n, const doubl
                               double* x_opt, double* f_opt, int* n_evals);
 int egx_prepare_multistart(int n_start, const double* theta0, const double* bounds, int dim,
                            unsigned long long seed, double* starts_out);
+/* egx_symmetric_eig: eigen-decomposition of a symmetric n x n matrix (row-major, overwritten by the
+ * eigenvectors as COLUMNS; w = eigenvalues, unsorted) -- the host half of the eigenvalue sampler,
+ * `cov_x.eigh()` gp/src/algorithm.rs:1171-1173.  Returns EGX_OK or EGX_INVALID_VALUE (no convergence). */
+int egx_symmetric_eig(int n, double* a, double* w);
 
 /* predict :253, predict_var :267, predict_valvar :282 (raw x, m x d) */
 int egx_gp_model_predict(egx_gp_model* m, const double* x, int npts, double* y);
@@ -258,6 +284,10 @@ int egx_gp_model_predict_var(egx_gp_model* m, const double* x, int npts, double*
 int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int npts, double* y, double* var);
 int egx_gp_model_predict_gradients(egx_gp_model* m, const double* x, int npts, double* grad /* npts x d */);
 int egx_gp_model_predict_var_gradients(egx_gp_model* m, const double* x, int npts, double* grad /* npts x d */);
+/* GaussianProcess::sample_chol / sample_eig (gp/src/algorithm.rs:383-395) and the covariance they factor (:310-326) */
+int egx_gp_model_covariance(egx_gp_model* m, const double* x, int npts, double* cov /* npts x npts */);
+int egx_gp_model_sample(egx_gp_model* m, const double* x, int npts, const double* z /* npts x n_traj */, int n_traj,
+                        int method, double* out /* npts x n_traj */);
 
 /* ============================================================================
  * Sparse GP (FITC / VFE) -- crates/gp/src/sparse_algorithm.rs.

@@ -439,6 +439,30 @@ class GaussianProcess:
             out[i] = (prime / self.x_std * self.inner.sigma2)[0]
         return out
 
+    # algorithm.rs:310-326 _compute_covariance: conditional covariance of the GP at the rows of x
+    def compute_covariance(self, x):
+        xn = self._xnorm(x)
+        corr = self._compute_correlation(xn)
+        rt, u = self._compute_rt_u(xn, corr)
+        k = corr_value(self.corr, pairwise_differences(xn, xn), self.theta, self.w_star)
+        k = k.reshape(xn.shape[0], xn.shape[0])
+        return self.inner.sigma2 * (k - rt.T.dot(rt) + u.T.dot(u))
+
+    # algorithm.rs:383-410 sample_chol / sample_eig / sample, :1153-1194 `sample`.  The reference draws
+    # the standard-normal matrix itself (ndarray-rand, unseeded); here it is an argument (n_eval x n_traj)
+    # so that the arithmetic can be compared.
+    def sample(self, x, z, method="eig"):
+        x = np.asarray(x, dtype=np.float64)
+        mean = self.predict(x)[:, None]
+        cov = self.compute_covariance(x)
+        if method == "chol":
+            c = sla.cholesky(cov, lower=True, check_finite=False)
+        else:
+            v, w = np.linalg.eigh(cov)
+            v = np.where(v < 1e-9, 0.0, np.sqrt(np.where(v < 1e-9, 1.0, v)))
+            c = w.dot(np.diag(v))
+        return mean + c.dot(np.asarray(z, dtype=np.float64))
+
     # algorithm.rs:267-279
     def predict_var(self, x, chunk=1024):
         return self.predict_valvar(x, chunk)[1]

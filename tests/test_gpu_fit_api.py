@@ -138,3 +138,32 @@ def test_gpx_save_load_reference_expert_layout(tmp_path, golden_dir):
     np.testing.assert_allclose(gpx3.predict(xq), gpx.predict(xq), rtol=1e-10, atol=1e-10)
     with pytest.raises(NotImplementedError):
         gpx.save(str(tmp_path / "gpdump.bin"))
+
+
+def test_model_sampling_api():
+    """GaussianProcess::sample / sample_chol / sample_eig (gp/src/algorithm.rs:383-395) and Gpx.sample
+    (python/src/gp_mix.rs:415-425); the reference's own test (`test_sampling`, algorithm.rs ~1680-1696) checks
+    the shape and the absence of NaNs."""
+    import egobox_b200 as eg
+    rng = np.random.default_rng(4)
+    xt = np.array([[0.0], [1.0], [2.0], [3.0], [4.0]])
+    yt = np.array([0.0, 1.0, 1.5, 0.9, 1.0])
+    gp = eg.Kriging.params().fit(xt, yt)
+    xs = np.linspace(0, 4, 35)[:, None]
+    for fn in (gp.sample, gp.sample_eig):
+        tr = fn(xs, 10, seed=1)
+        assert tr.shape == (35, 10) and np.all(np.isfinite(tr))
+    # trajectories interpolate the data: zero spread at the training points
+    z = rng.standard_normal((5, 4))
+    np.testing.assert_allclose(gp.sample_eig(xt, 4, z=z), np.repeat(yt[:, None], 4, axis=1), atol=1e-4)
+    cov = gp.covariance(xs)
+    v = gp.predict_var(xs)
+    np.testing.assert_allclose(np.clip(np.diag(cov), 0, None), v, rtol=1e-8, atol=1e-10 * gp.variance())
+    # empirical covariance of many trajectories approaches cov
+    tr = gp.sample_eig(xs, 20000, seed=3) - gp.predict(xs)[:, None]
+    emp = tr.dot(tr.T) / tr.shape[1]
+    assert np.abs(emp - cov).max() < 0.05 * np.abs(cov).max()
+    gpx = eg.Gpx.builder().fit(xt, yt)
+    s = gpx.sample(xs, 7)
+    assert s.shape == (35, 7) and np.all(np.isfinite(s))
+    gp.close()

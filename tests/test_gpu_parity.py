@@ -445,3 +445,82 @@ def test_bug_var_derivatives_through_gpu():
     assert g[0, 0] == pytest.approx((v[1] - v[2]) / (2 * e), abs=1e-5)
     assert g[0, 1] == pytest.approx((v[3] - v[4]) / (2 * e), abs=1e-5)
     ctx.close()
+
+
+# ------------------------------------------------- conditional covariance and sampling ------------
+@pytest.mark.parametrize("n,d,corr,mean,m", [
+    (60, 1, O.SQEXP, O.CONSTANT, 30),
+    (200, 2, O.MATERN52, O.CONSTANT, 150),
+    (300, 3, O.MATERN32, O.LINEAR, 129),
+    (150, 2, O.ABSEXP, O.QUADRATIC, 64),
+])
+def test_conditional_covariance(n, d, corr, mean, m):
+    """egx_gp_covariance against the oracle's `_compute_covariance` (algorithm.rs:310-326)."""
+    x, y = make_problem(n, d, seed=n + m)
+    theta = np.full(d, 1.5) if corr != O.SQEXP else np.full(d, 6.0)
+    ctx, _ = make_context(x, y, corr, mean)
+    gp = oracle_gp(x, y, corr, mean, theta)
+    st, _res = ctx.finalize(theta)
+    assert st == 0
+    xs = np.random.default_rng(m).random((m, d))
+    cov_ref = gp.compute_covariance(xs)
+    cov = ctx.covariance(xs)
+    s2 = gp.inner.sigma2
+    # the entries are O(sigma2) differences of O(sigma2) terms through L^-1: absolute bound relative to sigma2
+    np.testing.assert_allclose(cov, cov_ref, rtol=1e-7, atol=1e-8 * s2)
+    np.testing.assert_allclose(cov, cov.T, atol=1e-12 * s2)
+    # diagonal = predict_var wherever the clamp at zero is inactive
+    v = ctx.predict_var(xs)
+    dg = np.diag(cov)
+    np.testing.assert_allclose(np.where(dg > 0, dg, 0.0), v, rtol=1e-9, atol=1e-10 * s2)
+    ctx.close()
+
+
+def test_sample_cholesky_and_eigen():
+    """egx_gp_sample with caller-supplied normal draws against the oracle's restatement of
+    algorithm.rs:1153-1194 (mean + C z)."""
+    n, d, m, nt = 120, 2, 70, 5
+    x, y = make_problem(n, d, seed=3)
+    theta = np.array([2.0, 3.0])
+    ctx, _ = make_context(x, y, O.ABSEXP, O.CONSTANT)          # AbsExp: well-conditioned conditional covariance
+    gp = oracle_gp(x, y, O.ABSEXP, O.CONSTANT, theta)
+    assert ctx.finalize(theta)[0] == 0
+    xs = np.random.default_rng(11).random((m, d))
+    z = np.random.default_rng(12).standard_normal((m, nt))
+    cov_ref = gp.compute_covariance(xs)
+    scale = np.sqrt(np.abs(cov_ref).max())
+    ref = gp.sample(xs, z, "chol")
+    out = ctx.sample(xs, z, method=0)
+    assert out.shape == (m, nt)
+    np.testing.assert_allclose(out, ref, rtol=1e-7, atol=1e-7 * scale)
+    # eigenvalue variant: eigenvectors are defined up to sign / rotation in degenerate subspaces, so compare
+    # what the factor reproduces: with z = I the output minus the mean IS the factor C, and C C^T = cov
+    mean = ctx.predict(xs)[:, None]
+    c_eig = ctx.sample(xs, np.eye(m), method=1) - mean
+    np.testing.assert_allclose(c_eig.dot(c_eig.T), cov_ref, atol=2e-9 * m + 1e-8 * np.abs(cov_ref).max())
+    c_chol = ctx.sample(xs, np.eye(m), method=0) - mean
+    np.testing.assert_allclose(c_chol.dot(c_chol.T), cov_ref, atol=1e-8 * np.abs(cov_ref).max())
+    assert np.allclose(np.triu(c_chol, 1), 0.0)
+    # same draws through both factors give trajectories with the same law; here just finite and mean-centred
+    out_e = ctx.sample(xs, z, method=1)
+    assert np.all(np.isfinite(out_e))
+    ctx.close()
+
+
+def test_sample_errors_and_rank_deficient_covariance():
+    """Sampling AT training points: the conditional covariance is ~0 there, Cholesky fails with the
+    reference's failure class (it panics at algorithm.rs:1164) and the eigenvalue variant returns the mean."""
+    import egobox_b200 as eg
+    n, d = 50, 1
+    x, y = make_problem(n, d, seed=9)
+    ctx, _ = make_context(x, y, O.SQEXP, O.CONSTANT)
+    assert ctx.finalize(np.array([3.0]))[0] == 0
+    xs = x[:20]
+    z = np.random.default_rng(0).standard_normal((20, 3))
+    out = ctx.sample(xs, z, method=1)
+    np.testing.assert_allclose(out, np.repeat(ctx.predict(xs)[:, None], 3, axis=1), atol=1e-3 * np.abs(y).max())
+    with pytest.raises(eg.GpuError):
+        ctx.sample(xs, z, method=0)
+    with pytest.raises(eg.GpuError):
+        ctx.sample(xs, z, method=7)
+    ctx.close()

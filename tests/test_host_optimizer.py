@@ -85,3 +85,38 @@ def test_kriging5_optimum_with_reference_settings(golden_dir):
             best = (fv, z)
     assert -best[0] == pytest.approx(k["likelihood"], rel=1e-6)
     assert 10.0 ** best[1][0] == pytest.approx(k["theta"], rel=5e-3)
+
+
+# ------------------------------------------------------ host eigen-decomposition (sampler) --------
+@pytest.mark.parametrize("n", [1, 2, 7, 40, 150])
+def test_symmetric_eig_against_numpy(n):
+    """egx_symmetric_eig is the `cov_x.eigh()` of gp/src/algorithm.rs:1171-1173 (host in the reference too)."""
+    rng = np.random.default_rng(n)
+    b = rng.normal(size=(n, n))
+    a = b.dot(b.T) + np.diag(rng.random(n))
+    if n >= 7:                                       # rank-deficient block, as conditional covariances are
+        a[:, -3:] = a[:, :3]
+        a[-3:, :] = a[:3, :]
+        a = 0.5 * (a + a.T)
+    w, v = G.symmetric_eig(a)
+    scale = np.abs(a).max()
+    np.testing.assert_allclose(v.T.dot(v), np.eye(n), atol=1e-12)
+    np.testing.assert_allclose(v.dot(np.diag(w)).dot(v.T), a, atol=1e-12 * scale * n)
+    np.testing.assert_allclose(np.sort(w), np.linalg.eigvalsh(a), atol=1e-12 * scale * n)
+
+
+def test_oracle_covariance_consistent_with_predict_var():
+    """The oracle's conditional covariance (algorithm.rs:310-326) has predict_var on its diagonal and the
+    sampler reproduces it: C C^T = cov for both decompositions (eigenvalues below 1e-9 dropped)."""
+    rng = np.random.default_rng(5)
+    x = rng.random((40, 2))
+    y = np.sin(4 * x[:, 0]) + x[:, 1] ** 2
+    gp = O.fit(x, y, corr=O.MATERN52, mean=O.CONSTANT, theta_init=np.array([1.0, 1.0]), fixed=True)
+    xs = rng.random((15, 2))
+    cov = gp.compute_covariance(xs)
+    np.testing.assert_allclose(np.diag(cov), gp.predict_var(xs), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(cov, cov.T, atol=1e-12)
+    mean = gp.predict(xs)[:, None]
+    for method in ("chol", "eig"):
+        c = gp.sample(xs, np.eye(15), method) - mean
+        np.testing.assert_allclose(c.dot(c.T), cov, atol=2e-9 * 15 + 1e-9 * np.abs(cov).max())
