@@ -167,3 +167,40 @@ def test_model_sampling_api():
     s = gpx.sample(xs, 7)
     assert s.shape == (35, 7) and np.all(np.isfinite(s))
     gp.close()
+
+
+def test_expert_mixture_gpu():
+    """a19 / (f)-2: k experts fitted on the GPU, hard and smooth recombination against the formulas of
+    moe/src/algorithm.rs:411-423, 670-685, 879-910 applied to the experts' own predictions."""
+    import egobox_b200 as eg
+    rng = np.random.default_rng(3)
+    x = rng.random((120, 2))
+    y = np.where(x[:, 0] < 0.5, np.sin(6 * x[:, 0]) + x[:, 1], 3.0 + x[:, 0] * x[:, 1])
+    centers = np.array([[0.25, 0.5], [0.75, 0.5]])
+
+    def probas(xq):
+        d2 = ((xq[:, None, :] - centers[None, :, :]) ** 2).sum(axis=2)
+        w = np.exp(-d2 / 0.05)
+        return w / w.sum(axis=1, keepdims=True)
+    labels = np.argmax(probas(x), axis=1)
+    xs = rng.random((64, 2))
+    params = eg.GaussianProcess.params(eg.ConstantMean, eg.Matern52Corr).n_start(2)
+    for rec in (eg.Recombination.HARD, eg.Recombination.SMOOTH):
+        mix = eg.ExpertMixture.fit(x, y, labels, probas, params=params, recombination=rec)
+        yv, vv = mix.predict_valvar(xs)
+        e = [mix.experts[c].predict_valvar(xs) for c in range(2)]
+        p = probas(xs)
+        if rec == eg.Recombination.SMOOTH:
+            yy, vr = eg.recombine_smooth(np.array([a[0] for a in e]), np.array([a[1] for a in e]), p)
+        else:
+            cl = np.argmax(p, axis=1)
+            yy = np.array([e[cl[i]][0][i] for i in range(64)])
+            vr = np.array([e[cl[i]][1][i] for i in range(64)])
+        np.testing.assert_allclose(yv, yy, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(vv, vr, rtol=1e-7, atol=1e-9)
+        # each expert interpolates its own cluster
+        for c in range(2):
+            rows = labels == c
+            np.testing.assert_allclose(mix.experts[c].predict(x[rows]), y[rows], atol=1e-3 * np.abs(y).max())
+        assert mix.table.shape == (2, 4)
+        mix.close()

@@ -95,3 +95,111 @@ def test_shard_indices_cover():
         assert allidx == list(range(n))
         sizes = [len(P.shard_indices(n, r, w)) for r in range(w)]
         assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------------------------------------------------------- mixture of experts -----------
+class _OracleExpert:
+    """Stand-in for a GPU expert on the CPU ranks: the ORACLE's fixed-theta GP (checker code, test only)."""
+
+    def __init__(self, x, y):
+        from oracle import gp_oracle as O
+        self.gp = O.fit(x, y, corr=O.SQEXP, mean=O.CONSTANT, theta_init=np.full(x.shape[1], 2.0), fixed=True)
+
+    def predict_valvar(self, x):
+        return self.gp.predict_valvar(x)
+
+    def likelihood(self):
+        return float(self.gp.likelihood)
+
+    def variance(self):
+        return float(self.gp.inner.sigma2)
+
+    def theta(self):
+        return np.asarray(self.gp.theta)
+
+    def close(self):
+        pass
+
+
+def _mix_problem():
+    rng = np.random.default_rng(3)
+    x = rng.random((90, 2))
+    y = np.where(x[:, 0] < 0.5, np.sin(6 * x[:, 0]) + x[:, 1], 3.0 + x[:, 0] * x[:, 1])
+    centers = np.array([[0.2, 0.5], [0.55, 0.5], [0.85, 0.5]])
+
+    def probas(xq):
+        d2 = ((xq[:, None, :] - centers[None, :, :]) ** 2).sum(axis=2)
+        w = np.exp(-d2 / 0.02)
+        return w / w.sum(axis=1, keepdims=True)
+    labels = np.argmax(probas(x), axis=1)
+    xs = rng.random((57, 2))
+    return x, y, labels, probas, xs
+
+
+def _mix_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from egobox_b200 import mixture as M
+    x, y, labels, probas, xs = _mix_problem()
+    out = {}
+    for rec in (M.Recombination.HARD, M.Recombination.SMOOTH):
+        mix = M.ExpertMixture.fit(x, y, labels, probas, recombination=rec, expert_fit=_OracleExpert)
+        yv, vv = mix.predict_valvar(xs)
+        out[rec] = (yv.tolist(), vv.tolist(), sorted(mix.experts), mix.table.tolist())
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_recombination_formulas():
+    """moe/src/algorithm.rs:417-421 (sum_k p_k y_k), :675-683 (sum_k p_k^2 var_k), :880 (argmax cluster)."""
+    from egobox_b200 import mixture as M
+    rng = np.random.default_rng(0)
+    preds, var = rng.normal(size=(3, 11)), rng.random((3, 11))
+    p = rng.random((11, 3))
+    p /= p.sum(axis=1, keepdims=True)
+    y, v = M.recombine_smooth(preds, var, p)
+    for i in range(11):
+        assert y[i] == pytest.approx(sum(p[i, k] * preds[k, i] for k in range(3)), rel=1e-14)
+        assert v[i] == pytest.approx(sum(p[i, k] ** 2 * var[k, i] for k in range(3)), rel=1e-14)
+    np.testing.assert_array_equal(M.hard_clusters(p), np.argmax(p, axis=1))
+
+
+@pytest.mark.timeout(240)
+def test_expert_mixture_world2_matches_single_process():
+    """Experts sharded over 2 gloo ranks (cluster c on rank c % 2) give the single-process mixture."""
+    from egobox_b200 import mixture as M
+    x, y, labels, probas, xs = _mix_problem()
+    ref = {}
+    for rec in (M.Recombination.HARD, M.Recombination.SMOOTH):
+        mix = M.ExpertMixture.fit(x, y, labels, probas, recombination=rec, expert_fit=_OracleExpert)
+        assert mix.n_clusters == 3
+        ref[rec] = mix.predict_valvar(xs)
+        # against the reference formulas applied to the three experts directly
+        e = [mix.experts[c].predict_valvar(xs) for c in range(3)]
+        p = probas(xs)
+        if rec == M.Recombination.SMOOTH:
+            yy, vv = M.recombine_smooth(np.array([a[0] for a in e]), np.array([a[1] for a in e]), p)
+        else:
+            cl = np.argmax(p, axis=1)
+            yy = np.array([e[cl[i]][0][i] for i in range(len(xs))])
+            vv = np.array([e[cl[i]][1][i] for i in range(len(xs))])
+        np.testing.assert_allclose(ref[rec][0], yy, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(ref[rec][1], vv, rtol=1e-12, atol=1e-12)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mix_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = sorted((q.get(timeout=200) for _ in range(2)), key=lambda t: t[0])
+    for p_ in procs:
+        p_.join(30)
+    for rank, out in res:
+        for rec in (M.Recombination.HARD, M.Recombination.SMOOTH):
+            yv, vv, mine, table = out[rec]
+            assert mine == [c for c in range(3) if c % 2 == rank]
+            np.testing.assert_allclose(np.array(yv), ref[rec][0], rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(np.array(vv), ref[rec][1], rtol=1e-12, atol=1e-12)
+            assert np.array(table).shape == (3, 4)
