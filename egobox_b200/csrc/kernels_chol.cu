@@ -338,21 +338,23 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
     const int wm = warp / WARPS_N, wn = warp % WARPS_N;
     const int gid = lane >> 2, tig = lane & 3;
 
+    // per-thread copy slots: chunk `ch` (16 bytes) of rows row0, row0 + 256/CH, ... ; the global pointers are formed
+    // once, a k-block step only adds kb * BK to them
+    constexpr int RSTEP = 256 / CH;                 // rows covered by one pass of the 256 threads
+    const int row0 = tid / CH, ch0 = tid % CH;
+    const double* a_src = Ag + static_cast<long>(row0) * g.lda + ch0 * 2;
+    const double* b_src = Bg + static_cast<long>(row0) * g.ldb + ch0 * 2;
+    const long a_step = static_cast<long>(RSTEP) * g.lda, b_step = static_cast<long>(RSTEP) * g.ldb;
+    const int s_off = row0 * LDS + ch0 * 2;
     auto load_stage = [&](int stage, int kb) {
-        double* as = As + stage * A_ELEMS;
-        double* bs = Bs + stage * B_ELEMS;
+        double* as = As + stage * A_ELEMS + s_off;
+        double* bs = Bs + stage * B_ELEMS + s_off;
+        const double* ap = a_src + kb * BK;
+        const double* bp = b_src + kb * BK;
 #pragma unroll
-        for (int i = 0; i < EGX_NB * CH / 256; ++i) {
-            const int idx = tid + i * 256;
-            const int row = idx / CH, ch = idx % CH;
-            cp_async16(as + row * LDS + ch * 2, Ag + static_cast<long>(row) * g.lda + kb * BK + ch * 2);
-        }
+        for (int i = 0; i < EGX_NB / RSTEP; ++i) cp_async16(as + i * RSTEP * LDS, ap + i * a_step);
 #pragma unroll
-        for (int i = 0; i < BN * CH / 256; ++i) {
-            const int idx = tid + i * 256;
-            const int row = idx / CH, ch = idx % CH;
-            cp_async16(bs + row * LDS + ch * 2, Bg + static_cast<long>(row) * g.ldb + kb * BK + ch * 2);
-        }
+        for (int i = 0; i < BN / RSTEP; ++i) cp_async16(bs + i * RSTEP * LDS, bp + i * b_step);
     };
 
     const int KB = g.K / BK;
@@ -393,8 +395,6 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
     for (int kb = 0; kb < KB; ++kb) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (kb + STAGES - 1 < KB) load_stage((kb + STAGES - 1) % STAGES, kb + STAGES - 1);
-        cp_async_commit();
         const double* as = As + (kb % STAGES) * A_ELEMS + (wm * (MI * 8) + gid) * LDS + tig;
         const double* bs = Bs + (kb % STAGES) * B_ELEMS + (wn * (NI * 8) + gid) * LDS + tig;
 #pragma unroll
@@ -408,6 +408,13 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
             for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            if (kk == 0) {
+                // the refill of the stage read in the previous iteration is issued AFTER the first 16 MMAs of this
+                // one are queued, so that the copy issue (address arithmetic + 6 LDGSTS) overlaps tensor work
+                // instead of standing between the barrier and the first MMA
+                if (kb + STAGES - 1 < KB) load_stage((kb + STAGES - 1) % STAGES, kb + STAGES - 1);
+                cp_async_commit();
+            }
         }
     }
     cp_async_wait<0>();
