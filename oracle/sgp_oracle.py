@@ -26,8 +26,14 @@ SGP_THETA_BOUNDS = (1e-2, 1e2)                               # sparse_parameters
 NOISE_DEFAULT = (1e-2, (100.0 * np.finfo(np.float64).eps, 1e10))   # sparse_parameters.rs:25-32
 
 
+USE_FAST_KERNEL = False      # full-size tests: build K with the C/OpenMP restatement (no (M N) x d temporaries)
+
+
 def compute_k(corr, a, b, w_star, theta, sigma2):
     """sparse_algorithm.rs:676-691."""
+    if USE_FAST_KERNEL:
+        from oracle import fast
+        return fast.cross_corr(corr, a, b, theta, w_star) * sigma2
     dx = O.pairwise_differences(a, b)
     r = O.corr_value(corr, dx, theta, w_star)
     return r.reshape(a.shape[0], b.shape[0]) * sigma2
