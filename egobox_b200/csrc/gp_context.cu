@@ -698,7 +698,10 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
     // the serial diagonal-block / panel chain of one factorisation overlaps the bulk updates of the others.
     // how many: the smaller the matrix, the more an evaluation is a latency chain (block columns x ~80 us)
     // rather than throughput work, and the cheaper a replica is (npad^2 x 8 bytes)
-    int W = (c->npad <= 2048) ? 12 : (c->npad <= 4096 ? 6 : 4);
+    // measured (tools/batch_sweep.py): n = 8192 plateaus at 4 (6.68 ms per evaluation; 7.23 at 2, 6.69 at 8),
+    // n = 4096 keeps improving to 8-12 (1.25 ms at 4, 1.08 at 6, 1.03 at 8 and 12); 12 also takes the 11
+    // chains of a fit in one wave
+    int W = (c->npad <= 4096) ? 12 : 4;
     if (const char* e = getenv("EGX_BATCH_STREAMS")) W = std::max(1, atoi(e));
     W = std::min(W, B);
     while (static_cast<int>(c->replicas.size()) < W - 1) {

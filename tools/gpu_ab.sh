@@ -1,7 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 240 2>&1 | tail -40 > gpurun_out/pytest_gpu.log; tail -8 gpurun_out/pytest_gpu.log
-echo "== probe 8192"; timeout 200 python tools/gpu_probe.py 8192 2>&1 | grep -E "batch12|noprof|stage_ms" | cut -c1-420
-echo "== sgp probe"; timeout 300 python tools/sgp_probe.py 100000 6 1024 2>&1 | tee gpurun_out/sgp_probe.log | tail -3 | cut -c1-500
-echo "== midsize"; timeout 300 python tools/round_probe.py 500 1000 2>&1 | cut -c1-400
+for w in 2 3 4 5 6 8; do EGX_BATCH_STREAMS=$w timeout 200 python tools/batch_sweep.py 8192 48 2>&1 | tail -1; done
+for w in 4 6 8 12; do EGX_BATCH_STREAMS=$w timeout 200 python tools/batch_sweep.py 4096 96 2>&1 | tail -1; done
