@@ -312,7 +312,42 @@ __device__ __forceinline__ void gemm_tile_decode(const GemmArgs& g, int t, int& 
 
 // ADD = false: C -= A B^T (the negation folds into the DMMA operand, SASS `DMMA R, -R, R, R`); ADD = true: C += A B^T
 // BK x STAGES: 16 x 3 (default) or 32 x 2 (half the barriers per tile, same shared-memory footprint class).
-template <int BN, bool ADD, int BK, int STAGES>
+// mbarrier helpers of the MB variant (no CTA-wide barrier in the main loop)
+__device__ __forceinline__ void mb_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar))),
+                 "r"(count));
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MB_DONE_%=;\n"
+        "bra MB_WAIT_%=;\n"
+        "MB_DONE_%=:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar)))
+                 : "memory");
+}
+// the calling thread's earlier cp.async copies arrive on the barrier when they have landed
+__device__ __forceinline__ void mb_cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(bar)))
+                 : "memory");
+}
+
+// MB = true: the per-k-block __syncthreads is replaced by two mbarrier arrays -- full[s] (256 arrivals, one per
+// thread, triggered by the completion of its cp.async copies into stage s) and empty[s] (8 arrivals, one per warp,
+// after its last fragment load from stage s).  A warp starts a k-block as soon as the data has landed, whatever the
+// progress of the other warps; only the refill of a stage waits for every warp to have left it, and that wait sits
+// behind 16 queued MMAs.
+template <int BN, bool ADD, int BK, int STAGES, bool MB = false>
 __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(const GemmArgs g) {
     constexpr int WARPS_N = (BN == 128) ? 4 : 2;
     constexpr int WARPS_M = 8 / WARPS_N;
@@ -324,6 +359,18 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
     extern __shared__ __align__(16) double gsm[];
     double* As = gsm;                               // [STAGES][128][LDS]
     double* Bs = gsm + STAGES * A_ELEMS;            // [STAGES][BN][LDS]
+    __shared__ uint64_t mb_full[STAGES], mb_empty[STAGES];
+    if constexpr (MB) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) {
+                mb_init(&mb_full[s], 256);
+                mb_init(&mb_empty[s], 8);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
 
     int tr, tc;
     gemm_tile_decode<BN>(g, blockIdx.x, tr, tc);
@@ -360,7 +407,10 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
     const int KB = g.K / BK;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KB) load_stage(s, s);
+        if (s < KB) {
+            load_stage(s, s);
+            if constexpr (MB) mb_cp_async_arrive(&mb_full[s]);
+        }
         cp_async_commit();
     }
 
@@ -393,8 +443,12 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
 
 #pragma unroll 1
     for (int kb = 0; kb < KB; ++kb) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
+        if constexpr (MB) {
+            mb_wait(&mb_full[kb % STAGES], (kb / STAGES) & 1);
+        } else {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+        }
         const double* as = As + (kb % STAGES) * A_ELEMS + (wm * (MI * 8) + gid) * LDS + tig;
         const double* bs = Bs + (kb % STAGES) * B_ELEMS + (wn * (NI * 8) + gid) * LDS + tig;
 #pragma unroll
@@ -412,9 +466,21 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
                 // the refill of the stage read in the previous iteration is issued AFTER the first 16 MMAs of this
                 // one are queued, so that the copy issue (address arithmetic + 6 LDGSTS) overlaps tensor work
                 // instead of standing between the barrier and the first MMA
-                if (kb + STAGES - 1 < KB) load_stage((kb + STAGES - 1) % STAGES, kb + STAGES - 1);
+                const int r = kb + STAGES - 1;
+                if (r < KB) {
+                    if constexpr (MB) {
+                        // stage r % STAGES was last read in iteration kb - 1: wait until all 8 warps have left it
+                        if (r >= STAGES) mb_wait(&mb_empty[r % STAGES], ((r / STAGES) - 1) & 1);
+                    }
+                    load_stage(r % STAGES, r);
+                    if constexpr (MB) mb_cp_async_arrive(&mb_full[r % STAGES]);
+                }
                 cp_async_commit();
             }
+        }
+        if constexpr (MB) {
+            __syncwarp();
+            if (lane == 0) mb_arrive(&mb_empty[kb % STAGES]);
         }
     }
     cp_async_wait<0>();
@@ -488,7 +554,7 @@ static int gemm_bk() {
     return bk;
 }
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, bool MB = false>
 static void gemm_launch_variant(const GemmArgs& g, dim3 grid, cudaStream_t s) {
     constexpr int smem = STAGES * (EGX_NB + BN) * (BK + 4) * static_cast<int>(sizeof(double));
     static bool configured_dev[64] = {false};
@@ -496,12 +562,12 @@ static void gemm_launch_variant(const GemmArgs& g, dim3 grid, cudaStream_t s) {
     cudaGetDevice(&dev_);
     bool& configured = configured_dev[dev_ & 63];   // the attribute is per device (one process may drive several)
     if (!configured) {
-        cudaFuncSetAttribute(gemm_nt_sub_kernel<BN, false, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(gemm_nt_sub_kernel<BN, true, BK, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(gemm_nt_sub_kernel<BN, false, BK, STAGES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(gemm_nt_sub_kernel<BN, true, BK, STAGES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
-    if (g.add) gemm_nt_sub_kernel<BN, true, BK, STAGES><<<grid, 256, smem, s>>>(g);
-    else gemm_nt_sub_kernel<BN, false, BK, STAGES><<<grid, 256, smem, s>>>(g);
+    if (g.add) gemm_nt_sub_kernel<BN, true, BK, STAGES, MB><<<grid, 256, smem, s>>>(g);
+    else gemm_nt_sub_kernel<BN, false, BK, STAGES, MB><<<grid, 256, smem, s>>>(g);
 }
 
 void launch_gemm_nt_sub(const GemmArgs& g_in, cudaStream_t s) {
@@ -521,7 +587,10 @@ void launch_gemm_nt_sub(const GemmArgs& g_in, cudaStream_t s) {
         if (bk32) gemm_launch_variant<128, 32, 2>(g, grid, s);
         else gemm_launch_variant<128, 16, 3>(g, grid, s);
     } else {
+        // measured at n = 8192, 48 evaluations in a batch: 6.68 (bar.sync) vs 6.56 ms (mbarrier pipeline) per evaluation
+        static const int use_mb = gemm_env("EGX_GEMM_MB", 1);
         if (bk32) gemm_launch_variant<64, 32, 2>(g, grid, s);
+        else if (use_mb) gemm_launch_variant<64, 16, 3, true>(g, grid, s);
         else gemm_launch_variant<64, 16, 3>(g, grid, s);
     }
 }
