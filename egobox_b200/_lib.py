@@ -44,6 +44,7 @@ SIGNATURES = {
     "egx_gp_predict_gradients": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_gp_predict_var_gradients": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_symmetric_eig": (C.c_int, [C.c_int, _dp, _dp]),
+    "egx_pls_rotations": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
     "egx_release_cached_memory": (None, []),
     "egx_gp_covariance": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_gp_sample": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp]),

@@ -565,7 +565,7 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
         egx_set_error("egx_gp_fit: invalid argument");
         return EGX_INVALID_VALUE;
     }
-    const bool kpls = prm->w_star != nullptr;
+    const bool kpls = prm->w_star != nullptr || prm->kpls_dim > 0;
     if (kpls && (prm->kpls_dim < 1 || prm->kpls_dim > d)) {
         // algorithm.rs:798-807
         egx_set_error("Dimension reduction %d should be smaller than actual training input dimensions %d",
@@ -598,8 +598,13 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
     normalize_cols(y, n, 1, yn, ym, ys);
     m->y_mean = ym[0];
     m->y_std = ys[0];
-    if (kpls) m->w_star.assign(prm->w_star, prm->w_star + static_cast<size_t>(d) * h);
-    else {
+    if (kpls && prm->w_star) m->w_star.assign(prm->w_star, prm->w_star + static_cast<size_t>(d) * h);
+    else if (kpls) {
+        // PLS rotations of the RAW data (algorithm.rs:843-855)
+        m->w_star.assign(static_cast<size_t>(d) * h, 0.0);
+        const int stp = egx_pls_rotations(x, n, d, y, h, m->w_star.data());
+        if (stp != EGX_OK) return stp;
+    } else {
         m->w_star.assign(static_cast<size_t>(d) * d, 0.0);
         for (int j = 0; j < d; ++j) m->w_star[static_cast<size_t>(j) * d + j] = 1.0;
     }
@@ -839,7 +844,7 @@ extern "C" int egx_sgp_fit(const egx_sgp_params* prm, const double* x, int n, in
         egx_set_error("egx_sgp_fit: invalid argument");
         return EGX_INVALID_VALUE;
     }
-    const bool kpls = prm->w_star != nullptr;
+    const bool kpls = prm->w_star != nullptr || prm->kpls_dim > 0;
     if (kpls && (prm->kpls_dim < 1 || prm->kpls_dim > d)) {
         egx_set_error("Dimension reduction %d should be smaller than actual training input dimensions %d",
                       prm->kpls_dim, d);
@@ -851,8 +856,13 @@ extern "C" int egx_sgp_fit(const egx_sgp_params* prm, const double* x, int n, in
     m->d = d;
     m->h = h;
     std::vector<double> w;
-    if (kpls) w.assign(prm->w_star, prm->w_star + static_cast<size_t>(d) * h);
-    else {
+    if (kpls && prm->w_star) w.assign(prm->w_star, prm->w_star + static_cast<size_t>(d) * h);
+    else if (kpls) {
+        // sparse_algorithm.rs:442-455
+        w.assign(static_cast<size_t>(d) * h, 0.0);
+        const int stp = egx_pls_rotations(x, n, d, y, h, w.data());
+        if (stp != EGX_OK) return stp;
+    } else {
         w.assign(static_cast<size_t>(d) * d, 0.0);
         for (int j = 0; j < d; ++j) w[static_cast<size_t>(j) * d + j] = 1.0;
     }

@@ -115,8 +115,9 @@ class GpParams:
         return self
 
     def kpls_dim(self, kpls_dim, w_star=None):
-        """KPLS reduction.  The PLS rotations come from linfa-pls in the reference
-        (algorithm.rs:843-855, third-party, not part of this path): pass them as ``w_star``."""
+        """KPLS reduction (algorithm.rs:798-813, 843-855).  The PLS rotations are computed by the
+        fit driver (``egx_pls_rotations``, the NIPALS regression of linfa-pls) unless ``w_star``
+        (d x kpls_dim) is given."""
         self._kpls_dim, self._w_star = kpls_dim, w_star
         return self
 
@@ -166,10 +167,6 @@ class GpParams:
                 raise InvalidValueError(
                     "Dimension reduction %d should be smaller than actual training input dimensions %d"
                     % (self._kpls_dim, d))
-            if self._w_star is None:
-                raise NotImplementedError(
-                    "KPLS needs the PLS rotations (linfa-pls, third-party in the reference): "
-                    "pass them with kpls_dim(k, w_star=...)")
         prm = GpParamsStruct()
         lib.egx_gp_params_default(C.byref(prm))
         prm.corr, prm.mean = int(self._corr), int(self._mean)
@@ -195,6 +192,8 @@ class GpParams:
             prm.w_star = w.ctypes.data_as(C.POINTER(C.c_double))
             prm.kpls_dim = w.shape[1]
             keep.append(w)
+        elif self._kpls_dim is not None:
+            prm.kpls_dim = int(self._kpls_dim)
         prm.device, prm.seed, prm.cobyla_ftol_rel = int(self._device), int(self._seed), float(self._ftol_rel)
         h = C.c_void_p()
         st = lib.egx_gp_fit(C.byref(prm), x.ctypes.data_as(C.POINTER(C.c_double)), n, d,

@@ -232,11 +232,12 @@ class SgpParams:
             if self._kpls_dim > d:
                 raise InvalidValueError("Dimension reduction %d should be smaller than actual training input "
                                         "dimensions %d" % (self._kpls_dim, d))
-            if self._w_star is None:
-                raise NotImplementedError("KPLS needs the PLS rotations (linfa-pls): pass kpls_dim(k, w_star=...)")
-            w = _f64(self._w_star)
-            prm.w_star, prm.kpls_dim = w.ctypes.data_as(_dp), w.shape[1]
-            keep.append(w)
+            if self._w_star is None:      # rotations computed by the fit driver (sparse_algorithm.rs:442-455)
+                prm.kpls_dim = int(self._kpls_dim)
+            else:
+                w = _f64(self._w_star)
+                prm.w_star, prm.kpls_dim = w.ctypes.data_as(_dp), w.shape[1]
+                keep.append(w)
         prm.device = int(self._device)
         prm.seed = int(self._seed if self._seed is not None else np.random.SeedSequence().entropy % (2 ** 63))
         prm.cobyla_ftol_rel = float(self._ftol_rel)

@@ -221,8 +221,9 @@ typedef struct egx_gp_params {
     int n_start;                 /* multistart count (n_start + 1 chains), algorithm.rs:33 */
     int max_eval;                /* per-chain budget = clamp(10*dim, 25, max_eval), algorithm.rs:936-937 */
     double nugget;
-    const double* w_star;        /* optional d x kpls_dim PLS rotations (algorithm.rs:843-855); NULL = identity */
-    int kpls_dim;                /* columns of w_star; ignored when w_star is NULL */
+    const double* w_star;        /* optional d x kpls_dim PLS rotations supplied by the caller; NULL = computed */
+    int kpls_dim;                /* KPLS components (algorithm.rs:798-813, 843-855): 0 = none (identity w_star);
+                                    > 0 with w_star == NULL: rotations by egx_pls_rotations (linfa-pls NIPALS) */
     int device;                  /* CUDA device ordinal */
     unsigned long long seed;     /* multistart LHS seed (reference: 42, optimization.rs:60-63) */
     double cobyla_rhobeg;        /* 0.5   optimization.rs:19 */
@@ -273,6 +274,10 @@ int egx_bound_cobyla_minimize(egx_objective_fn f, void* user, int n, const doubl
                               double* x_opt, double* f_opt, int* n_evals);
 int egx_prepare_multistart(int n_start, const double* theta0, const double* bounds, int dim,
                            unsigned long long seed, double* starts_out);
+/* egx_pls_rotations: `PlsRegression::params(k).fit(&ds)?.rotations().0` of gp/src/algorithm.rs:843-855 and
+ * gp/src/sparse_algorithm.rs:442-455 (linfa-pls 0.8.0 = scikit-learn's NIPALS PLSRegression, scale = true):
+ * x n x d raw, y n raw -> w_star d x k.  A numerically constant y residual yields zeros, like the reference. */
+int egx_pls_rotations(const double* x, int n, int d, const double* y, int k, double* w_star);
 /* egx_symmetric_eig: eigen-decomposition of a symmetric n x n matrix (row-major, overwritten by the
  * eigenvectors as COLUMNS; w = eigenvalues, unsorted) -- the host half of the eigenvalue sampler,
  * `cov_x.eigh()` gp/src/algorithm.rs:1171-1173.  Returns EGX_OK or EGX_INVALID_VALUE (no convergence). */
@@ -330,7 +335,7 @@ typedef struct egx_sgp_params {
     int n_inducings;             /* Inducings::Randomized(n) when z == NULL (default 10) */
     int n_start, max_eval;
     double nugget;
-    const double* w_star;
+    const double* w_star;        /* as in egx_gp_params: NULL + kpls_dim > 0 = PLS rotations computed here */
     int kpls_dim;
     int device;
     unsigned long long seed;

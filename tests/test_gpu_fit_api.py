@@ -204,3 +204,54 @@ def test_expert_mixture_gpu():
             np.testing.assert_allclose(mix.experts[c].predict(x[rows]), y[rows], atol=1e-3 * np.abs(y).max())
         assert mix.table.shape == (2, 4)
         mix.close()
+
+
+def _griewank(x):
+    d = x.shape[1]
+    return (x ** 2).sum(axis=1) / 4000.0 - np.prod(np.cos(x / np.sqrt(np.arange(1, d + 1))), axis=1) + 1.0
+
+
+def test_kpls_fit_computes_pls_rotations():
+    """kpls_dim without explicit rotations: the fit driver runs the PLS regression itself
+    (algorithm.rs:843-855); the fitted state equals the oracle's with the oracle's own PLS weights."""
+    import egobox_b200 as egx
+    from oracle import pls_oracle as P
+    rng = np.random.default_rng(11)
+    x = -600.0 + 1200.0 * rng.random((100, 5))
+    y = _griewank(x)
+    w = P.kpls_w_star(x, y, 3)
+    gp = (egx.GaussianProcess.params(egx.ConstantMean, egx.SquaredExponentialCorr)
+          .theta_tuning(egx.ThetaTuning.Fixed([0.4, 0.2, 0.7])).kpls_dim(3).fit(x, y))
+    np.testing.assert_allclose(gp.normalization()["w_star"], w, rtol=1e-10, atol=1e-12)
+    ogp = O.fit(x, y, corr=O.SQEXP, mean=O.CONSTANT, theta_init=[0.4, 0.2, 0.7], fixed=True, w_star=w)
+    assert gp.likelihood() == pytest.approx(ogp.likelihood, rel=1e-9)
+    xt = -600.0 + 1200.0 * rng.random((50, 5))
+    yo, vo = ogp.predict_valvar(xt)
+    np.testing.assert_allclose(gp.predict(xt), yo, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(gp.predict_var(xt), vo, rtol=1e-6, atol=1e-9 * ogp.inner.sigma2)
+
+
+def test_kpls_griewank_accuracy():
+    """gp/src/algorithm.rs:1326-1374 (test_kpls_griewank): nt = 100, dim = 5, kpls_dim 3, nrmse < 1e-2."""
+    import egobox_b200 as egx
+    rng = np.random.default_rng(42)
+    x = -600.0 + 1200.0 * rng.random((100, 5))
+    gp = egx.GaussianProcess.params(egx.ConstantMean, egx.SquaredExponentialCorr).kpls_dim(3).fit(x, _griewank(x))
+    assert gp.theta().shape == (3,)
+    xt = -600.0 + 1200.0 * np.random.default_rng(0).random((100, 5))
+    yt = _griewank(xt)
+    nrmse = np.linalg.norm(yt - gp.predict(xt)) / np.linalg.norm(yt)
+    assert nrmse < 1e-2
+
+
+def test_sparse_kpls_fit_runs():
+    """sparse_algorithm.rs:442-455: same PLS step in the sparse fit driver."""
+    import egobox_b200 as egx
+    rng = np.random.default_rng(5)
+    x = rng.random((400, 4))
+    y = np.sin(3 * x[:, 0]) + 0.3 * x[:, 1] + 0.01 * rng.standard_normal(400)
+    sgp = (egx.SparseGaussianProcess.params(egx.SquaredExponentialCorr, egx.Inducings.Randomized(30))
+           .kpls_dim(2).seed(7).fit(x, y))
+    assert np.asarray(sgp.theta()).shape == (2,)
+    err = np.linalg.norm(sgp.predict(x) - y) / np.linalg.norm(y)
+    assert err < 0.2
