@@ -43,6 +43,16 @@ SIGNATURES = {
     "egx_gp_predict_valvar_dev": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "egx_gp_predict_gradients": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_gp_predict_var_gradients": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_gp_predict_gradients_dev": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "egx_gp_predict_var_gradients_dev": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "egx_moe_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double]),
+    "egx_moe_destroy": (None, [_vp]),
+    "egx_moe_set_heaviside_factor": (C.c_int, [_vp, C.c_double]),
+    "egx_moe_set_expert": (C.c_int, [_vp, C.c_int, _vp]),
+    "egx_moe_parameters": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "egx_moe_predict_probas": (C.c_int, [_vp, _dp, C.c_int, _dp, _ip]),
+    "egx_moe_predict_probas_derivatives": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_moe_predict": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]),
     "egx_symmetric_eig": (C.c_int, [C.c_int, _dp, _dp]),
     "egx_pls_rotations": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
     "egx_release_cached_memory": (None, []),

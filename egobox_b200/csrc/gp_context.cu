@@ -822,9 +822,33 @@ extern "C" int egx_gp_predict_valvar(egx_gp_ctx* c, const double* x, int m, doub
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_impl(c, x, m, y, var, false);
 }
+namespace {
+int predict_gradients_impl(egx_gp_ctx* c, const double* x, int m, double* grad, bool device_ptrs);
+int predict_var_gradients_impl(egx_gp_ctx* c, const double* x, int m, double* grad, bool device_ptrs);
+}  // namespace
 extern "C" int egx_gp_predict_gradients(egx_gp_ctx* c, const double* x, int m, double* grad) {
     if (!c || !x || !grad || m < 0) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
+    return predict_gradients_impl(c, x, m, grad, false);
+}
+extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int m, double* grad) {
+    if (!c || !x || !grad || m < 0) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return predict_var_gradients_impl(c, x, m, grad, false);
+}
+/* device-pointer variants: x_dev (m x d) and grad_dev (m x d) live on the context's device */
+extern "C" int egx_gp_predict_gradients_dev(egx_gp_ctx* c, const double* x_dev, int m, double* grad_dev) {
+    if (!c || !x_dev || !grad_dev || m < 0) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return predict_gradients_impl(c, x_dev, m, grad_dev, true);
+}
+extern "C" int egx_gp_predict_var_gradients_dev(egx_gp_ctx* c, const double* x_dev, int m, double* grad_dev) {
+    if (!c || !x_dev || !grad_dev || m < 0) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return predict_var_gradients_impl(c, x_dev, m, grad_dev, true);
+}
+namespace {
+int predict_gradients_impl(egx_gp_ctx* c, const double* x, int m, double* grad, bool device_ptrs) {
     if (!c->trained) {
         egx_set_error("predict_gradients called before a successful egx_gp_finalize");
         return EGX_INVALID_VALUE;
@@ -837,20 +861,29 @@ extern "C" int egx_gp_predict_gradients(egx_gp_ctx* c, const double* x, int m, d
     EGX_CUDA_TRY(cudaSetDevice(c->device));
     const int mb = std::min(round_up(m, EGX_NB), PREDICT_CHUNK);
     double *xd = nullptr, *gd = nullptr;
-    EGX_CUDA_TRY(egx_dev_malloc(&xd, static_cast<size_t>(mb) * c->d * sizeof(double)));
-    EGX_CUDA_TRY(egx_dev_malloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    if (!device_ptrs) {
+        EGX_CUDA_TRY(egx_dev_malloc(&xd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    }
     int st = EGX_OK;
     for (int i0 = 0; i0 < m && st == EGX_OK; i0 += mb) {
         const int mc = std::min(mb, m - i0);
-        cudaMemcpyAsync(xd, x + static_cast<long>(i0) * c->d, static_cast<size_t>(mc) * c->d * sizeof(double),
-                        cudaMemcpyHostToDevice, c->stream);
+        const double* xin = x + static_cast<long>(i0) * c->d;
+        double* gout = grad + static_cast<long>(i0) * c->d;
+        if (!device_ptrs) {
+            cudaMemcpyAsync(xd, xin, static_cast<size_t>(mc) * c->d * sizeof(double), cudaMemcpyHostToDevice,
+                            c->stream);
+            xin = xd;
+            gout = gd;
+        }
         {
             StageScope sc(c->env.prof, EGX_STAGE_CROSS_CORR, 1, c->stream);
-            launch_predict_grad(c->corr, xd, mc, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d, c->terms, c->nterms,
-                                c->rho, c->beta, c->basis_i, c->basis_j, c->p, c->y_std, gd, c->stream);
+            launch_predict_grad(c->corr, xin, mc, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d, c->terms, c->nterms,
+                                c->rho, c->beta, c->basis_i, c->basis_j, c->p, c->y_std, gout, c->stream);
         }
-        cudaMemcpyAsync(grad + static_cast<long>(i0) * c->d, gd, static_cast<size_t>(mc) * c->d * sizeof(double),
-                        cudaMemcpyDeviceToHost, c->stream);
+        if (!device_ptrs)
+            cudaMemcpyAsync(grad + static_cast<long>(i0) * c->d, gd, static_cast<size_t>(mc) * c->d * sizeof(double),
+                            cudaMemcpyDeviceToHost, c->stream);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = EGX_CUDA_ERROR;
     }
     egx_dev_free(xd);
@@ -862,9 +895,7 @@ extern "C" int egx_gp_predict_gradients(egx_gp_ctx* c, const double* x, int m, d
     resolve_profile(c);
     return EGX_OK;
 }
-extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int m, double* grad) {
-    if (!c || !x || !grad || m < 0) return EGX_INVALID_VALUE;
-    std::lock_guard<std::mutex> lk(c->mu);
+int predict_var_gradients_impl(egx_gp_ctx* c, const double* x, int m, double* grad, bool device_ptrs) {
     if (!c->trained) {
         egx_set_error("predict_var_gradients called before a successful egx_gp_finalize");
         return EGX_INVALID_VALUE;
@@ -892,15 +923,21 @@ extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int 
     int st = ensure_predict_buffers(c, mb);
     if (st != EGX_OK) return st;
     double* gd = nullptr;
-    EGX_CUDA_TRY(egx_dev_malloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
+    if (!device_ptrs) EGX_CUDA_TRY(egx_dev_malloc(&gd, static_cast<size_t>(mb) * c->d * sizeof(double)));
     for (int i0 = 0; i0 < m && st == EGX_OK; i0 += mb) {
         const int mc = std::min(mb, m - i0);
         const int mpad = round_up(mc, EGX_NB);
-        cudaMemcpyAsync(c->xchunk, x + static_cast<long>(i0) * c->d, static_cast<size_t>(mc) * c->d * sizeof(double),
-                        cudaMemcpyHostToDevice, c->stream);
+        const double* xin = x + static_cast<long>(i0) * c->d;
+        double* gout = grad + static_cast<long>(i0) * c->d;
+        if (!device_ptrs) {
+            cudaMemcpyAsync(c->xchunk, xin, static_cast<size_t>(mc) * c->d * sizeof(double), cudaMemcpyHostToDevice,
+                            c->stream);
+            xin = c->xchunk;
+            gout = gd;
+        }
         {
             StageScope sc(c->env.prof, EGX_STAGE_CROSS_CORR, 1, c->stream);
-            launch_cross_corr(c->corr, c->xchunk, mc, mpad, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d, c->terms,
+            launch_cross_corr(c->corr, xin, mc, mpad, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d, c->terms,
                               c->nterms, nullptr, nullptr, c->basis_i, c->basis_j, 0, 0.0, 1.0, c->Y, c->npad, nullptr,
                               c->stream);
         }
@@ -931,12 +968,13 @@ extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int 
         }
         {
             StageScope sc(c->env.prof, EGX_STAGE_VAR_FINISH, 1, c->stream);
-            launch_var_grad(c->corr, c->Y, c->npad, c->xchunk, mc, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d,
+            launch_var_grad(c->corr, c->Y, c->npad, xin, mc, c->x_mean, c->x_std, c->X, c->n, c->npad, c->d,
                             c->terms, c->nterms, c->KF, c->npad, c->G, c->p, c->basis_i, c->basis_j, c->sigma2_scaled,
-                            gd, c->stream);
+                            gout, c->stream);
         }
-        cudaMemcpyAsync(grad + static_cast<long>(i0) * c->d, gd, static_cast<size_t>(mc) * c->d * sizeof(double),
-                        cudaMemcpyDeviceToHost, c->stream);
+        if (!device_ptrs)
+            cudaMemcpyAsync(grad + static_cast<long>(i0) * c->d, gd, static_cast<size_t>(mc) * c->d * sizeof(double),
+                            cudaMemcpyDeviceToHost, c->stream);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = EGX_CUDA_ERROR;
     }
     egx_dev_free(gd);
@@ -947,6 +985,7 @@ extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int 
     resolve_profile(c);
     return EGX_OK;
 }
+}  // namespace
 // ---------------------------------------------------------------------------------------------
 // Conditional covariance and trajectory sampling (gp/src/algorithm.rs:310-326, 383-410, 1153-1194).
 // ---------------------------------------------------------------------------------------------

@@ -152,6 +152,9 @@ int egx_gp_sample(egx_gp_ctx* ctx, const double* x, int m, const double* z, int 
  * pointers).  Used to time the kernels without the PCIe copies. */
 int egx_gp_predict_valvar_dev(egx_gp_ctx* ctx, const double* x_dev, int m,
                               double* y_dev, double* var_dev);
+/* Device-pointer variants of the prediction gradients (x_dev m x d, grad_dev m x d), used by the mixture. */
+int egx_gp_predict_gradients_dev(egx_gp_ctx* ctx, const double* x_dev, int m, double* grad_dev);
+int egx_gp_predict_var_gradients_dev(egx_gp_ctx* ctx, const double* x_dev, int m, double* grad_dev);
 
 /* ---- building blocks exposed for parity tests ------------------------------
  * R(theta) as assembled at gp/src/algorithm.rs:997-1001 (full symmetric n x n,
@@ -356,6 +359,36 @@ int egx_sgp_model_woodbury(egx_sgp_model* m, double* w_vec, double* w_inv);
 egx_sgp_ctx* egx_sgp_model_context(egx_sgp_model* m);
 int egx_sgp_model_predict(egx_sgp_model* m, const double* x, int npts, double* y);
 int egx_sgp_model_predict_var(egx_sgp_model* m, const double* x, int npts, double* var);
+
+/* ============================================================================
+ * Mixture of experts -- crates/moe/src/gaussian_mixture.rs + the recombination of
+ * crates/moe/src/algorithm.rs.
+ * An egx_moe holds the predict-side Gaussian mixture `gmx` (weights k, means k x d,
+ * covariances k x d x d, heaviside factor: GaussianMixture::new :62-83 +
+ * heaviside_factor :101-106) and BORROWS one fitted expert context per cluster
+ * (egx_gp_model_context of the expert trained on the rows of that cluster,
+ * algorithm.rs:165-177).  The points stay on the device between the
+ * responsibilities, the experts' batched predictions and the recombination.
+ * ========================================================================== */
+#define EGX_RECOMB_HARD   0   /* Recombination::Hard      moe/src/types.rs */
+#define EGX_RECOMB_SMOOTH 1   /* Recombination::Smooth(f) (f = the mixture's heaviside factor) */
+typedef struct egx_moe egx_moe;
+int egx_moe_create(egx_moe** out, int device, int k, int d, const double* weights, const double* means,
+                   const double* covariances, double heaviside_factor);
+void egx_moe_destroy(egx_moe* moe);
+int egx_moe_set_heaviside_factor(egx_moe* moe, double factor);           /* gaussian_mixture.rs:101-106 */
+int egx_moe_set_expert(egx_moe* moe, int cluster, egx_gp_ctx* expert);   /* borrowed, must outlive the calls */
+/* precisions / precisions_chol (k x d x d) and log_det (k) as serialised in the `gmx` block; any may be NULL */
+int egx_moe_parameters(const egx_moe* moe, double* precisions, double* precisions_chol, double* log_det);
+/* predict_probas :109-116 (m x k) and predict :306-318 (arg-max cluster per point); either output may be NULL */
+int egx_moe_predict_probas(egx_moe* moe, const double* x, int m, double* probas, int* clusters);
+/* predict_probas_derivatives :158-170 (m x k x d) */
+int egx_moe_predict_probas_derivatives(egx_moe* moe, const double* x, int m, double* dprobas);
+/* GpMixture::predict / predict_var / predict_valvar / predict_gradients / predict_var_gradients /
+ * predict_valvar_gradients (algorithm.rs:455-541 dispatching to :411-423, 670-1010): any of y (m),
+ * var (m), grad_y (m x d), grad_var (m x d) may be NULL. */
+int egx_moe_predict(egx_moe* moe, int recombination, const double* x, int m, double* y, double* var,
+                    double* grad_y, double* grad_var);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,15 @@ def main():
     expert = json.loads(js[start:i + 1])
     expert["source"] = "doc/Gpx_Tutorial.ipynb:420-421 (experts[0])"
     (OUT / "gpx_tutorial_linear_matern52.json").write_text(json.dumps(expert, indent=1))
+    # --- mixture-level blocks of the same stored model (gmx of the one-cluster GMM, the params with the
+    #     regression / correlation spec sets the expert was SELECTED from by cross-validation), plus the
+    #     `Gpx string` line printed next to it
+    full = json.loads(js)
+    mix = {k: full[k] for k in ("recombination", "gmx", "gp_type", "training_data", "params")}
+    mix["display"] = re.search(r"Gpx string: (.*)", t).group(1).strip()
+    mix["selected_expert"] = full["experts"][0]["type_fullgp"]
+    mix["source"] = "doc/Gpx_Tutorial.ipynb:420-421 (mixture-level blocks)"
+    (OUT / "gpx_tutorial_mixture.json").write_text(json.dumps(mix, indent=1))
     print("wrote", [p.name for p in OUT.glob("gpx_tutorial_*.json")])
 
 
