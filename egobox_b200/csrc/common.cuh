@@ -78,6 +78,11 @@ void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const do
                       int nblocks64, cudaStream_t s);
 void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s);
 int gemm_smem_bytes();
+// kernels_ozaki.cu: the trailing SYRK update on tcgen05 (int8-sliced fp64)
+size_t ozaki_slice_bytes(long rows);
+void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int8_t* S, cudaStream_t s);
+void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,
+                       long long* dbg = nullptr);
 // kernels_solve.cu
 void launch_gls(const double* M, long ld, int n, int npad, int p, double* work, double* G,
                 double* beta, double* rho, EvalResult* res, const int* info, cudaStream_t s);

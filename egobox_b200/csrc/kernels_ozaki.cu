@@ -1,31 +1,32 @@
 // K4o: the trailing SYRK update  C -= P P^T  (K = 256, fp64 result) on the 5th-generation tensor cores.
 //
-// tcgen05 has no f64 kind, so the fp64 panel P is split ONCE per panel pair into 8 signed 7-bit slices per entry
-// (int8), relative to a power-of-two scale per ROW (Ozaki splitting):
-//     P[i][k] = 2^e_i * sum_{s=0..7} S_s[i][k] * 2^-7(s+1)   (+ truncation below 2^(e_i-56)),   |S_s| <= 127.
-// A product of two slices is exact in int32 (127^2 * 256 < 2^22; the <= 8 slice pairs that share a weight sum to
-// < 2^25), so   (P P^T)[i][j] = 2^(e_i+e_j) * sum_g 2^-7(g+2) * ACC_g[i][j],   ACC_g = sum_{p+q=g} S_p S_q^T
-// with every ACC_g an exact integer matrix produced by `tcgen05.mma.kind::i8` (SASS UTCIMMA) into tensor memory.
-// Slice pairs with p + q > 7 are dropped: they sit below 2^-56 * K * 7 of |row_i|_max |row_j|_max, i.e. at the level
-// of the rounding of the fp64 dot product itself.  36 int8 MMAs replace one fp64 MMA: 8192 int8 MAC/clk/SM
-// (measured, tools/micro/i8mma_probe.cu) against 64 fp64 FMA/clk/SM on the DMMA pipe.
+// tcgen05 has no f64 kind, so the fp64 panel P is split ONCE per panel pair into 7 balanced base-256 digits per entry
+// (int8, the full range -128..127), relative to a power-of-two scale per ROW (Ozaki splitting):
+//     P[i][k] = s_i * sum_{d=0..6} S_d[i][k] * 256^-(d+1)   (rounded at s_i 2^-57),   s_i = 2^e >= 4 |row i|_max.
+// A product of two digit slices is exact in int32 (2^14 * 256 = 2^22 per pair; the <= 7 pairs that share a weight stay
+// below 2^25), so   (P P^T)[i][j] = s_i s_j * sum_w 256^-(w+2) * ACC_w[i][j],   ACC_w = sum_{p+q=w} S_p S_q^T
+// with every ACC_w an exact integer matrix produced by `tcgen05.mma.kind::i8` (SASS UTCIMMA) into tensor memory.
+// Digit pairs with p + q > 6 are dropped: they sit below 2^-47 of s_i s_j, i.e. at the level of the rounding of the
+// fp64 dot product itself (measured against a long-double loop in tools/micro/ozaki_probe.cu).  28 int8 MMAs replace
+// one fp64 MMA: 8190 int8 MAC/clk/SM (measured, tools/micro/i8mma_probe.cu) against 64 fp64 FMA/clk/SM on the DMMA pipe.
 //
 // Reference being replaced: the trailing update inside `r_mx.cholesky()` gp/src/algorithm.rs:1004 / :1077.
 //
 // Data layout.  The slices of a (rows x 256) panel live in HBM as
-//     S[row block rb of 128][K step ks of 32][slice s][K chunk kc of 16][row r of 128][16 bytes]
-// so that (i) the 128 x 32 operand of one MMA is the canonical K-major / no-swizzle shared-memory layout of the
-// tensor core (core matrix = 8 rows x 16 bytes contiguous; 128 bytes between row groups, 2048 bytes between the two
-// K chunks) and (ii) all slices a CTA needs for one K step are ONE contiguous run -> one 1-D TMA bulk copy per
-// operand and stage (cp.async.bulk, SASS UBLKCP), no tensor map.
+//     S[row block rb of 128][K step ks of 32][slot s of 8][row group of 8][K chunk kc of 16][row in group][16 bytes]
+// (slots 0..6 = the digits, slot 7 unused) so that (i) the 128 x 32 operand of one MMA is the canonical K-major /
+// no-swizzle shared-memory layout of the tensor core (core matrix = 8 rows x 16 bytes contiguous; 128 bytes between
+// the two K chunks, 256 bytes between row groups), (ii) all slices a CTA needs for one K step are ONE contiguous run
+// -> one 1-D TMA bulk copy per operand and stage (cp.async.bulk, SASS UBLKCP), no tensor map, and (iii) any 64-row
+// half of a slice is contiguous too (the two-CTA kernel splits the B rows between the CTAs of a pair).
 //
 // Kernel.  One CTA per 128 x 128 tile of C, 10 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
-// warps 2..9 = epilogue.  Tensor memory holds 4 accumulators of 128 columns (all 512 columns), so the 8 weights are
-// done in two passes over K: pass 0 = weights 0..3 (slices 0..3, 10 pairs), pass 1 = weights 4..7 (slices 0..7, 26
-// pairs).  After a pass the epilogue reads the 4 accumulators (tcgen05.ld 16x256b: a quad of lanes holds 8
-// consecutive columns of a row, so the read-modify-write of C uses full 32-byte sectors), folds them exactly
-// into one int64  T = (a0<<21) + (a1<<14) + (a2<<7) + a3 , converts once and applies
-//     C[i][j] -= T * 2^(e_i + e_j - 35 - 28 pass).
+// warps 2..9 = epilogue.  Tensor memory holds 4 accumulators of 128 columns (all 512 columns), so the 7 weights are
+// done in two passes over K: pass 0 = weights 0..3 (digits 0..3, 10 pairs), pass 1 = weights 4..6 (digits 0..6, 18
+// pairs).  After a pass the epilogue reads the accumulators (tcgen05.ld 16x256b: a quad of lanes holds 8 consecutive
+// columns of a row, so C moves in full 32-byte sectors), folds them exactly into one int64
+//     T = ((a0 * 256 + a1) * 256 + a2) * 256 + a3 ,  converts once and applies  C[i][j] -= T * s_i s_j 2^-40
+// (pass 1: three accumulators, 2^-64).  An epilogue thread keeps its 64 entries of C in registers across both passes.
 #include <cstdint>
 #include <cstdlib>
 
@@ -34,14 +35,15 @@
 
 namespace {
 
-constexpr int OZ_SLICES = 8;
+constexpr int OZ_SLICES = 7;                     // balanced base-256 digits per entry
+constexpr int OZ_SLOTS = 8;                      // slice slots per K step in the layout (slot 7 unused)
 constexpr int OZ_K = 256;                        // contraction length (a panel pair)
 constexpr int OZ_KSTEPS = OZ_K / 32;             // MMA K = 32 bytes
 constexpr int OZ_SLICE_STEP_BYTES = 128 * 32;    // one slice, one K step, 128 rows
-constexpr int OZ_STAGE_OPERAND = OZ_SLICES * OZ_SLICE_STEP_BYTES;   // 32 KB
+constexpr int OZ_STAGE_OPERAND = OZ_SLOTS * OZ_SLICE_STEP_BYTES;    // 32 KB
 constexpr int OZ_STAGE_BYTES = 2 * OZ_STAGE_OPERAND;                // A + B
 constexpr int OZ_STAGES = 3;
-constexpr int OZ_THREADS = 320;
+constexpr int OZ_THREADS = 352;                   // warp 0: A producer, 1: MMA issuer, 2..9: epilogue, 10: B producer
 constexpr long OZ_RB_BYTES = static_cast<long>(OZ_KSTEPS) * OZ_STAGE_OPERAND;   // slices of one 128-row block: 256 KB
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -73,10 +75,10 @@ __device__ __forceinline__ void oz_umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem_u32(bar))
                  : "memory");
 }
-// K-major, no swizzle: LBO = byte distance of the two 16-byte K chunks, SBO = byte distance of 8-row groups
+// K-major, no swizzle: LBO = byte distance of the two 16-byte K chunks (128), SBO = byte distance of 8-row groups (256)
 __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
-    return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) | (static_cast<uint64_t>(2048 >> 4) << 16) |
-           (static_cast<uint64_t>(128 >> 4) << 32) | (static_cast<uint64_t>(1) << 46);
+    return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) | (static_cast<uint64_t>(128 >> 4) << 16) |
+           (static_cast<uint64_t>(256 >> 4) << 32) | (static_cast<uint64_t>(1) << 46);
 }
 // instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = 128
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(128 >> 3) << 17) |
@@ -88,6 +90,7 @@ __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db
         "l"(da), "l"(db), "r"(OZ_IDESC), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void oz_mma2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate);
 // 16 lanes x 256 bit, 4 repetitions along the columns: 32 columns of 16 rows; thread t holds, for repetition j,
 // v[4j+0..1] = row (t / 4), columns 8 j + 2 (t % 4) + {0, 1} and v[4j+2..3] = row (t / 4) + 8, same columns
 __device__ __forceinline__ void oz_tmem_ld(uint32_t addr, uint32_t (&v)[16]) {
@@ -116,7 +119,7 @@ __device__ __forceinline__ void oz_tile_decode(int t, int tri, int& r, int& c) {
 // ---------------------------------------------------------------------------------------------------------------
 // slicing: (rows x 256) fp64 panel -> row scales 2^e_i and the int8 slices
 // ---------------------------------------------------------------------------------------------------------------
-// one warp per row: 2^e with |row|_max < 2^e (0 for an all-zero row)
+// one warp per row: s = 2^e with 4 |row|_max <= s (0 for an all-zero row)
 __global__ void __launch_bounds__(256) ozaki_rowscale_kernel(const double* __restrict__ P, long ldp, int rows,
                                                              double* __restrict__ rscale) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -132,45 +135,53 @@ __global__ void __launch_bounds__(256) ozaki_rowscale_kernel(const double* __res
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) {
         double s = 0.0;
-        if (m > 0.0 && m < 1.0e300) s = scalbn(1.0, ilogb(m) + 1);
+        if (m > 0.0 && m < 1.0e300) s = scalbn(1.0, ilogb(m) + 3);
         rscale[row] = s;
     }
 }
 
-// thread = (row, 16-entry K chunk): 16 doubles in, 8 x 16 bytes out
+// thread = (row, 16-entry K chunk): 16 doubles in, 7 x 16 bytes out.
+// t = rint(x 2^56 / s) (|t| < 2^54); adding 0x80 to each of its 7 low bytes makes every byte the balanced digit + 128
+// with no borrows, so the digits are the bytes of (t + 0x00808080 80808080) XOR 0x80: byte j = digit 6 - j.
 __global__ void __launch_bounds__(128) ozaki_slice_kernel(const double* __restrict__ P, long ldp,
                                                           const double* __restrict__ rscale, int8_t* __restrict__ S) {
     const int rb = blockIdx.x, chunk = blockIdx.y, rr = threadIdx.x;
     const long row = static_cast<long>(rb) * 128 + rr;
     const double sc = rscale[row];
-    const double inv = sc > 0.0 ? 72057594037927936.0 / sc : 0.0;           // 2^56 / 2^e
+    const double inv = sc > 0.0 ? 72057594037927936.0 / sc : 0.0;           // 2^56 / s
     const double* p = P + row * ldp + chunk * 16;
     uint32_t w[OZ_SLICES][4];
 #pragma unroll
-    for (int s = 0; s < OZ_SLICES; ++s)
+    for (int q4 = 0; q4 < 4; ++q4) {                                         // 4 consecutive entries -> one word per slice
+        uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w[s][q] = 0u;
-#pragma unroll
-    for (int e2 = 0; e2 < 8; ++e2) {
-        const double2 v = *reinterpret_cast<const double2*>(p + 2 * e2);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int e = 2 * e2 + h;
-            const long long t = __double2ll_rz((h ? v.y : v.x) * inv);     // |t| < 2^56, exact scaling
-            const unsigned long long mag = static_cast<unsigned long long>(t < 0 ? -t : t);
-#pragma unroll
-            for (int s = 0; s < OZ_SLICES; ++s) {
-                int d = static_cast<int>((mag >> (7 * (7 - s))) & 127ull);
-                if (t < 0) d = -d;
-                w[s][e >> 2] |= (static_cast<uint32_t>(d) & 0xffu) << (8 * (e & 3));
-            }
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const double2 v = *reinterpret_cast<const double2*>(p + 4 * q4 + 2 * h2);
+            const unsigned long long u0 = static_cast<unsigned long long>(__double2ll_rn(v.x * inv)) + 0x0080808080808080ull;
+            const unsigned long long u1 = static_cast<unsigned long long>(__double2ll_rn(v.y * inv)) + 0x0080808080808080ull;
+            lo[2 * h2] = static_cast<uint32_t>(u0);
+            hi[2 * h2] = static_cast<uint32_t>(u0 >> 32);
+            lo[2 * h2 + 1] = static_cast<uint32_t>(u1);
+            hi[2 * h2 + 1] = static_cast<uint32_t>(u1 >> 32);
         }
+        // 4 x 4 byte transposes: word k of the result = byte k of the four entries
+        const uint32_t l01a = __byte_perm(lo[0], lo[1], 0x5140), l01b = __byte_perm(lo[0], lo[1], 0x7362);
+        const uint32_t l23a = __byte_perm(lo[2], lo[3], 0x5140), l23b = __byte_perm(lo[2], lo[3], 0x7362);
+        const uint32_t h01a = __byte_perm(hi[0], hi[1], 0x5140), h01b = __byte_perm(hi[0], hi[1], 0x7362);
+        const uint32_t h23a = __byte_perm(hi[2], hi[3], 0x5140), h23b = __byte_perm(hi[2], hi[3], 0x7362);
+        w[6][q4] = __byte_perm(l01a, l23a, 0x5410) ^ 0x80808080u;           // byte 0 = digit 6
+        w[5][q4] = __byte_perm(l01a, l23a, 0x7632) ^ 0x80808080u;
+        w[4][q4] = __byte_perm(l01b, l23b, 0x5410) ^ 0x80808080u;
+        w[3][q4] = __byte_perm(l01b, l23b, 0x7632) ^ 0x80808080u;
+        w[2][q4] = __byte_perm(h01a, h23a, 0x5410) ^ 0x80808080u;           // byte 4 = digit 2
+        w[1][q4] = __byte_perm(h01a, h23a, 0x7632) ^ 0x80808080u;
+        w[0][q4] = __byte_perm(h01b, h23b, 0x5410) ^ 0x80808080u;           // byte 6 = digit 0 (most significant)
     }
     const int ks = chunk >> 1, kc = chunk & 1;
 #pragma unroll
     for (int s = 0; s < OZ_SLICES; ++s) {
-        int8_t* dst = S + static_cast<long>(rb) * OZ_RB_BYTES +
-                      ((static_cast<long>(ks) * OZ_SLICES + s) * 2 + kc) * 2048 + rr * 16;
+        int8_t* dst = S + static_cast<long>(rb) * OZ_RB_BYTES + (static_cast<long>(ks) * OZ_SLOTS + s) * OZ_SLICE_STEP_BYTES +
+                      (rr >> 3) * 256 + kc * 128 + (rr & 7) * 16;
         *reinterpret_cast<uint4*>(dst) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
     }
 }
@@ -184,23 +195,90 @@ struct OzakiArgs {
     const int8_t* S;          // slices of the panel rows; row block 0 = first tile row / column of C
     const double* rscale;     // 2^e per panel row
     int Mt, tri;              // tile rows; the first `tri` rows are triangular (c <= r), the others full (c < tri)
+    long long* dbg;           // OZ_TIMING builds (tools/micro/ozaki_probe.cu): clock64 stamps of CTA 0
 };
+#ifdef OZ_TIMING
+#define OZ_STAMP(slot) do { if (blockIdx.x == 0 && g.dbg) g.dbg[slot] = clock64(); } while (0)
+#else
+#define OZ_STAMP(slot) do { } while (0)
+#endif
 
 struct __align__(8) OzBarriers {
     uint64_t full[OZ_STAGES], empty[OZ_STAGES], acc_full, acc_empty;
     uint32_t tmem_base, pad_;
 };
 
+// x2: 16 columns of 16 rows; thread t holds, for repetition j = 0, 1,
+// v[4j+0..1] = row (t / 4), columns 8 j + 2 (t % 4) + {0, 1} and v[4j+2..3] = row (t / 4) + 8, same columns
+__device__ __forceinline__ void oz_tmem_ld2(uint32_t addr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(addr));
+}
+
+// exact int64 -> double for |t| < 2^51 without the slow 64-bit convert: bias into the mantissa of 2^52 + 2^51
+__device__ __forceinline__ double oz_i64_to_double(long long t) {
+    return __longlong_as_double(t + 0x4338000000000000LL) - 6755399441055744.0;
+}
+
+// Fold the NACC accumulators of a pass (weights w0 .. w0 + NACC - 1, accumulator g at columns 128 g) into the 64
+// entries of C this thread owns: rows 32 quarter + 16 rh + r_in (+8), columns 64 chalf + 8 j + cq + {0, 1}.
+// rsA / rsB point at the row scales of this thread's first row / column; wscale = 256^-(w_last + 2).
+template <int NACC>
+__device__ __forceinline__ void oz_drain(uint32_t tmem, int quarter, int chalf, const double* __restrict__ rsA,
+                                         const double* __restrict__ rsB, double wscale, double2 (&c)[2][2][8]) {
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+        const double sr0 = rsA[16 * rh] * wscale, sr1 = rsA[16 * rh + 8] * wscale;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            uint32_t a[NACC][8];
+            const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * quarter + 16 * rh) << 16) + 64 * chalf + 16 * jj;
+#pragma unroll
+            for (int gg = 0; gg < NACC; ++gg) oz_tmem_ld2(taddr + gg * 128, a[gg]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
+                const int j = 2 * jj + rep;
+                const double sc0 = rsB[8 * j], sc1 = rsB[8 * j + 1];
+                double d[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    long long t = static_cast<long long>(static_cast<int32_t>(a[0][4 * rep + e]));
+#pragma unroll
+                    for (int gg = 1; gg < NACC; ++gg) t = t * 256LL + static_cast<long long>(static_cast<int32_t>(a[gg][4 * rep + e]));
+                    d[e] = oz_i64_to_double(t);
+                }
+                c[rh][0][j].x = fma(-d[0], sr0 * sc0, c[rh][0][j].x);
+                c[rh][0][j].y = fma(-d[1], sr0 * sc1, c[rh][0][j].y);
+                c[rh][1][j].x = fma(-d[2], sr1 * sc0, c[rh][1][j].x);
+                c[rh][1][j].y = fma(-d[3], sr1 * sc1, c[rh][1][j].y);
+            }
+        }
+    }
+}
+
+// All MMAs of one K step of a pass, fully unrolled: the issuing thread is a single thread, so every integer
+// instruction between two tcgen05.mma counts against the 64-clock budget of an MMA (a run-time (p, q) loop with
+// descriptor arithmetic issued one MMA per ~100 clocks).  The descriptors of the digit slices differ only in the
+// start-address field (bits 0..13, units of 16 bytes).
+template <int PASS, int B_SLICE_BYTES, bool TWO_CTA>
+__device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint32_t sb, uint32_t not_first_ks);
+
+// Persistent: CTA b works on tiles b, b + gridDim.x, ...  The stage ring and the accumulator hand-shake run across
+// tiles, so the producer is already streaming the next tile while the epilogue folds the last pass of this one.
+// An epilogue thread owns the same 64 entries of C in both passes: they are loaded while the MMAs of pass 0 run,
+// updated in registers after each pass and stored once.
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiArgs g) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
     OzBarriers* bars = reinterpret_cast<OzBarriers*>(oz_smem + OZ_STAGES * OZ_STAGE_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int tr, tc;
-    oz_tile_decode(blockIdx.x, g.tri, tr, tc);
+    const int ntiles = g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri;
+    if (tid == 0) OZ_STAMP(0);
 
     if (tid == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) {
-            oz_mbar_init(&bars->full[s], 1);
+            oz_mbar_init(&bars->full[s], 2);
             oz_mbar_init(&bars->empty[s], 1);
         }
         oz_mbar_init(&bars->acc_full, 1);
@@ -216,114 +294,350 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = bars->tmem_base;
+    if (tid == 0) OZ_STAMP(1);
 
-    if (warp == 0) {
-        // ===== producer: one elected lane streams the K steps of both passes through the stage ring =====
+    if (warp == 0 || warp == 10) {
+        // ===== producers: warp 0 streams the A slices, warp 10 the B slices (bulk copies issued by one thread are
+        // served one after the other, ~600 clocks each whatever their size; two threads run in parallel) =====
         if (lane == 0) {
-            const int8_t* Ag = g.S + static_cast<long>(tr) * OZ_RB_BYTES;
-            const int8_t* Bg = g.S + static_cast<long>(tc) * OZ_RB_BYTES;
-            for (int it = 0; it < 2 * OZ_KSTEPS; ++it) {
-                const int stage = it % OZ_STAGES, pass = it / OZ_KSTEPS, ks = it % OZ_KSTEPS;
-                const uint32_t bytes = (pass == 0 ? 4 : 8) * OZ_SLICE_STEP_BYTES;
-                oz_mbar_wait(&bars->empty[stage], ((it / OZ_STAGES) & 1) ^ 1);
-                oz_mbar_expect_tx(&bars->full[stage], 2 * bytes);
-                unsigned char* st = oz_smem + stage * OZ_STAGE_BYTES;
-                oz_bulk_g2s(st, Ag + static_cast<long>(ks) * OZ_STAGE_OPERAND, bytes, &bars->full[stage]);
-                oz_bulk_g2s(st + OZ_STAGE_OPERAND, Bg + static_cast<long>(ks) * OZ_STAGE_OPERAND, bytes, &bars->full[stage]);
+            const bool isB = warp == 10;
+            uint32_t n = 0;                                  // global K-step counter
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                int tr, tc;
+                oz_tile_decode(tile, g.tri, tr, tc);
+                const int8_t* Sg = g.S + static_cast<long>(isB ? tc : tr) * OZ_RB_BYTES;
+                for (int it = 0; it < 2 * OZ_KSTEPS; ++it, ++n) {
+                    const uint32_t stage = n % OZ_STAGES, round = n / OZ_STAGES;
+                    const int pass = it / OZ_KSTEPS, ks = it % OZ_KSTEPS;
+                    const uint32_t bytes = (pass == 0 ? 4 : OZ_SLICES) * OZ_SLICE_STEP_BYTES;
+                    oz_mbar_wait(&bars->empty[stage], (round & 1) ^ 1);
+                    oz_mbar_expect_tx(&bars->full[stage], bytes);
+                    oz_bulk_g2s(oz_smem + stage * OZ_STAGE_BYTES + (isB ? OZ_STAGE_OPERAND : 0),
+                                Sg + static_cast<long>(ks) * OZ_STAGE_OPERAND, bytes, &bars->full[stage]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            for (int it = 0; it < 2 * OZ_KSTEPS; ++it) {
-                const int stage = it % OZ_STAGES, pass = it / OZ_KSTEPS, ks = it % OZ_KSTEPS;
-                if (it == OZ_KSTEPS) {                     // pass 1 reuses the accumulators: wait for the drain
-                    oz_mbar_wait(&bars->acc_empty, 0);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                oz_mbar_wait(&bars->full[stage], (it / OZ_STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = oz_smem_u32(oz_smem + stage * OZ_STAGE_BYTES);
-                const uint32_t sb = sa + OZ_STAGE_OPERAND;
-                const int g0 = pass * 4;
-#pragma unroll
-                for (int gg = 0; gg < 4; ++gg) {
-                    const int w = g0 + gg;                 // weight p + q
-                    for (int p = 0; p <= w; ++p) {
-                        const int q = w - p;
-                        if (p > 7 || q > 7) continue;
-                        oz_mma(tmem + gg * 128, oz_desc(sa + p * OZ_SLICE_STEP_BYTES), oz_desc(sb + q * OZ_SLICE_STEP_BYTES),
-                               (ks > 0 || p > 0) ? 1u : 0u);
+            uint32_t n = 0, P = 0;                           // global K-step / pass counters
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int pass = 0; pass < 2; ++pass, ++P) {
+                    if (P > 0) {                             // the accumulators are reused: wait for the drain of pass P-1
+                        oz_mbar_wait(&bars->acc_empty, (P - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    for (int ks = 0; ks < OZ_KSTEPS; ++ks, ++n) {
+                        const uint32_t stage = n % OZ_STAGES, round = n / OZ_STAGES;
+                        oz_mbar_wait(&bars->full[stage], round & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (P == 0 && ks == 0) OZ_STAMP(2);
+                        if (P == 1 && ks == 0) OZ_STAMP(3);
+                        const uint32_t sa = oz_smem_u32(oz_smem + stage * OZ_STAGE_BYTES);
+                        const uint32_t sb = sa + OZ_STAGE_OPERAND;
+                        if (pass == 0) oz_issue_kstep<0, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sb, ks > 0 ? 1u : 0u);
+                        else oz_issue_kstep<1, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sb, ks > 0 ? 1u : 0u);
+                        oz_umma_commit(&bars->empty[stage]);   // frees the stage when these MMAs have read it
+                        if (ks == OZ_KSTEPS - 1) oz_umma_commit(&bars->acc_full);
                     }
                 }
-                oz_umma_commit(&bars->empty[stage]);       // frees the stage when these MMAs have read it
-                if (ks == OZ_KSTEPS - 1) oz_umma_commit(&bars->acc_full);
             }
         }
     } else {
         // ===== epilogue: 8 warps; lane quarter = warp % 4, column half = (warp - 2) / 4 =====
         const int quarter = warp & 3, chalf = (warp - 2) >> 2;
         const int r_in = lane >> 2, cq = 2 * (lane & 3);
-        double* Cb = g.C + static_cast<long>(tr) * 128 * g.ldc + static_cast<long>(tc) * 128;
-        const double* rsA = g.rscale + static_cast<long>(tr) * 128;
-        const double* rsB = g.rscale + static_cast<long>(tc) * 128;
-        for (int pass = 0; pass < 2; ++pass) {
-            oz_mbar_wait(&bars->acc_full, pass);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const double wscale = pass == 0 ? 2.9103830456733704e-11 /* 2^-35 */ : 1.0842021724855044e-19 /* 2^-63 */;
+        uint32_t P = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int tr, tc;
+            oz_tile_decode(tile, g.tri, tr, tc);
+            // this thread's entries: rows 32 quarter + 16 rh + r_in (+8), columns 64 chalf + 8 j + cq + {0,1}
+            double* Cb = g.C + (static_cast<long>(tr) * 128 + 32 * quarter + r_in) * g.ldc + static_cast<long>(tc) * 128 +
+                         64 * chalf + cq;
+            const double* rsA = g.rscale + static_cast<long>(tr) * 128 + 32 * quarter + r_in;
+            const double* rsB = g.rscale + static_cast<long>(tc) * 128 + 64 * chalf + cq;
+            double2 c[2][2][8];                              // [rh][row r_in / r_in + 8][j]
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        c[rh][h][j] = *reinterpret_cast<const double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j);
 #pragma unroll 1
-            for (int rh = 0; rh < 2; ++rh) {
-                const int row0 = 32 * quarter + 16 * rh;          // TMEM lane of row r_in = 0 of this block
-                const double sr0 = rsA[row0 + r_in] * wscale, sr1 = rsA[row0 + r_in + 8] * wscale;
-#pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int col0 = 64 * chalf + 32 * cc;
-                    uint32_t a[4][16];
-#pragma unroll
-                    for (int gg = 0; gg < 4; ++gg)
-                        oz_tmem_ld(tmem + (static_cast<uint32_t>(row0) << 16) + gg * 128 + col0, a[gg]);
-                    // the C values of this thread: rows row0 + r_in (+8), columns col0 + 8 j + cq + {0,1}
-                    double2 c0[4], c1[4];
-                    double* p0 = Cb + static_cast<long>(row0 + r_in) * g.ldc + col0 + cq;
-                    double* p1 = p0 + 8 * g.ldc;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        c0[j] = *reinterpret_cast<const double2*>(p0 + 8 * j);
-                        c1[j] = *reinterpret_cast<const double2*>(p1 + 8 * j);
-                    }
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double sc0 = rsB[col0 + 8 * j + cq], sc1 = rsB[col0 + 8 * j + cq + 1];
-                        long long t[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            t[e] = static_cast<long long>(static_cast<int32_t>(a[0][4 * j + e])) * 2097152LL +
-                                   static_cast<long long>(static_cast<int32_t>(a[1][4 * j + e])) * 16384LL +
-                                   static_cast<long long>(static_cast<int32_t>(a[2][4 * j + e])) * 128LL +
-                                   static_cast<long long>(static_cast<int32_t>(a[3][4 * j + e]));
-                        c0[j].x = fma(-static_cast<double>(t[0]), sr0 * sc0, c0[j].x);
-                        c0[j].y = fma(-static_cast<double>(t[1]), sr0 * sc1, c0[j].y);
-                        c1[j].x = fma(-static_cast<double>(t[2]), sr1 * sc0, c1[j].x);
-                        c1[j].y = fma(-static_cast<double>(t[3]), sr1 * sc1, c1[j].y);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        *reinterpret_cast<double2*>(p0 + 8 * j) = c0[j];
-                        *reinterpret_cast<double2*>(p1 + 8 * j) = c1[j];
-                    }
-                }
-            }
-            if (pass == 0) {
+            for (int pass = 0; pass < 2; ++pass, ++P) {
+                const double wscale = pass == 0 ? 9.094947017729282e-13 /* 256^-5 */ : 5.421010862427522e-20 /* 256^-8 */;
+                oz_mbar_wait(&bars->acc_full, P & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tid == 64 && tile == blockIdx.x) OZ_STAMP(4 + 2 * pass);
+                if (pass == 0) oz_drain<4>(tmem, quarter, chalf, rsA, rsB, wscale, c);
+                else oz_drain<3>(tmem, quarter, chalf, rsA, rsB, wscale, c);
+                // all TMEM reads of this pass are complete: hand the accumulators back
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) oz_mbar_arrive(&bars->acc_empty);
+                if (tid == 64 && tile == blockIdx.x) OZ_STAMP(5 + 2 * pass);
             }
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) = c[rh][h][j];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tid == 0) OZ_STAMP(8);
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// =================================================================================================================
+// Two-CTA variant (thread-block cluster of 2, tcgen05 cta_group::2).
+// With both operands read from shared memory an M = 128, N = 128 int8 MMA needs 128 B/clk of shared-memory
+// bandwidth -- all there is -- and the TMA refills of the stages come on top: the single-CTA kernel is bound by the
+// shared-memory port (83 clk per MMA measured instead of 64).  A CTA pair works on a 256 x 128 tile: each CTA holds the
+// slices of ITS 128 rows (A) and HALF of the 128 B rows, the pair-wide MMA (M = 256) reads A 4 KB + B 2 KB per CTA and
+// instruction (96 B/clk) and every B slice crosses L2 -> SM once per pair instead of once per CTA.
+//   rank 0 (leader): issues the MMAs for the pair; rank 1: its warp 1 relays "my stage has landed" to the leader.
+//   stage free / accumulators ready: tcgen05.commit multicast to both CTAs; accumulators drained: both epilogues
+//   arrive on the leader's barrier (remote arrive for rank 1).
+// =================================================================================================================
+constexpr int OZ2_STAGES = 4;
+constexpr int OZ2_A_BYTES = OZ_STAGE_OPERAND;                  // 8 slices x 128 rows x 32 B
+constexpr int OZ2_BH_SLICE = 64 * 32;                          // one slice of the 64-row half, one K step
+constexpr int OZ2_BH_BYTES = OZ_SLOTS * OZ2_BH_SLICE;          // 16 KB
+constexpr int OZ2_STAGE_BYTES = OZ2_A_BYTES + OZ2_BH_BYTES;    // 48 KB
+
+struct __align__(8) Oz2Barriers {
+    uint64_t full[OZ2_STAGES], peer_full[OZ2_STAGES], empty[OZ2_STAGES], acc_full, acc_empty;
+    uint32_t tmem_base, pad_;
+};
+constexpr int OZ2_SMEM_BYTES = OZ2_STAGES * OZ2_STAGE_BYTES + static_cast<int>(sizeof(Oz2Barriers));
+
+__device__ __forceinline__ uint32_t oz_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t oz_mapa(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void oz_remote_arrive(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(oz_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void oz_umma_commit2(uint64_t* bar) {      // arrive on the same barrier of BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            oz_smem_u32(bar)),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+constexpr uint32_t OZ2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(128 >> 3) << 17) |
+                               (static_cast<uint32_t>(256 >> 4) << 24);
+__device__ __forceinline__ void oz_mma2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(OZ2_IDESC), "r"(accumulate)
+        : "memory");
+}
+
+template <int PASS, int B_SLICE_BYTES, bool TWO_CTA>
+__device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint32_t sb, uint32_t not_first_ks) {
+    const uint64_t da0 = oz_desc(sa), db0 = oz_desc(sb);
+    constexpr int W0 = PASS * 4, NW = PASS == 0 ? 4 : 3;
+#pragma unroll
+    for (int gg = 0; gg < NW; ++gg) {
+#pragma unroll
+        for (int p = 0; p < OZ_SLICES; ++p) {
+            const int q = W0 + gg - p;
+            if (q < 0 || q >= OZ_SLICES) continue;
+            const uint64_t da = da0 + static_cast<uint64_t>(p * (OZ_SLICE_STEP_BYTES >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>(q * (B_SLICE_BYTES >> 4));
+            const uint32_t acc = (p == 0) ? not_first_ks : 1u;        // p = 0 is the first pair of every weight
+            if (TWO_CTA) oz_mma2(tmem + gg * 128, da, db, acc);
+            else oz_mma(tmem + gg * 128, da, db, acc);
+        }
+    }
+}
+
+// work item w -> (pair row a, column block tc): pair a = row blocks 2a, 2a+1 and columns 0 .. min(2a+2, tri) - 1
+__device__ __forceinline__ void oz2_decode(int w, int tri, int& a, int& tc) {
+    a = 0;
+    for (;;) {
+        const int nc = (2 * a + 2 < tri) ? 2 * a + 2 : tri;
+        if (w < nc) break;
+        w -= nc;
+        ++a;
+    }
+    tc = w;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki_syrk2_kernel(const OzakiArgs g, int nwork) {
+    extern __shared__ __align__(1024) unsigned char oz_smem[];
+    Oz2Barriers* bars = reinterpret_cast<Oz2Barriers*>(oz_smem + OZ2_STAGES * OZ2_STAGE_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = oz_cluster_rank();
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    if (tid == 0) OZ_STAMP(0);
+
+    if (tid == 0) {
+        for (int s = 0; s < OZ2_STAGES; ++s) {
+            oz_mbar_init(&bars->full[s], 2);
+            oz_mbar_init(&bars->peer_full[s], 1);
+            oz_mbar_init(&bars->empty[s], 1);
+        }
+        oz_mbar_init(&bars->acc_full, 1);
+        oz_mbar_init(&bars->acc_empty, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&bars->tmem_base)),
+                     "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    oz_cluster_sync();                                        // both CTAs: barriers initialised, TMEM allocated
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = bars->tmem_base;
+    if (tid == 0) OZ_STAMP(1);
+
+    if (warp == 0 || warp == 10) {
+        // ===== producers (both CTAs): warp 0 = own A rows, warp 10 = own half of the B rows =====
+        if (lane == 0) {
+            const bool isB = warp == 10;
+            uint32_t n = 0;
+            for (int w = cluster_id; w < nwork; w += nclusters) {
+                int a, tc;
+                oz2_decode(w, g.tri, a, tc);
+                int tr = 2 * a + static_cast<int>(rank);
+                if (tr >= g.Mt) tr = g.Mt - 1;               // odd tile-row count: the partner reloads the last block
+                const int8_t* Ag = g.S + static_cast<long>(tr) * OZ_RB_BYTES;
+                const int8_t* Bg = g.S + static_cast<long>(tc) * OZ_RB_BYTES + rank * OZ2_BH_SLICE;
+                for (int it = 0; it < 2 * OZ_KSTEPS; ++it, ++n) {
+                    const uint32_t stage = n % OZ2_STAGES, round = n / OZ2_STAGES;
+                    const int pass = it / OZ_KSTEPS, ks = it % OZ_KSTEPS;
+                    const int nsl = pass == 0 ? 4 : OZ_SLICES;
+                    oz_mbar_wait_cluster(&bars->empty[stage], (round & 1) ^ 1);
+                    unsigned char* st = oz_smem + stage * OZ2_STAGE_BYTES;
+                    if (!isB) {
+                        oz_mbar_expect_tx(&bars->full[stage], nsl * OZ_SLICE_STEP_BYTES);
+                        oz_bulk_g2s(st, Ag + static_cast<long>(ks) * OZ_STAGE_OPERAND, nsl * OZ_SLICE_STEP_BYTES, &bars->full[stage]);
+                    } else {
+                        oz_mbar_expect_tx(&bars->full[stage], nsl * OZ2_BH_SLICE);
+                        const int8_t* bsrc = Bg + static_cast<long>(ks) * OZ_STAGE_OPERAND;
+                        for (int c = 0; c < nsl; ++c)        // the 64-row half of slice c: 2 KB contiguous
+                            oz_bulk_g2s(st + OZ2_A_BYTES + c * OZ2_BH_SLICE, bsrc + c * OZ_SLICE_STEP_BYTES, OZ2_BH_SLICE,
+                                        &bars->full[stage]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 1) {
+            // ===== relay: tell the leader that this CTA's stage has landed =====
+            uint32_t n = 0;
+            for (int w = cluster_id; w < nwork; w += nclusters)
+                for (int it = 0; it < 2 * OZ_KSTEPS; ++it, ++n) {
+                    const uint32_t stage = n % OZ2_STAGES, round = n / OZ2_STAGES;
+                    oz_mbar_wait(&bars->full[stage], round & 1);
+                    oz_remote_arrive(oz_mapa(oz_smem_u32(&bars->peer_full[stage]), 0));
+                }
+        } else if (lane == 0) {
+            // ===== MMA issuer (leader) =====
+            uint32_t n = 0, P = 0;
+            for (int w = cluster_id; w < nwork; w += nclusters) {
+                for (int pass = 0; pass < 2; ++pass, ++P) {
+                    if (P > 0) {
+                        oz_mbar_wait_cluster(&bars->acc_empty, (P - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    for (int ks = 0; ks < OZ_KSTEPS; ++ks, ++n) {
+                        const uint32_t stage = n % OZ2_STAGES, round = n / OZ2_STAGES;
+                        oz_mbar_wait(&bars->full[stage], round & 1);
+                        oz_mbar_wait_cluster(&bars->peer_full[stage], round & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (P == 0 && ks == 0) OZ_STAMP(2);
+                        if (P == 1 && ks == 0) OZ_STAMP(3);
+                        const uint32_t sa = oz_smem_u32(oz_smem + stage * OZ2_STAGE_BYTES);
+                        const uint32_t sb = sa + OZ2_A_BYTES;
+                        if (pass == 0) oz_issue_kstep<0, OZ2_BH_SLICE, true>(tmem, sa, sb, ks > 0 ? 1u : 0u);
+                        else oz_issue_kstep<1, OZ2_BH_SLICE, true>(tmem, sa, sb, ks > 0 ? 1u : 0u);
+                        oz_umma_commit2(&bars->empty[stage]);
+                        if (ks == OZ_KSTEPS - 1) oz_umma_commit2(&bars->acc_full);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): rows of row block 2a + rank =====
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        const int r_in = lane >> 2, cq = 2 * (lane & 3);
+        const uint32_t acc_empty_leader = oz_mapa(oz_smem_u32(&bars->acc_empty), 0);
+        uint32_t P = 0;
+        for (int w = cluster_id; w < nwork; w += nclusters) {
+            int a, tc;
+            oz2_decode(w, g.tri, a, tc);
+            const int tr = 2 * a + static_cast<int>(rank);
+            const bool live = tr < g.Mt;
+            const int trc = live ? tr : g.Mt - 1;
+            double* Cb = g.C + (static_cast<long>(trc) * 128 + 32 * quarter + r_in) * g.ldc + static_cast<long>(tc) * 128 +
+                         64 * chalf + cq;
+            const double* rsA = g.rscale + static_cast<long>(trc) * 128 + 32 * quarter + r_in;
+            const double* rsB = g.rscale + static_cast<long>(tc) * 128 + 64 * chalf + cq;
+            double2 c[2][2][8];
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        c[rh][h][j] = *reinterpret_cast<const double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j);
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass, ++P) {
+                const double wscale = pass == 0 ? 9.094947017729282e-13 /* 256^-5 */ : 5.421010862427522e-20 /* 256^-8 */;
+                oz_mbar_wait_cluster(&bars->acc_full, P & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tid == 64 && w == cluster_id) OZ_STAMP(4 + 2 * pass);
+                if (pass == 0) oz_drain<4>(tmem, quarter, chalf, rsA, rsB, wscale, c);
+                else oz_drain<3>(tmem, quarter, chalf, rsA, rsB, wscale, c);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) oz_remote_arrive(acc_empty_leader);
+                if (tid == 64 && w == cluster_id) OZ_STAMP(5 + 2 * pass);
+            }
+            if (live) {
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) = c[rh][h][j];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    oz_cluster_sync();                                        // nobody signals a departed CTA; all MMAs / reads done
+    if (tid == 0) OZ_STAMP(8);
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + static_cast<int>(sizeof(OzBarriers));
@@ -341,17 +655,35 @@ void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int
 }
 
 // C (tile rows Mt, first `tri` triangular) -= P P^T from the slices of P
-void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s) {
+void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,
+                       long long* dbg) {
     static bool configured_dev[64] = {false};
     int dev_ = 0;
     cudaGetDevice(&dev_);
     bool& configured = configured_dev[dev_ & 63];
     if (!configured) {
         cudaFuncSetAttribute(ozaki_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+        cudaFuncSetAttribute(ozaki_syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM_BYTES);
         configured = true;
     }
+    static int sm_count_dev[64] = {0};
+    int& sms = sm_count_dev[dev_ & 63];
+    if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_);
     const int tiles = tri * (tri + 1) / 2 + (Mt - tri) * tri;
     if (tiles <= 0) return;
-    OzakiArgs g{C, ldc, S, rscale, Mt, tri};
-    ozaki_syrk_kernel<<<tiles, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g);
+    OzakiArgs g{C, ldc, S, rscale, Mt, tri, dbg};
+    // EGX_OZAKI_PERSIST=1: a resident grid loops over the tiles (prefetch across tiles, no per-tile set-up) -- but it
+    // keeps the high-priority panel / look-ahead kernels of the sweep waiting for SMs; default: one work item per
+    // CTA (pair), so that they slip in between waves like they do with the DMMA kernel.
+    static const int persist = getenv("EGX_OZAKI_PERSIST") != nullptr ? atoi(getenv("EGX_OZAKI_PERSIST")) : 0;
+    static const int two_cta = getenv("EGX_OZAKI_2CTA") != nullptr ? atoi(getenv("EGX_OZAKI_2CTA")) : 0;
+    if (two_cta) {
+        int nwork = 0;
+        for (int a = 0; 2 * a < Mt; ++a) nwork += (2 * a + 2 < tri) ? 2 * a + 2 : tri;
+        const int clusters = (persist && nwork > sms / 2) ? sms / 2 : nwork;
+        ozaki_syrk2_kernel<<<2 * clusters, OZ_THREADS, OZ2_SMEM_BYTES, s>>>(g, nwork);
+        return;
+    }
+    const int grid = (persist && tiles > sms) ? sms : tiles;
+    ozaki_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g);
 }

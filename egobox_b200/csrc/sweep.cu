@@ -67,6 +67,8 @@ int SweepEnv::init(int max_block_cols) {
     EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     const char* e = getenv("EGX_LOOKAHEAD");
     lookahead = !(e != nullptr && atoi(e) == 0);
+    if ((e = getenv("EGX_OZAKI")) != nullptr) ozaki = atoi(e);
+    if ((e = getenv("EGX_OZAKI_MIN_TRI")) != nullptr) ozaki_min_tri = atoi(e) > 1 ? atoi(e) : 1;
     return EGX_OK;
 }
 
@@ -76,6 +78,14 @@ int SweepEnv::ensure_panel_rows(long rows) {
         egx_dev_free(P2[i]);
         P2[i] = nullptr;
         EGX_CUDA_TRY(egx_dev_malloc(&P2[i], static_cast<size_t>(rows) * 2 * EGX_NB * sizeof(double)));
+    }
+    egx_dev_free(oz_S);
+    egx_dev_free(oz_scale);
+    oz_S = nullptr;
+    oz_scale = nullptr;
+    if (ozaki) {
+        EGX_CUDA_TRY(egx_dev_malloc(&oz_S, ozaki_slice_bytes(rows)));
+        EGX_CUDA_TRY(egx_dev_malloc(&oz_scale, static_cast<size_t>(rows) * sizeof(double)));
     }
     p_rows = rows;
     ++generation;
@@ -94,6 +104,10 @@ void SweepEnv::destroy() {
     if (ev_join) cudaEventDestroy(ev_join);
     egx_dev_free(P2[0]);
     egx_dev_free(P2[1]);
+    egx_dev_free(oz_S);
+    egx_dev_free(oz_scale);
+    oz_S = nullptr;
+    oz_scale = nullptr;
     if (sp) cudaStreamDestroy(sp);
     if (sb) cudaStreamDestroy(sb);
     sb = sp = nullptr;
@@ -107,6 +121,24 @@ void SweepEnv::destroy() {
 // on the high-priority stream while the bulk of the trailing update is still in flight on the bulk stream.
 // The multi-RHS solve has no serial part and runs as plain back-to-back launches (measured 22.9 vs 28.8 ms
 // per 8192-point chunk at n = 8192 with / without stream splitting).
+// The K = 256 trailing update of the factorisation, C(tile rows Mt, first `tri` triangular) -= A A^T with A the
+// (Mt * 128) x 256 panel-pair rows: on tcgen05 through the int8 slices when the tile set is large enough to pay
+// for the slicing pass, else on the DMMA kernel.
+static void trailing_syrk(SweepEnv& env, const GemmArgs& g, cudaStream_t st) {
+    if (env.ozaki && env.oz_S != nullptr && g.tri >= env.ozaki_min_tri && g.K == 2 * EGX_NB && g.A == g.B &&
+        g.lda == 2 * EGX_NB && static_cast<long>(g.Mt) * EGX_NB <= env.p_rows) {
+        {
+            StageScope sc(env.prof, EGX_STAGE_OZAKI_SLICE, 2, st);
+            launch_ozaki_slice(g.A, g.lda, g.Mt * EGX_NB, env.oz_scale, env.oz_S, st);
+        }
+        StageScope sc(env.prof, EGX_STAGE_OZAKI_SYRK, 1, st);
+        launch_ozaki_syrk(g.C, g.ldc, env.oz_S, env.oz_scale, g.Mt, g.tri, st);
+        return;
+    }
+    StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, st);
+    launch_gemm_nt_sub(g, st);
+}
+
 void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows, long ld_rows, int row_tiles,
                    int slabs64) {
     const int T = f.T, Qt = f.qpad / EGX_NB;
@@ -208,8 +240,12 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             g.tri = factor ? tri2 : 0;
             g.Mt = factor ? tri2 + Qt : row_tiles;
             g.Nt = tri2;
-            StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, sb);
-            launch_gemm_nt_sub(g, sb);
+            if (factor) {
+                trailing_syrk(env, g, sb);
+            } else {
+                StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, sb);
+                launch_gemm_nt_sub(g, sb);
+            }
             continue;
         }
         // look-ahead part: the next pair's two block columns, on the panel stream
@@ -233,8 +269,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             gb.tri = tri2 - 2;
             gb.Mt = tri2 - 2 + Qt;
             gb.Nt = tri2 - 2;
-            StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, sb);
-            launch_gemm_nt_sub(gb, sb);
+            trailing_syrk(env, gb, sb);
         }
         cudaEventRecord(env.ev_bulk[pair], sb);
     }

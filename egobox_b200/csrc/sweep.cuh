@@ -41,6 +41,11 @@ struct SweepEnv {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double* P2[2] = {nullptr, nullptr};   // double-buffered contiguous panel copies (rows x 128)
     long p_rows = 0;
+    // tcgen05 path of the trailing update (kernels_ozaki.cu): int8 slices + row scales of the current panel pair
+    int8_t* oz_S = nullptr;
+    double* oz_scale = nullptr;
+    int ozaki = 1;                        // EGX_OZAKI=0 keeps every update on the DMMA kernel
+    int ozaki_min_tri = 8;                // smallest trailing tile-triangle worth the slicing pass (EGX_OZAKI_MIN_TRI)
     int generation = 0;                   // bumped when a buffer captured in a CUDA graph is reallocated
     Profiler prof;
     int init(int max_block_cols);

@@ -178,7 +178,9 @@ int egx_gp_cross_correlation(egx_gp_ctx* ctx, const double* x, int m, double* c)
 #define EGX_STAGE_VAR_FINISH   7  /* row norms, u, variance                      */
 #define EGX_STAGE_SMALL_BATCH  8  /* one-CTA-per-theta small-n likelihood        */
 #define EGX_STAGE_GEMM_LOOKAHEAD 9 /* updates issued ahead on the panel stream (partner column, next pair's two columns) */
-#define EGX_NUM_STAGES         10
+#define EGX_STAGE_OZAKI_SLICE  10 /* fp64 panel pair -> row scales + 8 int8 slices (tcgen05 path)           */
+#define EGX_STAGE_OZAKI_SYRK   11 /* trailing SYRK update on tcgen05 (int8-sliced, UTCIMMA, TMEM accumulators) */
+#define EGX_NUM_STAGES         12
 int egx_gp_set_profiling(egx_gp_ctx* ctx, int enabled);
 int egx_gp_reset_profile(egx_gp_ctx* ctx);
 /* ms[EGX_NUM_STAGES], launches[EGX_NUM_STAGES] */

@@ -49,7 +49,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __host__ __device__ inline int tile_off(int r, int kb, int R) { return (kb >> 4) * R * 16 + r * 16 + (kb & 15); }
 
 template <int N>
-__global__ void __launch_bounds__(128) probe_kernel(const int8_t* A, const int8_t* B, int32_t* D, int reps, long long* cycles) {
+__global__ void __launch_bounds__(128) probe_kernel(const int8_t* A, const int8_t* B, int32_t* D, int reps, long long* cycles, int nacc) {
     extern __shared__ __align__(1024) unsigned char smem[];
     int8_t* sA = reinterpret_cast<int8_t*>(smem);              // 128 x 32
     int8_t* sB = sA + 128 * 32;                                // N x 32
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const int8_t* A, const int8_
     long long t0 = 0, t1 = 0;
     if (tid == 0) {
         t0 = clock64();
-        for (int r = 0; r < reps; ++r) mma_i8(tmem + (r & 1) * N, da, db, idesc, r >= 2 ? 1u : 0u);
+        for (int r = 0; r < reps; ++r) mma_i8(tmem + (r % nacc) * N, da, db, idesc, r >= nacc ? 1u : 0u);
         umma_commit(bar);
     }
     mbar_wait(bar, 0);
@@ -126,7 +126,7 @@ int run(int reps_time) {
     cudaMemcpy(dB, bt.data(), bt.size(), cudaMemcpyHostToDevice);
     const int smem = 128 * 32 + N * 32 + 64;
     // (1) correctness: reps = 1 -> D = A B^T
-    probe_kernel<N><<<1, 128, smem>>>(dA, dB, dD, 1, dC);
+    probe_kernel<N><<<1, 128, smem>>>(dA, dB, dD, 1, dC, 1);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         printf("N=%d: CUDA error %s\n", N, cudaGetErrorString(e));
@@ -146,12 +146,13 @@ int run(int reps_time) {
         }
     printf("N=%d: single MMA mismatches = %ld of %d\n", N, bad, 128 * N);
     // (2) timing: a chain of MMAs alternating between two accumulators
-    for (int reps : {reps_time, 2 * reps_time}) {
-        probe_kernel<N><<<1, 128, smem>>>(dA, dB, dD, reps, dC);
+    for (int nacc : {1, 2, 512 / N})
+    for (int reps : {reps_time}) {
+        probe_kernel<N><<<1, 128, smem>>>(dA, dB, dD, reps, dC, nacc);
         cudaDeviceSynchronize();
         long long cyc = 0;
         cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost);
-        printf("N=%d: %d MMAs (128x%dx32 int8) in %lld cycles = %.1f cycles/MMA, %.0f MAC/cycle/SM\n", N, reps, N, cyc,
+        printf("N=%d: %d MMAs (128x%dx32 int8) round-robin over %d accumulator(s) in %lld cycles = %.1f cycles/MMA, %.0f MAC/cycle/SM\n", N, reps, N, nacc, cyc,
                double(cyc) / reps, 128.0 * N * 32 * reps / double(cyc));
     }
     return bad != 0;
