@@ -82,7 +82,7 @@ int gemm_smem_bytes();
 size_t ozaki_slice_bytes(long rows);
 void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int8_t* S, cudaStream_t s);
 void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,
-                       long long* dbg = nullptr);
+                       long long* dbg = nullptr, int persist_hint = 0);
 // kernels_solve.cu
 void launch_gls(const double* M, long ld, int n, int npad, int p, double* work, double* G,
                 double* beta, double* rho, EvalResult* res, const int* info, cudaStream_t s);

@@ -399,6 +399,7 @@ int evaluate_collect(egx_gp_ctx* c, double* rlf_out) {
 
 int evaluate(egx_gp_ctx* c, const double* theta, double* rlf_out) {
     *rlf_out = NAN;
+    c->env.oz_persist = 0;
     int st = evaluate_launch(c, theta);
     if (st != EGX_OK) return st;
     return evaluate_collect(c, rlf_out);
@@ -727,6 +728,7 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
         }
         if (b < B) {
             rlf[b] = NAN;
+            w->env.oz_persist = (W > 1) ? 1 : 0;
             status[b] = evaluate_launch(w, thetas + static_cast<long>(b) * c->h);
             if (status[b] == EGX_CUDA_ERROR) return EGX_CUDA_ERROR;
             owner[b % W] = b;

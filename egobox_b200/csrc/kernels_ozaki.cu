@@ -43,7 +43,8 @@ constexpr int OZ_SLICE_STEP_BYTES = 128 * 32;    // one slice, one K step, 128 r
 constexpr int OZ_STAGE_OPERAND = OZ_SLOTS * OZ_SLICE_STEP_BYTES;    // 32 KB
 constexpr int OZ_STAGE_BYTES = 2 * OZ_STAGE_OPERAND;                // A + B
 constexpr int OZ_STAGES = 3;
-constexpr int OZ_THREADS = 352;                   // warp 0: A producer, 1: MMA issuer, 2..9: epilogue, 10: B producer
+constexpr int OZ_THREADS = 384;                   // warps 0..3: A producer, MMA issuer, B producer, idle; warps 4..11: epilogue
+constexpr int OZ_REGS_CTRL = 56, OZ_REGS_EPI = 216;   // setmaxnreg: 128 x 56 + 256 x 216 = 62464 <= 65536
 constexpr long OZ_RB_BYTES = static_cast<long>(OZ_KSTEPS) * OZ_STAGE_OPERAND;   // slices of one 128-row block: 256 KB
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -225,36 +226,48 @@ __device__ __forceinline__ double oz_i64_to_double(long long t) {
 // entries of C this thread owns: rows 32 quarter + 16 rh + r_in (+8), columns 64 chalf + 8 j + cq + {0, 1}.
 // rsA / rsB point at the row scales of this thread's first row / column; wscale = 256^-(w_last + 2).
 template <int NACC>
+__device__ __forceinline__ void oz_fold8(const uint32_t (&a)[NACC][8], int jj, const double* __restrict__ rsB, double sr0,
+                                         double sr1, double2 (&c0)[8], double2 (&c1)[8]) {
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+        const int j = 2 * jj + rep;
+        const double sc0 = rsB[8 * j], sc1 = rsB[8 * j + 1];
+        double d[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            long long t = static_cast<long long>(static_cast<int32_t>(a[0][4 * rep + e]));
+#pragma unroll
+            for (int gg = 1; gg < NACC; ++gg) t = t * 256LL + static_cast<long long>(static_cast<int32_t>(a[gg][4 * rep + e]));
+            d[e] = oz_i64_to_double(t);
+        }
+        c0[j].x = fma(-d[0], sr0 * sc0, c0[j].x);
+        c0[j].y = fma(-d[1], sr0 * sc1, c0[j].y);
+        c1[j].x = fma(-d[2], sr1 * sc0, c1[j].x);
+        c1[j].y = fma(-d[3], sr1 * sc1, c1[j].y);
+    }
+}
+// The TMEM loads of step i + 1 are in flight while step i is folded (two register sets).
+template <int NACC>
 __device__ __forceinline__ void oz_drain(uint32_t tmem, int quarter, int chalf, const double* __restrict__ rsA,
                                          const double* __restrict__ rsB, double wscale, double2 (&c)[2][2][8]) {
+    uint32_t a0[NACC][8], a1[NACC][8];
+    const uint32_t tbase = tmem + (static_cast<uint32_t>(32 * quarter) << 16) + 64 * chalf;
+    auto issue = [&](int step, uint32_t (&dst)[NACC][8]) {
+        const uint32_t taddr = tbase + (static_cast<uint32_t>(16 * (step >> 2)) << 16) + 16 * (step & 3);
 #pragma unroll
-    for (int rh = 0; rh < 2; ++rh) {
+        for (int gg = 0; gg < NACC; ++gg) oz_tmem_ld2(taddr + gg * 128, dst[gg]);
+    };
+    issue(0, a0);
+#pragma unroll
+    for (int step = 0; step < 8; step += 2) {
+        const int rh = step >> 2;
         const double sr0 = rsA[16 * rh] * wscale, sr1 = rsA[16 * rh + 8] * wscale;
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            uint32_t a[NACC][8];
-            const uint32_t taddr = tmem + (static_cast<uint32_t>(32 * quarter + 16 * rh) << 16) + 64 * chalf + 16 * jj;
-#pragma unroll
-            for (int gg = 0; gg < NACC; ++gg) oz_tmem_ld2(taddr + gg * 128, a[gg]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int rep = 0; rep < 2; ++rep) {
-                const int j = 2 * jj + rep;
-                const double sc0 = rsB[8 * j], sc1 = rsB[8 * j + 1];
-                double d[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    long long t = static_cast<long long>(static_cast<int32_t>(a[0][4 * rep + e]));
-#pragma unroll
-                    for (int gg = 1; gg < NACC; ++gg) t = t * 256LL + static_cast<long long>(static_cast<int32_t>(a[gg][4 * rep + e]));
-                    d[e] = oz_i64_to_double(t);
-                }
-                c[rh][0][j].x = fma(-d[0], sr0 * sc0, c[rh][0][j].x);
-                c[rh][0][j].y = fma(-d[1], sr0 * sc1, c[rh][0][j].y);
-                c[rh][1][j].x = fma(-d[2], sr1 * sc0, c[rh][1][j].x);
-                c[rh][1][j].y = fma(-d[3], sr1 * sc1, c[rh][1][j].y);
-            }
-        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        issue(step + 1, a1);
+        oz_fold8<NACC>(a0, step & 3, rsB, sr0, sr1, c[rh][0], c[rh][1]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (step + 2 < 8) issue(step + 2, a0);
+        oz_fold8<NACC>(a1, (step + 1) & 3, rsB, sr0, sr1, c[rh][0], c[rh][1]);
     }
 }
 
@@ -296,11 +309,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
     const uint32_t tmem = bars->tmem_base;
     if (tid == 0) OZ_STAMP(1);
 
-    if (warp == 0 || warp == 10) {
-        // ===== producers: warp 0 streams the A slices, warp 10 the B slices (bulk copies issued by one thread are
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OZ_REGS_CTRL));
+    if (warp == 0 || warp == 2) {
+        // ===== producers: warp 0 streams the A slices, warp 2 the B slices (bulk copies issued by one thread are
         // served one after the other, ~600 clocks each whatever their size; two threads run in parallel) =====
         if (lane == 0) {
-            const bool isB = warp == 10;
+            const bool isB = warp == 2;
             uint32_t n = 0;                                  // global K-step counter
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 int tr, tc;
@@ -343,9 +358,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                 }
             }
         }
+    }
     } else {
-        // ===== epilogue: 8 warps; lane quarter = warp % 4, column half = (warp - 2) / 4 =====
-        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(OZ_REGS_EPI));
+        // ===== epilogue: 8 warps; lane quarter = warp % 4, column half = (warp - 4) / 4 =====
+        const int quarter = warp & 3, chalf = (warp - 4) >> 2;
         const int r_in = lane >> 2, cq = 2 * (lane & 3);
         uint32_t P = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -356,35 +373,53 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                          64 * chalf + cq;
             const double* rsA = g.rscale + static_cast<long>(tr) * 128 + 32 * quarter + r_in;
             const double* rsB = g.rscale + static_cast<long>(tc) * 128 + 64 * chalf + cq;
-            double2 c[2][2][8];                              // [rh][row r_in / r_in + 8][j]
+            double2 c[2][2][8];                              // -(P P^T) of this thread's entries, [rh][row r_in / +8][j]
 #pragma unroll
             for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        c[rh][h][j] = *reinterpret_cast<const double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j);
+                    for (int j = 0; j < 8; ++j) c[rh][h][j] = make_double2(0.0, 0.0);
+            // pull this thread's share of the C tile into L2 now (HBM -> L2 only, no traffic into the SM): the
+            // read-modify-write after the second pass then sees L2 latency
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j));
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass, ++P) {
                 const double wscale = pass == 0 ? 9.094947017729282e-13 /* 256^-5 */ : 5.421010862427522e-20 /* 256^-8 */;
                 oz_mbar_wait(&bars->acc_full, P & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (tid == 64 && tile == blockIdx.x) OZ_STAMP(4 + 2 * pass);
+                if (tid == 128 && tile == blockIdx.x) OZ_STAMP(4 + 2 * pass);
                 if (pass == 0) oz_drain<4>(tmem, quarter, chalf, rsA, rsB, wscale, c);
                 else oz_drain<3>(tmem, quarter, chalf, rsA, rsB, wscale, c);
                 // all TMEM reads of this pass are complete: hand the accumulators back
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) oz_mbar_arrive(&bars->acc_empty);
-                if (tid == 64 && tile == blockIdx.x) OZ_STAMP(5 + 2 * pass);
+                if (tid == 128 && tile == blockIdx.x) OZ_STAMP(5 + 2 * pass);
             }
+            // C += c : the tile is read only now (its 128 KB would compete with the stage refills of pass 0), while the
+            // MMAs of the next tile are already running
 #pragma unroll
-            for (int rh = 0; rh < 2; ++rh)
+            for (int rh = 0; rh < 2; ++rh) {                 // two rows (16 loads in flight) at a time
+                double2 v[2][8];
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) = c[rh][h][j];
+                        v[h][j] = *reinterpret_cast<const double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) =
+                            make_double2(v[h][j].x + c[rh][h][j].x, v[h][j].y + c[rh][h][j].y);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -519,10 +554,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
     const uint32_t tmem = bars->tmem_base;
     if (tid == 0) OZ_STAMP(1);
 
-    if (warp == 0 || warp == 10) {
-        // ===== producers (both CTAs): warp 0 = own A rows, warp 10 = own half of the B rows =====
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OZ_REGS_CTRL));
+    if (warp == 0 || warp == 2) {
+        // ===== producers (both CTAs): warp 0 = own A rows, warp 2 = own half of the B rows =====
         if (lane == 0) {
-            const bool isB = warp == 10;
+            const bool isB = warp == 2;
             uint32_t n = 0;
             for (int w = cluster_id; w < nwork; w += nclusters) {
                 int a, tc;
@@ -586,9 +623,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
                 }
             }
         }
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(OZ_REGS_EPI));
         // ===== epilogue (both CTAs): rows of row block 2a + rank =====
-        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        const int quarter = warp & 3, chalf = (warp - 4) >> 2;
         const int r_in = lane >> 2, cq = 2 * (lane & 3);
         const uint32_t acc_empty_leader = oz_mapa(oz_smem_u32(&bars->acc_empty), 0);
         uint32_t P = 0;
@@ -608,29 +647,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        c[rh][h][j] = *reinterpret_cast<const double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j);
+                    for (int j = 0; j < 8; ++j) c[rh][h][j] = make_double2(0.0, 0.0);
+            // pull this thread's share of the C tile into L2 now (HBM -> L2 only, no traffic into the SM): the
+            // read-modify-write after the second pass then sees L2 latency
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j));
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass, ++P) {
                 const double wscale = pass == 0 ? 9.094947017729282e-13 /* 256^-5 */ : 5.421010862427522e-20 /* 256^-8 */;
                 oz_mbar_wait_cluster(&bars->acc_full, P & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (tid == 64 && w == cluster_id) OZ_STAMP(4 + 2 * pass);
+                if (tid == 128 && w == cluster_id) OZ_STAMP(4 + 2 * pass);
                 if (pass == 0) oz_drain<4>(tmem, quarter, chalf, rsA, rsB, wscale, c);
                 else oz_drain<3>(tmem, quarter, chalf, rsA, rsB, wscale, c);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) oz_remote_arrive(acc_empty_leader);
-                if (tid == 64 && w == cluster_id) OZ_STAMP(5 + 2 * pass);
+                if (tid == 128 && w == cluster_id) OZ_STAMP(5 + 2 * pass);
             }
             if (live) {
 #pragma unroll
-                for (int rh = 0; rh < 2; ++rh)
+                for (int rh = 0; rh < 2; ++rh) {
+                    double2 v[2][8];
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) = c[rh][h][j];
+                            v[h][j] = *reinterpret_cast<const double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) =
+                                make_double2(v[h][j].x + c[rh][h][j].x, v[h][j].y + c[rh][h][j].y);
+                }
             }
         }
     }
@@ -656,7 +711,7 @@ void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int
 
 // C (tile rows Mt, first `tri` triangular) -= P P^T from the slices of P
 void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,
-                       long long* dbg) {
+                       long long* dbg, int persist_hint) {
     static bool configured_dev[64] = {false};
     int dev_ = 0;
     cudaGetDevice(&dev_);
@@ -672,10 +727,13 @@ void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscal
     const int tiles = tri * (tri + 1) / 2 + (Mt - tri) * tri;
     if (tiles <= 0) return;
     OzakiArgs g{C, ldc, S, rscale, Mt, tri, dbg};
-    // EGX_OZAKI_PERSIST=1: a resident grid loops over the tiles (prefetch across tiles, no per-tile set-up) -- but it
-    // keeps the high-priority panel / look-ahead kernels of the sweep waiting for SMs; default: one work item per
-    // CTA (pair), so that they slip in between waves like they do with the DMMA kernel.
-    static const int persist = getenv("EGX_OZAKI_PERSIST") != nullptr ? atoi(getenv("EGX_OZAKI_PERSIST")) : 0;
+    // persistent: a resident grid loops over the tiles (prefetch across tiles, no per-tile set-up, the C update of a
+    // tile overlaps the MMAs of the next) -- but it keeps the high-priority panel / look-ahead kernels of the SAME
+    // factorisation waiting for SMs.  The sweep asks for it when several evaluations are in flight (the batched entry
+    // point: other evaluations fill the gaps; 4.39 -> 4.05 ms per evaluation at n = 8192) and not for a single one
+    // (6.9 vs 7.7 ms).  EGX_OZAKI_PERSIST=0/1 overrides.
+    static const int persist_env = getenv("EGX_OZAKI_PERSIST") != nullptr ? atoi(getenv("EGX_OZAKI_PERSIST")) : -1;
+    const int persist = persist_env >= 0 ? persist_env : persist_hint;
     static const int two_cta = getenv("EGX_OZAKI_2CTA") != nullptr ? atoi(getenv("EGX_OZAKI_2CTA")) : 0;
     if (two_cta) {
         int nwork = 0;

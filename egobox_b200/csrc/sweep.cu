@@ -132,7 +132,7 @@ static void trailing_syrk(SweepEnv& env, const GemmArgs& g, cudaStream_t st) {
             launch_ozaki_slice(g.A, g.lda, g.Mt * EGX_NB, env.oz_scale, env.oz_S, st);
         }
         StageScope sc(env.prof, EGX_STAGE_OZAKI_SYRK, 1, st);
-        launch_ozaki_syrk(g.C, g.ldc, env.oz_S, env.oz_scale, g.Mt, g.tri, st);
+        launch_ozaki_syrk(g.C, g.ldc, env.oz_S, env.oz_scale, g.Mt, g.tri, st, nullptr, env.oz_persist);
         return;
     }
     StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, st);

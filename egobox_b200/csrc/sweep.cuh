@@ -45,6 +45,7 @@ struct SweepEnv {
     int8_t* oz_S = nullptr;
     double* oz_scale = nullptr;
     int ozaki = 1;                        // EGX_OZAKI=0 keeps every update on the DMMA kernel
+    int oz_persist = 0;                   // set by the batched entry point: several evaluations share the GPU
     int ozaki_min_tri = 8;                // smallest trailing tile-triangle worth the slicing pass (EGX_OZAKI_MIN_TRI)
     int generation = 0;                   // bumped when a buffer captured in a CUDA graph is reallocated
     Profiler prof;

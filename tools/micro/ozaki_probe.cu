@@ -98,7 +98,7 @@ static int check_update(int Mt, int tri, bool timing_only, int reps) {
     long long* dbg;
     cudaMalloc(&dbg, 16 * 8);
     cudaMemset(dbg, 0, 16 * 8);
-    for (int r = 0; r < reps; ++r) launch_ozaki_syrk(dC, ldc, dS, dR, Mt, tri, 0, dbg);
+    for (int r = 0; r < reps; ++r) launch_ozaki_syrk(dC, ldc, dS, dR, Mt, tri, 0, dbg, 0);
     cudaEventRecord(e2);
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) {
