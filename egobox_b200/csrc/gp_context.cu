@@ -702,8 +702,13 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
     // measured (tools/batch_sweep.py): n = 8192 plateaus at 4 (6.68 ms per evaluation; 7.23 at 2, 6.69 at 8),
     // n = 4096 keeps improving to 8-12 (1.25 ms at 4, 1.08 at 6, 1.03 at 8 and 12); 12 also takes the 11
     // chains of a fit in one wave
-    int W = (c->npad <= 4096) ? 12 : 4;
+    // with the tcgen05 trailing update an evaluation is ~40 % less GPU work while its serial panel chain is unchanged:
+    // more evaluations in flight pay (n = 8192: 4.04 / 4.05 / 4.02 ms at W = 4 / 6 / 8 with look-ahead, 4.08 / 3.74 /
+    // 3.70 ms without -- the other evaluations hide the chain better than look-ahead does, and the whole K = 256
+    // update then goes through the tcgen05 kernel in one launch)
+    int W = (c->npad <= 4096) ? 12 : (c->env.ozaki ? 8 : 4);
     if (const char* e = getenv("EGX_BATCH_STREAMS")) W = std::max(1, atoi(e));
+    static const int batch_la = getenv("EGX_BATCH_LOOKAHEAD") != nullptr ? atoi(getenv("EGX_BATCH_LOOKAHEAD")) : -1;
     W = std::min(W, B);
     while (static_cast<int>(c->replicas.size()) < W - 1) {
         egx_gp_ctx* r = nullptr;
@@ -729,7 +734,11 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
         if (b < B) {
             rlf[b] = NAN;
             w->env.oz_persist = (W > 1) ? 1 : 0;
+            const bool la_saved = w->env.lookahead;
+            if (batch_la >= 0) w->env.lookahead = la_saved && batch_la != 0;
+            else if (W >= 6 && w->env.ozaki && c->npad > 4096) w->env.lookahead = false;
             status[b] = evaluate_launch(w, thetas + static_cast<long>(b) * c->h);
+            w->env.lookahead = la_saved;
             if (status[b] == EGX_CUDA_ERROR) return EGX_CUDA_ERROR;
             owner[b % W] = b;
         }

@@ -69,6 +69,7 @@ int SweepEnv::init(int max_block_cols) {
     lookahead = !(e != nullptr && atoi(e) == 0);
     if ((e = getenv("EGX_OZAKI")) != nullptr) ozaki = atoi(e);
     if ((e = getenv("EGX_OZAKI_MIN_TRI")) != nullptr) ozaki_min_tri = atoi(e) > 1 ? atoi(e) : 1;
+    if ((e = getenv("EGX_OZAKI_MIN_T")) != nullptr) ozaki_min_T = atoi(e);
     return EGX_OK;
 }
 
@@ -124,8 +125,8 @@ void SweepEnv::destroy() {
 // The K = 256 trailing update of the factorisation, C(tile rows Mt, first `tri` triangular) -= A A^T with A the
 // (Mt * 128) x 256 panel-pair rows: on tcgen05 through the int8 slices when the tile set is large enough to pay
 // for the slicing pass, else on the DMMA kernel.
-static void trailing_syrk(SweepEnv& env, const GemmArgs& g, cudaStream_t st) {
-    if (env.ozaki && env.oz_S != nullptr && g.tri >= env.ozaki_min_tri && g.K == 2 * EGX_NB && g.A == g.B &&
+static void trailing_syrk(SweepEnv& env, const GemmArgs& g, cudaStream_t st, int T) {
+    if (env.ozaki && env.oz_S != nullptr && T >= env.ozaki_min_T && g.tri >= env.ozaki_min_tri && g.K == 2 * EGX_NB && g.A == g.B &&
         g.lda == 2 * EGX_NB && static_cast<long>(g.Mt) * EGX_NB <= env.p_rows) {
         {
             StageScope sc(env.prof, EGX_STAGE_OZAKI_SLICE, 2, st);
@@ -241,7 +242,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             g.Mt = factor ? tri2 + Qt : row_tiles;
             g.Nt = tri2;
             if (factor) {
-                trailing_syrk(env, g, sb);
+                trailing_syrk(env, g, sb, T);
             } else {
                 StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, sb);
                 launch_gemm_nt_sub(g, sb);
@@ -269,7 +270,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             gb.tri = tri2 - 2;
             gb.Mt = tri2 - 2 + Qt;
             gb.Nt = tri2 - 2;
-            trailing_syrk(env, gb, sb);
+            trailing_syrk(env, gb, sb, T);
         }
         cudaEventRecord(env.ev_bulk[pair], sb);
     }
