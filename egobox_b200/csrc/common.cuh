@@ -75,12 +75,13 @@ void launch_mean_basis_rows(const double* X, int n, int npad, int d, const int* 
 // kernels_chol.cu
 void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* Dinv, cudaStream_t s);
 void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, long ldp,
-                      int nblocks64, cudaStream_t s);
+                      int nblocks64, cudaStream_t s, double* rmaxq = nullptr /* optional [row][4] quarter-row max |x|, see kernels_ozaki.cu */);
 void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s);
 int gemm_smem_bytes();
 // kernels_ozaki.cu: the trailing SYRK update on tcgen05 (int8-sliced fp64)
 size_t ozaki_slice_bytes(long rows);
-void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int8_t* S, cudaStream_t s);
+void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int8_t* S, cudaStream_t s,
+                        const double* rmaxq = nullptr /* [row][4] from the panel solves: no row-maximum pass */);
 void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,
                        long long* dbg = nullptr, int persist_hint = 0);
 // kernels_solve.cu

@@ -166,7 +166,8 @@ __device__ __forceinline__ void tr_cp_async16(void* smem_dst, const void* gsrc) 
 __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, long ldx,
                                                         const double* __restrict__ L, long ldl,
                                                         const double* __restrict__ Dinv,
-                                                        double* __restrict__ P, long ldp) {
+                                                        double* __restrict__ P, long ldp,
+                                                        double* __restrict__ rmaxq) {
     extern __shared__ __align__(16) double sm[];
     double* Xs = sm;                              // [64][132]
     double* Ds = Xs + TR_ROWS * TR_LDX;           // [4][32][36]
@@ -254,12 +255,20 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
         __syncthreads();        // X_b visible to the next block step
     }
     // panel copy for the trailing update: 128 columns of a (rows x ldp) buffer (ldp = 256: two panels side by side)
+    // rmaxq (optional): max |x| of every 64-column quarter of the solved rows, [row][2] at the caller's offset -- the
+    // row scales of the int8 slicing (kernels_ozaki.cu) then need no extra pass over the panel
     double* Pg = (P != nullptr) ? P + static_cast<long>(blockIdx.x) * TR_ROWS * ldp : nullptr;
     for (int e = tid; e < TR_ROWS * 64; e += 256) {
-        const int r = e >> 6, ch = e & 63;
+        const int r = e >> 6, ch = e & 63;        // a warp covers 64 consecutive columns of one row
         const double2 v = *reinterpret_cast<const double2*>(&Xs[r * TR_LDX + ch * 2]);
         *reinterpret_cast<double2*>(Xg + static_cast<long>(r) * ldx + ch * 2) = v;
         if (Pg != nullptr) *reinterpret_cast<double2*>(Pg + static_cast<long>(r) * ldp + ch * 2) = v;
+        if (rmaxq != nullptr) {
+            double mx = fmax(fabs(v.x), fabs(v.y));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) rmaxq[(static_cast<long>(blockIdx.x) * TR_ROWS + r) * 4 + (ch >> 5)] = mx;
+        }
     }
 }
 
@@ -525,7 +534,7 @@ void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* 
 }
 
 void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, long ldp,
-                      int nblocks64, cudaStream_t s) {
+                      int nblocks64, cudaStream_t s, double* rmaxq) {
     static bool configured_dev[64] = {false};
     int dev_ = 0;
     cudaGetDevice(&dev_);
@@ -536,7 +545,7 @@ void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const do
         configured = true;
     }
     if (nblocks64 <= 0) return;
-    trsm_rows_kernel<<<nblocks64, 256, smem, s>>>(X, ldx, Lkk, ldl, Dinv, P, ldp);
+    trsm_rows_kernel<<<nblocks64, 256, smem, s>>>(X, ldx, Lkk, ldl, Dinv, P, ldp, rmaxq);
 }
 
 static int gemm_env(const char* name, int dflt) {

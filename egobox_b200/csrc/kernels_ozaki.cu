@@ -144,11 +144,21 @@ __global__ void __launch_bounds__(256) ozaki_rowscale_kernel(const double* __res
 // thread = (row, 16-entry K chunk): 16 doubles in, 7 x 16 bytes out.
 // t = rint(x 2^56 / s) (|t| < 2^54); adding 0x80 to each of its 7 low bytes makes every byte the balanced digit + 128
 // with no borrows, so the digits are the bytes of (t + 0x00808080 80808080) XOR 0x80: byte j = digit 6 - j.
-__global__ void __launch_bounds__(128) ozaki_slice_kernel(const double* __restrict__ P, long ldp,
-                                                          const double* __restrict__ rscale, int8_t* __restrict__ S) {
+// rmaxq != nullptr: the row maxima come as four quarter-row values from the panel solves (trsm_rows_kernel) and the
+// scale is formed here (the chunk-0 block also stores it for the update kernel); else rscale is an input.
+__global__ void __launch_bounds__(128) ozaki_slice_kernel(const double* __restrict__ P, long ldp, double* __restrict__ rscale,
+                                                          const double* __restrict__ rmaxq, int8_t* __restrict__ S) {
     const int rb = blockIdx.x, chunk = blockIdx.y, rr = threadIdx.x;
     const long row = static_cast<long>(rb) * 128 + rr;
-    const double sc = rscale[row];
+    double sc;
+    if (rmaxq != nullptr) {
+        const double4 q = *reinterpret_cast<const double4*>(rmaxq + row * 4);
+        const double m = fmax(fmax(q.x, q.y), fmax(q.z, q.w));
+        sc = (m > 0.0 && m < 1.0e300) ? scalbn(1.0, ilogb(m) + 3) : 0.0;
+        if (chunk == 0) rscale[row] = sc;
+    } else {
+        sc = rscale[row];
+    }
     const double inv = sc > 0.0 ? 72057594037927936.0 / sc : 0.0;           // 2^56 / s
     const double* p = P + row * ldp + chunk * 16;
     uint32_t w[OZ_SLICES][4];
@@ -703,10 +713,11 @@ constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + static_cast<int>(size
 size_t ozaki_slice_bytes(long rows) { return static_cast<size_t>(rows / 128) * OZ_RB_BYTES; }
 
 // P: rows x 256 (ldp), rows a multiple of 128 -> rscale[rows], S
-void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int8_t* S, cudaStream_t s) {
+void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int8_t* S, cudaStream_t s,
+                        const double* rmaxq) {
     if (rows <= 0) return;
-    ozaki_rowscale_kernel<<<(rows + 7) / 8, 256, 0, s>>>(P, ldp, rows, rscale);
-    ozaki_slice_kernel<<<dim3(rows / 128, OZ_K / 16), 128, 0, s>>>(P, ldp, rscale, S);
+    if (rmaxq == nullptr) ozaki_rowscale_kernel<<<(rows + 7) / 8, 256, 0, s>>>(P, ldp, rows, rscale);
+    ozaki_slice_kernel<<<dim3(rows / 128, OZ_K / 16), 128, 0, s>>>(P, ldp, rscale, rmaxq, S);
 }
 
 // C (tile rows Mt, first `tri` triangular) -= P P^T from the slices of P

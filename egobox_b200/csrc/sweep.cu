@@ -84,9 +84,14 @@ int SweepEnv::ensure_panel_rows(long rows) {
     egx_dev_free(oz_scale);
     oz_S = nullptr;
     oz_scale = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        egx_dev_free(oz_rmaxq[i]);
+        oz_rmaxq[i] = nullptr;
+    }
     if (ozaki) {
         EGX_CUDA_TRY(egx_dev_malloc(&oz_S, ozaki_slice_bytes(rows)));
         EGX_CUDA_TRY(egx_dev_malloc(&oz_scale, static_cast<size_t>(rows) * sizeof(double)));
+        for (int i = 0; i < 2; ++i) EGX_CUDA_TRY(egx_dev_malloc(&oz_rmaxq[i], static_cast<size_t>(rows) * 4 * sizeof(double)));
     }
     p_rows = rows;
     ++generation;
@@ -109,6 +114,10 @@ void SweepEnv::destroy() {
     egx_dev_free(oz_scale);
     oz_S = nullptr;
     oz_scale = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        egx_dev_free(oz_rmaxq[i]);
+        oz_rmaxq[i] = nullptr;
+    }
     if (sp) cudaStreamDestroy(sp);
     if (sb) cudaStreamDestroy(sb);
     sb = sp = nullptr;
@@ -125,12 +134,12 @@ void SweepEnv::destroy() {
 // The K = 256 trailing update of the factorisation, C(tile rows Mt, first `tri` triangular) -= A A^T with A the
 // (Mt * 128) x 256 panel-pair rows: on tcgen05 through the int8 slices when the tile set is large enough to pay
 // for the slicing pass, else on the DMMA kernel.
-static void trailing_syrk(SweepEnv& env, const GemmArgs& g, cudaStream_t st, int T) {
+static void trailing_syrk(SweepEnv& env, const GemmArgs& g, cudaStream_t st, int T, const double* rmaxq) {
     if (env.ozaki && env.oz_S != nullptr && T >= env.ozaki_min_T && g.tri >= env.ozaki_min_tri && g.K == 2 * EGX_NB && g.A == g.B &&
         g.lda == 2 * EGX_NB && static_cast<long>(g.Mt) * EGX_NB <= env.p_rows) {
         {
-            StageScope sc(env.prof, EGX_STAGE_OZAKI_SLICE, 2, st);
-            launch_ozaki_slice(g.A, g.lda, g.Mt * EGX_NB, env.oz_scale, env.oz_S, st);
+            StageScope sc(env.prof, EGX_STAGE_OZAKI_SLICE, rmaxq ? 1 : 2, st);
+            launch_ozaki_slice(g.A, g.lda, g.Mt * EGX_NB, env.oz_scale, env.oz_S, st, rmaxq);
         }
         StageScope sc(env.prof, EGX_STAGE_OZAKI_SYRK, 1, st);
         launch_ozaki_syrk(g.C, g.ldc, env.oz_S, env.oz_scale, g.Mt, g.tri, st, nullptr, env.oz_persist);
@@ -155,6 +164,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
     for (int k = 0; k < T; k += 2) {
         const int pair = k >> 1;
         double* Pw = env.P2[pair & 1];                 // rows x 256; factor: row 0 = first row of block k+1
+        double* Rq = (factor && env.ozaki) ? env.oz_rmaxq[pair & 1] : nullptr;   // quarter-row maxima, same row origin
         const bool two = (k + 1 < T);
         // ---- panel A (block column k) -----------------------------------------------------------------
         if (factor) {
@@ -166,7 +176,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             if (rows_below > 0) {
                 StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
                 launch_trsm_rows(blk(k + 1, k), ld, blk(k, k), ld, f.Dinv + static_cast<long>(k) * 4096, Pw, LDP,
-                                 rows_below / 64, sp);
+                                 rows_below / 64, sp, Rq);
             }
         } else {
             StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
@@ -210,7 +220,8 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             if (rows_below > 0) {
                 StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
                 launch_trsm_rows(blk(k + 2, k + 1), ld, blk(k + 1, k + 1), ld, f.Dinv + static_cast<long>(k + 1) * 4096,
-                                 Pw + static_cast<long>(EGX_NB) * LDP + EGX_NB, LDP, rows_below / 64, sp);
+                                 Pw + static_cast<long>(EGX_NB) * LDP + EGX_NB, LDP, rows_below / 64, sp,
+                                 Rq ? Rq + static_cast<long>(EGX_NB) * 4 + 2 : nullptr);
             }
         } else {
             StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
@@ -242,7 +253,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             g.Mt = factor ? tri2 + Qt : row_tiles;
             g.Nt = tri2;
             if (factor) {
-                trailing_syrk(env, g, sb, T);
+                trailing_syrk(env, g, sb, T, Rq ? Rq + static_cast<long>(EGX_NB) * 4 : nullptr);
             } else {
                 StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, sb);
                 launch_gemm_nt_sub(g, sb);
@@ -270,7 +281,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             gb.tri = tri2 - 2;
             gb.Mt = tri2 - 2 + Qt;
             gb.Nt = tri2 - 2;
-            trailing_syrk(env, gb, sb, T);
+            trailing_syrk(env, gb, sb, T, Rq ? Rq + static_cast<long>(3 * EGX_NB) * 4 : nullptr);
         }
         cudaEventRecord(env.ev_bulk[pair], sb);
     }

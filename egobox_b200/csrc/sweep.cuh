@@ -44,6 +44,7 @@ struct SweepEnv {
     // tcgen05 path of the trailing update (kernels_ozaki.cu): int8 slices + row scales of the current panel pair
     int8_t* oz_S = nullptr;
     double* oz_scale = nullptr;
+    double* oz_rmaxq[2] = {nullptr, nullptr};   // [row][4] quarter-row maxima written by the panel solves, per P2 buffer
     int ozaki = 1;                        // EGX_OZAKI=0 keeps every update on the DMMA kernel
     int oz_persist = 0;                   // set by the batched entry point: several evaluations share the GPU
     int ozaki_min_tri = 8;                // smallest trailing tile-triangle worth the slicing pass (EGX_OZAKI_MIN_TRI)

@@ -91,8 +91,10 @@ def test_c2_factorisation_checksum_and_interpolation(c2):
 
 
 def test_c2_idempotence_and_batch(c2):
-    """Re-evaluation is bit-identical; the batched entry point (4 workspaces in flight) returns the single-call
-    values bit for bit (same kernels, same order of operations)."""
+    """Re-evaluation is bit-identical, and so are equal candidates inside a batch.  The batched entry point
+    (up to 8 workspaces in flight, no look-ahead: every K = 256 update through the tcgen05 kernel) and the single
+    call (look-ahead: the next pair's two block columns are updated by the DMMA kernel) may round differently in
+    the last bit."""
     ctx, theta = c2["ctx"], c2["theta"]
     st1, a = ctx.reduced_likelihood(theta)
     st2, b = ctx.reduced_likelihood(theta)
@@ -100,9 +102,9 @@ def test_c2_idempotence_and_batch(c2):
     thetas = np.tile(theta, (6, 1)) * np.array([1.0, 0.7, 1.3, 1.0, 2.0, 0.7])[:, None]
     st, rl = ctx.reduced_likelihood_batch(thetas)
     assert np.all(st == 0)
-    assert rl[0] == a and rl[3] == a and rl[1] == rl[5]
+    assert rl[0] == rl[3] and rl[1] == rl[5] and rl[0] == pytest.approx(a, rel=1e-13)
     for k in (1, 2, 4):
-        assert ctx.reduced_likelihood(thetas[k])[1] == rl[k]
+        assert ctx.reduced_likelihood(thetas[k])[1] == pytest.approx(rl[k], rel=1e-13)
 
 
 def test_c2_linearity_in_y(c2):

@@ -1,6 +1,6 @@
 #!/bin/bash
 export PYTHONUNBUFFERED=1
-echo "== new tests"; timeout 600 python -m pytest tests/test_gpu_ozaki.py -q -p no:cacheprovider --timeout 300 2>&1 | tail -15
-for n in 2048 2560 3072 3584; do for oz in 0 1; do
-  echo "== n=$n EGX_OZAKI=$oz (MIN_T=1)"; EGX_OZAKI_MIN_T=1 EGX_OZAKI=$oz timeout 200 python tools/batch_sweep.py $n 96 2>&1 | tail -1 | cut -c1-200
-done; done
+echo "== tests"; timeout 900 python -m pytest tests/test_gpu_ozaki.py tests/test_gpu_parity.py tests/test_gpu_fullsize.py -q -p no:cacheprovider --timeout 300 2>&1 | tail -8
+echo "== batch 8192"; timeout 200 python tools/batch_sweep.py 8192 48 2>&1 | tail -1
+echo "== probe 8192"; timeout 300 python tools/gpu_probe.py 8192 2>&1 | grep -v predict_valvar | cut -c1-900
+echo "== sanitize target (plain)"; timeout 300 python tools/sanitize_target.py 2>&1 | tail -6

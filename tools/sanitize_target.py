@@ -22,3 +22,22 @@ ctx = eg.SgpContext(X, Y, X[:140].copy(), corr=eg.MATERN32, method=eg.SparseMeth
 st, res = ctx.finalize([1.5, 1.0], 0.8, 0.02, want_inv=True)
 v = ctx.predict_var(X[:100])
 print("sparse ok", st, res["likelihood"], float(v.mean()))
+# tcgen05 trailing update (13 block columns -> sliced launches in the look-ahead and in the batched form)
+from tools._util import make_problem, make_context   # noqa: E402
+xo, yo = make_problem(1664, 3, seed=1)
+cto = make_context(xo, yo, eg.MATERN52, eg.CONSTANT)
+cto.set_profiling(True)
+st, rl = cto.reduced_likelihood(np.full(3, 1.0))
+stb, rlb = cto.reduced_likelihood_batch(np.full((3, 3), 1.0) * np.array([[0.9], [1.0], [1.1]]))
+print("tcgen05 ok", st, rl, stb.tolist(), cto.profile()["ozaki_syrk"][1])
+cto.close()
+# mixture of experts on the device (responsibilities, hard / smooth recombination, gradients) + KPLS fit
+xm = rng.random((160, 2))
+ym = np.where(xm[:, 0] < 0.5, np.sin(4 * xm).sum(axis=1), 3.0 + (xm ** 2).sum(axis=1))
+for rec in (eg.Recombination.HARD, eg.Recombination.SMOOTH):
+    gpx = eg.Gpx.builder(n_clusters=2, recombination=rec, n_start=1, seed=1).fit(xm, ym)
+    xq = rng.random((50, 2))
+    print("moe ok", rec, float(gpx.predict(xq).mean()), float(gpx.predict_var(xq).mean()),
+          float(np.abs(gpx.predict_gradients(xq)).mean()), float(np.abs(gpx.predict_var_gradients(xq)).mean()))
+gk = eg.GaussianProcess.params(eg.ConstantMean, eg.SquaredExponentialCorr).kpls_dim(2).n_start(1).fit(rng.random((80, 5)), rng.random(80))
+print("kpls ok", gk.theta().tolist())
