@@ -35,6 +35,9 @@ SIGNATURES = {
     "egx_gp_reduced_likelihood": (C.c_int, [_vp, _dp, _dp]),
     "egx_gp_reduced_likelihood_batch": (C.c_int, [_vp, _dp, C.c_int, _dp, _ip]),
     "egx_gp_finalize": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "egx_gp_async_slots": (C.c_int, [_vp, C.c_int]),
+    "egx_gp_eval_begin": (C.c_int, [_vp, C.c_int, _dp]),
+    "egx_gp_eval_end": (C.c_int, [_vp, C.c_int, _dp]),
     "egx_gp_reduced_likelihood_grad": (C.c_int, [_vp, _dp, C.c_double, _dp, _dp]),
     "egx_gp_download_chol": (C.c_int, [_vp, _dp]),
     "egx_gp_predict": (C.c_int, [_vp, _dp, C.c_int, _dp]),

@@ -146,6 +146,7 @@ struct egx_gp_ctx {
     int graph_nterms = -1, graph_generation = -1;
     bool graph_lookahead = false, use_graphs = true;
     long long graph_launches[EGX_NUM_STAGES] = {0};
+    int async_slots = 0;         // workspaces handed out by egx_gp_async_slots
     long long direct_evals = 0;
     std::mutex mu;
 };
@@ -744,6 +745,61 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
         }
     }
     return EGX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Asynchronous seam for independent optimiser chains (the rayon fan-out of gp/src/algorithm.rs:928-945 runs every
+// chain on its own): `slots` workspaces, each holding at most one evaluation in flight; a chain whose evaluation is
+// back proposes its next theta while the evaluations of the other chains are still running, so there is no
+// per-iteration barrier across chains.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int egx_gp_async_slots(egx_gp_ctx* c, int wanted) {
+    if (!c || wanted < 1) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (cudaSetDevice(c->device) != cudaSuccess) return 0;
+    if (small_path_ok(c)) return 0;               // one CTA per theta: a lock-step batch is one launch, keep it
+    int W = (c->npad <= 4096) ? 12 : (c->env.ozaki ? 8 : 4);
+    if (const char* e = getenv("EGX_BATCH_STREAMS")) W = std::max(1, atoi(e));
+    W = std::min(W, wanted);
+    while (static_cast<int>(c->replicas.size()) < W - 1) {
+        egx_gp_ctx* r = nullptr;
+        const int st = egx_gp_create(&r, c->device, c->corr, c->mean, c->xnorm_h.data(), c->n, c->d, c->ynorm_h.data(),
+                                     c->x_mean_h.data(), c->x_std_h.data(), c->y_mean, c->y_std, c->w_star.data(),
+                                     c->h, c->nugget);
+        if (st != EGX_OK) return static_cast<int>(c->replicas.size()) + 1;
+        r->env.prof.on = c->env.prof.on;
+        c->replicas.push_back(r);
+    }
+    c->async_slots = W;
+    return W;
+}
+
+extern "C" int egx_gp_eval_begin(egx_gp_ctx* c, int slot, const double* theta) {
+    if (!c || !theta || slot < 0 || slot >= c->async_slots) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    egx_gp_ctx* w = slot == 0 ? c : c->replicas[slot - 1];
+    static const int batch_la = getenv("EGX_BATCH_LOOKAHEAD") != nullptr ? atoi(getenv("EGX_BATCH_LOOKAHEAD")) : -1;
+    const int W = c->async_slots;
+    w->env.oz_persist = (W > 1) ? 1 : 0;
+    const bool la_saved = w->env.lookahead;
+    if (batch_la >= 0) w->env.lookahead = la_saved && batch_la != 0;
+    else if (W >= 6 && w->env.ozaki && c->npad > 4096) w->env.lookahead = false;
+    const int st = evaluate_launch(w, theta);
+    w->env.lookahead = la_saved;
+    return st;
+}
+
+extern "C" int egx_gp_eval_end(egx_gp_ctx* c, int slot, double* rlf) {
+    if (!c || !rlf || slot < 0 || slot >= c->async_slots) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    egx_gp_ctx* w = slot == 0 ? c : c->replicas[slot - 1];
+    if (!w->pending_eval) {
+        egx_set_error("egx_gp_eval_end: no evaluation in flight on slot %d", slot);
+        return EGX_INVALID_VALUE;
+    }
+    return evaluate_collect(w, rlf);
 }
 
 extern "C" int egx_gp_reduced_likelihood_grad(egx_gp_ctx* c, const double* theta, double rel_step, double* rlf,

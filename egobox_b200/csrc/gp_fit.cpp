@@ -674,6 +674,63 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
             chains.reserve(starts.size());
             for (auto& s0 : starts) chains.emplace_back(s0, lo, hi, prm->cobyla_rhobeg, prm->cobyla_ftol_rel, maxeval);
 
+            auto theta_of = [&](const std::vector<double>& z) {
+                std::vector<double> th = theta0;
+                for (int i = 0; i < na; ++i) th[active[i]] = std::pow(10.0, z[i]);
+                return th;
+            };
+            static const bool lockstep_forced = getenv("EGX_FIT_LOCKSTEP") != nullptr && atoi(getenv("EGX_FIT_LOCKSTEP")) != 0;
+            const int slots = lockstep_forced ? 0 : egx_gp_async_slots(m->ctx, static_cast<int>(chains.size()));
+            if (slots >= 2) {
+                // Independent chains, as in the reference (one rayon task per start): `slots` evaluations stay in
+                // flight; whenever the oldest one is back its chain is told the value and asks for the next theta,
+                // which goes out on the same slot at once.  Every chain sees exactly the sequence it would see alone.
+                std::vector<int> chain_of(slots, -1);          // slot -> chain with an evaluation in flight
+                std::vector<char> busy(chains.size(), 0);
+                size_t next_chain = 0;
+                int head = 0, in_flight = 0;
+                auto feed = [&](int slot) -> int {
+                    for (size_t tries = 0; tries < chains.size(); ++tries) {
+                        const size_t ci = (next_chain + tries) % chains.size();
+                        if (busy[ci] || chains[ci].done()) continue;
+                        const std::vector<double> th = theta_of(chains[ci].ask());
+                        const int s1 = egx_gp_eval_begin(m->ctx, slot, th.data());
+                        if (s1 == EGX_CUDA_ERROR) return s1;
+                        m->n_evals += 1;
+                        if (s1 != EGX_OK) {                      // rejected before launch (invalid theta): Err(_) -> +inf
+                            chains[ci].tell(kInf);
+                            --tries;
+                            continue;
+                        }
+                        busy[ci] = 1;
+                        chain_of[slot] = static_cast<int>(ci);
+                        next_chain = ci + 1;
+                        ++in_flight;
+                        return EGX_OK;
+                    }
+                    chain_of[slot] = -1;
+                    return EGX_OK;
+                };
+                for (int sl = 0; sl < slots; ++sl) {
+                    st = feed(sl);
+                    if (st != EGX_OK) return st;
+                }
+                while (in_flight > 0) {
+                    while (chain_of[head] < 0) head = (head + 1) % slots;
+                    const int ci = chain_of[head];
+                    double v = NAN;
+                    const int s2 = egx_gp_eval_end(m->ctx, head, &v);
+                    if (s2 == EGX_CUDA_ERROR) return s2;
+                    --in_flight;
+                    busy[ci] = 0;
+                    double f = (s2 == EGX_OK) ? -v : kInf;      // Err(_) -> +inf, algorithm.rs:893-896
+                    if (std::isnan(f)) f = kInf;                // optimization.rs:157-161
+                    chains[ci].tell(f);
+                    st = feed(head);                            // the slot is free again: next chain in line
+                    if (st != EGX_OK) return st;
+                    head = (head + 1) % slots;
+                }
+            } else {
             std::vector<double> thetas, rlf;
             std::vector<int> status, who;
             for (;;) {
@@ -681,9 +738,7 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
                 who.clear();
                 for (size_t c = 0; c < chains.size(); ++c) {
                     if (chains[c].done()) continue;
-                    const std::vector<double>& z = chains[c].ask();
-                    std::vector<double> th = theta0;
-                    for (int i = 0; i < na; ++i) th[active[i]] = std::pow(10.0, z[i]);
+                    const std::vector<double> th = theta_of(chains[c].ask());
                     thetas.insert(thetas.end(), th.begin(), th.end());
                     who.push_back(static_cast<int>(c));
                 }
@@ -700,6 +755,7 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
                     if (std::isnan(f)) f = kInf;
                     chains[who[b]].tell(f);
                 }
+            }
             }
             // reduce (algorithm.rs:942-945): first strictly smaller wins, default theta = 1 (log10 = 0)
             double fbest = kInf;

@@ -43,6 +43,8 @@ constexpr int OZ_SLICE_STEP_BYTES = 128 * 32;    // one slice, one K step, 128 r
 constexpr int OZ_STAGE_OPERAND = OZ_SLOTS * OZ_SLICE_STEP_BYTES;    // 32 KB
 constexpr int OZ_STAGE_BYTES = 2 * OZ_STAGE_OPERAND;                // A + B
 constexpr int OZ_STAGES = 3;
+constexpr int OZ_CSTG_ROW = 1088;                 // staging row pitch (128 doubles + 64 B: conflict-free 16-byte stores)
+constexpr int OZ_CSTG_BYTES = 32 * OZ_CSTG_ROW;   // 32 rows of the C update staged for cp.reduce.async.bulk
 constexpr int OZ_THREADS = 384;                   // warps 0..3: A producer, MMA issuer, B producer, idle; warps 4..11: epilogue
 constexpr int OZ_REGS_CTRL = 56, OZ_REGS_EPI = 216;   // setmaxnreg: 128 x 56 + 256 x 216 = 62464 <= 65536
 constexpr long OZ_RB_BYTES = static_cast<long>(OZ_KSTEPS) * OZ_STAGE_OPERAND;   // slices of one 128-row block: 256 KB
@@ -207,6 +209,7 @@ struct OzakiArgs {
     const double* rscale;     // 2^e per panel row
     int Mt, tri;              // tile rows; the first `tri` rows are triangular (c <= r), the others full (c < tri)
     long long* dbg;           // OZ_TIMING builds (tools/micro/ozaki_probe.cu): clock64 stamps of CTA 0
+    int c_reduce;             // 1: C += c through shared memory + cp.reduce.async.bulk (no read of C); 0: load / add / store
 };
 #ifdef OZ_TIMING
 #define OZ_STAMP(slot) do { if (blockIdx.x == 0 && g.dbg) g.dbg[slot] = clock64(); } while (0)
@@ -294,7 +297,8 @@ __device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint3
 // updated in registers after each pass and stored once.
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiArgs g) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
-    OzBarriers* bars = reinterpret_cast<OzBarriers*>(oz_smem + OZ_STAGES * OZ_STAGE_BYTES);
+    unsigned char* cstg = oz_smem + OZ_STAGES * OZ_STAGE_BYTES;
+    OzBarriers* bars = reinterpret_cast<OzBarriers*>(cstg + OZ_CSTG_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri;
     if (tid == 0) OZ_STAMP(0);
@@ -392,13 +396,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                     for (int j = 0; j < 8; ++j) c[rh][h][j] = make_double2(0.0, 0.0);
             // pull this thread's share of the C tile into L2 now (HBM -> L2 only, no traffic into the SM): the
             // read-modify-write after the second pass then sees L2 latency
+            if (!g.c_reduce) {
 #pragma unroll
-            for (int rh = 0; rh < 2; ++rh)
+                for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int j = 0; j < 8; j += 2)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j));
+                        for (int j = 0; j < 8; j += 2)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j));
+            }
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass, ++P) {
                 const double wscale = pass == 0 ? 9.094947017729282e-13 /* 256^-5 */ : 5.421010862427522e-20 /* 256^-8 */;
@@ -413,6 +419,34 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                 if (lane == 0) oz_mbar_arrive(&bars->acc_empty);
                 if (tid == 128 && tile == blockIdx.x) OZ_STAMP(5 + 2 * pass);
             }
+            if (g.c_reduce) {
+                // C += c without reading C: 32 rows at a time go through shared memory and leave as one
+                // cp.reduce.async.bulk (.add.f64, SASS UBLKRED) per row -- the adds happen in L2, nothing comes back
+#pragma unroll 1
+                for (int qq = 0; qq < 4; ++qq) {
+                    if (quarter == qq) {
+#pragma unroll
+                        for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    *reinterpret_cast<double2*>(cstg + (16 * rh + 8 * h + r_in) * OZ_CSTG_ROW +
+                                                                (64 * chalf + 8 * j + cq) * 8) = c[rh][h][j];
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (warp == 4) {
+                        double* dst = g.C + (static_cast<long>(tr) * 128 + 32 * qq + lane) * g.ldc + static_cast<long>(tc) * 128;
+                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst),
+                                     "r"(oz_smem_u32(cstg + lane * OZ_CSTG_ROW)), "r"(1024)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+            } else {
             // C += c : the tile is read only now (its 128 KB would compete with the stage refills of pass 0), while the
             // MMAs of the next tile are already running
 #pragma unroll
@@ -429,6 +463,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) =
                             make_double2(v[h][j].x + c[rh][h][j].x, v[h][j].y + c[rh][h][j].y);
+            }
             }
         }
     }
@@ -705,7 +740,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
-constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + static_cast<int>(sizeof(OzBarriers));
+constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_CSTG_BYTES + static_cast<int>(sizeof(OzBarriers));
 
 }  // namespace
 
@@ -737,7 +772,8 @@ void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscal
     if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_);
     const int tiles = tri * (tri + 1) / 2 + (Mt - tri) * tri;
     if (tiles <= 0) return;
-    OzakiArgs g{C, ldc, S, rscale, Mt, tri, dbg};
+    static const int c_reduce = getenv("EGX_OZAKI_CRED") != nullptr ? atoi(getenv("EGX_OZAKI_CRED")) : 0;   // measured: same tile rate as load / add / store (the 128 row reductions of a tile serialise in the TMA unit)
+    OzakiArgs g{C, ldc, S, rscale, Mt, tri, dbg, c_reduce};
     // persistent: a resident grid loops over the tiles (prefetch across tiles, no per-tile set-up, the C update of a
     // tile overlaps the MMAs of the next) -- but it keeps the high-priority panel / look-ahead kernels of the SAME
     // factorisation waiting for SMs.  The sweep asks for it when several evaluations are in flight (the batched entry

@@ -148,6 +148,15 @@ int egx_gp_covariance(egx_gp_ctx* ctx, const double* x, int m, double* cov);
 #define EGX_SAMPLE_EIGENVALUES 1
 int egx_gp_sample(egx_gp_ctx* ctx, const double* x, int m, const double* z, int n_traj, int method, double* out);
 
+/* Asynchronous form for INDEPENDENT optimiser chains -- the reference runs its n_start + 1 COBYLA chains on rayon
+ * threads, each calling reduced_likelihood on its own (gp/src/algorithm.rs:928-945).  egx_gp_async_slots prepares up
+ * to `wanted` workspaces and returns how many there are (0: use the batched call -- small problems run a whole batch
+ * as one launch); a slot holds at most one evaluation in flight: egx_gp_eval_begin enqueues it and returns,
+ * egx_gp_eval_end waits for it and returns the status / value of egx_gp_reduced_likelihood. */
+int egx_gp_async_slots(egx_gp_ctx* ctx, int wanted);
+int egx_gp_eval_begin(egx_gp_ctx* ctx, int slot, const double* theta);
+int egx_gp_eval_end(egx_gp_ctx* ctx, int slot, double* rlf);
+
 /* Same, with x / y / var already resident on the context's device (device
  * pointers).  Used to time the kernels without the PCIe copies. */
 int egx_gp_predict_valvar_dev(egx_gp_ctx* ctx, const double* x_dev, int m,
