@@ -84,6 +84,8 @@ void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int
                         const double* rmaxq = nullptr /* [row][4] from the panel solves: no row-maximum pass */);
 void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,
                        long long* dbg = nullptr, int persist_hint = 0);
+void launch_ozaki_gemm(double* C, long ldc, const int8_t* SA, const double* rsA, const int8_t* SB, const double* rsB, int Mt,
+                       int Nt, cudaStream_t s, int persist_hint = 0);
 // kernels_solve.cu
 void launch_gls(const double* M, long ld, int n, int npad, int p, double* work, double* G,
                 double* beta, double* rho, EvalResult* res, const int* info, cudaStream_t s);

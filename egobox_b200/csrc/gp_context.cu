@@ -147,6 +147,11 @@ struct egx_gp_ctx {
     bool graph_lookahead = false, use_graphs = true;
     long long graph_launches[EGX_NUM_STAGES] = {0};
     int async_slots = 0;         // workspaces handed out by egx_gp_async_slots
+    // int8 digit slices of L for the multi-RHS solve of predict_var on tcgen05 (built lazily after a finalize)
+    int8_t* Lsl = nullptr;
+    double* Lsc = nullptr;
+    std::vector<long> Lsl_off, Lsc_off;
+    bool Lslices_ready = false;
     long long direct_evals = 0;
     std::mutex mu;
 };
@@ -359,6 +364,7 @@ int capture_eval_graph(egx_gp_ctx* c) {
 int evaluate_launch(egx_gp_ctx* c, const double* theta) {
     c->trained = false;
     c->grad_ready = false;
+    c->Lslices_ready = false;
     c->pending_eval = false;
     int st = build_terms_host(c, theta);
     if (st != EGX_OK) return st;
@@ -425,6 +431,36 @@ int ensure_predict_buffers(egx_gp_ctx* c, int mb) {
 
 constexpr int PREDICT_CHUNK = 8192;
 
+// Slices of the block rows of L below every column pair (the B operand of the solve updates), once per trained model:
+// as many bytes as the lower triangle of L itself (268 MB at n = 8192), ~1 ms to build.
+int ensure_L_slices(egx_gp_ctx* c) {
+    if (c->Lslices_ready) return EGX_OK;
+    const int T = c->npad / EGX_NB;
+    if (!c->env.ozaki || T < c->env.ozaki_min_T || T - 2 < c->env.ozaki_min_tri) return EGX_OK;
+    if (c->Lsl == nullptr) {
+        long bytes = 0, rows = 0;
+        c->Lsl_off.assign((T + 1) / 2, 0);
+        c->Lsc_off.assign((T + 1) / 2, 0);
+        for (int k = 0; k + 2 < T; k += 2) {
+            c->Lsl_off[k >> 1] = bytes;
+            c->Lsc_off[k >> 1] = rows;
+            bytes += static_cast<long>(ozaki_slice_bytes(static_cast<long>(T - k - 2) * EGX_NB));
+            rows += static_cast<long>(T - k - 2) * EGX_NB;
+        }
+        EGX_CUDA_TRY(egx_dev_malloc(&c->Lsl, static_cast<size_t>(bytes)));
+        EGX_CUDA_TRY(egx_dev_malloc(&c->Lsc, static_cast<size_t>(rows) * sizeof(double)));
+    }
+    for (int k = 0; k + 2 < T; k += 2) {
+        const int rows_k = (T - k - 2) * EGX_NB;
+        if (rows_k / EGX_NB < c->env.ozaki_min_tri) break;
+        StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SLICE, 2, c->stream);
+        launch_ozaki_slice(c->M + static_cast<long>(k + 2) * EGX_NB * c->ld + static_cast<long>(k) * EGX_NB, c->ld, rows_k,
+                           c->Lsc + c->Lsc_off[k >> 1], c->Lsl + c->Lsl_off[k >> 1], c->stream);
+    }
+    c->Lslices_ready = true;
+    return EGX_OK;
+}
+
 // One chunk of <= mb_alloc points whose raw inputs are at x_dev (device).
 int predict_chunk_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, double* var_dev, double* c_out_dev) {
     const int mpad = round_up(m, EGX_NB);
@@ -442,7 +478,18 @@ int predict_chunk_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, 
                                        static_cast<size_t>(c->n) * sizeof(double), m, cudaMemcpyDeviceToDevice,
                                        c->stream));
     if (!want_var) return EGX_OK;
-    blocked_sweep(c->env, factor_ref(c), false, c->Y, c->npad, mpad / EGX_NB, mpad / 64);
+    FactorRef fr = factor_ref(c);
+    if (mpad / EGX_NB >= 8) {                      // enough rows for full waves of 128 x 128 tiles
+        const int stl = ensure_L_slices(c);
+        if (stl != EGX_OK) return stl;
+        if (c->Lslices_ready) {
+            fr.Lsl = c->Lsl;
+            fr.Lsc = c->Lsc;
+            fr.Lsl_off = c->Lsl_off.data();
+            fr.Lsc_off = c->Lsc_off.data();
+        }
+    }
+    blocked_sweep(c->env, fr, false, c->Y, c->npad, mpad / EGX_NB, mpad / 64);
     {
         StageScope sc(c->env.prof, EGX_STAGE_VAR_FINISH, 1, c->stream);
         launch_var_finish(c->Y, c->npad, m, c->npad, x_dev, c->x_mean, c->x_std, c->d,
@@ -499,6 +546,10 @@ int predict_impl(egx_gp_ctx* c, const double* x, int m, double* y, double* var, 
 
 void free_ctx(egx_gp_ctx* c) {
     if (!c) return;
+    egx_dev_free(c->Lsl);
+    egx_dev_free(c->Lsc);
+    c->Lsl = nullptr;
+    c->Lsc = nullptr;
     for (egx_gp_ctx* r : c->replicas) free_ctx(r);
     c->replicas.clear();
     cudaSetDevice(c->device);

@@ -104,7 +104,14 @@ __device__ __forceinline__ void oz_tmem_ld(uint32_t addr, uint32_t (&v)[16]) {
         : "r"(addr));
 }
 
-__device__ __forceinline__ void oz_tile_decode(int t, int tri, int& r, int& c) {
+// tri > 0: lower-triangular tile set (+ full rows below); tri == 0: Mt x Nt rectangle, row index fastest (consecutive
+// CTAs share the B slices)
+__device__ __forceinline__ void oz_tile_decode(int t, int tri, int Mt, int& r, int& c) {
+    if (tri == 0) {
+        c = t / Mt;
+        r = t - c * Mt;
+        return;
+    }
     const int ntri = tri * (tri + 1) / 2;
     if (t < ntri) {
         int rr = static_cast<int>((sqrtf(8.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f);
@@ -208,6 +215,9 @@ struct OzakiArgs {
     const int8_t* S;          // slices of the panel rows; row block 0 = first tile row / column of C
     const double* rscale;     // 2^e per panel row
     int Mt, tri;              // tile rows; the first `tri` rows are triangular (c <= r), the others full (c < tri)
+    const int8_t* SB;         // tri == 0 (rectangular Mt x Nt product C -= A B^T): slices / scales of the B rows
+    const double* rscaleB;
+    int Nt;
     long long* dbg;           // OZ_TIMING builds (tools/micro/ozaki_probe.cu): clock64 stamps of CTA 0
     int c_reduce;             // 1: C += c through shared memory + cp.reduce.async.bulk (no read of C); 0: load / add / store
 };
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
     unsigned char* cstg = oz_smem + OZ_STAGES * OZ_STAGE_BYTES;
     OzBarriers* bars = reinterpret_cast<OzBarriers*>(cstg + OZ_CSTG_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntiles = g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri;
+    const int ntiles = g.tri > 0 ? g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri : g.Mt * g.Nt;
     if (tid == 0) OZ_STAMP(0);
 
     if (tid == 0) {
@@ -333,8 +343,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
             uint32_t n = 0;                                  // global K-step counter
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 int tr, tc;
-                oz_tile_decode(tile, g.tri, tr, tc);
-                const int8_t* Sg = g.S + static_cast<long>(isB ? tc : tr) * OZ_RB_BYTES;
+                oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
+                const int8_t* Sg = isB ? g.SB + static_cast<long>(tc) * OZ_RB_BYTES : g.S + static_cast<long>(tr) * OZ_RB_BYTES;
                 for (int it = 0; it < 2 * OZ_KSTEPS; ++it, ++n) {
                     const uint32_t stage = n % OZ_STAGES, round = n / OZ_STAGES;
                     const int pass = it / OZ_KSTEPS, ks = it % OZ_KSTEPS;
@@ -381,12 +391,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
         uint32_t P = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             int tr, tc;
-            oz_tile_decode(tile, g.tri, tr, tc);
+            oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
             // this thread's entries: rows 32 quarter + 16 rh + r_in (+8), columns 64 chalf + 8 j + cq + {0,1}
             double* Cb = g.C + (static_cast<long>(tr) * 128 + 32 * quarter + r_in) * g.ldc + static_cast<long>(tc) * 128 +
                          64 * chalf + cq;
             const double* rsA = g.rscale + static_cast<long>(tr) * 128 + 32 * quarter + r_in;
-            const double* rsB = g.rscale + static_cast<long>(tc) * 128 + 64 * chalf + cq;
+            const double* rsB = g.rscaleB + static_cast<long>(tc) * 128 + 64 * chalf + cq;
             double2 c[2][2][8];                              // -(P P^T) of this thread's entries, [rh][row r_in / +8][j]
 #pragma unroll
             for (int rh = 0; rh < 2; ++rh)
@@ -755,9 +765,10 @@ void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int
     ozaki_slice_kernel<<<dim3(rows / 128, OZ_K / 16), 128, 0, s>>>(P, ldp, rscale, rmaxq, S);
 }
 
-// C (tile rows Mt, first `tri` triangular) -= P P^T from the slices of P
-void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,
-                       long long* dbg, int persist_hint) {
+// C -= A B^T from the slices of A (SA, rsA) and of B (SB, rsB).  tri > 0: SYRK form (B = A), lower-triangular tile set
+// with Mt - tri full tile rows below; tri == 0: rectangular Mt x Nt.
+static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rsA, const int8_t* SB, const double* rsB, int Mt,
+                         int Nt, int tri, cudaStream_t s, long long* dbg, int persist_hint) {
     static bool configured_dev[64] = {false};
     int dev_ = 0;
     cudaGetDevice(&dev_);
@@ -770,10 +781,10 @@ void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscal
     static int sm_count_dev[64] = {0};
     int& sms = sm_count_dev[dev_ & 63];
     if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_);
-    const int tiles = tri * (tri + 1) / 2 + (Mt - tri) * tri;
+    const int tiles = tri > 0 ? tri * (tri + 1) / 2 + (Mt - tri) * tri : Mt * Nt;
     if (tiles <= 0) return;
     static const int c_reduce = getenv("EGX_OZAKI_CRED") != nullptr ? atoi(getenv("EGX_OZAKI_CRED")) : 0;   // measured: same tile rate as load / add / store (the 128 row reductions of a tile serialise in the TMA unit)
-    OzakiArgs g{C, ldc, S, rscale, Mt, tri, dbg, c_reduce};
+    OzakiArgs g{C, ldc, SA, rsA, Mt, tri, SB, rsB, Nt, dbg, c_reduce};
     // persistent: a resident grid loops over the tiles (prefetch across tiles, no per-tile set-up, the C update of a
     // tile overlaps the MMAs of the next) -- but it keeps the high-priority panel / look-ahead kernels of the SAME
     // factorisation waiting for SMs.  The sweep asks for it when several evaluations are in flight (the batched entry
@@ -782,7 +793,7 @@ void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscal
     static const int persist_env = getenv("EGX_OZAKI_PERSIST") != nullptr ? atoi(getenv("EGX_OZAKI_PERSIST")) : -1;
     const int persist = persist_env >= 0 ? persist_env : persist_hint;
     static const int two_cta = getenv("EGX_OZAKI_2CTA") != nullptr ? atoi(getenv("EGX_OZAKI_2CTA")) : 0;
-    if (two_cta) {
+    if (two_cta && tri > 0) {
         int nwork = 0;
         for (int a = 0; 2 * a < Mt; ++a) nwork += (2 * a + 2 < tri) ? 2 * a + 2 : tri;
         const int clusters = (persist && nwork > sms / 2) ? sms / 2 : nwork;
@@ -791,4 +802,16 @@ void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscal
     }
     const int grid = (persist && tiles > sms) ? sms : tiles;
     ozaki_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g);
+}
+
+void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,
+                       long long* dbg, int persist_hint) {
+    ozaki_launch(C, ldc, S, rscale, S, rscale, Mt, tri, tri, s, dbg, persist_hint);
+}
+
+// rectangular: C (Mt x Nt tiles) -= A B^T ; the multi-RHS triangular solve of predict_var (A = solved rows of the point
+// chunk, B = block rows of L, sliced once per model)
+void launch_ozaki_gemm(double* C, long ldc, const int8_t* SA, const double* rsA, const int8_t* SB, const double* rsB, int Mt,
+                       int Nt, cudaStream_t s, int persist_hint) {
+    ozaki_launch(C, ldc, SA, rsA, SB, rsB, Mt, Nt, 0, s, nullptr, persist_hint);
 }

@@ -164,7 +164,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
     for (int k = 0; k < T; k += 2) {
         const int pair = k >> 1;
         double* Pw = env.P2[pair & 1];                 // rows x 256; factor: row 0 = first row of block k+1
-        double* Rq = (factor && env.ozaki) ? env.oz_rmaxq[pair & 1] : nullptr;   // quarter-row maxima, same row origin
+        double* Rq = (env.ozaki && (factor || f.Lsl != nullptr)) ? env.oz_rmaxq[pair & 1] : nullptr;   // quarter-row maxima, same row origin as Pw
         const bool two = (k + 1 < T);
         // ---- panel A (block column k) -----------------------------------------------------------------
         if (factor) {
@@ -181,7 +181,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
         } else {
             StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
             launch_trsm_rows(rows + static_cast<long>(k) * EGX_NB, ld_rows, blk(k, k), ld,
-                             f.Dinv + static_cast<long>(k) * 4096, Pw, LDP, slabs64, sp);
+                             f.Dinv + static_cast<long>(k) * 4096, Pw, LDP, slabs64, sp, Rq);
         }
         if (!two) break;
         const int tri1 = T - k - 1;                    // block columns right of k
@@ -226,7 +226,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
         } else {
             StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
             launch_trsm_rows(rows + static_cast<long>(k + 1) * EGX_NB, ld_rows, blk(k + 1, k + 1), ld,
-                             f.Dinv + static_cast<long>(k + 1) * 4096, Pw + EGX_NB, LDP, slabs64, sp);
+                             f.Dinv + static_cast<long>(k + 1) * 4096, Pw + EGX_NB, LDP, slabs64, sp, Rq ? Rq + 2 : nullptr);
         }
         const int tri2 = T - k - 2;                    // block columns right of the pair
         if (la) cudaEventRecord(env.ev_panel[pair], sp);
@@ -254,6 +254,17 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             g.Nt = tri2;
             if (factor) {
                 trailing_syrk(env, g, sb, T, Rq ? Rq + static_cast<long>(EGX_NB) * 4 : nullptr);
+            } else if (f.Lsl != nullptr && env.ozaki && env.oz_S != nullptr && T >= env.ozaki_min_T && tri2 >= env.ozaki_min_tri &&
+                       static_cast<long>(row_tiles) * EGX_NB <= env.p_rows) {
+                // multi-RHS solve on tcgen05: rows[:, (k+2)..] -= Pw L[(k+2).., pair]^T with the slices of L made once per
+                // model and the slices of the freshly solved rows made here
+                {
+                    StageScope sc(env.prof, EGX_STAGE_OZAKI_SLICE, 1, sb);
+                    launch_ozaki_slice(Pw, LDP, row_tiles * EGX_NB, env.oz_scale, env.oz_S, sb, Rq);
+                }
+                StageScope sc(env.prof, EGX_STAGE_OZAKI_SYRK, 1, sb);
+                launch_ozaki_gemm(g.C, g.ldc, env.oz_S, env.oz_scale, f.Lsl + f.Lsl_off[pair], f.Lsc + f.Lsc_off[pair], row_tiles,
+                                  tri2, sb, 1);
             } else {
                 StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, sb);
                 launch_gemm_nt_sub(g, sb);

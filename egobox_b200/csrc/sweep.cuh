@@ -66,6 +66,12 @@ struct FactorRef {
     int qpad;
     double* Dinv;   // [T][4][32][32]
     int* info;
+    // optional (solves only): int8 digit slices + row scales of the block rows of L below every column PAIR, in the
+    // layout of kernels_ozaki.cu; pair p = block columns 2p, 2p+1 starts at Lsl + Lsl_off[p] bytes / Lsc + Lsc_off[p]
+    const int8_t* Lsl = nullptr;
+    const double* Lsc = nullptr;
+    const long* Lsl_off = nullptr;
+    const long* Lsc_off = nullptr;
 };
 
 // factor = true : in-place Cholesky of f.M (+ appended rows become (L^-1 B)^T)
