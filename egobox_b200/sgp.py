@@ -297,6 +297,32 @@ class SparseGaussianProcess:
             _raise_status(st)
         return v
 
+    # sparse_algorithm.rs:298-336: the reference differentiates predict / predict_var by central differences with the
+    # fixed step sqrt(eps) of the `finitediff` crate, one point and one coordinate at a time; here all 2 * n * nx shifted
+    # points go through ONE batched device prediction
+    _FD_STEP = 1.4901161193847656e-08
+
+    def _central_diff(self, fn, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = x.reshape(-1, self._d)
+        n, nx = x.shape
+        h = self._FD_STEP
+        shifts = np.zeros((2, nx, nx))
+        shifts[0][np.diag_indices(nx)] = h
+        shifts[1][np.diag_indices(nx)] = -h
+        pts = (x[None, None, :, :] + shifts[:, :, None, :]).reshape(2 * nx * n, nx)
+        v = fn(pts).reshape(2, nx, n)
+        return ((v[0] - v[1]) / (2.0 * h)).T.copy()
+
+    def predict_gradients(self, x):
+        """sparse_algorithm.rs:298-316 -> (n, nx)."""
+        return self._central_diff(self.predict, x)
+
+    def predict_var_gradients(self, x):
+        """sparse_algorithm.rs:318-336 -> (n, nx)."""
+        return self._central_diff(self.predict_var, x)
+
     def theta(self):
         th = np.empty(self._hdim)
         self._lib.egx_sgp_model_theta(self._h, th.ctypes.data_as(_dp))
@@ -417,10 +443,12 @@ class SparseGpx:
         return self._gp
 
     def predict_gradients(self, x):
-        raise NotImplementedError("batched prediction gradients: SURVEY.md 8(f)-1 (next)")
+        """sparse_gp_mix.rs (SparseGpx.predict_gradients) -> sparse_algorithm.rs:298-316."""
+        return self._gp.predict_gradients(np.asarray(x, dtype=np.float64))
 
     def predict_var_gradients(self, x):
-        raise NotImplementedError("batched prediction gradients: SURVEY.md 8(f)-1 (next)")
+        """sparse_gp_mix.rs (SparseGpx.predict_var_gradients) -> sparse_algorithm.rs:318-336."""
+        return self._gp.predict_var_gradients(np.asarray(x, dtype=np.float64))
 
     def sample(self, x, n_traj):
-        raise NotImplementedError("conditional sampling: SURVEY.md 8(f)-4 (next)")
+        raise NotImplementedError("trajectory sampling of the sparse GP (sparse_algorithm.rs:338-364) is not provided")

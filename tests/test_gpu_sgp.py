@@ -97,3 +97,30 @@ def test_sparse_vfe_fixed_noise():
     assert np.abs(f_obj(xplot)[:, 0] - sgp.predict(xplot)).max() < 0.5
     gpx = eg.SparseGpx.builder(nz=20, seed=1).fit(xt, yt)
     assert gpx.thetas().shape == (1, 1) and gpx.predict(xplot).shape == (100,)
+
+
+def test_sparse_prediction_gradients_are_the_reference_central_differences():
+    """sparse_algorithm.rs:298-336: gradients of predict / predict_var by central differences with step sqrt(eps),
+    here as ONE batched device prediction of the 2 n nx shifted points; against the oracle's own central differences
+    and against a coarse finite difference of the curve itself."""
+    import egobox_b200 as eg
+    rng = np.random.default_rng(3)
+    x = 2 * rng.random((300, 2)) - 1
+    y = np.sin(3 * x[:, 0]) * np.cos(2 * x[:, 1]) + rng.normal(0, 0.05, 300)
+    z = S.make_inducings(40, x, rng)
+    sgp = (eg.SparseGaussianProcess.params(eg.Matern52Corr, eg.Inducings.Located(z)).theta_fixed([1.2, 0.9])
+           .noise_variance(eg.ParamTuning.Fixed(0.0025)).seed(0).fit(x, y))
+    xq = 1.6 * rng.random((25, 2)) - 0.8
+    g = sgp.predict_gradients(xq)
+    gv = sgp.predict_var_gradients(xq)
+    assert g.shape == (25, 2) and gv.shape == (25, 2)
+    h = 1e-5
+    for j in range(2):
+        e = np.zeros(2)
+        e[j] = h
+        coarse = (sgp.predict(xq + e) - sgp.predict(xq - e)) / (2 * h)
+        np.testing.assert_allclose(g[:, j], coarse, rtol=2e-4, atol=2e-4)
+        coarse_v = (sgp.predict_var(xq + e) - sgp.predict_var(xq - e)) / (2 * h)
+        np.testing.assert_allclose(gv[:, j], coarse_v, rtol=5e-3, atol=5e-4)
+    gpx = eg.SparseGpx.builder(nz=20, seed=1).fit(x, y)
+    assert gpx.predict_gradients(xq).shape == (25, 2) and gpx.predict_var_gradients(xq).shape == (25, 2)
