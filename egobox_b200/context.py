@@ -81,6 +81,19 @@ class GpContext:
             self._h, _ptr(th), B, _ptr(rlf), status.ctypes.data_as(C.POINTER(C.c_int))))
         return status, rlf
 
+    # asynchronous seam: independent chains, one slot each (egx_gp_async_slots / eval_begin / eval_end)
+    def async_slots(self, wanted):
+        return int(self._lib.egx_gp_async_slots(self._h, int(wanted)))
+
+    def eval_begin(self, slot, theta):
+        th = _f64(theta).reshape(-1)
+        return int(self._lib.egx_gp_eval_begin(self._h, int(slot), _ptr(th)))
+
+    def eval_end(self, slot):
+        out = C.c_double()
+        st = int(self._lib.egx_gp_eval_end(self._h, int(slot), C.byref(out)))
+        return st, out.value
+
     def reduced_likelihood_grad(self, theta, rel_step=1e-6):
         """-> (status, rlf, d rlf / d theta) by one batch of 2h+1 evaluations (central differences)."""
         th = _f64(theta).reshape(-1)

@@ -843,13 +843,18 @@ extern "C" int egx_gp_eval_begin(egx_gp_ctx* c, int slot, const double* theta) {
 
 extern "C" int egx_gp_eval_end(egx_gp_ctx* c, int slot, double* rlf) {
     if (!c || !rlf || slot < 0 || slot >= c->async_slots) return EGX_INVALID_VALUE;
-    std::lock_guard<std::mutex> lk(c->mu);
-    EGX_CUDA_TRY(cudaSetDevice(c->device));
-    egx_gp_ctx* w = slot == 0 ? c : c->replicas[slot - 1];
-    if (!w->pending_eval) {
-        egx_set_error("egx_gp_eval_end: no evaluation in flight on slot %d", slot);
-        return EGX_INVALID_VALUE;
+    egx_gp_ctx* w = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        w = slot == 0 ? c : c->replicas[slot - 1];
+        if (!w->pending_eval) {
+            egx_set_error("egx_gp_eval_end: no evaluation in flight on slot %d", slot);
+            return EGX_INVALID_VALUE;
+        }
     }
+    // the wait happens OUTSIDE the context lock: a slot is touched by one caller at a time (contract), and the
+    // threads that own the other slots must be able to enqueue meanwhile (one rayon worker per slot)
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
     return evaluate_collect(w, rlf);
 }
 

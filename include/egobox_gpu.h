@@ -152,7 +152,8 @@ int egx_gp_sample(egx_gp_ctx* ctx, const double* x, int m, const double* z, int 
  * threads, each calling reduced_likelihood on its own (gp/src/algorithm.rs:928-945).  egx_gp_async_slots prepares up
  * to `wanted` workspaces and returns how many there are (0: use the batched call -- small problems run a whole batch
  * as one launch); a slot holds at most one evaluation in flight: egx_gp_eval_begin enqueues it and returns,
- * egx_gp_eval_end waits for it and returns the status / value of egx_gp_reduced_likelihood. */
+ * egx_gp_eval_end waits for it and returns the status / value of egx_gp_reduced_likelihood.  Different slots may be
+ * driven from different threads concurrently (one rayon worker per slot); one slot, one caller at a time. */
 int egx_gp_async_slots(egx_gp_ctx* ctx, int wanted);
 int egx_gp_eval_begin(egx_gp_ctx* ctx, int slot, const double* theta);
 int egx_gp_eval_end(egx_gp_ctx* ctx, int slot, double* rlf);

@@ -255,3 +255,37 @@ def test_sparse_kpls_fit_runs():
     assert np.asarray(sgp.theta()).shape == (2,)
     err = np.linalg.norm(sgp.predict(x) - y) / np.linalg.norm(y)
     assert err < 0.2
+
+
+def test_async_evaluation_seam_from_threads():
+    """egx_gp_async_slots / egx_gp_eval_begin / egx_gp_eval_end: independent chains, one slot per thread (what a
+    rayon worker of gp/src/algorithm.rs:928-945 would do); values equal the plain reduced_likelihood call."""
+    import threading
+    import egobox_b200 as eg
+    from tests.gpu_util import make_problem, make_context
+    x, y = make_problem(700, 4, seed=2)
+    ctx, _ = make_context(x, y, eg.MATERN52, eg.CONSTANT)
+    slots = ctx.async_slots(4)
+    assert slots == 4
+    thetas = np.full((4, 5, 4), 1.0) * np.linspace(0.5, 1.5, 20).reshape(4, 5, 1)
+    got = np.zeros((4, 5))
+
+    def chain(slot):
+        for i in range(5):
+            assert ctx.eval_begin(slot, thetas[slot, i]) == 0
+            st, v = ctx.eval_end(slot)
+            assert st == 0
+            got[slot, i] = v
+
+    ts = [threading.Thread(target=chain, args=(s,)) for s in range(slots)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for s in range(4):
+        for i in range(5):
+            st, v = ctx.reduced_likelihood(thetas[s, i])
+            assert st == 0 and got[s, i] == pytest.approx(v, rel=1e-12)
+    st, _ = ctx.eval_end(0)
+    assert st == 4                      # nothing in flight: EGX_INVALID_VALUE
+    ctx.close()
