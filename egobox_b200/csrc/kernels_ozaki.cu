@@ -86,6 +86,17 @@ __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
 // instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = 128
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(128 >> 3) << 17) |
                               (static_cast<uint32_t>(128 >> 4) << 24);
+// same with N = 256: the B descriptor then spans TWO adjacent digit slices (a slice slot is exactly 16 row groups x 256 B, so
+// slice q+1 continues the row-group stride of slice q) and the result lands in two adjacent accumulators
+constexpr uint32_t OZ_IDESC_N256 = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(256 >> 3) << 17) |
+                                   (static_cast<uint32_t>(128 >> 4) << 24);
+__device__ __forceinline__ void oz_mma_n256(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(OZ_IDESC_N256), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -220,6 +231,7 @@ struct OzakiArgs {
     int Nt;
     long long* dbg;           // OZ_TIMING builds (tools/micro/ozaki_probe.cu): clock64 stamps of CTA 0
     int c_reduce;             // 1: C += c through shared memory + cp.reduce.async.bulk (no read of C); 0: load / add / store
+    int prod3;                // 1: one producer thread per ring stage (both operands); 0: one per operand
 };
 #ifdef OZ_TIMING
 #define OZ_STAMP(slot) do { if (blockIdx.x == 0 && g.dbg) g.dbg[slot] = clock64(); } while (0)
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
 
     if (tid == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) {
-            oz_mbar_init(&bars->full[s], 2);
+            oz_mbar_init(&bars->full[s], g.prod3 ? 1 : 2);
             oz_mbar_init(&bars->empty[s], 1);
         }
         oz_mbar_init(&bars->acc_full, 1);
@@ -335,10 +347,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OZ_REGS_CTRL));
-    if (warp == 0 || warp == 2) {
-        // ===== producers: warp 0 streams the A slices, warp 2 the B slices (bulk copies issued by one thread are
-        // served one after the other, ~600 clocks each whatever their size; two threads run in parallel) =====
-        if (lane == 0) {
+    if (warp != 1 && !g.prod3) {
+        // ===== producers, one per operand: warp 0 streams the A slices, warp 2 the B slices =====
+        if (lane == 0 && warp != 3) {
             const bool isB = warp == 2;
             uint32_t n = 0;                                  // global K-step counter
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -354,6 +365,32 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                     oz_bulk_g2s(oz_smem + stage * OZ_STAGE_BYTES + (isB ? OZ_STAGE_OPERAND : 0),
                                 Sg + static_cast<long>(ks) * OZ_STAGE_OPERAND, bytes, &bars->full[stage]);
                 }
+            }
+        }
+    } else if (warp != 1) {
+        // ===== producers: warps 0, 2, 3 (lane 0).  Bulk copies issued by ONE thread are served one after the other
+        // (600 clk each on an idle chip, 1000-1300 in the steady state of this kernel, whatever their size), so every
+        // stage of the ring has its own producer thread, which loads both operands of its K steps: three K steps in
+        // flight.  (Three lanes of one warp do NOT work: their mbarrier spin loops serialise inside the warp.) =====
+        if (lane == 0) {
+            const uint32_t stage = warp == 0 ? 0u : static_cast<uint32_t>(warp - 1);     // warps 0, 2, 3 -> stages 0, 1, 2
+            const int my_tiles = ntiles > static_cast<int>(blockIdx.x) ? (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+            const uint32_t total = static_cast<uint32_t>(my_tiles) * 2 * OZ_KSTEPS;
+            for (uint32_t n = stage; n < total; n += OZ_STAGES) {      // global K-step counter; n % OZ_STAGES == stage
+                const int tile = static_cast<int>(blockIdx.x) + static_cast<int>(n / (2 * OZ_KSTEPS)) * static_cast<int>(gridDim.x);
+                const int it = static_cast<int>(n % (2 * OZ_KSTEPS));
+                int tr, tc;
+                oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
+                const uint32_t round = n / OZ_STAGES;
+                const int pass = it / OZ_KSTEPS, ks = it % OZ_KSTEPS;
+                const uint32_t bytes = (pass == 0 ? 4 : OZ_SLICES) * OZ_SLICE_STEP_BYTES;
+                oz_mbar_wait(&bars->empty[stage], (round & 1) ^ 1);
+                oz_mbar_expect_tx(&bars->full[stage], 2 * bytes);
+                unsigned char* st = oz_smem + stage * OZ_STAGE_BYTES;
+                oz_bulk_g2s(st, g.S + static_cast<long>(tr) * OZ_RB_BYTES + static_cast<long>(ks) * OZ_STAGE_OPERAND, bytes,
+                            &bars->full[stage]);
+                oz_bulk_g2s(st + OZ_STAGE_OPERAND, g.SB + static_cast<long>(tc) * OZ_RB_BYTES + static_cast<long>(ks) * OZ_STAGE_OPERAND,
+                            bytes, &bars->full[stage]);
             }
         }
     } else if (warp == 1) {
@@ -372,6 +409,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (P == 0 && ks == 0) OZ_STAMP(2);
                         if (P == 1 && ks == 0) OZ_STAMP(3);
+                        if (P == 2 && ks == 0) OZ_STAMP(15);
+                        if (P == 2 && ks == 7) OZ_STAMP(16);
+                        if (P == 3 && ks == 0) OZ_STAMP(17);
                         const uint32_t sa = oz_smem_u32(oz_smem + stage * OZ_STAGE_BYTES);
                         const uint32_t sb = sa + OZ_STAGE_OPERAND;
                         if (pass == 0) oz_issue_kstep<0, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sb, ks > 0 ? 1u : 0u);
@@ -421,6 +461,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                 oz_mbar_wait(&bars->acc_full, P & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tid == 128 && tile == blockIdx.x) OZ_STAMP(4 + 2 * pass);
+                if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(10 + 2 * pass);
                 if (pass == 0) oz_drain<4>(tmem, quarter, chalf, rsA, rsB, wscale, c);
                 else oz_drain<3>(tmem, quarter, chalf, rsA, rsB, wscale, c);
                 // all TMEM reads of this pass are complete: hand the accumulators back
@@ -428,6 +469,29 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                 __syncwarp();
                 if (lane == 0) oz_mbar_arrive(&bars->acc_empty);
                 if (tid == 128 && tile == blockIdx.x) OZ_STAMP(5 + 2 * pass);
+                if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(11 + 2 * pass);
+                if (pass == 0 && !g.c_reduce) {
+                    // c = C - (pass-0 part): the tile is READ here, while the 144 MMAs of pass 1 run and these warps
+                    // would only wait (pass 1 is bound by the shared-memory port, not by the L2 -> SM path); after the
+                    // second pass only the store is left.  Read at the start of the tile it would compete with the stage
+                    // refills of pass 0, read after pass 1 it lands on the next tile's pass 0 (measured: 12 k clk each).
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh) {             // two rows (16 loads in flight) at a time
+                        double2 v[2][8];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                v[h][j] = *reinterpret_cast<const double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                c[rh][h][j].x += v[h][j].x;
+                                c[rh][h][j].y += v[h][j].y;
+                            }
+                    }
+                }
             }
             if (g.c_reduce) {
                 // C += c without reading C: 32 rows at a time go through shared memory and leave as one
@@ -457,24 +521,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
             } else {
-            // C += c : the tile is read only now (its 128 KB would compete with the stage refills of pass 0), while the
-            // MMAs of the next tile are already running
 #pragma unroll
-            for (int rh = 0; rh < 2; ++rh) {                 // two rows (16 loads in flight) at a time
-                double2 v[2][8];
+                for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        v[h][j] = *reinterpret_cast<const double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j);
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) =
-                            make_double2(v[h][j].x + c[rh][h][j].x, v[h][j].y + c[rh][h][j].y);
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) = c[rh][h][j];
             }
-            }
+            if (tid == 128 && tile == blockIdx.x) OZ_STAMP(9);
+            if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(14);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -553,17 +609,35 @@ template <int PASS, int B_SLICE_BYTES, bool TWO_CTA>
 __device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint32_t sb, uint32_t not_first_ks) {
     const uint64_t da0 = oz_desc(sa), db0 = oz_desc(sb);
     constexpr int W0 = PASS * 4, NW = PASS == 0 ? 4 : 3;
+    if constexpr (TWO_CTA) {
 #pragma unroll
-    for (int gg = 0; gg < NW; ++gg) {
+        for (int gg = 0; gg < NW; ++gg) {
+#pragma unroll
+            for (int p = 0; p < OZ_SLICES; ++p) {
+                const int q = W0 + gg - p;
+                if (q < 0 || q >= OZ_SLICES) continue;
+                const uint64_t da = da0 + static_cast<uint64_t>(p * (OZ_SLICE_STEP_BYTES >> 4));
+                const uint64_t db = db0 + static_cast<uint64_t>(q * (B_SLICE_BYTES >> 4));
+                oz_mma2(tmem + gg * 128, da, db, (p == 0) ? not_first_ks : 1u);   // p = 0 is the first pair of every weight
+            }
+        }
+    } else {
+        // digit p of A against every digit q of B whose weight p + q belongs to this pass; two consecutive q share ONE
+        // N = 256 MMA (the A slice is read once for both, 12 KB instead of 16 KB of shared-memory reads per pair of
+        // products): pass 0 = 4 x N256 + 2 x N128, pass 1 = 6 x N256 + 6 x N128.  p = 0 touches every accumulator first.
 #pragma unroll
         for (int p = 0; p < OZ_SLICES; ++p) {
-            const int q = W0 + gg - p;
-            if (q < 0 || q >= OZ_SLICES) continue;
+            const int q_lo = (W0 - p) > 0 ? (W0 - p) : 0;
+            const int q_hi = (W0 + NW - 1 - p) < (OZ_SLICES - 1) ? (W0 + NW - 1 - p) : (OZ_SLICES - 1);
             const uint64_t da = da0 + static_cast<uint64_t>(p * (OZ_SLICE_STEP_BYTES >> 4));
-            const uint64_t db = db0 + static_cast<uint64_t>(q * (B_SLICE_BYTES >> 4));
-            const uint32_t acc = (p == 0) ? not_first_ks : 1u;        // p = 0 is the first pair of every weight
-            if (TWO_CTA) oz_mma2(tmem + gg * 128, da, db, acc);
-            else oz_mma(tmem + gg * 128, da, db, acc);
+            const uint32_t acc = (p == 0) ? not_first_ks : 1u;
+#pragma unroll
+            for (int q = q_lo; q <= q_hi; q += 2) {
+                const uint64_t db = db0 + static_cast<uint64_t>(q * (B_SLICE_BYTES >> 4));
+                const uint32_t dst = tmem + (p + q - W0) * 128;
+                if (q + 1 <= q_hi) oz_mma_n256(dst, da, db, acc);
+                else oz_mma(dst, da, db, acc);
+            }
         }
     }
 }
@@ -784,7 +858,8 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
     const int tiles = tri > 0 ? tri * (tri + 1) / 2 + (Mt - tri) * tri : Mt * Nt;
     if (tiles <= 0) return;
     static const int c_reduce = getenv("EGX_OZAKI_CRED") != nullptr ? atoi(getenv("EGX_OZAKI_CRED")) : 0;   // measured: same tile rate as load / add / store (the 128 row reductions of a tile serialise in the TMA unit)
-    OzakiArgs g{C, ldc, SA, rsA, Mt, tri, SB, rsB, Nt, dbg, c_reduce};
+    static const int prod3 = getenv("EGX_OZAKI_PROD3") != nullptr ? atoi(getenv("EGX_OZAKI_PROD3")) : 0;
+    OzakiArgs g{C, ldc, SA, rsA, Mt, tri, SB, rsB, Nt, dbg, c_reduce, prod3};
     // persistent: a resident grid loops over the tiles (prefetch across tiles, no per-tile set-up, the C update of a
     // tile overlaps the MMAs of the next) -- but it keeps the high-priority panel / look-ahead kernels of the SAME
     // factorisation waiting for SMs.  The sweep asks for it when several evaluations are in flight (the batched entry

@@ -96,8 +96,8 @@ static int check_update(int Mt, int tri, bool timing_only, int reps) {
     launch_ozaki_slice(dP, ldp, rows, dR, dS, 0);
     cudaEventRecord(e1);
     long long* dbg;
-    cudaMalloc(&dbg, 16 * 8);
-    cudaMemset(dbg, 0, 16 * 8);
+    cudaMalloc(&dbg, 24 * 8);
+    cudaMemset(dbg, 0, 24 * 8);
     for (int r = 0; r < reps; ++r) launch_ozaki_syrk(dC, ldc, dS, dR, Mt, tri, 0, dbg, 0);
     cudaEventRecord(e2);
     cudaError_t err = cudaDeviceSynchronize();
@@ -112,11 +112,15 @@ static int check_update(int Mt, int tri, bool timing_only, int reps) {
     printf("Mt=%d tri=%d: %ld tiles, slice %.3f ms, update %.3f ms per launch -> %.1f fp64-equivalent TFLOP/s\n", Mt, tri, tiles,
            ms_slice, ms_upd / reps, 2.0 * 128 * 128 * 256 * tiles / (ms_upd / reps * 1e-3) / 1e12);
     {
-        long long h[16];
+        long long h[24];
         cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
         printf("  CTA 0 clocks from start: setup %lld, first stage landed %lld, pass-1 first stage %lld | epilogue: acc0 ready %lld, "
                "drain0 done %lld, acc1 ready %lld, drain1 done %lld | CTA end %lld\n", h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0],
                h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0]);
+        printf("    first tile C update done %lld | second tile: acc0 ready %lld, drain0 done %lld, acc1 ready %lld, drain1 done %lld, C update done %lld\n",
+               h[9] - h[0], h[10] - h[0], h[11] - h[0], h[12] - h[0], h[13] - h[0], h[14] - h[0]);
+        printf("    MMA warp, second tile: pass-0 first stage ready %lld, last K step issued %lld, pass-1 first stage %lld\n", h[15] - h[0],
+               h[16] - h[0], h[17] - h[0]);
     }
     if (timing_only) return 0;
     std::vector<double> Cg(C.size());
