@@ -252,6 +252,12 @@ __device__ __forceinline__ void oz_tmem_ld2(uint32_t addr, uint32_t (&v)[8]) {
                  : "r"(addr));
 }
 
+__device__ __forceinline__ double2 oz_shfl_xor4(double2 v) {
+    v.x = __shfl_xor_sync(0xffffffffu, v.x, 4);
+    v.y = __shfl_xor_sync(0xffffffffu, v.y, 4);
+    return v;
+}
+
 // exact int64 -> double for |t| < 2^51 without the slow 64-bit convert: bias into the mantissa of 2^52 + 2^51
 __device__ __forceinline__ double oz_i64_to_double(long long t) {
     return __longlong_as_double(t + 0x4338000000000000LL) - 6755399441055744.0;
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
 
     if (tid == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) {
-            oz_mbar_init(&bars->full[s], g.prod3 ? 1 : 2);
+            oz_mbar_init(&bars->full[s], g.prod3 == 1 ? 1 : 2);
             oz_mbar_init(&bars->empty[s], 1);
         }
         oz_mbar_init(&bars->acc_full, 1);
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OZ_REGS_CTRL));
-    if (warp != 1 && !g.prod3) {
+    if (warp != 1 && g.prod3 != 1) {
         // ===== producers, one per operand: warp 0 streams the A slices, warp 2 the B slices =====
         if (lane == 0 && warp != 3) {
             const bool isB = warp == 2;
@@ -428,6 +434,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
         // ===== epilogue: 8 warps; lane quarter = warp % 4, column half = (warp - 4) / 4 =====
         const int quarter = warp & 3, chalf = (warp - 4) >> 2;
         const int r_in = lane >> 2, cq = 2 * (lane & 3);
+        const bool odd = (r_in & 1) != 0;
         uint32_t P = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             int tr, tc;
@@ -475,22 +482,35 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                     // would only wait (pass 1 is bound by the shared-memory port, not by the L2 -> SM path); after the
                     // second pass only the store is left.  Read at the start of the tile it would compete with the stage
                     // refills of pass 0, read after pass 1 it lands on the next tile's pass 0 (measured: 12 k clk each).
+                    // Two adjacent quads (rows r, r+1 of the fragment) team up so that ONE instruction covers 128 contiguous
+                    // bytes of a row (4 full lines per warp instruction instead of 8 half lines): the even quad reads
+                    // columns 8j.. of the even row and of the odd row, the odd quad columns 8(j+1).. of both; what belongs
+                    // to the partner changes hands through shfl.xor 4.
 #pragma unroll
-                    for (int rh = 0; rh < 2; ++rh) {             // two rows (16 loads in flight) at a time
-                        double2 v[2][8];
+                    for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
-                        for (int h = 0; h < 2; ++h)
+                        for (int h = 0; h < 2; ++h) {
+                            const double* base = Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + (odd ? 8 : 0);
+                            const double* row_e = base - (odd ? g.ldc : 0);
+                            const double* row_o = row_e + g.ldc;
+                            double2 ve[4], vo[4];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                v[h][j] = *reinterpret_cast<const double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                c[rh][h][j].x += v[h][j].x;
-                                c[rh][h][j].y += v[h][j].y;
+                            for (int jp = 0; jp < 4; ++jp) {
+                                ve[jp] = *reinterpret_cast<const double2*>(row_e + 16 * jp);
+                                vo[jp] = *reinterpret_cast<const double2*>(row_o + 16 * jp);
                             }
-                    }
+#pragma unroll
+                            for (int jp = 0; jp < 4; ++jp) {
+                                // even lane: ve = own (j), vo = partner's (j);  odd lane: vo = own (j+1), ve = partner's (j+1)
+                                const double2 got = oz_shfl_xor4(odd ? ve[jp] : vo[jp]);
+                                const double2 own = odd ? vo[jp] : ve[jp];
+                                const double2 add0 = odd ? got : own, add1 = odd ? own : got;     // for columns 8j.. / 8(j+1)..
+                                c[rh][h][2 * jp].x += add0.x;
+                                c[rh][h][2 * jp].y += add0.y;
+                                c[rh][h][2 * jp + 1].x += add1.x;
+                                c[rh][h][2 * jp + 1].y += add1.y;
+                            }
+                        }
                 }
             }
             if (g.c_reduce) {
@@ -521,13 +541,27 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
             } else {
+#ifdef OZ_TIMING
+                if (g.prod3 == 7 && c[0][0][0].x != 1.2345e300) goto skip_store;     // timing experiment: no C store
+#endif
 #pragma unroll
                 for (int rh = 0; rh < 2; ++rh)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < 2; ++h) {
+                        double* base = Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + (odd ? 8 : 0);
+                        double* row_e = base - (odd ? g.ldc : 0);
+                        double* row_o = row_e + g.ldc;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<double2*>(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j) = c[rh][h][j];
+                        for (int jp = 0; jp < 4; ++jp) {
+                            const double2 own = odd ? c[rh][h][2 * jp + 1] : c[rh][h][2 * jp];
+                            const double2 got = oz_shfl_xor4(odd ? c[rh][h][2 * jp] : c[rh][h][2 * jp + 1]);
+                            *reinterpret_cast<double2*>(row_e + 16 * jp) = odd ? got : own;     // 128 B of the even row per quad pair
+                            *reinterpret_cast<double2*>(row_o + 16 * jp) = odd ? own : got;     // 128 B of the odd row
+                        }
+                    }
+#ifdef OZ_TIMING
+            skip_store:;
+#endif
             }
             if (tid == 128 && tile == blockIdx.x) OZ_STAMP(9);
             if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(14);
