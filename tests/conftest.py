@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a real B200 (run with -m gpu on the GPU box)")
+    # a fresh checkout has no libegobox_gpu.so (built artefacts are git-ignored): build it once (nvcc cross-compiles
+    # sm_100a without a GPU); the product package itself never builds or falls back silently
+    from egobox_b200 import _build
+    if not os.path.exists(_build.LIB):
+        _build.build_library()
 
 
 @pytest.fixture(scope="session")
