@@ -29,6 +29,9 @@
 // (pass 1: three accumulators, 2^-64).  An epilogue thread keeps its 64 entries of C in registers across both passes.
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
+
+#include <cuda.h>              // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "common.cuh"
 #include "../../include/egobox_gpu.h"
@@ -323,7 +326,7 @@ __device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint3
 // tiles, so the producer is already streaming the next tile while the epilogue folds the last pass of this one.
 // An epilogue thread owns the same 64 entries of C in both passes: they are loaded while the MMAs of pass 0 run,
 // updated in registers after each pass and stored once.
-__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiArgs g) {
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiArgs g, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
     unsigned char* cstg = oz_smem + OZ_STAGES * OZ_STAGE_BYTES;
     OzBarriers* bars = reinterpret_cast<OzBarriers*>(cstg + OZ_CSTG_BYTES);
@@ -513,7 +516,42 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                         }
                 }
             }
-            if (g.c_reduce) {
+            if (g.c_reduce == 2) {
+                // C += c without reading C, through the TMA: 32 rows x 128 columns at a time are staged densely in shared
+                // memory (quad pairs exchange fragments so that an instruction writes 128-byte row segments) and leave
+                // as ONE cp.reduce.async.bulk.tensor (.add, fp64 tensor map of C; SASS UTMAREDG): the adds happen in L2
+#pragma unroll 1
+                for (int qq = 0; qq < 4; ++qq) {
+                    if (quarter == qq) {
+#pragma unroll
+                        for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                double* base = reinterpret_cast<double*>(cstg) + (16 * rh + 8 * h + r_in) * 128 + 64 * chalf + cq + (odd ? 8 : 0);
+                                double* row_e = base - (odd ? 128 : 0);
+                                double* row_o = row_e + 128;
+#pragma unroll
+                                for (int jp = 0; jp < 4; ++jp) {
+                                    const double2 own = odd ? c[rh][h][2 * jp + 1] : c[rh][h][2 * jp];
+                                    const double2 got = oz_shfl_xor4(odd ? c[rh][h][2 * jp] : c[rh][h][2 * jp + 1]);
+                                    *reinterpret_cast<double2*>(row_e + 16 * jp) = odd ? got : own;
+                                    *reinterpret_cast<double2*>(row_o + 16 * jp) = odd ? own : got;
+                                }
+                            }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (warp == 4 && lane == 0) {
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&cmap)),
+                                     "r"(oz_smem_u32(cstg)), "r"(tc * 128), "r"(tr * 128 + 32 * qq)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+            } else if (g.c_reduce) {
                 // C += c without reading C: 32 rows at a time go through shared memory and leave as one
                 // cp.reduce.async.bulk (.add.f64, SASS UBLKRED) per row -- the adds happen in L2, nothing comes back
 #pragma unroll 1
@@ -894,6 +932,28 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
     static const int c_reduce = getenv("EGX_OZAKI_CRED") != nullptr ? atoi(getenv("EGX_OZAKI_CRED")) : 0;   // measured: same tile rate as load / add / store (the 128 row reductions of a tile serialise in the TMA unit)
     static const int prod3 = getenv("EGX_OZAKI_PROD3") != nullptr ? atoi(getenv("EGX_OZAKI_PROD3")) : 0;
     OzakiArgs g{C, ldc, SA, rsA, Mt, tri, SB, rsB, Nt, dbg, c_reduce, prod3};
+    alignas(64) CUtensorMap cmap;
+    memset(&cmap, 0, sizeof(cmap));
+    if (c_reduce == 2) {
+        // fp64 tensor map of the C region of this launch: (columns, rows), row pitch ldc, boxes of 128 columns x 32 rows
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static encode_fn encode = nullptr;
+        if (encode == nullptr) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess) encode = reinterpret_cast<encode_fn>(fn);
+        }
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Nt) * 128, static_cast<cuuint64_t>(Mt) * 128};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldc) * sizeof(double)};
+        const cuuint32_t box[2] = {128, 32}, estr[2] = {1, 1};
+        if (encode == nullptr ||
+            encode(&cmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            g.c_reduce = 0;                        // no encoder / unsupported shape: plain load / add / store
+        }
+    }
     // persistent: a resident grid loops over the tiles (prefetch across tiles, no per-tile set-up, the C update of a
     // tile overlaps the MMAs of the next) -- but it keeps the high-priority panel / look-ahead kernels of the SAME
     // factorisation waiting for SMs.  The sweep asks for it when several evaluations are in flight (the batched entry
@@ -916,7 +976,7 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
         const int rounds = (tiles + sms - 1) / sms;
         grid = (tiles + rounds - 1) / rounds;
     }
-    ozaki_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g);
+    ozaki_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g, cmap);
 }
 
 void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,
