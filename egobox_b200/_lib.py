@@ -15,9 +15,9 @@ EGX_OK, EGX_NOT_POSITIVE_DEFINITE, EGX_ILL_CONDITIONED_FT, EGX_ILL_CONDITIONED_F
     EGX_INVALID_VALUE, EGX_CUDA_ERROR = range(6)
 STATUS_NAMES = {0: "OK", 1: "NOT_POSITIVE_DEFINITE", 2: "ILL_CONDITIONED_FT", 3: "ILL_CONDITIONED_F",
                 4: "INVALID_VALUE", 5: "CUDA_ERROR"}
-NUM_STAGES = 12
+NUM_STAGES = 13
 STAGE_NAMES = ["corr_build", "potrf_diag", "trsm_panel", "syrk_gemm", "gls", "backsolve",
-               "cross_corr", "var_finish", "small_batch", "gemm_lookahead", "ozaki_slice", "ozaki_syrk"]
+               "cross_corr", "var_finish", "small_batch", "gemm_lookahead", "ozaki_slice", "ozaki_syrk", "theta_grad"]
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -39,6 +39,7 @@ SIGNATURES = {
     "egx_gp_eval_begin": (C.c_int, [_vp, C.c_int, _dp]),
     "egx_gp_eval_end": (C.c_int, [_vp, C.c_int, _dp]),
     "egx_gp_reduced_likelihood_grad": (C.c_int, [_vp, _dp, C.c_double, _dp, _dp]),
+    "egx_gp_reduced_likelihood_grad_analytic": (C.c_int, [_vp, _dp, _dp, _dp]),
     "egx_gp_download_chol": (C.c_int, [_vp, _dp]),
     "egx_gp_predict": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_gp_predict_var": (C.c_int, [_vp, _dp, C.c_int, _dp]),

@@ -102,6 +102,14 @@ class GpContext:
         st = self._check(self._lib.egx_gp_reduced_likelihood_grad(self._h, _ptr(th), float(rel_step), C.byref(out), _ptr(g)))
         return st, out.value, g
 
+    def reduced_likelihood_grad_analytic(self, theta):
+        """-> (status, rlf, d rlf / d theta) in closed form from one factorisation (h <= 32)."""
+        th = _f64(theta).reshape(-1)
+        out = C.c_double()
+        g = np.empty(self.h)
+        st = self._check(self._lib.egx_gp_reduced_likelihood_grad_analytic(self._h, _ptr(th), C.byref(out), _ptr(g)))
+        return st, out.value, g
+
     def finalize(self, theta, want_ft=True):
         th = _f64(theta).reshape(-1)
         rlf, s2 = C.c_double(), C.c_double()

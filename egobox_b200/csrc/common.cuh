@@ -20,6 +20,14 @@ struct CorrTerm {
     double k3;   // Matern52: tw * tw
 };
 
+// One (input dimension j, component l) term of the theta-gradient pair kernel (kernels_thetagrad.cu).
+struct ThetaGradTerm {
+    int dim;
+    int comp;
+    double a;    // SqExp: -theta_l W_jl^2 | AbsExp: -|W_jl| | Matern: |W_jl|
+    double tw;   // SqExp: (theta_l W_jl)^2 | others: theta_l |W_jl|
+};
+
 // Result block written by the GLS kernel (one per likelihood evaluation).
 struct EvalResult {
     double rlf;        // reduced likelihood, algorithm.rs:1043
@@ -102,6 +110,13 @@ void launch_normalize_rows(const double* x, int m, int mpad, int d, const double
 void launch_zero_upper(double* A, long ld, int npad, cudaStream_t s);
 void launch_bcast_rows(double* out, long ld, int m, int mpad, int cols, const double* mean, cudaStream_t s);
 int egx_host_symmetric_eig(int n, double* a, double* w);
+// kernels_thetagrad.cu
+int egx_fill_theta_grad_terms(int corr, int d, int h, const double* w, const double* theta, ThetaGradTerm* t);
+int theta_grad_blocks(int npad);
+void launch_theta_grad(int corr, const double* X, int n, int npad, int d, const ThetaGradTerm* terms, int nterms,
+                       const double* Cneg_rinv, long ldc, const double* gamma, const EvalResult* res, int h,
+                       double* partial, double* grad, cudaStream_t s);
+void launch_set_identity(double* A, long ld, int npad, cudaStream_t s);
 
 // cached allocators (devmem.cu): same contract as cudaMalloc / cudaFree / cudaMallocHost / cudaFreeHost
 cudaError_t egx_dev_malloc_bytes(void** p, size_t bytes);

@@ -153,6 +153,9 @@ struct egx_gp_ctx {
     std::vector<long> Lsl_off, Lsc_off;
     bool Lslices_ready = false;
     long long direct_evals = 0;
+    // closed-form theta gradient (built lazily): W = L^-T, -R^-1, per-CTA partial sums, term list
+    double *tgW = nullptr, *tgRinv = nullptr, *tgPartial = nullptr, *tgGrad = nullptr, *tgGrad_h = nullptr;
+    ThetaGradTerm *tgTerms = nullptr, *tgTerms_h = nullptr;
     std::mutex mu;
 };
 
@@ -546,6 +549,13 @@ int predict_impl(egx_gp_ctx* c, const double* x, int m, double* y, double* var, 
 
 void free_ctx(egx_gp_ctx* c) {
     if (!c) return;
+    egx_dev_free(c->tgW);
+    egx_dev_free(c->tgRinv);
+    egx_dev_free(c->tgPartial);
+    egx_dev_free(c->tgGrad);
+    egx_dev_free(c->tgTerms);
+    egx_host_free(c->tgGrad_h);
+    egx_host_free(c->tgTerms_h);
     egx_dev_free(c->Lsl);
     egx_dev_free(c->Lsc);
     c->Lsl = nullptr;
@@ -879,6 +889,94 @@ extern "C" int egx_gp_reduced_likelihood_grad(egx_gp_ctx* c, const double* theta
         grad[k] = (st[1 + 2 * k] == EGX_OK && st[2 + 2 * k] == EGX_OK) ? (val[1 + 2 * k] - val[2 + 2 * k]) / (hi - lo) : NAN;
     }
     return st[0];
+}
+
+// d rlf / d theta in closed form (kernels_thetagrad.cu):  one evaluation, gamma, W = L^-T by the multi-RHS sweep on the
+// identity, -R^-1 = -W W^T (W is upper triangular: column panel kp only touches the rows above its end, so the SYRK is a
+// sum of growing triangles -- on tcgen05 where the triangle is large enough, else DMMA), then the pair kernel.
+extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const double* theta, double* rlf, double* grad) {
+    if (!c || !theta || !rlf || !grad) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const int h = c->h, npad = c->npad, T = npad / EGX_NB;
+    for (int l = 0; l < h; ++l) grad[l] = NAN;
+    *rlf = NAN;
+    if (h > 32) {
+        egx_set_error("closed-form theta gradient supports up to 32 components (got %d): use egx_gp_reduced_likelihood_grad", h);
+        return EGX_INVALID_VALUE;
+    }
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    int st = evaluate(c, theta, rlf);
+    if (st != EGX_OK) return st;
+    backsolve_vector(c->env, factor_ref(c), c->rho);          // gamma = L^-T rho (algorithm.rs:1034)
+    const int nblocks = theta_grad_blocks(npad);
+    if (c->tgW == nullptr) {
+        const size_t sq = static_cast<size_t>(npad) * npad * sizeof(double);
+        EGX_CUDA_TRY(egx_dev_malloc(&c->tgW, sq));
+        EGX_CUDA_TRY(egx_dev_malloc(&c->tgRinv, sq));
+        EGX_CUDA_TRY(egx_dev_malloc(&c->tgPartial, static_cast<size_t>(nblocks) * h * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&c->tgGrad, h * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&c->tgTerms, static_cast<size_t>(c->d) * h * sizeof(ThetaGradTerm)));
+        EGX_CUDA_TRY(egx_host_malloc(&c->tgGrad_h, h * sizeof(double)));
+        EGX_CUDA_TRY(egx_host_malloc(&c->tgTerms_h, static_cast<size_t>(c->d) * h * sizeof(ThetaGradTerm)));
+    }
+    if (c->env.ensure_panel_rows(npad) != EGX_OK) return EGX_CUDA_ERROR;
+    const int nt = egx_fill_theta_grad_terms(c->corr, c->d, h, c->w_star.data(), theta, c->tgTerms_h);
+    if (nt > 0)
+        EGX_CUDA_TRY(cudaMemcpyAsync(c->tgTerms, c->tgTerms_h, nt * sizeof(ThetaGradTerm), cudaMemcpyHostToDevice, c->stream));
+    // W = I L^-T
+    launch_set_identity(c->tgW, npad, npad, c->stream);
+    FactorRef fr = factor_ref(c);
+    if (T >= 8) {
+        st = ensure_L_slices(c);
+        if (st != EGX_OK) return st;
+        if (c->Lslices_ready) {
+            fr.Lsl = c->Lsl;
+            fr.Lsc = c->Lsc;
+            fr.Lsl_off = c->Lsl_off.data();
+            fr.Lsc_off = c->Lsc_off.data();
+        }
+    }
+    blocked_sweep(c->env, fr, false, c->tgW, npad, T, npad / 64);
+    // -R^-1 = 0 - W W^T, lower block triangle
+    EGX_CUDA_TRY(cudaMemsetAsync(c->tgRinv, 0, static_cast<size_t>(npad) * npad * sizeof(double), c->stream));
+    const bool oz = c->env.ozaki && c->env.oz_S != nullptr && T >= c->env.ozaki_min_T;
+    for (int k = 0; k < T; k += 2) {
+        const int kw = (k + 1 < T) ? 2 : 1;                   // block columns in this panel
+        const int rt = k + kw;                                // tile rows of W that are non-zero in it
+        const double* P = c->tgW + static_cast<long>(k) * EGX_NB;
+        if (oz && kw == 2 && rt >= c->env.ozaki_min_tri) {
+            {
+                StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SLICE, 2, c->stream);
+                launch_ozaki_slice(P, npad, rt * EGX_NB, c->env.oz_scale, c->env.oz_S, c->stream);
+            }
+            StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SYRK, 1, c->stream);
+            launch_ozaki_syrk(c->tgRinv, npad, c->env.oz_S, c->env.oz_scale, rt, rt, c->stream);
+        } else {
+            GemmArgs g;
+            g.C = c->tgRinv;
+            g.ldc = npad;
+            g.A = P;
+            g.lda = npad;
+            g.B = P;
+            g.ldb = npad;
+            g.K = kw * EGX_NB;
+            g.tri = rt;
+            g.Mt = g.Nt = rt;
+            StageScope sc(c->env.prof, EGX_STAGE_SYRK_GEMM, 1, c->stream);
+            launch_gemm_nt_sub(g, c->stream);
+        }
+    }
+    {
+        StageScope sc(c->env.prof, EGX_STAGE_THETA_GRAD, 2, c->stream);
+        launch_theta_grad(c->corr, c->X, c->n, npad, c->d, c->tgTerms, nt, c->tgRinv, npad, c->rho, c->res, h, c->tgPartial,
+                          c->tgGrad, c->stream);
+    }
+    EGX_CUDA_TRY(cudaMemcpyAsync(c->tgGrad_h, c->tgGrad, h * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EGX_CUDA_TRY(cudaGetLastError());
+    resolve_profile(c);
+    std::memcpy(grad, c->tgGrad_h, h * sizeof(double));
+    return EGX_OK;
 }
 
 extern "C" int egx_gp_finalize(egx_gp_ctx* c, const double* theta, double* rlf, double* sigma2, double* beta,

@@ -102,6 +102,13 @@ int egx_gp_reduced_likelihood_batch(egx_gp_ctx* ctx, const double* thetas, int B
 int egx_gp_reduced_likelihood_grad(egx_gp_ctx* ctx, const double* theta, double rel_step, double* rlf,
                                    double* grad);
 
+/* The same gradient in closed form (h <= 32):
+ *   d rlf / d theta_l = [ gamma^T (dR/dtheta_l) gamma / sigma2 - tr(R^-1 dR/dtheta_l) ] / ln 10
+ * from ONE factorisation: R^-1 = W W^T with W = L^-T (multi-RHS sweep on the identity + SYRK), then one pass over the
+ * pairs.  About three factorisations' worth of work instead of 2h+1, and exact to rounding.  grad is d/d theta (not
+ * d/d log10 theta); leaves the context untrained, like egx_gp_reduced_likelihood.  Uses 2 n^2 doubles of extra memory. */
+int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* ctx, const double* theta, double* rlf, double* grad);
+
 /* Final evaluation at the selected theta (gp/src/algorithm.rs:966-968): keeps
  * the Cholesky factor, gamma, beta, Ft, G on the device for predict*, and
  * optionally returns GpInnerParams (algorithm.rs:47-60) -- any output pointer
@@ -190,7 +197,8 @@ int egx_gp_cross_correlation(egx_gp_ctx* ctx, const double* x, int m, double* c)
 #define EGX_STAGE_GEMM_LOOKAHEAD 9 /* updates issued ahead on the panel stream (partner column, next pair's two columns) */
 #define EGX_STAGE_OZAKI_SLICE  10 /* fp64 panel pair -> row scales + 8 int8 slices (tcgen05 path)           */
 #define EGX_STAGE_OZAKI_SYRK   11 /* trailing SYRK update on tcgen05 (int8-sliced, UTCIMMA, TMEM accumulators) */
-#define EGX_NUM_STAGES         12
+#define EGX_STAGE_THETA_GRAD   12 /* closed-form theta gradient: pair kernel + partial-sum reduction */
+#define EGX_NUM_STAGES         13
 int egx_gp_set_profiling(egx_gp_ctx* ctx, int enabled);
 int egx_gp_reset_profile(egx_gp_ctx* ctx);
 /* ms[EGX_NUM_STAGES], launches[EGX_NUM_STAGES] */

@@ -244,6 +244,55 @@ def corr_matrix(kind, xnorm, theta, w, nugget=DEFAULT_NUGGET, chunk=256):
     return R
 
 
+def corr_theta_log_derivatives(kind, d, theta, w):
+    """d ln r / d theta_l for a (P, nx) array of component differences -> (P, h).  Not in the reference
+    (`CorrelationModel` has no theta derivative; algorithm.rs:880 ignores `_gradient`): differentiates the four
+    `value` formulas restated in corr_value, term by term."""
+    d = np.asarray(d, dtype=np.float64)
+    theta = np.asarray(theta, dtype=np.float64).reshape(-1)
+    w = np.asarray(w, dtype=np.float64)
+    abs_d = np.abs(d)
+    if kind == SQEXP:                                   # ln r = -1/2 sum_j d_j^2 sum_l (theta_l W_jl)^2
+        return -(d ** 2).dot(w ** 2) * theta[None, :]
+    if kind == ABSEXP:                                  # ln r = -sum_j |d_j| sum_l |W_jl| theta_l
+        return -abs_d.dot(np.abs(w))
+    s = math.sqrt(3.0) if kind == MATERN32 else math.sqrt(5.0)
+    out = np.zeros((d.shape[0], theta.size))
+    for j in range(d.shape[1]):
+        for l in range(theta.size):
+            a = abs(w[j, l]) * abs_d[:, j]              # dv/dtheta_l with v = theta_l |W_jl| |d_j|
+            v = theta[l] * a
+            if kind == MATERN32:                        # d/dv [ln(1 + s v) - s v] = -3 v / (1 + s v)
+                out[:, l] += a * (-3.0 * v / (1.0 + s * v))
+            else:                                       # d/dv [ln(1 + s v + 5/3 v^2) - s v]
+                out[:, l] += a * (-(5.0 / 3.0) * v * (1.0 + s * v) / (1.0 + s * v + (5.0 / 3.0) * v * v))
+    return out
+
+
+def reduced_likelihood_grad(kind, xnorm, fx, ynorm, y_std, theta, w, nugget=DEFAULT_NUGGET, chunk=256):
+    """(rlf, d rlf / d theta) in closed form.  With rlf = -n log10 sigma2 - log10 det R (algorithm.rs:1039-1043), beta
+    the generalised least-squares minimiser (so its own derivative drops out) and gamma = R^-1 (y - F beta) (:1034):
+        d rlf / d theta_l = [ gamma^T (dR/dtheta_l) gamma / sigma2 - tr(R^-1 dR/dtheta_l) ] / ln 10.
+    The diagonal of R is the constant 1 + nugget, so only pairs i != j contribute."""
+    x = np.asarray(xnorm, dtype=np.float64)
+    theta = np.asarray(theta, dtype=np.float64).reshape(-1)
+    n = x.shape[0]
+    rlf, inner = reduced_likelihood(kind, x, fx, ynorm, y_std, theta, w, nugget)
+    gamma = inner.gamma.reshape(-1)
+    sigma2 = inner.sigma2 / (y_std * y_std)
+    rinv = sla.cho_solve((inner.r_chol, True), np.eye(n), check_finite=False)
+    weight = np.outer(gamma, gamma) / sigma2 - rinv
+    np.fill_diagonal(weight, 0.0)
+    grad = np.zeros(theta.size)
+    for i0 in range(0, n, chunk):
+        i1 = min(n, i0 + chunk)
+        dx = pairwise_differences(x[i0:i1], x)
+        r = corr_value(kind, np.abs(dx), theta, w)
+        dlog = corr_theta_log_derivatives(kind, dx, theta, w)
+        grad += (weight[i0:i1].reshape(-1) * r).dot(dlog)
+    return rlf, grad / math.log(10.0)
+
+
 # --------------------------------------------------------------------------
 # algorithm.rs: reduced likelihood
 # --------------------------------------------------------------------------

@@ -288,3 +288,28 @@ def test_var_gradients_vs_fd_general(corr, mean):
         xm[0, k] -= e
         fd = (gp.predict_var(xp)[0] - gp.predict_var(xm)[0]) / (2 * e)
         assert g[0, k] == pytest.approx(fd, rel=1e-4, abs=1e-7)
+
+
+# --------------------------------------------------------------------------- closed-form theta gradient (not in the reference)
+@pytest.mark.parametrize("kind", [O.SQEXP, O.ABSEXP, O.MATERN32, O.MATERN52])
+@pytest.mark.parametrize("kpls", [False, True])
+def test_oracle_theta_gradient_against_central_differences(kind, kpls):
+    """The reference has no theta gradient (algorithm.rs:880 ignores `_gradient`); the oracle's closed form is held to
+    central differences of the oracle's own rlf, which the notebook fixture pins."""
+    rng = np.random.default_rng(3)
+    n, d = 90, 4
+    x = rng.uniform(-1.0, 1.0, (n, d))
+    y = np.sin(x.sum(axis=1)) + 0.1 * x[:, 0] ** 2
+    xn, _, _ = O.normalize(x)
+    yn, _, ys = O.normalize(y.reshape(-1, 1))
+    w = rng.normal(size=(d, 2)) if kpls else np.eye(d)
+    theta = rng.uniform(0.5, 1.5, w.shape[1])
+    fx = O.mean_value(O.CONSTANT, xn)
+    rlf, g = O.reduced_likelihood_grad(kind, xn, fx, yn[:, 0], float(ys[0]), theta, w)
+    f = lambda t: O.reduced_likelihood(kind, xn, fx, yn[:, 0], float(ys[0]), t, w)[0]
+    assert rlf == f(theta)
+    for k in range(theta.size):
+        e = np.zeros(theta.size)
+        e[k] = 1e-6 * theta[k]
+        fd = (f(theta + e) - f(theta - e)) / (2.0 * e[k])
+        assert g[k] == pytest.approx(fd, rel=2e-6, abs=1e-6)
