@@ -117,6 +117,7 @@ void launch_theta_grad(int corr, const double* X, int n, int npad, int d, const 
                        const double* Cneg_rinv, long ldc, const double* gamma, const EvalResult* res, int h,
                        double* partial, double* grad, cudaStream_t s);
 void launch_set_identity(double* A, long ld, int npad, cudaStream_t s);
+void launch_upper_gemv(const double* W, long ld, int n, const double* rho, double* out, cudaStream_t s);
 
 // cached allocators (devmem.cu): same contract as cudaMalloc / cudaFree / cudaMallocHost / cudaFreeHost
 cudaError_t egx_dev_malloc_bytes(void** p, size_t bytes);

@@ -154,7 +154,7 @@ struct egx_gp_ctx {
     bool Lslices_ready = false;
     long long direct_evals = 0;
     // closed-form theta gradient (built lazily): W = L^-T, -R^-1, per-CTA partial sums, term list
-    double *tgW = nullptr, *tgRinv = nullptr, *tgPartial = nullptr, *tgGrad = nullptr, *tgGrad_h = nullptr;
+    double *tgW = nullptr, *tgRinv = nullptr, *tgPartial = nullptr, *tgGrad = nullptr, *tgGrad_h = nullptr, *tgGamma = nullptr;
     ThetaGradTerm *tgTerms = nullptr, *tgTerms_h = nullptr;
     std::mutex mu;
 };
@@ -553,6 +553,7 @@ void free_ctx(egx_gp_ctx* c) {
     egx_dev_free(c->tgRinv);
     egx_dev_free(c->tgPartial);
     egx_dev_free(c->tgGrad);
+    egx_dev_free(c->tgGamma);
     egx_dev_free(c->tgTerms);
     egx_host_free(c->tgGrad_h);
     egx_host_free(c->tgTerms_h);
@@ -891,8 +892,8 @@ extern "C" int egx_gp_reduced_likelihood_grad(egx_gp_ctx* c, const double* theta
     return st[0];
 }
 
-// d rlf / d theta in closed form (kernels_thetagrad.cu):  one evaluation, gamma, W = L^-T by the multi-RHS sweep on the
-// identity, -R^-1 = -W W^T (W is upper triangular: column panel kp only touches the rows above its end, so the SYRK is a
+// d rlf / d theta in closed form (kernels_thetagrad.cu):  one evaluation, W = L^-T by the multi-RHS sweep on the identity
+// (only the row tiles above each column pair: a third of the full sweep), gamma = W rho, -R^-1 = -W W^T (W is upper triangular: column panel kp only touches the rows above its end, so the SYRK is a
 // sum of growing triangles -- on tcgen05 where the triangle is large enough, else DMMA), then the pair kernel.
 extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const double* theta, double* rlf, double* grad) {
     if (!c || !theta || !rlf || !grad) return EGX_INVALID_VALUE;
@@ -907,7 +908,6 @@ extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const doub
     EGX_CUDA_TRY(cudaSetDevice(c->device));
     int st = evaluate(c, theta, rlf);
     if (st != EGX_OK) return st;
-    backsolve_vector(c->env, factor_ref(c), c->rho);          // gamma = L^-T rho (algorithm.rs:1034)
     const int nblocks = theta_grad_blocks(npad);
     if (c->tgW == nullptr) {
         const size_t sq = static_cast<size_t>(npad) * npad * sizeof(double);
@@ -915,6 +915,7 @@ extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const doub
         EGX_CUDA_TRY(egx_dev_malloc(&c->tgRinv, sq));
         EGX_CUDA_TRY(egx_dev_malloc(&c->tgPartial, static_cast<size_t>(nblocks) * h * sizeof(double)));
         EGX_CUDA_TRY(egx_dev_malloc(&c->tgGrad, h * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&c->tgGamma, static_cast<size_t>(npad) * sizeof(double)));
         EGX_CUDA_TRY(egx_dev_malloc(&c->tgTerms, static_cast<size_t>(c->d) * h * sizeof(ThetaGradTerm)));
         EGX_CUDA_TRY(egx_host_malloc(&c->tgGrad_h, h * sizeof(double)));
         EGX_CUDA_TRY(egx_host_malloc(&c->tgTerms_h, static_cast<size_t>(c->d) * h * sizeof(ThetaGradTerm)));
@@ -936,7 +937,11 @@ extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const doub
             fr.Lsc_off = c->Lsc_off.data();
         }
     }
-    blocked_sweep(c->env, fr, false, c->tgW, npad, T, npad / 64);
+    blocked_sweep(c->env, fr, false, c->tgW, npad, T, npad / 64, true);
+    {
+        StageScope sc(c->env.prof, EGX_STAGE_BACKSOLVE, 1, c->stream);   // gamma = L^-T rho = W rho (algorithm.rs:1034)
+        launch_upper_gemv(c->tgW, npad, c->n, c->rho, c->tgGamma, c->stream);
+    }
     // -R^-1 = 0 - W W^T, lower block triangle
     EGX_CUDA_TRY(cudaMemsetAsync(c->tgRinv, 0, static_cast<size_t>(npad) * npad * sizeof(double), c->stream));
     const bool oz = c->env.ozaki && c->env.oz_S != nullptr && T >= c->env.ozaki_min_T;
@@ -968,7 +973,7 @@ extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const doub
     }
     {
         StageScope sc(c->env.prof, EGX_STAGE_THETA_GRAD, 2, c->stream);
-        launch_theta_grad(c->corr, c->X, c->n, npad, c->d, c->tgTerms, nt, c->tgRinv, npad, c->rho, c->res, h, c->tgPartial,
+        launch_theta_grad(c->corr, c->X, c->n, npad, c->d, c->tgTerms, nt, c->tgRinv, npad, c->tgGamma, c->res, h, c->tgPartial,
                           c->tgGrad, c->stream);
     }
     EGX_CUDA_TRY(cudaMemcpyAsync(c->tgGrad_h, c->tgGrad, h * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

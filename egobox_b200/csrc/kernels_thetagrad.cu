@@ -150,6 +150,21 @@ __global__ void __launch_bounds__(256)
     if (tid == 0) grad[k] = sm[0] * (2.0 / 2.302585092994046);
 }
 
+// out = W rho for the upper-triangular W = L^-T (row i: columns i .. n-1): gamma = L^-T rho (algorithm.rs:1034) without the
+// 2 T launches of the blocked back substitution, W being at hand.  One warp per row.
+__global__ void __launch_bounds__(256)
+    upper_gemv_kernel(const double* __restrict__ W, long ld, int n, const double* __restrict__ rho, double* __restrict__ out) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double* w = W + static_cast<long>(row) * ld;
+    double acc = 0.0;
+    for (int k = (row & ~31) + lane; k < n; k += 32)
+        if (k >= row) acc += w[k] * rho[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[row] = acc;
+}
+
 __global__ void set_identity_kernel(double* __restrict__ A, long ld, int npad) {
     const long e = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long total = static_cast<long>(npad) * npad;
@@ -235,4 +250,8 @@ void launch_theta_grad(int corr, const double* X, int n, int npad, int d, const 
 void launch_set_identity(double* A, long ld, int npad, cudaStream_t s) {
     const long total = static_cast<long>(npad) * npad;
     set_identity_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(A, ld, npad);
+}
+
+void launch_upper_gemv(const double* W, long ld, int n, const double* rho, double* out, cudaStream_t s) {
+    upper_gemv_kernel<<<(n + 7) / 8, 256, 0, s>>>(W, ld, n, rho, out);
 }

@@ -149,8 +149,8 @@ static void trailing_syrk(SweepEnv& env, const GemmArgs& g, cudaStream_t st, int
     launch_gemm_nt_sub(g, st);
 }
 
-void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows, long ld_rows, int row_tiles,
-                   int slabs64) {
+void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows, long ld_rows, int row_tiles_all,
+                   int slabs64_all, bool upper_rows) {
     const int T = f.T, Qt = f.qpad / EGX_NB;
     const long ld = f.ld;
     const long LDP = 2 * EGX_NB;
@@ -166,6 +166,10 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
         double* Pw = env.P2[pair & 1];                 // rows x 256; factor: row 0 = first row of block k+1
         double* Rq = (env.ozaki && (factor || f.Lsl != nullptr)) ? env.oz_rmaxq[pair & 1] : nullptr;   // quarter-row maxima, same row origin as Pw
         const bool two = (k + 1 < T);
+        // upper_rows (solves only): the rows are upper triangular (the identity on entry), so row tiles below block
+        // column k + 1 are still zero in this pair's columns and their updates would subtract zeros
+        const int row_tiles = (upper_rows && k + 2 < row_tiles_all) ? k + 2 : row_tiles_all;
+        const int slabs64 = (upper_rows && k + 2 < row_tiles_all) ? 2 * (k + 2) : slabs64_all;
         // ---- panel A (block column k) -----------------------------------------------------------------
         if (factor) {
             {

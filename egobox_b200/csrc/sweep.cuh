@@ -76,8 +76,9 @@ struct FactorRef {
 
 // factor = true : in-place Cholesky of f.M (+ appended rows become (L^-1 B)^T)
 // factor = false: rows (row_tiles*128 x T*128, ld_rows) <- rows * L^-T using the factor f
+// upper_rows: the rows are upper triangular (factor = false only): step k works on row tiles 0 .. k+1
 void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows, long ld_rows, int row_tiles,
-                   int slabs64);
+                   int slabs64, bool upper_rows = false);
 
 // Per-theta kernel weights: (dimension, component) term list consumed by K1/K2 (correlation_models.rs
 // :97-100, 191, 333, 505).  Returns the number of terms written (<= d*h).
