@@ -83,10 +83,13 @@ class GpParamsStruct(C.Structure):
                 ("active", _ip), ("n_active", C.c_int),
                 ("n_start", C.c_int), ("max_eval", C.c_int), ("nugget", C.c_double),
                 ("w_star", _dp), ("kpls_dim", C.c_int), ("device", C.c_int),
-                ("seed", C.c_ulonglong), ("cobyla_rhobeg", C.c_double), ("cobyla_ftol_rel", C.c_double)]
+                ("seed", C.c_ulonglong), ("cobyla_rhobeg", C.c_double), ("cobyla_ftol_rel", C.c_double),
+                ("optimizer", C.c_int)]
 
 
+EGX_OPT_COBYLA, EGX_OPT_LBFGSB = 0, 1
 OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, _dp, C.c_int, C.c_void_p)
+OBJECTIVE_GRAD_FN = C.CFUNCTYPE(C.c_double, _dp, C.c_int, _dp, C.c_void_p)
 _pp = C.POINTER(GpParamsStruct)
 SIGNATURES.update({
     "egx_gp_params_default": (None, [_pp]),
@@ -109,6 +112,8 @@ SIGNATURES.update({
     "egx_gp_model_sample": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp]),
     "egx_bound_cobyla_minimize": (C.c_int, [OBJECTIVE_FN, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_double,
                                             C.c_double, C.c_int, _dp, _dp, _ip]),
+    "egx_bound_lbfgs_minimize": (C.c_int, [OBJECTIVE_GRAD_FN, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_double,
+                                           C.c_double, C.c_int, _dp, _dp, _ip]),
     "egx_prepare_multistart": (C.c_int, [C.c_int, _dp, _dp, C.c_int, C.c_ulonglong, _dp]),
 })
 

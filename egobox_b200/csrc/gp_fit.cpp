@@ -679,6 +679,52 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
                 for (int i = 0; i < na; ++i) th[active[i]] = std::pow(10.0, z[i]);
                 return th;
             };
+            // reduce (algorithm.rs:942-945): first strictly smaller wins, default theta = 1 (log10 = 0)
+            double fbest = kInf;
+            std::vector<double> zbest(na, 0.0);
+            if (prm->optimizer == EGX_OPT_LBFGSB && h > 32) {
+                egx_set_error("EGX_OPT_LBFGSB needs the closed-form theta gradient (at most 32 components, got %d)", h);
+                return EGX_INVALID_VALUE;
+            }
+            if (prm->optimizer == EGX_OPT_LBFGSB) {
+                // gradient-based multistart: one projected L-BFGS run per start on
+                // f(z) = -rlf(10^z), df/dz_i = -ln(10) theta_i d rlf / d theta_i, same starts and budget as the chains
+                struct GradUser {
+                    egx_gp_ctx* ctx;
+                    const std::vector<int>* active;
+                    const std::vector<double>* theta0;
+                    long long* n_evals;
+                    int h;
+                    int fatal;
+                } gu{m->ctx, &active, &theta0, &m->n_evals, h, EGX_OK};
+                auto fg = [](const double* z, int nz, double* grad, void* user) -> double {
+                    GradUser* u = static_cast<GradUser*>(user);
+                    std::vector<double> th = *u->theta0, gth(u->h, 0.0);
+                    for (int i = 0; i < nz; ++i) th[(*u->active)[i]] = std::pow(10.0, z[i]);
+                    double v = NAN;
+                    const int s1 = egx_gp_reduced_likelihood_grad_analytic(u->ctx, th.data(), &v, gth.data());
+                    *u->n_evals += 1;
+                    if (s1 == EGX_CUDA_ERROR) u->fatal = s1;
+                    for (int i = 0; i < nz; ++i) {
+                        const int a = (*u->active)[i];
+                        grad[i] = -2.302585092994046 * th[a] * gth[a];
+                    }
+                    return (s1 == EGX_OK && !std::isnan(v)) ? -v : kInf;      // Err(_) -> +inf, algorithm.rs:893-896
+                };
+                for (auto& s0 : starts) {
+                    std::vector<double> zopt(na);
+                    double fopt = kInf;
+                    int nev = 0;
+                    st = egx_bound_lbfgs_minimize(fg, &gu, na, s0.data(), lo.data(), hi.data(), 1e-9, 1e-7, maxeval,
+                                                  zopt.data(), &fopt, &nev);
+                    if (st != EGX_OK) return st;
+                    if (gu.fatal != EGX_OK) return gu.fatal;
+                    if (fopt < fbest) {
+                        fbest = fopt;
+                        zbest = zopt;
+                    }
+                }
+            } else {
             static const bool lockstep_forced = getenv("EGX_FIT_LOCKSTEP") != nullptr && atoi(getenv("EGX_FIT_LOCKSTEP")) != 0;
             const int slots = lockstep_forced ? 0 : egx_gp_async_slots(m->ctx, static_cast<int>(chains.size()));
             if (slots >= 2) {
@@ -757,14 +803,12 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
                 }
             }
             }
-            // reduce (algorithm.rs:942-945): first strictly smaller wins, default theta = 1 (log10 = 0)
-            double fbest = kInf;
-            std::vector<double> zbest(na, 0.0);
             for (auto& ch : chains)
                 if (ch.best_f() < fbest) {
                     fbest = ch.best_f();
                     zbest = ch.best_x();
                 }
+            }
             // algorithm.rs:947-964
             if (prm->theta_tuning == EGX_THETA_PARTIAL) {
                 theta_opt = theta0;

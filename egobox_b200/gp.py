@@ -91,6 +91,7 @@ class GpParams:
         self._device = 0
         self._seed = 42
         self._ftol_rel = 1e-4
+        self._optimizer = "cobyla"
 
     def mean(self, mean):
         self._mean = mean
@@ -139,6 +140,14 @@ class GpParams:
 
     def cobyla_ftol_rel(self, ftol_rel):
         self._ftol_rel = ftol_rel
+        return self
+
+    def optimizer(self, name):
+        """"cobyla" (default, the reference's optimiser) or "lbfgsb": projected L-BFGS per start on the closed-form
+        theta gradient -- same starts and evaluation budget; not in the reference."""
+        if name not in ("cobyla", "lbfgsb"):
+            raise InvalidValueError("optimizer should be 'cobyla' or 'lbfgsb', got %r" % (name,))
+        self._optimizer = name
         return self
 
     def check(self):
@@ -195,6 +204,7 @@ class GpParams:
         elif self._kpls_dim is not None:
             prm.kpls_dim = int(self._kpls_dim)
         prm.device, prm.seed, prm.cobyla_ftol_rel = int(self._device), int(self._seed), float(self._ftol_rel)
+        prm.optimizer = _lib.EGX_OPT_LBFGSB if self._optimizer == "lbfgsb" else _lib.EGX_OPT_COBYLA
         h = C.c_void_p()
         st = lib.egx_gp_fit(C.byref(prm), x.ctypes.data_as(C.POINTER(C.c_double)), n, d,
                             y.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h))
@@ -412,6 +422,31 @@ def bound_cobyla_minimize(fun, x0, bounds, rhobeg=0.5, ftol_rel=1e-4, maxeval=20
     st = lib.egx_bound_cobyla_minimize(cb, None, n, x0.ctypes.data_as(dp), lo.ctypes.data_as(dp),
                                        hi.ctypes.data_as(dp), rhobeg, ftol_rel, maxeval, xopt.ctypes.data_as(dp),
                                        C.byref(fopt), C.byref(nev))
+    if st != EGX_OK:
+        _raise_status(st)
+    return xopt, fopt.value, nev.value
+
+
+def bound_lbfgs_minimize(fun_and_grad, x0, bounds, ftol_rel=1e-9, gtol=1e-7, maxeval=200):
+    """Host-only access to the per-start optimiser of optimizer("lbfgsb"); fun_and_grad(x) -> (f, grad)."""
+    lib = _lib.load()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    n = x0.size
+    lo = np.ascontiguousarray([b[0] for b in bounds], dtype=np.float64)
+    hi = np.ascontiguousarray([b[1] for b in bounds], dtype=np.float64)
+
+    def _cb(xp, nn, gp, _user):
+        f, g = fun_and_grad(np.ctypeslib.as_array(xp, shape=(nn,)).copy())
+        np.ctypeslib.as_array(gp, shape=(nn,))[:] = np.asarray(g, dtype=np.float64)
+        return float(f)
+
+    cb = _lib.OBJECTIVE_GRAD_FN(_cb)
+    xopt = np.empty(n)
+    fopt = C.c_double()
+    nev = C.c_int()
+    dp = C.POINTER(C.c_double)
+    st = lib.egx_bound_lbfgs_minimize(cb, None, n, x0.ctypes.data_as(dp), lo.ctypes.data_as(dp), hi.ctypes.data_as(dp),
+                                      ftol_rel, gtol, maxeval, xopt.ctypes.data_as(dp), C.byref(fopt), C.byref(nev))
     if st != EGX_OK:
         _raise_status(st)
     return xopt, fopt.value, nev.value

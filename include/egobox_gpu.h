@@ -231,6 +231,8 @@ int egx_gp_set_force_blocked(egx_gp_ctx* ctx, int enabled);
 /* GpValidParams, gp/src/parameters.rs:90-120.  Use egx_gp_params_default() to
  * get the reference defaults (theta init 0.1, bounds [1e-2, 10], n_start 10,
  * max_eval 1000, nugget 100*eps, constant mean, squared exponential). */
+#define EGX_OPT_COBYLA 0
+#define EGX_OPT_LBFGSB 1
 typedef struct egx_gp_params {
     int corr;                    /* EGX_CORR_*  */
     int mean;                    /* EGX_MEAN_*  */
@@ -251,6 +253,9 @@ typedef struct egx_gp_params {
     unsigned long long seed;     /* multistart LHS seed (reference: 42, optimization.rs:60-63) */
     double cobyla_rhobeg;        /* 0.5   optimization.rs:19 */
     double cobyla_ftol_rel;      /* 1e-4  optimization.rs:20; <= 0 disables the early stop */
+    int optimizer;               /* EGX_OPT_COBYLA (default, the reference's optimiser) or EGX_OPT_LBFGSB: projected L-BFGS
+                                    per start on the closed-form theta gradient (egx_gp_reduced_likelihood_grad_analytic),
+                                    same starts, same evaluation budget -- not in the reference, opt-in */
 } egx_gp_params;
 
 typedef struct egx_gp_model egx_gp_model;
@@ -297,6 +302,13 @@ int egx_bound_cobyla_minimize(egx_objective_fn f, void* user, int n, const doubl
                               double* x_opt, double* f_opt, int* n_evals);
 int egx_prepare_multistart(int n_start, const double* theta0, const double* bounds, int dim,
                            unsigned long long seed, double* starts_out);
+/* egx_bound_lbfgs_minimize: the per-start optimiser of EGX_OPT_LBFGSB -- projected limited-memory BFGS (8 pairs) with
+ * Armijo backtracking over the box [lo, hi]; fg returns f and writes the gradient.  Stops on
+ * f_prev - f <= ftol_rel * max(|f_prev|, |f|, 1), on |projected gradient|_inf <= gtol * max(1, |f|), or on the budget. */
+typedef double (*egx_objective_grad_fn)(const double* x, int n, double* grad, void* user);
+int egx_bound_lbfgs_minimize(egx_objective_grad_fn fg, void* user, int n, const double* x0, const double* lo,
+                             const double* hi, double ftol_rel, double gtol, int maxeval,
+                             double* x_opt, double* f_opt, int* n_evals);
 /* egx_pls_rotations: `PlsRegression::params(k).fit(&ds)?.rotations().0` of gp/src/algorithm.rs:843-855 and
  * gp/src/sparse_algorithm.rs:442-455 (linfa-pls 0.8.0 = scikit-learn's NIPALS PLSRegression, scale = true):
  * x n x d raw, y n raw -> w_star d x k.  A numerically constant y residual yields zeros, like the reference. */

@@ -88,3 +88,47 @@ def test_closed_form_gradient_rejects_more_than_32_components():
         ctx.reduced_likelihood_grad_analytic(np.full(d, 0.5))
     assert "32 components" in str(e.value)
     ctx.close()
+
+
+def test_fit_with_the_gradient_based_multistart():
+    """optimizer("lbfgsb"): same starts and budget as the COBYLA chains.  Checker: the same host
+    minimiser driven by the ORACLE's closed-form gradient from the same starts -- the device only supplies (rlf, gradient)."""
+    import math
+    import egobox_b200 as egx
+    from egobox_b200 import gp as G
+    n, d = 200, 4
+    x, y = make_problem(n, d, seed=9)
+    base = lambda: egx.GaussianProcess.params().corr(O.MATERN32).n_start(4)
+    gp = base().optimizer("lbfgsb").fit(x, y)
+    gp_cobyla = base().fit(x, y)
+
+    xn, _, _ = O.normalize(x)
+    yn, _, ys = O.normalize(y.reshape(-1, 1))
+    fx = O.mean_value(O.CONSTANT, xn)
+
+    def fg(z):
+        th = 10.0 ** z
+        try:
+            rlf, g = O.reduced_likelihood_grad(O.MATERN32, xn, fx, yn[:, 0], float(ys[0]), th, np.eye(d))
+        except (O.LinalgError, O.LikelihoodComputationError):
+            return math.inf, np.zeros(d)
+        return -rlf, -math.log(10.0) * th * g
+
+    starts = G.prepare_multistart(4, np.full(d, 0.1), [(1e-2, 1e1)] * d, seed=42)
+    best_f, best_z, evals = math.inf, None, 0
+    for s0 in starts:
+        z, f, nev = G.bound_lbfgs_minimize(fg, s0, [(-2.0, 1.0)] * d, ftol_rel=1e-9, gtol=1e-7, maxeval=40)
+        evals += nev
+        if f < best_f:
+            best_f, best_z = f, z
+    assert gp.likelihood() == pytest.approx(-best_f, rel=1e-6)
+    np.testing.assert_allclose(gp.theta(), 10.0 ** best_z, rtol=5e-3)
+    assert gp.n_evals() <= 5 * 40 + 1
+    # likelihood at the returned theta is the oracle's, and the optimum is at least as good as the derivative-free one
+    rlf_o, _ = O.reduced_likelihood(O.MATERN32, xn, fx, yn[:, 0], float(ys[0]), gp.theta(), np.eye(d))
+    assert gp.likelihood() == pytest.approx(rlf_o, rel=1e-9)
+    assert gp.likelihood() >= gp_cobyla.likelihood() - 1e-6 * abs(gp_cobyla.likelihood())
+    xs = np.random.default_rng(1).random((50, d))
+    assert np.all(np.isfinite(gp.predict(xs))) and np.all(gp.predict_var(xs) >= 0.0)
+    gp.close()
+    gp_cobyla.close()

@@ -120,3 +120,58 @@ def test_oracle_covariance_consistent_with_predict_var():
     for method in ("chol", "eig"):
         c = gp.sample(xs, np.eye(15), method) - mean
         np.testing.assert_allclose(c.dot(c.T), cov, atol=2e-9 * 15 + 1e-9 * np.abs(cov).max())
+
+
+# --------------------------------------------------------------------------- projected L-BFGS (optimizer "lbfgsb", not in the reference)
+def _rosen(x):
+    f = np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1.0 - x[:-1]) ** 2)
+    g = np.zeros_like(x)
+    g[:-1] = -400.0 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2.0 * (1.0 - x[:-1])
+    g[1:] += 200.0 * (x[1:] - x[:-1] ** 2)
+    return f, g
+
+
+def test_lbfgs_rosenbrock_against_scipy():
+    from scipy.optimize import minimize
+    x0 = np.array([-1.2, 1.0, -0.5, 0.8, 1.5])
+    bounds = [(-2.0, 2.0)] * 5
+    x, f, nev = G.bound_lbfgs_minimize(_rosen, x0, bounds, ftol_rel=1e-14, gtol=1e-9, maxeval=2000)
+    ref = minimize(_rosen, x0, jac=True, method="L-BFGS-B", bounds=bounds, options={"ftol": 1e-15, "gtol": 1e-10})
+    assert f <= 1e-10 and ref.fun <= 1e-10
+    np.testing.assert_allclose(x, ref.x, atol=1e-4)
+    np.testing.assert_allclose(x, np.ones(5), atol=1e-4)
+    assert nev < 400
+
+
+def test_lbfgs_active_bounds_against_scipy():
+    from scipy.optimize import minimize
+    c = np.array([2.0, -1.0, 0.3])
+
+    def fg(x):
+        return float(np.sum((x - c) ** 2) + 0.5 * x[0] * x[2]), 2.0 * (x - c) + 0.5 * np.array([x[2], 0.0, x[0]])
+
+    bounds = [(0.0, 1.0)] * 3
+    x, f, nev = G.bound_lbfgs_minimize(fg, np.full(3, 0.5), bounds, ftol_rel=1e-15, gtol=1e-10, maxeval=200)
+    ref = minimize(fg, np.full(3, 0.5), jac=True, method="L-BFGS-B", bounds=bounds, options={"ftol": 1e-15, "gtol": 1e-12})
+    np.testing.assert_allclose(x, ref.x, atol=1e-6)
+    assert x[0] == 1.0 and x[1] == 0.0                       # both on their bounds, exactly
+    assert f == pytest.approx(ref.fun, rel=1e-10)
+
+
+def test_lbfgs_budget_inf_and_start_outside_the_box():
+    calls = []
+
+    def fg(x):
+        calls.append(x.copy())
+        if x[0] > 0.8:                                       # Err(_) -> +inf region (algorithm.rs:893-896)
+            return math.inf, np.zeros(2)
+        return float((x[0] - 1.0) ** 2 + (x[1] - 0.2) ** 2), np.array([2.0 * (x[0] - 1.0), 2.0 * (x[1] - 0.2)])
+
+    x, f, nev = G.bound_lbfgs_minimize(fg, np.array([-3.0, 5.0]), [(0.0, 1.0), (0.0, 1.0)], maxeval=60)
+    assert np.all(calls[0] == [0.0, 1.0])                    # start projected into the box
+    assert nev == len(calls) <= 60
+    # the wall is a discontinuity: a line-search method stops against it, short of the constrained optimum (0.8, 0.2)
+    assert 0.7 <= x[0] <= 0.8 and math.isfinite(f) and f < fg(np.array([0.0, 1.0]))[0] and f == fg(x)[0]
+    # an infinite start gives up at once and reports it
+    x, f, nev = G.bound_lbfgs_minimize(lambda z: (math.inf, np.zeros(1)), np.array([0.5]), [(0.0, 1.0)])
+    assert nev == 1 and math.isinf(f) and x[0] == 0.5
