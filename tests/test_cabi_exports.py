@@ -41,3 +41,30 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_header_is_plain_c99_and_the_c_example_links(tmp_path):
+    """The boundary is a C ABI: include/egobox_gpu.h must compile as C99 (what cgo / bindgen / a JNI stub read), and
+    examples/kriging.c -- the reference's crates/gp/examples/kriging.rs through the C ABI -- must link against the shared
+    library alone (no CUDA runtime, no torch).  Without a device it reports the CUDA error and exits 2."""
+    import shutil
+    import subprocess
+    from egobox_b200 import _lib
+    _lib.load()
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "egobox_gpu.h")], check=True)
+    libdir = os.path.join(ROOT, "egobox_b200")
+    exe = str(tmp_path / "kriging_c")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + inc,
+                    os.path.join(ROOT, "examples", "kriging.c"), "-L" + libdir, "-legobox_gpu",
+                    "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    import egobox_b200 as eg
+    if eg.device_count() > 0:
+        assert r.returncode == 0 and "likelihood" in r.stdout, r.stderr
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
