@@ -3,8 +3,8 @@
 Same builder signature, defaults and return shapes as the PyO3 classes; the model behind it is a
 ``egobox_b200.moe.GpMixture``: one B200-resident GaussianProcess expert per cluster, multi-bit
 ``regr_spec`` / ``corr_spec`` resolved by the 5-fold cross-validation of moe/src/algorithm.rs:209-347
-(a batch of GPU fits), hard / smooth recombination on the device.  Only the automatic choice of the
-NUMBER of clusters (``n_clusters <= 0``, moe/src/clustering.rs:62-300) is not provided."""
+(a batch of GPU fits), hard / smooth recombination on the device; ``n_clusters <= 0`` picks the number of clusters (and hard / smooth recombination) by the
+cross-validated search of moe/src/clustering.rs:59-390 (``moe.find_best_number_of_clusters``)."""
 from __future__ import annotations
 
 import json
@@ -72,13 +72,11 @@ class GpMix:
         if n_start < 0:                                            # gp_mix.rs:200-206
             tuning = _gp.ThetaTuning.Fixed(tuning.init)
             n_start = 0
-        if self.n_clusters <= 0:
-            raise NotImplementedError("automatic number of clusters (n_clusters <= 0, moe/src/clustering.rs:62-300) "
-                                      "is egobox-moe's control plane: pass n_clusters >= 1")
+        # n_clusters = 0: automatic, < 0: automatic up to -n_clusters (gp_mix.rs:197-201); one tuning then serves all experts
         params = _moe.GpMixtureParams().set(
             n_clusters=int(self.n_clusters), recombination=int(self.recombination),
             regression_spec=int(self.regr_spec), correlation_spec=int(self.corr_spec),
-            theta_tunings=[tuning] * int(self.n_clusters), kpls_dim=self.kpls_dim, w_star=self.w_star,
+            theta_tunings=[tuning] * max(int(self.n_clusters), 1), kpls_dim=self.kpls_dim, w_star=self.w_star,
             n_start=n_start, max_eval=MOE_GP_MAX_EVAL, gmx=self.gmx, seed=self.seed, device=self.device)
         return Gpx(params.fit(xt, yt), self)
 

@@ -266,6 +266,127 @@ def extract_part(data, quantile):
     return data[~mask], data[mask]
 
 
+def _folds(n, k):
+    """linfa `Dataset::fold(k)`: validation rows [i fs, (i + 1) fs) with fs = n / k, everything else trains."""
+    fs = n // k
+    for i in range(k):
+        va = np.arange(i * fs, (i + 1) * fs)
+        tr = np.concatenate([np.arange(0, i * fs), np.arange((i + 1) * fs, n)])
+        yield tr, va
+
+
+def _median(v):
+    return float(np.median(v)) if len(v) else math.nan
+
+
+def find_best_number_of_clusters(x, y, max_nb_clusters, fit_mixture, seed=None, gmm_fit=None):
+    """moe/src/clustering.rs:59-390 (`NbClusters::Auto`): for 1, 2, ... clusters, 5-fold cross-validation of a mixture
+    trained with that many clusters; hard-recombination error sum|pred - y| / sum|y| and smooth(1.0) error
+    sum|pred - y| (:196-227, the two are scaled differently in the reference and compared as they are, :354-362);
+    the count with the smallest MEDIAN error wins, and with it hard or smooth(None) recombination.  The search stops
+    when both medians rose twice in a row (:290-300) and only looks at counts whose every cluster kept more than 3
+    values (rows x columns, :169-172) in every fold.
+
+    fit_mixture(n_clusters, xtrain, ytrain) -> object with predict_hard(x), predict_smooth1(x), close(); a raised
+    GpError counts as the reference's failed `fit` (:229-233).  Returns (n_clusters, recombination, heaviside) with
+    heaviside None = to be optimised."""
+    x = _f64(x)
+    y = _f64(y).reshape(-1)
+    n, nx = x.shape
+    if gmm_fit is None:
+        gmm_fit = fit_gmm
+    if max_nb_clusters == 0:
+        max_nb_clusters = n // 10 + 1
+    data = np.concatenate([x, y[:, None]], axis=1)
+    med_h, med_s, ok_counts = [], [], []
+    ok1 = True
+    i, stop = 0, False
+    while i < max_nb_clusters and not stop:
+        k = i + 1
+        h_errors, s_errors = [], []
+        ok = True
+        try:
+            gmm = gmm_fit(data, k, seed=seed)
+        except _gp.GpError:
+            gmm = None
+        if gmm is not None:
+            for tr, va in _folds(n, 5):
+                try:
+                    mix = fit_mixture(k, x[tr], y[tr])
+                except _gp.GpError:
+                    ok = False
+                    s_errors.append(1.0)
+                    h_errors.append(1.0)
+                    continue
+                try:
+                    labels = np.argmax(_e_step(data[tr], *gmm)[1], axis=1)
+                    for c in range(k):
+                        ok = ok and int((labels == c).sum()) * (nx + 1) > 3
+                    actual = y[va]
+                    for which, errs in (("h", h_errors), ("s", s_errors)):
+                        try:
+                            pred = mix.predict_hard(x[va]) if which == "h" else mix.predict_smooth1(x[va])
+                        except _gp.GpError:
+                            ok = False
+                            errs.append(1.0)
+                            continue
+                        if np.any(np.isinf(pred)):
+                            errs.append(1.0)
+                        elif np.any(np.isnan(pred)):
+                            ok = False
+                            errs.append(1.0)
+                        elif which == "h":
+                            errs.append(float(np.abs(pred - actual).sum() / np.abs(actual).sum()))
+                        else:
+                            errs.append(float(np.abs(pred - actual).sum()))
+                finally:
+                    mix.close()
+        if ok and s_errors and h_errors:
+            ok_counts.append(i)
+        med_s.append(_median(s_errors))
+        med_h.append(_median(h_errors))
+        if i > 3:
+            ok2, ok1 = ok1, ok
+            stop = (not ok) and (not ok1) and (not ok2)
+            stop = (med_h[i - 1] >= med_h[i - 2] and med_s[i - 1] >= med_s[i - 2] and
+                    med_h[i] >= med_h[i - 1] and med_s[i] >= med_s[i - 1])          # the median rule has the last word
+        i += 1
+    if not ok_counts:
+        return 1, SMOOTH, None
+    cluster_h = cluster_s = 1
+    min_h, min_s = med_h[ok_counts[0]], med_s[ok_counts[0]]
+    for k in ok_counts:
+        if min_h > med_h[k]:
+            min_h, cluster_h = med_h[k], k + 1
+        if min_s > med_s[k]:
+            min_s, cluster_s = med_s[k], k + 1
+    if med_h[cluster_h - 1] < med_s[cluster_s - 1]:
+        return cluster_h, HARD, None
+    return cluster_s, SMOOTH, None
+
+
+class _CvMixture:
+    """The two predictions the cluster-count search needs from a trained mixture (hard, and smooth with factor 1)."""
+
+    def __init__(self, mix):
+        self.mix = mix
+
+    def predict_hard(self, x):
+        m = self.mix
+        return m.experts[0].predict(x) if m._one() else m.gmx._predict(HARD, x, ("y",))[0]
+
+    def predict_smooth1(self, x):
+        m = self.mix
+        if m._one():
+            return m.experts[0].predict(x)
+        if m.gmx.heaviside_factor() != 1.0:
+            m.gmx.set_heaviside_factor(1.0)
+        return m.gmx._predict(SMOOTH, x, ("y",))[0]
+
+    def close(self):
+        self.mix.close()
+
+
 # ----------------------------------------------------------------------------------------------------
 # GpMixtureParams / GpMixture
 # ----------------------------------------------------------------------------------------------------
@@ -350,8 +471,23 @@ class GpMixtureParams:
         xt = _f64(xt)
         yt = _f64(yt).reshape(-1)
         if self.n_clusters < 1:
-            raise NotImplementedError("automatic number of clusters (NbClusters::Auto, moe/src/clustering.rs:62-300) "
-                                      "is egobox-moe's control plane: pass n_clusters >= 1")
+            # NbClusters::Auto { max } (moe/src/algorithm.rs:85-101): n_clusters = 0 -> up to n / 10 + 1, -m -> up to m
+            def cv_fit(k, xtr, ytr):
+                # GpMixtureParams::default() + the three specs (clustering.rs:148-154); its preset `gmm` is never read
+                # by `train` (algorithm.rs:118 looks at `gmx` only), so every fold clusters its own training rows
+                p = GpMixtureParams().set(n_clusters=k, regression_spec=self.regression_spec,
+                                          correlation_spec=self.correlation_spec, kpls_dim=self.kpls_dim,
+                                          seed=self.seed, device=self.device)
+                return _CvMixture(p.fit(xtr, ytr))
+
+            max_nb = -self.n_clusters if self.n_clusters < 0 else xt.shape[0] // 10 + 1
+            k, recomb, heaviside = find_best_number_of_clusters(xt, yt, max_nb, cv_fit, seed=self.seed)
+            chosen = GpMixtureParams()
+            chosen.__dict__.update(self.__dict__)
+            chosen.n_clusters, chosen.recombination, chosen.heaviside = k, recomb, heaviside
+            if len(chosen.theta_tunings) != k:
+                chosen.theta_tunings = [self.theta_tunings[0]]          # one tuning for all experts (gp_mix.rs:210-214)
+            return chosen.fit(xt, yt)
         nx = xt.shape[1]
         data = np.concatenate([xt, yt[:, None]], axis=1)
         multi = self.n_clusters > 1
