@@ -161,3 +161,40 @@ def test_cluster_search_rules_with_scripted_errors():
     # max_nb_clusters = 0 -> n / 10 + 1 = 11 candidates at most (the rise rule may stop earlier)
     (_, _, _), calls = run({k: (1.0 / k, 1.0 / k) for k in range(1, 12)}, 0)
     assert max(calls) == 11
+
+
+def test_auto_cluster_glue_in_fit_without_a_device(monkeypatch):
+    """GpMixtureParams.fit with n_clusters <= 0: the search result is turned into a fixed-count fit with the chosen
+    recombination.  The device classes are replaced by recorders, only the host glue runs here."""
+    from egobox_b200 import moe as E
+    fits = []
+
+    class FakeGmx:
+        def __init__(self, w, mu, cov, factor, device):
+            self.k = len(w)
+
+        def n_clusters(self):
+            return self.k
+
+    class FakeMix:
+        def __init__(self, k):
+            self.k = k
+
+    def fake_train(self, xt, yt, gmx):
+        fits.append((self.n_clusters, self.recombination, self.heaviside, xt.shape[0], len(self.theta_tunings)))
+        return FakeMix(gmx.n_clusters())
+
+    monkeypatch.setattr(E, "GaussianMixture", FakeGmx)
+    monkeypatch.setattr(E.GpMixtureParams, "train_on_clusters", fake_train)
+    monkeypatch.setattr(E, "find_best_number_of_clusters",
+                        lambda x, y, max_nb, fit_mixture, seed=None: (fits.append(("search", max_nb)), (3, E.SMOOTH, None))[1])
+    x = np.linspace(0.0, 1.0, 60)[:, None]
+    y = _f_test_1d(x)
+    mix = E.GpMixtureParams().set(n_clusters=0, seed=1).fit(x, y)
+    assert fits[0] == ("search", 7)                                   # n / 10 + 1
+    # 3 clusters, Smooth(None) (the heaviside search follows inside train_on_clusters), one tuning for all experts; the
+    # experts see every row -- only the clustering is trained on the 95 % split (algorithm.rs:108-116, 143)
+    assert fits[1] == (3, E.SMOOTH, None, 60, 1) and mix.k == 3
+    fits.clear()
+    E.GpMixtureParams().set(n_clusters=-4, seed=1).fit(x, y)
+    assert fits[0] == ("search", 4)
