@@ -263,9 +263,9 @@ typedef struct egx_gp_model egx_gp_model;
 void egx_gp_params_default(egx_gp_params* p);
 
 /* impl Fit for GpValidParams::fit, gp/src/algorithm.rs:791-979.
- * x: n x d raw inputs, y: n raw outputs.  The n_start+1 COBYLA chains are
- * advanced in lock step so that every optimiser iteration is one
- * egx_gp_reduced_likelihood_batch call (the rayon fan-out of :928-945). */
+ * x: n x d raw inputs, y: n raw outputs.  The n_start+1 COBYLA chains are independent, as in the
+ * reference (the rayon fan-out of :928-945): their evaluations overlap on the workspace slots of the
+ * asynchronous seam (egx_gp_eval_begin / egx_gp_eval_end). */
 int egx_gp_fit(const egx_gp_params* params, const double* x, int n, int d, const double* y,
                egx_gp_model** out);
 void egx_gp_model_destroy(egx_gp_model* m);
