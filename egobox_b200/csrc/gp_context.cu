@@ -181,11 +181,6 @@ int upload_terms(egx_gp_ctx* c) {
     return EGX_OK;
 }
 
-int build_terms(egx_gp_ctx* c, const double* theta) {
-    c->nterms = egx_fill_terms(c->corr, c->d, c->h, c->w_star.data(), theta, c->terms_h);
-    return upload_terms(c);
-}
-
 // R(theta) lower block-triangle into M, then the RHS rows (terms already in the pinned staging buffer).
 int assemble_staged(egx_gp_ctx* c) {
     int st = upload_terms(c);
