@@ -7,12 +7,17 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+# Written after this round's GPU minutes were spent: neither test has run on a B200 yet.  Non-strict xfail keeps an
+# unverified test from stopping `pytest -x`; the marker goes once the first GPU run has been looked at (XPASS = it holds).
+_unverified = pytest.mark.xfail(strict=False, reason="not yet run on a B200 (GPU budget of the round exhausted)")
+
 
 def _f_test_1d(x):
     x = x[:, 0]
     return np.where(x < 0.4, x * x, np.where(x < 0.8, 3.0 * x + 1.0, np.sin(10.0 * x)))
 
 
+@_unverified
 def test_moe_auto():
     import egobox_b200 as egx
     xt = np.random.default_rng(42).random((60, 1))
@@ -24,3 +29,19 @@ def test_moe_auto():
     gpx2 = egx.Gpx.builder(n_clusters=-2, seed=42).fit(xt, yt)
     assert 1 <= gpx2.thetas().shape[0] <= 2
     assert np.all(np.isfinite(gpx2.predict(xt)))
+
+
+@_unverified
+def test_constant_function():
+    """gp/src/algorithm.rs:1217-1237: y = 3.1 everywhere, KPLS with one component.  The PLS power method reports a constant
+    residual -> all-zero rotations (:846-851) -> R = ones + nugget I, sigma2 = 0, likelihood +inf; the fit must still come
+    back and predict the constant."""
+    import egobox_b200 as egx
+    from oracle import gp_oracle as O
+    xt = O.lhs_classic(np.array([[0.0, 1.0]] * 3), 5, np.random.default_rng(42))
+    yt = np.full(5, 3.1)
+    gp = egx.GaussianProcess.params().theta_init([0.1]).kpls_dim(1).fit(xt, yt)
+    xtest = O.lhs_classic(np.array([[0.0, 1.0]] * 3), 5, np.random.default_rng(43))
+    np.testing.assert_allclose(gp.predict(xtest), np.full(5, 3.1), atol=1e-6)
+    assert np.all(gp.predict_var(xtest) >= 0.0)
+    gp.close()
