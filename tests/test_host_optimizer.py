@@ -175,3 +175,26 @@ def test_lbfgs_budget_inf_and_start_outside_the_box():
     # an infinite start gives up at once and reports it
     x, f, nev = G.bound_lbfgs_minimize(lambda z: (math.inf, np.zeros(1)), np.array([0.5]), [(0.0, 1.0)])
     assert nev == 1 and math.isinf(f) and x[0] == 0.5
+
+
+@pytest.mark.parametrize("n,d,corr,seed", [(60, 2, O.SQEXP, 1), (80, 3, O.MATERN52, 2), (90, 5, O.ABSEXP, 5)])
+def test_multistart_reaches_the_likelihood_of_powells_cobyla(n, d, corr, seed):
+    """The reference optimises with the third-party `cobyla 0.8.0` crate (Powell's COBYLA, optimization.rs:122-169), which is
+    not under /root/reference; the chain optimiser here is of the same family, not a transcription.  What a fit returns is
+    the best likelihood over the multistart: with the reference's settings (11 starts, rhobeg 0.5, ftol_rel 1e-4,
+    clamp(10 d, 25, 1000) evaluations per start) it must reach what Powell's algorithm (scipy's COBYLA) reaches from the same
+    starts, to 5e-4 relative."""
+    from scipy.optimize import minimize
+    from tests.gpu_util import make_problem
+    x, y = make_problem(n, d, seed=seed)
+    xn, _, _ = O.normalize(x)
+    yn, _, ys = O.normalize(y.reshape(-1, 1))
+    fx = O.mean_value(O.CONSTANT, xn)
+    obj = lambda z: O.objective(corr, xn, fx, yn[:, 0], float(ys[0]), 10.0 ** np.asarray(z), np.eye(d))
+    starts = G.prepare_multistart(10, np.full(d, 0.1), [(1e-2, 1e1)] * d, seed=42)
+    bounds = [(-2.0, 1.0)] * d
+    maxeval = min(max(10 * d, 25), 1000)
+    mine = min(G.bound_cobyla_minimize(obj, s0, bounds, rhobeg=0.5, ftol_rel=1e-4, maxeval=maxeval)[1] for s0 in starts)
+    powell = min(minimize(obj, s0, method="COBYLA", bounds=bounds,
+                          options={"rhobeg": 0.5, "maxiter": maxeval, "tol": 1e-4}).fun for s0 in starts)
+    assert mine <= powell + 5e-4 * abs(powell)
