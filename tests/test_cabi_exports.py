@@ -68,3 +68,22 @@ def test_header_is_plain_c99_and_the_c_example_links(tmp_path):
         assert r.returncode == 0 and "likelihood" in r.stdout, r.stderr
     else:
         assert r.returncode == 2 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
+
+
+def test_host_only_entry_points_from_plain_c(tmp_path):
+    """tests/c/host_abi.c: optimisers, multistart seeds, eigen-solver and PLS rotations called from C99 with no Python in
+    between -- the way a cgo / JNI / Rust FFI consumer reaches them."""
+    import shutil
+    import subprocess
+    from egobox_b200 import _lib
+    _lib.load()
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "egobox_b200")
+    exe = str(tmp_path / "host_abi")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "host_abi.c"), "-L" + libdir, "-legobox_gpu", "-Wl,-rpath," + libdir,
+                    "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "host ABI ok" in r.stdout, r.stderr
