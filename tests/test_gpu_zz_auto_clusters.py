@@ -18,6 +18,7 @@ def _f_test_1d(x):
 
 
 @_unverified
+@pytest.mark.timeout(600)
 def test_moe_auto():
     import egobox_b200 as egx
     xt = np.random.default_rng(42).random((60, 1))
@@ -32,6 +33,7 @@ def test_moe_auto():
 
 
 @_unverified
+@pytest.mark.timeout(300)
 def test_constant_function():
     """gp/src/algorithm.rs:1217-1237: y = 3.1 everywhere, KPLS with one component.  The PLS power method reports a constant
     residual -> all-zero rotations (:846-851) -> R = ones + nugget I, sigma2 = 0, likelihood +inf; the fit must still come
