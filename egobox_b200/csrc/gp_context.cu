@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "sweep.cuh"
 #include "../../include/egobox_gpu.h"
+#include "abi_guard.h"
 
 // ---------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -28,7 +29,7 @@ void egx_set_error(const char* fmt, ...) {
 }
 extern "C" const char* egx_last_error(void) { return g_err; }
 extern "C" const char* egx_version(void) { return "egobox_b200 0.1 (sm_100a)"; }
-extern "C" int egx_device_count(void) {
+extern "C" int egx_device_count(void) try {
     int c = 0;
     if (cudaGetDeviceCount(&c) != cudaSuccess) {
         cudaGetLastError();
@@ -36,6 +37,7 @@ extern "C" int egx_device_count(void) {
     }
     return c;
 }
+EGX_ABI_CATCH
 
 namespace {
 
@@ -606,7 +608,7 @@ void free_ctx(egx_gp_ctx* c) {
 // ---------------------------------------------------------------------------
 extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, const double* xnorm, int n, int d,
                              const double* ynorm, const double* x_mean, const double* x_std, double y_mean,
-                             double y_std, const double* w_star, int h, double nugget) {
+                             double y_std, const double* w_star, int h, double nugget) try {
     if (!out) return EGX_INVALID_VALUE;
     *out = nullptr;
     if (n < 1 || d < 1 || h < 1 || h > d || !xnorm || !ynorm || !x_mean || !x_std || !w_star || corr < 0 ||
@@ -724,10 +726,11 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
     *out = c;
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
 extern "C" void egx_gp_destroy(egx_gp_ctx* ctx) { free_ctx(ctx); }
 
-extern "C" int egx_gp_dims(const egx_gp_ctx* c, int* n, int* d, int* h, int* p) {
+extern "C" int egx_gp_dims(const egx_gp_ctx* c, int* n, int* d, int* h, int* p) try {
     if (!c) return EGX_INVALID_VALUE;
     if (n) *n = c->n;
     if (d) *d = c->d;
@@ -735,8 +738,9 @@ extern "C" int egx_gp_dims(const egx_gp_ctx* c, int* n, int* d, int* h, int* p) 
     if (p) *p = c->p;
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_reduced_likelihood(egx_gp_ctx* c, const double* theta, double* rlf) {
+extern "C" int egx_gp_reduced_likelihood(egx_gp_ctx* c, const double* theta, double* rlf) try {
     if (!c || !theta || !rlf) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
@@ -747,8 +751,9 @@ extern "C" int egx_gp_reduced_likelihood(egx_gp_ctx* c, const double* theta, dou
     }
     return evaluate(c, theta, rlf);
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thetas, int B, double* rlf, int* status) {
+extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thetas, int B, double* rlf, int* status) try {
     if (!c || !thetas || !rlf || !status || B < 0) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
@@ -803,6 +808,7 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
     }
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
 // ---------------------------------------------------------------------------------------------------------------
 // Asynchronous seam for independent optimiser chains (the rayon fan-out of gp/src/algorithm.rs:928-945 runs every
@@ -810,7 +816,7 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
 // back proposes its next theta while the evaluations of the other chains are still running, so there is no
 // per-iteration barrier across chains.
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int egx_gp_async_slots(egx_gp_ctx* c, int wanted) {
+extern "C" int egx_gp_async_slots(egx_gp_ctx* c, int wanted) try {
     if (!c || wanted < 1) return 0;
     std::lock_guard<std::mutex> lk(c->mu);
     if (cudaSetDevice(c->device) != cudaSuccess) return 0;
@@ -830,8 +836,9 @@ extern "C" int egx_gp_async_slots(egx_gp_ctx* c, int wanted) {
     c->async_slots = W;
     return W;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_eval_begin(egx_gp_ctx* c, int slot, const double* theta) {
+extern "C" int egx_gp_eval_begin(egx_gp_ctx* c, int slot, const double* theta) try {
     if (!c || !theta || slot < 0 || slot >= c->async_slots) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
@@ -846,8 +853,9 @@ extern "C" int egx_gp_eval_begin(egx_gp_ctx* c, int slot, const double* theta) {
     w->env.lookahead = la_saved;
     return st;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_eval_end(egx_gp_ctx* c, int slot, double* rlf) {
+extern "C" int egx_gp_eval_end(egx_gp_ctx* c, int slot, double* rlf) try {
     if (!c || !rlf || slot < 0 || slot >= c->async_slots) return EGX_INVALID_VALUE;
     egx_gp_ctx* w = nullptr;
     {
@@ -863,9 +871,10 @@ extern "C" int egx_gp_eval_end(egx_gp_ctx* c, int slot, double* rlf) {
     EGX_CUDA_TRY(cudaSetDevice(c->device));
     return evaluate_collect(w, rlf);
 }
+EGX_ABI_CATCH
 
 extern "C" int egx_gp_reduced_likelihood_grad(egx_gp_ctx* c, const double* theta, double rel_step, double* rlf,
-                                              double* grad) {
+                                              double* grad) try {
     if (!c || !theta || !rlf || !grad || !(rel_step > 0.0)) return EGX_INVALID_VALUE;
     const int h = c->h, B = 2 * h + 1;
     std::vector<double> th(static_cast<size_t>(B) * h), val(B);
@@ -886,11 +895,12 @@ extern "C" int egx_gp_reduced_likelihood_grad(egx_gp_ctx* c, const double* theta
     }
     return st[0];
 }
+EGX_ABI_CATCH
 
 // d rlf / d theta in closed form (kernels_thetagrad.cu):  one evaluation, W = L^-T by the multi-RHS sweep on the identity
 // (only the row tiles above each column pair: a third of the full sweep), gamma = W rho, -R^-1 = -W W^T (W is upper triangular: column panel kp only touches the rows above its end, so the SYRK is a
 // sum of growing triangles -- on tcgen05 where the triangle is large enough, else DMMA), then the pair kernel.
-extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const double* theta, double* rlf, double* grad) {
+extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const double* theta, double* rlf, double* grad) try {
     if (!c || !theta || !rlf || !grad) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     const int h = c->h, npad = c->npad, T = npad / EGX_NB;
@@ -978,9 +988,10 @@ extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const doub
     std::memcpy(grad, c->tgGrad_h, h * sizeof(double));
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
 extern "C" int egx_gp_finalize(egx_gp_ctx* c, const double* theta, double* rlf, double* sigma2, double* beta,
-                               double* gamma, double* ft, double* ft_qr_r) {
+                               double* gamma, double* ft, double* ft_qr_r) try {
     if (!c || !theta) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
@@ -1012,8 +1023,9 @@ extern "C" int egx_gp_finalize(egx_gp_ctx* c, const double* theta, double* rlf, 
     c->trained = true;
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_download_chol(egx_gp_ctx* c, double* r_chol) {
+extern "C" int egx_gp_download_chol(egx_gp_ctx* c, double* r_chol) try {
     if (!c || !r_chol) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     if (!c->trained) {
@@ -1027,47 +1039,55 @@ extern "C" int egx_gp_download_chol(egx_gp_ctx* c, double* r_chol) {
         for (int j = i + 1; j < c->n; ++j) r_chol[static_cast<size_t>(i) * c->n + j] = 0.0;
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_predict(egx_gp_ctx* c, const double* x, int m, double* y) {
+extern "C" int egx_gp_predict(egx_gp_ctx* c, const double* x, int m, double* y) try {
     if (!c || !y) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_impl(c, x, m, y, nullptr, false);
 }
-extern "C" int egx_gp_predict_var(egx_gp_ctx* c, const double* x, int m, double* var) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_predict_var(egx_gp_ctx* c, const double* x, int m, double* var) try {
     if (!c || !var) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_impl(c, x, m, nullptr, var, false);
 }
-extern "C" int egx_gp_predict_valvar(egx_gp_ctx* c, const double* x, int m, double* y, double* var) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_predict_valvar(egx_gp_ctx* c, const double* x, int m, double* y, double* var) try {
     if (!c || !y || !var) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_impl(c, x, m, y, var, false);
 }
+EGX_ABI_CATCH
 namespace {
 int predict_gradients_impl(egx_gp_ctx* c, const double* x, int m, double* grad, bool device_ptrs);
 int predict_var_gradients_impl(egx_gp_ctx* c, const double* x, int m, double* grad, bool device_ptrs);
 }  // namespace
-extern "C" int egx_gp_predict_gradients(egx_gp_ctx* c, const double* x, int m, double* grad) {
+extern "C" int egx_gp_predict_gradients(egx_gp_ctx* c, const double* x, int m, double* grad) try {
     if (!c || !x || !grad || m < 0) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_gradients_impl(c, x, m, grad, false);
 }
-extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int m, double* grad) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_predict_var_gradients(egx_gp_ctx* c, const double* x, int m, double* grad) try {
     if (!c || !x || !grad || m < 0) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_var_gradients_impl(c, x, m, grad, false);
 }
+EGX_ABI_CATCH
 /* device-pointer variants: x_dev (m x d) and grad_dev (m x d) live on the context's device */
-extern "C" int egx_gp_predict_gradients_dev(egx_gp_ctx* c, const double* x_dev, int m, double* grad_dev) {
+extern "C" int egx_gp_predict_gradients_dev(egx_gp_ctx* c, const double* x_dev, int m, double* grad_dev) try {
     if (!c || !x_dev || !grad_dev || m < 0) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_gradients_impl(c, x_dev, m, grad_dev, true);
 }
-extern "C" int egx_gp_predict_var_gradients_dev(egx_gp_ctx* c, const double* x_dev, int m, double* grad_dev) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_predict_var_gradients_dev(egx_gp_ctx* c, const double* x_dev, int m, double* grad_dev) try {
     if (!c || !x_dev || !grad_dev || m < 0) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_var_gradients_impl(c, x_dev, m, grad_dev, true);
 }
+EGX_ABI_CATCH
 namespace {
 int predict_gradients_impl(egx_gp_ctx* c, const double* x, int m, double* grad, bool device_ptrs) {
     if (!c->trained) {
@@ -1289,7 +1309,7 @@ int conditional_cov_dev(egx_gp_ctx* c, const double* x, int m, CovWork& w) {
 
 }  // namespace
 
-extern "C" int egx_gp_covariance(egx_gp_ctx* c, const double* x, int m, double* cov) {
+extern "C" int egx_gp_covariance(egx_gp_ctx* c, const double* x, int m, double* cov) try {
     if (!c || !x || !cov) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     CovWork w;
@@ -1303,9 +1323,10 @@ extern "C" int egx_gp_covariance(egx_gp_ctx* c, const double* x, int m, double* 
     resolve_profile(c);
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
 extern "C" int egx_gp_sample(egx_gp_ctx* c, const double* x, int m, const double* z, int n_traj, int method,
-                             double* out) {
+                             double* out) try {
     if (!c || !x || !z || !out || n_traj < 1) return EGX_INVALID_VALUE;
     if (method != EGX_SAMPLE_CHOLESKY && method != EGX_SAMPLE_EIGENVALUES) {
         egx_set_error("unknown sampling method %d", method);
@@ -1403,14 +1424,16 @@ extern "C" int egx_gp_sample(egx_gp_ctx* c, const double* x, int m, const double
     resolve_profile(c);
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_predict_valvar_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, double* var_dev) {
+extern "C" int egx_gp_predict_valvar_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, double* var_dev) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return predict_impl(c, x_dev, m, y_dev, var_dev, true);
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_correlation_matrix(egx_gp_ctx* c, const double* theta, double* r) {
+extern "C" int egx_gp_correlation_matrix(egx_gp_ctx* c, const double* theta, double* r) try {
     if (!c || !theta || !r) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
@@ -1426,8 +1449,9 @@ extern "C" int egx_gp_correlation_matrix(egx_gp_ctx* c, const double* theta, dou
         for (int j = i + 1; j < c->n; ++j) r[static_cast<size_t>(i) * c->n + j] = r[static_cast<size_t>(j) * c->n + i];
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_cross_correlation(egx_gp_ctx* c, const double* x, int m, double* out) {
+extern "C" int egx_gp_cross_correlation(egx_gp_ctx* c, const double* x, int m, double* out) try {
     if (!c || !x || !out || m < 1) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     if (!c->trained) {
@@ -1456,22 +1480,25 @@ extern "C" int egx_gp_cross_correlation(egx_gp_ctx* c, const double* x, int m, d
     resolve_profile(c);
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_set_profiling(egx_gp_ctx* c, int enabled) {
+extern "C" int egx_gp_set_profiling(egx_gp_ctx* c, int enabled) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     c->env.prof.on = enabled != 0;
     for (egx_gp_ctx* r : c->replicas) r->env.prof.on = c->env.prof.on;
     return EGX_OK;
 }
-extern "C" int egx_gp_reset_profile(egx_gp_ctx* c) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_reset_profile(egx_gp_ctx* c) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     c->env.prof.reset();
     for (egx_gp_ctx* r : c->replicas) r->env.prof.reset();
     return EGX_OK;
 }
-extern "C" int egx_gp_get_profile(egx_gp_ctx* c, double* ms, long long* launches) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_get_profile(egx_gp_ctx* c, double* ms, long long* launches) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     for (int i = 0; i < EGX_NUM_STAGES; ++i) {
@@ -1484,7 +1511,8 @@ extern "C" int egx_gp_get_profile(egx_gp_ctx* c, double* ms, long long* launches
     }
     return EGX_OK;
 }
-extern "C" int egx_gp_timer_start(egx_gp_ctx* c) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_timer_start(egx_gp_ctx* c) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
@@ -1495,7 +1523,8 @@ extern "C" int egx_gp_timer_start(egx_gp_ctx* c) {
     EGX_CUDA_TRY(cudaEventRecord(c->timer_a, c->stream));
     return EGX_OK;
 }
-extern "C" int egx_gp_timer_stop(egx_gp_ctx* c, double* elapsed_ms) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_timer_stop(egx_gp_ctx* c, double* elapsed_ms) try {
     if (!c || !elapsed_ms || !c->timer_a) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
@@ -1510,16 +1539,19 @@ extern "C" int egx_gp_timer_stop(egx_gp_ctx* c, double* elapsed_ms) {
     *elapsed_ms = ms;
     return EGX_OK;
 }
-extern "C" int egx_gp_set_lookahead(egx_gp_ctx* c, int enabled) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_set_lookahead(egx_gp_ctx* c, int enabled) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     c->env.lookahead = enabled != 0;
     for (egx_gp_ctx* r : c->replicas) r->env.lookahead = c->env.lookahead;
     return EGX_OK;
 }
-extern "C" int egx_gp_set_force_blocked(egx_gp_ctx* c, int enabled) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_set_force_blocked(egx_gp_ctx* c, int enabled) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     c->force_blocked = enabled != 0;
     return EGX_OK;
 }
+EGX_ABI_CATCH

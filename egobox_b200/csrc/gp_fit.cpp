@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/egobox_gpu.h"
+#include "abi_guard.h"
 
 void egx_set_error(const char* fmt, ...);
 
@@ -498,7 +499,7 @@ struct egx_gp_model {
 // callers that want the reference's `optimize_params` (optimization.rs:122-169) semantics.
 extern "C" int egx_bound_cobyla_minimize(egx_objective_fn f, void* user, int n, const double* x0, const double* lo,
                                          const double* hi, double rhobeg, double ftol_rel, int maxeval,
-                                         double* x_opt, double* f_opt, int* n_evals) {
+                                         double* x_opt, double* f_opt, int* n_evals) try {
     if (!f || !x0 || !lo || !hi || n < 1 || !x_opt || !f_opt) return EGX_INVALID_VALUE;
     BoundCobyla opt(std::vector<double>(x0, x0 + n), std::vector<double>(lo, lo + n), std::vector<double>(hi, hi + n),
                     rhobeg, ftol_rel, maxeval);
@@ -514,10 +515,11 @@ extern "C" int egx_bound_cobyla_minimize(egx_objective_fn f, void* user, int n, 
     if (n_evals) *n_evals = opt.nfev();
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
 // prepare_multistart seeds (optimization.rs:26-71): (n_start + 1) x dim log10 starts
 extern "C" int egx_prepare_multistart(int n_start, const double* theta0, const double* bounds, int dim,
-                                      unsigned long long seed, double* starts_out) {
+                                      unsigned long long seed, double* starts_out) try {
     if (!theta0 || !bounds || dim < 1 || n_start < 0 || !starts_out) return EGX_INVALID_VALUE;
     for (int i = 0; i < dim; ++i) starts_out[i] = std::log10(theta0[i]);
     Xoshiro256Plus rng(seed);
@@ -536,6 +538,7 @@ extern "C" int egx_prepare_multistart(int n_start, const double* theta0, const d
     }
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
 extern "C" void egx_gp_params_default(egx_gp_params* p) {
     if (!p) return;
@@ -558,7 +561,7 @@ extern "C" void egx_gp_model_destroy(egx_gp_model* m) {
 }
 
 extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int d, const double* y,
-                          egx_gp_model** out) {
+                          egx_gp_model** out) try {
     if (!out) return EGX_INVALID_VALUE;
     *out = nullptr;
     if (!prm || !x || !y || n < 1 || d < 1) {
@@ -829,8 +832,9 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
     *out = m.release();
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_model_dims(const egx_gp_model* m, int* n, int* d, int* h, int* p) {
+extern "C" int egx_gp_model_dims(const egx_gp_model* m, int* n, int* d, int* h, int* p) try {
     if (!m) return EGX_INVALID_VALUE;
     if (n) *n = m->n;
     if (d) *d = m->d;
@@ -838,18 +842,20 @@ extern "C" int egx_gp_model_dims(const egx_gp_model* m, int* n, int* d, int* h, 
     if (p) *p = m->p;
     return EGX_OK;
 }
-extern "C" int egx_gp_model_theta(const egx_gp_model* m, double* theta) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_model_theta(const egx_gp_model* m, double* theta) try {
     if (!m || !theta) return EGX_INVALID_VALUE;
     std::memcpy(theta, m->theta.data(), sizeof(double) * m->h);
     return EGX_OK;
 }
+EGX_ABI_CATCH
 extern "C" double egx_gp_model_variance(const egx_gp_model* m) { return m ? m->sigma2 : NAN; }
 extern "C" double egx_gp_model_likelihood(const egx_gp_model* m) { return m ? m->likelihood : NAN; }
 extern "C" long long egx_gp_model_n_evals(const egx_gp_model* m) { return m ? m->n_evals : 0; }
 extern "C" egx_gp_ctx* egx_gp_model_context(egx_gp_model* m) { return m ? m->ctx : nullptr; }
 
 extern "C" int egx_gp_model_inner_params(egx_gp_model* m, double* beta, double* gamma, double* r_chol, double* ft,
-                                         double* ft_qr_r) {
+                                         double* ft_qr_r) try {
     if (!m) return EGX_INVALID_VALUE;
     // re-run the final evaluation to fetch the requested pieces (the factor stays on the device)
     double rlf, s2;
@@ -858,9 +864,10 @@ extern "C" int egx_gp_model_inner_params(egx_gp_model* m, double* beta, double* 
     if (r_chol) st = egx_gp_download_chol(m->ctx, r_chol);
     return st;
 }
+EGX_ABI_CATCH
 
 extern "C" int egx_gp_model_normalization(const egx_gp_model* m, double* x_mean, double* x_std, double* y_mean,
-                                          double* y_std, double* w_star) {
+                                          double* y_std, double* w_star) try {
     if (!m) return EGX_INVALID_VALUE;
     if (x_mean) std::memcpy(x_mean, m->x_mean.data(), sizeof(double) * m->d);
     if (x_std) std::memcpy(x_std, m->x_std.data(), sizeof(double) * m->d);
@@ -869,37 +876,45 @@ extern "C" int egx_gp_model_normalization(const egx_gp_model* m, double* x_mean,
     if (w_star) std::memcpy(w_star, m->w_star.data(), sizeof(double) * m->d * m->h);
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_model_predict(egx_gp_model* m, const double* x, int npts, double* y) {
+extern "C" int egx_gp_model_predict(egx_gp_model* m, const double* x, int npts, double* y) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_predict(m->ctx, x, npts, y);
 }
-extern "C" int egx_gp_model_predict_var(egx_gp_model* m, const double* x, int npts, double* var) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_model_predict_var(egx_gp_model* m, const double* x, int npts, double* var) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_predict_var(m->ctx, x, npts, var);
 }
-extern "C" int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int npts, double* y, double* var) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_model_predict_valvar(egx_gp_model* m, const double* x, int npts, double* y, double* var) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_predict_valvar(m->ctx, x, npts, y, var);
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_gp_model_predict_var_gradients(egx_gp_model* m, const double* x, int npts, double* grad) {
+extern "C" int egx_gp_model_predict_var_gradients(egx_gp_model* m, const double* x, int npts, double* grad) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_predict_var_gradients(m->ctx, x, npts, grad);
 }
-extern "C" int egx_gp_model_covariance(egx_gp_model* m, const double* x, int npts, double* cov) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_model_covariance(egx_gp_model* m, const double* x, int npts, double* cov) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_covariance(m->ctx, x, npts, cov);
 }
+EGX_ABI_CATCH
 extern "C" int egx_gp_model_sample(egx_gp_model* m, const double* x, int npts, const double* z, int n_traj, int method,
-                                   double* out) {
+                                   double* out) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_sample(m->ctx, x, npts, z, n_traj, method, out);
 }
-extern "C" int egx_gp_model_predict_gradients(egx_gp_model* m, const double* x, int npts, double* grad) {
+EGX_ABI_CATCH
+extern "C" int egx_gp_model_predict_gradients(egx_gp_model* m, const double* x, int npts, double* grad) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_gp_predict_gradients(m->ctx, x, npts, grad);
 }
+EGX_ABI_CATCH
 
 // ============================================================================================
 // Sparse GP fit driver: impl Fit for SgpValidParams, sparse_algorithm.rs:416-648.
@@ -937,7 +952,7 @@ extern "C" void egx_sgp_model_destroy(egx_sgp_model* m) {
 }
 
 extern "C" int egx_sgp_fit(const egx_sgp_params* prm, const double* x, int n, int d, const double* y,
-                           egx_sgp_model** out) {
+                           egx_sgp_model** out) try {
     if (!out) return EGX_INVALID_VALUE;
     *out = nullptr;
     if (!prm || !x || !y || n < 2 || d < 1) {
@@ -1114,8 +1129,9 @@ extern "C" int egx_sgp_fit(const egx_sgp_params* prm, const double* x, int n, in
     *out = m.release();
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_sgp_model_dims(const egx_sgp_model* m, int* n, int* d, int* h, int* nz) {
+extern "C" int egx_sgp_model_dims(const egx_sgp_model* m, int* n, int* d, int* h, int* nz) try {
     if (!m) return EGX_INVALID_VALUE;
     if (n) *n = m->n;
     if (d) *d = m->d;
@@ -1123,31 +1139,37 @@ extern "C" int egx_sgp_model_dims(const egx_sgp_model* m, int* n, int* d, int* h
     if (nz) *nz = m->m;
     return EGX_OK;
 }
-extern "C" int egx_sgp_model_theta(const egx_sgp_model* m, double* theta) {
+EGX_ABI_CATCH
+extern "C" int egx_sgp_model_theta(const egx_sgp_model* m, double* theta) try {
     if (!m || !theta) return EGX_INVALID_VALUE;
     std::memcpy(theta, m->theta.data(), sizeof(double) * m->h);
     return EGX_OK;
 }
+EGX_ABI_CATCH
 extern "C" double egx_sgp_model_variance(const egx_sgp_model* m) { return m ? m->sigma2 : NAN; }
 extern "C" double egx_sgp_model_noise_variance(const egx_sgp_model* m) { return m ? m->noise : NAN; }
 extern "C" double egx_sgp_model_likelihood(const egx_sgp_model* m) { return m ? m->likelihood : NAN; }
 extern "C" long long egx_sgp_model_n_evals(const egx_sgp_model* m) { return m ? m->n_evals : 0; }
-extern "C" int egx_sgp_model_inducings(const egx_sgp_model* m, double* z) {
+extern "C" int egx_sgp_model_inducings(const egx_sgp_model* m, double* z) try {
     if (!m || !z) return EGX_INVALID_VALUE;
     std::memcpy(z, m->z.data(), sizeof(double) * m->z.size());
     return EGX_OK;
 }
-extern "C" int egx_sgp_model_woodbury(egx_sgp_model* m, double* w_vec, double* w_inv) {
+EGX_ABI_CATCH
+extern "C" int egx_sgp_model_woodbury(egx_sgp_model* m, double* w_vec, double* w_inv) try {
     if (!m) return EGX_INVALID_VALUE;
     double lik;
     return egx_sgp_finalize(m->ctx, m->theta.data(), m->sigma2, m->noise, &lik, w_vec, w_inv);
 }
+EGX_ABI_CATCH
 extern "C" egx_sgp_ctx* egx_sgp_model_context(egx_sgp_model* m) { return m ? m->ctx : nullptr; }
-extern "C" int egx_sgp_model_predict(egx_sgp_model* m, const double* x, int npts, double* y) {
+extern "C" int egx_sgp_model_predict(egx_sgp_model* m, const double* x, int npts, double* y) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_sgp_predict(m->ctx, x, npts, y);
 }
-extern "C" int egx_sgp_model_predict_var(egx_sgp_model* m, const double* x, int npts, double* var) {
+EGX_ABI_CATCH
+extern "C" int egx_sgp_model_predict_var(egx_sgp_model* m, const double* x, int npts, double* var) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_sgp_predict_var(m->ctx, x, npts, var);
 }
+EGX_ABI_CATCH

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "../../include/egobox_gpu.h"
+#include "abi_guard.h"
 
 // a: n x n symmetric, row-major.  On return the COLUMNS of a are the orthonormal eigenvectors and
 // w[j] the matching eigenvalues (unsorted).  Returns 0, or 1 if the QL iteration did not converge.
@@ -149,7 +150,8 @@ int egx_host_symmetric_eig(int n, double* a, double* w) {
     return status;
 }
 
-extern "C" int egx_symmetric_eig(int n, double* a, double* w) {
+extern "C" int egx_symmetric_eig(int n, double* a, double* w) try {
     if (n < 0 || (n > 0 && (!a || !w))) return EGX_INVALID_VALUE;
     return egx_host_symmetric_eig(n, a, w) == 0 ? EGX_OK : EGX_INVALID_VALUE;
 }
+EGX_ABI_CATCH

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/egobox_gpu.h"
+#include "abi_guard.h"
 
 namespace {
 
@@ -28,7 +29,7 @@ double dot(const std::vector<double>& a, const std::vector<double>& b) {
 
 extern "C" int egx_bound_lbfgs_minimize(egx_objective_grad_fn fg, void* user, int n, const double* x0, const double* lo,
                                         const double* hi, double ftol_rel, double gtol, int maxeval, double* x_opt,
-                                        double* f_opt, int* n_evals) {
+                                        double* f_opt, int* n_evals) try {
     if (!fg || !x0 || !lo || !hi || n < 1 || !x_opt || !f_opt) return EGX_INVALID_VALUE;
     for (int i = 0; i < n; ++i)
         if (!(lo[i] <= hi[i])) return EGX_INVALID_VALUE;
@@ -142,3 +143,4 @@ extern "C" int egx_bound_lbfgs_minimize(egx_objective_grad_fn fg, void* user, in
     if (n_evals) *n_evals = nfev;
     return EGX_OK;
 }
+EGX_ABI_CATCH

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "../../include/egobox_gpu.h"
+#include "abi_guard.h"
 
 namespace {
 
@@ -70,7 +71,7 @@ bool invert(std::vector<double>& a, int k, std::vector<double>& inv) {
 
 // x: n x d raw inputs, y: n raw outputs (single target, as in gp `fit`), k components.
 // w_star: d x k, row-major.  Zeros (and EGX_OK) on a constant residual, like the reference.
-extern "C" int egx_pls_rotations(const double* x, int n, int d, const double* y, int k, double* w_star) {
+extern "C" int egx_pls_rotations(const double* x, int n, int d, const double* y, int k, double* w_star) try {
     if (!x || !y || !w_star || n < 2 || d < 1 || k < 1 || k > d) {
         egx_set_error("egx_pls_rotations: invalid argument (n=%d d=%d k=%d)", n, d, k);
         return EGX_INVALID_VALUE;
@@ -158,3 +159,4 @@ extern "C" int egx_pls_rotations(const double* x, int n, int d, const double* y,
         }
     return EGX_OK;
 }
+EGX_ABI_CATCH

@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "../../include/egobox_gpu.h"
+#include "abi_guard.h"
 
 extern "C" int egx_gp_predict_valvar_dev(egx_gp_ctx* c, const double* x_dev, int m, double* y_dev, double* var_dev);
 extern "C" int egx_gp_predict_gradients_dev(egx_gp_ctx* c, const double* x_dev, int m, double* grad_dev);
@@ -346,7 +347,7 @@ int predict_chunk(egx_moe* q, int recomb, const double* x, int m, double* y, dou
 }  // namespace
 
 extern "C" int egx_moe_create(egx_moe** out, int device, int k, int d, const double* weights, const double* means,
-                              const double* covariances, double heaviside_factor) {
+                              const double* covariances, double heaviside_factor) try {
     if (!out) return EGX_INVALID_VALUE;
     *out = nullptr;
     if (k < 1 || d < 1 || !weights || !means || !covariances || !(heaviside_factor > 0.0)) {
@@ -411,6 +412,7 @@ extern "C" int egx_moe_create(egx_moe** out, int device, int k, int d, const dou
     *out = q;
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
 extern "C" void egx_moe_destroy(egx_moe* q) {
     if (!q) return;
@@ -425,15 +427,16 @@ extern "C" void egx_moe_destroy(egx_moe* q) {
     delete q;
 }
 
-extern "C" int egx_moe_set_heaviside_factor(egx_moe* q, double factor) {
+extern "C" int egx_moe_set_heaviside_factor(egx_moe* q, double factor) try {
     if (!q || !(factor > 0.0)) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(q->mtx);
     EGX_CUDA_TRY(cudaSetDevice(q->device));
     q->heaviside = factor;
     return upload(q);
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_moe_set_expert(egx_moe* q, int cluster, egx_gp_ctx* ctx) {
+extern "C" int egx_moe_set_expert(egx_moe* q, int cluster, egx_gp_ctx* ctx) try {
     if (!q || cluster < 0 || cluster >= q->k) return EGX_INVALID_VALUE;
     if (ctx) {
         int d = 0;
@@ -447,8 +450,9 @@ extern "C" int egx_moe_set_expert(egx_moe* q, int cluster, egx_gp_ctx* ctx) {
     q->experts[cluster] = ctx;
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_moe_parameters(const egx_moe* q, double* precisions, double* precisions_chol, double* log_det) {
+extern "C" int egx_moe_parameters(const egx_moe* q, double* precisions, double* precisions_chol, double* log_det) try {
     if (!q) return EGX_INVALID_VALUE;
     const size_t kdd = static_cast<size_t>(q->k) * q->d * q->d;
     if (precisions) std::memcpy(precisions, q->precisions.data(), kdd * sizeof(double));
@@ -463,8 +467,9 @@ extern "C" int egx_moe_parameters(const egx_moe* q, double* precisions, double* 
     }
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_moe_predict_probas(egx_moe* q, const double* x, int m, double* probas, int* clusters) {
+extern "C" int egx_moe_predict_probas(egx_moe* q, const double* x, int m, double* probas, int* clusters) try {
     if (!q || m < 0 || (m > 0 && !x) || (!probas && !clusters)) return EGX_INVALID_VALUE;
     if (m == 0) return EGX_OK;
     std::lock_guard<std::mutex> lk(q->mtx);
@@ -491,8 +496,9 @@ extern "C" int egx_moe_predict_probas(egx_moe* q, const double* x, int m, double
     }
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_moe_predict_probas_derivatives(egx_moe* q, const double* x, int m, double* dprobas) {
+extern "C" int egx_moe_predict_probas_derivatives(egx_moe* q, const double* x, int m, double* dprobas) try {
     if (!q || m < 0 || (m > 0 && (!x || !dprobas))) return EGX_INVALID_VALUE;
     if (m == 0) return EGX_OK;
     std::lock_guard<std::mutex> lk(q->mtx);
@@ -516,9 +522,10 @@ extern "C" int egx_moe_predict_probas_derivatives(egx_moe* q, const double* x, i
     }
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
 extern "C" int egx_moe_predict(egx_moe* q, int recombination, const double* x, int m, double* y, double* var,
-                               double* grad_y, double* grad_var) {
+                               double* grad_y, double* grad_var) try {
     if (!q || m < 0 || (m > 0 && !x) || (recombination != EGX_RECOMB_HARD && recombination != EGX_RECOMB_SMOOTH))
         return EGX_INVALID_VALUE;
     if (!y && !var && !grad_y && !grad_var) return EGX_INVALID_VALUE;
@@ -537,3 +544,4 @@ extern "C" int egx_moe_predict(egx_moe* q, int recombination, const double* x, i
     }
     return EGX_OK;
 }
+EGX_ABI_CATCH

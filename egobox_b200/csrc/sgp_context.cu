@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "sweep.cuh"
 #include "../../include/egobox_gpu.h"
+#include "abi_guard.h"
 
 void launch_sgp_rowstats(const double* Y, long ldy, int mc, int mpad_rows, int Mpad, const double* yv, int method,
                          double sigma2, double noise, double beta_const, double* sqrtb, double* by, double* scal,
@@ -223,7 +224,7 @@ int sgp_predict_impl(egx_sgp_ctx* c, const double* x, int m, double* y, double* 
 }  // namespace
 
 extern "C" int egx_sgp_create(egx_sgp_ctx** out, int device, int corr, int method, const double* x, int n, int d,
-                              const double* y, const double* z, int m, const double* w_star, int h, double nugget) {
+                              const double* y, const double* z, int m, const double* w_star, int h, double nugget) try {
     if (!out) return EGX_INVALID_VALUE;
     *out = nullptr;
     if (!x || !y || !z || !w_star || n < 1 || d < 1 || m < 1 || h < 1 || h > d || corr < 0 || corr > 3 || method < 0 ||
@@ -305,19 +306,21 @@ extern "C" int egx_sgp_create(egx_sgp_ctx** out, int device, int corr, int metho
     *out = c;
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
 extern "C" void egx_sgp_destroy(egx_sgp_ctx* c) { free_sgp(c); }
 
 extern "C" int egx_sgp_reduced_likelihood(egx_sgp_ctx* c, const double* theta, double sigma2, double noise,
-                                          double* lik) {
+                                          double* lik) try {
     if (!c || !theta || !lik) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
     return sgp_evaluate(c, theta, sigma2, noise, lik);
 }
+EGX_ABI_CATCH
 
 extern "C" int egx_sgp_finalize(egx_sgp_ctx* c, const double* theta, double sigma2, double noise, double* lik,
-                                double* w_vec, double* w_inv) {
+                                double* w_vec, double* w_inv) try {
     if (!c || !theta) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     EGX_CUDA_TRY(cudaSetDevice(c->device));
@@ -375,25 +378,29 @@ extern "C" int egx_sgp_finalize(egx_sgp_ctx* c, const double* theta, double sigm
     c->trained = true;
     return EGX_OK;
 }
+EGX_ABI_CATCH
 
-extern "C" int egx_sgp_predict(egx_sgp_ctx* c, const double* x, int m, double* y) {
+extern "C" int egx_sgp_predict(egx_sgp_ctx* c, const double* x, int m, double* y) try {
     if (!c || !x || !y) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return sgp_predict_impl(c, x, m, y, nullptr);
 }
-extern "C" int egx_sgp_predict_var(egx_sgp_ctx* c, const double* x, int m, double* var) {
+EGX_ABI_CATCH
+extern "C" int egx_sgp_predict_var(egx_sgp_ctx* c, const double* x, int m, double* var) try {
     if (!c || !x || !var) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     return sgp_predict_impl(c, x, m, nullptr, var);
 }
-extern "C" int egx_sgp_set_profiling(egx_sgp_ctx* c, int enabled) {
+EGX_ABI_CATCH
+extern "C" int egx_sgp_set_profiling(egx_sgp_ctx* c, int enabled) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     c->env.prof.on = enabled != 0;
     c->env.prof.reset();
     return EGX_OK;
 }
-extern "C" int egx_sgp_get_profile(egx_sgp_ctx* c, double* ms, long long* launches) {
+EGX_ABI_CATCH
+extern "C" int egx_sgp_get_profile(egx_sgp_ctx* c, double* ms, long long* launches) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);
     for (int i = 0; i < EGX_NUM_STAGES; ++i) {
@@ -402,3 +409,4 @@ extern "C" int egx_sgp_get_profile(egx_sgp_ctx* c, double* ms, long long* launch
     }
     return EGX_OK;
 }
+EGX_ABI_CATCH

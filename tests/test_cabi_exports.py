@@ -87,3 +87,46 @@ def test_host_only_entry_points_from_plain_c(tmp_path):
                     "-lm", "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "host ABI ok" in r.stdout, r.stderr
+
+
+def test_every_status_returning_entry_point_has_the_exception_barrier(tmp_path):
+    """A C++ exception must never unwind through the C ABI into a C / Rust / JVM caller: every `extern "C" int egx_*`
+    definition is a function-try-block closed by EGX_ABI_CATCH (csrc/abi_guard.h), and the macro turns bad_alloc /
+    length_error / anything else into EGX_CUDA_ERROR with a message (tests/c/abi_guard_check.cpp)."""
+    import shutil
+    import subprocess
+    csrc = os.path.join(ROOT, "egobox_b200", "csrc")
+    guarded = 0
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith((".cu", ".cpp")):
+            continue
+        lines = open(os.path.join(csrc, f)).read().split("\n")
+        i = 0
+        while i < len(lines):
+            if lines[i].startswith('extern "C" int egx_'):
+                j = i
+                while not lines[j].rstrip().endswith(("{", ";", "}")):
+                    j += 1
+                last = lines[j].rstrip()
+                if last.endswith("{"):                                   # a multi-line definition
+                    assert last.endswith("try {"), "%s:%d is not a function-try-block" % (f, j + 1)
+                    k = j + 1
+                    while lines[k] != "}":
+                        k += 1
+                    assert lines[k + 1] == "EGX_ABI_CATCH", "%s:%d" % (f, k + 2)
+                    guarded += 1
+                    i = k
+            i += 1
+    assert guarded >= 69
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    from egobox_b200 import _lib
+    _lib.load()
+    libdir = os.path.join(ROOT, "egobox_b200")
+    exe = str(tmp_path / "abi_guard")
+    subprocess.run([gxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), "-I" + csrc,
+                    os.path.join(ROOT, "tests", "c", "abi_guard_check.cpp"), "-L" + libdir, "-legobox_gpu",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "abi guard ok" in r.stdout, r.stderr
