@@ -18,3 +18,9 @@ void egx_set_error(const char* fmt, ...);
         egx_set_error("internal error: unknown C++ exception");        \
         return EGX_CUDA_ERROR;                                         \
     }
+
+// for the two entry points whose int is a COUNT, not a status (egx_device_count, egx_gp_async_slots): 0 on any exception
+#define EGX_ABI_CATCH_COUNT \
+    catch (...) {           \
+        return 0;           \
+    }

@@ -37,7 +37,7 @@ extern "C" int egx_device_count(void) try {
     }
     return c;
 }
-EGX_ABI_CATCH
+EGX_ABI_CATCH_COUNT
 
 namespace {
 
@@ -836,7 +836,7 @@ extern "C" int egx_gp_async_slots(egx_gp_ctx* c, int wanted) try {
     c->async_slots = W;
     return W;
 }
-EGX_ABI_CATCH
+EGX_ABI_CATCH_COUNT
 
 extern "C" int egx_gp_eval_begin(egx_gp_ctx* c, int slot, const double* theta) try {
     if (!c || !theta || slot < 0 || slot >= c->async_slots) return EGX_INVALID_VALUE;
