@@ -115,6 +115,12 @@ SIGNATURES.update({
     "egx_bound_lbfgs_minimize": (C.c_int, [OBJECTIVE_GRAD_FN, C.c_void_p, C.c_int, _dp, _dp, _dp, C.c_double,
                                            C.c_double, C.c_int, _dp, _dp, _ip]),
     "egx_prepare_multistart": (C.c_int, [C.c_int, _dp, _dp, C.c_int, C.c_ulonglong, _dp]),
+    "egx_comm_init": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int]),
+    "egx_comm_destroy": (None, [_vp]),
+    "egx_comm_rank": (C.c_int, [_vp]),
+    "egx_comm_size": (C.c_int, [_vp]),
+    "egx_comm_allgather": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_argmin_allreduce": (C.c_int, [_vp, _dp, _dp, C.c_int, _ip]),
 })
 
 

@@ -104,3 +104,55 @@ def fit_experts(fit_one, n_experts, theta_dim):
     for r, part in enumerate(parts):
         table[shard_indices(n_experts, r, world)] = part
     return models, table
+
+
+class HostComm:
+    """The exchange of the sharded path without torch: `egx_comm_*` of the C ABI (csrc/host_comm.cpp), a TCP star on
+    addr:port (rank 0 listens).  What a Rust / C caller of the library uses; the functions above do the same exchange over a
+    torch process group (NCCL / gloo)."""
+
+    def __init__(self, nranks, rank, addr="127.0.0.1", port=29600, timeout_ms=60000):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib.load()
+        self._h = C.c_void_p()
+        st = self._lib.egx_comm_init(C.byref(self._h), int(nranks), int(rank), str(addr).encode(), int(port), int(timeout_ms))
+        if st != 0:
+            raise _lib.GpuError(st, _lib.last_error())
+        self.rank, self.size = int(rank), int(nranks)
+
+    def allgather(self, values):
+        """(count,) doubles of this rank -> (size, count) array of every rank, on every rank."""
+        C = self._C
+        v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
+        out = np.empty((self.size, v.size))
+        dp = C.POINTER(C.c_double)
+        st = self._lib.egx_comm_allgather(self._h, v.ctypes.data_as(dp), v.size, out.ctypes.data_as(dp))
+        if st != 0:
+            from . import _lib
+            raise _lib.GpuError(st, _lib.last_error())
+        return out
+
+    def argmin(self, value, payload):
+        """-> (value, payload, winner rank) of the rank with the smallest value (gp/src/algorithm.rs:942-945 across ranks)."""
+        C = self._C
+        v = C.c_double(float(value))
+        p = np.ascontiguousarray(payload, dtype=np.float64).reshape(-1).copy()
+        w = C.c_int(-1)
+        dp = C.POINTER(C.c_double)
+        st = self._lib.egx_argmin_allreduce(self._h, C.byref(v), p.ctypes.data_as(dp), p.size, C.byref(w))
+        if st != 0:
+            from . import _lib
+            raise _lib.GpuError(st, _lib.last_error())
+        return v.value, p, w.value
+
+    def close(self):
+        if self._h:
+            self._lib.egx_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -313,6 +313,23 @@ int egx_bound_lbfgs_minimize(egx_objective_grad_fn fg, void* user, int n, const 
  * gp/src/sparse_algorithm.rs:442-455 (linfa-pls 0.8.0 = scikit-learn's NIPALS PLSRegression, scale = true):
  * x n x d raw, y n raw -> w_star d x k.  A numerically constant y residual yields zeros, like the reference. */
 int egx_pls_rotations(const double* x, int n, int d, const double* y, int k, double* w_star);
+/* ---- the exchange of the sharded path (multi-process, one rank per GPU) -----------------------------------------------
+ * Multistart chains, theta candidates and experts shard across ranks with NO data-path collective; at the end the ranks
+ * exchange (value, payload[h]) -- 8 (h + 2) bytes each -- and keep the best: the reduction of gp/src/algorithm.rs:942-945
+ * across processes.  A TCP star (rank 0 listens on addr:port, the MASTER_ADDR convention of torchrun; use a port of your
+ * own, torchrun's MASTER_PORT is taken by its store) so that a caller needs no NCCL binding for a message of a few dozen
+ * bytes; Python callers with a torch process group use egobox_b200/parallel.py (NCCL all_gather) instead.
+ *   egx_comm_init       blocks until all nranks ranks have joined (timeout_ms <= 0: 60 s); nranks == 1 needs no address
+ *   egx_comm_allgather  every rank contributes `count` doubles and receives nranks * count doubles in rank order
+ *   egx_argmin_allreduce  in place: the pair of the rank with the smallest value (ties: lowest rank, NaN never wins) */
+typedef struct egx_comm egx_comm;
+int egx_comm_init(egx_comm** out, int nranks, int rank, const char* addr, int port, int timeout_ms);
+void egx_comm_destroy(egx_comm* comm);
+int egx_comm_rank(const egx_comm* comm);
+int egx_comm_size(const egx_comm* comm);
+int egx_comm_allgather(egx_comm* comm, const double* send, int count, double* recv);
+int egx_argmin_allreduce(egx_comm* comm, double* value, double* payload, int h, int* winner_rank);
+
 /* egx_symmetric_eig: eigen-decomposition of a symmetric n x n matrix (row-major, overwritten by the
  * eigenvectors as COLUMNS; w = eigenvalues, unsorted) -- the host half of the eigenvalue sampler,
  * `cov_x.eigh()` gp/src/algorithm.rs:1171-1173.  Returns EGX_OK or EGX_INVALID_VALUE (no convergence). */

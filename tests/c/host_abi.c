@@ -65,6 +65,16 @@ int main(void) {
         CHECK(st == EGX_OK, "pls status");
         CHECK(fabs(w[0] / w[1] + 2.0) < 1e-12 && fabs(w[0] * w[0] + w[1] * w[1] - 1.0) < 1e-12, "pls rotation");
     }
+    {   /* the exchange of the sharded path, world size 1 (tests/test_host_comm.py runs three processes) */
+        egx_comm* comm = 0;
+        double v = 2.5, pay[2] = {1.0, 2.0}, all[2];
+        int winner = -1;
+        CHECK(egx_comm_init(&comm, 1, 0, 0, 0, 0) == EGX_OK && egx_comm_size(comm) == 1 && egx_comm_rank(comm) == 0, "comm init");
+        CHECK(egx_comm_allgather(comm, pay, 2, all) == EGX_OK && all[0] == 1.0 && all[1] == 2.0, "comm allgather");
+        CHECK(egx_argmin_allreduce(comm, &v, pay, 2, &winner) == EGX_OK && winner == 0 && v == 2.5, "comm argmin");
+        egx_comm_destroy(comm);
+        CHECK(egx_comm_init(&comm, 2, 5, "127.0.0.1", 29999, 100) == EGX_INVALID_VALUE && comm == 0, "comm bad rank");
+    }
     CHECK(egx_device_count() >= 0 && egx_version() != 0, "version / device count");
     if (failures == 0) printf("host ABI ok\n");
     return failures;
