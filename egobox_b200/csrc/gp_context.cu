@@ -910,6 +910,17 @@ extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const doub
         egx_set_error("closed-form theta gradient supports up to 32 components (got %d): use egx_gp_reduced_likelihood_grad", h);
         return EGX_INVALID_VALUE;
     }
+    {
+        // shared memory of the pair kernel: two 64 x d coordinate tiles, gamma, the warp partials and up to d * h terms
+        const int hmax = h <= 8 ? 8 : (h <= 16 ? 16 : 32);
+        const size_t smem = (2 * static_cast<size_t>(EGX_CT) * c->d + 2 * EGX_CT + 8 * hmax) * sizeof(double) +
+                            static_cast<size_t>(c->d) * h * sizeof(ThetaGradTerm);
+        if (smem > 227 * 1024) {
+            egx_set_error("closed-form theta gradient: d = %d with %d components needs %zu bytes of shared memory per CTA "
+                          "(limit 232448): use egx_gp_reduced_likelihood_grad", c->d, h, smem);
+            return EGX_INVALID_VALUE;
+        }
+    }
     EGX_CUDA_TRY(cudaSetDevice(c->device));
     int st = evaluate(c, theta, rlf);
     if (st != EGX_OK) return st;
