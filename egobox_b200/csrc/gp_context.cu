@@ -621,6 +621,17 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
         egx_set_error("egx_gp_create: regression basis size p=%d unsupported (need p <= min(255, n=%d))", p, n);
         return EGX_INVALID_VALUE;
     }
+    {
+        // the correlation kernels stage three 64 x d coordinate tiles and the (dimension, component) term list in shared
+        // memory (kernels_corr.cu): refuse shapes that cannot fit instead of failing at the first launch
+        const size_t terms = (corr == EGX_CORR_MATERN32 || corr == EGX_CORR_MATERN52) ? static_cast<size_t>(d) * h : d;
+        const size_t smem = 16 + (3 * static_cast<size_t>(EGX_CT) * d + 2 * EGX_CT) * sizeof(double) + terms * sizeof(CorrTerm);
+        if (smem > 227 * 1024) {
+            egx_set_error("egx_gp_create: d = %d (h = %d) needs %zu bytes of shared memory per CTA in the correlation kernels "
+                          "(limit 232448); reduce the input dimension (KPLS does not shrink the coordinate tiles)", d, h, smem);
+            return EGX_INVALID_VALUE;
+        }
+    }
     if (egx_device_count() <= device || device < 0) {
         egx_set_error("egx_gp_create: CUDA device %d not available (no CPU fallback exists)", device);
         return EGX_CUDA_ERROR;

@@ -132,3 +132,13 @@ def test_every_status_returning_entry_point_has_the_exception_barrier(tmp_path):
                     "-Wl,-rpath," + libdir, "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "abi guard ok" in r.stdout, r.stderr
+
+
+def test_input_dimension_that_cannot_fit_the_correlation_kernels_is_refused_up_front():
+    """Three 64 x d coordinate tiles live in shared memory (kernels_corr.cu): d = 160 would fail at the first launch, so
+    egx_gp_create says so (checked before the device is touched, hence testable here)."""
+    import egobox_b200 as eg
+    d = 160
+    with pytest.raises(eg.GpuError) as e:
+        eg.GpContext(np.zeros((5, d)), np.zeros(5), np.zeros(d), np.ones(d), 0.0, 1.0, eg.SQUARED_EXPONENTIAL, eg.CONSTANT)
+    assert "shared memory" in str(e.value) and "INVALID_VALUE" in str(e.value)
