@@ -337,6 +337,16 @@ class GaussianProcess:
         """algorithm.rs:393-395: alias of sample_eig."""
         return self.sample_eig(x, n_traj, seed, z)
 
+    def q2_score(self, kfold, fit=None):
+        """`PredictScore::q2_score`, gp/src/metrics.rs:35-53: 1 - PRESS / TSS over `kfold` refits with the model's own
+        parameters (linfa `fold`: validation rows [i fs, (i + 1) fs), fs = n / kfold; TSS around the mean of ALL targets).
+        `fit(x, y) -> model with predict` defaults to this model's parameter set (a fan-out of GPU fits)."""
+        return _q2_score(self.training_data, kfold, fit if fit is not None else self.params_.fit)
+
+    def looq2_score(self, fit=None):
+        """`PredictScore::looq2_score`, gp/src/metrics.rs:55-58: leave-one-out."""
+        return self.q2_score(self.training_data[0].shape[0], fit)
+
     def theta(self):
         th = np.empty(self._hdim)
         self._lib.egx_gp_model_theta(self._h, th.ctypes.data_as(C.POINTER(C.c_double)))
@@ -401,6 +411,28 @@ class Kriging:
     @staticmethod
     def params():
         return GpParams(ConstantMean, SquaredExponentialCorr)
+
+
+def _q2_score(training_data, kfold, fit):
+    x, y = training_data
+    n = x.shape[0]
+    if kfold < 1 or kfold > n:
+        raise InvalidValueError("kfold should be in 1..%d, got %d" % (n, kfold))
+    fs = n // kfold
+    y_mean = y.mean()
+    press = tss = 0.0
+    for i in range(kfold):
+        va = np.arange(i * fs, (i + 1) * fs)
+        tr = np.concatenate([np.arange(0, i * fs), np.arange((i + 1) * fs, n)])
+        model = fit(x[tr], y[tr])                      # `.expect("cross-validation: sub model fitted")`: a failure propagates
+        try:
+            pred = model.predict(x[va])
+        finally:
+            if hasattr(model, "close"):
+                model.close()
+        press += float(((y[va] - pred) ** 2).sum())
+        tss += float(((y[va] - y_mean) ** 2).sum())
+    return 1.0 - press / tss
 
 
 def bound_cobyla_minimize(fun, x0, bounds, rhobeg=0.5, ftol_rel=1e-4, maxeval=200):

@@ -323,6 +323,14 @@ class SparseGaussianProcess:
         """sparse_algorithm.rs:318-336 -> (n, nx)."""
         return self._central_diff(self.predict_var, x)
 
+    def q2_score(self, kfold, fit=None):
+        """`PredictScore::q2_score` for the sparse GP, gp/src/metrics.rs:35-53, 77-91."""
+        from .gp import _q2_score
+        return _q2_score(self.training_data, kfold, fit if fit is not None else self.params_.fit)
+
+    def looq2_score(self, fit=None):
+        return self.q2_score(self.training_data[0].shape[0], fit)
+
     def theta(self):
         th = np.empty(self._hdim)
         self._lib.egx_sgp_model_theta(self._h, th.ctypes.data_as(_dp))

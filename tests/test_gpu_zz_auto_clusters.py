@@ -47,3 +47,20 @@ def test_constant_function():
     np.testing.assert_allclose(gp.predict(xtest), np.full(5, 3.1), atol=1e-6)
     assert np.all(gp.predict_var(xtest) >= 0.0)
     gp.close()
+
+
+@_unverified
+@pytest.mark.timeout(600)
+def test_q2_gp_griewank():
+    """gp/src/metrics.rs:117-150: KPLS(3) kriging on 100 LHS points of the 5-D Griewank function; leave-one-out and
+    10-fold Q2 within 1e-2 of 1 (100 + 10 refits on the device)."""
+    import egobox_b200 as egx
+    from oracle import gp_oracle as O
+    dim, nt = 5, 100
+    xt = O.lhs_classic(np.array([[-600.0, 600.0]] * dim), nt, np.random.default_rng(42))
+    dd = np.sqrt(np.linspace(1.0, dim, dim))
+    yt = (xt ** 2).sum(axis=1) / 4000.0 - np.prod(np.cos(xt / dd), axis=1) + 1.0
+    gp = egx.GaussianProcess.params().kpls_dim(3).fit(xt, yt)
+    assert gp.looq2_score() == pytest.approx(1.0, abs=1e-2)
+    assert gp.q2_score(10) == pytest.approx(1.0, abs=1e-2)
+    gp.close()

@@ -198,3 +198,26 @@ def test_multistart_reaches_the_likelihood_of_powells_cobyla(n, d, corr, seed):
     powell = min(minimize(obj, s0, method="COBYLA", bounds=bounds,
                           options={"rhobeg": 0.5, "maxiter": maxeval, "tol": 1e-4}).fun for s0 in starts)
     assert mine <= powell + 5e-4 * abs(powell)
+
+
+def test_q2_score_fold_logic_against_a_direct_computation():
+    """gp/src/metrics.rs:35-58 (`q2_score`, `looq2_score`): the fold arithmetic is host logic; the refits are oracle kriging
+    models here (on the device they are `params.fit`)."""
+    from egobox_b200.gp import _q2_score
+    rng = np.random.default_rng(0)
+    x = rng.random((23, 2))
+    y = np.sin(3.0 * x[:, 0]) + x[:, 1] ** 2
+    fit = lambda xs, ys: O.fit(xs, ys, corr=O.SQEXP, mean=O.CONSTANT, theta_init=[1.0], fixed=True)
+    for kfold in (4, 23):
+        fs = 23 // kfold
+        press = tss = 0.0
+        for i in range(kfold):
+            va = list(range(i * fs, (i + 1) * fs))
+            tr = [j for j in range(23) if j not in va]               # the remainder rows (n % kfold) always train
+            pred = fit(x[tr], y[tr]).predict(x[va])
+            press += ((y[va] - pred) ** 2).sum()
+            tss += ((y[va] - y.mean()) ** 2).sum()
+        assert _q2_score((x, y), kfold, fit) == pytest.approx(1.0 - press / tss, rel=1e-13)
+    assert _q2_score((x, y), 23, fit) > 0.9                           # leave-one-out on a smooth function
+    with pytest.raises(G.InvalidValueError):
+        _q2_score((x, y), 24, fit)
