@@ -7,7 +7,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-# Written after this round's GPU minutes were spent: neither test has run on a B200 yet.  Non-strict xfail keeps an
+# Written after this round's GPU minutes were spent: none of these tests has run on a B200 yet.  Non-strict xfail keeps an
 # unverified test from stopping `pytest -x`; the marker goes once the first GPU run has been looked at (XPASS = it holds).
 _unverified = pytest.mark.xfail(strict=False, reason="not yet run on a B200 (GPU budget of the round exhausted)")
 
