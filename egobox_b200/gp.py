@@ -337,6 +337,14 @@ class GaussianProcess:
         """algorithm.rs:393-395: alias of sample_eig."""
         return self.sample_eig(x, n_traj, seed, z)
 
+    def predict_kth_derivatives(self, x, kx):
+        """gp/src/algorithm.rs:443-508: derivative of the mean with respect to the kx-th input, (n,) -- one column of the
+        batched `predict_gradients` (the reference evaluates it on its own)."""
+        kx = int(kx)
+        if kx < 0 or kx >= self._d:
+            raise InvalidValueError("kx should be in 0..%d, got %d" % (self._d - 1, kx))
+        return np.ascontiguousarray(self.predict_gradients(x)[:, kx])
+
     def q2_score(self, kfold, fit=None):
         """`PredictScore::q2_score`, gp/src/metrics.rs:35-53: 1 - PRESS / TSS over `kfold` refits with the model's own
         parameters (linfa `fold`: validation rows [i fs, (i + 1) fs), fs = n / kfold; TSS around the mean of ALL targets).
