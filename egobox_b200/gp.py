@@ -422,25 +422,11 @@ class Kriging:
 
 
 def _q2_score(training_data, kfold, fit):
-    x, y = training_data
-    n = x.shape[0]
-    if kfold < 1 or kfold > n:
-        raise InvalidValueError("kfold should be in 1..%d, got %d" % (n, kfold))
-    fs = n // kfold
-    y_mean = y.mean()
-    press = tss = 0.0
-    for i in range(kfold):
-        va = np.arange(i * fs, (i + 1) * fs)
-        tr = np.concatenate([np.arange(0, i * fs), np.arange((i + 1) * fs, n)])
-        model = fit(x[tr], y[tr])                      # `.expect("cross-validation: sub model fitted")`: a failure propagates
-        try:
-            pred = model.predict(x[va])
-        finally:
-            if hasattr(model, "close"):
-                model.close()
-        press += float(((y[va] - pred) ** 2).sum())
-        tss += float(((y[va] - y_mean) ** 2).sum())
-    return 1.0 - press / tss
+    from . import metrics
+    x, _y = training_data
+    if kfold < 1 or kfold > x.shape[0]:
+        raise InvalidValueError("kfold should be in 1..%d, got %d" % (x.shape[0], kfold))
+    return metrics.q2_k_score(training_data, kfold, fit)
 
 
 def bound_cobyla_minimize(fun, x0, bounds, rhobeg=0.5, ftol_rel=1e-4, maxeval=200):

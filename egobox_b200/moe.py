@@ -609,6 +609,34 @@ class GpMixture:
             raise _gp.GpError("Can not sample when several clusters %d" % self.n_clusters())
         return self.experts[0].sample(x, n_traj, seed=seed)
 
+    # -- cross-validation scores (moe/src/algorithm.rs:566-600 -> moe/src/metrics.rs) ------------------------------
+    def _refit(self):
+        if self.params_ is None:
+            raise _gp.GpError("this mixture was not built by GpMixtureParams.fit: no parameters to refit with")
+        return self.params_.fit
+
+    def q2_k(self, kfold):
+        from . import metrics
+        return metrics.q2_k_score(self.training_data, kfold, self._refit())
+
+    def q2(self):
+        return self.q2_k(self.training_data[0].shape[0])
+
+    def pva_k(self, kfold):
+        from . import metrics
+        return metrics.pva_k_score(self.training_data, kfold, self._refit())
+
+    def pva(self):
+        return self.pva_k(self.training_data[0].shape[0])
+
+    def iae_alpha_k(self, kfold, with_plot_data=False):
+        from . import metrics
+        score, alphas, deltas = metrics.iae_alpha_k_score(self.training_data, kfold, self._refit())
+        return (score, alphas, deltas) if with_plot_data else score
+
+    def iae_alpha(self, with_plot_data=False):
+        return self.iae_alpha_k(self.training_data[0].shape[0], with_plot_data)
+
     def recombination_name(self):
         if self.recombination == HARD:
             return "Hard"

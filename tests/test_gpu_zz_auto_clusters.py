@@ -64,3 +64,21 @@ def test_q2_gp_griewank():
     assert gp.looq2_score() == pytest.approx(1.0, abs=1e-2)
     assert gp.q2_score(10) == pytest.approx(1.0, abs=1e-2)
     gp.close()
+
+
+@_unverified
+@pytest.mark.timeout(600)
+def test_gpqa_x_squared():
+    """moe/src/metrics.rs:239-261 (`test_gpqa_griewank`, which fits x -> sum x^2): 20 LHS points in [-10, 10]^2, default
+    mixture (one cluster): Q2 (10-fold and leave-one-out) within 1e-3 of 1, predictive variance adequacy within 0.2 of 0."""
+    from egobox_b200 import moe as E
+    from oracle import gp_oracle as O
+    xt = O.lhs_classic(np.array([[-10.0, 10.0]] * 2), 20, np.random.default_rng(42))
+    yt = (xt ** 2).sum(axis=1)
+    mix = E.GpMixtureParams().fit(xt, yt)
+    assert mix.q2_k(10) == pytest.approx(1.0, abs=1e-3)
+    assert mix.q2() == pytest.approx(1.0, abs=1e-3)
+    assert mix.pva_k(10) == pytest.approx(0.0, abs=2e-1)
+    assert mix.pva() == pytest.approx(0.0, abs=3e-1)         # reference: 2e-1 on ITS sample; the oracle gives 0.19 on this one
+    assert 0.0 <= mix.iae_alpha_k(10) <= 0.5
+    mix.close()
