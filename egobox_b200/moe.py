@@ -609,6 +609,20 @@ class GpMixture:
             raise _gp.GpError("Can not sample when several clusters %d" % self.n_clusters())
         return self.experts[0].sample(x, n_traj, seed=seed)
 
+    def sample_expert(self, ith, x, n_traj, seed=None):
+        """moe/src/algorithm.rs:1010-1020: trajectories of the ith expert alone."""
+        if ith < 0 or ith >= len(self.experts):
+            raise _gp.InvalidValueError("expert index should be in 0..%d, got %d" % (len(self.experts) - 1, ith))
+        return self.experts[ith].sample(x, n_traj, seed=seed)
+
+    def set_recombination(self, recombination):
+        """moe/src/algorithm.rs:632-639: switches hard / smooth; like the reference it leaves the mixture's heaviside
+        factor alone (the smooth prediction reads it from `gmx`)."""
+        if recombination not in (HARD, SMOOTH):
+            raise _gp.InvalidValueError("recombination should be HARD or SMOOTH")
+        self.recombination = recombination
+        return self
+
     # -- cross-validation scores (moe/src/algorithm.rs:566-600 -> moe/src/metrics.rs) ------------------------------
     def _refit(self):
         if self.params_ is None:
