@@ -12,5 +12,6 @@ from .gp import (GaussianProcess, GpParams, Kriging, ThetaTuning, GpError, Linal
 from .gpx import Gpx, GpMix, RegressionSpec, CorrelationSpec, Recombination  # noqa: F401
 from .sgp import (SparseGaussianProcess, SgpParams, SparseKriging, SgpContext, ParamTuning, Inducings,  # noqa: F401
                   SparseMethod, SparseGpx, SparseGpMix)
-from .moe import GaussianMixture, GpMixture, GpMixtureParams, fit_gmm  # noqa: F401
+from .moe import GaussianMixture, GpMixture, GpMixtureParams, fit_gmm, find_best_number_of_clusters  # noqa: F401
+from . import metrics  # noqa: F401
 from .mixture import ExpertMixture, recombine_smooth, hard_clusters  # noqa: F401,E402
