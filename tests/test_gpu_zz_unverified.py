@@ -1,7 +1,8 @@
-"""-m gpu: automatic number of clusters (`Gpx.builder(n_clusters=0)`, NbClusters::Auto) end to end on the device.
-Mirrors `test_moe_auto`, moe/src/algorithm.rs:1291-1311.  The search itself (moe.find_best_number_of_clusters) is covered on
-the CPU in tests/test_moe_host.py with oracle stand-ins; here every cross-validated mixture is a device mixture.
-(Sorted last on purpose: ~140 small GPU fits.)"""
+"""-m gpu: device mirrors of reference tests that were written after this round's GPU minutes were spent and have not run on
+a B200 yet -- automatic number of clusters (`test_moe_auto`, moe/src/algorithm.rs:1291-1311), the constant-function edge case
+(gp/src/algorithm.rs:1217-1237), the cross-validation scores (gp/src/metrics.rs:117-150, moe/src/metrics.rs:239-261).  Their
+host logic is covered on the CPU (tests/test_moe_host.py, tests/test_metrics_host.py, tests/test_host_optimizer.py) with
+oracle stand-ins; here every fit is a device fit.  Sorted last on purpose."""
 import numpy as np
 import pytest
 
