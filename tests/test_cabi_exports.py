@@ -142,3 +142,12 @@ def test_input_dimension_that_cannot_fit_the_correlation_kernels_is_refused_up_f
     with pytest.raises(eg.GpuError) as e:
         eg.GpContext(np.zeros((5, d)), np.zeros(5), np.zeros(d), np.ones(d), 0.0, 1.0, eg.SQUARED_EXPONENTIAL, eg.CONSTANT)
     assert "shared memory" in str(e.value) and "INVALID_VALUE" in str(e.value)
+
+
+def test_every_gpu_test_module_is_marked():
+    """`pytest -m "not gpu"` (run without a device) must deselect every module that creates device contexts."""
+    tests = os.path.join(ROOT, "tests")
+    for f in sorted(os.listdir(tests)):
+        if f.startswith("test_gpu_") and f.endswith(".py"):
+            src = open(os.path.join(tests, f)).read()
+            assert "pytestmark = pytest.mark.gpu" in src, f
