@@ -150,4 +150,4 @@ def test_every_gpu_test_module_is_marked():
     for f in sorted(os.listdir(tests)):
         if f.startswith("test_gpu_") and f.endswith(".py"):
             src = open(os.path.join(tests, f)).read()
-            assert "pytestmark = pytest.mark.gpu" in src, f
+            assert re.search(r"^pytestmark = .*pytest\.mark\.gpu", src, flags=re.M), f
