@@ -58,6 +58,8 @@ SIGNATURES = {
     "egx_moe_predict_probas_derivatives": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_moe_predict": (C.c_int, [_vp, C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp]),
     "egx_symmetric_eig": (C.c_int, [C.c_int, _dp, _dp]),
+    "egx_lhs_sample": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, C.c_ulonglong, _dp]),
+    "egx_shuffled_indices": (C.c_int, [C.c_int, C.c_ulonglong, _ip]),
     "egx_pls_rotations": (C.c_int, [_dp, C.c_int, C.c_int, _dp, C.c_int, _dp]),
     "egx_release_cached_memory": (None, []),
     "egx_gp_covariance": (C.c_int, [_vp, _dp, C.c_int, _dp]),

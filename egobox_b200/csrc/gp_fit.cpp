@@ -58,18 +58,50 @@ struct Xoshiro256Plus {
         s[3] = rotl(s[3], 45);
         return r;
     }
-    double uniform() { return static_cast<double>(next() >> 11) * (1.0 / 9007199254740992.0); }
-    uint64_t below(uint64_t n) { return next() % n; }
+    // The draws below restate rand 0.8.5 / rand_xoshiro 0.6.0 (the versions Cargo.lock pins for crates/gp, crates/doe), so that
+    // a seed gives the SAME LHS multistart points and the SAME inducing points as the reference (pinned on the fixture of
+    // crates/doe/src/lhs.rs:332-347 in tests/test_host_rng.py):
+    //   RngCore::next_u32 = upper half of next_u64; Uniform::new(0., 1.) = 52 mantissa bits of next_u64 (UniformFloat::sample);
+    //   SliceRandom::shuffle = for i in (1..len).rev(): swap(i, gen_index(i + 1)); gen_index = UniformInt<u32>::sample_single
+    //   (widening multiply, rejection zone (range << lz) - 1).
+    uint32_t next_u32() { return static_cast<uint32_t>(next() >> 32); }
+    double uniform() { return static_cast<double>(next() >> 12) * (1.0 / 4503599627370496.0); }
+    uint64_t below(uint64_t n) {
+        if (n > 0xffffffffULL) {                       // usize path of gen_index (never reached by the sizes of this path)
+            const uint64_t zone = (n << __builtin_clzll(n)) - 1;
+            for (;;) {
+                const unsigned __int128 m = static_cast<unsigned __int128>(next()) * n;
+                if (static_cast<uint64_t>(m) <= zone) return static_cast<uint64_t>(m >> 64);
+            }
+        }
+        const uint32_t range = static_cast<uint32_t>(n);
+        const uint32_t zone = (range << __builtin_clz(range)) - 1;
+        for (;;) {
+            const uint64_t m = static_cast<uint64_t>(next_u32()) * range;
+            if (static_cast<uint32_t>(m) <= zone) return m >> 32;
+        }
+    }
+    template <class T>
+    void shuffle(std::vector<T>& v) {
+        for (size_t i = v.size(); i-- > 1;) std::swap(v[i], v[below(i + 1)]);
+    }
 };
 
-// crates/doe/src/lhs.rs:247-268 (classic) and :283-304 (maximin = best of 5 by min pair distance)
+// crates/doe/src/lhs.rs:235-258 (classic: ALL uniforms first, column by column, then one shuffle per column) and :283-304
+// (maximin = best of 5 classic designs by smallest pair distance)
 std::vector<double> lhs_classic(int ns, int nx, Xoshiro256Plus& rng) {
     std::vector<double> pts(static_cast<size_t>(ns) * nx);
+    const double step = 1.0 / ns;                      // Array::linspace(0., 1., ns + 1): cut[i] = 0 + step * i
+    std::vector<std::vector<double>> cols(nx, std::vector<double>(ns));
+    for (int j = 0; j < nx; ++j)
+        for (int i = 0; i < ns; ++i) cols[j][i] = rng.uniform();
     for (int j = 0; j < nx; ++j) {
-        std::vector<double> col(ns);
-        for (int i = 0; i < ns; ++i) col[i] = (i + rng.uniform()) / ns;
-        for (int i = ns - 1; i > 0; --i) std::swap(col[i], col[rng.below(i + 1)]);
-        for (int i = 0; i < ns; ++i) pts[static_cast<size_t>(i) * nx + j] = col[i];
+        for (int i = 0; i < ns; ++i) {
+            const double a = step * i, b = step * (i + 1);
+            cols[j][i] = cols[j][i] * (b - a) + a;
+        }
+        rng.shuffle(cols[j]);
+        for (int i = 0; i < ns; ++i) pts[static_cast<size_t>(i) * nx + j] = cols[j][i];
     }
     return pts;
 }
@@ -540,6 +572,31 @@ extern "C" int egx_prepare_multistart(int n_start, const double* theta0, const d
 }
 EGX_ABI_CATCH
 
+// doe/src/lhs.rs:67-88 (SamplingMethod::sample = normalized_sample * (upper - lower) + lower)
+extern "C" int egx_lhs_sample(int kind, int ns, int nx, const double* xlimits, unsigned long long seed, double* out) try {
+    if (!xlimits || !out || ns < 1 || nx < 1 || kind < 0 || kind > 1) return EGX_INVALID_VALUE;
+    Xoshiro256Plus rng(seed);
+    const std::vector<double> pts = kind == 0 ? lhs_classic(ns, nx, rng) : lhs_maximin(ns, nx, rng);
+    for (int i = 0; i < ns; ++i)
+        for (int j = 0; j < nx; ++j) {
+            const double lo = xlimits[2 * j], hi = xlimits[2 * j + 1];
+            out[static_cast<size_t>(i) * nx + j] = pts[static_cast<size_t>(i) * nx + j] * (hi - lo) + lo;
+        }
+    return EGX_OK;
+}
+EGX_ABI_CATCH
+
+extern "C" int egx_shuffled_indices(int n, unsigned long long seed, int* out) try {
+    if (!out || n < 0) return EGX_INVALID_VALUE;
+    Xoshiro256Plus rng(seed);
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    rng.shuffle(idx);
+    std::copy(idx.begin(), idx.end(), out);
+    return EGX_OK;
+}
+EGX_ABI_CATCH
+
 extern "C" void egx_gp_params_default(egx_gp_params* p) {
     if (!p) return;
     std::memset(p, 0, sizeof(*p));
@@ -989,7 +1046,7 @@ extern "C" int egx_sgp_fit(const egx_sgp_params* prm, const double* x, int n, in
     } else {
         std::vector<int> idx(n);
         for (int i = 0; i < n; ++i) idx[i] = i;
-        for (int i = n - 1; i > 0; --i) std::swap(idx[i], idx[rng.below(i + 1)]);
+        rng.shuffle(idx);
         m->m = std::min(prm->n_inducings, n);
         m->z.resize(static_cast<size_t>(m->m) * d);
         for (int r = 0; r < m->m; ++r)

@@ -49,7 +49,7 @@ constexpr int OZ_STAGES = 3;
 constexpr int OZ_CSTG_ROW = 1088;                 // staging row pitch (128 doubles + 64 B: conflict-free 16-byte stores)
 constexpr int OZ_CSTG_BYTES = 32 * OZ_CSTG_ROW;   // 32 rows of the C update staged for cp.reduce.async.bulk
 constexpr int OZ_THREADS = 384;                   // warps 0..3: A producer, MMA issuer, B producer, idle; warps 4..11: epilogue
-constexpr int OZ_REGS_CTRL = 56, OZ_REGS_EPI = 216;   // setmaxnreg: 128 x 56 + 256 x 216 = 62464 <= 65536
+constexpr int OZ_REGS_CTRL = 56, OZ_REGS_EPI = 224;   // setmaxnreg: 128 x 56 + 256 x 224 = 64512 <= 65536
 constexpr long OZ_RB_BYTES = static_cast<long>(OZ_KSTEPS) * OZ_STAGE_OPERAND;   // slices of one 128-row block: 256 KB
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -235,6 +235,8 @@ struct OzakiArgs {
     long long* dbg;           // OZ_TIMING builds (tools/micro/ozaki_probe.cu): clock64 stamps of CTA 0
     int c_reduce;             // 1: C += c through shared memory + cp.reduce.async.bulk (no read of C); 0: load / add / store
     int prod3;                // 1: one producer thread per ring stage (both operands); 0: one per operand
+    int xp;                   // OZ_TIMING builds only (tools/micro/ozaki_probe.cu): timing experiments, bit mask --
+                              // 1 half of the MMAs, 2 no B loads, 4 one-slice loads, 8 no read of C, 16 no store of C
 };
 #ifdef OZ_TIMING
 #define OZ_STAMP(slot) do { if (blockIdx.x == 0 && g.dbg) g.dbg[slot] = clock64(); } while (0)
@@ -319,13 +321,16 @@ __device__ __forceinline__ void oz_drain(uint32_t tmem, int quarter, int chalf, 
 // instruction between two tcgen05.mma counts against the 64-clock budget of an MMA (a run-time (p, q) loop with
 // descriptor arithmetic issued one MMA per ~100 clocks).  The descriptors of the digit slices differ only in the
 // start-address field (bits 0..13, units of 16 bytes).
-template <int PASS, int B_SLICE_BYTES, bool TWO_CTA>
-__device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint32_t sb, uint32_t not_first_ks);
+template <int W0, int NW, int B_SLICE_BYTES, bool TWO_CTA>
+__device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint32_t sb, uint32_t not_first_ks, int half = 0);
 
 // Persistent: CTA b works on tiles b, b + gridDim.x, ...  The stage ring and the accumulator hand-shake run across
 // tiles, so the producer is already streaming the next tile while the epilogue folds the last pass of this one.
 // An epilogue thread owns the same 64 entries of C in both passes: they are loaded while the MMAs of pass 0 run,
 // updated in registers after each pass and stored once.
+// NW0 = number of weights (= digits of each operand) of pass 0: 4 -> passes {0..3}, {4..6} (11 slice loads per operand and
+// K step), 3 -> passes {0..2}, {3..6} (10 slice loads)
+template <int NW0>
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiArgs g, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
     unsigned char* cstg = oz_smem + OZ_STAGES * OZ_STAGE_BYTES;
@@ -368,7 +373,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                 for (int it = 0; it < 2 * OZ_KSTEPS; ++it, ++n) {
                     const uint32_t stage = n % OZ_STAGES, round = n / OZ_STAGES;
                     const int pass = it / OZ_KSTEPS, ks = it % OZ_KSTEPS;
-                    const uint32_t bytes = (pass == 0 ? 4 : OZ_SLICES) * OZ_SLICE_STEP_BYTES;
+                    uint32_t bytes = (pass == 0 ? NW0 : OZ_SLICES) * OZ_SLICE_STEP_BYTES;
+#ifdef OZ_TIMING
+                    if (g.xp & 4) bytes = OZ_SLICE_STEP_BYTES;
+                    if ((g.xp & 2) && isB) bytes = 16;
+#endif
                     oz_mbar_wait(&bars->empty[stage], (round & 1) ^ 1);
                     oz_mbar_expect_tx(&bars->full[stage], bytes);
                     oz_bulk_g2s(oz_smem + stage * OZ_STAGE_BYTES + (isB ? OZ_STAGE_OPERAND : 0),
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                 oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
                 const uint32_t round = n / OZ_STAGES;
                 const int pass = it / OZ_KSTEPS, ks = it % OZ_KSTEPS;
-                const uint32_t bytes = (pass == 0 ? 4 : OZ_SLICES) * OZ_SLICE_STEP_BYTES;
+                const uint32_t bytes = (pass == 0 ? NW0 : OZ_SLICES) * OZ_SLICE_STEP_BYTES;
                 oz_mbar_wait(&bars->empty[stage], (round & 1) ^ 1);
                 oz_mbar_expect_tx(&bars->full[stage], 2 * bytes);
                 unsigned char* st = oz_smem + stage * OZ_STAGE_BYTES;
@@ -423,8 +432,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                         if (P == 3 && ks == 0) OZ_STAMP(17);
                         const uint32_t sa = oz_smem_u32(oz_smem + stage * OZ_STAGE_BYTES);
                         const uint32_t sb = sa + OZ_STAGE_OPERAND;
-                        if (pass == 0) oz_issue_kstep<0, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sb, ks > 0 ? 1u : 0u);
-                        else oz_issue_kstep<1, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sb, ks > 0 ? 1u : 0u);
+#ifdef OZ_TIMING
+                        const int half = g.xp & 1;
+#else
+                        constexpr int half = 0;
+#endif
+                        if (pass == 0) oz_issue_kstep<0, NW0, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sb, ks > 0 ? 1u : 0u, half);
+                        else oz_issue_kstep<NW0, OZ_SLICES - NW0, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sb, ks > 0 ? 1u : 0u, half);
                         oz_umma_commit(&bars->empty[stage]);   // frees the stage when these MMAs have read it
                         if (ks == OZ_KSTEPS - 1) oz_umma_commit(&bars->acc_full);
                     }
@@ -467,19 +481,24 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
             }
 #pragma unroll 1
             for (int pass = 0; pass < 2; ++pass, ++P) {
-                const double wscale = pass == 0 ? 9.094947017729282e-13 /* 256^-5 */ : 5.421010862427522e-20 /* 256^-8 */;
+                // 256^-(last weight of the pass + 2)
+                const double wscale = pass == 0 ? (NW0 == 4 ? 9.094947017729282e-13 /* 256^-5 */ : 2.3283064365386963e-10 /* 256^-4 */)
+                                                : 5.421010862427522e-20 /* 256^-8 */;
                 oz_mbar_wait(&bars->acc_full, P & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tid == 128 && tile == blockIdx.x) OZ_STAMP(4 + 2 * pass);
                 if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(10 + 2 * pass);
-                if (pass == 0) oz_drain<4>(tmem, quarter, chalf, rsA, rsB, wscale, c);
-                else oz_drain<3>(tmem, quarter, chalf, rsA, rsB, wscale, c);
+                if (pass == 0) oz_drain<NW0>(tmem, quarter, chalf, rsA, rsB, wscale, c);
+                else oz_drain<OZ_SLICES - NW0>(tmem, quarter, chalf, rsA, rsB, wscale, c);
                 // all TMEM reads of this pass are complete: hand the accumulators back
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) oz_mbar_arrive(&bars->acc_empty);
                 if (tid == 128 && tile == blockIdx.x) OZ_STAMP(5 + 2 * pass);
                 if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(11 + 2 * pass);
+#ifdef OZ_TIMING
+                if (g.xp & 8) continue;
+#endif
                 if (pass == 0 && !g.c_reduce) {
                     // c = C - (pass-0 part): the tile is READ here, while the 144 MMAs of pass 1 run and these warps
                     // would only wait (pass 1 is bound by the shared-memory port, not by the L2 -> SM path); after the
@@ -580,7 +599,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk_kernel(const OzakiAr
                 }
             } else {
 #ifdef OZ_TIMING
-                if (g.prod3 == 7 && c[0][0][0].x != 1.2345e300) goto skip_store;     // timing experiment: no C store
+                if ((g.prod3 == 7 || (g.xp & 16)) && c[0][0][0].x != 1.2345e300) goto skip_store;     // timing experiment: no C store
 #endif
 #pragma unroll
                 for (int rh = 0; rh < 2; ++rh)
@@ -677,10 +696,9 @@ __device__ __forceinline__ void oz_mma2(uint32_t tmem_d, uint64_t da, uint64_t d
         : "memory");
 }
 
-template <int PASS, int B_SLICE_BYTES, bool TWO_CTA>
-__device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint32_t sb, uint32_t not_first_ks) {
+template <int W0, int NW, int B_SLICE_BYTES, bool TWO_CTA>
+__device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint32_t sb, uint32_t not_first_ks, int half) {
     const uint64_t da0 = oz_desc(sa), db0 = oz_desc(sb);
-    constexpr int W0 = PASS * 4, NW = PASS == 0 ? 4 : 3;
     if constexpr (TWO_CTA) {
 #pragma unroll
         for (int gg = 0; gg < NW; ++gg) {
@@ -699,6 +717,9 @@ __device__ __forceinline__ void oz_issue_kstep(uint32_t tmem, uint32_t sa, uint3
         // products): pass 0 = 4 x N256 + 2 x N128, pass 1 = 6 x N256 + 6 x N128.  p = 0 touches every accumulator first.
 #pragma unroll
         for (int p = 0; p < OZ_SLICES; ++p) {
+#ifdef OZ_TIMING
+            if (half && (p & 1)) continue;
+#endif
             const int q_lo = (W0 - p) > 0 ? (W0 - p) : 0;
             const int q_hi = (W0 + NW - 1 - p) < (OZ_SLICES - 1) ? (W0 + NW - 1 - p) : (OZ_SLICES - 1);
             const uint64_t da = da0 + static_cast<uint64_t>(p * (OZ_SLICE_STEP_BYTES >> 4));
@@ -816,8 +837,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
                         if (P == 1 && ks == 0) OZ_STAMP(3);
                         const uint32_t sa = oz_smem_u32(oz_smem + stage * OZ2_STAGE_BYTES);
                         const uint32_t sb = sa + OZ2_A_BYTES;
-                        if (pass == 0) oz_issue_kstep<0, OZ2_BH_SLICE, true>(tmem, sa, sb, ks > 0 ? 1u : 0u);
-                        else oz_issue_kstep<1, OZ2_BH_SLICE, true>(tmem, sa, sb, ks > 0 ? 1u : 0u);
+                        if (pass == 0) oz_issue_kstep<0, 4, OZ2_BH_SLICE, true>(tmem, sa, sb, ks > 0 ? 1u : 0u);
+                        else oz_issue_kstep<4, 3, OZ2_BH_SLICE, true>(tmem, sa, sb, ks > 0 ? 1u : 0u);
                         oz_umma_commit2(&bars->empty[stage]);
                         if (ks == OZ_KSTEPS - 1) oz_umma_commit2(&bars->acc_full);
                     }
@@ -896,6 +917,254 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
+
+// =================================================================================================================
+// v4 (r02): the same two passes, fed through an 8-slot ring.
+// Measured on the r01 kernel (profiles/r02/x1_ozaki_bound_experiment.txt): loading ONE slice per operand instead of 4 / 7
+// changes the time of a 1830-tile launch by 3 % (0.246 vs 0.253 ms) and issuing HALF of the MMAs by 10 % -- the K loops
+// were bound neither by the shared-memory port nor by L2 -> SM bandwidth nor by the tensor pipe, but by the DEPTH of the
+// 3-stage ring: a stage is refilled only after the MMAs that read it have completed (tcgen05.commit -> mbarrier -> the
+// producer wakes -> cp.async.bulk -> ~1200 clk of L2 latency -> mbarrier -> the issuer wakes: ~2500 clk), and 3 stages of
+// K = 32 hold 640 (pass 0) to 1150 (pass 1) clk of MMA work each.  Here:
+//   * passes {0,1,2} / {3..6}: 3 + 7 = 10 slice loads per operand and K step instead of 4 + 7, 6 + 22 products;
+//   * slot = 28 KB = all 7 digits of ONE operand for one K step.  Pass 1 uses two slots per K step (A, B): 4 K steps =
+//     5600 clk of MMA work in flight; a pass-0 K step needs 3 + 3 digits = 24 KB and takes ONE slot: 8 K steps in flight;
+//   * 8 + 16 = 24 slot uses per tile = 3 revolutions of the ring: the slot of every (pass, K step) is static;
+//   * two producer threads: even / odd slot uses (pass 1: A / B blocks).
+// =================================================================================================================
+constexpr int OZ4_SLOTS = 8;
+constexpr int OZ4_SLOT_BYTES = OZ_SLICES * OZ_SLICE_STEP_BYTES;         // 28 KB
+constexpr int OZ4_NW0 = 3;
+constexpr int OZ4_P0_OPERAND = OZ4_NW0 * OZ_SLICE_STEP_BYTES;           // 12 KB
+constexpr int OZ4_USES = OZ_KSTEPS + 2 * OZ_KSTEPS;                     // slot uses per tile (24)
+static_assert(OZ4_USES % OZ4_SLOTS == 0, "the slot of a (pass, K step) must not depend on the tile");
+constexpr int OZ4_REVS = OZ4_USES / OZ4_SLOTS;
+
+struct __align__(8) Oz4Barriers {
+    uint64_t full[OZ4_SLOTS], empty[OZ4_SLOTS], acc_full, acc_empty;
+    uint32_t tmem_base, pad_;
+};
+constexpr int OZ4_SMEM_BYTES = OZ4_SLOTS * OZ4_SLOT_BYTES + static_cast<int>(sizeof(Oz4Barriers));
+static_assert(OZ4_SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
+
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk4_kernel(const OzakiArgs g) {
+    extern __shared__ __align__(1024) unsigned char oz_smem[];
+    Oz4Barriers* bars = reinterpret_cast<Oz4Barriers*>(oz_smem + OZ4_SLOTS * OZ4_SLOT_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = g.tri > 0 ? g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri : g.Mt * g.Nt;
+    if (tid == 0) OZ_STAMP(0);
+
+    if (tid == 0) {
+        for (int s = 0; s < OZ4_SLOTS; ++s) {
+            oz_mbar_init(&bars->full[s], 1);
+            oz_mbar_init(&bars->empty[s], 1);
+        }
+        oz_mbar_init(&bars->acc_full, 1);
+        oz_mbar_init(&bars->acc_empty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&bars->tmem_base)),
+                     "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = bars->tmem_base;
+    if (tid == 0) OZ_STAMP(1);
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OZ_REGS_CTRL));
+        if ((warp == 0 || warp == 2) && lane == 0) {
+            // ===== producers: warp 0 = even slot uses (pass 0: even K steps, pass 1: the A blocks), warp 2 = odd =====
+            const int par = warp >> 1;
+            uint32_t rev = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rev += OZ4_REVS) {
+                int tr, tc;
+                oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
+                const int8_t* Ag = g.S + static_cast<long>(tr) * OZ_RB_BYTES;
+                const int8_t* Bg = g.SB + static_cast<long>(tc) * OZ_RB_BYTES;
+                for (int u = par; u < OZ4_USES; u += 2) {
+                    const uint32_t slot = u & (OZ4_SLOTS - 1), r = rev + (u >> 3);
+                    unsigned char* dst = oz_smem + slot * OZ4_SLOT_BYTES;
+                    oz_mbar_wait(&bars->empty[slot], (r & 1) ^ 1);
+                    if (u < OZ_KSTEPS) {
+                        uint32_t bytes = OZ4_P0_OPERAND;
+#ifdef OZ_TIMING
+                        if (g.xp & 4) bytes = 1024;
+#endif
+                        oz_mbar_expect_tx(&bars->full[slot], 2 * bytes);
+                        oz_bulk_g2s(dst, Ag + static_cast<long>(u) * OZ_STAGE_OPERAND, bytes, &bars->full[slot]);
+                        oz_bulk_g2s(dst + OZ4_P0_OPERAND, Bg + static_cast<long>(u) * OZ_STAGE_OPERAND, bytes, &bars->full[slot]);
+                    } else {
+                        const int ks = (u - OZ_KSTEPS) >> 1;
+                        uint32_t bytes = OZ4_SLOT_BYTES;
+#ifdef OZ_TIMING
+                        if (g.xp & 4) bytes = 1024;
+#endif
+                        oz_mbar_expect_tx(&bars->full[slot], bytes);
+                        oz_bulk_g2s(dst, (par ? Bg : Ag) + static_cast<long>(ks) * OZ_STAGE_OPERAND, bytes, &bars->full[slot]);
+                    }
+                }
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===== MMA issuer =====
+#ifdef OZ_TIMING
+            const int half = g.xp & 1;
+#else
+            constexpr int half = 0;
+#endif
+            uint32_t rev = 0, P = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rev += OZ4_REVS) {
+                // pass 0: weights 0..2 into accumulators 0..2
+                if (P > 0) {
+                    oz_mbar_wait(&bars->acc_empty, (P - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int ks = 0; ks < OZ_KSTEPS; ++ks) {
+                    oz_mbar_wait(&bars->full[ks], rev & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (P == 0 && ks == 0) OZ_STAMP(2);
+                    if (P == 2 && ks == 0) OZ_STAMP(15);
+                    if (P == 2 && ks == 7) OZ_STAMP(16);
+                    const uint32_t sa = oz_smem_u32(oz_smem + ks * OZ4_SLOT_BYTES);
+                    oz_issue_kstep<0, OZ4_NW0, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sa + OZ4_P0_OPERAND, ks > 0 ? 1u : 0u, half);
+                    oz_umma_commit(&bars->empty[ks]);
+                }
+                oz_umma_commit(&bars->acc_full);
+                ++P;
+                // pass 1: weights 3..6 into accumulators 0..3
+                oz_mbar_wait(&bars->acc_empty, (P - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int ks = 0; ks < OZ_KSTEPS; ++ks) {
+                    const uint32_t u = OZ_KSTEPS + 2 * ks, slot = u & (OZ4_SLOTS - 1), r = rev + (u >> 3);
+                    oz_mbar_wait(&bars->full[slot], r & 1);
+                    oz_mbar_wait(&bars->full[slot + 1], r & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (P == 1 && ks == 0) OZ_STAMP(3);
+                    if (P == 3 && ks == 0) OZ_STAMP(17);
+                    const uint32_t sa = oz_smem_u32(oz_smem + slot * OZ4_SLOT_BYTES);
+                    oz_issue_kstep<OZ4_NW0, OZ_SLICES - OZ4_NW0, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sa + OZ4_SLOT_BYTES, ks > 0 ? 1u : 0u,
+                                                                                             half);
+                    oz_umma_commit(&bars->empty[slot]);
+                    oz_umma_commit(&bars->empty[slot + 1]);
+                }
+                oz_umma_commit(&bars->acc_full);
+                ++P;
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(OZ_REGS_EPI));
+        // ===== epilogue: 8 warps; lane quarter = warp % 4, column half = (warp - 4) / 4 =====
+        const int quarter = warp & 3, chalf = (warp - 4) >> 2;
+        const int r_in = lane >> 2, cq = 2 * (lane & 3);
+        const bool odd = (r_in & 1) != 0;
+        uint32_t P = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int tr, tc;
+            oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
+            // this thread's entries: rows 32 quarter + 16 rh + r_in (+8), columns 64 chalf + 8 j + cq + {0,1}
+            double* Cb = g.C + (static_cast<long>(tr) * 128 + 32 * quarter + r_in) * g.ldc + static_cast<long>(tc) * 128 +
+                         64 * chalf + cq;
+            const double* rsA = g.rscale + static_cast<long>(tr) * 128 + 32 * quarter + r_in;
+            const double* rsB = g.rscaleB + static_cast<long>(tc) * 128 + 64 * chalf + cq;
+            double2 c[2][2][8];                              // -(P P^T) of this thread's entries, [rh][row r_in / +8][j]
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) c[rh][h][j] = make_double2(0.0, 0.0);
+            // pull this thread's share of the C tile into L2 now (HBM -> L2 only): the read after pass 0 sees L2 latency
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j));
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass, ++P) {
+                // 256^-(last weight of the pass + 2)
+                const double wscale = pass == 0 ? 2.3283064365386963e-10 /* 256^-4 */ : 5.421010862427522e-20 /* 256^-8 */;
+                oz_mbar_wait(&bars->acc_full, P & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tid == 128 && tile == blockIdx.x) OZ_STAMP(4 + 2 * pass);
+                if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(10 + 2 * pass);
+                if (pass == 0) oz_drain<OZ4_NW0>(tmem, quarter, chalf, rsA, rsB, wscale, c);
+                else oz_drain<OZ_SLICES - OZ4_NW0>(tmem, quarter, chalf, rsA, rsB, wscale, c);
+                // all TMEM reads of this pass are complete: hand the accumulators back
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) oz_mbar_arrive(&bars->acc_empty);
+                if (tid == 128 && tile == blockIdx.x) OZ_STAMP(5 + 2 * pass);
+                if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(11 + 2 * pass);
+#ifdef OZ_TIMING
+                if (g.xp & 8) continue;
+#endif
+                if (pass == 0) {
+                    // c = C - (pass-0 part): the tile is READ here, while the MMAs of pass 1 run and these warps would only
+                    // wait.  Two adjacent quads (rows r, r+1 of the fragment) team up so that ONE instruction covers 128
+                    // contiguous bytes of a row: the even quad reads columns 8j.. of the even row and of the odd row, the
+                    // odd quad columns 8(j+1).. of both; what belongs to the partner changes hands through shfl.xor 4.
+#pragma unroll
+                    for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const double* base = Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + (odd ? 8 : 0);
+                            const double* row_e = base - (odd ? g.ldc : 0);
+                            const double* row_o = row_e + g.ldc;
+                            double2 ve[4], vo[4];
+#pragma unroll
+                            for (int jp = 0; jp < 4; ++jp) {
+                                ve[jp] = *reinterpret_cast<const double2*>(row_e + 16 * jp);
+                                vo[jp] = *reinterpret_cast<const double2*>(row_o + 16 * jp);
+                            }
+#pragma unroll
+                            for (int jp = 0; jp < 4; ++jp) {
+                                const double2 got = oz_shfl_xor4(odd ? ve[jp] : vo[jp]);
+                                const double2 own = odd ? vo[jp] : ve[jp];
+                                const double2 add0 = odd ? got : own, add1 = odd ? own : got;     // for columns 8j.. / 8(j+1)..
+                                c[rh][h][2 * jp].x += add0.x;
+                                c[rh][h][2 * jp].y += add0.y;
+                                c[rh][h][2 * jp + 1].x += add1.x;
+                                c[rh][h][2 * jp + 1].y += add1.y;
+                            }
+                        }
+                }
+            }
+#ifdef OZ_TIMING
+            if ((g.xp & 16) && c[0][0][0].x != 1.2345e300) goto skip_store4;     // timing experiment: no C store
+#endif
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double* base = Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + (odd ? 8 : 0);
+                    double* row_e = base - (odd ? g.ldc : 0);
+                    double* row_o = row_e + g.ldc;
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {
+                        const double2 own = odd ? c[rh][h][2 * jp + 1] : c[rh][h][2 * jp];
+                        const double2 got = oz_shfl_xor4(odd ? c[rh][h][2 * jp] : c[rh][h][2 * jp + 1]);
+                        *reinterpret_cast<double2*>(row_e + 16 * jp) = odd ? got : own;     // 128 B of the even row per quad pair
+                        *reinterpret_cast<double2*>(row_o + 16 * jp) = odd ? own : got;     // 128 B of the odd row
+                    }
+                }
+#ifdef OZ_TIMING
+        skip_store4:;
+#endif
+            if (tid == 128 && tile == blockIdx.x) OZ_STAMP(9);
+            if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(14);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) OZ_STAMP(8);
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_CSTG_BYTES + static_cast<int>(sizeof(OzBarriers));
 
 }  // namespace
@@ -920,8 +1189,10 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
     cudaGetDevice(&dev_);
     bool& configured = configured_dev[dev_ & 63];
     if (!configured) {
-        cudaFuncSetAttribute(ozaki_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+        cudaFuncSetAttribute(ozaki_syrk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+        cudaFuncSetAttribute(ozaki_syrk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
         cudaFuncSetAttribute(ozaki_syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM_BYTES);
+        cudaFuncSetAttribute(ozaki_syrk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ4_SMEM_BYTES);
         configured = true;
     }
     static int sm_count_dev[64] = {0};
@@ -931,7 +1202,9 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
     if (tiles <= 0) return;
     static const int c_reduce = getenv("EGX_OZAKI_CRED") != nullptr ? atoi(getenv("EGX_OZAKI_CRED")) : 0;   // measured: same tile rate as load / add / store (the 128 row reductions of a tile serialise in the TMA unit)
     static const int prod3 = getenv("EGX_OZAKI_PROD3") != nullptr ? atoi(getenv("EGX_OZAKI_PROD3")) : 0;
-    OzakiArgs g{C, ldc, SA, rsA, Mt, tri, SB, rsB, Nt, dbg, c_reduce, prod3};
+    static const int xp = getenv("EGX_OZAKI_XP") != nullptr ? atoi(getenv("EGX_OZAKI_XP")) : 0;           // probe builds only
+    static const int nw0 = getenv("EGX_OZAKI_NW0") != nullptr ? atoi(getenv("EGX_OZAKI_NW0")) : 4;
+    OzakiArgs g{C, ldc, SA, rsA, Mt, tri, SB, rsB, Nt, dbg, c_reduce, prod3, xp};
     alignas(64) CUtensorMap cmap;
     memset(&cmap, 0, sizeof(cmap));
     if (c_reduce == 2) {
@@ -976,7 +1249,10 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
         const int rounds = (tiles + sms - 1) / sms;
         grid = (tiles + rounds - 1) / rounds;
     }
-    ozaki_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g, cmap);
+    static const int version = getenv("EGX_OZAKI_V") != nullptr ? atoi(getenv("EGX_OZAKI_V")) : 4;     // 3: the r01 kernel (3-stage ring)
+    if (version == 4) ozaki_syrk4_kernel<<<grid, OZ_THREADS, OZ4_SMEM_BYTES, s>>>(g);
+    else if (nw0 == 3) ozaki_syrk_kernel<3><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g, cmap);
+    else ozaki_syrk_kernel<4><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g, cmap);
 }
 
 void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,

@@ -383,6 +383,32 @@ class SparseMethod:
     Fitc, Vfe = 0, 1
 
 
+def _expert_seed(mixture_seed):
+    """moe/src/algorithm.rs:330: the mixture hands its expert `self.rng().gen()` read as Option<u64> (surrogates.rs:42),
+    i.e. rand 0.8.5's Standard for Option: one bool (sign bit of next_u32) and, if true, one next_u64 of
+    Xoshiro256Plus::seed_from_u64(mixture_seed); None = the expert seeds itself from entropy (sparse_algorithm.rs:457-460)."""
+    if mixture_seed is None:
+        return None
+    m64 = (1 << 64) - 1
+    z, st = int(mixture_seed) & m64, []
+    for _ in range(4):                                   # SplitMix64 seeding of rand_xoshiro 0.6.0
+        z = (z + 0x9E3779B97F4A7C15) & m64
+        x = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m64
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & m64
+        st.append(x ^ (x >> 31))
+
+    def nxt():
+        r, t = (st[0] + st[3]) & m64, (st[1] << 17) & m64
+        st[2] ^= st[0]
+        st[3] ^= st[1]
+        st[1] ^= st[2]
+        st[0] ^= st[3]
+        st[2] ^= t
+        st[3] = ((st[3] << 45) | (st[3] >> 19)) & m64
+        return r
+    return nxt() if (nxt() >> 63) == 1 else None
+
+
 class SparseGpMix:
     """python/src/sparse_gp_mix.rs:64-219 (single cluster)."""
 
@@ -410,7 +436,8 @@ class SparseGpMix:
             ind = Inducings.Randomized(self.nz)
         else:
             raise ValueError("You must specify inducing points")      # sparse_gp_mix.rs:176-178
-        p = SgpParams(_CORR[self.corr_spec], ind).sparse_method(self.method).n_start(self.n_start).seed(self.seed)
+        p = SgpParams(_CORR[self.corr_spec], ind).sparse_method(self.method).n_start(self.n_start)
+        p = p.seed(_expert_seed(self.seed))
         p = p.device(self.device)
         if self.theta_init is not None:
             p = p.theta_init(self.theta_init)

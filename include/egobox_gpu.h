@@ -302,6 +302,15 @@ int egx_bound_cobyla_minimize(egx_objective_fn f, void* user, int n, const doubl
                               double* x_opt, double* f_opt, int* n_evals);
 int egx_prepare_multistart(int n_start, const double* theta0, const double* bounds, int dim,
                            unsigned long long seed, double* starts_out);
+/* The seeded random streams of the path, restated from rand 0.8.5 / rand_xoshiro 0.6.0 (Cargo.lock) so that a seed
+ * gives the reference's own points:
+ * egx_lhs_sample: `Lhs::new(xlimits).kind(..).with_rng(Xoshiro256Plus::seed_from_u64(seed)).sample(ns)`,
+ *   doe/src/lhs.rs:67-88, 235-258 (kind 0 = Classic), 283-304 (kind 1 = Maximin, what prepare_multistart uses);
+ *   xlimits = nx (lower, upper) pairs, out = ns x nx row-major.  Pinned on the fixture of doe/src/lhs.rs:332-347.
+ * egx_shuffled_indices: `(0..n).collect::<Vec<_>>().shuffle(&mut Xoshiro256Plus::seed_from_u64(seed))`, the index
+ *   stream of make_inducings (gp/src/sparse_algorithm.rs:833-847): the inducing points are rows out[0..nz) of xt. */
+int egx_lhs_sample(int kind, int ns, int nx, const double* xlimits, unsigned long long seed, double* out);
+int egx_shuffled_indices(int n, unsigned long long seed, int* out);
 /* egx_bound_lbfgs_minimize: the per-start optimiser of EGX_OPT_LBFGSB -- projected limited-memory BFGS (8 pairs) with
  * Armijo backtracking over the box [lo, hi]; fg returns f and writes the gradient.  Stops on
  * f_prev - f <= ftol_rel * max(|f_prev|, |f|, 1), on |projected gradient|_inf <= gtol * max(1, |f|), or on the budget. */
