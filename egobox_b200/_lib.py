@@ -36,6 +36,7 @@ SIGNATURES = {
     "egx_gp_reduced_likelihood_batch": (C.c_int, [_vp, _dp, C.c_int, _dp, _ip]),
     "egx_gp_finalize": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "egx_gp_async_slots": (C.c_int, [_vp, C.c_int]),
+    "egx_gp_release_workspaces": (C.c_int, [_vp]),
     "egx_gp_eval_begin": (C.c_int, [_vp, C.c_int, _dp]),
     "egx_gp_eval_end": (C.c_int, [_vp, C.c_int, _dp]),
     "egx_gp_reduced_likelihood_grad": (C.c_int, [_vp, _dp, C.c_double, _dp, _dp]),
@@ -77,6 +78,9 @@ SIGNATURES = {
 
 
 
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_void_p)
+
+
 class GpParamsStruct(C.Structure):
     """egx_gp_params (include/egobox_gpu.h)."""
     _fields_ = [("corr", C.c_int), ("mean", C.c_int), ("theta_tuning", C.c_int),
@@ -86,7 +90,8 @@ class GpParamsStruct(C.Structure):
                 ("n_start", C.c_int), ("max_eval", C.c_int), ("nugget", C.c_double),
                 ("w_star", _dp), ("kpls_dim", C.c_int), ("device", C.c_int),
                 ("seed", C.c_ulonglong), ("cobyla_rhobeg", C.c_double), ("cobyla_ftol_rel", C.c_double),
-                ("optimizer", C.c_int)]
+                ("optimizer", C.c_int), ("chain_rank", C.c_int), ("chain_world", C.c_int),
+                ("exchange", EXCHANGE_FN), ("exchange_user", C.c_void_p)]
 
 
 EGX_OPT_COBYLA, EGX_OPT_LBFGSB = 0, 1

@@ -849,6 +849,20 @@ extern "C" int egx_gp_async_slots(egx_gp_ctx* c, int wanted) try {
 }
 EGX_ABI_CATCH_COUNT
 
+// Give the replica workspaces of the batched / asynchronous entry points back to the block cache (each holds a full
+// (npad + 128) x npad matrix, panels, slices, streams: ~0.6 GB at n = 8192).  A trained model only needs the primary
+// workspace for predict*; the next batch or fit re-creates replicas from the cache.
+extern "C" int egx_gp_release_workspaces(egx_gp_ctx* c) try {
+    if (!c) return EGX_INVALID_VALUE;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (cudaSetDevice(c->device) != cudaSuccess) return EGX_CUDA_ERROR;
+    for (egx_gp_ctx* r : c->replicas) free_ctx(r);
+    c->replicas.clear();
+    c->async_slots = 0;
+    return EGX_OK;
+}
+EGX_ABI_CATCH
+
 extern "C" int egx_gp_eval_begin(egx_gp_ctx* c, int slot, const double* theta) try {
     if (!c || !theta || slot < 0 || slot >= c->async_slots) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);

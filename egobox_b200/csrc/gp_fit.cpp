@@ -730,6 +730,19 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
                 }
             }
             const int maxeval = std::min(std::max(10 * na, GP_COBYLA_MIN_EVAL), std::max(prm->max_eval, 1));
+            // chains sharded over processes (one per GPU): chain c belongs to rank c % world; the reduce by min of
+            // algorithm.rs:942-945 is completed across ranks by prm->exchange below
+            const int cworld = std::max(prm->chain_world, 1), crank = prm->chain_rank;
+            if (crank < 0 || crank >= cworld) {
+                egx_set_error("egx_gp_fit: chain_rank %d outside [0, %d)", crank, cworld);
+                return EGX_INVALID_VALUE;
+            }
+            if (cworld > 1) {
+                std::vector<std::vector<double>> mine;
+                for (size_t c = 0; c < starts.size(); ++c)
+                    if (static_cast<int>(c % cworld) == crank) mine.push_back(starts[c]);
+                starts.swap(mine);
+            }
             std::vector<BoundCobyla> chains;
             chains.reserve(starts.size());
             for (auto& s0 : starts) chains.emplace_back(s0, lo, hi, prm->cobyla_rhobeg, prm->cobyla_ftol_rel, maxeval);
@@ -869,6 +882,12 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
                     zbest = ch.best_x();
                 }
             }
+            if (prm->exchange != nullptr) {
+                if (prm->exchange(&fbest, zbest.data(), na, prm->exchange_user) != 0) {
+                    egx_set_error("egx_gp_fit: the exchange callback of the sharded multistart failed");
+                    return EGX_CUDA_ERROR;
+                }
+            }
             // algorithm.rs:947-964
             if (prm->theta_tuning == EGX_THETA_PARTIAL) {
                 theta_opt = theta0;
@@ -882,6 +901,7 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
     double rlf = NAN, s2 = NAN;
     st = egx_gp_finalize(m->ctx, theta_opt.data(), &rlf, &s2, nullptr, nullptr, nullptr, nullptr);
     m->n_evals += 1;
+    egx_gp_release_workspaces(m->ctx);  // the multistart workspaces (up to 11 x 0.6 GB at n = 8192) are not needed by predict*
     if (st != EGX_OK) return st;        // `?` at algorithm.rs:967-968
     m->theta = theta_opt;
     m->likelihood = rlf;

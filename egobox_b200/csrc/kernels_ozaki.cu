@@ -1165,6 +1165,342 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk4_kernel(const OzakiA
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
+
+// =================================================================================================================
+// v5 (r02): four weight groups, two accumulator buffers -- the accumulator drains run UNDER the MMAs.
+// What the r02 probes showed (profiles/r02/pattern_probe.txt, x1_*, x2_*):
+//   * an N = 256 MMA (two adjacent B digits) runs at the nominal 128 clk, an N = 128 MMA takes 100 clk, not 64 (operand
+//     fetch: 8 KB of shared memory per MMA); every mbarrier wait of the issuing thread costs ~130 clk that the tensor
+//     pipe does NOT hide (the MMA queue is shallow), and so does anything else that slows that one thread down;
+//   * operand loads are far from any limit (one slice instead of 4 / 7 per load: 3 % faster), L2 -> SM sustains 68 B/clk/SM
+//     with all SMs pulling (bulk_probe), the two-pass kernels need ~25;
+//   * in the two-pass kernels the tensor pipe idles through both drains (all 512 TMEM columns are live): 7.4 k of 31 k clk.
+// Schedule: weights {5,6}, {3,4}, {1,2}, {0}, alternating between the TMEM halves X (columns 0..255) and Y (256..511):
+// while the MMAs of a group fill one half, the epilogue drains the other.  In this order a group needs digits 0..6, 0..4,
+// 0..2, 0 of both operands: 16 slice loads per operand and K step (10 in the two-pass form -- affordable, see above), and
+// 19 of the 28 products still pair up into N = 256 MMAs (6 + 4 + 2 N256, 1 + 1 + 1 + 1 N128: 1936 clk per K step at the
+// measured rates, the same as the two-pass form).  Ring: 4 stages x 56 KB (A half | B half); a stage holds 1 / 1 / 2 / 7
+// K steps of group 0 / 1 / 2 / 3, so the issuing thread waits 8 + 8 + 4 + 2 = 22 times per tile.
+// Epilogue: c -= T 2^E for every group, T = a0 256 + a1 exact in int64, and since the row scales are powers of two the
+// scaling is folded into the int -> double conversion: bits(1.5 * 2^(52+E)) + T is the double 1.5 * 2^(52+E) + T 2^E
+// EXACTLY (|T| < 2^51), so one integer add and one DADD replace convert + DMUL.
+// =================================================================================================================
+constexpr int OZ5_STAGES = 3;
+constexpr int OZ5_HALF = OZ_SLICES * OZ_SLICE_STEP_BYTES;                // 28 KB: one operand
+constexpr int OZ5_STAGE_BYTES = 2 * OZ5_HALF;                            // 56 KB
+constexpr int OZ5_GROUPS = 4;
+constexpr int OZ5_PIECE_ROWS = 8;                                        // C leaves in pieces of 8 rows x 128 columns (8 KB) ...
+constexpr int OZ5_PIECE_BYTES = OZ5_PIECE_ROWS * 128 * 8;                // ... one staging buffer per lane quarter (warp pair)
+constexpr int OZ5_STAGING_BYTES = 4 * OZ5_PIECE_BYTES;                   // 32 KB
+
+struct __align__(8) Oz5Barriers {
+    uint64_t full[OZ5_STAGES], empty[OZ5_STAGES], acc_full[2], acc_empty[2];
+    uint32_t tmem_base, pad_;
+};
+constexpr int OZ5_SMEM_BYTES = OZ5_STAGES * OZ5_STAGE_BYTES + OZ5_STAGING_BYTES + static_cast<int>(sizeof(Oz5Barriers));
+static_assert(OZ5_SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
+
+// group g: weights W0 .. W0 + NW - 1, digits 0 .. D - 1 of both operands, KPS K steps per ring stage
+template <int G> struct Oz5Group;
+template <> struct Oz5Group<0> { static constexpr int W0 = 5, NW = 2, D = 7, KPS = 1; };
+template <> struct Oz5Group<1> { static constexpr int W0 = 3, NW = 2, D = 5, KPS = 1; };
+template <> struct Oz5Group<2> { static constexpr int W0 = 1, NW = 2, D = 3, KPS = 2; };
+template <> struct Oz5Group<3> { static constexpr int W0 = 0, NW = 1, D = 1, KPS = 7; };
+
+// producer of ONE operand: all stage uses of group G of the current tile
+template <int G>
+__device__ __forceinline__ void oz5_produce(unsigned char* smem, Oz5Barriers* bars, const int8_t* Sg, int operand, uint32_t& n,
+                                            int tiny) {
+    using Gp = Oz5Group<G>;
+#pragma unroll 1
+    for (int ks0 = 0; ks0 < OZ_KSTEPS; ks0 += Gp::KPS, ++n) {
+        const int nk = (OZ_KSTEPS - ks0) < Gp::KPS ? (OZ_KSTEPS - ks0) : Gp::KPS;
+        const uint32_t stage = n % OZ5_STAGES, round = n / OZ5_STAGES;
+        uint32_t bytes = Gp::D * OZ_SLICE_STEP_BYTES;
+        if (tiny) bytes = 1024;
+        unsigned char* dst = smem + stage * OZ5_STAGE_BYTES + operand * OZ5_HALF;
+        oz_mbar_wait(&bars->empty[stage], (round & 1) ^ 1);
+        oz_mbar_expect_tx(&bars->full[stage], static_cast<uint32_t>(nk) * bytes);
+        for (int j = 0; j < nk; ++j)
+            oz_bulk_g2s(dst + j * (Gp::D * OZ_SLICE_STEP_BYTES), Sg + static_cast<long>(ks0 + j) * OZ_STAGE_OPERAND, bytes,
+                        &bars->full[stage]);
+    }
+}
+
+// MMA issue of group G of the current tile into the accumulator buffer at tmem_buf
+template <int G>
+__device__ __forceinline__ void oz5_issue(unsigned char* smem, Oz5Barriers* bars, uint32_t tmem_buf, uint32_t& n, int half) {
+    using Gp = Oz5Group<G>;
+#pragma unroll 1
+    for (int ks0 = 0; ks0 < OZ_KSTEPS; ks0 += Gp::KPS, ++n) {
+        const int nk = (OZ_KSTEPS - ks0) < Gp::KPS ? (OZ_KSTEPS - ks0) : Gp::KPS;
+        const uint32_t stage = n % OZ5_STAGES, round = n / OZ5_STAGES;
+        const uint32_t sa = oz_smem_u32(smem + stage * OZ5_STAGE_BYTES);
+        oz_mbar_wait(&bars->full[stage], round & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int j = 0; j < nk; ++j) {
+            const uint32_t a = sa + j * (Gp::D * OZ_SLICE_STEP_BYTES);
+            oz_issue_kstep<Gp::W0, Gp::NW, OZ_SLICE_STEP_BYTES, false>(tmem_buf, a, a + OZ5_HALF, (ks0 + j) > 0 ? 1u : 0u, half);
+        }
+        oz_umma_commit(&bars->empty[stage]);
+    }
+}
+
+// Integer accumulation of the groups.  Measured (profiles/r02/alu_probe.txt, drain_probe.txt): while int8 MMAs stream, fp64
+// instructions (DADD / DFMA) of ANY warp of the SM run 7 - 8 x slower, integer and fp32 instructions are unaffected -- a
+// drain that folds in fp64 takes 68 k instead of 1.8 k clk under a saturated MMA stream.  So an entry is kept as ONE int64
+//     T = a0 2^40 + a1 2^32 + a2 2^24 + a3 2^16 + a4 2^8 + a5 + round(a6 / 256)      (units of 256^-7 s_i s_j)
+// (|a_w| <= (w + 1) 2^22: |T| < 2^63; dropping the low 8 bits of the last weight is 2^-57 s_i s_j, far below the digit pairs the
+// scheme drops anyway), accumulated with IMAD.WIDE / IADD3 as the groups complete, and meets fp64 once per tile:
+// one int64 -> double conversion, the power-of-two scales applied to its exponent field, one DADD with C.
+// thread t holds, for repetition jr of a 16x256b.x4 load, v[4jr+0..1] = row (t/4), columns 8 jr + 2 (t%4) + {0,1}, v[4jr+2..3] = row + 8
+template <int G, int NACC>
+__device__ __forceinline__ void oz5_fold(const uint32_t (&a)[NACC][16], int j0, long long (&T0)[8][2], long long (&T1)[8][2]) {
+#pragma unroll
+    for (int rep = 0; rep < 4; ++rep) {
+        const int j = j0 + rep;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            long long& t = (e & 2) ? T1[j][e & 1] : T0[j][e & 1];
+            const long long x0 = static_cast<long long>(static_cast<int32_t>(a[0][4 * rep + e]));
+            if constexpr (G == 0) {          // weights 5, 6 -- the first group of a tile initialises T
+                const int32_t x1 = static_cast<int32_t>(a[1][4 * rep + e]);
+                t = x0 + static_cast<long long>((x1 + 128) >> 8);
+            } else if constexpr (G == 1) {   // weights 3, 4
+                const long long x1 = static_cast<long long>(static_cast<int32_t>(a[1][4 * rep + e]));
+                t += x0 * 65536LL + x1 * 256LL;
+            } else if constexpr (G == 2) {   // weights 1, 2
+                const long long x1 = static_cast<long long>(static_cast<int32_t>(a[1][4 * rep + e]));
+                t += x0 * 4294967296LL + x1 * 16777216LL;
+            } else {                         // weight 0
+                t += x0 * 1099511627776LL;
+            }
+        }
+    }
+}
+// 4 steps of 16 rows x 32 columns (tcgen05.ld.16x256b.x4), the loads of step i + 1 in flight while step i is folded
+template <int G, int NACC>
+__device__ __forceinline__ void oz5_drain(uint32_t tmem_buf, int quarter, int chalf, long long (&T)[2][2][8][2]) {
+    uint32_t a0[NACC][16], a1[NACC][16];
+    const uint32_t tbase = tmem_buf + (static_cast<uint32_t>(32 * quarter) << 16) + 64 * chalf;
+    auto issue = [&](int step, uint32_t (&dst)[NACC][16]) {
+        const uint32_t taddr = tbase + (static_cast<uint32_t>(16 * (step >> 1)) << 16) + 32 * (step & 1);
+#pragma unroll
+        for (int gg = 0; gg < NACC; ++gg) oz_tmem_ld(taddr + gg * 128, dst[gg]);
+    };
+    issue(0, a0);
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        issue(2 * rh + 1, a1);
+        oz5_fold<G, NACC>(a0, 0, T[rh][0], T[rh][1]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (rh == 0) issue(2, a0);
+        oz5_fold<G, NACC>(a1, 4, T[rh][0], T[rh][1]);
+    }
+}
+// exponent of a power-of-two scale as e << 20 (the position of the exponent field in the high word of a double), made safe for the
+// exponent arithmetic: 0 (an all-zero row: its T is 0 whatever E) -> 2^0, below 2^-480 -> 2^-480 (such a row contributes < 2^-900 to C)
+__device__ __forceinline__ int oz5_scale_hi(const double* p) {
+    const int hi = __double2hiint(*p);
+    return hi == 0 ? 0 : ((hi < ((1023 - 480) << 20) ? ((1023 - 480) << 20) : hi) - (1023 << 20));
+}
+// T 2^E, E = e_i + e_j - 56 (the unit of T is 256^-7 s_i s_j): (e_i << 20) + (e_j << 20) + OZ5_ECONST = E << 20 is ADDED to the high
+// word of (double) T -- an exponent shift, exact; T == 0 stays 0
+constexpr int OZ5_ECONST = -56 * 1048576;
+// (double) t * 2^E with INTEGER instructions only (I2F.F64.S64 sits on the fp64 pipe too: 64 conversions per thread took 15 k clk
+// under the MMA stream): normalise |t| (bit 63 set), keep 53 bits rounded half-up (1 ulp of 2^-53 relative against RN at worst,
+// far below the scheme's own truncation), assemble sign | exponent | mantissa.  eshift = E << 20.
+// Returns -t 2^E (the update is ADDED to C by the TMA reduction).
+__device__ __forceinline__ double oz5_scaled(long long t, int eshift) {
+    const unsigned long long a = t < 0 ? 0ULL - static_cast<unsigned long long>(t) : static_cast<unsigned long long>(t);
+    const int lz = __clzll(static_cast<long long>(a | 1ULL));
+    const unsigned long long nrm = a << lz;
+    const unsigned long long mant = (nrm >> 11) + ((nrm >> 10) & 1ULL);           // 2^52 .. 2^53 (the implicit bit included)
+    int hi = ((1085 - lz) << 20) + eshift + static_cast<int>(mant >> 32);        // (exponent - 1) << 20, + the implicit bit
+    hi |= ~static_cast<int>(static_cast<unsigned long long>(t) >> 32) & static_cast<int>(0x80000000u);
+    const bool nz = t != 0;
+    return __hiloint2double(nz ? hi : 0, nz ? static_cast<int>(static_cast<uint32_t>(mant)) : 0);
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiArgs g, const __grid_constant__ CUtensorMap cmap) {
+    extern __shared__ __align__(1024) unsigned char oz_smem[];
+    unsigned char* staging = oz_smem + OZ5_STAGES * OZ5_STAGE_BYTES;
+    Oz5Barriers* bars = reinterpret_cast<Oz5Barriers*>(staging + OZ5_STAGING_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = g.tri > 0 ? g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri : g.Mt * g.Nt;
+    if (tid == 0) OZ_STAMP(0);
+
+    if (tid == 0) {
+        for (int s = 0; s < OZ5_STAGES; ++s) {
+            oz_mbar_init(&bars->full[s], 2);
+            oz_mbar_init(&bars->empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            oz_mbar_init(&bars->acc_full[b], 1);
+            oz_mbar_init(&bars->acc_empty[b], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&bars->tmem_base)),
+                     "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = bars->tmem_base;
+    if (tid == 0) OZ_STAMP(1);
+#ifdef OZ_TIMING
+    const int xp = g.xp;
+#else
+    constexpr int xp = 0;
+#endif
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OZ_REGS_CTRL));
+        if ((warp == 0 || warp == 2) && lane == 0) {
+            // ===== producers: warp 0 = the A halves of the stages, warp 2 = the B halves =====
+            const int operand = warp >> 1;
+            uint32_t n = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                int tr, tc;
+                oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
+                const int8_t* Sg = operand ? g.SB + static_cast<long>(tc) * OZ_RB_BYTES : g.S + static_cast<long>(tr) * OZ_RB_BYTES;
+                oz5_produce<0>(oz_smem, bars, Sg, operand, n, xp & 4);
+                oz5_produce<1>(oz_smem, bars, Sg, operand, n, xp & 4);
+                oz5_produce<2>(oz_smem, bars, Sg, operand, n, xp & 4);
+                oz5_produce<3>(oz_smem, bars, Sg, operand, n, xp & 4);
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===== MMA issuer: groups 0, 2 -> buffer X, groups 1, 3 -> buffer Y; use u of a buffer waits for the drain of use u - 1 =====
+            uint32_t n = 0, u = 0;                            // stage uses; uses of EACH buffer so far (both advance together)
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const bool t1 = tile == static_cast<int>(blockIdx.x + gridDim.x);
+                if (u > 0) { oz_mbar_wait(&bars->acc_empty[0], (u - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                if (t1) OZ_STAMP(20);
+                oz5_issue<0>(oz_smem, bars, tmem, n, xp & 1);
+                oz_umma_commit(&bars->acc_full[0]);
+                if (u > 0) { oz_mbar_wait(&bars->acc_empty[1], (u - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                if (t1) OZ_STAMP(21);
+                oz5_issue<1>(oz_smem, bars, tmem + 256, n, xp & 1);
+                oz_umma_commit(&bars->acc_full[1]);
+                ++u;
+                oz_mbar_wait(&bars->acc_empty[0], (u - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (t1) OZ_STAMP(22);
+                oz5_issue<2>(oz_smem, bars, tmem, n, xp & 1);
+                oz_umma_commit(&bars->acc_full[0]);
+                oz_mbar_wait(&bars->acc_empty[1], (u - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (t1) OZ_STAMP(23);
+                oz5_issue<3>(oz_smem, bars, tmem + 256, n, xp & 1);
+                oz_umma_commit(&bars->acc_full[1]);
+                ++u;
+                if (t1) OZ_STAMP(24);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(OZ_REGS_EPI));
+        // ===== epilogue: 8 warps; lane quarter = warp % 4, column half = (warp - 4) / 4 =====
+        const int quarter = warp & 3, chalf = (warp - 4) >> 2;
+        const int r_in = lane >> 2, cq = 2 * (lane & 3);
+        const bool odd = (r_in & 1) != 0;
+        uint32_t u = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const bool t0 = tile == static_cast<int>(blockIdx.x), t1 = tile == static_cast<int>(blockIdx.x + gridDim.x);
+            int tr, tc;
+            oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
+            // this thread's entries: rows 32 quarter + 16 rh + r_in (+8), columns 64 chalf + 8 j + cq + {0,1}
+            double* Cb = g.C + (static_cast<long>(tr) * 128 + 32 * quarter + r_in) * g.ldc + static_cast<long>(tc) * 128 +
+                         64 * chalf + cq;
+            const double* rsA = g.rscale + static_cast<long>(tr) * 128 + 32 * quarter + r_in;
+            const double* rsB = g.rscaleB + static_cast<long>(tc) * 128 + 64 * chalf + cq;
+            int hiA[2][2], hiB[8][2];
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) hiA[rh][h] = oz5_scale_hi(rsA + 16 * rh + 8 * h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                hiB[j][0] = oz5_scale_hi(rsB + 8 * j);
+                hiB[j][1] = oz5_scale_hi(rsB + 8 * j + 1);
+            }
+            long long T[2][2][8][2];                         // this thread's entries, [rh][row r_in / +8][j][column parity]
+#pragma unroll
+            for (int grp = 0; grp < OZ5_GROUPS; ++grp) {
+                const int b = grp & 1;
+                if (grp == 2) ++u;
+                oz_mbar_wait(&bars->acc_full[b], u & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tid == 128 && t1) OZ_STAMP(25 + 2 * grp);
+                if (grp == 0) oz5_drain<0, 2>(tmem, quarter, chalf, T);
+                else if (grp == 1) oz5_drain<1, 2>(tmem + 256, quarter, chalf, T);
+                else if (grp == 2) oz5_drain<2, 2>(tmem, quarter, chalf, T);
+                else oz5_drain<3, 1>(tmem + 256, quarter, chalf, T);
+                // all TMEM reads of this group are complete: hand the buffer back
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) oz_mbar_arrive(&bars->acc_empty[b]);
+                if (tid == 128 && t1) OZ_STAMP(26 + 2 * grp);
+            }
+            ++u;
+            // C += -T 2^E WITHOUT the fp64 pipe and without reading C: the entries are converted with integer instructions,
+            // staged in shared memory 8 rows x 128 columns at a time (one buffer per lane quarter = per pair of warps) and
+            // leave as cp.reduce.async.bulk.tensor .add on an fp64 tensor map of C (SASS UTMAREDG): the adds happen in L2.
+            // Two adjacent quads (rows r, r+1 of the fragment) team up so that 8 lanes write 128 contiguous bytes of one
+            // row (no bank conflicts): the even quad writes columns 8j.. of the even row and of the odd row, the odd quad
+            // columns 8(j+1).. of both; what belongs to the partner changes hands through shfl.xor 4.
+            {
+                double* stg = reinterpret_cast<double*>(staging + quarter * OZ5_PIECE_BYTES);
+                double* st_e = stg + (r_in - (odd ? 1 : 0)) * 128 + 64 * chalf + cq + (odd ? 8 : 0);
+                double* st_o = st_e + 128;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int rh = q >> 1, h = q & 1;
+                    const int er = hiA[rh][h] + OZ5_ECONST;
+                    // the previous piece of this warp pair has been read by the TMA (the issuing thread waited) before anybody writes
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {
+                        double2 c0, c1;                                               // columns 8 (2 jp).. / 8 (2 jp + 1).. of this thread's row
+                        c0.x = oz5_scaled(T[rh][h][2 * jp][0], er + hiB[2 * jp][0]);
+                        c0.y = oz5_scaled(T[rh][h][2 * jp][1], er + hiB[2 * jp][1]);
+                        c1.x = oz5_scaled(T[rh][h][2 * jp + 1][0], er + hiB[2 * jp + 1][0]);
+                        c1.y = oz5_scaled(T[rh][h][2 * jp + 1][1], er + hiB[2 * jp + 1][1]);
+                        const double2 mine = odd ? c1 : c0;
+                        const double2 back = oz_shfl_xor4(odd ? c0 : c1);
+                        *reinterpret_cast<double2*>(st_e + 16 * jp) = odd ? back : mine;      // 128 B of the even row per quad pair
+                        *reinterpret_cast<double2*>(st_o + 16 * jp) = odd ? mine : back;      // 128 B of the odd row
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+                    if (chalf == 0 && lane == 0) {
+                        if (!(xp & 16)) {
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(&cmap)),
+                                         "r"(oz_smem_u32(stg)), "r"(tc * 128), "r"(tr * 128 + 32 * quarter + 16 * rh + 8 * h)
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
+                    }
+                }
+            }
+            if (tid == 128 && t0) OZ_STAMP(9);
+            if (tid == 128 && t1) OZ_STAMP(14);
+        }
+        // the reductions of this thread have been performed (not only read from shared memory) before the CTA retires
+        if (chalf == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) OZ_STAMP(8);
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + OZ_CSTG_BYTES + static_cast<int>(sizeof(OzBarriers));
 
 }  // namespace
@@ -1193,6 +1529,7 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
         cudaFuncSetAttribute(ozaki_syrk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
         cudaFuncSetAttribute(ozaki_syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM_BYTES);
         cudaFuncSetAttribute(ozaki_syrk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ4_SMEM_BYTES);
+        cudaFuncSetAttribute(ozaki_syrk5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ5_SMEM_BYTES);
         configured = true;
     }
     static int sm_count_dev[64] = {0};
@@ -1207,8 +1544,10 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
     OzakiArgs g{C, ldc, SA, rsA, Mt, tri, SB, rsB, Nt, dbg, c_reduce, prod3, xp};
     alignas(64) CUtensorMap cmap;
     memset(&cmap, 0, sizeof(cmap));
-    if (c_reduce == 2) {
-        // fp64 tensor map of the C region of this launch: (columns, rows), row pitch ldc, boxes of 128 columns x 32 rows
+    static const int version = getenv("EGX_OZAKI_V") != nullptr ? atoi(getenv("EGX_OZAKI_V")) : 5;     // 3: the r01 kernel (3-stage ring, two passes)
+    bool have_map = false;
+    if (c_reduce == 2 || version == 5) {
+        // fp64 tensor map of the C region of this launch: (columns, rows), row pitch ldc, boxes of 128 columns x 32 (v5: 8) rows
         typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1220,11 +1559,13 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
         }
         const cuuint64_t dims[2] = {static_cast<cuuint64_t>(Nt) * 128, static_cast<cuuint64_t>(Mt) * 128};
         const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldc) * sizeof(double)};
-        const cuuint32_t box[2] = {128, 32}, estr[2] = {1, 1};
+        const cuuint32_t box[2] = {128, static_cast<cuuint32_t>(version == 5 ? OZ5_PIECE_ROWS : 32)}, estr[2] = {1, 1};
         if (encode == nullptr ||
             encode(&cmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-            g.c_reduce = 0;                        // no encoder / unsupported shape: plain load / add / store
+            g.c_reduce = 0;                        // no encoder / unsupported shape: plain load / add / store (the r01 kernel)
+        } else {
+            have_map = true;
         }
     }
     // persistent: a resident grid loops over the tiles (prefetch across tiles, no per-tile set-up, the C update of a
@@ -1249,8 +1590,8 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
         const int rounds = (tiles + sms - 1) / sms;
         grid = (tiles + rounds - 1) / rounds;
     }
-    static const int version = getenv("EGX_OZAKI_V") != nullptr ? atoi(getenv("EGX_OZAKI_V")) : 4;     // 3: the r01 kernel (3-stage ring)
-    if (version == 4) ozaki_syrk4_kernel<<<grid, OZ_THREADS, OZ4_SMEM_BYTES, s>>>(g);
+    if (version == 5 && have_map) ozaki_syrk5_kernel<<<grid, OZ_THREADS, OZ5_SMEM_BYTES, s>>>(g, cmap);
+    else if (version == 4) ozaki_syrk4_kernel<<<grid, OZ_THREADS, OZ4_SMEM_BYTES, s>>>(g);
     else if (nw0 == 3) ozaki_syrk_kernel<3><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g, cmap);
     else ozaki_syrk_kernel<4><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g, cmap);
 }

@@ -160,6 +160,12 @@ class GpParams:
             raise InvalidValueError("theta_tuning: init and bounds should have the same size")
         return self
 
+    def chain_shard(self, rank, world, exchange):
+        """Run only the multistart chains c with c % world == rank here; `exchange(f_best, z_best) -> (f, z)` returns the
+        best (objective, log10 theta) over all ranks (see parallel.fit_multistart)."""
+        self._chain_shard = (rank, world, exchange)
+        return self
+
     def fit(self, x, y):
         """impl Fit for GpValidParams, algorithm.rs:791-979."""
         self.check()
@@ -205,6 +211,22 @@ class GpParams:
             prm.kpls_dim = int(self._kpls_dim)
         prm.device, prm.seed, prm.cobyla_ftol_rel = int(self._device), int(self._seed), float(self._ftol_rel)
         prm.optimizer = _lib.EGX_OPT_LBFGSB if self._optimizer == "lbfgsb" else _lib.EGX_OPT_COBYLA
+        shard = getattr(self, "_chain_shard", None)
+        if shard is not None:                 # multistart chains sharded over ranks (egobox_b200/parallel.py::fit_multistart)
+            rank, world, exchange = shard
+
+            def _cb(f_ptr, z_ptr, nz, _user):
+                try:
+                    z = np.ctypeslib.as_array(z_ptr, shape=(nz,))
+                    f, zb = exchange(float(f_ptr[0]), z.copy())
+                    f_ptr[0] = f
+                    z[:] = zb
+                    return 0
+                except Exception:             # never unwind through the C frames
+                    return 1
+            cb = _lib.EXCHANGE_FN(_cb)
+            keep.append(cb)
+            prm.chain_rank, prm.chain_world, prm.exchange = int(rank), int(world), cb
         h = C.c_void_p()
         st = lib.egx_gp_fit(C.byref(prm), x.ctypes.data_as(C.POINTER(C.c_double)), n, d,
                             y.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h))

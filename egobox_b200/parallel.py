@@ -106,6 +106,50 @@ def fit_experts(fit_one, n_experts, theta_dim):
     return models, table
 
 
+def argmin_exchange(f_best, z_best):
+    """The `reduce` by min of gp/src/algorithm.rs:942-945 completed across ranks: every rank contributes its best
+    (objective, log10 theta); all get those of the rank with the smallest objective (ties: lowest rank; +inf / NaN lose)."""
+    z = np.asarray(z_best, dtype=np.float64).reshape(-1)
+    dist = _dist()
+    if dist is None:
+        return float(f_best), z
+    world = dist.get_world_size()
+    f = float(f_best)
+    row = np.concatenate([[f if np.isfinite(f) else np.inf], z])[None, :]
+    parts = all_gather_rows(row, z.size + 1, [1] * world)
+    table = np.concatenate(parts, axis=0)
+    win = int(np.argmin(table[:, 0]))
+    return float(table[win, 0]), table[win, 1:].copy()
+
+
+def fit_multistart(params, x, y):
+    """`Fit::fit` (gp/src/algorithm.rs:791-979) with the n_start + 1 optimiser chains sharded over the ranks: chain c runs on
+    rank c % world against that rank's replica of the training set, one all-gather of (objective, theta) -- 8 (h + 1) bytes
+    per rank -- replaces the rayon `reduce` (:942-945), and EVERY rank finalises at the winning theta, so each holds the
+    complete trained model (needed for point-sharded prediction)."""
+    dist = _dist()
+    if dist is None:
+        return params.fit(x, y)
+    return params.chain_shard(dist.get_rank(), dist.get_world_size(), argmin_exchange).fit(x, y)
+
+
+def predict_sharded(predict_fn, x, width=1):
+    """Point-sharded prediction: rank r evaluates `predict_fn` (e.g. gp.predict_var) on the contiguous slice r of the rows
+    of x; one all-gather returns the full result on every rank."""
+    x = np.asarray(x, dtype=np.float64)
+    dist = _dist()
+    if dist is None:
+        return np.asarray(predict_fn(x))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    m = x.shape[0]
+    bounds = [(m * r) // world for r in range(world + 1)]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    local = np.asarray(predict_fn(x[lo:hi]), dtype=np.float64).reshape(hi - lo, width) if hi > lo else np.zeros((0, width))
+    parts = all_gather_rows(local, width, [bounds[r + 1] - bounds[r] for r in range(world)])
+    out = np.concatenate(parts, axis=0)
+    return out[:, 0] if width == 1 else out
+
+
 class HostComm:
     """The exchange of the sharded path without torch: `egx_comm_*` of the C ABI (csrc/host_comm.cpp), a TCP star on
     addr:port (rank 0 listens).  What a Rust / C caller of the library uses; the functions above do the same exchange over a

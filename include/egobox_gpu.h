@@ -162,6 +162,9 @@ int egx_gp_sample(egx_gp_ctx* ctx, const double* x, int m, const double* z, int 
  * egx_gp_eval_end waits for it and returns the status / value of egx_gp_reduced_likelihood.  Different slots may be
  * driven from different threads concurrently (one rayon worker per slot); one slot, one caller at a time. */
 int egx_gp_async_slots(egx_gp_ctx* ctx, int wanted);
+/* Returns the extra workspaces created by egx_gp_reduced_likelihood_batch / egx_gp_async_slots to the block cache (they
+ * are re-created on demand).  egx_gp_fit calls it once the optimum is found, so a trained model holds ONE workspace. */
+int egx_gp_release_workspaces(egx_gp_ctx* ctx);
 int egx_gp_eval_begin(egx_gp_ctx* ctx, int slot, const double* theta);
 int egx_gp_eval_end(egx_gp_ctx* ctx, int slot, double* rlf);
 
@@ -233,6 +236,13 @@ int egx_gp_set_force_blocked(egx_gp_ctx* ctx, int enabled);
  * max_eval 1000, nugget 100*eps, constant mean, squared exponential). */
 #define EGX_OPT_COBYLA 0
 #define EGX_OPT_LBFGSB 1
+/* Exchange step of a multistart fit whose chains are sharded over several processes / GPUs: called ONCE, after the
+ * local chains have finished, with the best objective (-likelihood) and its log10 theta (n values) of this process; must
+ * overwrite both with those of the process holding the smallest objective (the `reduce` by min of
+ * gp/src/algorithm.rs:942-945 across ranks: an NCCL / gloo all-gather in egobox_b200/parallel.py, egx_argmin_allreduce for
+ * C callers) and return 0. */
+typedef int (*egx_exchange_fn)(double* f_best, double* z_best, int n, void* user);
+
 typedef struct egx_gp_params {
     int corr;                    /* EGX_CORR_*  */
     int mean;                    /* EGX_MEAN_*  */
@@ -256,6 +266,10 @@ typedef struct egx_gp_params {
     int optimizer;               /* EGX_OPT_COBYLA (default, the reference's optimiser) or EGX_OPT_LBFGSB: projected L-BFGS
                                     per start on the closed-form theta gradient (egx_gp_reduced_likelihood_grad_analytic),
                                     same starts, same evaluation budget -- not in the reference, opt-in */
+    int chain_rank;              /* multi-GPU multistart: this process runs the chains c with c % chain_world == chain_rank */
+    int chain_world;             /* (0 or 1: all chains here) ... */
+    egx_exchange_fn exchange;    /* ... and `exchange` makes the best (objective, theta) of all processes known to each */
+    void* exchange_user;
 } egx_gp_params;
 
 typedef struct egx_gp_model egx_gp_model;

@@ -58,7 +58,14 @@ def _worker(rank, world, port, q):
     def fit_one(e):
         return ("model%d" % e, 10.0 * e + 1.0, 0.5 * e, [e, e + 0.5, e + 0.25])
     models, table = P.fit_experts(fit_one, 5, 3)
-    q.put((rank, status.tolist(), rlf.tolist(), best, sum(calls), sorted(models), table.tolist()))
+    # the reduce by min of the sharded multistart and the point-sharded prediction
+    f_loc = [3.5, 1.25][rank] if world == 2 else 3.5
+    fwin, zwin = P.argmin_exchange(f_loc, np.array([10.0 * rank + 1.0, 10.0 * rank + 2.0]))
+    finf, zinf = P.argmin_exchange(float("inf") if rank == 0 else float("nan"), np.array([float(rank)]))
+    xs = np.arange(22.0).reshape(11, 2)
+    pred = P.predict_sharded(lambda a: a[:, 0] * 2.0 + a[:, 1], xs)
+    q.put((rank, status.tolist(), rlf.tolist(), best, sum(calls), sorted(models), table.tolist(),
+           (fwin, zwin.tolist(), finf, zinf.tolist(), pred.tolist())))
     dist.destroy_process_group()
 
 
@@ -77,7 +84,12 @@ def test_theta_sweep_and_experts_world2():
     res = sorted(q.get(timeout=150) for _ in range(2))
     for p in procs:
         p.join(30)
-    for rank, status, rlf, best, ncalls, models, table in res:
+    for rank, status, rlf, best, ncalls, models, table, extra in res:
+        fwin, zwin, finf, zinf, pred = extra
+        assert fwin == 1.25 and zwin == [11.0, 12.0]             # rank 1 holds the smaller objective
+        assert finf == float("inf") and zinf == [0.0]            # nobody succeeded: +inf, lowest rank
+        xs = np.arange(22.0).reshape(11, 2)
+        np.testing.assert_array_equal(np.array(pred), xs[:, 0] * 2.0 + xs[:, 1])
         assert status == st1.tolist()
         np.testing.assert_allclose(np.array(rlf), rlf1, rtol=0, atol=0, equal_nan=True)
         assert best == best1
