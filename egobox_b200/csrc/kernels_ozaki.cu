@@ -1461,8 +1461,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiA
                 for (int q = 0; q < 4; ++q) {
                     const int rh = q >> 1, h = q & 1;
                     const int er = hiA[rh][h] + OZ5_ECONST;
-                    // the previous piece of this warp pair has been read by the TMA (the issuing thread waited) before anybody writes
-                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+                    // convert first (registers only): this overlaps the TMA's read of the previous piece of this warp pair
+                    double2 se[4], so[4];
 #pragma unroll
                     for (int jp = 0; jp < 4; ++jp) {
                         double2 c0, c1;                                               // columns 8 (2 jp).. / 8 (2 jp + 1).. of this thread's row
@@ -1472,20 +1472,25 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiA
                         c1.y = oz5_scaled(T[rh][h][2 * jp + 1][1], er + hiB[2 * jp + 1][1]);
                         const double2 mine = odd ? c1 : c0;
                         const double2 back = oz_shfl_xor4(odd ? c0 : c1);
-                        *reinterpret_cast<double2*>(st_e + 16 * jp) = odd ? back : mine;      // 128 B of the even row per quad pair
-                        *reinterpret_cast<double2*>(st_o + 16 * jp) = odd ? mine : back;      // 128 B of the odd row
+                        se[jp] = odd ? back : mine;                                   // 128 B of the even row per quad pair
+                        so[jp] = odd ? mine : back;                                   // 128 B of the odd row
+                    }
+                    // the previous piece has been read by the TMA before anybody overwrites the buffer
+                    if (chalf == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {
+                        *reinterpret_cast<double2*>(st_e + 16 * jp) = se[jp];
+                        *reinterpret_cast<double2*>(st_o + 16 * jp) = so[jp];
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
-                    if (chalf == 0 && lane == 0) {
-                        if (!(xp & 16)) {
-                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                                             reinterpret_cast<uint64_t>(&cmap)),
-                                         "r"(oz_smem_u32(stg)), "r"(tc * 128), "r"(tr * 128 + 32 * quarter + 16 * rh + 8 * h)
-                                         : "memory");
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        }
+                    if (chalf == 0 && lane == 0 && !(xp & 16)) {
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&cmap)),
+                                     "r"(oz_smem_u32(stg)), "r"(tc * 128), "r"(tr * 128 + 32 * quarter + 16 * rh + 8 * h)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
             }

@@ -13,9 +13,9 @@ _LIB = None
 def _lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "liboracle.so")
+        from . import build_oracle
+        path = build_oracle.OUT
         if not os.path.exists(path):
-            from . import build_oracle
             build_oracle.build()
         lib = C.CDLL(path)
         dp = C.POINTER(C.c_double)

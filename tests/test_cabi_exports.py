@@ -43,6 +43,29 @@ def test_product_package_does_not_import_oracle():
                 assert "import oracle" not in src and "from oracle" not in src, f
 
 
+@pytest.mark.gpu
+def test_c99_example_fits_and_predicts_on_the_device(tmp_path):
+    """examples/kriging.c (the reference's crates/gp/examples/kriging.rs through the C ABI) built with plain gcc and RUN on the
+    GPU: fit + predict + predict_var from a C99 caller, no Python in the process."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    inc, libdir = os.path.join(ROOT, "include"), os.path.join(ROOT, "egobox_b200")
+    exe = str(tmp_path / "kriging_c")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + inc,
+                    os.path.join(ROOT, "examples", "kriging.c"), "-L" + libdir, "-legobox_gpu",
+                    "-Wl,-rpath," + libdir, "-lm", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "likelihood" in r.stdout
+    # the example prints theta / likelihood of the 5-point kriging case of python/egobox/tests/test_gpmix.py:37-53
+    import re
+    m = re.search(r"likelihood\s*=?\s*([-+0-9.eE]+)", r.stdout)
+    assert m is not None and abs(float(m.group(1)) - 0.578174) < 5e-3, r.stdout
+
+
 def test_header_is_plain_c99_and_the_c_example_links(tmp_path):
     """The boundary is a C ABI: include/egobox_gpu.h must compile as C99 (what cgo / bindgen / a JNI stub read), and
     examples/kriging.c -- the reference's crates/gp/examples/kriging.rs through the C ABI -- must link against the shared

@@ -214,13 +214,39 @@ def test_ill_conditioned_ft_status():
     y = np.sin(3 * t)
     ctx, _ = make_context(x, y, O.SQEXP, O.QUADRATIC)
     st, _ = ctx.reduced_likelihood([1.0, 1.0])
-    assert st in (2, 3)
+    # algorithm.rs:1012-1026: cond(G) < 1e-10, then cond(F) = 8e16 > 1e15 -> "F is too ill conditioned" (EGX_ILL_CONDITIONED_F = 3),
+    # not the "ft" branch (2): the two normalised input columns coincide, so F itself has exactly dependent columns
+    assert st == 3
     from oracle.gp_oracle import LikelihoodComputationError
     xn, _, _ = O.normalize(x)
     yn, _, ys = O.normalize(y.reshape(-1, 1))
-    with pytest.raises(LikelihoodComputationError):
+    with pytest.raises(LikelihoodComputationError, match="F is too ill conditioned"):
         O.reduced_likelihood(O.SQEXP, xn, O.mean_value(O.QUADRATIC, xn), yn, float(ys[0]), [1.0, 1.0], np.eye(2))
     ctx.close()
+
+
+def test_ill_conditioned_ft_branch_status():
+    """The OTHER branch of algorithm.rs:1012-1026: F is fine (cond ~ 1e1) but R is numerically singular along the trend, so
+    Ft = L^-1 F loses rank -> "ft is too ill conditioned" (EGX_ILL_CONDITIONED_FT = 2).  Whatever the oracle decides on this
+    input is what the device path must return."""
+    from oracle.gp_oracle import LikelihoodComputationError
+    rng = np.random.default_rng(5)
+    x = rng.random((60, 2))
+    y = np.sin(3 * x[:, 0]) + x[:, 1]
+    for theta in ([1e-7, 1e-7], [1e-5, 1e-5], [1e-4, 1e-4]):
+        xn, _, _ = O.normalize(x)
+        yn, _, ys = O.normalize(y.reshape(-1, 1))
+        want = 0
+        try:
+            O.reduced_likelihood(O.SQEXP, xn, O.mean_value(O.LINEAR, xn), yn, float(ys[0]), theta, np.eye(2))
+        except LikelihoodComputationError as e:
+            want = 3 if "F is" in str(e) else 2
+        except np.linalg.LinAlgError:
+            want = 1
+        ctx, _ = make_context(x, y, O.SQEXP, O.LINEAR)
+        st, _ = ctx.reduced_likelihood(theta)
+        ctx.close()
+        assert st == want, (theta, st, want)
 
 
 # ------------------------------------------- accuracy against exact arithmetic -----------
