@@ -1185,65 +1185,102 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk4_kernel(const OzakiA
 // scaling is folded into the int -> double conversion: bits(1.5 * 2^(52+E)) + T is the double 1.5 * 2^(52+E) + T 2^E
 // EXACTLY (|T| < 2^51), so one integer add and one DADD replace convert + DMUL.
 // =================================================================================================================
-constexpr int OZ5_STAGES = 3;
-constexpr int OZ5_HALF = OZ_SLICES * OZ_SLICE_STEP_BYTES;                // 28 KB: one operand
-constexpr int OZ5_STAGE_BYTES = 2 * OZ5_HALF;                            // 56 KB
+constexpr int OZ5_NB = 8;                                                // full / empty barrier pairs: block n uses pair n % OZ5_NB
+constexpr int OZ5_RING_BYTES = 192 * 1024;                               // byte-granular ring of operand blocks
 constexpr int OZ5_GROUPS = 4;
 constexpr int OZ5_PIECE_ROWS = 8;                                        // C leaves in pieces of 8 rows x 128 columns (8 KB) ...
 constexpr int OZ5_PIECE_BYTES = OZ5_PIECE_ROWS * 128 * 8;                // ... one staging buffer per lane quarter (warp pair)
 constexpr int OZ5_STAGING_BYTES = 4 * OZ5_PIECE_BYTES;                   // 32 KB
 
 struct __align__(8) Oz5Barriers {
-    uint64_t full[OZ5_STAGES], empty[OZ5_STAGES], acc_full[2], acc_empty[2];
+    uint64_t full[OZ5_NB], empty[OZ5_NB], acc_full[2], acc_empty[2];
     uint32_t tmem_base, pad_;
 };
-constexpr int OZ5_SMEM_BYTES = OZ5_STAGES * OZ5_STAGE_BYTES + OZ5_STAGING_BYTES + static_cast<int>(sizeof(Oz5Barriers));
+constexpr int OZ5_SMEM_BYTES = OZ5_RING_BYTES + OZ5_STAGING_BYTES + static_cast<int>(sizeof(Oz5Barriers));
 static_assert(OZ5_SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 
-// group g: weights W0 .. W0 + NW - 1, digits 0 .. D - 1 of both operands, KPS K steps per ring stage
+// group g: weights W0 .. W0 + NW - 1, digits 0 .. D - 1 of both operands, KPS K steps per ring block.
+// A block = [A part | B part], each KPS x D x 4 KB; blocks per tile: 8 x 56 KB, 4 x 80 KB, 4 x 48 KB, 56 KB + 8 KB = 18 blocks, 1 MB.
 template <int G> struct Oz5Group;
 template <> struct Oz5Group<0> { static constexpr int W0 = 5, NW = 2, D = 7, KPS = 1; };
-template <> struct Oz5Group<1> { static constexpr int W0 = 3, NW = 2, D = 5, KPS = 1; };
+template <> struct Oz5Group<1> { static constexpr int W0 = 3, NW = 2, D = 5, KPS = 2; };
 template <> struct Oz5Group<2> { static constexpr int W0 = 1, NW = 2, D = 3, KPS = 2; };
 template <> struct Oz5Group<3> { static constexpr int W0 = 0, NW = 1, D = 1, KPS = 7; };
+constexpr int OZ5_BLOCKS_PER_TILE = 18;
+__device__ __forceinline__ uint32_t oz5_block_bytes(uint32_t n) {        // size of block n of the (tile-periodic) sequence
+    const uint32_t i = n % OZ5_BLOCKS_PER_TILE;
+    return (i < 8 ? 56u : i < 12 ? 80u : i < 16 ? 48u : i == 16 ? 56u : 8u) * 1024u;
+}
+// The ring allocator: blocks are laid one after the other, a block that would cross the end starts at 0 again.  Producers and
+// the issuer replay the same deterministic sequence.
+struct Oz5Ring {
+    uint32_t head = 0;
+    __device__ __forceinline__ uint32_t place(uint32_t size) const { return head + size > OZ5_RING_BYTES ? 0u : head; }
+    __device__ __forceinline__ uint32_t alloc(uint32_t size) {
+        const uint32_t o = place(size);
+        head = o + size;
+        return o;
+    }
+};
+// producer side: blocks tail_n .. n - 1 are live (filled or being filled, not yet released by the MMAs that read them); before
+// block n is written every live block it overlaps -- always the oldest ones -- must have been released, and at most OZ5_NB - 1
+// blocks may be live (block n reuses the barrier pair of block n - OZ5_NB)
+struct Oz5Producer {
+    Oz5Ring ring, tail_ring;
+    uint32_t n = 0, tail_n = 0;
+    __device__ __forceinline__ uint32_t acquire(Oz5Barriers* bars, uint32_t size) {
+        const uint32_t off = ring.alloc(size);
+        while (tail_n < n) {
+            const uint32_t ts = oz5_block_bytes(tail_n), to = tail_ring.place(ts);
+            const bool overlap = off < to + ts && to < off + size;
+            if (!overlap && n - tail_n < OZ5_NB) break;
+            oz_mbar_wait(&bars->empty[tail_n % OZ5_NB], (tail_n / OZ5_NB) & 1);
+            tail_ring.alloc(ts);
+            ++tail_n;
+        }
+        return off;
+    }
+};
 
-// producer of ONE operand: all stage uses of group G of the current tile
+// producer of ONE operand: all blocks of group G of the current tile
 template <int G>
-__device__ __forceinline__ void oz5_produce(unsigned char* smem, Oz5Barriers* bars, const int8_t* Sg, int operand, uint32_t& n,
+__device__ __forceinline__ void oz5_produce(unsigned char* smem, Oz5Barriers* bars, const int8_t* Sg, int operand, Oz5Producer& pr,
                                             int tiny) {
     using Gp = Oz5Group<G>;
 #pragma unroll 1
-    for (int ks0 = 0; ks0 < OZ_KSTEPS; ks0 += Gp::KPS, ++n) {
+    for (int ks0 = 0; ks0 < OZ_KSTEPS; ks0 += Gp::KPS) {
         const int nk = (OZ_KSTEPS - ks0) < Gp::KPS ? (OZ_KSTEPS - ks0) : Gp::KPS;
-        const uint32_t stage = n % OZ5_STAGES, round = n / OZ5_STAGES;
+        const uint32_t part = static_cast<uint32_t>(nk) * (Gp::D * OZ_SLICE_STEP_BYTES);      // one operand
+        const uint32_t off = pr.acquire(bars, 2 * part);
+        const uint32_t b = pr.n % OZ5_NB;
         uint32_t bytes = Gp::D * OZ_SLICE_STEP_BYTES;
         if (tiny) bytes = 1024;
-        unsigned char* dst = smem + stage * OZ5_STAGE_BYTES + operand * OZ5_HALF;
-        oz_mbar_wait(&bars->empty[stage], (round & 1) ^ 1);
-        oz_mbar_expect_tx(&bars->full[stage], static_cast<uint32_t>(nk) * bytes);
+        unsigned char* dst = smem + off + operand * part;
+        oz_mbar_expect_tx(&bars->full[b], static_cast<uint32_t>(nk) * bytes);
         for (int j = 0; j < nk; ++j)
             oz_bulk_g2s(dst + j * (Gp::D * OZ_SLICE_STEP_BYTES), Sg + static_cast<long>(ks0 + j) * OZ_STAGE_OPERAND, bytes,
-                        &bars->full[stage]);
+                        &bars->full[b]);
+        ++pr.n;
     }
 }
 
 // MMA issue of group G of the current tile into the accumulator buffer at tmem_buf
 template <int G>
-__device__ __forceinline__ void oz5_issue(unsigned char* smem, Oz5Barriers* bars, uint32_t tmem_buf, uint32_t& n, int half) {
+__device__ __forceinline__ void oz5_issue(unsigned char* smem, Oz5Barriers* bars, uint32_t tmem_buf, Oz5Ring& ring, uint32_t& n, int half) {
     using Gp = Oz5Group<G>;
 #pragma unroll 1
     for (int ks0 = 0; ks0 < OZ_KSTEPS; ks0 += Gp::KPS, ++n) {
         const int nk = (OZ_KSTEPS - ks0) < Gp::KPS ? (OZ_KSTEPS - ks0) : Gp::KPS;
-        const uint32_t stage = n % OZ5_STAGES, round = n / OZ5_STAGES;
-        const uint32_t sa = oz_smem_u32(smem + stage * OZ5_STAGE_BYTES);
-        oz_mbar_wait(&bars->full[stage], round & 1);
+        const uint32_t part = static_cast<uint32_t>(nk) * (Gp::D * OZ_SLICE_STEP_BYTES);
+        const uint32_t sa = oz_smem_u32(smem + ring.alloc(2 * part));
+        oz_mbar_wait(&bars->full[n % OZ5_NB], (n / OZ5_NB) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
         for (int j = 0; j < nk; ++j) {
             const uint32_t a = sa + j * (Gp::D * OZ_SLICE_STEP_BYTES);
-            oz_issue_kstep<Gp::W0, Gp::NW, OZ_SLICE_STEP_BYTES, false>(tmem_buf, a, a + OZ5_HALF, (ks0 + j) > 0 ? 1u : 0u, half);
+            oz_issue_kstep<Gp::W0, Gp::NW, OZ_SLICE_STEP_BYTES, false>(tmem_buf, a, a + part, (ks0 + j) > 0 ? 1u : 0u, half);
         }
-        oz_umma_commit(&bars->empty[stage]);
+        oz_umma_commit(&bars->empty[n % OZ5_NB]);
     }
 }
 
@@ -1326,14 +1363,14 @@ __device__ __forceinline__ double oz5_scaled(long long t, int eshift) {
 
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiArgs g, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
-    unsigned char* staging = oz_smem + OZ5_STAGES * OZ5_STAGE_BYTES;
+    unsigned char* staging = oz_smem + OZ5_RING_BYTES;
     Oz5Barriers* bars = reinterpret_cast<Oz5Barriers*>(staging + OZ5_STAGING_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = g.tri > 0 ? g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri : g.Mt * g.Nt;
     if (tid == 0) OZ_STAMP(0);
 
     if (tid == 0) {
-        for (int s = 0; s < OZ5_STAGES; ++s) {
+        for (int s = 0; s < OZ5_NB; ++s) {
             oz_mbar_init(&bars->full[s], 2);
             oz_mbar_init(&bars->empty[s], 1);
         }
@@ -1364,39 +1401,40 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiA
         if ((warp == 0 || warp == 2) && lane == 0) {
             // ===== producers: warp 0 = the A halves of the stages, warp 2 = the B halves =====
             const int operand = warp >> 1;
-            uint32_t n = 0;
+            Oz5Producer pr;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 int tr, tc;
                 oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
                 const int8_t* Sg = operand ? g.SB + static_cast<long>(tc) * OZ_RB_BYTES : g.S + static_cast<long>(tr) * OZ_RB_BYTES;
-                oz5_produce<0>(oz_smem, bars, Sg, operand, n, xp & 4);
-                oz5_produce<1>(oz_smem, bars, Sg, operand, n, xp & 4);
-                oz5_produce<2>(oz_smem, bars, Sg, operand, n, xp & 4);
-                oz5_produce<3>(oz_smem, bars, Sg, operand, n, xp & 4);
+                oz5_produce<0>(oz_smem, bars, Sg, operand, pr, xp & 4);
+                oz5_produce<1>(oz_smem, bars, Sg, operand, pr, xp & 4);
+                oz5_produce<2>(oz_smem, bars, Sg, operand, pr, xp & 4);
+                oz5_produce<3>(oz_smem, bars, Sg, operand, pr, xp & 4);
             }
         } else if (warp == 1 && lane == 0) {
             // ===== MMA issuer: groups 0, 2 -> buffer X, groups 1, 3 -> buffer Y; use u of a buffer waits for the drain of use u - 1 =====
-            uint32_t n = 0, u = 0;                            // stage uses; uses of EACH buffer so far (both advance together)
+            Oz5Ring ring;
+            uint32_t n = 0, u = 0;                            // blocks; uses of EACH buffer so far (both advance together)
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const bool t1 = tile == static_cast<int>(blockIdx.x + gridDim.x);
                 if (u > 0) { oz_mbar_wait(&bars->acc_empty[0], (u - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
                 if (t1) OZ_STAMP(20);
-                oz5_issue<0>(oz_smem, bars, tmem, n, xp & 1);
+                oz5_issue<0>(oz_smem, bars, tmem, ring, n, xp & 1);
                 oz_umma_commit(&bars->acc_full[0]);
                 if (u > 0) { oz_mbar_wait(&bars->acc_empty[1], (u - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
                 if (t1) OZ_STAMP(21);
-                oz5_issue<1>(oz_smem, bars, tmem + 256, n, xp & 1);
+                oz5_issue<1>(oz_smem, bars, tmem + 256, ring, n, xp & 1);
                 oz_umma_commit(&bars->acc_full[1]);
                 ++u;
                 oz_mbar_wait(&bars->acc_empty[0], (u - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (t1) OZ_STAMP(22);
-                oz5_issue<2>(oz_smem, bars, tmem, n, xp & 1);
+                oz5_issue<2>(oz_smem, bars, tmem, ring, n, xp & 1);
                 oz_umma_commit(&bars->acc_full[0]);
                 oz_mbar_wait(&bars->acc_empty[1], (u - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (t1) OZ_STAMP(23);
-                oz5_issue<3>(oz_smem, bars, tmem + 256, n, xp & 1);
+                oz5_issue<3>(oz_smem, bars, tmem + 256, ring, n, xp & 1);
                 oz_umma_commit(&bars->acc_full[1]);
                 ++u;
                 if (t1) OZ_STAMP(24);
@@ -1579,7 +1617,10 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
     // point: other evaluations fill the gaps; 4.39 -> 4.05 ms per evaluation at n = 8192) and not for a single one
     // (6.9 vs 7.7 ms).  EGX_OZAKI_PERSIST=0/1 overrides.
     static const int persist_env = getenv("EGX_OZAKI_PERSIST") != nullptr ? atoi(getenv("EGX_OZAKI_PERSIST")) : -1;
-    const int persist = persist_env >= 0 ? persist_env : persist_hint;
+    // v5 overlaps the drain / C update of a tile with the MMAs of the next, so a resident grid is 30 % faster than one tile per
+    // CTA (0.170 vs 0.241 ms on 1830 tiles) and -- unlike the r01 kernel -- costs a single evaluation with look-ahead nothing
+    // (6.78 ms either way, profiles/r02/x6_*): always persistent
+    const int persist = persist_env >= 0 ? persist_env : (version == 5 ? 1 : persist_hint);
     static const int two_cta = getenv("EGX_OZAKI_2CTA") != nullptr ? atoi(getenv("EGX_OZAKI_2CTA")) : 0;
     if (two_cta && tri > 0) {
         int nwork = 0;
@@ -1590,9 +1631,13 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
     }
     // persistent grid: as few CTAs as finish in the same number of tile rounds (230 tiles: 115 CTAs x 2 rounds instead of
     // 148 CTAs of which 66 idle through the second round) -- the SMs left over go to the other evaluations in flight
+    // EGX_OZAKI_MAXCTAS caps the resident grid: with several evaluations in flight the SMs left over run the panel / solve /
+    // correlation kernels of the OTHER evaluations instead of queueing behind this launch
+    static const int max_ctas = getenv("EGX_OZAKI_MAXCTAS") != nullptr ? atoi(getenv("EGX_OZAKI_MAXCTAS")) : 0;
+    const int avail = (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;
     int grid = tiles;
-    if (persist && tiles > sms) {
-        const int rounds = (tiles + sms - 1) / sms;
+    if (persist && tiles > avail) {
+        const int rounds = (tiles + avail - 1) / avail;
         grid = (tiles + rounds - 1) / rounds;
     }
     if (version == 5 && have_map) ozaki_syrk5_kernel<<<grid, OZ_THREADS, OZ5_SMEM_BYTES, s>>>(g, cmap);

@@ -227,12 +227,15 @@ class Gpx:
         }
 
     def save(self, filename):
-        """JSON in the reference's GpMixture layout (see to_dict).  bincode (any other extension in the reference,
-        gp_mix.rs:310-320) is not provided."""
-        if not str(filename).endswith(".json"):
-            raise NotImplementedError("bincode persistence is not provided; use a .json filename")
-        with open(filename, "w") as f:
-            json.dump(self.to_dict(), f)
+        """gp_mix.rs:310-320: `.json` -> serde JSON in the reference's GpMixture layout (see to_dict), any other name ->
+        bincode 2 standard configuration of the same structure (egobox_b200/bincode.py)."""
+        if str(filename).endswith(".json"):
+            with open(filename, "w") as f:
+                json.dump(self.to_dict(), f)
+        else:
+            from . import bincode
+            with open(filename, "wb") as f:
+                f.write(bincode.encode_mixture(self.to_dict()))
         return True
 
     @staticmethod
@@ -244,7 +247,9 @@ class Gpx:
         params = (_gp.GaussianProcess.params(mean, corr).theta_tuning(_gp.ThetaTuning.Fixed(_unarr(e["theta"])))
                   .nugget(prm.get("nugget", _gp.DEFAULT_NUGGET)).device(device))
         w = _unarr(e["w_star"])
-        if w.shape[1] < w.shape[0]:
+        # KPLS is on when the stored parameters say so (kpls_dim == d is legal: w_star is then a d x d rotation, not the
+        # identity); files without the key fall back to the shape test
+        if prm.get("kpls_dim") is not None or w.shape[1] < w.shape[0]:
             params = params.kpls_dim(w.shape[1], w)
         return params.fit(x, y)
 
@@ -252,8 +257,13 @@ class Gpx:
     def load(filename, device=0):
         """Rebuild the device-resident mixture from a file written by save() or by stock egobox (JSON): every expert
         by one final evaluation at its stored theta (Fixed tuning), the Gaussian mixture from the `gmx` block."""
-        with open(filename) as f:
-            obj = json.load(f)
+        if str(filename).endswith(".json"):
+            with open(filename) as f:
+                obj = json.load(f)
+        else:
+            from . import bincode
+            with open(filename, "rb") as f:
+                obj = bincode.decode_mixture(f.read())
         experts_json = obj["experts"] if "experts" in obj else [obj]
         experts = [Gpx._load_expert(e, device) for e in experts_json]
         first = experts_json[0]

@@ -136,8 +136,15 @@ def test_gpx_save_load_reference_expert_layout(tmp_path, golden_dir):
     # a stock egobox expert block loads too (the golden fixture IS one)
     gpx3 = egx.Gpx.load(os.path.join(golden_dir, "gpx_tutorial_linear_matern52.json"))
     np.testing.assert_allclose(gpx3.predict(xq), gpx.predict(xq), rtol=1e-10, atol=1e-10)
-    with pytest.raises(NotImplementedError):
-        gpx.save(str(tmp_path / "gpdump.bin"))
+    # any other file name -> bincode 2 (python/src/gp_mix.rs:310-337; test_gpmix.py:55-82 round-trips "gpdump.bin")
+    fb = str(tmp_path / "gpdump.bin")
+    assert gpx.save(fb)
+    from egobox_b200 import bincode
+    assert bincode.decode_mixture(open(fb, "rb").read()) == json.load(open(fn))       # the same structure, bit for bit
+    gpx4 = egx.Gpx.load(fb)
+    np.testing.assert_allclose(gpx4.predict(xq), gpx.predict(xq), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(gpx4.predict_var(xq), gpx.predict_var(xq), rtol=1e-9, atol=1e-9)
+    assert gpx4.predict(np.array([[-3.0]])).item() == pytest.approx(float(yt[list(xt[:, 0]).index(-3.0)]), abs=1e-9)   # interpolates
 
 
 def test_model_sampling_api():

@@ -147,6 +147,12 @@ def test_moe_smooth_three_clusters_and_heaviside_search(tmp_path):
     xq = np.array([[0.6], [0.1], [0.95]])
     np.testing.assert_allclose(again.predict(xq), gpx.predict(xq), atol=1e-6)
     np.testing.assert_allclose(again.predict_var(xq), gpx.predict_var(xq), atol=1e-6)
+    # the binary format of the same three-expert mixture (moe/src/algorithm.rs:1361-1380 saves with GpFileFormat::Binary too)
+    fb = str(tmp_path / "saved_moe.bin")
+    assert gpx.save(fb)
+    again_b = egx.Gpx.load(fb)
+    np.testing.assert_allclose(again_b.predict(xq), gpx.predict(xq), atol=1e-6)
+    np.testing.assert_allclose(again_b.predict_var(xq), gpx.predict_var(xq), atol=1e-6)
 
 
 def test_smooth_equals_hard_for_one_cluster():
