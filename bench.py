@@ -182,12 +182,12 @@ def cpu_sample(n, d, m, evals, sample_pts=2048, sample_evals=4):
             "full_step_s_scaled_from_sample": t_fit + t_pred}
 
 
-def cpu_sample_clean_env(n, d, m, evals):
+def cpu_sample_clean_env(n, d, m, evals, flag="--cpu-sample-only"):
     """Run cpu_sample in a child process whose environment does not pin the thread pools to one thread
     (torchrun exports OMP_NUM_THREADS=1 and OpenBLAS sizes its pool from it at load time)."""
     env = {k: v for k, v in os.environ.items()
            if k not in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "GOTO_NUM_THREADS")}
-    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-sample-only", "--ntrain", str(n), "--dim", str(d),
+    cmd = [sys.executable, os.path.abspath(__file__), flag, "--ntrain", str(n), "--dim", str(d),
            "--npred", str(m), "--evals", str(evals)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True)
     for line in reversed(r.stdout.strip().splitlines()):
@@ -425,6 +425,8 @@ def run_ours(args):
     # ---------------- the other multi-GPU configurations of BASELINE.json ----------------------------
     extra = {}
     if not args.no_extra:
+        if world == 1:
+            extra["c3_sparse_gp"] = leg_c3(args, eg)
         extra["c5_theta_sweep"] = leg_c5(args, eg, P, torch, dist, local_rank, world, barrier)
         extra["c4_moe_experts"] = leg_c4(args, eg, P, torch, dist, local_rank, rank, world, barrier)
 
@@ -541,9 +543,75 @@ def run_ours(args):
         out.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_sample_clean_env(n, d, m, E)
+            if "c3_sparse_gp" in out:
+                try:
+                    out["c3_sparse_gp"]["cpu_baseline"] = cpu_sample_clean_env(n, d, m, E, flag="--cpu-c3-only")
+                    out["c3_sparse_gp"]["speedup_vs_cpu_port"] = (out["c3_sparse_gp"]["cpu_baseline"]["ms_per_likelihood_eval_scaled"]
+                                                                  / out["c3_sparse_gp"]["ms_per_likelihood_eval"])
+                except Exception as exc:       # the secondary baseline must not take the headline line down
+                    out["c3_sparse_gp"]["cpu_baseline"] = {"error": str(exc)[:200]}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def c3_inputs(N, d, M):
+    rng = np.random.default_rng(42)
+    x = rng.random((N, d))
+    y = np.sum(np.sin(3 * np.pi * x), axis=1) + rng.normal(0, 0.1, N)
+    z = x[rng.permutation(N)[:M]].copy()
+    return x, y, z
+
+
+def leg_c3(args, eg):
+    """BASELINE configs[2]: sparse GP (FITC), N = 100000, d = 6, M = 1024 inducing points, one GPU: likelihood evaluations
+    (what the fit driver repeats) and predict_var on 100000 points, through the device seam egx_sgp_*."""
+    N, d, M = 100000, 6, 1024
+    x, y, z = c3_inputs(N, d, M)
+    ctx = eg.SgpContext(x, y, z, corr=eg.MATERN52, method=eg.SparseMethod.FITC)
+    theta = np.full(d, 1.0)
+    for _ in range(2):
+        ctx.reduced_likelihood(theta, 1.0, 0.01)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        st, lik = ctx.reduced_likelihood(theta, 1.0, 0.01)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    ctx.finalize(theta, 1.0, 0.01)
+    xs = np.random.default_rng(43).random((100000, d))
+    ctx.predict_var(xs[:1024])
+    t0 = time.perf_counter()
+    v = ctx.predict_var(xs)
+    pms = (time.perf_counter() - t0) * 1e3
+    ctx.close()
+    return {"N": N, "d": d, "M": M, "method": "FITC", "status": int(st), "likelihood": float(lik), "ms_per_likelihood_eval": ms,
+            "likelihood_evals_per_s": 1e3 / ms, "algorithmic_flops_2M2N": 2.0 * M * M * N,
+            "tflops_fp64_equivalent": 2.0 * M * M * N / (ms * 1e-3) / 1e12, "predict_var_100k_ms": pms,
+            "predict_var_points_per_s": 1e5 / (pms * 1e-3), "var_mean": float(v.mean())}
+
+
+def cpu_c3_sample(Ns=20000):
+    """The oracle's FITC likelihood (C/OpenMP kernel + LAPACK, all host threads) on the first Ns points of the C3 inputs, the
+    same 1024 inducing points; the cost is linear in N (2 M^2 N flops), so the full evaluation is the sample x N / Ns."""
+    from oracle import fast, gp_oracle as O, sgp_oracle as S
+    cores = len(os.sched_getaffinity(0))
+    fast.set_threads(cores)
+    try:
+        import scipy.linalg  # noqa: F401
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    N, d, M = 100000, 6, 1024
+    x, y, z = c3_inputs(N, d, M)
+    S.USE_FAST_KERNEL = True
+    theta = np.full(d, 1.0)
+    S.reduced_likelihood(S.FITC, O.MATERN52, theta, 1.0, 0.01, np.eye(d), x[:2000], y[:2000], z)       # warm the pools
+    t0 = time.perf_counter()
+    lik, _ = S.reduced_likelihood(S.FITC, O.MATERN52, theta, 1.0, 0.01, np.eye(d), x[:Ns], y[:Ns], z)
+    t = time.perf_counter() - t0
+    return {"kind": "port", "cores": cores, "sample": "FITC likelihood on %d of the %d points (%.2f s), scaled x%.1f" % (Ns, N, t, N / Ns),
+            "sample_wall_s": t, "ms_per_likelihood_eval_scaled": 1e3 * t * N / Ns, "likelihood_of_sample": float(lik)}
 
 
 def leg_c5(args, eg, P, torch, dist, local_rank, world, barrier):
@@ -631,9 +699,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the c5 / c4 legs")
     ap.add_argument("--cpu-sample-only", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-c3-only", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_sample_only:
         print(json.dumps(cpu_sample(args.n, args.d, args.m, args.evals)), flush=True)
+        return
+    if args.cpu_c3_only:
+        print(json.dumps(cpu_c3_sample()), flush=True)
         return
     if args.impl == "reference":
         run_reference(args)

@@ -88,6 +88,8 @@ void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s);
 int gemm_smem_bytes();
 // kernels_ozaki.cu: the trailing SYRK update on tcgen05 (int8-sliced fp64)
 size_t ozaki_slice_bytes(long rows);
+void launch_ozaki_slice_panels(const double* P, long ldp, int rows, int kpanels, double* rscale, int8_t* S, cudaStream_t s);
+bool launch_ozaki_syrk_add_panels(double* C, long ldc, const int8_t* S, const double* rscale, int tri, int kpanels, cudaStream_t s);
 void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int8_t* S, cudaStream_t s,
                         const double* rmaxq = nullptr /* [row][4] from the panel solves: no row-maximum pass */);
 void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscale, int Mt, int tri, cudaStream_t s,

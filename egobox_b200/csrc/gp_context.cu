@@ -622,10 +622,17 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
         return EGX_INVALID_VALUE;
     }
     {
-        // the correlation kernels stage three 64 x d coordinate tiles and the (dimension, component) term list in shared
-        // memory (kernels_corr.cu): refuse shapes that cannot fit instead of failing at the first launch
-        const size_t terms = (corr == EGX_CORR_MATERN32 || corr == EGX_CORR_MATERN52) ? static_cast<size_t>(d) * h : d;
-        const size_t smem = 16 + (3 * static_cast<size_t>(EGX_CT) * d + 2 * EGX_CT) * sizeof(double) + terms * sizeof(CorrTerm);
+        // the correlation kernels stage two raw 64 x d coordinate tiles, two scaled term-major tiles [terms][64] and the
+        // (dimension, component) term list in shared memory (kernels_corr.cu): refuse shapes that cannot fit instead of failing
+        // at the first launch
+        // (Matern: one term per NON-ZERO weight W_jl -- d for the identity, up to d * h with KPLS rotations; the exponential
+        // kernels fold the components of a dimension into one term)
+        size_t terms = d;
+        if (corr == EGX_CORR_MATERN32 || corr == EGX_CORR_MATERN52) {
+            terms = 0;
+            for (long e = 0; e < static_cast<long>(d) * h; ++e) terms += (w_star[e] != 0.0) ? 1 : 0;
+        }
+        const size_t smem = 16 + (2 * static_cast<size_t>(EGX_CT) * (d + terms) + 2 * EGX_CT) * sizeof(double) + terms * sizeof(CorrTerm);
         if (smem > 227 * 1024) {
             egx_set_error("egx_gp_create: d = %d (h = %d) needs %zu bytes of shared memory per CTA in the correlation kernels "
                           "(limit 232448); reduce the input dimension (KPLS does not shrink the coordinate tiles)", d, h, smem);

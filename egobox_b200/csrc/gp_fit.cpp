@@ -797,6 +797,10 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
                         zbest = zopt;
                     }
                 }
+                if (!std::isfinite(fbest) && prm->exchange == nullptr) {
+                    egx_set_error("egx_gp_fit (EGX_OPT_LBFGSB): the likelihood could not be evaluated at any multistart point");
+                    return EGX_NOT_POSITIVE_DEFINITE;
+                }
             } else {
             static const bool lockstep_forced = getenv("EGX_FIT_LOCKSTEP") != nullptr && atoi(getenv("EGX_FIT_LOCKSTEP")) != 0;
             const int slots = lockstep_forced ? 0 : egx_gp_async_slots(m->ctx, static_cast<int>(chains.size()));

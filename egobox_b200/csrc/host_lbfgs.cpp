@@ -47,6 +47,15 @@ extern "C" int egx_bound_lbfgs_minimize(egx_objective_grad_fn fg, void* user, in
         return v;
     };
     double f = eval(x, g);
+    // a start that fails (non positive definite R, ill-conditioned regression: +inf, algorithm.rs:893-896) is not given up at
+    // once: the COBYLA chains treat +inf as an ordinary bad vertex and keep exploring, so a few points on the way to the centre
+    // of the box are tried before this start is abandoned
+    for (int probe = 1; probe <= 4 && !std::isfinite(f) && nfev < maxeval; ++probe) {
+        const double w = 0.25 * probe;
+        for (int i = 0; i < n; ++i) x[i] = (1.0 - w) * x0[i] + w * 0.5 * (lo[i] + hi[i]);
+        for (int i = 0; i < n; ++i) x[i] = std::min(std::max(x[i], lo[i]), hi[i]);
+        f = eval(x, g);
+    }
     std::memcpy(x_opt, x.data(), sizeof(double) * n);
     *f_opt = f;
     std::deque<std::vector<double>> S, Y;

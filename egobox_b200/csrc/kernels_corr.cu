@@ -74,11 +74,55 @@ __device__ __forceinline__ double pair_finish(double acc, double prod) {
     return prod * exp(-2.23606797749979 * acc);
 }
 
-// Each of the 256 threads owns a 4 x 4 patch of the 64 x 64 tile:
-// rows ty + 16*ri, columns 2*tx + 32*cj + {0,1}.
+// Pre-scaled coordinates (r02): every (dimension, component) term t gets its own copy of the coordinate, multiplied by the
+// term's weight -- u_t = c_t x_dim(t), c_t = sqrt(k1) (squared exponential), k1 (absolute exponential), sqrt(3) tw / sqrt(5) tw
+// (Matern) -- so that a = |u_i - u_j| is already the argument of the kernel:
+//   squared exponential  acc += a^2                      (DADD + DFMA instead of DADD + DMUL + DFMA)
+//   Matern-5/2           prod *= 1 + a (1 + a / 3), acc += a   (5 fp64 instructions per pair and term instead of 7)
+// and the square roots 3 / 5 leave pair_finish.  The kernels are bound by fp64 issue, so this is
+// the lever; the results differ from the unscaled form by rounding only (|u| ulps instead of |x| ulps in the difference).
 template <int CORR>
-__device__ __forceinline__ void tile_values(const double* __restrict__ Xi, const double* __restrict__ XjT,
-                                            const CorrTerm* __restrict__ terms, int nterms, int d, int ty,
+__device__ __forceinline__ double term_coef(const CorrTerm& t) {
+    if (CORR == EGX_CORR_SQUARED_EXPONENTIAL) return sqrt(t.k1);
+    if (CORR == EGX_CORR_ABSOLUTE_EXPONENTIAL) return t.k1;
+    return t.k2;
+}
+template <int CORR>
+__device__ __forceinline__ void pair_term_s(double du, double& acc, double& prod) {
+    if (CORR == EGX_CORR_SQUARED_EXPONENTIAL) {
+        acc = fma(du, du, acc);
+    } else if (CORR == EGX_CORR_ABSOLUTE_EXPONENTIAL) {
+        acc += fabs(du);
+    } else if (CORR == EGX_CORR_MATERN32) {
+        const double a = fabs(du);
+        prod *= 1.0 + a;
+        acc += a;
+    } else {
+        const double a = fabs(du);
+        prod *= fma(a, fma(a, 1.0 / 3.0, 1.0), 1.0);
+        acc += a;
+    }
+}
+template <int CORR>
+__device__ __forceinline__ double pair_finish_s(double acc, double prod) {
+    if (CORR == EGX_CORR_SQUARED_EXPONENTIAL) return exp(-0.5 * acc);
+    if (CORR == EGX_CORR_ABSOLUTE_EXPONENTIAL) return exp(-acc);
+    return prod * exp(-acc);
+}
+// scaled, term-major copy of a 64-row coordinate tile: out[t][r] = c_t X[r][dim(t)]
+template <int CORR>
+__device__ __forceinline__ void scale_tile(const double* __restrict__ Xrow, const CorrTerm* __restrict__ terms, int nterms, int d,
+                                           double* __restrict__ out, int tid) {
+    for (int e = tid; e < nterms * EGX_CT; e += 256) {
+        const int t = e / EGX_CT, r = e - t * EGX_CT;
+        out[e] = term_coef<CORR>(terms[t]) * Xrow[r * d + terms[t].dim];
+    }
+}
+
+// Each of the 256 threads owns a 4 x 4 patch of the 64 x 64 tile:
+// rows ty + 16*ri, columns 2*tx + 32*cj + {0,1}.  XiS / XjS: scaled term-major tiles [nterms][64].
+template <int CORR>
+__device__ __forceinline__ void tile_values(const double* __restrict__ XiS, const double* __restrict__ XjS, int nterms, int ty,
                                             int tx, double (&out)[4][4]) {
     double acc[4][4], prod[4][4];
 #pragma unroll
@@ -89,22 +133,21 @@ __device__ __forceinline__ void tile_values(const double* __restrict__ Xi, const
             prod[a][b] = 1.0;
         }
     for (int t = 0; t < nterms; ++t) {
-        const CorrTerm tm = terms[t];
         double xi[4];
 #pragma unroll
-        for (int ri = 0; ri < 4; ++ri) xi[ri] = Xi[(ty + 16 * ri) * d + tm.dim];
-        const double2 xa = *reinterpret_cast<const double2*>(&XjT[tm.dim * EGX_CT + 2 * tx]);
-        const double2 xb = *reinterpret_cast<const double2*>(&XjT[tm.dim * EGX_CT + 2 * tx + 32]);
+        for (int ri = 0; ri < 4; ++ri) xi[ri] = XiS[t * EGX_CT + ty + 16 * ri];
+        const double2 xa = *reinterpret_cast<const double2*>(&XjS[t * EGX_CT + 2 * tx]);
+        const double2 xb = *reinterpret_cast<const double2*>(&XjS[t * EGX_CT + 2 * tx + 32]);
         const double xj[4] = {xa.x, xa.y, xb.x, xb.y};
 #pragma unroll
         for (int ri = 0; ri < 4; ++ri)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) pair_term<CORR>(tm, xi[ri] - xj[c], acc[ri][c], prod[ri][c]);
+            for (int c = 0; c < 4; ++c) pair_term_s<CORR>(xi[ri] - xj[c], acc[ri][c], prod[ri][c]);
     }
 #pragma unroll
     for (int ri = 0; ri < 4; ++ri)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) out[ri][c] = pair_finish<CORR>(acc[ri][c], prod[ri][c]);
+        for (int c = 0; c < 4; ++c) out[ri][c] = pair_finish_s<CORR>(acc[ri][c], prod[ri][c]);
 }
 
 __device__ __forceinline__ void tri_decode(int t, int& r, int& c) {
@@ -127,8 +170,9 @@ __global__ void __launch_bounds__(256)
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* Xi = reinterpret_cast<double*>(smem_raw + 16);
     double* Xj = Xi + EGX_CT * d;
-    double* XjT = Xj + EGX_CT * d;
-    CorrTerm* terms = reinterpret_cast<CorrTerm*>(XjT + EGX_CT * d);
+    double* XiS = Xj + EGX_CT * d;
+    double* XjS = XiS + EGX_CT * nterms;
+    CorrTerm* terms = reinterpret_cast<CorrTerm*>(XjS + EGX_CT * nterms);
 
     const int tid = threadIdx.x;
     const int pair = blockIdx.x >> 2, sub = blockIdx.x & 3;
@@ -149,16 +193,15 @@ __global__ void __launch_bounds__(256)
         bulk_g2s(Xj, X + static_cast<long>(j0) * d, bytes, bar);
     }
     for (int t = tid; t < nterms; t += 256) terms[t] = gterms[t];
+    __syncthreads();                 // the term list is read by every thread below
     mbar_wait(bar, 0);
-    for (int e = tid; e < EGX_CT * d; e += 256) {
-        const int r = e / d, c = e - r * d;
-        XjT[c * EGX_CT + r] = Xj[e];
-    }
+    scale_tile<CORR>(Xi, terms, nterms, d, XiS, tid);
+    scale_tile<CORR>(Xj, terms, nterms, d, XjS, tid);
     __syncthreads();
 
     const int ty = tid >> 4, tx = tid & 15;
     double v[4][4];
-    tile_values<CORR>(Xi, XjT, terms, nterms, d, ty, tx, v);
+    tile_values<CORR>(XiS, XjS, nterms, ty, tx, v);
 
 #pragma unroll
     for (int ri = 0; ri < 4; ++ri) {
@@ -199,8 +242,9 @@ __global__ void __launch_bounds__(256)
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* Xp = reinterpret_cast<double*>(smem_raw + 16);
     double* Xj = Xp + EGX_CT * d;
-    double* XjT = Xj + EGX_CT * d;
-    double* gam = XjT + EGX_CT * d;
+    double* XpS = Xj + EGX_CT * d;
+    double* XjS = XpS + EGX_CT * nterms;
+    double* gam = XjS + EGX_CT * nterms;
     double* ysum = gam + EGX_CT;
     CorrTerm* terms = reinterpret_cast<CorrTerm*>(ysum + EGX_CT);
 
@@ -219,6 +263,7 @@ __global__ void __launch_bounds__(256)
     }
     for (int t = tid; t < nterms; t += 256) terms[t] = gterms[t];
     __syncthreads();
+    scale_tile<CORR>(Xp, terms, nterms, d, XpS, tid);
 
     const int ty = tid >> 4, tx = tid & 15;
     double yacc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -231,14 +276,11 @@ __global__ void __launch_bounds__(256)
         }
         if (tid < EGX_CT) gam[tid] = (gamma != nullptr && j0 + tid < n) ? gamma[j0 + tid] : 0.0;
         mbar_wait(bar, jt & 1);
-        for (int e = tid; e < EGX_CT * d; e += 256) {
-            const int r = e / d, c = e - r * d;
-            XjT[c * EGX_CT + r] = Xj[e];
-        }
+        scale_tile<CORR>(Xj, terms, nterms, d, XjS, tid);
         __syncthreads();
 
         double v[4][4];
-        tile_values<CORR>(Xp, XjT, terms, nterms, d, ty, tx, v);
+        tile_values<CORR>(XpS, XjS, nterms, ty, tx, v);
 #pragma unroll
         for (int ri = 0; ri < 4; ++ri) {
             const int i = i0 + ty + 16 * ri;
@@ -253,7 +295,7 @@ __global__ void __launch_bounds__(256)
                     *reinterpret_cast<double2*>(&Y[static_cast<long>(i) * ldy + j0 + jl]) = make_double2(a, b);
             }
         }
-        __syncthreads();   // Xj / XjT / gam are overwritten by the next tile
+        __syncthreads();   // Xj / XjS / gam are overwritten by the next tile
     }
 
     if (yout != nullptr) {
@@ -396,9 +438,12 @@ __global__ void mean_basis_rows_kernel(const double* __restrict__ X, int n, int 
     FyT[static_cast<long>(p) * ld + j] = (j < n) ? ynorm[j] : 0.0;
 }
 
-size_t corr_build_smem(int d, int nterms) { return 16 + 3 * EGX_CT * d * sizeof(double) + nterms * sizeof(CorrTerm); }
+// two raw 64 x d tiles (TMA destinations) + two scaled term-major tiles [nterms][64] + the term list
+size_t corr_build_smem(int d, int nterms) {
+    return 16 + 2 * EGX_CT * (static_cast<size_t>(d) + nterms) * sizeof(double) + nterms * sizeof(CorrTerm);
+}
 size_t cross_corr_smem(int d, int nterms) {
-    return 16 + 3 * EGX_CT * d * sizeof(double) + 2 * EGX_CT * sizeof(double) + nterms * sizeof(CorrTerm);
+    return 16 + 2 * EGX_CT * (static_cast<size_t>(d) + nterms) * sizeof(double) + 2 * EGX_CT * sizeof(double) + nterms * sizeof(CorrTerm);
 }
 
 template <typename K>

@@ -148,6 +148,8 @@ __global__ void __launch_bounds__(256) ozaki_rowscale_kernel(const double* __res
                                                              double* __restrict__ rscale) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
+    P += static_cast<long>(blockIdx.z) * OZ_K;                      // K panel blockIdx.z: columns 256 z .. of the same rows
+    rscale += static_cast<long>(blockIdx.z) * rows;
     const double* p = P + static_cast<long>(row) * ldp;
     double m = 0.0;
 #pragma unroll
@@ -173,6 +175,9 @@ __global__ void __launch_bounds__(128) ozaki_slice_kernel(const double* __restri
                                                           const double* __restrict__ rmaxq, int8_t* __restrict__ S) {
     const int rb = blockIdx.x, chunk = blockIdx.y, rr = threadIdx.x;
     const long row = static_cast<long>(rb) * 128 + rr;
+    P += static_cast<long>(blockIdx.z) * OZ_K;                      // K panel blockIdx.z (launch_ozaki_slice_panels)
+    rscale += static_cast<long>(blockIdx.z) * (static_cast<long>(gridDim.x) * 128);
+    S += static_cast<long>(blockIdx.z) * (static_cast<long>(gridDim.x) * OZ_RB_BYTES);
     double sc;
     if (rmaxq != nullptr) {
         const double4 q = *reinterpret_cast<const double4*>(rmaxq + row * 4);
@@ -235,6 +240,10 @@ struct OzakiArgs {
     long long* dbg;           // OZ_TIMING builds (tools/micro/ozaki_probe.cu): clock64 stamps of CTA 0
     int c_reduce;             // 1: C += c through shared memory + cp.reduce.async.bulk (no read of C); 0: load / add / store
     int prod3;                // 1: one producer thread per ring stage (both operands); 0: one per operand
+    int kpanels;              // v5 only: > 1 = the tile set is repeated for `kpanels` K panels of 256 whose products all go to the SAME C
+    long panel_bytes;         //   tiles (split-K through the L2 reduction): slices / scales of panel kp start at S + kp * panel_bytes,
+    long panel_rows;          //   rscale + kp * panel_rows
+    int add;                  // v5 only: 1 = C += A B^T instead of C -= A B^T
     int xp;                   // OZ_TIMING builds only (tools/micro/ozaki_probe.cu): timing experiments, bit mask --
                               // 1 half of the MMAs, 2 no B loads, 4 one-slice loads, 8 no read of C, 16 no store of C
 };
@@ -919,254 +928,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1) ozaki
 
 
 // =================================================================================================================
-// v4 (r02): the same two passes, fed through an 8-slot ring.
-// Measured on the r01 kernel (profiles/r02/x1_ozaki_bound_experiment.txt): loading ONE slice per operand instead of 4 / 7
-// changes the time of a 1830-tile launch by 3 % (0.246 vs 0.253 ms) and issuing HALF of the MMAs by 10 % -- the K loops
-// were bound neither by the shared-memory port nor by L2 -> SM bandwidth nor by the tensor pipe, but by the DEPTH of the
-// 3-stage ring: a stage is refilled only after the MMAs that read it have completed (tcgen05.commit -> mbarrier -> the
-// producer wakes -> cp.async.bulk -> ~1200 clk of L2 latency -> mbarrier -> the issuer wakes: ~2500 clk), and 3 stages of
-// K = 32 hold 640 (pass 0) to 1150 (pass 1) clk of MMA work each.  Here:
-//   * passes {0,1,2} / {3..6}: 3 + 7 = 10 slice loads per operand and K step instead of 4 + 7, 6 + 22 products;
-//   * slot = 28 KB = all 7 digits of ONE operand for one K step.  Pass 1 uses two slots per K step (A, B): 4 K steps =
-//     5600 clk of MMA work in flight; a pass-0 K step needs 3 + 3 digits = 24 KB and takes ONE slot: 8 K steps in flight;
-//   * 8 + 16 = 24 slot uses per tile = 3 revolutions of the ring: the slot of every (pass, K step) is static;
-//   * two producer threads: even / odd slot uses (pass 1: A / B blocks).
-// =================================================================================================================
-constexpr int OZ4_SLOTS = 8;
-constexpr int OZ4_SLOT_BYTES = OZ_SLICES * OZ_SLICE_STEP_BYTES;         // 28 KB
-constexpr int OZ4_NW0 = 3;
-constexpr int OZ4_P0_OPERAND = OZ4_NW0 * OZ_SLICE_STEP_BYTES;           // 12 KB
-constexpr int OZ4_USES = OZ_KSTEPS + 2 * OZ_KSTEPS;                     // slot uses per tile (24)
-static_assert(OZ4_USES % OZ4_SLOTS == 0, "the slot of a (pass, K step) must not depend on the tile");
-constexpr int OZ4_REVS = OZ4_USES / OZ4_SLOTS;
-
-struct __align__(8) Oz4Barriers {
-    uint64_t full[OZ4_SLOTS], empty[OZ4_SLOTS], acc_full, acc_empty;
-    uint32_t tmem_base, pad_;
-};
-constexpr int OZ4_SMEM_BYTES = OZ4_SLOTS * OZ4_SLOT_BYTES + static_cast<int>(sizeof(Oz4Barriers));
-static_assert(OZ4_SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
-
-__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk4_kernel(const OzakiArgs g) {
-    extern __shared__ __align__(1024) unsigned char oz_smem[];
-    Oz4Barriers* bars = reinterpret_cast<Oz4Barriers*>(oz_smem + OZ4_SLOTS * OZ4_SLOT_BYTES);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntiles = g.tri > 0 ? g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri : g.Mt * g.Nt;
-    if (tid == 0) OZ_STAMP(0);
-
-    if (tid == 0) {
-        for (int s = 0; s < OZ4_SLOTS; ++s) {
-            oz_mbar_init(&bars->full[s], 1);
-            oz_mbar_init(&bars->empty[s], 1);
-        }
-        oz_mbar_init(&bars->acc_full, 1);
-        oz_mbar_init(&bars->acc_empty, 8);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(&bars->tmem_base)),
-                     "n"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = bars->tmem_base;
-    if (tid == 0) OZ_STAMP(1);
-
-    if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OZ_REGS_CTRL));
-        if ((warp == 0 || warp == 2) && lane == 0) {
-            // ===== producers: warp 0 = even slot uses (pass 0: even K steps, pass 1: the A blocks), warp 2 = odd =====
-            const int par = warp >> 1;
-            uint32_t rev = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rev += OZ4_REVS) {
-                int tr, tc;
-                oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
-                const int8_t* Ag = g.S + static_cast<long>(tr) * OZ_RB_BYTES;
-                const int8_t* Bg = g.SB + static_cast<long>(tc) * OZ_RB_BYTES;
-                for (int u = par; u < OZ4_USES; u += 2) {
-                    const uint32_t slot = u & (OZ4_SLOTS - 1), r = rev + (u >> 3);
-                    unsigned char* dst = oz_smem + slot * OZ4_SLOT_BYTES;
-                    oz_mbar_wait(&bars->empty[slot], (r & 1) ^ 1);
-                    if (u < OZ_KSTEPS) {
-                        uint32_t bytes = OZ4_P0_OPERAND;
-#ifdef OZ_TIMING
-                        if (g.xp & 4) bytes = 1024;
-#endif
-                        oz_mbar_expect_tx(&bars->full[slot], 2 * bytes);
-                        oz_bulk_g2s(dst, Ag + static_cast<long>(u) * OZ_STAGE_OPERAND, bytes, &bars->full[slot]);
-                        oz_bulk_g2s(dst + OZ4_P0_OPERAND, Bg + static_cast<long>(u) * OZ_STAGE_OPERAND, bytes, &bars->full[slot]);
-                    } else {
-                        const int ks = (u - OZ_KSTEPS) >> 1;
-                        uint32_t bytes = OZ4_SLOT_BYTES;
-#ifdef OZ_TIMING
-                        if (g.xp & 4) bytes = 1024;
-#endif
-                        oz_mbar_expect_tx(&bars->full[slot], bytes);
-                        oz_bulk_g2s(dst, (par ? Bg : Ag) + static_cast<long>(ks) * OZ_STAGE_OPERAND, bytes, &bars->full[slot]);
-                    }
-                }
-            }
-        } else if (warp == 1 && lane == 0) {
-            // ===== MMA issuer =====
-#ifdef OZ_TIMING
-            const int half = g.xp & 1;
-#else
-            constexpr int half = 0;
-#endif
-            uint32_t rev = 0, P = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, rev += OZ4_REVS) {
-                // pass 0: weights 0..2 into accumulators 0..2
-                if (P > 0) {
-                    oz_mbar_wait(&bars->acc_empty, (P - 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                for (int ks = 0; ks < OZ_KSTEPS; ++ks) {
-                    oz_mbar_wait(&bars->full[ks], rev & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (P == 0 && ks == 0) OZ_STAMP(2);
-                    if (P == 2 && ks == 0) OZ_STAMP(15);
-                    if (P == 2 && ks == 7) OZ_STAMP(16);
-                    const uint32_t sa = oz_smem_u32(oz_smem + ks * OZ4_SLOT_BYTES);
-                    oz_issue_kstep<0, OZ4_NW0, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sa + OZ4_P0_OPERAND, ks > 0 ? 1u : 0u, half);
-                    oz_umma_commit(&bars->empty[ks]);
-                }
-                oz_umma_commit(&bars->acc_full);
-                ++P;
-                // pass 1: weights 3..6 into accumulators 0..3
-                oz_mbar_wait(&bars->acc_empty, (P - 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int ks = 0; ks < OZ_KSTEPS; ++ks) {
-                    const uint32_t u = OZ_KSTEPS + 2 * ks, slot = u & (OZ4_SLOTS - 1), r = rev + (u >> 3);
-                    oz_mbar_wait(&bars->full[slot], r & 1);
-                    oz_mbar_wait(&bars->full[slot + 1], r & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (P == 1 && ks == 0) OZ_STAMP(3);
-                    if (P == 3 && ks == 0) OZ_STAMP(17);
-                    const uint32_t sa = oz_smem_u32(oz_smem + slot * OZ4_SLOT_BYTES);
-                    oz_issue_kstep<OZ4_NW0, OZ_SLICES - OZ4_NW0, OZ_SLICE_STEP_BYTES, false>(tmem, sa, sa + OZ4_SLOT_BYTES, ks > 0 ? 1u : 0u,
-                                                                                             half);
-                    oz_umma_commit(&bars->empty[slot]);
-                    oz_umma_commit(&bars->empty[slot + 1]);
-                }
-                oz_umma_commit(&bars->acc_full);
-                ++P;
-            }
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(OZ_REGS_EPI));
-        // ===== epilogue: 8 warps; lane quarter = warp % 4, column half = (warp - 4) / 4 =====
-        const int quarter = warp & 3, chalf = (warp - 4) >> 2;
-        const int r_in = lane >> 2, cq = 2 * (lane & 3);
-        const bool odd = (r_in & 1) != 0;
-        uint32_t P = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            int tr, tc;
-            oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
-            // this thread's entries: rows 32 quarter + 16 rh + r_in (+8), columns 64 chalf + 8 j + cq + {0,1}
-            double* Cb = g.C + (static_cast<long>(tr) * 128 + 32 * quarter + r_in) * g.ldc + static_cast<long>(tc) * 128 +
-                         64 * chalf + cq;
-            const double* rsA = g.rscale + static_cast<long>(tr) * 128 + 32 * quarter + r_in;
-            const double* rsB = g.rscaleB + static_cast<long>(tc) * 128 + 64 * chalf + cq;
-            double2 c[2][2][8];                              // -(P P^T) of this thread's entries, [rh][row r_in / +8][j]
-#pragma unroll
-            for (int rh = 0; rh < 2; ++rh)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) c[rh][h][j] = make_double2(0.0, 0.0);
-            // pull this thread's share of the C tile into L2 now (HBM -> L2 only): the read after pass 0 sees L2 latency
-#pragma unroll
-            for (int rh = 0; rh < 2; ++rh)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int j = 0; j < 8; j += 2)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + 8 * j));
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass, ++P) {
-                // 256^-(last weight of the pass + 2)
-                const double wscale = pass == 0 ? 2.3283064365386963e-10 /* 256^-4 */ : 5.421010862427522e-20 /* 256^-8 */;
-                oz_mbar_wait(&bars->acc_full, P & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (tid == 128 && tile == blockIdx.x) OZ_STAMP(4 + 2 * pass);
-                if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(10 + 2 * pass);
-                if (pass == 0) oz_drain<OZ4_NW0>(tmem, quarter, chalf, rsA, rsB, wscale, c);
-                else oz_drain<OZ_SLICES - OZ4_NW0>(tmem, quarter, chalf, rsA, rsB, wscale, c);
-                // all TMEM reads of this pass are complete: hand the accumulators back
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) oz_mbar_arrive(&bars->acc_empty);
-                if (tid == 128 && tile == blockIdx.x) OZ_STAMP(5 + 2 * pass);
-                if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(11 + 2 * pass);
-#ifdef OZ_TIMING
-                if (g.xp & 8) continue;
-#endif
-                if (pass == 0) {
-                    // c = C - (pass-0 part): the tile is READ here, while the MMAs of pass 1 run and these warps would only
-                    // wait.  Two adjacent quads (rows r, r+1 of the fragment) team up so that ONE instruction covers 128
-                    // contiguous bytes of a row: the even quad reads columns 8j.. of the even row and of the odd row, the
-                    // odd quad columns 8(j+1).. of both; what belongs to the partner changes hands through shfl.xor 4.
-#pragma unroll
-                    for (int rh = 0; rh < 2; ++rh)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const double* base = Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + (odd ? 8 : 0);
-                            const double* row_e = base - (odd ? g.ldc : 0);
-                            const double* row_o = row_e + g.ldc;
-                            double2 ve[4], vo[4];
-#pragma unroll
-                            for (int jp = 0; jp < 4; ++jp) {
-                                ve[jp] = *reinterpret_cast<const double2*>(row_e + 16 * jp);
-                                vo[jp] = *reinterpret_cast<const double2*>(row_o + 16 * jp);
-                            }
-#pragma unroll
-                            for (int jp = 0; jp < 4; ++jp) {
-                                const double2 got = oz_shfl_xor4(odd ? ve[jp] : vo[jp]);
-                                const double2 own = odd ? vo[jp] : ve[jp];
-                                const double2 add0 = odd ? got : own, add1 = odd ? own : got;     // for columns 8j.. / 8(j+1)..
-                                c[rh][h][2 * jp].x += add0.x;
-                                c[rh][h][2 * jp].y += add0.y;
-                                c[rh][h][2 * jp + 1].x += add1.x;
-                                c[rh][h][2 * jp + 1].y += add1.y;
-                            }
-                        }
-                }
-            }
-#ifdef OZ_TIMING
-            if ((g.xp & 16) && c[0][0][0].x != 1.2345e300) goto skip_store4;     // timing experiment: no C store
-#endif
-#pragma unroll
-            for (int rh = 0; rh < 2; ++rh)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    double* base = Cb + static_cast<long>(16 * rh + 8 * h) * g.ldc + (odd ? 8 : 0);
-                    double* row_e = base - (odd ? g.ldc : 0);
-                    double* row_o = row_e + g.ldc;
-#pragma unroll
-                    for (int jp = 0; jp < 4; ++jp) {
-                        const double2 own = odd ? c[rh][h][2 * jp + 1] : c[rh][h][2 * jp];
-                        const double2 got = oz_shfl_xor4(odd ? c[rh][h][2 * jp] : c[rh][h][2 * jp + 1]);
-                        *reinterpret_cast<double2*>(row_e + 16 * jp) = odd ? got : own;     // 128 B of the even row per quad pair
-                        *reinterpret_cast<double2*>(row_o + 16 * jp) = odd ? own : got;     // 128 B of the odd row
-                    }
-                }
-#ifdef OZ_TIMING
-        skip_store4:;
-#endif
-            if (tid == 128 && tile == blockIdx.x) OZ_STAMP(9);
-            if (tid == 128 && tile == blockIdx.x + gridDim.x) OZ_STAMP(14);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) OZ_STAMP(8);
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
-}
-
-
-// =================================================================================================================
 // v5 (r02): four weight groups, two accumulator buffers -- the accumulator drains run UNDER the MMAs.
 // What the r02 probes showed (profiles/r02/pattern_probe.txt, x1_*, x2_*):
 //   * an N = 256 MMA (two adjacent B digits) runs at the nominal 128 clk, an N = 128 MMA takes 100 clk, not 64 (operand
@@ -1179,108 +940,76 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk4_kernel(const OzakiA
 // while the MMAs of a group fill one half, the epilogue drains the other.  In this order a group needs digits 0..6, 0..4,
 // 0..2, 0 of both operands: 16 slice loads per operand and K step (10 in the two-pass form -- affordable, see above), and
 // 19 of the 28 products still pair up into N = 256 MMAs (6 + 4 + 2 N256, 1 + 1 + 1 + 1 N128: 1936 clk per K step at the
-// measured rates, the same as the two-pass form).  Ring: 4 stages x 56 KB (A half | B half); a stage holds 1 / 1 / 2 / 7
-// K steps of group 0 / 1 / 2 / 3, so the issuing thread waits 8 + 8 + 4 + 2 = 22 times per tile.
-// Epilogue: c -= T 2^E for every group, T = a0 256 + a1 exact in int64, and since the row scales are powers of two the
-// scaling is folded into the int -> double conversion: bits(1.5 * 2^(52+E)) + T is the double 1.5 * 2^(52+E) + T 2^E
-// EXACTLY (|T| < 2^51), so one integer add and one DADD replace convert + DMUL.
+// measured rates, the same as the two-pass form).  Ring: 3 stages x 56 KB (A half | B half) -- the rest of shared
+// memory stages the C update, see the epilogue; a stage holds 1 / 1 / 2 / 7 K steps of group 0 / 1 / 2 / 3, so the issuing
+// thread waits 8 + 8 + 4 + 2 = 22 times per tile.  (Measured and dropped: a byte-granular ring of 192 KB with 80 KB blocks for
+// group 1 -- four of its K steps in flight instead of three, 18 waits -- was 5 % SLOWER, 0.184 vs 0.176 ms on 1830 tiles,
+// profiles/r02/x7_v5_byte_ring.txt: the extra index arithmetic sits in the producer / issuer threads whose latency is what the
+// ring exists to hide.)
+// Epilogue: NO fp64 instruction at all (while int8 MMAs stream, DADD / DFMA / I2F.F64 of any warp of the SM run 7 - 130 x
+// slower: profiles/r02/alu_probe.txt, drain_probe.txt).  The groups are accumulated into one int64 per entry, converted to
+// -T 2^E with integer instructions (the row scales are powers of two: an exponent-field add), staged in shared memory and
+// ADDED to C by the L2 through cp.reduce.async.bulk.tensor (.add, fp64 tensor map of C): C is never read by the SM.
 // =================================================================================================================
-constexpr int OZ5_NB = 8;                                                // full / empty barrier pairs: block n uses pair n % OZ5_NB
-constexpr int OZ5_RING_BYTES = 192 * 1024;                               // byte-granular ring of operand blocks
+constexpr int OZ5_STAGES = 3;
+constexpr int OZ5_HALF = OZ_SLICES * OZ_SLICE_STEP_BYTES;                // 28 KB: one operand
+constexpr int OZ5_STAGE_BYTES = 2 * OZ5_HALF;                            // 56 KB
 constexpr int OZ5_GROUPS = 4;
 constexpr int OZ5_PIECE_ROWS = 8;                                        // C leaves in pieces of 8 rows x 128 columns (8 KB) ...
 constexpr int OZ5_PIECE_BYTES = OZ5_PIECE_ROWS * 128 * 8;                // ... one staging buffer per lane quarter (warp pair)
 constexpr int OZ5_STAGING_BYTES = 4 * OZ5_PIECE_BYTES;                   // 32 KB
 
 struct __align__(8) Oz5Barriers {
-    uint64_t full[OZ5_NB], empty[OZ5_NB], acc_full[2], acc_empty[2];
+    uint64_t full[OZ5_STAGES], empty[OZ5_STAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_base, pad_;
 };
-constexpr int OZ5_SMEM_BYTES = OZ5_RING_BYTES + OZ5_STAGING_BYTES + static_cast<int>(sizeof(Oz5Barriers));
+constexpr int OZ5_SMEM_BYTES = OZ5_STAGES * OZ5_STAGE_BYTES + OZ5_STAGING_BYTES + static_cast<int>(sizeof(Oz5Barriers));
 static_assert(OZ5_SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 
-// group g: weights W0 .. W0 + NW - 1, digits 0 .. D - 1 of both operands, KPS K steps per ring block.
-// A block = [A part | B part], each KPS x D x 4 KB; blocks per tile: 8 x 56 KB, 4 x 80 KB, 4 x 48 KB, 56 KB + 8 KB = 18 blocks, 1 MB.
+// group g: weights W0 .. W0 + NW - 1, digits 0 .. D - 1 of both operands, KPS K steps per ring stage
 template <int G> struct Oz5Group;
 template <> struct Oz5Group<0> { static constexpr int W0 = 5, NW = 2, D = 7, KPS = 1; };
-template <> struct Oz5Group<1> { static constexpr int W0 = 3, NW = 2, D = 5, KPS = 2; };
+template <> struct Oz5Group<1> { static constexpr int W0 = 3, NW = 2, D = 5, KPS = 1; };
 template <> struct Oz5Group<2> { static constexpr int W0 = 1, NW = 2, D = 3, KPS = 2; };
 template <> struct Oz5Group<3> { static constexpr int W0 = 0, NW = 1, D = 1, KPS = 7; };
-constexpr int OZ5_BLOCKS_PER_TILE = 18;
-__device__ __forceinline__ uint32_t oz5_block_bytes(uint32_t n) {        // size of block n of the (tile-periodic) sequence
-    const uint32_t i = n % OZ5_BLOCKS_PER_TILE;
-    return (i < 8 ? 56u : i < 12 ? 80u : i < 16 ? 48u : i == 16 ? 56u : 8u) * 1024u;
-}
-// The ring allocator: blocks are laid one after the other, a block that would cross the end starts at 0 again.  Producers and
-// the issuer replay the same deterministic sequence.
-struct Oz5Ring {
-    uint32_t head = 0;
-    __device__ __forceinline__ uint32_t place(uint32_t size) const { return head + size > OZ5_RING_BYTES ? 0u : head; }
-    __device__ __forceinline__ uint32_t alloc(uint32_t size) {
-        const uint32_t o = place(size);
-        head = o + size;
-        return o;
-    }
-};
-// producer side: blocks tail_n .. n - 1 are live (filled or being filled, not yet released by the MMAs that read them); before
-// block n is written every live block it overlaps -- always the oldest ones -- must have been released, and at most OZ5_NB - 1
-// blocks may be live (block n reuses the barrier pair of block n - OZ5_NB)
-struct Oz5Producer {
-    Oz5Ring ring, tail_ring;
-    uint32_t n = 0, tail_n = 0;
-    __device__ __forceinline__ uint32_t acquire(Oz5Barriers* bars, uint32_t size) {
-        const uint32_t off = ring.alloc(size);
-        while (tail_n < n) {
-            const uint32_t ts = oz5_block_bytes(tail_n), to = tail_ring.place(ts);
-            const bool overlap = off < to + ts && to < off + size;
-            if (!overlap && n - tail_n < OZ5_NB) break;
-            oz_mbar_wait(&bars->empty[tail_n % OZ5_NB], (tail_n / OZ5_NB) & 1);
-            tail_ring.alloc(ts);
-            ++tail_n;
-        }
-        return off;
-    }
-};
 
-// producer of ONE operand: all blocks of group G of the current tile
+// producer of ONE operand: all stage uses of group G of the current tile
 template <int G>
-__device__ __forceinline__ void oz5_produce(unsigned char* smem, Oz5Barriers* bars, const int8_t* Sg, int operand, Oz5Producer& pr,
+__device__ __forceinline__ void oz5_produce(unsigned char* smem, Oz5Barriers* bars, const int8_t* Sg, int operand, uint32_t& n,
                                             int tiny) {
     using Gp = Oz5Group<G>;
 #pragma unroll 1
-    for (int ks0 = 0; ks0 < OZ_KSTEPS; ks0 += Gp::KPS) {
+    for (int ks0 = 0; ks0 < OZ_KSTEPS; ks0 += Gp::KPS, ++n) {
         const int nk = (OZ_KSTEPS - ks0) < Gp::KPS ? (OZ_KSTEPS - ks0) : Gp::KPS;
-        const uint32_t part = static_cast<uint32_t>(nk) * (Gp::D * OZ_SLICE_STEP_BYTES);      // one operand
-        const uint32_t off = pr.acquire(bars, 2 * part);
-        const uint32_t b = pr.n % OZ5_NB;
+        const uint32_t stage = n % OZ5_STAGES, round = n / OZ5_STAGES;
         uint32_t bytes = Gp::D * OZ_SLICE_STEP_BYTES;
         if (tiny) bytes = 1024;
-        unsigned char* dst = smem + off + operand * part;
-        oz_mbar_expect_tx(&bars->full[b], static_cast<uint32_t>(nk) * bytes);
+        unsigned char* dst = smem + stage * OZ5_STAGE_BYTES + operand * OZ5_HALF;
+        oz_mbar_wait(&bars->empty[stage], (round & 1) ^ 1);
+        oz_mbar_expect_tx(&bars->full[stage], static_cast<uint32_t>(nk) * bytes);
         for (int j = 0; j < nk; ++j)
             oz_bulk_g2s(dst + j * (Gp::D * OZ_SLICE_STEP_BYTES), Sg + static_cast<long>(ks0 + j) * OZ_STAGE_OPERAND, bytes,
-                        &bars->full[b]);
-        ++pr.n;
+                        &bars->full[stage]);
     }
 }
 
 // MMA issue of group G of the current tile into the accumulator buffer at tmem_buf
 template <int G>
-__device__ __forceinline__ void oz5_issue(unsigned char* smem, Oz5Barriers* bars, uint32_t tmem_buf, Oz5Ring& ring, uint32_t& n, int half) {
+__device__ __forceinline__ void oz5_issue(unsigned char* smem, Oz5Barriers* bars, uint32_t tmem_buf, uint32_t& n, int half) {
     using Gp = Oz5Group<G>;
 #pragma unroll 1
     for (int ks0 = 0; ks0 < OZ_KSTEPS; ks0 += Gp::KPS, ++n) {
         const int nk = (OZ_KSTEPS - ks0) < Gp::KPS ? (OZ_KSTEPS - ks0) : Gp::KPS;
-        const uint32_t part = static_cast<uint32_t>(nk) * (Gp::D * OZ_SLICE_STEP_BYTES);
-        const uint32_t sa = oz_smem_u32(smem + ring.alloc(2 * part));
-        oz_mbar_wait(&bars->full[n % OZ5_NB], (n / OZ5_NB) & 1);
+        const uint32_t stage = n % OZ5_STAGES, round = n / OZ5_STAGES;
+        const uint32_t sa = oz_smem_u32(smem + stage * OZ5_STAGE_BYTES);
+        oz_mbar_wait(&bars->full[stage], round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
         for (int j = 0; j < nk; ++j) {
             const uint32_t a = sa + j * (Gp::D * OZ_SLICE_STEP_BYTES);
-            oz_issue_kstep<Gp::W0, Gp::NW, OZ_SLICE_STEP_BYTES, false>(tmem_buf, a, a + part, (ks0 + j) > 0 ? 1u : 0u, half);
+            oz_issue_kstep<Gp::W0, Gp::NW, OZ_SLICE_STEP_BYTES, false>(tmem_buf, a, a + OZ5_HALF, (ks0 + j) > 0 ? 1u : 0u, half);
         }
-        oz_umma_commit(&bars->empty[n % OZ5_NB]);
+        oz_umma_commit(&bars->empty[stage]);
     }
 }
 
@@ -1349,28 +1078,29 @@ constexpr int OZ5_ECONST = -56 * 1048576;
 // (double) t * 2^E with INTEGER instructions only (I2F.F64.S64 sits on the fp64 pipe too: 64 conversions per thread took 15 k clk
 // under the MMA stream): normalise |t| (bit 63 set), keep 53 bits rounded half-up (1 ulp of 2^-53 relative against RN at worst,
 // far below the scheme's own truncation), assemble sign | exponent | mantissa.  eshift = E << 20.
-// Returns -t 2^E (the update is ADDED to C by the TMA reduction).
-__device__ __forceinline__ double oz5_scaled(long long t, int eshift) {
+// Returns -t 2^E (the update is ADDED to C by the TMA reduction); sign_flip = 0x80000000 returns +t 2^E.
+__device__ __forceinline__ double oz5_scaled(long long t, int eshift, int sign_flip = 0) {
     const unsigned long long a = t < 0 ? 0ULL - static_cast<unsigned long long>(t) : static_cast<unsigned long long>(t);
     const int lz = __clzll(static_cast<long long>(a | 1ULL));
     const unsigned long long nrm = a << lz;
     const unsigned long long mant = (nrm >> 11) + ((nrm >> 10) & 1ULL);           // 2^52 .. 2^53 (the implicit bit included)
     int hi = ((1085 - lz) << 20) + eshift + static_cast<int>(mant >> 32);        // (exponent - 1) << 20, + the implicit bit
-    hi |= ~static_cast<int>(static_cast<unsigned long long>(t) >> 32) & static_cast<int>(0x80000000u);
+    hi |= (~static_cast<int>(static_cast<unsigned long long>(t) >> 32) ^ sign_flip) & static_cast<int>(0x80000000u);
     const bool nz = t != 0;
     return __hiloint2double(nz ? hi : 0, nz ? static_cast<int>(static_cast<uint32_t>(mant)) : 0);
 }
 
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiArgs g, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
-    unsigned char* staging = oz_smem + OZ5_RING_BYTES;
+    unsigned char* staging = oz_smem + OZ5_STAGES * OZ5_STAGE_BYTES;
     Oz5Barriers* bars = reinterpret_cast<Oz5Barriers*>(staging + OZ5_STAGING_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntiles = g.tri > 0 ? g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri : g.Mt * g.Nt;
+    const int base_tiles = g.tri > 0 ? g.tri * (g.tri + 1) / 2 + (g.Mt - g.tri) * g.tri : g.Mt * g.Nt;
+    const int ntiles = base_tiles * (g.kpanels > 1 ? g.kpanels : 1);     // task t = (K panel t / base_tiles, tile t % base_tiles)
     if (tid == 0) OZ_STAMP(0);
 
     if (tid == 0) {
-        for (int s = 0; s < OZ5_NB; ++s) {
+        for (int s = 0; s < OZ5_STAGES; ++s) {
             oz_mbar_init(&bars->full[s], 2);
             oz_mbar_init(&bars->empty[s], 1);
         }
@@ -1401,40 +1131,41 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiA
         if ((warp == 0 || warp == 2) && lane == 0) {
             // ===== producers: warp 0 = the A halves of the stages, warp 2 = the B halves =====
             const int operand = warp >> 1;
-            Oz5Producer pr;
+            uint32_t n = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 int tr, tc;
-                oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
-                const int8_t* Sg = operand ? g.SB + static_cast<long>(tc) * OZ_RB_BYTES : g.S + static_cast<long>(tr) * OZ_RB_BYTES;
-                oz5_produce<0>(oz_smem, bars, Sg, operand, pr, xp & 4);
-                oz5_produce<1>(oz_smem, bars, Sg, operand, pr, xp & 4);
-                oz5_produce<2>(oz_smem, bars, Sg, operand, pr, xp & 4);
-                oz5_produce<3>(oz_smem, bars, Sg, operand, pr, xp & 4);
+                const int kp = tile / base_tiles;
+                oz_tile_decode(tile - kp * base_tiles, g.tri, g.Mt, tr, tc);
+                const int8_t* Sg = (operand ? g.SB + static_cast<long>(tc) * OZ_RB_BYTES : g.S + static_cast<long>(tr) * OZ_RB_BYTES) +
+                                   static_cast<long>(kp) * g.panel_bytes;
+                oz5_produce<0>(oz_smem, bars, Sg, operand, n, xp & 4);
+                oz5_produce<1>(oz_smem, bars, Sg, operand, n, xp & 4);
+                oz5_produce<2>(oz_smem, bars, Sg, operand, n, xp & 4);
+                oz5_produce<3>(oz_smem, bars, Sg, operand, n, xp & 4);
             }
         } else if (warp == 1 && lane == 0) {
             // ===== MMA issuer: groups 0, 2 -> buffer X, groups 1, 3 -> buffer Y; use u of a buffer waits for the drain of use u - 1 =====
-            Oz5Ring ring;
-            uint32_t n = 0, u = 0;                            // blocks; uses of EACH buffer so far (both advance together)
+            uint32_t n = 0, u = 0;                            // stage uses; uses of EACH buffer so far (both advance together)
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const bool t1 = tile == static_cast<int>(blockIdx.x + gridDim.x);
                 if (u > 0) { oz_mbar_wait(&bars->acc_empty[0], (u - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
                 if (t1) OZ_STAMP(20);
-                oz5_issue<0>(oz_smem, bars, tmem, ring, n, xp & 1);
+                oz5_issue<0>(oz_smem, bars, tmem, n, xp & 1);
                 oz_umma_commit(&bars->acc_full[0]);
                 if (u > 0) { oz_mbar_wait(&bars->acc_empty[1], (u - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
                 if (t1) OZ_STAMP(21);
-                oz5_issue<1>(oz_smem, bars, tmem + 256, ring, n, xp & 1);
+                oz5_issue<1>(oz_smem, bars, tmem + 256, n, xp & 1);
                 oz_umma_commit(&bars->acc_full[1]);
                 ++u;
                 oz_mbar_wait(&bars->acc_empty[0], (u - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (t1) OZ_STAMP(22);
-                oz5_issue<2>(oz_smem, bars, tmem, ring, n, xp & 1);
+                oz5_issue<2>(oz_smem, bars, tmem, n, xp & 1);
                 oz_umma_commit(&bars->acc_full[0]);
                 oz_mbar_wait(&bars->acc_empty[1], (u - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (t1) OZ_STAMP(23);
-                oz5_issue<3>(oz_smem, bars, tmem + 256, ring, n, xp & 1);
+                oz5_issue<3>(oz_smem, bars, tmem + 256, n, xp & 1);
                 oz_umma_commit(&bars->acc_full[1]);
                 ++u;
                 if (t1) OZ_STAMP(24);
@@ -1450,12 +1181,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiA
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const bool t0 = tile == static_cast<int>(blockIdx.x), t1 = tile == static_cast<int>(blockIdx.x + gridDim.x);
             int tr, tc;
-            oz_tile_decode(tile, g.tri, g.Mt, tr, tc);
+            const int kp = tile / base_tiles;
+            oz_tile_decode(tile - kp * base_tiles, g.tri, g.Mt, tr, tc);
+            const int sign_flip = g.add ? static_cast<int>(0x80000000u) : 0;
             // this thread's entries: rows 32 quarter + 16 rh + r_in (+8), columns 64 chalf + 8 j + cq + {0,1}
             double* Cb = g.C + (static_cast<long>(tr) * 128 + 32 * quarter + r_in) * g.ldc + static_cast<long>(tc) * 128 +
                          64 * chalf + cq;
-            const double* rsA = g.rscale + static_cast<long>(tr) * 128 + 32 * quarter + r_in;
-            const double* rsB = g.rscaleB + static_cast<long>(tc) * 128 + 64 * chalf + cq;
+            const double* rsA = g.rscale + static_cast<long>(kp) * g.panel_rows + static_cast<long>(tr) * 128 + 32 * quarter + r_in;
+            const double* rsB = g.rscaleB + static_cast<long>(kp) * g.panel_rows + static_cast<long>(tc) * 128 + 64 * chalf + cq;
             int hiA[2][2], hiB[8][2];
 #pragma unroll
             for (int rh = 0; rh < 2; ++rh)
@@ -1504,10 +1237,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiA
 #pragma unroll
                     for (int jp = 0; jp < 4; ++jp) {
                         double2 c0, c1;                                               // columns 8 (2 jp).. / 8 (2 jp + 1).. of this thread's row
-                        c0.x = oz5_scaled(T[rh][h][2 * jp][0], er + hiB[2 * jp][0]);
-                        c0.y = oz5_scaled(T[rh][h][2 * jp][1], er + hiB[2 * jp][1]);
-                        c1.x = oz5_scaled(T[rh][h][2 * jp + 1][0], er + hiB[2 * jp + 1][0]);
-                        c1.y = oz5_scaled(T[rh][h][2 * jp + 1][1], er + hiB[2 * jp + 1][1]);
+                        c0.x = oz5_scaled(T[rh][h][2 * jp][0], er + hiB[2 * jp][0], sign_flip);
+                        c0.y = oz5_scaled(T[rh][h][2 * jp][1], er + hiB[2 * jp][1], sign_flip);
+                        c1.x = oz5_scaled(T[rh][h][2 * jp + 1][0], er + hiB[2 * jp + 1][0], sign_flip);
+                        c1.y = oz5_scaled(T[rh][h][2 * jp + 1][1], er + hiB[2 * jp + 1][1], sign_flip);
                         const double2 mine = odd ? c1 : c0;
                         const double2 back = oz_shfl_xor4(odd ? c0 : c1);
                         se[jp] = odd ? back : mine;                                   // 128 B of the even row per quad pair
@@ -1559,10 +1292,19 @@ void launch_ozaki_slice(const double* P, long ldp, int rows, double* rscale, int
     ozaki_slice_kernel<<<dim3(rows / 128, OZ_K / 16), 128, 0, s>>>(P, ldp, rscale, rmaxq, S);
 }
 
+// P: rows x (256 kpanels) (ldp): every K panel of 256 columns is sliced on its own (own row scales):
+// rscale[kp][rows], S[kp][rows / 128][256 KB]
+void launch_ozaki_slice_panels(const double* P, long ldp, int rows, int kpanels, double* rscale, int8_t* S, cudaStream_t s) {
+    if (rows <= 0 || kpanels <= 0) return;
+    ozaki_rowscale_kernel<<<dim3((rows + 7) / 8, 1, kpanels), 256, 0, s>>>(P, ldp, rows, rscale);
+    ozaki_slice_kernel<<<dim3(rows / 128, OZ_K / 16, kpanels), 128, 0, s>>>(P, ldp, rscale, nullptr, S);
+}
+
 // C -= A B^T from the slices of A (SA, rsA) and of B (SB, rsB).  tri > 0: SYRK form (B = A), lower-triangular tile set
 // with Mt - tri full tile rows below; tri == 0: rectangular Mt x Nt.
 static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rsA, const int8_t* SB, const double* rsB, int Mt,
-                         int Nt, int tri, cudaStream_t s, long long* dbg, int persist_hint) {
+                         int Nt, int tri, cudaStream_t s, long long* dbg, int persist_hint, int kpanels = 1, long panel_bytes = 0,
+                         long panel_rows = 0, int add = 0) {
     static bool configured_dev[64] = {false};
     int dev_ = 0;
     cudaGetDevice(&dev_);
@@ -1571,20 +1313,19 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
         cudaFuncSetAttribute(ozaki_syrk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
         cudaFuncSetAttribute(ozaki_syrk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
         cudaFuncSetAttribute(ozaki_syrk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ2_SMEM_BYTES);
-        cudaFuncSetAttribute(ozaki_syrk4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ4_SMEM_BYTES);
         cudaFuncSetAttribute(ozaki_syrk5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ5_SMEM_BYTES);
         configured = true;
     }
     static int sm_count_dev[64] = {0};
     int& sms = sm_count_dev[dev_ & 63];
     if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_);
-    const int tiles = tri > 0 ? tri * (tri + 1) / 2 + (Mt - tri) * tri : Mt * Nt;
+    const int tiles = (tri > 0 ? tri * (tri + 1) / 2 + (Mt - tri) * tri : Mt * Nt) * (kpanels > 1 ? kpanels : 1);
     if (tiles <= 0) return;
     static const int c_reduce = getenv("EGX_OZAKI_CRED") != nullptr ? atoi(getenv("EGX_OZAKI_CRED")) : 0;   // measured: same tile rate as load / add / store (the 128 row reductions of a tile serialise in the TMA unit)
     static const int prod3 = getenv("EGX_OZAKI_PROD3") != nullptr ? atoi(getenv("EGX_OZAKI_PROD3")) : 0;
     static const int xp = getenv("EGX_OZAKI_XP") != nullptr ? atoi(getenv("EGX_OZAKI_XP")) : 0;           // probe builds only
     static const int nw0 = getenv("EGX_OZAKI_NW0") != nullptr ? atoi(getenv("EGX_OZAKI_NW0")) : 4;
-    OzakiArgs g{C, ldc, SA, rsA, Mt, tri, SB, rsB, Nt, dbg, c_reduce, prod3, xp};
+    OzakiArgs g{C, ldc, SA, rsA, Mt, tri, SB, rsB, Nt, dbg, c_reduce, prod3, kpanels, panel_bytes, panel_rows, add, xp};
     alignas(64) CUtensorMap cmap;
     memset(&cmap, 0, sizeof(cmap));
     static const int version = getenv("EGX_OZAKI_V") != nullptr ? atoi(getenv("EGX_OZAKI_V")) : 5;     // 3: the r01 kernel (3-stage ring, two passes)
@@ -1634,14 +1375,15 @@ static void ozaki_launch(double* C, long ldc, const int8_t* SA, const double* rs
     // EGX_OZAKI_MAXCTAS caps the resident grid: with several evaluations in flight the SMs left over run the panel / solve /
     // correlation kernels of the OTHER evaluations instead of queueing behind this launch
     static const int max_ctas = getenv("EGX_OZAKI_MAXCTAS") != nullptr ? atoi(getenv("EGX_OZAKI_MAXCTAS")) : 0;
-    const int avail = (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;
+    // measured with 8 evaluations in flight at n = 8192 (profiles/r02/x8_batch_sweep.txt): 148 / 132 / 120 / 104 CTAs -> 3.32 / 3.28 /
+    // 3.23 / 3.28 ms per evaluation: the batched entry point (persist_hint) leaves 24 SMs to the other evaluations' small kernels
+    const int avail = (max_ctas > 0 && max_ctas < sms) ? max_ctas : ((persist_hint && max_ctas == 0 && sms > 48) ? sms - 24 : sms);
     int grid = tiles;
     if (persist && tiles > avail) {
         const int rounds = (tiles + avail - 1) / avail;
         grid = (tiles + rounds - 1) / rounds;
     }
     if (version == 5 && have_map) ozaki_syrk5_kernel<<<grid, OZ_THREADS, OZ5_SMEM_BYTES, s>>>(g, cmap);
-    else if (version == 4) ozaki_syrk4_kernel<<<grid, OZ_THREADS, OZ4_SMEM_BYTES, s>>>(g);
     else if (nw0 == 3) ozaki_syrk_kernel<3><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g, cmap);
     else ozaki_syrk_kernel<4><<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(g, cmap);
 }
@@ -1656,4 +1398,16 @@ void launch_ozaki_syrk(double* C, long ldc, const int8_t* S, const double* rscal
 void launch_ozaki_gemm(double* C, long ldc, const int8_t* SA, const double* rsA, const int8_t* SB, const double* rsB, int Mt,
                        int Nt, cudaStream_t s, int persist_hint) {
     ozaki_launch(C, ldc, SA, rsA, SB, rsB, Mt, Nt, 0, s, nullptr, persist_hint);
+}
+
+// C (lower tile triangle, tri x tri tiles) += sum over `kpanels` K panels of 256 of W_kp W_kp^T, from the panel-wise slices of
+// launch_ozaki_slice_panels: ONE launch of tri (tri + 1) / 2 x kpanels tile tasks whose results meet in L2 (the TMA reduction is
+// atomic per element).  The split-K SYRK of the sparse GP (A = I + V diag(beta) V^T, gp/src/sparse_algorithm.rs:727-731, 798).
+// Returns false when the v5 kernel is not in use (EGX_OZAKI_V=3) -- the caller keeps its DMMA path.
+bool launch_ozaki_syrk_add_panels(double* C, long ldc, const int8_t* S, const double* rscale, int tri, int kpanels, cudaStream_t s) {
+    static const int version = getenv("EGX_OZAKI_V") != nullptr ? atoi(getenv("EGX_OZAKI_V")) : 5;
+    if (version != 5) return false;
+    ozaki_launch(C, ldc, S, rscale, S, rscale, tri, tri, tri, s, nullptr, 1, kpanels, static_cast<long>(ozaki_slice_bytes(tri * 128L)),
+                 tri * 128L, 1);
+    return true;
 }

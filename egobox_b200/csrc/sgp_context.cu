@@ -63,6 +63,12 @@ struct egx_sgp_ctx {
     int *info1 = nullptr, *info2 = nullptr;
     double *Y = nullptr, *W = nullptr, *sqrtb = nullptr, *by = nullptr, *partial = nullptr, *tvec = nullptr;
     double *scal = nullptr, *out = nullptr, *out_h = nullptr;
+    int8_t* Lsl1 = nullptr;       // tcgen05 path of the solves Vt = Knm U^-T: digit slices / row scales of the block rows of U below every
+    double* Lsc1 = nullptr;       // column pair (rebuilt after every factorisation of Kmm), offsets per pair
+    std::vector<long> Lsl1_off, Lsc1_off;
+    bool Lsl1_ready = false;
+    int8_t* ozS = nullptr;        // tcgen05 path of the split-K W W^T: int8 digit slices of every K panel of 256 points of a chunk ...
+    double* ozScale = nullptr;    // ... and their row scales (kernels_ozaki.cu, launch_ozaki_slice_panels)
     double *vec = nullptr, *s1 = nullptr, *s2 = nullptr, *xchunk = nullptr, *ychunk = nullptr, *vchunk = nullptr;
     bool trained = false;
     double sigma2 = 0.0, noise = 0.0;
@@ -79,6 +85,12 @@ FactorRef fref(egx_sgp_ctx* c, int which) {
     f.qpad = which == 1 ? 0 : EGX_NB;
     f.Dinv = which == 1 ? c->Dinv1 : c->Dinv2;
     f.info = which == 1 ? c->info1 : c->info2;
+    if (which == 1 && c->Lsl1_ready) {
+        f.Lsl = c->Lsl1;
+        f.Lsc = c->Lsc1;
+        f.Lsl_off = c->Lsl1_off.data();
+        f.Lsc_off = c->Lsc1_off.data();
+    }
     return f;
 }
 
@@ -90,6 +102,10 @@ void free_sgp(egx_sgp_ctx* c) {
                       c->by, c->partial, c->tvec, c->scal, c->out, c->vec, c->s1, c->s2, c->xchunk, c->ychunk,
                       c->vchunk})
         cudaFree(p);
+    cudaFree(c->ozS);
+    cudaFree(c->ozScale);
+    cudaFree(c->Lsl1);
+    cudaFree(c->Lsc1);
     cudaFree(c->terms);
     cudaFree(c->info1);
     cudaFree(c->info2);
@@ -127,7 +143,18 @@ int sgp_evaluate(egx_sgp_ctx* c, const double* theta, double sigma2, double nois
         launch_corr_build(c->corr, c->Z, c->M, Mpad, c->d, c->terms, c->nterms, c->F1, Mpad, sigma2 + c->nugget, s,
                           sigma2);
     }
+    c->Lsl1_ready = false;
     blocked_sweep(c->env, fref(c, 1), true, nullptr, 0, 0, 0);          // U = chol(Kmm)
+    if (c->Lsl1 != nullptr) {
+        // slices of the block rows of U below every column pair: the B operand of the tcgen05 solve updates of all chunks
+        const int T = Mpad / EGX_NB;
+        for (int k = 0; k + 2 < T; k += 2) {
+            StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SLICE, 2, s);
+            launch_ozaki_slice(c->F1 + static_cast<long>(k + 2) * EGX_NB * Mpad + static_cast<long>(k) * EGX_NB, Mpad, (T - k - 2) * EGX_NB,
+                               c->Lsc1 + c->Lsc1_off[k >> 1], c->Lsl1 + c->Lsl1_off[k >> 1], s);
+        }
+        c->Lsl1_ready = true;
+    }
     const double beta_const = 1.0 / std::max(noise, c->nugget);           // vfe :796
     for (int i0 = 0; i0 < c->N; i0 += c->chunk) {
         const int mc = std::min(c->chunk, c->N - i0);
@@ -145,22 +172,41 @@ int sgp_evaluate(egx_sgp_ctx* c, const double* theta, double sigma2, double nois
                                 c->by, c->scal, s);
             launch_sgp_scale_transpose(c->Y, Mpad, mpad, Mpad, c->sqrtb, c->by, c->W, c->chunk, c->tvec, s);
         }
-        GemmArgs g;
-        g.C = c->partial;
-        g.ldc = Mpad;
-        g.A = c->W;
-        g.lda = c->chunk;
-        g.B = c->W;
-        g.ldb = c->chunk;
-        g.tri = Mpad / EGX_NB;
-        g.Mt = g.tri;
-        g.Nt = g.tri;
-        g.add = 1;
-        g.splits = SGP_SPLITS;
-        g.K = mpad / SGP_SPLITS;
-        g.split_c_stride = static_cast<long>(Mpad) * Mpad;
-        StageScope sc(c->env.prof, EGX_STAGE_SYRK_GEMM, 1, s);
-        launch_gemm_nt_sub(g, s);
+        // A += W W^T over the mpad points of the chunk (fitc :727-731 / vfe :798).  tcgen05: every K panel of 256 points is
+        // sliced into int8 digits on its own and ONE launch runs (tile, panel) tasks whose fp64 results meet in L2 through the
+        // TMA reduction (kernels_ozaki.cu, launch_ozaki_syrk_add_panels) -- no split-K partial buffers; the DMMA kernel with
+        // 4-way split-K stays for small problems and for EGX_OZAKI=0.
+        const int tri = Mpad / EGX_NB, kp = (mpad + 255) / 256;
+        bool done = false;
+        if (c->ozS != nullptr && static_cast<long>(tri) * (tri + 1) / 2 * kp >= 64) {
+            if (mpad % 256 != 0)        // the last panel is half empty: its 128 extra columns of W must be zeros
+                EGX_CUDA_TRY(cudaMemset2DAsync(c->W + mpad, static_cast<size_t>(c->chunk) * sizeof(double), 0, 128 * sizeof(double),
+                                               Mpad, s));
+            {
+                StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SLICE, 2, s);
+                launch_ozaki_slice_panels(c->W, c->chunk, Mpad, kp, c->ozScale, c->ozS, s);
+            }
+            StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SYRK, 1, s);
+            done = launch_ozaki_syrk_add_panels(c->partial, Mpad, c->ozS, c->ozScale, tri, kp, s);
+        }
+        if (!done) {
+            GemmArgs g;
+            g.C = c->partial;
+            g.ldc = Mpad;
+            g.A = c->W;
+            g.lda = c->chunk;
+            g.B = c->W;
+            g.ldb = c->chunk;
+            g.tri = Mpad / EGX_NB;
+            g.Mt = g.tri;
+            g.Nt = g.tri;
+            g.add = 1;
+            g.splits = SGP_SPLITS;
+            g.K = mpad / SGP_SPLITS;
+            g.split_c_stride = static_cast<long>(Mpad) * Mpad;
+            StageScope sc(c->env.prof, EGX_STAGE_SYRK_GEMM, 1, s);
+            launch_gemm_nt_sub(g, s);
+        }
     }
     {
         StageScope sc(c->env.prof, EGX_STAGE_GLS, 1, s);
@@ -292,6 +338,26 @@ extern "C" int egx_sgp_create(egx_sgp_ctx** out, int device, int corr, int metho
     SGP_TRY(cudaMalloc(&c->by, CH * sizeof(double)));
     SGP_TRY(cudaMalloc(&c->partial, static_cast<size_t>(SGP_SPLITS) * Mpad * Mpad * sizeof(double)));
     SGP_TRY(cudaMalloc(&c->tvec, Mpad * sizeof(double)));
+    if (c->env.ozaki && Mpad / EGX_NB >= 4) {
+        const int T = Mpad / EGX_NB;
+        long bytes = 0, rows = 0;
+        c->Lsl1_off.assign((T + 1) / 2, 0);
+        c->Lsc1_off.assign((T + 1) / 2, 0);
+        for (int k = 0; k + 2 < T; k += 2) {
+            c->Lsl1_off[k >> 1] = bytes;
+            c->Lsc1_off[k >> 1] = rows;
+            bytes += static_cast<long>(ozaki_slice_bytes(static_cast<long>(T - k - 2) * EGX_NB));
+            rows += static_cast<long>(T - k - 2) * EGX_NB;
+        }
+        SGP_TRY(cudaMalloc(&c->Lsl1, static_cast<size_t>(bytes)));
+        SGP_TRY(cudaMalloc(&c->Lsc1, static_cast<size_t>(rows) * sizeof(double)));
+        c->env.ozaki_min_tri_solve = 2;
+    }
+    if (c->env.ozaki) {
+        const int kp_max = (CH + 255) / 256;
+        SGP_TRY(cudaMalloc(&c->ozS, ozaki_slice_bytes(Mpad) * kp_max));
+        SGP_TRY(cudaMalloc(&c->ozScale, static_cast<size_t>(kp_max) * Mpad * sizeof(double)));
+    }
     SGP_TRY(cudaMalloc(&c->scal, 4 * sizeof(double)));
     SGP_TRY(cudaMalloc(&c->out, 3 * sizeof(double)));
     SGP_TRY(cudaMallocHost(&c->out_h, 3 * sizeof(double)));

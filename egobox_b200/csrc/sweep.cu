@@ -69,6 +69,7 @@ int SweepEnv::init(int max_block_cols) {
     lookahead = !(e != nullptr && atoi(e) == 0);
     if ((e = getenv("EGX_OZAKI")) != nullptr) ozaki = atoi(e);
     if ((e = getenv("EGX_OZAKI_MIN_TRI")) != nullptr) ozaki_min_tri = atoi(e) > 1 ? atoi(e) : 1;
+    ozaki_min_tri_solve = ozaki_min_tri;
     if ((e = getenv("EGX_OZAKI_MIN_T")) != nullptr) ozaki_min_T = atoi(e);
     return EGX_OK;
 }
@@ -258,7 +259,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             g.Nt = tri2;
             if (factor) {
                 trailing_syrk(env, g, sb, T, Rq ? Rq + static_cast<long>(EGX_NB) * 4 : nullptr);
-            } else if (f.Lsl != nullptr && env.ozaki && env.oz_S != nullptr && T >= env.ozaki_min_T && tri2 >= env.ozaki_min_tri &&
+            } else if (f.Lsl != nullptr && env.ozaki && env.oz_S != nullptr && T >= env.ozaki_min_T && tri2 >= env.ozaki_min_tri_solve &&
                        static_cast<long>(row_tiles) * EGX_NB <= env.p_rows) {
                 // multi-RHS solve on tcgen05: rows[:, (k+2)..] -= Pw L[(k+2).., pair]^T with the slices of L made once per
                 // model and the slices of the freshly solved rows made here

@@ -48,6 +48,8 @@ struct SweepEnv {
     int ozaki = 1;                        // EGX_OZAKI=0 keeps every update on the DMMA kernel
     int oz_persist = 0;                   // set by the batched entry point: several evaluations share the GPU
     int ozaki_min_tri = 8;                // smallest trailing tile-triangle worth the slicing pass (EGX_OZAKI_MIN_TRI)
+    int ozaki_min_tri_solve = 8;          // the same for the updates of a multi-RHS solve (row_tiles x tri2 tiles: the sparse GP
+                                          // solves 64 row tiles against 8 block columns and sets 2)
     int ozaki_min_T = 1;                  // smallest factor (block columns) that uses it at all (EGX_OZAKI_MIN_T); measured
                                           // on batches of 96: ahead of DMMA from n = 2048 (0.165 vs 0.187 ms) upwards
     int generation = 0;                   // bumped when a buffer captured in a CUDA graph is reallocated

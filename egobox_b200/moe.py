@@ -488,6 +488,10 @@ class GpMixtureParams:
             if len(chosen.theta_tunings) != k:
                 chosen.theta_tunings = [self.theta_tunings[0]]          # one tuning for all experts (gp_mix.rs:210-214)
             return chosen.fit(xt, yt)
+        # GpMixtureParams::check (moe/src/parameters.rs): one theta tuning for all experts or one per cluster
+        if len(self.theta_tunings) not in (1, self.n_clusters):
+            raise _gp.InvalidValueError("Number of theta tunings should be 1 or the number of clusters (%d), got %d"
+                                        % (self.n_clusters, len(self.theta_tunings)))
         nx = xt.shape[1]
         data = np.concatenate([xt, yt[:, None]], axis=1)
         multi = self.n_clusters > 1
@@ -525,10 +529,14 @@ class GpMixtureParams:
             factor = optimize_heaviside_factor(experts, gmx, test[:, :nx], test[:, nx])
             for e in experts:
                 e.close()
+            # moe/src/algorithm.rs:186-192: retrain with `GpMixtureParams::from(self.clone())` and the optimised factor; a mixture
+            # the caller preset (self.gmx) is kept -- train() reuses it (:118-119) -- only its heaviside factor changes
             again = GpMixtureParams()
             again.__dict__.update(self.__dict__)
             again.heaviside = factor
-            again.gmx = None
+            if self.gmx is not None:
+                preset = GaussianMixture(self.gmx.weights(), self.gmx.means(), self.gmx.covariances(), factor, self.gmx._device)
+                again.gmx = preset
             return again.fit(xt, yt)
         if self.recombination == SMOOTH and self.heaviside is not None and gmx.heaviside_factor() != self.heaviside:
             gmx.set_heaviside_factor(self.heaviside)

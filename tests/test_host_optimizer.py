@@ -172,9 +172,14 @@ def test_lbfgs_budget_inf_and_start_outside_the_box():
     assert nev == len(calls) <= 60
     # the wall is a discontinuity: a line-search method stops against it, short of the constrained optimum (0.8, 0.2)
     assert 0.7 <= x[0] <= 0.8 and math.isfinite(f) and f < fg(np.array([0.0, 1.0]))[0] and f == fg(x)[0]
-    # an infinite start gives up at once and reports it
+    # a start where the objective is +inf (a failed likelihood) probes four points towards the centre of the box before it
+    # gives up and reports +inf ...
     x, f, nev = G.bound_lbfgs_minimize(lambda z: (math.inf, np.zeros(1)), np.array([0.5]), [(0.0, 1.0)])
-    assert nev == 1 and math.isinf(f) and x[0] == 0.5
+    assert nev == 5 and math.isinf(f)
+    # ... and carries on from the first finite one: f = +inf for z > 0.8, (z - 0.3)^2 below; start at 1.0, centre 0.5
+    wall = lambda z: (math.inf, np.zeros(1)) if z[0] > 0.8 else ((z[0] - 0.3) ** 2, np.array([2.0 * (z[0] - 0.3)]))   # noqa: E731
+    x, f, nev = G.bound_lbfgs_minimize(wall, np.array([1.0]), [(0.0, 1.0)], maxeval=40)
+    assert math.isfinite(f) and abs(x[0] - 0.3) < 1e-4
 
 
 def test_multistart_reaches_the_likelihood_of_powells_cobyla():

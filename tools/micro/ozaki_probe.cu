@@ -168,7 +168,7 @@ static int check_update(int Mt, int tri, bool timing_only, int reps) {
 //   commit_each: tcgen05.commit to a dummy mbarrier after every K step; vary_addr: K step ks reads slot ks % 4
 __global__ void __launch_bounds__(128, 1) pattern_kernel(int mode, int ksteps, int commit_each, int vary_addr, int wait_each, long long* cyc) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + 8 * OZ4_SLOT_BYTES - 256);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + 8 * OZ5_HALF - 256);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 16);
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128, 1) pattern_kernel(int mode, int ksteps, i
         uint32_t ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int ks = 0; ks < ksteps; ++ks) {
             const int slot = vary_addr ? (ks & 3) : 0;
-            const uint32_t sa = oz_smem_u32(oz_smem + (2 * slot) * OZ4_SLOT_BYTES), sb = sa + OZ4_SLOT_BYTES;
+            const uint32_t sa = oz_smem_u32(oz_smem + (2 * slot) * OZ5_HALF), sb = sa + OZ5_HALF;
             const uint32_t nf = ks > 0 ? 1u : 0u;
             if (wait_each && ks >= wait_each) {          // wait for the commit of K step ks - wait_each (ring of depth wait_each)
                 const int b = (ks - wait_each) & 7;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(128, 1) pattern_kernel(int mode, int ksteps, i
 static void pattern_probe() {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * OZ4_SLOT_BYTES);
+    cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * OZ5_HALF);
     long long* d;
     cudaMalloc(&d, 256 * 8);
     long long h[256];
@@ -240,7 +240,7 @@ static void pattern_probe() {
             for (int cfg = 0; cfg < 5; ++cfg) {
                 const int commit_each = cfg >= 1, vary = cfg >= 2, wait_each = cfg == 3 ? 4 : (cfg == 4 ? 2 : 0);
                 const int ksteps = 256;
-                for (int rep = 0; rep < 2; ++rep) pattern_kernel<<<grid, 128, 8 * OZ4_SLOT_BYTES>>>(mode, ksteps, commit_each, vary, wait_each, d);
+                for (int rep = 0; rep < 2; ++rep) pattern_kernel<<<grid, 128, 8 * OZ5_HALF>>>(mode, ksteps, commit_each, vary, wait_each, d);
                 if (cudaDeviceSynchronize() != cudaSuccess) { printf("pattern: error %s\n", cudaGetErrorString(cudaGetLastError())); return; }
                 cudaMemcpy(h, d, grid * 8, cudaMemcpyDeviceToHost);
                 long long mx = 0;
@@ -320,7 +320,7 @@ __device__ __forceinline__ uint32_t ldtm_pass(uint32_t tbase) {
 // mma_mode: 0 none, 1 N = 256 MMAs into columns 256..511 (the other half), 2 N = 128 MMAs into columns 256..383
 __global__ void __launch_bounds__(384, 1) ldtm_kernel(int shape, int passes, int mma_mode, int nreaders, long long* cyc, uint32_t* sink) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + 4 * OZ4_SLOT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + 4 * OZ5_HALF);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
     volatile int* stop = reinterpret_cast<volatile int*>(tslot + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(384, 1) ldtm_kernel(int shape, int passes, int
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tslot;
     if (tid == 32 && mma_mode) {
-        const uint64_t da = oz_desc(oz_smem_u32(oz_smem)), db = oz_desc(oz_smem_u32(oz_smem + OZ4_SLOT_BYTES));
+        const uint64_t da = oz_desc(oz_smem_u32(oz_smem)), db = oz_desc(oz_smem_u32(oz_smem + OZ5_HALF));
         uint32_t n = 0;
         if (mma_mode <= 2) {
             while (!*stop) {
@@ -427,7 +427,7 @@ done:
 }
 
 static void drain_probe() {
-    cudaFuncSetAttribute(ldtm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * OZ4_SLOT_BYTES + 256);
+    cudaFuncSetAttribute(ldtm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * OZ5_HALF + 256);
     long long* d;
     uint32_t* sink;
     cudaMalloc(&d, 64);
@@ -438,7 +438,7 @@ static void drain_probe() {
         for (int shape = 4; shape < 7; ++shape) {
             const int passes = 64;
             cudaMemset(d, 0, 64);
-            for (int rep = 0; rep < 2; ++rep) ldtm_kernel<<<1, 384, 4 * OZ4_SLOT_BYTES + 256>>>(shape, passes, mma_mode, 8, d, sink);
+            for (int rep = 0; rep < 2; ++rep) ldtm_kernel<<<1, 384, 4 * OZ5_HALF + 256>>>(shape, passes, mma_mode, 8, d, sink);
             if (cudaDeviceSynchronize() != cudaSuccess) { printf("drain: error %s\n", cudaGetErrorString(cudaGetLastError())); return; }
             long long h[2];
             cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
@@ -452,7 +452,7 @@ static void drain_probe() {
 }
 
 static void ldtm_probe() {
-    cudaFuncSetAttribute(ldtm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * OZ4_SLOT_BYTES + 256);
+    cudaFuncSetAttribute(ldtm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * OZ5_HALF + 256);
     long long* d;
     uint32_t* sink;
     cudaMalloc(&d, 64);
@@ -463,7 +463,7 @@ static void ldtm_probe() {
             for (int shape = 0; shape < 4; ++shape) {
                 const int passes = 256;
                 cudaMemset(d, 0, 64);
-                for (int rep = 0; rep < 2; ++rep) ldtm_kernel<<<1, 384, 4 * OZ4_SLOT_BYTES + 256>>>(shape, passes, mma_mode, nreaders, d, sink);
+                for (int rep = 0; rep < 2; ++rep) ldtm_kernel<<<1, 384, 4 * OZ5_HALF + 256>>>(shape, passes, mma_mode, nreaders, d, sink);
                 if (cudaDeviceSynchronize() != cudaSuccess) { printf("ldtm: error %s\n", cudaGetErrorString(cudaGetLastError())); return; }
                 long long h[2];
                 cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
@@ -480,7 +480,7 @@ static void ldtm_probe() {
 // instructions of one type each (8 chains per thread); one thread of warp 1 free-runs N = 256 MMAs.
 __global__ void __launch_bounds__(384, 1) alu_kernel(int kind, int mma_on, long long* cyc, double* sink) {
     extern __shared__ __align__(1024) unsigned char oz_smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + 4 * OZ4_SLOT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(oz_smem + 4 * OZ5_HALF);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
     volatile int* stop = reinterpret_cast<volatile int*>(tslot + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(384, 1) alu_kernel(int kind, int mma_on, long 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tslot;
     if (tid == 32 && mma_on) {
-        const uint64_t da = oz_desc(oz_smem_u32(oz_smem)), db = oz_desc(oz_smem_u32(oz_smem + OZ4_SLOT_BYTES));
+        const uint64_t da = oz_desc(oz_smem_u32(oz_smem)), db = oz_desc(oz_smem_u32(oz_smem + OZ5_HALF));
         while (!*stop) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) oz_mma_n256(tmem + 256, da + (i & 3) * 256, db + (i & 1) * 512, 1u);
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(384, 1) alu_kernel(int kind, int mma_on, long 
 }
 
 static void alu_probe() {
-    cudaFuncSetAttribute(alu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * OZ4_SLOT_BYTES + 256);
+    cudaFuncSetAttribute(alu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * OZ5_HALF + 256);
     long long* d;
     double* sink;
     cudaMalloc(&d, 16 * 8);
@@ -556,7 +556,7 @@ static void alu_probe() {
         double base = 0;
         for (int mma_on = 0; mma_on < 2; ++mma_on) {
             cudaMemset(d, 0, 16 * 8);
-            for (int rep = 0; rep < 2; ++rep) alu_kernel<<<1, 384, 4 * OZ4_SLOT_BYTES + 256>>>(kind, mma_on, d, sink);
+            for (int rep = 0; rep < 2; ++rep) alu_kernel<<<1, 384, 4 * OZ5_HALF + 256>>>(kind, mma_on, d, sink);
             if (cudaDeviceSynchronize() != cudaSuccess) { printf("alu: error %s\n", cudaGetErrorString(cudaGetLastError())); return; }
             long long h[16];
             cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
