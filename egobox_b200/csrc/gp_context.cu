@@ -787,7 +787,7 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
     // more evaluations in flight pay (n = 8192: 4.04 / 4.05 / 4.02 ms at W = 4 / 6 / 8 with look-ahead, 4.08 / 3.74 /
     // 3.70 ms without -- the other evaluations hide the chain better than look-ahead does, and the whole K = 256
     // update then goes through the tcgen05 kernel in one launch)
-    int W = (c->npad <= 4096) ? 12 : (c->env.ozaki ? 8 : 4);
+    int W = (c->npad <= 4096) ? 16 : (c->env.ozaki ? 8 : 4);
     if (const char* e = getenv("EGX_BATCH_STREAMS")) W = std::max(1, atoi(e));
     static const int batch_la = getenv("EGX_BATCH_LOOKAHEAD") != nullptr ? atoi(getenv("EGX_BATCH_LOOKAHEAD")) : -1;
     W = std::min(W, B);
@@ -839,7 +839,7 @@ extern "C" int egx_gp_async_slots(egx_gp_ctx* c, int wanted) try {
     std::lock_guard<std::mutex> lk(c->mu);
     if (cudaSetDevice(c->device) != cudaSuccess) return 0;
     if (small_path_ok(c)) return 0;               // one CTA per theta: a lock-step batch is one launch, keep it
-    int W = (c->npad <= 4096) ? 12 : (c->env.ozaki ? 8 : 4);
+    int W = (c->npad <= 4096) ? 16 : (c->env.ozaki ? 8 : 4);
     if (const char* e = getenv("EGX_BATCH_STREAMS")) W = std::max(1, atoi(e));
     W = std::min(W, wanted);
     while (static_cast<int>(c->replicas.size()) < W - 1) {

@@ -65,6 +65,15 @@ __device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "memory");
     } while (!ok);
 }
+// non-blocking probe of a phase: the result comes back ~150 clk later, but nothing waits for it until it is used
+__device__ __forceinline__ uint32_t oz_mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(oz_smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok;
+}
 __device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(oz_smem_u32(bar)) : "memory");
 }
@@ -993,23 +1002,30 @@ __device__ __forceinline__ void oz5_produce(unsigned char* smem, Oz5Barriers* ba
     }
 }
 
-// MMA issue of group G of the current tile into the accumulator buffer at tmem_buf
+// MMA issue of group G of the current tile into the accumulator buffer at tmem_buf.
+// Every mbarrier wait of this thread costs ~130 clk that the tensor pipe does not hide (its queue is shallow: pattern_probe).  So
+// the full barrier of the NEXT stage use is probed (test_wait, non-blocking) BEFORE the MMAs of this one are issued -- the probe's
+// latency passes under their issue -- and the blocking wait is skipped when the probe has already seen the data (`ready`): with
+// the producers two to three stages ahead that is the normal case.
 template <int G>
-__device__ __forceinline__ void oz5_issue(unsigned char* smem, Oz5Barriers* bars, uint32_t tmem_buf, uint32_t& n, int half) {
+__device__ __forceinline__ void oz5_issue(unsigned char* smem, Oz5Barriers* bars, uint32_t tmem_buf, uint32_t& n, uint32_t& ready,
+                                          int half) {
     using Gp = Oz5Group<G>;
 #pragma unroll 1
     for (int ks0 = 0; ks0 < OZ_KSTEPS; ks0 += Gp::KPS, ++n) {
         const int nk = (OZ_KSTEPS - ks0) < Gp::KPS ? (OZ_KSTEPS - ks0) : Gp::KPS;
         const uint32_t stage = n % OZ5_STAGES, round = n / OZ5_STAGES;
         const uint32_t sa = oz_smem_u32(smem + stage * OZ5_STAGE_BYTES);
-        oz_mbar_wait(&bars->full[stage], round & 1);
+        if (!ready) oz_mbar_wait(&bars->full[stage], round & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t next_ok = oz_mbar_test(&bars->full[(n + 1) % OZ5_STAGES], ((n + 1) / OZ5_STAGES) & 1);
 #pragma unroll 1
         for (int j = 0; j < nk; ++j) {
             const uint32_t a = sa + j * (Gp::D * OZ_SLICE_STEP_BYTES);
             oz_issue_kstep<Gp::W0, Gp::NW, OZ_SLICE_STEP_BYTES, false>(tmem_buf, a, a + OZ5_HALF, (ks0 + j) > 0 ? 1u : 0u, half);
         }
         oz_umma_commit(&bars->empty[stage]);
+        ready = next_ok;
     }
 }
 
@@ -1145,27 +1161,27 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiA
             }
         } else if (warp == 1 && lane == 0) {
             // ===== MMA issuer: groups 0, 2 -> buffer X, groups 1, 3 -> buffer Y; use u of a buffer waits for the drain of use u - 1 =====
-            uint32_t n = 0, u = 0;                            // stage uses; uses of EACH buffer so far (both advance together)
+            uint32_t n = 0, u = 0, ready = 0;                 // stage uses; uses of EACH buffer so far (both advance together)
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const bool t1 = tile == static_cast<int>(blockIdx.x + gridDim.x);
                 if (u > 0) { oz_mbar_wait(&bars->acc_empty[0], (u - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
                 if (t1) OZ_STAMP(20);
-                oz5_issue<0>(oz_smem, bars, tmem, n, xp & 1);
+                oz5_issue<0>(oz_smem, bars, tmem, n, ready, xp & 1);
                 oz_umma_commit(&bars->acc_full[0]);
                 if (u > 0) { oz_mbar_wait(&bars->acc_empty[1], (u - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
                 if (t1) OZ_STAMP(21);
-                oz5_issue<1>(oz_smem, bars, tmem + 256, n, xp & 1);
+                oz5_issue<1>(oz_smem, bars, tmem + 256, n, ready, xp & 1);
                 oz_umma_commit(&bars->acc_full[1]);
                 ++u;
                 oz_mbar_wait(&bars->acc_empty[0], (u - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (t1) OZ_STAMP(22);
-                oz5_issue<2>(oz_smem, bars, tmem, n, xp & 1);
+                oz5_issue<2>(oz_smem, bars, tmem, n, ready, xp & 1);
                 oz_umma_commit(&bars->acc_full[0]);
                 oz_mbar_wait(&bars->acc_empty[1], (u - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (t1) OZ_STAMP(23);
-                oz5_issue<3>(oz_smem, bars, tmem + 256, n, xp & 1);
+                oz5_issue<3>(oz_smem, bars, tmem + 256, n, ready, xp & 1);
                 oz_umma_commit(&bars->acc_full[1]);
                 ++u;
                 if (t1) OZ_STAMP(24);
@@ -1199,6 +1215,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiA
                 hiB[j][0] = oz5_scale_hi(rsB + 8 * j);
                 hiB[j][1] = oz5_scale_hi(rsB + 8 * j + 1);
             }
+            // (prefetching the C tile into L2 at this point was measured: 0.182 vs 0.178 ms -- the reductions do not wait for it)
             long long T[2][2][8][2];                         // this thread's entries, [rh][row r_in / +8][j][column parity]
 #pragma unroll
             for (int grp = 0; grp < OZ5_GROUPS; ++grp) {
@@ -1257,10 +1274,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_syrk5_kernel(const OzakiA
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
                     if (chalf == 0 && lane == 0 && !(xp & 16)) {
-                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                                         reinterpret_cast<uint64_t>(&cmap)),
-                                     "r"(oz_smem_u32(stg)), "r"(tc * 128), "r"(tr * 128 + 32 * quarter + 16 * rh + 8 * h)
-                                     : "memory");
+                        if (xp & 32) {      // timing experiment (probe builds): a plain TMA store instead of the reduction
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(&cmap)),
+                                         "r"(oz_smem_u32(stg)), "r"(tc * 128), "r"(tr * 128 + 32 * quarter + 16 * rh + 8 * h)
+                                         : "memory");
+                        } else {
+                            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(&cmap)),
+                                         "r"(oz_smem_u32(stg)), "r"(tc * 128), "r"(tr * 128 + 32 * quarter + 16 * rh + 8 * h)
+                                         : "memory");
+                        }
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
