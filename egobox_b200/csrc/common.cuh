@@ -82,6 +82,7 @@ void launch_mean_basis_rows(const double* X, int n, int npad, int d, const int* 
                             cudaStream_t s);
 // kernels_chol.cu
 void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* Dinv, cudaStream_t s);
+void launch_diag_tile_update(double* C, long ldc, const double* A, long lda, int K /* 128 or 256 */, cudaStream_t s);
 void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, long ldp,
                       int nblocks64, cudaStream_t s, double* rmaxq = nullptr /* optional [row][4] quarter-row max |x|, see kernels_ozaki.cu */);
 void launch_gemm_nt_sub(const GemmArgs& g, cudaStream_t s);
@@ -99,6 +100,7 @@ void launch_ozaki_gemm(double* C, long ldc, const int8_t* SA, const double* rsA,
 // kernels_solve.cu
 void launch_gls(const double* M, long ld, int n, int npad, int p, double* work, double* G,
                 double* beta, double* rho, EvalResult* res, const int* info, cudaStream_t s);
+void launch_backsolve_chain(const double* L, long ld, const double* Dinv, int T, double* v, int* flags, cudaStream_t s);
 void launch_backsolve_diag(const double* Lkk, long ld, double* rho_k, cudaStream_t s);
 void launch_backsolve_update(const double* Lrow, long ld, const double* gamma_k, double* rho, int ncolblocks,
                              cudaStream_t s);

@@ -436,7 +436,7 @@ constexpr int PREDICT_CHUNK = 8192;
 int ensure_L_slices(egx_gp_ctx* c) {
     if (c->Lslices_ready) return EGX_OK;
     const int T = c->npad / EGX_NB;
-    if (!c->env.ozaki || T < c->env.ozaki_min_T || T - 2 < c->env.ozaki_min_tri) return EGX_OK;
+    if (!c->env.ozaki || T < c->env.ozaki_min_T || T - 2 < c->env.ozaki_min_tri_solve) return EGX_OK;
     if (c->Lsl == nullptr) {
         long bytes = 0, rows = 0;
         c->Lsl_off.assign((T + 1) / 2, 0);
@@ -452,7 +452,7 @@ int ensure_L_slices(egx_gp_ctx* c) {
     }
     for (int k = 0; k + 2 < T; k += 2) {
         const int rows_k = (T - k - 2) * EGX_NB;
-        if (rows_k / EGX_NB < c->env.ozaki_min_tri) break;
+        if (rows_k / EGX_NB < c->env.ozaki_min_tri_solve) break;
         StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SLICE, 2, c->stream);
         launch_ozaki_slice(c->M + static_cast<long>(k + 2) * EGX_NB * c->ld + static_cast<long>(k) * EGX_NB, c->ld, rows_k,
                            c->Lsc + c->Lsc_off[k >> 1], c->Lsl + c->Lsl_off[k >> 1], c->stream);
@@ -817,7 +817,7 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
             w->env.oz_persist = (W > 1) ? 1 : 0;
             const bool la_saved = w->env.lookahead;
             if (batch_la >= 0) w->env.lookahead = la_saved && batch_la != 0;
-            else if (W >= 6 && w->env.ozaki && c->npad > 4096) w->env.lookahead = false;
+            else if (W >= 6 && w->env.ozaki && (c->npad > 4096 || c->npad <= 2048)) w->env.lookahead = false;   // measured r02 (y3 / y4): C5 n = 2048 72 -> 66 ms, n = 4096 expert fit 1.91 -> 2.05 ms per evaluation
             status[b] = evaluate_launch(w, thetas + static_cast<long>(b) * c->h);
             w->env.lookahead = la_saved;
             if (status[b] == EGX_CUDA_ERROR) return EGX_CUDA_ERROR;
@@ -880,7 +880,7 @@ extern "C" int egx_gp_eval_begin(egx_gp_ctx* c, int slot, const double* theta) t
     w->env.oz_persist = (W > 1) ? 1 : 0;
     const bool la_saved = w->env.lookahead;
     if (batch_la >= 0) w->env.lookahead = la_saved && batch_la != 0;
-    else if (W >= 6 && w->env.ozaki && c->npad > 4096) w->env.lookahead = false;
+    else if (W >= 6 && w->env.ozaki && (c->npad > 4096 || c->npad <= 2048)) w->env.lookahead = false;   // measured r02 (y3 / y4): C5 n = 2048 72 -> 66 ms, n = 4096 expert fit 1.91 -> 2.05 ms per evaluation
     const int st = evaluate_launch(w, theta);
     w->env.lookahead = la_saved;
     return st;

@@ -135,20 +135,6 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
     }
 }
 
-// ---------------------------------------------------------------------------
-// K5: X (64 x 128 slab, in place) <- X * L^-T with L = 128 x 128 lower block, blocked by
-// 32 columns on the FP64 tensor pipe:
-//   for b = 0..3:  T   = X_b - sum_{b' < b} X_b' * L[b, b']^T      (DMMA, K = 32 b)
-//                  X_b = T * Dinv_b^T                               (DMMA, K = 32)
-// Dinv_b are the inverted 32 x 32 diagonal sub-blocks produced by K3 (the standard blocked
-// TRSM of GPU BLAS libraries).  Also emits the contiguous panel copy P used by K4.
-// 256 threads = 8 warps as 4 (rows) x 2 (cols), warp tile 16 x 16 of the 64 x 32 output.
-// ---------------------------------------------------------------------------
-constexpr int TR_ROWS = 64;
-constexpr int TR_LDX = 132;   // (4 g + t) mod 16 distinct -> conflict-free fragment loads
-constexpr int TR_LDL = 100;   // 96 columns of one 32-row block of L (+4 pad)
-constexpr int TR_LDD = 36;
-
 __device__ __forceinline__ void dmma884_t(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
@@ -160,23 +146,296 @@ __device__ __forceinline__ void tr_cp_async16(void* smem_dst, const void* gsrc) 
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-// Shared memory: X slab 64 x 132 (67.6 KB) + the four Dinv blocks (36.9 KB) + ONE 32-row block of L
-// (32 x 100, 25.6 KB, re-staged per block step) = 130 KB, so that a solve CTA can share an SM with a
-// CTA of the trailing-update kernel (92 KB) instead of waiting for the whole SM to drain.
+// ---------------------------------------------------------------------------
+// K3 (r02 form): the same 128 x 128 factorisation with the latency chain taken out of the CTA-wide barriers.
+// The tile sits in shared memory; it is factorised in four 32-column block steps:
+//   column phase (no CTA barrier): warp w < 3 - b holds, one row per lane, the 32 x 32 diagonal block (every warp
+//     its own copy, symmetric storage) AND the 32 rows of panel block w below it.  Per column: the pivot is
+//     shuffled from its lane, every lane scales its entries with rsqrt(pivot), the scaled column goes through a
+//     warp-private 32-entry shared vector and the rank-1 update of diagonal block and panel rows runs out of
+//     registers.  The dependent chain of a column is shuffle + rsqrt + DMUL + DFMA (~120 clk against ~650 clk of the
+//     barrier form), the panel rows ride in its issue bubbles, so the in-tile panel solve needs no inverse.
+//   update phase: the trailing (96 - 32 b)^2 lower triangle -= X X^T (K = 32) on the FP64 tensor pipe, 16 x 16
+//     macro tiles over the 8 warps.
+// Warp 4 inverts the previous 32 x 32 diagonal block (for K5) while the other warps are in the column phase.
+// ---------------------------------------------------------------------------
+constexpr int P2_LD = 132;     // (4 g + t) mod 16 distinct: conflict-free DMMA fragment loads
+#ifdef POTRF_TIMING             // tools/micro/potrf_probe.cu: clock stamps of the phases of one launch
+__device__ long long potrf_dbg[32];
+#define POTRF_STAMP(i) do { if ((threadIdx.x & 31) == 0) potrf_dbg[i] = clock64(); } while (0)
+#else
+#define POTRF_STAMP(i) do { } while (0)
+#endif
+
+// y ~ d^-1/2 to fp64 accuracy: MUFU.RSQ64H seed (2^-22) + one third-order step (e^3 term ~ 2^-67), 4 dependent
+// fp64 operations instead of the ~7 of rsqrt()
+__device__ __forceinline__ double potrf_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double t = d * y;
+    const double e = fma(-t, y, 1.0);              // 1 - d y^2
+    const double pc = fma(0.375, e, 0.5);          // 1/2 + 3/8 e
+    const double ye = y * e;
+    return fma(ye, pc, y);                         // y (1 + e/2 + 3 e^2/8)
+}
+
+template <bool PANEL>
+__device__ __forceinline__ void potrf32_columns(double (&a)[32], double (&p)[32], double dg, double* lb, int lane,
+                                                int& fail_col) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const double d = __shfl_sync(0xffffffffu, dg, j);
+        if (!(d > 0.0) && fail_col < 0) fail_col = j;       // uniform over the warp
+#ifdef POTRF_LIBRSQRT
+        const double rs = rsqrt(d);
+#else
+        const double rs = potrf_rsqrt(d);
+#endif
+        const double l = a[j] * rs;                          // lane j: d * rs = sqrt(d)
+        a[j] = l;
+        double lp = 0.0;
+        if (PANEL) {
+            lp = p[j] * rs;
+            p[j] = lp;
+        }
+        dg = fma(-l, l, dg);                                 // the lane's own diagonal entry: no round trip on the chain
+        if (j < 31) {
+            double* buf = lb + (j & 1) * 32;
+            buf[lane] = l;
+            __syncwarp();
+            if (((j + 1) & 1) != 0) {
+                const double lk = buf[j + 1];
+                a[j + 1] = fma(-l, lk, a[j + 1]);
+                if (PANEL) p[j + 1] = fma(-lp, lk, p[j + 1]);
+            }
+#pragma unroll
+            for (int k = (j + 2) & ~1; k < 32; k += 2) {
+                const double2 lk = *reinterpret_cast<const double2*>(buf + k);
+                a[k] = fma(-l, lk.x, a[k]);
+                a[k + 1] = fma(-l, lk.y, a[k + 1]);
+                if (PANEL) {
+                    p[k] = fma(-lp, lk.x, p[k]);
+                    p[k + 1] = fma(-lp, lk.y, p[k + 1]);
+                }
+            }
+        }
+    }
+}
+
+// inverse of the 32 x 32 lower block at Sb (leading dimension P2_LD): lane c solves L x = e_c by forward substitution
+// (componentwise accurate; a blocked form X21 = -C^-1 B A^-1 on four warps was 2x faster and lost the ill-conditioned
+// band test -- cond(R) ~ 1e15 -- to its larger error, profiles/r02/y3_potrf_probe.txt).  Row i of L is read as
+// 16-byte broadcast loads; two partial sums, the term of x[i-1] -- the only one on the dependent chain of the rows -- last.
+__device__ __forceinline__ void potrf_invert32(const double* Sb, double* __restrict__ Do, int lane) {
+    const double myrd = 1.0 / Sb[lane * P2_LD + lane];
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j + 1 <= i - 2; j += 2) {       // pairs (j, j+1) below the last term
+            const double2 lv = *reinterpret_cast<const double2*>(&Sb[i * P2_LD + j]);
+            s0 = fma(-lv.x, x[j], s0);
+            s1 = fma(-lv.y, x[j + 1], s1);
+        }
+        if (i >= 2 && ((i - 1) & 1)) s0 = fma(-Sb[i * P2_LD + i - 2], x[i - 2], s0);   // odd count of terms below i-1: the last single
+        double sacc = s0 + s1;
+        if (i >= 1) sacc = fma(-Sb[i * P2_LD + i - 1], x[i - 1], sacc);
+        x[i] = sacc * __shfl_sync(0xffffffffu, myrd, i);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) Do[i * 32 + lane] = x[i];
+}
+
+__global__ void __launch_bounds__(256, 1) potrf_diag2_kernel(double* __restrict__ A, long ld, int* __restrict__ info,
+                                                             int base_index, double* __restrict__ Dinv) {
+    extern __shared__ __align__(16) double psm[];
+    double* S = psm;                                   // [128][P2_LD]
+    double* lbuf = psm + EGX_NB * P2_LD;               // [4 warps][2][32]
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    // lower triangle of the tile -> shared memory (16-byte chunks that touch columns <= row)
+    for (int e = tid; e < EGX_NB * 64; e += 256) {
+        const int r = e >> 6, ch = e & 63;
+        if (ch * 2 <= r) tr_cp_async16(&S[r * P2_LD + ch * 2], A + static_cast<long>(r) * ld + ch * 2);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (tid == 0) POTRF_STAMP(0);
+    __syncthreads();
+    if (tid == 0) POTRF_STAMP(1);
+
+    int fail_col = -1;
+#pragma unroll 1
+    for (int b = 0; b < 4; ++b) {
+        const int c0 = 32 * b;
+        const int npanel = 3 - b;
+        if (warp < npanel || warp == 0) {
+            double a[32], p[32];
+            // diagonal block, symmetric: entry (lane, k) from the stored lower triangle
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int hi = lane > k ? lane : k, lo = lane > k ? k : lane;
+                a[k] = S[(c0 + hi) * P2_LD + c0 + lo];
+            }
+            const double dg = S[(c0 + lane) * P2_LD + c0 + lane];
+            double* lb = lbuf + warp * 64;
+            if (tid == 0) POTRF_STAMP(2 + 4 * b);     // registers loaded (diagonal block)
+#ifdef POTRF_ONE_INST
+            if (true) {
+                const int prow = warp < npanel ? c0 + 32 * (warp + 1) + lane : c0 + lane;   // b = 3: a second copy of the diagonal rows
+                const double* pr = &S[prow * P2_LD + c0];
+#else
+            if (warp < npanel) {
+                const int prow = c0 + 32 * (warp + 1) + lane;
+                const double* pr = &S[prow * P2_LD + c0];
+#endif
+#pragma unroll
+                for (int k = 0; k < 32; k += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(pr + k);
+                    p[k] = v.x;
+                    p[k + 1] = v.y;
+                }
+                int fc = -1;
+                potrf32_columns<true>(a, p, dg, lb, lane, fc);
+                if (fail_col < 0 && fc >= 0) fail_col = c0 + fc;
+                if (tid == 0) POTRF_STAMP(3 + 4 * b);  // columns done
+                if (warp < npanel) {
+                    double* pw = &S[prow * P2_LD + c0];
+#pragma unroll
+                    for (int k = 0; k < 32; k += 2) *reinterpret_cast<double2*>(pw + k) = make_double2(p[k], p[k + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) p[k] = 0.0;
+                int fc = -1;
+                potrf32_columns<false>(a, p, dg, lb, lane, fc);
+                if (fail_col < 0 && fc >= 0) fail_col = c0 + fc;
+                if (tid == 0) POTRF_STAMP(3 + 4 * b);
+            }
+            if (warp == 0) {
+                // entries right of the diagonal are scratch: nothing reads the upper triangle of S
+                double* dw = &S[(c0 + lane) * P2_LD + c0];
+#pragma unroll
+                for (int k = 0; k < 32; k += 2) *reinterpret_cast<double2*>(dw + k) = make_double2(a[k], a[k + 1]);
+            }
+        } else if (warp == 4 && b > 0) {
+            potrf_invert32(&S[(c0 - 32) * P2_LD + c0 - 32], Dinv + (b - 1) * 1024, lane);
+        }
+        __syncthreads();
+        if (tid == 0) POTRF_STAMP(4 + 4 * b);          // column phase over for the CTA (incl. the inverse of the previous block)
+        if (b == 3) break;
+        // trailing update: rows / columns c0 + 32 .. 127, lower triangle in 16 x 16 macro tiles
+        const int t0 = c0 + 32;
+        const int nt = (EGX_NB - t0) / 16;
+        const int ntile = nt * (nt + 1) / 2;
+        const int gid = lane >> 2, tig = lane & 3;
+        for (int t = warp; t < ntile; t += 8) {
+            int tr = 0;
+            while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+            const int tc = t - tr * (tr + 1) / 2;
+            const int r0 = t0 + 16 * tr, q0 = t0 + 16 * tc;
+            double acc[2][2][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    const double2 v = *reinterpret_cast<const double2*>(&S[(r0 + mi * 8 + gid) * P2_LD + q0 + ni * 8 + 2 * tig]);
+                    acc[mi][ni][0] = v.x;
+                    acc[mi][ni][1] = v.y;
+                }
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 4) {
+                double af[2], bf[2];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) af[mi] = -S[(r0 + mi * 8 + gid) * P2_LD + c0 + k0 + tig];
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) bf[ni] = S[(q0 + ni * 8 + gid) * P2_LD + c0 + k0 + tig];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni)
+                    *reinterpret_cast<double2*>(&S[(r0 + mi * 8 + gid) * P2_LD + q0 + ni * 8 + 2 * tig]) =
+                        make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+        __syncthreads();
+        if (tid == 0) POTRF_STAMP(5 + 4 * b);          // trailing update done
+    }
+    // LAPACK dpotrf: 1-based index of the first non-positive (or NaN) pivot; warp 0 saw every pivot
+    if (tid == 0 && fail_col >= 0) atomicCAS(info, 0, base_index + fail_col + 1);
+    if (warp == 4) {
+        potrf_invert32(&S[96 * P2_LD + 96], Dinv + 3 * 1024, lane);
+        POTRF_STAMP(20);
+        return;
+    }
+    // lower triangle back to the matrix: 7 warps, 8 chunks of 16 bytes in flight per thread
+    {
+        const int wt = warp < 4 ? tid : tid - 32;       // 0 .. 223
+        for (int e0 = 0; e0 < EGX_NB * 64; e0 += 224 * 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * 224 + wt;
+                const int r = e >> 6, c = (e & 63) * 2;
+                if (e < EGX_NB * 64 && c <= r) v[u] = *reinterpret_cast<const double2*>(&S[r * P2_LD + c]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * 224 + wt;
+                const int r = e >> 6, c = (e & 63) * 2;
+                if (e < EGX_NB * 64) {
+                    if (c < r) *reinterpret_cast<double2*>(A + static_cast<long>(r) * ld + c) = v[u];
+                    else if (c == r) A[static_cast<long>(r) * ld + c] = v[u].x;
+                }
+            }
+        }
+    }
+    if (tid == 0) POTRF_STAMP(21);
+}
+
+// ---------------------------------------------------------------------------
+// K5: X (64 x 128 slab, in place) <- X * L^-T with L = 128 x 128 lower block, blocked by
+// 32 columns on the FP64 tensor pipe:
+//   for b = 0..3:  T   = X_b - sum_{b' < b} X_b' * L[b, b']^T      (DMMA, K = 32 b)
+//                  X_b = T * Dinv_b^T                               (DMMA, K = 32)
+// Dinv_b are the inverted 32 x 32 diagonal sub-blocks produced by K3 (the standard blocked
+// TRSM of GPU BLAS libraries).  Also emits the contiguous panel copy P used by K4.
+// 256 threads = 8 warps as 4 (rows) x 2 (cols), warp tile 16 x 16 of the 64 x 32 output.
+// ---------------------------------------------------------------------------
+constexpr int TR_LDX = 132;   // (4 g + t) mod 16 distinct -> conflict-free fragment loads
+constexpr int TR_LDL = 100;   // 96 columns of one 32-row block of L (+4 pad)
+constexpr int TR_LDD = 36;
+
+// Shared memory: X slab ROWS x 132 + the four Dinv blocks (36.9 KB) + the 96 rows of L below its first diagonal
+// sub-block (96 x 100, 76.8 KB) -- everything is staged ONCE at the start (r01 re-staged one 32-row block of L per
+// block step to stay under 130 KB beside a 92 KB update CTA; the r02 update kernel fills an SM on its own, and the three
+// exposed global round trips cost ~3 us of a kernel on the serial chain).
+// ROWS = 64: 8 warps as 4 x 2, warp tile 16 x 16.  ROWS = 32 (chosen when the 32-row slabs still fit in one wave):
+// 8 warps as 2 x 4, warp tile 16 x 8 -- half the FP64 work per CTA on the chain.
+template <int ROWS>
 __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, long ldx,
                                                         const double* __restrict__ L, long ldl,
                                                         const double* __restrict__ Dinv,
                                                         double* __restrict__ P, long ldp,
                                                         double* __restrict__ rmaxq) {
+    constexpr int WN = (ROWS == 64) ? 2 : 4;      // warps along the 32 output columns of a block step
+    constexpr int NI = 4 / WN;                    // n8 tiles per warp
+    constexpr int NW = 8 * NI;                    // output columns per warp
     extern __shared__ __align__(16) double sm[];
-    double* Xs = sm;                              // [64][132]
-    double* Ds = Xs + TR_ROWS * TR_LDX;           // [4][32][36]
-    double* Lb = Ds + 4 * 32 * TR_LDD;            // [32][100] rows of block b, columns 0..32b-1
+    double* Xs = sm;                              // [ROWS][132]
+    double* Ds = Xs + ROWS * TR_LDX;              // [4][32][36]
+    double* Lb = Ds + 4 * 32 * TR_LDD;            // [96][100]: rows 32 .. 127 of L, columns 0 .. 32 (row / 32) - 1
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    double* Xg = X + static_cast<long>(blockIdx.x) * TR_ROWS * ldx;
+    double* Xg = X + static_cast<long>(blockIdx.x) * ROWS * ldx;
 
-    for (int e = tid; e < TR_ROWS * 64; e += 256) {
+    for (int e = tid; e < ROWS * 64; e += 256) {
         const int r = e >> 6, ch = e & 63;
         tr_cp_async16(&Xs[r * TR_LDX + ch * 2], Xg + static_cast<long>(r) * ldx + ch * 2);
     }
@@ -184,72 +443,71 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
         const int b = e >> 9, r = (e >> 4) & 31, ch = e & 15;
         tr_cp_async16(&Ds[(b * 32 + r) * TR_LDD + ch * 2], Dinv + e * 2);
     }
+    for (int e = tid; e < 96 * 48; e += 256) {
+        const int r = e / 48, ch = e - r * 48;     // row 32 + r of L, 16-byte chunk ch
+        if (ch < 16 * (1 + (r >> 5))) tr_cp_async16(&Lb[r * TR_LDL + ch * 2], L + static_cast<long>(32 + r) * ldl + ch * 2);
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 
-    const int wm = warp >> 1, wn = warp & 1;
+    const int wm = warp / WN, wn = warp % WN;
     const int gid = lane >> 2, tig = lane & 3;
     const int row0 = wm * 16;        // rows of this warp inside the slab
 #pragma unroll 1
     for (int b = 0; b < 4; ++b) {
-        // stage L[32b .. 32b+31][0 .. 32b-1] (16 b chunks of 16 bytes per row)
-        for (int e = tid; e < 32 * 16 * b; e += 256) {
-            const int r = e / (16 * b), ch = e - r * (16 * b);
-            tr_cp_async16(&Lb[r * TR_LDL + ch * 2], L + static_cast<long>(32 * b + r) * ldl + ch * 2);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        const int col0 = b * 32 + wn * 16;          // output columns of this warp
-        double acc[2][2][2];
+        const int col0 = b * 32 + wn * NW;          // output columns of this warp
+        double acc[2][NI][2];
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) {
+            for (int ni = 0; ni < NI; ++ni) {
                 const double2 v = *reinterpret_cast<const double2*>(&Xs[(row0 + mi * 8 + gid) * TR_LDX + col0 + ni * 8 + 2 * tig]);
                 acc[mi][ni][0] = v.x;
                 acc[mi][ni][1] = v.y;
             }
         // T = X_b - X[:, 0:32b] * L[b-block rows, 0:32b]^T
+        const double* Lrow = Lb + ((b - 1) * 32 + wn * NW + gid) * TR_LDL + tig;
         for (int k0 = 0; k0 < 32 * b; k0 += 4) {
-            double af[2], bf[2];
+            double af[2], bf[NI];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) af[mi] = -Xs[(row0 + mi * 8 + gid) * TR_LDX + k0 + tig];
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) bf[ni] = Lb[(wn * 16 + ni * 8 + gid) * TR_LDL + k0 + tig];
+            for (int ni = 0; ni < NI; ++ni) bf[ni] = Lrow[ni * 8 * TR_LDL + k0];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                for (int ni = 0; ni < NI; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni)
+            for (int ni = 0; ni < NI; ++ni)
                 *reinterpret_cast<double2*>(&Xs[(row0 + mi * 8 + gid) * TR_LDX + col0 + ni * 8 + 2 * tig]) =
                     make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-        __syncthreads();        // T is visible; every warp is done with Lb
+        __syncthreads();        // T is visible
         // X_b = T * Dinv_b^T
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int ni = 0; ni < NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 #pragma unroll
         for (int k0 = 0; k0 < 32; k0 += 4) {
-            double af[2], bf[2];
+            double af[2], bf[NI];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi) af[mi] = Xs[(row0 + mi * 8 + gid) * TR_LDX + b * 32 + k0 + tig];
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni) bf[ni] = Ds[(b * 32 + wn * 16 + ni * 8 + gid) * TR_LDD + k0 + tig];
+            for (int ni = 0; ni < NI; ++ni) bf[ni] = Ds[(b * 32 + wn * NW + ni * 8 + gid) * TR_LDD + k0 + tig];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                for (int ni = 0; ni < 2; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                for (int ni = 0; ni < NI; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
         __syncthreads();        // all reads of T done before it is overwritten by X_b
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni)
+            for (int ni = 0; ni < NI; ++ni)
                 *reinterpret_cast<double2*>(&Xs[(row0 + mi * 8 + gid) * TR_LDX + col0 + ni * 8 + 2 * tig]) =
                     make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         __syncthreads();        // X_b visible to the next block step
@@ -257,8 +515,8 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
     // panel copy for the trailing update: 128 columns of a (rows x ldp) buffer (ldp = 256: two panels side by side)
     // rmaxq (optional): max |x| of every 64-column quarter of the solved rows, [row][2] at the caller's offset -- the
     // row scales of the int8 slicing (kernels_ozaki.cu) then need no extra pass over the panel
-    double* Pg = (P != nullptr) ? P + static_cast<long>(blockIdx.x) * TR_ROWS * ldp : nullptr;
-    for (int e = tid; e < TR_ROWS * 64; e += 256) {
+    double* Pg = (P != nullptr) ? P + static_cast<long>(blockIdx.x) * ROWS * ldp : nullptr;
+    for (int e = tid; e < ROWS * 64; e += 256) {
         const int r = e >> 6, ch = e & 63;        // a warp covers 64 consecutive columns of one row
         const double2 v = *reinterpret_cast<const double2*>(&Xs[r * TR_LDX + ch * 2]);
         *reinterpret_cast<double2*>(Xg + static_cast<long>(r) * ldx + ch * 2) = v;
@@ -267,7 +525,7 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
             double mx = fmax(fabs(v.x), fabs(v.y));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (lane == 0) rmaxq[(static_cast<long>(blockIdx.x) * TR_ROWS + r) * 4 + (ch >> 5)] = mx;
+            if (lane == 0) rmaxq[(static_cast<long>(blockIdx.x) * ROWS + r) * 4 + (ch >> 5)] = mx;
         }
     }
 }
@@ -525,27 +783,126 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
         }
 }
 
+// ---------------------------------------------------------------------------
+// Diagonal tile ahead of its column (look-ahead schedule of sweep.cu): C(128 x 128, lower 32 x 32 sub-tiles)
+// -= A A^T with A = 128 x K panel rows (K = 128 or 256).  A whole 128 x 64 tile of K4 occupies one SM for
+// 128*64*K / 64 clk (17 us at K = 256) -- too long for the serial panel chain -- so the tile is cut into its ten
+// lower 32 x 32 sub-tiles, one CTA each, the 8 warps of a CTA splitting K (fixed-order reduction through shared
+// memory: bit-reproducible).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) diag_tile_update_kernel(double* __restrict__ C, long ldc,
+                                                               const double* __restrict__ A, long lda, int K) {
+    extern __shared__ __align__(16) double dsm[];      // [8 warps][1024]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gid = lane >> 2, tig = lane & 3;
+    int sr = 0;
+    while ((sr + 1) * (sr + 2) / 2 <= static_cast<int>(blockIdx.x)) ++sr;
+    const int sc = static_cast<int>(blockIdx.x) - sr * (sr + 1) / 2;
+    const int kw = K / 8;                               // K range of this warp
+    const double* Ar = A + static_cast<long>(32 * sr + gid) * lda + warp * kw + tig;
+    const double* Ac = A + static_cast<long>(32 * sc + gid) * lda + warp * kw + tig;
+    double acc[4][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll 4
+    for (int k0 = 0; k0 < kw; k0 += 4) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) af[mi] = Ar[static_cast<long>(mi) * 8 * lda + k0];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bf[ni] = Ac[static_cast<long>(ni) * 8 * lda + k0];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+    double* mine = dsm + warp * 1024;
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+            *reinterpret_cast<double2*>(mine + ((mi * 4 + ni) * 32 + lane) * 2) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+    __syncthreads();
+    for (int q = tid; q < 512; q += 256) {
+        const int t = q >> 5, l = q & 31;
+        const int row = 32 * sr + (t >> 2) * 8 + (l >> 2), col = 32 * sc + (t & 3) * 8 + 2 * (l & 3);
+        double2 sum = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const double2 v = *reinterpret_cast<const double2*>(dsm + w * 1024 + q * 2);
+            sum.x += v.x;
+            sum.y += v.y;
+        }
+        double2* cp = reinterpret_cast<double2*>(C + static_cast<long>(row) * ldc + col);
+        double2 c = *cp;
+        c.x -= sum.x;
+        c.y -= sum.y;
+        *cp = c;
+    }
+}
+
 }  // namespace
 
 int gemm_smem_bytes() { return 3 * (EGX_NB + 128) * 20 * static_cast<int>(sizeof(double)); }
 
 void launch_potrf_diag(double* Akk, long ld, int* info, int base_index, double* Dinv, cudaStream_t s) {
-    potrf_diag_kernel<<<1, 256, 0, s>>>(Akk, ld, info, base_index, Dinv);
+    // EGX_POTRF_V=1: the r01 kernel (CTA-wide barrier per column), kept for A/B
+    static const int version = getenv("EGX_POTRF_V") != nullptr ? atoi(getenv("EGX_POTRF_V")) : 2;
+    if (version == 1) {
+        potrf_diag_kernel<<<1, 256, 0, s>>>(Akk, ld, info, base_index, Dinv);
+        return;
+    }
+    static bool configured_dev[64] = {false};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& configured = configured_dev[dev_ & 63];
+    const int smem = (EGX_NB * P2_LD + 4 * 64) * static_cast<int>(sizeof(double));
+    if (!configured) {
+        cudaFuncSetAttribute(potrf_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    potrf_diag2_kernel<<<1, 256, smem, s>>>(Akk, ld, info, base_index, Dinv);
+}
+
+void launch_diag_tile_update(double* C, long ldc, const double* A, long lda, int K, cudaStream_t s) {
+    static bool configured_dev[64] = {false};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& configured = configured_dev[dev_ & 63];
+    const int smem = 8 * 1024 * static_cast<int>(sizeof(double));
+    if (!configured) {
+        cudaFuncSetAttribute(diag_tile_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    diag_tile_update_kernel<<<10, 256, smem, s>>>(C, ldc, A, lda, K);
 }
 
 void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, long ldp,
                       int nblocks64, cudaStream_t s, double* rmaxq) {
     static bool configured_dev[64] = {false};
+    static int sms_dev[64] = {0};
     int dev_ = 0;
     cudaGetDevice(&dev_);
     bool& configured = configured_dev[dev_ & 63];   // the attribute is per device (one process may drive several)
-    const int smem = (TR_ROWS * TR_LDX + 4 * 32 * TR_LDD + 32 * TR_LDL) * sizeof(double);
+    constexpr int smem_fixed = (4 * 32 * TR_LDD + 96 * TR_LDL) * static_cast<int>(sizeof(double));
+    constexpr int smem64 = 64 * TR_LDX * static_cast<int>(sizeof(double)) + smem_fixed;
+    constexpr int smem32 = 32 * TR_LDX * static_cast<int>(sizeof(double)) + smem_fixed;
     if (!configured) {
-        cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(trsm_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
+        cudaFuncSetAttribute(trsm_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+        cudaDeviceGetAttribute(&sms_dev[dev_ & 63], cudaDevAttrMultiProcessorCount, dev_);
         configured = true;
     }
     if (nblocks64 <= 0) return;
-    trsm_rows_kernel<<<nblocks64, 256, smem, s>>>(X, ldx, Lkk, ldl, Dinv, P, ldp, rmaxq);
+    // 32-row slabs while they still make one wave (one CTA per SM): half the FP64 work per CTA of a kernel that sits on
+    // the serial chain of the factorisation (EGX_TRSM_ROWS=64 keeps the 64-row slabs)
+    static const int force64 = getenv("EGX_TRSM_ROWS") != nullptr && atoi(getenv("EGX_TRSM_ROWS")) == 64;
+    if (!force64 && 2 * nblocks64 <= sms_dev[dev_ & 63])
+        trsm_rows_kernel<32><<<2 * nblocks64, 256, smem32, s>>>(X, ldx, Lkk, ldl, Dinv, P, ldp, rmaxq);
+    else
+        trsm_rows_kernel<64><<<nblocks64, 256, smem64, s>>>(X, ldx, Lkk, ldl, Dinv, P, ldp, rmaxq);
 }
 
 static int gemm_env(const char* name, int dflt) {

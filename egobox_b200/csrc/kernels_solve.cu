@@ -179,6 +179,101 @@ __global__ void __launch_bounds__(128) backsolve_update_kernel(const double* __r
     rho[blockIdx.x * EGX_NB + tid] -= (s0 + s1) + (s2 + s3);
 }
 
+// ---------------------------------------------------------------------------
+// v <- L^-T v in ONE launch (r02; the r01 form was 2 T launches of one-CTA kernels, 5.2 ms at T = 64).
+// CTA q owns block c = T-1-q of the vector.  It walks k = T-1 .. c+1: the rows of L[k, c] it needs are loaded into
+// registers BEFORE it waits for gamma_k (they do not depend on it), so the wait hides the loads; then
+// b_c -= L[k, c]^T gamma_k.  When gamma_{c+1} has been folded in it solves its own diagonal block with the inverted
+// 32 x 32 sub-blocks of K3 (a blocked back substitution of four 32-wide steps out of shared memory), publishes
+// gamma_c and raises flags[c].  A CTA only ever waits for CTAs with a smaller blockIdx, which the hardware has
+// dispatched before it, so the chain cannot dead-lock whatever the number of resident CTAs.
+// ---------------------------------------------------------------------------
+constexpr int BSC_THREADS = 512;
+
+__device__ __forceinline__ int bsc_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bsc_st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(BSC_THREADS) backsolve_chain_kernel(const double* __restrict__ L, long ld,
+                                                                      const double* __restrict__ Dinv, int T,
+                                                                      double* v, int* flags) {
+    extern __shared__ __align__(16) double bsm[];
+    double* Lsub = bsm;                   // the six 32 x 32 blocks below the diagonal of L_cc: block (s', s'') at s'(s'-1)/2 + s''
+    double* Dis = Lsub + 6 * 1024;        // inverted diagonal 32 x 32 blocks
+    double* g = Dis + 4 * 1024;           // gamma_k of the step / x of the diagonal solve
+    double* b = g + EGX_NB;
+    double (*part)[EGX_NB] = reinterpret_cast<double (*)[EGX_NB]>(b + EGX_NB);
+    const int tid = threadIdx.x;
+    const int col = tid & 127, rg = tid >> 7;      // column of the block, group of 32 rows
+    const int c = T - 1 - static_cast<int>(blockIdx.x);
+    const double* Lcc = L + static_cast<long>(c) * EGX_NB * ld + static_cast<long>(c) * EGX_NB;
+    for (int e = tid; e < 6 * 1024; e += BSC_THREADS) {
+        const int blk = e >> 10, k = (e >> 5) & 31, i = e & 31;
+        const int sp = blk == 0 ? 1 : (blk < 3 ? 2 : 3);
+        const int spp = blk - sp * (sp - 1) / 2;
+        Lsub[e] = Lcc[static_cast<long>(32 * sp + k) * ld + 32 * spp + i];
+    }
+    for (int e = tid; e < 4096; e += BSC_THREADS) Dis[e] = Dinv[static_cast<long>(c) * 4096 + e];
+    double acc = 0.0;     // sum over k of (L[k, c]^T gamma_k)[col], rows of group rg
+    for (int k = T - 1; k > c; --k) {
+        const double* Lk = L + (static_cast<long>(k) * EGX_NB + rg * 32) * ld + static_cast<long>(c) * EGX_NB + col;
+        double lv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) lv[i] = __ldcs(Lk + static_cast<long>(i) * ld);
+        if (tid == 0)
+            while (bsc_ld_acquire(flags + k) == 0) {
+            }
+        __syncthreads();
+        if (tid < EGX_NB) g[tid] = __ldcg(v + static_cast<long>(k) * EGX_NB + tid);
+        __syncthreads();
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            s0 = fma(lv[i], g[rg * 32 + i], s0);
+            s1 = fma(lv[i + 1], g[rg * 32 + i + 1], s1);
+        }
+        acc += s0 + s1;
+    }
+    part[rg][col] = acc;
+    __syncthreads();
+    if (tid < EGX_NB) b[tid] = v[static_cast<long>(c) * EGX_NB + tid] - ((part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]));
+    __syncthreads();
+    // x = L_cc^-T b:  for s = 3 .. 0:  x_s = Dinv_s^T b_s ;  b_s'' -= L[s, s'']^T x_s (s'' < s)
+    for (int s = 3; s >= 0; --s) {
+        if (tid < 32) {
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {       // Dinv is lower triangular: rows k < tid hold zeros above the diagonal
+                x0 = fma(Dis[s * 1024 + k * 32 + tid], b[32 * s + k], x0);
+                x1 = fma(Dis[s * 1024 + (k + 1) * 32 + tid], b[32 * s + k + 1], x1);
+            }
+            g[32 * s + tid] = x0 + x1;
+        }
+        __syncthreads();
+        if (tid < 32 * s) {
+            const int spp = tid >> 5, i = tid & 31;
+            const double* Lb = Lsub + (s * (s - 1) / 2 + spp) * 1024 + i;
+            double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+                u0 = fma(Lb[k * 32], g[32 * s + k], u0);
+                u1 = fma(Lb[(k + 1) * 32], g[32 * s + k + 1], u1);
+            }
+            b[tid] -= u0 + u1;
+        }
+        __syncthreads();
+    }
+    if (tid < EGX_NB) v[static_cast<long>(c) * EGX_NB + tid] = g[tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) bsc_st_release(flags + c, 1);
+}
+
 // variance epilogue: one warp per prediction point, 8 points per CTA.
 //   s1 = sum_j rt_j^2 ; z = Ft^T rt - f(x) ; u = G^-T z ; var = sigma2 * max(0, 1 - s1 + |u|^2)
 __global__ void __launch_bounds__(256)
@@ -316,6 +411,21 @@ void launch_bcast_rows(double* out, long ld, int m, int mpad, int cols, const do
 void launch_gls(const double* M, long ld, int n, int npad, int p, double* work, double* G, double* beta, double* rho,
                 EvalResult* res, const int* info, cudaStream_t s) {
     gls_kernel<<<1, GLS_THREADS, 0, s>>>(M, ld, n, npad, p, work, G, beta, rho, res, info);
+}
+
+void launch_backsolve_chain(const double* L, long ld, const double* Dinv, int T, double* v, int* flags, cudaStream_t s) {
+    if (T <= 0) return;
+    static bool configured_dev[64] = {false};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& configured = configured_dev[dev_ & 63];
+    const int smem = (6 * 1024 + 4 * 1024 + 6 * EGX_NB) * static_cast<int>(sizeof(double));
+    if (!configured) {
+        cudaFuncSetAttribute(backsolve_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    cudaMemsetAsync(flags, 0, static_cast<size_t>(T) * sizeof(int), s);
+    backsolve_chain_kernel<<<T, BSC_THREADS, smem, s>>>(L, ld, Dinv, T, v, flags);
 }
 
 void launch_backsolve_diag(const double* Lkk, long ld, double* rho_k, cudaStream_t s) {

@@ -57,19 +57,35 @@ int SweepEnv::init(int max_block_cols) {
     EGX_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     EGX_CUDA_TRY(cudaStreamCreateWithPriority(&sb, cudaStreamNonBlocking, lo));
     EGX_CUDA_TRY(cudaStreamCreateWithPriority(&sp, cudaStreamNonBlocking, hi));
+    EGX_CUDA_TRY(cudaStreamCreateWithPriority(&sq, cudaStreamNonBlocking, hi));
+    const int npairs = (max_block_cols + 1) / 2;
     ev_panel.assign(max_block_cols, nullptr);
     ev_bulk.assign(max_block_cols, nullptr);
+    ev_trsm_a.assign(npairs, nullptr);
+    ev_partner.assign(npairs, nullptr);
+    ev_colrest.assign(npairs, nullptr);
     for (int k = 0; k < max_block_cols; ++k) {
         EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
         EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_bulk[k], cudaEventDisableTiming));
     }
+    for (int k = 0; k < npairs; ++k) {
+        EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_trsm_a[k], cudaEventDisableTiming));
+        EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_partner[k], cudaEventDisableTiming));
+        EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_colrest[k], cudaEventDisableTiming));
+    }
     EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_join_q, cudaEventDisableTiming));
+    if (const char* v = getenv("EGX_LOOKAHEAD_V")) lookahead_v = atoi(v);
+    bs_flags_n = max_block_cols;
+    EGX_CUDA_TRY(egx_dev_malloc(&bs_flags, static_cast<size_t>(max_block_cols > 0 ? max_block_cols : 1) * sizeof(int)));
     const char* e = getenv("EGX_LOOKAHEAD");
     lookahead = !(e != nullptr && atoi(e) == 0);
     if ((e = getenv("EGX_OZAKI")) != nullptr) ozaki = atoi(e);
-    if ((e = getenv("EGX_OZAKI_MIN_TRI")) != nullptr) ozaki_min_tri = atoi(e) > 1 ? atoi(e) : 1;
-    ozaki_min_tri_solve = ozaki_min_tri;
+    if ((e = getenv("EGX_OZAKI_MIN_TRI")) != nullptr) {
+        ozaki_min_tri = atoi(e) > 1 ? atoi(e) : 1;
+        ozaki_min_tri_solve = ozaki_min_tri;
+    }
     if ((e = getenv("EGX_OZAKI_MIN_T")) != nullptr) ozaki_min_T = atoi(e);
     return EGX_OK;
 }
@@ -102,13 +118,19 @@ int SweepEnv::ensure_panel_rows(long rows) {
 void SweepEnv::destroy() {
     if (sb) cudaStreamSynchronize(sb);
     if (sp) cudaStreamSynchronize(sp);
+    if (sq) cudaStreamSynchronize(sq);
     prof.destroy();
-    for (auto e : ev_panel)
-        if (e) cudaEventDestroy(e);
-    for (auto e : ev_bulk)
-        if (e) cudaEventDestroy(e);
+    for (auto* vec : {&ev_panel, &ev_bulk, &ev_trsm_a, &ev_partner, &ev_colrest}) {
+        for (auto e : *vec)
+            if (e) cudaEventDestroy(e);
+        vec->clear();
+    }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_join_q) cudaEventDestroy(ev_join_q);
+    ev_fork = ev_join = ev_join_q = nullptr;
+    egx_dev_free(bs_flags);
+    bs_flags = nullptr;
     egx_dev_free(P2[0]);
     egx_dev_free(P2[1]);
     egx_dev_free(oz_S);
@@ -119,9 +141,10 @@ void SweepEnv::destroy() {
         egx_dev_free(oz_rmaxq[i]);
         oz_rmaxq[i] = nullptr;
     }
+    if (sq) cudaStreamDestroy(sq);
     if (sp) cudaStreamDestroy(sp);
     if (sb) cudaStreamDestroy(sb);
-    sb = sp = nullptr;
+    sb = sp = sq = nullptr;
 }
 
 // Two-level blocking: block columns are processed in PAIRS (outer block 256 = two 128-panels).  Panel A, the
@@ -150,12 +173,141 @@ static void trailing_syrk(SweepEnv& env, const GemmArgs& g, cudaStream_t st, int
     launch_gemm_nt_sub(g, st);
 }
 
+// Factorisation with the r02 look-ahead schedule: the serial chain of a block column is
+//   diagonal-tile update (ten 32 x 32 CTAs) -> K3 -> K5
+// on the panel stream `sp`; the rest of the column (everything below the diagonal tile) is updated on `sq` WHILE K3 runs
+// and joins before K5.  r01 updated whole columns on the panel stream before K3 (EGX_LOOKAHEAD_V=1): one 128 x 64 tile with
+// K = 256 keeps an SM busy for 17 us and the early columns are bound by the FP64 pipe of the whole GPU (28 us at n = 8192).
+static void factor_sweep_lookahead(SweepEnv& env, const FactorRef& f) {
+    const int T = f.T, Qt = f.qpad / EGX_NB;
+    const long ld = f.ld;
+    const long LDP = 2 * EGX_NB;
+    cudaStream_t sb = env.sb, sp = env.sp, sq = env.sq;
+    cudaEventRecord(env.ev_fork, sb);
+    cudaStreamWaitEvent(sp, env.ev_fork, 0);
+    cudaStreamWaitEvent(sq, env.ev_fork, 0);
+    auto blk = [&](int r, int c) { return f.M + static_cast<long>(r) * EGX_NB * ld + static_cast<long>(c) * EGX_NB; };
+    bool rest_pending = false;       // sq still updates this pair's columns (ev_colrest of the previous pair)
+    for (int k = 0; k < T; k += 2) {
+        const int pair = k >> 1;
+        double* Pw = env.P2[pair & 1];                 // rows x 256, row 0 = first row of block k+1
+        double* Rq = env.ozaki ? env.oz_rmaxq[pair & 1] : nullptr;
+        const bool two = (k + 1 < T);
+        // ---- panel A ----------------------------------------------------------------------------------
+        {
+            StageScope sc(env.prof, EGX_STAGE_POTRF_DIAG, 1, sp);
+            launch_potrf_diag(blk(k, k), ld, f.info, k * EGX_NB, f.Dinv + static_cast<long>(k) * 4096, sp);
+        }
+        if (rest_pending) {
+            cudaStreamWaitEvent(sp, env.ev_colrest[pair - 1], 0);
+            rest_pending = false;
+        }
+        const int rows_below = (T - k - 1) * EGX_NB + f.qpad;
+        if (rows_below > 0) {
+            StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
+            launch_trsm_rows(blk(k + 1, k), ld, blk(k, k), ld, f.Dinv + static_cast<long>(k) * 4096, Pw, LDP, rows_below / 64, sp, Rq);
+        }
+        if (!two) break;
+        const int tri1 = T - k - 1;                    // block columns right of k
+        cudaEventRecord(env.ev_trsm_a[pair], sp);
+        // ---- partner column k+1: its diagonal tile on the chain, the rows below it beside K3 --------------
+        {
+            StageScope sc(env.prof, EGX_STAGE_GEMM_LOOKAHEAD, 1, sp);
+            launch_diag_tile_update(blk(k + 1, k + 1), ld, Pw, LDP, EGX_NB, sp);
+        }
+        const int rest1 = tri1 - 1 + Qt;
+        if (rest1 > 0) {
+            cudaStreamWaitEvent(sq, env.ev_trsm_a[pair], 0);
+            GemmArgs g;
+            g.C = blk(k + 2, k + 1);
+            g.ldc = ld;
+            g.A = Pw + static_cast<long>(EGX_NB) * LDP;
+            g.lda = LDP;
+            g.B = Pw;
+            g.ldb = LDP;
+            g.K = EGX_NB;
+            g.tri = 0;
+            g.Mt = rest1;
+            g.Nt = 1;
+            StageScope sc(env.prof, EGX_STAGE_GEMM_LOOKAHEAD, 1, sq);
+            launch_gemm_nt_sub(g, sq);
+            cudaEventRecord(env.ev_partner[pair], sq);
+        }
+        {
+            StageScope sc(env.prof, EGX_STAGE_POTRF_DIAG, 1, sp);
+            launch_potrf_diag(blk(k + 1, k + 1), ld, f.info, (k + 1) * EGX_NB, f.Dinv + static_cast<long>(k + 1) * 4096, sp);
+        }
+        if (rest1 > 0) {
+            cudaStreamWaitEvent(sp, env.ev_partner[pair], 0);
+            StageScope sc(env.prof, EGX_STAGE_TRSM_PANEL, 1, sp);
+            launch_trsm_rows(blk(k + 2, k + 1), ld, blk(k + 1, k + 1), ld, f.Dinv + static_cast<long>(k + 1) * 4096,
+                             Pw + static_cast<long>(EGX_NB) * LDP + EGX_NB, LDP, rest1 * 2, sp,
+                             Rq ? Rq + static_cast<long>(EGX_NB) * 4 + 2 : nullptr);
+        }
+        const int tri2 = T - k - 2;                    // block columns right of the pair
+        cudaEventRecord(env.ev_panel[pair], sp);
+        if (tri2 <= 0) continue;
+        // ---- next pair's columns, K = 256: diagonal tile on the chain, the rest beside the next K3 -------------
+        if (pair > 0) cudaStreamWaitEvent(sp, env.ev_bulk[pair - 1], 0);
+        {
+            StageScope sc(env.prof, EGX_STAGE_GEMM_LOOKAHEAD, 1, sp);
+            launch_diag_tile_update(blk(k + 2, k + 2), ld, Pw + static_cast<long>(EGX_NB) * LDP, LDP, 2 * EGX_NB, sp);
+        }
+        const int nla = tri2 < 2 ? tri2 : 2;
+        const int rest2 = tri2 - 1 + Qt;
+        if (rest2 > 0) {
+            cudaStreamWaitEvent(sq, env.ev_panel[pair], 0);
+            if (pair > 0) cudaStreamWaitEvent(sq, env.ev_bulk[pair - 1], 0);
+            GemmArgs g;
+            g.C = blk(k + 3, k + 2);
+            g.ldc = ld;
+            g.A = Pw + static_cast<long>(2 * EGX_NB) * LDP;
+            g.lda = LDP;
+            g.B = Pw + static_cast<long>(EGX_NB) * LDP;
+            g.ldb = LDP;
+            g.K = 2 * EGX_NB;
+            g.tri = 0;
+            g.Mt = rest2;
+            g.Nt = nla;
+            StageScope sc(env.prof, EGX_STAGE_GEMM_LOOKAHEAD, 1, sq);
+            launch_gemm_nt_sub(g, sq);
+            cudaEventRecord(env.ev_colrest[pair], sq);
+            rest_pending = true;
+        }
+        // ---- bulk: block columns k+4 .., on the bulk stream -------------------------------------------------
+        cudaStreamWaitEvent(sb, env.ev_panel[pair], 0);
+        if (tri2 > 2) {
+            GemmArgs gb;
+            gb.K = 2 * EGX_NB;
+            gb.lda = LDP;
+            gb.ldb = LDP;
+            gb.ldc = ld;
+            gb.C = blk(k + 4, k + 4);
+            gb.A = Pw + static_cast<long>(3 * EGX_NB) * LDP;
+            gb.B = gb.A;
+            gb.tri = tri2 - 2;
+            gb.Mt = tri2 - 2 + Qt;
+            gb.Nt = tri2 - 2;
+            trailing_syrk(env, gb, sb, T, Rq ? Rq + static_cast<long>(3 * EGX_NB) * 4 : nullptr);
+        }
+        cudaEventRecord(env.ev_bulk[pair], sb);
+    }
+    cudaEventRecord(env.ev_join, sp);
+    cudaStreamWaitEvent(sb, env.ev_join, 0);
+    cudaEventRecord(env.ev_join_q, sq);
+    cudaStreamWaitEvent(sb, env.ev_join_q, 0);
+}
+
 void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows, long ld_rows, int row_tiles_all,
                    int slabs64_all, bool upper_rows) {
     const int T = f.T, Qt = f.qpad / EGX_NB;
     const long ld = f.ld;
     const long LDP = 2 * EGX_NB;
     const bool la = env.lookahead && factor && T > 4 && static_cast<int>(env.ev_panel.size()) >= (T + 1) / 2;
+    if (la && env.lookahead_v != 1 && env.sq != nullptr && static_cast<int>(env.ev_colrest.size()) >= (T + 1) / 2) {
+        factor_sweep_lookahead(env, f);
+        return;
+    }
     cudaStream_t sb = env.sb, sp = la ? env.sp : env.sb;
     if (la) {
         cudaEventRecord(env.ev_fork, sb);
@@ -348,6 +500,13 @@ int egx_fill_terms(int corr, int d, int h, const double* w, const double* theta,
 }
 
 void backsolve_vector(SweepEnv& env, const FactorRef& f, double* v) {
+    // EGX_BACKSOLVE_V=1: the r01 form (2 T one-CTA launches), kept for A/B
+    static const int version = getenv("EGX_BACKSOLVE_V") != nullptr ? atoi(getenv("EGX_BACKSOLVE_V")) : 2;
+    if (version != 1 && env.bs_flags != nullptr && f.T <= env.bs_flags_n && f.Dinv != nullptr) {
+        StageScope sc(env.prof, EGX_STAGE_BACKSOLVE, 1, env.sb);
+        launch_backsolve_chain(f.M, f.ld, f.Dinv, f.T, v, env.bs_flags, env.sb);
+        return;
+    }
     for (int k = f.T - 1; k >= 0; --k) {
         const double* Lkk = f.M + static_cast<long>(k) * EGX_NB * f.ld + static_cast<long>(k) * EGX_NB;
         StageScope sc(env.prof, EGX_STAGE_BACKSOLVE, k > 0 ? 2 : 1, env.sb);

@@ -36,9 +36,12 @@ struct StageScope {
 struct SweepEnv {
     cudaStream_t sb = nullptr;   // bulk stream
     cudaStream_t sp = nullptr;   // high-priority panel / look-ahead stream
+    cudaStream_t sq = nullptr;   // high-priority stream of the column updates that run beside the diagonal-block chain (r02)
     bool lookahead = true;
     std::vector<cudaEvent_t> ev_panel, ev_bulk;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::vector<cudaEvent_t> ev_trsm_a, ev_partner, ev_colrest;   // r02 look-ahead: per column pair
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_q = nullptr;
+    int lookahead_v = 2;                  // EGX_LOOKAHEAD_V=1: the r01 schedule (whole columns on the panel stream)
     double* P2[2] = {nullptr, nullptr};   // double-buffered contiguous panel copies (rows x 128)
     long p_rows = 0;
     // tcgen05 path of the trailing update (kernels_ozaki.cu): int8 slices + row scales of the current panel pair
@@ -47,11 +50,13 @@ struct SweepEnv {
     double* oz_rmaxq[2] = {nullptr, nullptr};   // [row][4] quarter-row maxima written by the panel solves, per P2 buffer
     int ozaki = 1;                        // EGX_OZAKI=0 keeps every update on the DMMA kernel
     int oz_persist = 0;                   // set by the batched entry point: several evaluations share the GPU
-    int ozaki_min_tri = 8;                // smallest trailing tile-triangle worth the slicing pass (EGX_OZAKI_MIN_TRI)
+    int ozaki_min_tri = 4;                // smallest trailing tile-triangle worth the slicing pass (EGX_OZAKI_MIN_TRI; r02: 8 -> 4, C5 66.1 -> 64.9 ms)
     int ozaki_min_tri_solve = 8;          // the same for the updates of a multi-RHS solve (row_tiles x tri2 tiles: the sparse GP
                                           // solves 64 row tiles against 8 block columns and sets 2)
     int ozaki_min_T = 1;                  // smallest factor (block columns) that uses it at all (EGX_OZAKI_MIN_T); measured
                                           // on batches of 96: ahead of DMMA from n = 2048 (0.165 vs 0.187 ms) upwards
+    int* bs_flags = nullptr;              // per-block-column flags of the chained back substitution (max_block_cols ints)
+    int bs_flags_n = 0;
     int generation = 0;                   // bumped when a buffer captured in a CUDA graph is reallocated
     Profiler prof;
     int init(int max_block_cols);
