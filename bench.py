@@ -225,7 +225,7 @@ def workload_config(args):
     return {"workload": "Kriging Matern52 n=%d d=%d fp64 constant mean: fit (%d likelihood evals = 11 chains x 100 "
                         "+ final) + predict_var on m=%d points" % (args.n, args.d, args.evals, args.m),
             "n": args.n, "d": args.d, "m": args.m, "likelihood_evals_per_fit": args.evals,
-            "l2": "inputs larger than L2 (R/L workspace %.0f MB, predict chunk %.0f MB vs 126 MB L2)" % (
+            "l2": "inputs larger than L2 (R/L workspace %.0f MB, predict chunk >= %.0f MB vs 126 MB L2)" % (
                 8e-6 * args.n * args.n, 8e-6 * min(args.m, 8192) * args.n),
             "parallelism": "likelihood evaluations and prediction points of ONE training set sharded over the GPUs; "
                            "collectives: one all-gather of (status, likelihood) per sweep, one all-gather of the variances"}
@@ -397,6 +397,8 @@ def run_ours(args):
     xs_pinned = torch.from_numpy(xs).pin_memory().numpy()
     x_h, y_h = np.ascontiguousarray(x), np.ascontiguousarray(y)
 
+    e2e_parts = []        # (fit, predict, close) wall ms of every e2e step of this rank, warm-up included
+
     def e2e_step():
         # same evaluation budget as the value leg: (n_start + 1) chains x clamp(10 d, 25, 1000) + 1 final; the chains are
         # sharded over the ranks (parallel.fit_multistart: chain c on rank c % world, one all-gather of (objective, theta)),
@@ -405,11 +407,16 @@ def run_ours(args):
         params = (eg.GaussianProcess.params(eg.ConstantMean, eg.Matern52Corr)
                   .n_start(max((E - 1) // per_chain - 1, 0)).max_eval(1000)
                   .cobyla_ftol_rel(0.0).device(local_rank))
+        t_a = time.perf_counter()
         gp = P.fit_multistart(params, x_h, y_h)
+        t_b = time.perf_counter()
         var = P.predict_sharded(gp.predict_var, xs_pinned)
+        t_c = time.perf_counter()
         nev = gp.n_evals()
         lik, th = gp.likelihood(), gp.theta()
         gp.close()
+        t_d = time.perf_counter()
+        e2e_parts.append(((t_b - t_a) * 1e3, (t_c - t_b) * 1e3, (t_d - t_c) * 1e3))
         return var, nev, lik, th
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -531,7 +538,8 @@ def run_ours(args):
                "e2e": {"value": e2e_value, "unit": "points/s", "ms_per_step": e2e_ms_all, "steps": e2e_steps,
                        "likelihood_evals": int(nev_all),
                        "h2d_bytes_per_step": int(world * (x_h.nbytes + y_h.nbytes) + xs_pinned.nbytes + nev_all * d * 8),
-                       "d2h_bytes_per_step": int(var.nbytes + nev_all * 64)},
+                       "d2h_bytes_per_step": int(var.nbytes + nev_all * 64),
+                       "fit_predict_close_ms_rank0": [[round(v, 1) for v in p3] for p3 in e2e_parts]},
                "gpu_launches": int(launches) * world,
                "launches_per_step_rank0": {k: int(v[1] // args.steps) for k, v in prof.items()},
                "stage_ms_roofline_pass": {k: round(v[0], 3) for k, v in roof_prof.items()},

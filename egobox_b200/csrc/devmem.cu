@@ -4,7 +4,7 @@
 // which at n ~ 1000 is more than the 90 likelihood rounds of the fit itself.  Blocks are reused by exact size
 // (buffer sizes are functions of n padded to 128, so they repeat from fit to fit); every context synchronises its
 // streams before releasing memory, so a cached block has no work in flight.
-// EGX_CACHE_MB caps the cached (idle) bytes per kind, default 4096; 0 disables the cache.
+// EGX_CACHE_MB caps the cached (idle) bytes per kind, default 16384 (device) / 4096 (pinned host); 0 disables the cache.
 #include <algorithm>
 #include <cstdlib>
 #include <map>
@@ -27,12 +27,14 @@ struct BlockCache {
 
     explicit BlockCache(bool h) : host(h) {}
 
-    static size_t cap() {
-        static const size_t c = [] {
+    // a fit at n = 8192 hands back 8 workspaces of 0.58 GB + panels, slices and the predict chunk = 6.5 GB: under the r01 cap
+    // of 4 GB every other fit of the bench's e2e leg paid ~0.3 s of cudaFree / cudaMalloc (profiles/r02/y7_bench_short.log)
+    size_t cap() const {
+        static const long env_mb = [] {
             const char* e = getenv("EGX_CACHE_MB");
-            return static_cast<size_t>(e ? std::max(0, atoi(e)) : 4096) << 20;
+            return e ? static_cast<long>(std::max(0, atoi(e))) : -1L;
         }();
-        return c;
+        return static_cast<size_t>(env_mb >= 0 ? env_mb : (host ? 4096 : 16384)) << 20;
     }
     cudaError_t raw_alloc(void** p, size_t bytes) { return host ? cudaMallocHost(p, bytes) : cudaMalloc(p, bytes); }
     void raw_free(void* p) {

@@ -145,8 +145,8 @@ struct egx_gp_ctx {
     // evaluation is 5-7 launches per block column, host launch-bound below n ~ 4096.  Re-captured when the
     // number of kernel terms, the look-ahead setting or a captured buffer changes; bypassed while profiling.
     cudaGraphExec_t eval_graph = nullptr;
-    int graph_nterms = -1, graph_generation = -1;
-    bool graph_lookahead = false, use_graphs = true;
+    int graph_nterms = -1, graph_generation = -1, graph_persist = -1;
+    bool graph_lookahead = false, use_graphs = true, use_graphs_lookahead = true;
     long long graph_launches[EGX_NUM_STAGES] = {0};
     int async_slots = 0;         // workspaces handed out by egx_gp_async_slots
     // int8 digit slices of L for the multi-RHS solve of predict_var on tcgen05 (built lazily after a finalize)
@@ -358,6 +358,7 @@ int capture_eval_graph(egx_gp_ctx* c) {
     c->graph_nterms = c->nterms;
     c->graph_lookahead = c->env.lookahead;
     c->graph_generation = c->env.generation;
+    c->graph_persist = c->env.oz_persist;
     return EGX_OK;
 }
 
@@ -369,9 +370,9 @@ int evaluate_launch(egx_gp_ctx* c, const double* theta) {
     int st = build_terms_host(c, theta);
     if (st != EGX_OK) return st;
     // the first evaluation of a context always launches directly (lazy module loading, function attributes)
-    if (c->use_graphs && !c->env.prof.on && c->direct_evals > 0) {
+    if ((c->use_graphs || (c->use_graphs_lookahead && c->env.lookahead)) && !c->env.prof.on && c->direct_evals > 0) {
         if (c->eval_graph == nullptr || c->graph_nterms != c->nterms || c->graph_lookahead != c->env.lookahead ||
-            c->graph_generation != c->env.generation) {
+            c->graph_generation != c->env.generation || c->graph_persist != c->env.oz_persist) {
             st = capture_eval_graph(c);
             if (st != EGX_OK) return st;
         }
@@ -430,6 +431,22 @@ int ensure_predict_buffers(egx_gp_ctx* c, int mb) {
 }
 
 constexpr int PREDICT_CHUNK = 8192;
+
+// Points per chunk of predict / predict_var: whole waves of the 64-row solve slabs (K5) -- two waves (18 944 points on 148 SMs)
+// while the chunk x npad buffer stays under 2 GB, else one wave, else 8192.  Measured on the sparse GP, whose chunks are the
+// same sweeps (profiles/r02/y7_sgp.txt): 8192 -> 18 944 points per chunk = 8.56 -> 7.05 ms.  EGX_PREDICT_CHUNK overrides.
+int predict_chunk_points(const egx_gp_ctx* c) {
+    static const int env_pts = getenv("EGX_PREDICT_CHUNK") != nullptr ? std::max(EGX_NB, atoi(getenv("EGX_PREDICT_CHUNK")) / EGX_NB * EGX_NB) : 0;
+    if (env_pts > 0) return env_pts;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess || sms <= 0) return PREDICT_CHUNK;
+    const long budget = 2L << 30;
+    for (int waves = 2; waves >= 1; --waves) {
+        const long pts = static_cast<long>(waves) * sms * 64 / EGX_NB * EGX_NB;
+        if (pts >= PREDICT_CHUNK && pts * c->npad * static_cast<long>(sizeof(double)) <= budget) return static_cast<int>(pts);
+    }
+    return PREDICT_CHUNK;
+}
 
 // Slices of the block rows of L below every column pair (the B operand of the solve updates), once per trained model:
 // as many bytes as the lower triangle of L itself (268 MB at n = 8192), ~1 ms to build.
@@ -510,7 +527,7 @@ int predict_impl(egx_gp_ctx* c, const double* x, int m, double* y, double* var, 
     }
     if (m == 0) return EGX_OK;
     EGX_CUDA_TRY(cudaSetDevice(c->device));
-    const int mb = std::min(round_up(m, EGX_NB), PREDICT_CHUNK);
+    const int mb = std::min(round_up(m, EGX_NB), predict_chunk_points(c));
     int st = ensure_predict_buffers(c, mb);
     if (st != EGX_OK) return st;
     for (int i0 = 0; i0 < m; i0 += mb) {
@@ -697,8 +714,11 @@ extern "C" int egx_gp_create(egx_gp_ctx** out, int device, int corr, int mean, c
     c->stream = c->env.sb;
     // measured (tools/midsize_probe.py, configs_probe.py): replay wins 1.5-2.7x for n <= 2048 and 6 % at n = 4096,
     // and loses 2.5 % at n = 8192 where the evaluation is throughput- not launch-bound
+    // r02: above 4096 the replay is used while the look-ahead schedule is on, i.e. with fewer than 6 evaluations in flight
+    // (single evaluations, the chains of one rank of a sharded fit): 5.24 -> 4.86 ms at n = 8192 (profiles/r02/y5_single.txt)
     c->use_graphs = c->npad <= 4096;
-    if (const char* e = getenv("EGX_GRAPHS")) c->use_graphs = atoi(e) != 0;
+    c->use_graphs_lookahead = true;
+    if (const char* e = getenv("EGX_GRAPHS")) c->use_graphs = c->use_graphs_lookahead = atoi(e) != 0;
     const size_t xbytes = static_cast<size_t>(c->npad) * d * sizeof(double);
     EGX_CREATE_TRY(egx_dev_malloc(&c->X, xbytes));
     EGX_CREATE_TRY(cudaMemsetAsync(c->X, 0, xbytes, c->stream));

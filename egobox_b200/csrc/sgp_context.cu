@@ -293,7 +293,17 @@ extern "C" int egx_sgp_create(egx_sgp_ctx** out, int device, int corr, int metho
     c->h = h;
     c->nugget = nugget;
     c->Mpad = round_up(m, EGX_NB);
-    c->chunk = std::min(round_up(n, EGX_NB), SGP_CHUNK);
+    // points per chunk: a multiple of 256 (the K panels of the split-K product); EGX_SGP_CHUNK overrides
+    // default: TWO full waves of 64-row solve slabs (148 SMs: 18 944 points).  Measured at N = 1e5, M = 1024
+    // (profiles/r02/y7_sgp.txt): 8192 -> 8.56 ms per evaluation (128 slabs on 148 SMs, 13 chunks), 9472 -> 7.81, 18944 -> 7.05
+    int chunk_pts = SGP_CHUNK;
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+            chunk_pts = std::max(SGP_CHUNK, 2 * sms * 64 / 256 * 256);
+    }
+    if (const char* e = getenv("EGX_SGP_CHUNK")) chunk_pts = std::max(256, atoi(e) / 256 * 256);
+    c->chunk = std::min(round_up(n, EGX_NB), chunk_pts);
     c->w_star.assign(w_star, w_star + static_cast<size_t>(d) * h);
     const int Mpad = c->Mpad, CH = c->chunk;
 #define SGP_TRY(expr)                                                        \
