@@ -439,7 +439,20 @@ def run_ours(args):
 
     # ---------------- reductions over ranks -------------------------------------------------
     step_ms_all, e2e_ms_all, dev_ms_all, nev_all = step_ms, e2e_ms, dev_ms, float(nev)
+    collective_us = None
     if world > 1:
+        # what the exchanges of the sharded path cost on this box: the (status, likelihood) all-gather of the sweep through
+        # parallel.all_gather_rows (host rows -> device -> NCCL -> host), as it runs inside the timed region, wall time
+        rows = np.zeros((len(P.shard_indices(E - 1, rank, world)), 2))
+        cnts = [len(P.shard_indices(E - 1, r, world)) for r in range(world)]
+        for _ in range(5):
+            P.all_gather_rows(rows, 2, cnts)
+        barrier()
+        t0c = time.perf_counter()
+        for _ in range(20):
+            P.all_gather_rows(rows, 2, cnts)
+        torch.cuda.synchronize()
+        collective_us = (time.perf_counter() - t0c) / 20 * 1e6
         t = torch.tensor([step_ms, e2e_ms, dev_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms_all, e2e_ms_all, dev_ms_all = float(t[0]), float(t[1]), float(t[2])
@@ -540,6 +553,7 @@ def run_ours(args):
                        "h2d_bytes_per_step": int(world * (x_h.nbytes + y_h.nbytes) + xs_pinned.nbytes + nev_all * d * 8),
                        "d2h_bytes_per_step": int(var.nbytes + nev_all * 64),
                        "fit_predict_close_ms_rank0": [[round(v, 1) for v in p3] for p3 in e2e_parts]},
+               "sweep_allgather_us_rank0": collective_us,
                "gpu_launches": int(launches) * world,
                "launches_per_step_rank0": {k: int(v[1] // args.steps) for k, v in prof.items()},
                "stage_ms_roofline_pass": {k: round(v[0], 3) for k, v in roof_prof.items()},

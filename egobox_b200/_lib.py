@@ -170,6 +170,8 @@ SIGNATURES.update({
     "egx_sgp_model_context": (_vp, [_vp]),
     "egx_sgp_model_predict": (C.c_int, [_vp, _dp, C.c_int, _dp]),
     "egx_sgp_model_predict_var": (C.c_int, [_vp, _dp, C.c_int, _dp]),
+    "egx_sgp_model_sample": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp]),
+    "egx_sgp_sample": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, C.c_int, _dp]),
 })
 
 _lib = None

@@ -1399,90 +1399,8 @@ extern "C" int egx_gp_sample(egx_gp_ctx* c, const double* x, int m, const double
     CovWork w;
     int st = conditional_cov_dev(c, x, m, w);
     if (st != EGX_OK) return st;
-    const int mpad = w.mpad, tpad = round_up(n_traj, EGX_NB);
-    struct Tmp {
-        double *ZT = nullptr, *OUT = nullptr, *Dinv = nullptr;
-        int* info = nullptr;
-        ~Tmp() {
-            egx_dev_free(ZT);
-            egx_dev_free(OUT);
-            egx_dev_free(Dinv);
-            egx_dev_free(info);
-        }
-    } t;
-    EGX_CUDA_TRY(egx_dev_malloc(&t.ZT, static_cast<size_t>(tpad) * mpad * sizeof(double)));
-    EGX_CUDA_TRY(egx_dev_malloc(&t.OUT, static_cast<size_t>(mpad) * tpad * sizeof(double)));
-    // the normal draws, one trajectory per row (the B operand of the NT product)
-    std::vector<double> zt(static_cast<size_t>(tpad) * mpad, 0.0);
-    for (int i = 0; i < m; ++i)
-        for (int k = 0; k < n_traj; ++k) zt[static_cast<size_t>(k) * mpad + i] = z[static_cast<size_t>(i) * n_traj + k];
-    EGX_CUDA_TRY(cudaMemcpyAsync(t.ZT, zt.data(), zt.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-
-    if (method == EGX_SAMPLE_CHOLESKY) {
-        // cov = C C^T with the same blocked factorisation as the likelihood (algorithm.rs:1162-1168)
-        EGX_CUDA_TRY(egx_dev_malloc(&t.Dinv, static_cast<size_t>(mpad / EGX_NB) * 4096 * sizeof(double)));
-        EGX_CUDA_TRY(egx_dev_malloc(&t.info, sizeof(int)));
-        EGX_CUDA_TRY(cudaMemsetAsync(t.info, 0, sizeof(int), c->stream));
-        FactorRef f;
-        f.M = w.K;
-        f.ld = mpad;
-        f.T = mpad / EGX_NB;
-        f.qpad = 0;
-        f.Dinv = t.Dinv;
-        f.info = t.info;
-        blocked_sweep(c->env, f, true, nullptr, 0, 0, 0);
-        int info_h = 0;
-        EGX_CUDA_TRY(cudaMemcpyAsync(&info_h, t.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (info_h != 0) {
-            egx_set_error("conditional covariance is not positive definite (pivot %d); use the eigenvalue method",
-                          info_h);
-            return EGX_NOT_POSITIVE_DEFINITE;
-        }
-        launch_zero_upper(w.K, mpad, mpad, c->stream);
-    } else {
-        // C = W diag(sqrt(max(v, 0))) with eigenvalues below 1e-9 dropped (algorithm.rs:1169-1187); the m x m
-        // eigen-decomposition runs on the host, as in the reference
-        std::vector<double> a(static_cast<size_t>(m) * m), ev(m);
-        EGX_CUDA_TRY(cudaMemcpy2DAsync(a.data(), static_cast<size_t>(m) * sizeof(double), w.K,
-                                       static_cast<size_t>(mpad) * sizeof(double), static_cast<size_t>(m) * sizeof(double),
-                                       m, cudaMemcpyDeviceToHost, c->stream));
-        EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (egx_host_symmetric_eig(m, a.data(), ev.data()) != 0) {
-            egx_set_error("eigen-decomposition of the conditional covariance did not converge");
-            return EGX_INVALID_VALUE;
-        }
-        for (int j = 0; j < m; ++j) ev[j] = (ev[j] < 1e-9) ? 0.0 : std::sqrt(ev[j]);
-        for (int i = 0; i < m; ++i)
-            for (int j = 0; j < m; ++j) a[static_cast<size_t>(i) * m + j] *= ev[j];
-        EGX_CUDA_TRY(cudaMemsetAsync(w.K, 0, static_cast<size_t>(mpad) * mpad * sizeof(double), c->stream));
-        EGX_CUDA_TRY(cudaMemcpy2DAsync(w.K, static_cast<size_t>(mpad) * sizeof(double), a.data(),
-                                       static_cast<size_t>(m) * sizeof(double), static_cast<size_t>(m) * sizeof(double), m,
-                                       cudaMemcpyHostToDevice, c->stream));
-        EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));      // `a` goes out of scope
-    }
-    // trajectories = mean + C Z   (algorithm.rs:1191-1193)
-    launch_bcast_rows(t.OUT, tpad, m, mpad, tpad, w.mean, c->stream);
-    {
-        GemmArgs g;
-        g.C = t.OUT;
-        g.ldc = tpad;
-        g.A = w.K;
-        g.lda = mpad;
-        g.B = t.ZT;
-        g.ldb = mpad;
-        g.K = mpad;
-        g.add = 1;
-        g.tri = 0;
-        g.Mt = mpad / EGX_NB;
-        g.Nt = tpad / EGX_NB;
-        StageScope sc(c->env.prof, EGX_STAGE_SYRK_GEMM, 1, c->stream);
-        launch_gemm_nt_sub(g, c->stream);
-    }
-    EGX_CUDA_TRY(cudaMemcpy2DAsync(out, static_cast<size_t>(n_traj) * sizeof(double), t.OUT,
-                                   static_cast<size_t>(tpad) * sizeof(double), static_cast<size_t>(n_traj) * sizeof(double),
-                                   m, cudaMemcpyDeviceToHost, c->stream));
-    EGX_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    st = sample_from_covariance(c->env, c->stream, w.K, m, w.mpad, w.mean, z, n_traj, method, out);
+    if (st != EGX_OK) return st;
     EGX_CUDA_TRY(cudaGetLastError());
     resolve_profile(c);
     return EGX_OK;

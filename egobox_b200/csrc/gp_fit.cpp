@@ -1249,6 +1249,12 @@ extern "C" int egx_sgp_model_predict(egx_sgp_model* m, const double* x, int npts
     return egx_sgp_predict(m->ctx, x, npts, y);
 }
 EGX_ABI_CATCH
+extern "C" int egx_sgp_model_sample(egx_sgp_model* m, const double* x, int npts, const double* z, int n_traj, int method,
+                                    double* out) try {
+    if (!m) return EGX_INVALID_VALUE;
+    return egx_sgp_sample(m->ctx, x, npts, z, n_traj, method, out);
+}
+EGX_ABI_CATCH
 extern "C" int egx_sgp_model_predict_var(egx_sgp_model* m, const double* x, int npts, double* var) try {
     if (!m) return EGX_INVALID_VALUE;
     return egx_sgp_predict_var(m->ctx, x, npts, var);

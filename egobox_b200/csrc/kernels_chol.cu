@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
     double* Xs = sm;                              // [ROWS][132]
     double* Ds = Xs + ROWS * TR_LDX;              // [4][32][36]
     double* Lb = Ds + 4 * 32 * TR_LDD;            // [96][100]: rows 32 .. 127 of L, columns 0 .. 32 (row / 32) - 1
+    double* Ts = Lb + 96 * TR_LDL;                // [ROWS][36]: T of the current block step (its own buffer: one barrier less per step)
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     double* Xg = X + static_cast<long>(blockIdx.x) * ROWS * ldx;
@@ -466,24 +467,29 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
                 acc[mi][ni][0] = v.x;
                 acc[mi][ni][1] = v.y;
             }
-        // T = X_b - X[:, 0:32b] * L[b-block rows, 0:32b]^T
+        // T = X_b - X[:, 0:32b] * L[b-block rows, 0:32b]^T   (8 b k-steps: unrolled by 8 so that the fragment loads run ahead)
         const double* Lrow = Lb + ((b - 1) * 32 + wn * NW + gid) * TR_LDL + tig;
-        for (int k0 = 0; k0 < 32 * b; k0 += 4) {
-            double af[2], bf[NI];
+        const double* Xrow = Xs + (row0 + gid) * TR_LDX + tig;
+#pragma unroll 1
+        for (int k1 = 0; k1 < 32 * b; k1 += 32) {
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi) af[mi] = -Xs[(row0 + mi * 8 + gid) * TR_LDX + k0 + tig];
+            for (int k0 = k1; k0 < k1 + 32; k0 += 4) {
+                double af[2], bf[NI];
 #pragma unroll
-            for (int ni = 0; ni < NI; ++ni) bf[ni] = Lrow[ni * 8 * TR_LDL + k0];
+                for (int mi = 0; mi < 2; ++mi) af[mi] = -Xrow[mi * 8 * TR_LDX + k0];
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
+                for (int ni = 0; ni < NI; ++ni) bf[ni] = Lrow[ni * 8 * TR_LDL + k0];
 #pragma unroll
-                for (int ni = 0; ni < NI; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < NI; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+            }
         }
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int ni = 0; ni < NI; ++ni)
-                *reinterpret_cast<double2*>(&Xs[(row0 + mi * 8 + gid) * TR_LDX + col0 + ni * 8 + 2 * tig]) =
+                *reinterpret_cast<double2*>(&Ts[(row0 + mi * 8 + gid) * TR_LDD + wn * NW + ni * 8 + 2 * tig]) =
                     make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         __syncthreads();        // T is visible
         // X_b = T * Dinv_b^T
@@ -495,7 +501,7 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
         for (int k0 = 0; k0 < 32; k0 += 4) {
             double af[2], bf[NI];
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi) af[mi] = Xs[(row0 + mi * 8 + gid) * TR_LDX + b * 32 + k0 + tig];
+            for (int mi = 0; mi < 2; ++mi) af[mi] = Ts[(row0 + mi * 8 + gid) * TR_LDD + k0 + tig];
 #pragma unroll
             for (int ni = 0; ni < NI; ++ni) bf[ni] = Ds[(b * 32 + wn * NW + ni * 8 + gid) * TR_LDD + k0 + tig];
 #pragma unroll
@@ -503,14 +509,13 @@ __global__ void __launch_bounds__(256) trsm_rows_kernel(double* __restrict__ X, 
 #pragma unroll
                 for (int ni = 0; ni < NI; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
         }
-        __syncthreads();        // all reads of T done before it is overwritten by X_b
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int ni = 0; ni < NI; ++ni)
                 *reinterpret_cast<double2*>(&Xs[(row0 + mi * 8 + gid) * TR_LDX + col0 + ni * 8 + 2 * tig]) =
                     make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-        __syncthreads();        // X_b visible to the next block step
+        __syncthreads();        // X_b visible to the next block step; every warp is done with T
     }
     // panel copy for the trailing update: 128 columns of a (rows x ldp) buffer (ldp = 256: two panels side by side)
     // rmaxq (optional): max |x| of every 64-column quarter of the solved rows, [row][2] at the caller's offset -- the
@@ -790,15 +795,16 @@ __global__ void __launch_bounds__(256, (BN == 128) ? 1 : 2) gemm_nt_sub_kernel(c
 // lower 32 x 32 sub-tiles, one CTA each, the 8 warps of a CTA splitting K (fixed-order reduction through shared
 // memory: bit-reproducible).
 // ---------------------------------------------------------------------------
+template <int K>
 __global__ void __launch_bounds__(256) diag_tile_update_kernel(double* __restrict__ C, long ldc,
-                                                               const double* __restrict__ A, long lda, int K) {
+                                                               const double* __restrict__ A, long lda) {
     extern __shared__ __align__(16) double dsm[];      // [8 warps][1024]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
     int sr = 0;
     while ((sr + 1) * (sr + 2) / 2 <= static_cast<int>(blockIdx.x)) ++sr;
     const int sc = static_cast<int>(blockIdx.x) - sr * (sr + 1) / 2;
-    const int kw = K / 8;                               // K range of this warp
+    constexpr int kw = K / 8;                           // K range of this warp
     const double* Ar = A + static_cast<long>(32 * sr + gid) * lda + warp * kw + tig;
     const double* Ac = A + static_cast<long>(32 * sc + gid) * lda + warp * kw + tig;
     double acc[4][4][2];
@@ -806,18 +812,21 @@ __global__ void __launch_bounds__(256) diag_tile_update_kernel(double* __restric
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-#pragma unroll 4
-    for (int k0 = 0; k0 < kw; k0 += 4) {
-        double af[4], bf[4];
+    // all fragment loads of the warp's K range are issued before the first MMA: ONE L2 round trip on the serial chain
+    double af[kw / 4][4], bf[kw / 4][4];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) af[mi] = Ar[static_cast<long>(mi) * 8 * lda + k0];
+    for (int ks = 0; ks < kw / 4; ++ks) {
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) bf[ni] = Ac[static_cast<long>(ni) * 8 * lda + k0];
+        for (int mi = 0; mi < 4; ++mi) af[ks][mi] = Ar[static_cast<long>(mi) * 8 * lda + 4 * ks];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) bf[ks][ni] = Ac[static_cast<long>(ni) * 8 * lda + 4 * ks];
+    }
+#pragma unroll
+    for (int ks = 0; ks < kw / 4; ++ks)
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-    }
+            for (int ni = 0; ni < 4; ++ni) dmma884_t(acc[mi][ni][0], acc[mi][ni][1], af[ks][mi], bf[ks][ni]);
     double* mine = dsm + warp * 1024;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
@@ -873,10 +882,12 @@ void launch_diag_tile_update(double* C, long ldc, const double* A, long lda, int
     bool& configured = configured_dev[dev_ & 63];
     const int smem = 8 * 1024 * static_cast<int>(sizeof(double));
     if (!configured) {
-        cudaFuncSetAttribute(diag_tile_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(diag_tile_update_kernel<EGX_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(diag_tile_update_kernel<2 * EGX_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
-    diag_tile_update_kernel<<<10, 256, smem, s>>>(C, ldc, A, lda, K);
+    if (K == EGX_NB) diag_tile_update_kernel<EGX_NB><<<10, 256, smem, s>>>(C, ldc, A, lda);
+    else diag_tile_update_kernel<2 * EGX_NB><<<10, 256, smem, s>>>(C, ldc, A, lda);
 }
 
 void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const double* Dinv, double* P, long ldp,
@@ -887,8 +898,8 @@ void launch_trsm_rows(double* X, long ldx, const double* Lkk, long ldl, const do
     cudaGetDevice(&dev_);
     bool& configured = configured_dev[dev_ & 63];   // the attribute is per device (one process may drive several)
     constexpr int smem_fixed = (4 * 32 * TR_LDD + 96 * TR_LDL) * static_cast<int>(sizeof(double));
-    constexpr int smem64 = 64 * TR_LDX * static_cast<int>(sizeof(double)) + smem_fixed;
-    constexpr int smem32 = 32 * TR_LDX * static_cast<int>(sizeof(double)) + smem_fixed;
+    constexpr int smem64 = 64 * (TR_LDX + TR_LDD) * static_cast<int>(sizeof(double)) + smem_fixed;
+    constexpr int smem32 = 32 * (TR_LDX + TR_LDD) * static_cast<int>(sizeof(double)) + smem_fixed;
     if (!configured) {
         cudaFuncSetAttribute(trsm_rows_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64);
         cudaFuncSetAttribute(trsm_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);

@@ -468,6 +468,60 @@ extern "C" int egx_sgp_predict_var(egx_sgp_ctx* c, const double* x, int m, doubl
     return sgp_predict_impl(c, x, m, nullptr, var);
 }
 EGX_ABI_CATCH
+// Trajectories of the sparse GP (sparse_algorithm.rs:338-364): mean = predict(x), covariance = sigma2 r(x, x) -- the PRIOR
+// covariance, as the reference's `_sample` takes it from `compute_k(x, x, ..)` --, then the decomposition shared with the dense GP.
+extern "C" int egx_sgp_sample(egx_sgp_ctx* c, const double* x, int m, const double* z, int n_traj, int method, double* out) try {
+    if (!c || !x || !z || !out || n_traj < 1) return EGX_INVALID_VALUE;
+    if (method != EGX_SAMPLE_CHOLESKY && method != EGX_SAMPLE_EIGENVALUES) {
+        egx_set_error("unknown sampling method %d", method);
+        return EGX_INVALID_VALUE;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->trained) {
+        egx_set_error("sparse GP sample before egx_sgp_finalize");
+        return EGX_INVALID_VALUE;
+    }
+    if (m < 1 || m > 8192) {
+        egx_set_error("sparse GP sample: 1 <= number of points <= 8192 (got %d)", m);
+        return EGX_INVALID_VALUE;
+    }
+    std::vector<double> mean_h(m);
+    int st = sgp_predict_impl(c, x, m, mean_h.data(), nullptr);
+    if (st != EGX_OK) return st;
+    EGX_CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int mpad = round_up(m, EGX_NB);
+    struct Tmp {
+        double *xs = nullptr, *K = nullptr, *mean = nullptr;
+        ~Tmp() {
+            egx_dev_free(xs);
+            egx_dev_free(K);
+            egx_dev_free(mean);
+        }
+    } t;
+    EGX_CUDA_TRY(egx_dev_malloc(&t.xs, static_cast<size_t>(mpad) * c->d * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&t.K, static_cast<size_t>(mpad) * mpad * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&t.mean, static_cast<size_t>(mpad) * sizeof(double)));
+    EGX_CUDA_TRY(cudaMemsetAsync(t.xs, 0, static_cast<size_t>(mpad) * c->d * sizeof(double), s));
+    EGX_CUDA_TRY(cudaMemcpyAsync(t.xs, x, static_cast<size_t>(m) * c->d * sizeof(double), cudaMemcpyHostToDevice, s));
+    EGX_CUDA_TRY(cudaMemsetAsync(t.mean, 0, static_cast<size_t>(mpad) * sizeof(double), s));
+    EGX_CUDA_TRY(cudaMemcpyAsync(t.mean, mean_h.data(), static_cast<size_t>(m) * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (c->env.ensure_panel_rows(mpad) != EGX_OK) return EGX_CUDA_ERROR;
+    {
+        // K = sigma2 r(x, x) with the kernel weights of the trained theta (still in c->terms after the finalize)
+        StageScope sc(c->env.prof, EGX_STAGE_CROSS_CORR, 1, s);
+        launch_cross_corr(c->corr, t.xs, m, mpad, c->zeros_d, c->ones_d, t.xs, m, mpad, c->d, c->terms, c->nterms, nullptr, nullptr,
+                          nullptr, nullptr, 0, 0.0, 1.0, t.K, mpad, nullptr, s, c->sigma2);
+    }
+    launch_cov_finish(t.K, mpad, m, mpad, nullptr, 0, 1.0, s);      // identity on the padding
+    st = sample_from_covariance(c->env, s, t.K, m, mpad, t.mean, z, n_traj, method, out);
+    if (st != EGX_OK) return st;
+    EGX_CUDA_TRY(cudaGetLastError());
+    c->env.prof.resolve();
+    return EGX_OK;
+}
+EGX_ABI_CATCH
+
 extern "C" int egx_sgp_set_profiling(egx_sgp_ctx* c, int enabled) try {
     if (!c) return EGX_INVALID_VALUE;
     std::lock_guard<std::mutex> lk(c->mu);

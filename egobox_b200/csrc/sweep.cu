@@ -1,6 +1,7 @@
 // Implementation of the shared sweep environment (see sweep.cuh).
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 #include "sweep.cuh"
 
@@ -513,4 +514,96 @@ void backsolve_vector(SweepEnv& env, const FactorRef& f, double* v) {
         launch_backsolve_diag(Lkk, f.ld, v + k * EGX_NB, env.sb);
         if (k > 0) launch_backsolve_update(f.M + static_cast<long>(k) * EGX_NB * f.ld, f.ld, v + k * EGX_NB, v, k, env.sb);
     }
+}
+
+// Trajectories from a covariance on the device (gp/src/algorithm.rs:1153-1194, shared by the dense and the sparse GP):
+// K (mpad x mpad, identity on the padding) is factorised in place -- Cholesky with the blocked sweep, or the host
+// eigen-decomposition with eigenvalues below 1e-9 dropped -- and out (m x n_traj, host) = mean + C z.
+int sample_from_covariance(SweepEnv& env, cudaStream_t s, double* K, int m, int mpad, const double* mean_dev, const double* z,
+                           int n_traj, int method, double* out) {
+    const int tpad = (n_traj + EGX_NB - 1) / EGX_NB * EGX_NB;
+    struct Tmp {
+        double *ZT = nullptr, *OUT = nullptr, *Dinv = nullptr;
+        int* info = nullptr;
+        ~Tmp() {
+            egx_dev_free(ZT);
+            egx_dev_free(OUT);
+            egx_dev_free(Dinv);
+            egx_dev_free(info);
+        }
+    } t;
+    EGX_CUDA_TRY(egx_dev_malloc(&t.ZT, static_cast<size_t>(tpad) * mpad * sizeof(double)));
+    EGX_CUDA_TRY(egx_dev_malloc(&t.OUT, static_cast<size_t>(mpad) * tpad * sizeof(double)));
+    // the normal draws, one trajectory per row (the B operand of the NT product)
+    std::vector<double> zt(static_cast<size_t>(tpad) * mpad, 0.0);
+    for (int i = 0; i < m; ++i)
+        for (int k = 0; k < n_traj; ++k) zt[static_cast<size_t>(k) * mpad + i] = z[static_cast<size_t>(i) * n_traj + k];
+    EGX_CUDA_TRY(cudaMemcpyAsync(t.ZT, zt.data(), zt.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+
+    if (method == EGX_SAMPLE_CHOLESKY) {
+        // cov = C C^T with the same blocked factorisation as the likelihood (algorithm.rs:1162-1168)
+        EGX_CUDA_TRY(egx_dev_malloc(&t.Dinv, static_cast<size_t>(mpad / EGX_NB) * 4096 * sizeof(double)));
+        EGX_CUDA_TRY(egx_dev_malloc(&t.info, sizeof(int)));
+        EGX_CUDA_TRY(cudaMemsetAsync(t.info, 0, sizeof(int), s));
+        FactorRef f;
+        f.M = K;
+        f.ld = mpad;
+        f.T = mpad / EGX_NB;
+        f.qpad = 0;
+        f.Dinv = t.Dinv;
+        f.info = t.info;
+        blocked_sweep(env, f, true, nullptr, 0, 0, 0);
+        int info_h = 0;
+        EGX_CUDA_TRY(cudaMemcpyAsync(&info_h, t.info, sizeof(int), cudaMemcpyDeviceToHost, s));
+        EGX_CUDA_TRY(cudaStreamSynchronize(s));
+        if (info_h != 0) {
+            egx_set_error("conditional covariance is not positive definite (pivot %d); use the eigenvalue method",
+                          info_h);
+            return EGX_NOT_POSITIVE_DEFINITE;
+        }
+        launch_zero_upper(K, mpad, mpad, s);
+    } else {
+        // C = W diag(sqrt(max(v, 0))) with eigenvalues below 1e-9 dropped (algorithm.rs:1169-1187); the m x m
+        // eigen-decomposition runs on the host, as in the reference
+        std::vector<double> a(static_cast<size_t>(m) * m), ev(m);
+        EGX_CUDA_TRY(cudaMemcpy2DAsync(a.data(), static_cast<size_t>(m) * sizeof(double), K,
+                                       static_cast<size_t>(mpad) * sizeof(double), static_cast<size_t>(m) * sizeof(double),
+                                       m, cudaMemcpyDeviceToHost, s));
+        EGX_CUDA_TRY(cudaStreamSynchronize(s));
+        if (egx_host_symmetric_eig(m, a.data(), ev.data()) != 0) {
+            egx_set_error("eigen-decomposition of the conditional covariance did not converge");
+            return EGX_INVALID_VALUE;
+        }
+        for (int j = 0; j < m; ++j) ev[j] = (ev[j] < 1e-9) ? 0.0 : std::sqrt(ev[j]);
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) a[static_cast<size_t>(i) * m + j] *= ev[j];
+        EGX_CUDA_TRY(cudaMemsetAsync(K, 0, static_cast<size_t>(mpad) * mpad * sizeof(double), s));
+        EGX_CUDA_TRY(cudaMemcpy2DAsync(K, static_cast<size_t>(mpad) * sizeof(double), a.data(),
+                                       static_cast<size_t>(m) * sizeof(double), static_cast<size_t>(m) * sizeof(double), m,
+                                       cudaMemcpyHostToDevice, s));
+        EGX_CUDA_TRY(cudaStreamSynchronize(s));      // `a` goes out of scope
+    }
+    // trajectories = mean + C Z   (algorithm.rs:1191-1193)
+    launch_bcast_rows(t.OUT, tpad, m, mpad, tpad, mean_dev, s);
+    {
+        GemmArgs g;
+        g.C = t.OUT;
+        g.ldc = tpad;
+        g.A = K;
+        g.lda = mpad;
+        g.B = t.ZT;
+        g.ldb = mpad;
+        g.K = mpad;
+        g.add = 1;
+        g.tri = 0;
+        g.Mt = mpad / EGX_NB;
+        g.Nt = tpad / EGX_NB;
+        StageScope sc(env.prof, EGX_STAGE_SYRK_GEMM, 1, s);
+        launch_gemm_nt_sub(g, s);
+    }
+    EGX_CUDA_TRY(cudaMemcpy2DAsync(out, static_cast<size_t>(n_traj) * sizeof(double), t.OUT,
+                                   static_cast<size_t>(tpad) * sizeof(double), static_cast<size_t>(n_traj) * sizeof(double),
+                                   m, cudaMemcpyDeviceToHost, s));
+    EGX_CUDA_TRY(cudaStreamSynchronize(s));
+    return EGX_OK;
 }

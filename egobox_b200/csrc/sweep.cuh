@@ -93,3 +93,9 @@ int egx_fill_terms(int corr, int d, int h, const double* w_star, const double* t
 
 // gamma-style single-vector back substitution  v <- L^-T v  with the blocked factor f (algorithm.rs:1034)
 void backsolve_vector(SweepEnv& env, const FactorRef& f, double* v);
+
+// Trajectories from a covariance on the device (gp/src/algorithm.rs:1153-1194): K (mpad x mpad, identity on the padding) is
+// factorised in place (method 0: Cholesky with the blocked sweep; 1: host eigen-decomposition, eigenvalues < 1e-9 dropped) and
+// out (m x n_traj, host) = mean + C z.  `s` must be env.sb.
+int sample_from_covariance(SweepEnv& env, cudaStream_t s, double* K, int m, int mpad, const double* mean_dev, const double* z,
+                           int n_traj, int method, double* out);

@@ -116,6 +116,18 @@ class SgpContext:
             _raise_status(st)
         return v
 
+    def sample(self, x, z, method=1):
+        """egx_sgp_sample: (m, n_traj) trajectories predict(x) + C z, C C^T = sigma2 r(x, x); z: (m, n_traj) normal draws,
+        method 0 = Cholesky, 1 = eigen-decomposition (sparse_algorithm.rs:338-364)."""
+        x = _f64(x).reshape(-1, self.d)
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(x.shape[0], -1)
+        out = np.empty_like(z)
+        st = self._lib.egx_sgp_sample(self._h, x.ctypes.data_as(_dp), x.shape[0], z.ctypes.data_as(_dp), z.shape[1], int(method),
+                                      out.ctypes.data_as(_dp))
+        if st != EGX_OK:
+            _raise_status(st)
+        return out
+
     def set_profiling(self, on=True):
         self._lib.egx_sgp_set_profiling(self._h, int(bool(on)))
 
@@ -297,6 +309,31 @@ class SparseGaussianProcess:
             _raise_status(st)
         return v
 
+    def _sample(self, x, n_traj, method, seed=None, z=None):
+        x = self._x(x)
+        if z is None:
+            # the reference draws from an unseeded generator (gp/src/algorithm.rs:1191-1192)
+            z = np.random.default_rng(seed).standard_normal((x.shape[0], int(n_traj)))
+        z = np.ascontiguousarray(z, dtype=np.float64).reshape(x.shape[0], -1)
+        out = np.empty_like(z)
+        st = self._lib.egx_sgp_model_sample(self._h, x.ctypes.data_as(_dp), x.shape[0], z.ctypes.data_as(_dp), z.shape[1],
+                                            int(method), out.ctypes.data_as(_dp))
+        if st != EGX_OK:
+            _raise_status(st)
+        return out
+
+    def sample_chol(self, x, n_traj, seed=None, z=None):
+        """sparse_algorithm.rs:338-341: (n, n_traj) trajectories, Cholesky of sigma2 r(x, x)."""
+        return self._sample(x, n_traj, 0, seed, z)
+
+    def sample_eig(self, x, n_traj, seed=None, z=None):
+        """sparse_algorithm.rs:343-346: eigen-decomposition (eigenvalues < 1e-9 dropped)."""
+        return self._sample(x, n_traj, 1, seed, z)
+
+    def sample(self, x, n_traj, seed=None, z=None):
+        """sparse_algorithm.rs:348-351: alias of sample_eig."""
+        return self.sample_eig(x, n_traj, seed, z)
+
     # sparse_algorithm.rs:298-336: the reference differentiates predict / predict_var by central differences with the
     # fixed step sqrt(eps) of the `finitediff` crate, one point and one coordinate at a time; here all 2 * n * nx shifted
     # points go through ONE batched device prediction
@@ -420,8 +457,6 @@ class SparseGpMix:
 
     def fit(self, xt, yt):
         from .gpx import _CORR
-        if self.corr_spec not in _CORR:
-            raise NotImplementedError("single corr_spec only (model selection by CV is egobox-moe's control plane)")
         xt = np.asarray(xt, dtype=np.float64)
         if xt.ndim == 1:
             xt = xt[:, None]
@@ -430,13 +465,27 @@ class SparseGpMix:
             if yt.shape[1] != 1:
                 raise ValueError("Bad training output data")
             yt = yt[:, 0]
+        corr_spec, self.cv_errors_ = self.corr_spec, None
+        if corr_spec not in _CORR:
+            # several correlation models: moe/src/algorithm.rs:209-260 decides by the 5-fold cross-validation error of the
+            # DENSE expert with constant mean (`compute_errors!` builds full GPs whatever the `gp_type`), then trains the
+            # sparse expert with the winner (:306-327)
+            from . import gp as _gp
+            from .moe import GpMixtureParams, _CORRS
+            allowed = [(nm, bit, c) for nm, bit, c in _CORRS if int(corr_spec) & bit]
+            if not allowed:
+                raise InvalidValueError("empty correlation specification")
+            cv = GpMixtureParams().set(kpls_dim=self.kpls_dim, w_star=self.w_star, device=self.device)
+            errs = [(nm, bit, cv._cv_error("Constant", _gp.ConstantMean, c, xt, yt)) for nm, bit, c in allowed]
+            self.cv_errors_ = {"Constant_%s" % nm: e for nm, _, e in errs}
+            corr_spec = min(errs, key=lambda e: e[2] if not np.isnan(e[2]) else np.inf)[1]
         if self.z is not None:
             ind = Inducings.Located(self.z)
         elif self.nz is not None:
             ind = Inducings.Randomized(self.nz)
         else:
             raise ValueError("You must specify inducing points")      # sparse_gp_mix.rs:176-178
-        p = SgpParams(_CORR[self.corr_spec], ind).sparse_method(self.method).n_start(self.n_start)
+        p = SgpParams(_CORR[corr_spec], ind).sparse_method(self.method).n_start(self.n_start)
         p = p.seed(_expert_seed(self.seed))
         p = p.device(self.device)
         if self.theta_init is not None:
@@ -445,7 +494,9 @@ class SparseGpMix:
             p = p.theta_bounds(self.theta_bounds)
         if self.kpls_dim is not None:
             p = p.kpls_dim(self.kpls_dim, self.w_star)
-        return SparseGpx(p.fit(xt, yt))
+        model = SparseGpx(p.fit(xt, yt))
+        model.cv_errors_ = self.cv_errors_
+        return model
 
 
 class SparseGpx:
@@ -485,5 +536,6 @@ class SparseGpx:
         """sparse_gp_mix.rs (SparseGpx.predict_var_gradients) -> sparse_algorithm.rs:318-336."""
         return self._gp.predict_var_gradients(np.asarray(x, dtype=np.float64))
 
-    def sample(self, x, n_traj):
-        raise NotImplementedError("trajectory sampling of the sparse GP (sparse_algorithm.rs:338-364) is not provided")
+    def sample(self, x, n_traj, seed=None, z=None):
+        """SparseGpx.sample (sparse_gp_mix.rs) -> sparse_algorithm.rs:348-364."""
+        return self._gp.sample(np.asarray(x, dtype=np.float64), n_traj, seed=seed, z=z)

@@ -391,6 +391,10 @@ int egx_sgp_finalize(egx_sgp_ctx* ctx, const double* theta, double sigma2, doubl
 /* predict :237-241, predict_var :245-257 (k^T inv k evaluated by two triangular sweeps, inv never formed) */
 int egx_sgp_predict(egx_sgp_ctx* ctx, const double* x, int m, double* y);
 int egx_sgp_predict_var(egx_sgp_ctx* ctx, const double* x, int m, double* var);
+/* sample_chol / sample_eig / sample, sparse_algorithm.rs:338-364: out (m x n_traj) = predict(x) + C z with C C^T = sigma2 r(x, x)
+ * (the reference's `_sample` takes the PRIOR covariance `compute_k(x, x, ..)`); z: m x n_traj standard normal draws of the caller,
+ * method: EGX_SAMPLE_CHOLESKY | EGX_SAMPLE_EIGENVALUES (decomposition as in gp/src/algorithm.rs:1153-1194); m <= 8192 */
+int egx_sgp_sample(egx_sgp_ctx* ctx, const double* x, int m, const double* z, int n_traj, int method, double* out);
 int egx_sgp_set_profiling(egx_sgp_ctx* ctx, int enabled);
 int egx_sgp_get_profile(egx_sgp_ctx* ctx, double* ms, long long* launches);
 
@@ -431,6 +435,7 @@ int egx_sgp_model_woodbury(egx_sgp_model* m, double* w_vec, double* w_inv);
 egx_sgp_ctx* egx_sgp_model_context(egx_sgp_model* m);
 int egx_sgp_model_predict(egx_sgp_model* m, const double* x, int npts, double* y);
 int egx_sgp_model_predict_var(egx_sgp_model* m, const double* x, int npts, double* var);
+int egx_sgp_model_sample(egx_sgp_model* m, const double* x, int npts, const double* z, int n_traj, int method, double* out);
 
 /* ============================================================================
  * Mixture of experts -- crates/moe/src/gaussian_mixture.rs + the recombination of

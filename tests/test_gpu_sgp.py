@@ -124,3 +124,51 @@ def test_sparse_prediction_gradients_are_the_reference_central_differences():
         np.testing.assert_allclose(gv[:, j], coarse_v, rtol=5e-3, atol=5e-4)
     gpx = eg.SparseGpx.builder(nz=20, seed=1).fit(x, y)
     assert gpx.predict_gradients(xq).shape == (25, 2) and gpx.predict_var_gradients(xq).shape == (25, 2)
+
+
+@pytest.mark.parametrize("corr,d,m", [(O.SQEXP, 1, 60), (O.MATERN52, 3, 150)])
+def test_sparse_trajectories_decompose_the_prior_covariance(corr, d, m):
+    """sparse_algorithm.rs:338-364: `_sample` = predict(x) + C z with C C^T = compute_k(x, x) = sigma2 r(x, x).  With z = I the
+    trajectories minus the mean ARE the factor C: its Gram matrix is held to the oracle's covariance for both decompositions
+    (Cholesky: lower triangular with a positive diagonal; eigenvalues below 1e-9 dropped: C C^T agrees to that level)."""
+    import egobox_b200 as eg
+    rng = np.random.default_rng(7 + m)
+    n = 400
+    x = 2 * rng.random((n, d)) - 1
+    y = np.sum(np.sin(3 * x), axis=1) + rng.normal(0, 0.1, n)
+    z_ind = S.make_inducings(40, x, rng)
+    theta = np.full(d, 60.0 if corr == O.SQEXP else 3.0)     # keeps sigma2 r(xs, xs) factorisable by Cholesky
+    sigma2, noise, nug = 0.7, 0.02, 1e-8
+    ctx = eg.SgpContext(x, y, z_ind, corr=corr, method=S.FITC, nugget=nug)
+    st, _ = ctx.finalize(theta, sigma2, noise)
+    assert st == 0
+    xs = 2 * rng.random((m, d)) - 1
+    mean = ctx.predict(xs)
+    cov = S.compute_k(corr, xs, xs, np.eye(d), theta, sigma2)
+    for method, tol in ((0, 1e-9), (1, 2e-7)):
+        c = ctx.sample(xs, np.eye(m), method=method) - mean[:, None]
+        np.testing.assert_allclose(c @ c.T, cov, rtol=0, atol=tol)
+        if method == 0:
+            assert np.allclose(np.triu(c, 1), 0.0, atol=1e-12) and np.all(np.diag(c) > 0)
+    # two trajectories from the caller's draws: linear in z
+    zz = rng.standard_normal((m, 2))
+    tr = ctx.sample(xs, zz, method=0)
+    c = ctx.sample(xs, np.eye(m), method=0) - mean[:, None]
+    np.testing.assert_allclose(tr, mean[:, None] + c @ zz, rtol=0, atol=1e-9)
+    ctx.close()
+
+
+def test_sparse_gpx_chooses_the_correlation_model_by_cross_validation():
+    """python/src/sparse_gp_mix.rs with corr_spec = SQUARED_EXPONENTIAL | MATERN52 -> moe/src/algorithm.rs:209-260: the 5-fold
+    error of the dense constant-mean expert decides, the sparse model is then trained with the winner."""
+    import egobox_b200 as eg
+    xt, yt, _ = make_1d(nt=120)
+    model = eg.SparseGpx.builder(corr_spec=1 | 8, nz=20, seed=0, n_start=2).fit(xt, yt)
+    errs = model.cv_errors_
+    assert set(errs) == {"Constant_SquaredExponential", "Constant_Matern52"} and all(np.isfinite(v) for v in errs.values())
+    want = min(errs, key=errs.get).split("_")[1]
+    assert want in str(model._gp)                               # "SGP(corr=<name>, ...)"
+    xs = np.linspace(-1, 1, 50)[:, None]
+    assert np.sqrt(np.mean((model.predict(xs) - f_obj(xs)[:, 0]) ** 2)) < 0.3
+    tr = model.sample(xs, 3, seed=1)
+    assert tr.shape == (50, 3) and np.all(np.isfinite(tr))
