@@ -281,6 +281,9 @@ __global__ void __launch_bounds__(256, 1) potrf_diag2_kernel(double* __restrict_
             }
             const double dg = S[(c0 + lane) * P2_LD + c0 + lane];
             double* lb = lbuf + warp * 64;
+            // every warp of the phase has its copy of the diagonal block before warp 0 may write the factor over it (it does so
+            // ~6 k clk later; compute-sanitizer racecheck rightly wants the order stated): named barrier of the 32 * npanel threads
+            if (npanel >= 2) asm volatile("bar.sync 1, %0;" ::"r"(32 * npanel) : "memory");
             if (tid == 0) POTRF_STAMP(2 + 4 * b);     // registers loaded (diagonal block)
 #ifdef POTRF_ONE_INST
             if (true) {
