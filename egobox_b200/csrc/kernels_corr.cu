@@ -12,6 +12,8 @@
 // SASS UBLKCP) completing on an mbarrier; the column tile is then transposed
 // in shared memory so that the 16 lanes of a half-warp read 16 consecutive
 // double2 (conflict free), and results leave as coalesced 16-byte stores.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/egobox_gpu.h"
 
@@ -110,18 +112,18 @@ __device__ __forceinline__ double pair_finish_s(double acc, double prod) {
     return prod * exp(-acc);
 }
 // scaled, term-major copy of a 64-row coordinate tile: out[t][r] = c_t X[r][dim(t)]
-template <int CORR>
+template <int CORR, int ROWS = EGX_CT>
 __device__ __forceinline__ void scale_tile(const double* __restrict__ Xrow, const CorrTerm* __restrict__ terms, int nterms, int d,
                                            double* __restrict__ out, int tid) {
-    for (int e = tid; e < nterms * EGX_CT; e += 256) {
-        const int t = e / EGX_CT, r = e - t * EGX_CT;
+    for (int e = tid; e < nterms * ROWS; e += 256) {
+        const int t = e / ROWS, r = e - t * ROWS;
         out[e] = term_coef<CORR>(terms[t]) * Xrow[r * d + terms[t].dim];
     }
 }
 
 // Each of the 256 threads owns a 4 x 4 patch of the 64 x 64 tile:
 // rows ty + 16*ri, columns 2*tx + 32*cj + {0,1}.  XiS / XjS: scaled term-major tiles [nterms][64].
-template <int CORR>
+template <int CORR, int STRIDE = EGX_CT>
 __device__ __forceinline__ void tile_values(const double* __restrict__ XiS, const double* __restrict__ XjS, int nterms, int ty,
                                             int tx, double (&out)[4][4]) {
     double acc[4][4], prod[4][4];
@@ -135,9 +137,9 @@ __device__ __forceinline__ void tile_values(const double* __restrict__ XiS, cons
     for (int t = 0; t < nterms; ++t) {
         double xi[4];
 #pragma unroll
-        for (int ri = 0; ri < 4; ++ri) xi[ri] = XiS[t * EGX_CT + ty + 16 * ri];
-        const double2 xa = *reinterpret_cast<const double2*>(&XjS[t * EGX_CT + 2 * tx]);
-        const double2 xb = *reinterpret_cast<const double2*>(&XjS[t * EGX_CT + 2 * tx + 32]);
+        for (int ri = 0; ri < 4; ++ri) xi[ri] = XiS[t * STRIDE + ty + 16 * ri];
+        const double2 xa = *reinterpret_cast<const double2*>(&XjS[t * STRIDE + 2 * tx]);
+        const double2 xb = *reinterpret_cast<const double2*>(&XjS[t * STRIDE + 2 * tx + 32]);
         const double xj[4] = {xa.x, xa.y, xb.x, xb.y};
 #pragma unroll
         for (int ri = 0; ri < 4; ++ri)
@@ -215,6 +217,68 @@ __global__ void __launch_bounds__(256)
             if (i == j) a = (i < n) ? diag_value : 1.0;
             if (i == j + 1) b = (i < n) ? diag_value : 1.0;
             *reinterpret_cast<double2*>(&M[static_cast<long>(i) * ld + j]) = make_double2(a, b);
+        }
+    }
+}
+
+// K1, one CTA per 128 x 128 block (r02): the two 128-row coordinate strips are loaded and scaled ONCE for the four 64 x 64
+// sub-tiles.  With a CTA per sub-tile the prologue (bulk copy + scaling + three barriers, ~2.5 k clk) stood against 1.9 k clk
+// of arithmetic for the squared exponential at d = 6 and 4.3 k for Matern-5/2 at d = 10 (profiles/r02/y12_corr_*.txt).  Used
+// while the strips fit beside a second CTA (d + nterms <= 46); larger dimensions keep the per-sub-tile kernel.
+template <int CORR>
+__global__ void __launch_bounds__(256)
+    corr_build128_kernel(const double* __restrict__ X, int n, int d, const CorrTerm* __restrict__ gterms,
+                         int nterms, double* __restrict__ M, long ld, double diag_value, double scale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* Xi = reinterpret_cast<double*>(smem_raw + 16);
+    double* Xj = Xi + EGX_NB * d;
+    double* XiS = Xj + EGX_NB * d;
+    double* XjS = XiS + EGX_NB * nterms;
+    CorrTerm* terms = reinterpret_cast<CorrTerm*>(XjS + EGX_NB * nterms);
+
+    const int tid = threadIdx.x;
+    int R, C;
+    tri_decode(blockIdx.x, R, C);
+    const int I0 = R * EGX_NB, J0 = C * EGX_NB;
+    const uint32_t bytes = static_cast<uint32_t>(EGX_NB * d * sizeof(double));
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, 2 * bytes);
+        bulk_g2s(Xi, X + static_cast<long>(I0) * d, bytes, bar);
+        bulk_g2s(Xj, X + static_cast<long>(J0) * d, bytes, bar);
+    }
+    for (int t = tid; t < nterms; t += 256) terms[t] = gterms[t];
+    __syncthreads();                 // the term list is read by every thread below
+    mbar_wait(bar, 0);
+    scale_tile<CORR, EGX_NB>(Xi, terms, nterms, d, XiS, tid);
+    scale_tile<CORR, EGX_NB>(Xj, terms, nterms, d, XjS, tid);
+    __syncthreads();
+
+    const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll 1
+    for (int sub = 0; sub < 4; ++sub) {
+        const int i0 = I0 + (sub >> 1) * EGX_CT, j0 = J0 + (sub & 1) * EGX_CT;
+        double v[4][4];
+        tile_values<CORR, EGX_NB>(XiS + (sub >> 1) * EGX_CT, XjS + (sub & 1) * EGX_CT, nterms, ty, tx, v);
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) {
+            const int i = i0 + ty + 16 * ri;
+#pragma unroll
+            for (int cj = 0; cj < 2; ++cj) {
+                const int j = j0 + 2 * tx + 32 * cj;
+                double a = scale * v[ri][2 * cj], b = scale * v[ri][2 * cj + 1];
+                if (i >= n || j >= n) a = 0.0;
+                if (i >= n || j + 1 >= n) b = 0.0;
+                if (i == j) a = (i < n) ? diag_value : 1.0;
+                if (i == j + 1) b = (i < n) ? diag_value : 1.0;
+                *reinterpret_cast<double2*>(&M[static_cast<long>(i) * ld + j]) = make_double2(a, b);
+            }
         }
     }
 }
@@ -456,11 +520,21 @@ void set_smem(K kernel, size_t bytes) {
 void launch_corr_build(int corr, const double* X, int n, int npad, int d, const CorrTerm* terms, int nterms,
                        double* M, long ld, double diag_value, cudaStream_t s, double scale) {
     const int T = npad / EGX_NB;
-    const int grid = 4 * (T * (T + 1) / 2);
-    const size_t smem = corr_build_smem(d, nterms);
+    // one CTA per 128 x 128 block while the two 128-row strips (raw + scaled) leave room for a second CTA on the SM
+    // (EGX_CORR_TILE=64 keeps the r01 form: one CTA per 64 x 64 sub-tile)
+    static const int force64 = getenv("EGX_CORR_TILE") != nullptr && atoi(getenv("EGX_CORR_TILE")) == 64;
+    const size_t smem128 = 16 + 2 * EGX_NB * (static_cast<size_t>(d) + nterms) * sizeof(double) + nterms * sizeof(CorrTerm);
+    const bool big = !force64 && smem128 <= 96 * 1024;
+    const int grid = (big ? 1 : 4) * (T * (T + 1) / 2);
+    const size_t smem = big ? smem128 : corr_build_smem(d, nterms);
 #define EGX_LAUNCH_K1(CK)                                                                         \
-    set_smem(corr_build_kernel<CK>, smem);                                                        \
-    corr_build_kernel<CK><<<grid, 256, smem, s>>>(X, n, d, terms, nterms, M, ld, diag_value, scale);
+    if (big) {                                                                                    \
+        set_smem(corr_build128_kernel<CK>, smem);                                                 \
+        corr_build128_kernel<CK><<<grid, 256, smem, s>>>(X, n, d, terms, nterms, M, ld, diag_value, scale); \
+    } else {                                                                                      \
+        set_smem(corr_build_kernel<CK>, smem);                                                    \
+        corr_build_kernel<CK><<<grid, 256, smem, s>>>(X, n, d, terms, nterms, M, ld, diag_value, scale); \
+    }
     switch (corr) {
         case EGX_CORR_SQUARED_EXPONENTIAL: EGX_LAUNCH_K1(EGX_CORR_SQUARED_EXPONENTIAL) break;
         case EGX_CORR_ABSOLUTE_EXPONENTIAL: EGX_LAUNCH_K1(EGX_CORR_ABSOLUTE_EXPONENTIAL) break;
