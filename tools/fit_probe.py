@@ -15,6 +15,8 @@ for n in [int(a) for a in sys.argv[1:]] or [2000, 8192]:
     d = 10
     x, y = make_problem(n, d, seed=42)
     prm = eg.GaussianProcess.params(eg.ConstantMean, eg.Matern52Corr).cobyla_ftol_rel(0.0)
+    if os.environ.get("PROBE_NSTART"):                     # n_start + 1 chains (what one rank of a sharded fit carries)
+        prm = prm.n_start(int(os.environ["PROBE_NSTART"]))
     if n <= 2500:
         prm.fit(x, y).close()                              # warm-up (module load, graph captures)
     for rep in range(2 if n > 2500 else 1):                # the second fit of a large problem is the warm one (block cache, modules)
