@@ -834,6 +834,9 @@ extern "C" int egx_gp_fit(const egx_gp_params* prm, const double* x, int n, int 
                     chain_of[slot] = -1;
                     return EGX_OK;
                 };
+                // (measured and dropped, profiles/r02/y16_stagger.txt: starting the chains 1-4 ms apart, so that the bulk-heavy
+                //  first half of one evaluation would meet the chain-bound second half of another, changes nothing: 3.88-3.90 ms
+                //  per evaluation with two chains at n = 8192 whatever the offset)
                 for (int sl = 0; sl < slots; ++sl) {
                     st = feed(sl);
                     if (st != EGX_OK) return st;
