@@ -65,6 +65,7 @@ int SweepEnv::init(int max_block_cols) {
     ev_trsm_a.assign(npairs, nullptr);
     ev_partner.assign(npairs, nullptr);
     ev_colrest.assign(npairs, nullptr);
+    ev_slice.assign(npairs, nullptr);
     for (int k = 0; k < max_block_cols; ++k) {
         EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
         EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_bulk[k], cudaEventDisableTiming));
@@ -73,11 +74,13 @@ int SweepEnv::init(int max_block_cols) {
         EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_trsm_a[k], cudaEventDisableTiming));
         EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_partner[k], cudaEventDisableTiming));
         EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_colrest[k], cudaEventDisableTiming));
+        EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_slice[k], cudaEventDisableTiming));
     }
     EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     EGX_CUDA_TRY(cudaEventCreateWithFlags(&ev_join_q, cudaEventDisableTiming));
     if (const char* v = getenv("EGX_LOOKAHEAD_V")) lookahead_v = atoi(v);
+    if (const char* v = getenv("EGX_LA_OZAKI")) la_ozaki = atoi(v);
     bs_flags_n = max_block_cols;
     EGX_CUDA_TRY(egx_dev_malloc(&bs_flags, static_cast<size_t>(max_block_cols > 0 ? max_block_cols : 1) * sizeof(int)));
     const char* e = getenv("EGX_LOOKAHEAD");
@@ -100,8 +103,10 @@ int SweepEnv::ensure_panel_rows(long rows) {
     }
     egx_dev_free(oz_S);
     egx_dev_free(oz_scale);
-    oz_S = nullptr;
-    oz_scale = nullptr;
+    egx_dev_free(oz_S2);
+    egx_dev_free(oz_scale2);
+    oz_S = oz_S2 = nullptr;
+    oz_scale = oz_scale2 = nullptr;
     for (int i = 0; i < 2; ++i) {
         egx_dev_free(oz_rmaxq[i]);
         oz_rmaxq[i] = nullptr;
@@ -109,6 +114,10 @@ int SweepEnv::ensure_panel_rows(long rows) {
     if (ozaki) {
         EGX_CUDA_TRY(egx_dev_malloc(&oz_S, ozaki_slice_bytes(rows)));
         EGX_CUDA_TRY(egx_dev_malloc(&oz_scale, static_cast<size_t>(rows) * sizeof(double)));
+        if (la_ozaki) {
+            EGX_CUDA_TRY(egx_dev_malloc(&oz_S2, ozaki_slice_bytes(rows)));
+            EGX_CUDA_TRY(egx_dev_malloc(&oz_scale2, static_cast<size_t>(rows) * sizeof(double)));
+        }
         for (int i = 0; i < 2; ++i) EGX_CUDA_TRY(egx_dev_malloc(&oz_rmaxq[i], static_cast<size_t>(rows) * 4 * sizeof(double)));
     }
     p_rows = rows;
@@ -121,7 +130,7 @@ void SweepEnv::destroy() {
     if (sp) cudaStreamSynchronize(sp);
     if (sq) cudaStreamSynchronize(sq);
     prof.destroy();
-    for (auto* vec : {&ev_panel, &ev_bulk, &ev_trsm_a, &ev_partner, &ev_colrest}) {
+    for (auto* vec : {&ev_panel, &ev_bulk, &ev_trsm_a, &ev_partner, &ev_colrest, &ev_slice}) {
         for (auto e : *vec)
             if (e) cudaEventDestroy(e);
         vec->clear();
@@ -136,8 +145,10 @@ void SweepEnv::destroy() {
     egx_dev_free(P2[1]);
     egx_dev_free(oz_S);
     egx_dev_free(oz_scale);
-    oz_S = nullptr;
-    oz_scale = nullptr;
+    egx_dev_free(oz_S2);
+    egx_dev_free(oz_scale2);
+    oz_S = oz_S2 = nullptr;
+    oz_scale = oz_scale2 = nullptr;
     for (int i = 0; i < 2; ++i) {
         egx_dev_free(oz_rmaxq[i]);
         oz_rmaxq[i] = nullptr;
@@ -256,6 +267,40 @@ static void factor_sweep_lookahead(SweepEnv& env, const FactorRef& f) {
         }
         const int nla = tri2 < 2 ? tri2 : 2;
         const int rest2 = tri2 - 1 + Qt;
+        // tcgen05 for the look-ahead columns too (r02b): the panel rows from block k+2 on are sliced ONCE on `sq`, the columns of
+        // the next pair are updated from those slices in the rectangular form and the bulk update on `sb` reuses them -- the
+        // 2 x rest2 tiles of K = 256 leave the FP64 pipe (0.3 ms of DMMA per evaluation at n = 8192, a sixth of the GPU work of
+        // an evaluation at n = 4096).  Slices are double-buffered by pair: the bulk update of pair p may still read its slices
+        // when pair p + 1 is sliced.
+        const bool oz_la = env.la_ozaki && env.ozaki && env.oz_S != nullptr && env.oz_S2 != nullptr && T >= env.ozaki_min_T &&
+                           tri2 - 2 >= env.ozaki_min_tri && static_cast<long>(tri2 + Qt) * EGX_NB <= env.p_rows;
+        if (oz_la) {
+            int8_t* S = (pair & 1) ? env.oz_S2 : env.oz_S;
+            double* sc = (pair & 1) ? env.oz_scale2 : env.oz_scale;
+            const size_t rb = ozaki_slice_bytes(EGX_NB);        // bytes of the slices of one 128-row block
+            cudaStreamWaitEvent(sq, env.ev_panel[pair], 0);
+            if (pair > 0) cudaStreamWaitEvent(sq, env.ev_bulk[pair - 1], 0);
+            {
+                StageScope sc1(env.prof, EGX_STAGE_OZAKI_SLICE, Rq ? 1 : 2, sq);
+                launch_ozaki_slice(Pw + static_cast<long>(EGX_NB) * LDP, LDP, (tri2 + Qt) * EGX_NB, sc, S, sq,
+                                   Rq ? Rq + static_cast<long>(EGX_NB) * 4 : nullptr);
+            }
+            cudaEventRecord(env.ev_slice[pair], sq);
+            {
+                StageScope sc2(env.prof, EGX_STAGE_GEMM_LOOKAHEAD, 1, sq);
+                launch_ozaki_gemm(blk(k + 3, k + 2), ld, S + rb, sc + EGX_NB, S, sc, rest2, nla, sq, env.oz_persist);
+            }
+            cudaEventRecord(env.ev_colrest[pair], sq);
+            rest_pending = true;
+            cudaStreamWaitEvent(sb, env.ev_panel[pair], 0);
+            cudaStreamWaitEvent(sb, env.ev_slice[pair], 0);
+            {
+                StageScope sc3(env.prof, EGX_STAGE_OZAKI_SYRK, 1, sb);
+                launch_ozaki_syrk(blk(k + 4, k + 4), ld, S + 2 * rb, sc + 2 * EGX_NB, tri2 - 2 + Qt, tri2 - 2, sb, nullptr, env.oz_persist);
+            }
+            cudaEventRecord(env.ev_bulk[pair], sb);
+            continue;
+        }
         if (rest2 > 0) {
             cudaStreamWaitEvent(sq, env.ev_panel[pair], 0);
             if (pair > 0) cudaStreamWaitEvent(sq, env.ev_bulk[pair - 1], 0);

@@ -39,7 +39,7 @@ struct SweepEnv {
     cudaStream_t sq = nullptr;   // high-priority stream of the column updates that run beside the diagonal-block chain (r02)
     bool lookahead = true;
     std::vector<cudaEvent_t> ev_panel, ev_bulk;
-    std::vector<cudaEvent_t> ev_trsm_a, ev_partner, ev_colrest;   // r02 look-ahead: per column pair
+    std::vector<cudaEvent_t> ev_trsm_a, ev_partner, ev_colrest, ev_slice;   // r02 look-ahead: per column pair
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_q = nullptr;
     int lookahead_v = 2;                  // EGX_LOOKAHEAD_V=1: the r01 schedule (whole columns on the panel stream)
     double* P2[2] = {nullptr, nullptr};   // double-buffered contiguous panel copies (rows x 128)
@@ -47,6 +47,9 @@ struct SweepEnv {
     // tcgen05 path of the trailing update (kernels_ozaki.cu): int8 slices + row scales of the current panel pair
     int8_t* oz_S = nullptr;
     double* oz_scale = nullptr;
+    int8_t* oz_S2 = nullptr;              // second slice / scale buffer: the look-ahead schedule slices pair p + 1 on `sq` while the bulk
+    double* oz_scale2 = nullptr;          // update of pair p still reads the slices of pair p on `sb` (buffer = pair & 1)
+    int la_ozaki = 1;                     // EGX_LA_OZAKI=0: look-ahead column updates on the DMMA kernel (r02 first form)
     double* oz_rmaxq[2] = {nullptr, nullptr};   // [row][4] quarter-row maxima written by the panel solves, per P2 buffer
     int ozaki = 1;                        // EGX_OZAKI=0 keeps every update on the DMMA kernel
     int oz_persist = 0;                   // set by the batched entry point: several evaluations share the GPU
