@@ -837,7 +837,7 @@ extern "C" int egx_gp_reduced_likelihood_batch(egx_gp_ctx* c, const double* thet
             w->env.oz_persist = (W > 1) ? 1 : 0;
             const bool la_saved = w->env.lookahead;
             if (batch_la >= 0) w->env.lookahead = la_saved && batch_la != 0;
-            else if (W >= 6 && w->env.ozaki && (c->npad > 4096 || c->npad <= 2048)) w->env.lookahead = false;   // measured r02 (y3 / y4): C5 n = 2048 72 -> 66 ms, n = 4096 expert fit 1.91 -> 2.05 ms per evaluation
+            else if (W >= 6 && w->env.ozaki && c->npad > 4096) w->env.lookahead = false;   // re-measured with the look-ahead columns on tcgen05 (profiles/r02/y19_*.txt): look-ahead ON wins up to n = 4096 (C5 n = 2048: 70.9 -> 62.0 ms, n = 4096: 0.570 -> 0.541 ms per evaluation), ties at n = 8192 (3.20 vs 3.22)
             status[b] = evaluate_launch(w, thetas + static_cast<long>(b) * c->h);
             w->env.lookahead = la_saved;
             if (status[b] == EGX_CUDA_ERROR) return EGX_CUDA_ERROR;
@@ -900,7 +900,7 @@ extern "C" int egx_gp_eval_begin(egx_gp_ctx* c, int slot, const double* theta) t
     w->env.oz_persist = (W > 1) ? 1 : 0;
     const bool la_saved = w->env.lookahead;
     if (batch_la >= 0) w->env.lookahead = la_saved && batch_la != 0;
-    else if (W >= 6 && w->env.ozaki && (c->npad > 4096 || c->npad <= 2048)) w->env.lookahead = false;   // measured r02 (y3 / y4): C5 n = 2048 72 -> 66 ms, n = 4096 expert fit 1.91 -> 2.05 ms per evaluation
+    else if (W >= 6 && w->env.ozaki && c->npad > 4096) w->env.lookahead = false;   // re-measured with the look-ahead columns on tcgen05 (profiles/r02/y19_*.txt): look-ahead ON wins up to n = 4096 (C5 n = 2048: 70.9 -> 62.0 ms, n = 4096: 0.570 -> 0.541 ms per evaluation), ties at n = 8192 (3.20 vs 3.22)
     const int st = evaluate_launch(w, theta);
     w->env.lookahead = la_saved;
     return st;
