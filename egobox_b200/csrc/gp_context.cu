@@ -1005,25 +1005,42 @@ extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const doub
             fr.Lsc_off = c->Lsc_off.data();
         }
     }
+    // r02b: the column panels of W W^T do not wait for the whole sweep -- panel kp only needs the two block columns of pair kp,
+    // final as soon as the sweep has solved them.  The sweep records one event per pair; -R^-1 is accumulated on the side stream
+    // `sq` from its own slice buffers, so its tcgen05 launches fill the gaps the sweep's small kernels (two solves, the K = 128
+    // partner update, slicing: ~60 us per pair) leave on the GPU.  EGX_GRAD_PIPELINE=0 restores the serial order.
+    static const int pipeline = getenv("EGX_GRAD_PIPELINE") != nullptr ? atoi(getenv("EGX_GRAD_PIPELINE")) : 1;
+    const bool oz = c->env.ozaki && c->env.oz_S != nullptr && T >= c->env.ozaki_min_T;
+    const bool piped = pipeline && c->env.sq != nullptr && c->env.oz_S2 != nullptr && static_cast<int>(c->env.ev_partner.size()) >= (T + 1) / 2;
+    cudaStream_t sw = piped ? c->env.sq : c->stream;              // stream of the W W^T accumulation
+    int8_t* wS = piped ? c->env.oz_S2 : c->env.oz_S;
+    double* wScale = piped ? c->env.oz_scale2 : c->env.oz_scale;
+    if (piped) {
+        cudaEventRecord(c->env.ev_fork, c->stream);              // the evaluation (and whatever used tgRinv before) is ahead of sq
+        cudaStreamWaitEvent(sw, c->env.ev_fork, 0);
+        EGX_CUDA_TRY(cudaMemsetAsync(c->tgRinv, 0, static_cast<size_t>(npad) * npad * sizeof(double), sw));
+        c->env.solve_pair_events = &c->env.ev_partner;
+    }
     blocked_sweep(c->env, fr, false, c->tgW, npad, T, npad / 64, true);
+    c->env.solve_pair_events = nullptr;
     {
         StageScope sc(c->env.prof, EGX_STAGE_BACKSOLVE, 1, c->stream);   // gamma = L^-T rho = W rho (algorithm.rs:1034)
         launch_upper_gemv(c->tgW, npad, c->n, c->rho, c->tgGamma, c->stream);
     }
     // -R^-1 = 0 - W W^T, lower block triangle
-    EGX_CUDA_TRY(cudaMemsetAsync(c->tgRinv, 0, static_cast<size_t>(npad) * npad * sizeof(double), c->stream));
-    const bool oz = c->env.ozaki && c->env.oz_S != nullptr && T >= c->env.ozaki_min_T;
+    if (!piped) EGX_CUDA_TRY(cudaMemsetAsync(c->tgRinv, 0, static_cast<size_t>(npad) * npad * sizeof(double), c->stream));
     for (int k = 0; k < T; k += 2) {
         const int kw = (k + 1 < T) ? 2 : 1;                   // block columns in this panel
         const int rt = k + kw;                                // tile rows of W that are non-zero in it
         const double* P = c->tgW + static_cast<long>(k) * EGX_NB;
+        if (piped) cudaStreamWaitEvent(sw, c->env.ev_partner[k >> 1], 0);
         if (oz && kw == 2 && rt >= c->env.ozaki_min_tri) {
             {
-                StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SLICE, 2, c->stream);
-                launch_ozaki_slice(P, npad, rt * EGX_NB, c->env.oz_scale, c->env.oz_S, c->stream);
+                StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SLICE, 2, sw);
+                launch_ozaki_slice(P, npad, rt * EGX_NB, wScale, wS, sw);
             }
-            StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SYRK, 1, c->stream);
-            launch_ozaki_syrk(c->tgRinv, npad, c->env.oz_S, c->env.oz_scale, rt, rt, c->stream);
+            StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SYRK, 1, sw);
+            launch_ozaki_syrk(c->tgRinv, npad, wS, wScale, rt, rt, sw);
         } else {
             GemmArgs g;
             g.C = c->tgRinv;
@@ -1035,9 +1052,13 @@ extern "C" int egx_gp_reduced_likelihood_grad_analytic(egx_gp_ctx* c, const doub
             g.K = kw * EGX_NB;
             g.tri = rt;
             g.Mt = g.Nt = rt;
-            StageScope sc(c->env.prof, EGX_STAGE_SYRK_GEMM, 1, c->stream);
-            launch_gemm_nt_sub(g, c->stream);
+            StageScope sc(c->env.prof, EGX_STAGE_SYRK_GEMM, 1, sw);
+            launch_gemm_nt_sub(g, sw);
         }
+    }
+    if (piped) {
+        cudaEventRecord(c->env.ev_join_q, sw);
+        cudaStreamWaitEvent(c->stream, c->env.ev_join_q, 0);
     }
     {
         StageScope sc(c->env.prof, EGX_STAGE_THETA_GRAD, 2, c->stream);

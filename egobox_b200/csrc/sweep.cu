@@ -386,7 +386,10 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
             launch_trsm_rows(rows + static_cast<long>(k) * EGX_NB, ld_rows, blk(k, k), ld,
                              f.Dinv + static_cast<long>(k) * 4096, Pw, LDP, slabs64, sp, Rq);
         }
-        if (!two) break;
+        if (!two) {
+            if (!factor && env.solve_pair_events != nullptr) cudaEventRecord((*env.solve_pair_events)[pair], sp);
+            break;
+        }
         const int tri1 = T - k - 1;                    // block columns right of k
         // ---- partner column k+1: K = 128 update with panel A ------------------------------------------
         {
@@ -433,6 +436,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
         }
         const int tri2 = T - k - 2;                    // block columns right of the pair
         if (la) cudaEventRecord(env.ev_panel[pair], sp);
+        if (!factor && env.solve_pair_events != nullptr) cudaEventRecord((*env.solve_pair_events)[pair], sp);
         if (tri2 <= 0) continue;                       // nothing right of the pair (appended rows only touch existing columns)
         // ---- trailing update with K = 256 ---------------------------------------------------------------
         GemmArgs g;

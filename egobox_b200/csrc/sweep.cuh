@@ -49,6 +49,7 @@ struct SweepEnv {
     double* oz_scale = nullptr;
     int8_t* oz_S2 = nullptr;              // second slice / scale buffer: the look-ahead schedule slices pair p + 1 on `sq` while the bulk
     double* oz_scale2 = nullptr;          // update of pair p still reads the slices of pair p on `sb` (buffer = pair & 1)
+    std::vector<cudaEvent_t>* solve_pair_events = nullptr;   // solves only: event [pair] recorded when the two block columns of a pair are final
     int la_ozaki = 1;                     // EGX_LA_OZAKI=0: look-ahead column updates on the DMMA kernel (r02 first form)
     double* oz_rmaxq[2] = {nullptr, nullptr};   // [row][4] quarter-row maxima written by the panel solves, per P2 buffer
     int ozaki = 1;                        // EGX_OZAKI=0 keeps every update on the DMMA kernel
