@@ -174,3 +174,19 @@ def test_every_gpu_test_module_is_marked():
         if f.startswith("test_gpu_") and f.endswith(".py"):
             src = open(os.path.join(tests, f)).read()
             assert re.search(r"^pytestmark = .*pytest\.mark\.gpu", src, flags=re.M), f
+
+
+def test_documented_switches_exist_in_the_sources():
+    """Every EGX_* environment switch the README documents is read somewhere in the library or the bench (a renamed or
+    removed switch must leave the table too)."""
+    import re
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    documented = set(re.findall(r"`(EGX_[A-Z0-9_]+)`", readme))
+    assert len(documented) >= 15
+    srcs = []
+    for base, _dirs, files in os.walk(os.path.join(ROOT, "egobox_b200")):
+        srcs += [os.path.join(base, f) for f in files if f.endswith((".cu", ".cpp", ".cuh", ".h", ".py"))]
+    srcs.append(os.path.join(ROOT, "bench.py"))
+    text = "\n".join(open(f, errors="ignore").read() for f in srcs)
+    missing = sorted(v for v in documented if '"%s"' % v not in text)
+    assert not missing, missing
