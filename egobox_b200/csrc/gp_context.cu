@@ -154,6 +154,9 @@ struct egx_gp_ctx {
     double* Lsc = nullptr;
     std::vector<long> Lsl_off, Lsc_off;
     bool Lslices_ready = false;
+    int Lsl_pairs_needed = 0;    // pairs a solve reads slices of (trailing rows >= ozaki_min_tri_solve tile rows)
+    int Lsl_pairs_written = 0;   // leading pairs the last factorisation wrote itself (look-ahead schedule, FactorRef::Lsl_w)
+    int graph_Lsl_pairs = 0;     // the same for the captured evaluation
     long long direct_evals = 0;
     // closed-form theta gradient (built lazily): W = L^-T, -R^-1, per-CTA partial sums, term list
     double *tgW = nullptr, *tgRinv = nullptr, *tgPartial = nullptr, *tgGrad = nullptr, *tgGrad_h = nullptr, *tgGamma = nullptr;
@@ -216,7 +219,21 @@ FactorRef factor_ref(egx_gp_ctx* c) {
     return f;
 }
 
-void cholesky(egx_gp_ctx* c) { blocked_sweep(c->env, factor_ref(c), true, nullptr, 0, 0, 0); }
+// Once a model has been asked for a solve on tcgen05 (predict_var, the closed-form gradient) its slice storage exists, and every
+// later factorisation under the look-ahead schedule writes the slices of its panel rows THERE instead of the rotating buffers:
+// they are the slices of the block rows of L the solves need (1 ms to rebuild at n = 8192 otherwise).
+void cholesky(egx_gp_ctx* c) {
+    FactorRef f = factor_ref(c);
+    c->Lsl_pairs_written = 0;
+    if (c->Lsl != nullptr && c->Lsc != nullptr) {
+        f.Lsl_w = c->Lsl;
+        f.Lsc_w = c->Lsc;
+        f.Lsl_off_w = c->Lsl_off.data();
+        f.Lsc_off_w = c->Lsc_off.data();
+        f.Lsl_w_pairs = &c->Lsl_pairs_written;
+    }
+    blocked_sweep(c->env, f, true, nullptr, 0, 0, 0);
+}
 
 // Condition-number test of gp/src/algorithm.rs:1010-1027 on the p x p factor G (host, O(p^3)).
 int cond_status(egx_gp_ctx* c, const double* G) {
@@ -355,6 +372,7 @@ int capture_eval_graph(egx_gp_ctx* c) {
         egx_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
         return EGX_CUDA_ERROR;
     }
+    c->graph_Lsl_pairs = c->Lsl_pairs_written;
     c->graph_nterms = c->nterms;
     c->graph_lookahead = c->env.lookahead;
     c->graph_generation = c->env.generation;
@@ -377,6 +395,7 @@ int evaluate_launch(egx_gp_ctx* c, const double* theta) {
             if (st != EGX_OK) return st;
         }
         for (int i = 0; i < EGX_NUM_STAGES; ++i) c->env.prof.launches[i] += c->graph_launches[i];
+        c->Lsl_pairs_written = c->graph_Lsl_pairs;
         EGX_CUDA_TRY(cudaGraphLaunch(c->eval_graph, c->stream));
     } else {
         st = enqueue_eval(c);
@@ -455,21 +474,27 @@ int ensure_L_slices(egx_gp_ctx* c) {
     const int T = c->npad / EGX_NB;
     if (!c->env.ozaki || T < c->env.ozaki_min_T || T - 2 < c->env.ozaki_min_tri_solve) return EGX_OK;
     if (c->Lsl == nullptr) {
+        // room per pair: its T - k - 2 block rows of L and the appended rows (a factorisation that writes the slices itself
+        // slices the whole panel, appended rows included; the solves read the first T - k - 2 row blocks)
         long bytes = 0, rows = 0;
         c->Lsl_off.assign((T + 1) / 2, 0);
         c->Lsc_off.assign((T + 1) / 2, 0);
         for (int k = 0; k + 2 < T; k += 2) {
             c->Lsl_off[k >> 1] = bytes;
             c->Lsc_off[k >> 1] = rows;
-            bytes += static_cast<long>(ozaki_slice_bytes(static_cast<long>(T - k - 2) * EGX_NB));
-            rows += static_cast<long>(T - k - 2) * EGX_NB;
+            const long rows_k = static_cast<long>(T - k - 2) * EGX_NB + c->qpad;
+            bytes += static_cast<long>(ozaki_slice_bytes(rows_k));
+            rows += rows_k;
         }
         EGX_CUDA_TRY(egx_dev_malloc(&c->Lsl, static_cast<size_t>(bytes)));
         EGX_CUDA_TRY(egx_dev_malloc(&c->Lsc, static_cast<size_t>(rows) * sizeof(double)));
+        c->Lsl_pairs_written = 0;
+        ++c->env.generation;          // a captured evaluation still writes to the rotating buffers: capture again
     }
     for (int k = 0; k + 2 < T; k += 2) {
         const int rows_k = (T - k - 2) * EGX_NB;
         if (rows_k / EGX_NB < c->env.ozaki_min_tri_solve) break;
+        if ((k >> 1) < c->Lsl_pairs_written) continue;          // the factorisation left them there (cholesky())
         StageScope sc(c->env.prof, EGX_STAGE_OZAKI_SLICE, 2, c->stream);
         launch_ozaki_slice(c->M + static_cast<long>(k + 2) * EGX_NB * c->ld + static_cast<long>(k) * EGX_NB, c->ld, rows_k,
                            c->Lsc + c->Lsc_off[k >> 1], c->Lsl + c->Lsl_off[k >> 1], c->stream);

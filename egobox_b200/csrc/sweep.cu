@@ -200,6 +200,7 @@ static void factor_sweep_lookahead(SweepEnv& env, const FactorRef& f) {
     cudaStreamWaitEvent(sq, env.ev_fork, 0);
     auto blk = [&](int r, int c) { return f.M + static_cast<long>(r) * EGX_NB * ld + static_cast<long>(c) * EGX_NB; };
     bool rest_pending = false;       // sq still updates this pair's columns (ev_colrest of the previous pair)
+    int slices_kept = 0;             // leading pairs whose slices went to the caller's persistent buffer (f.Lsl_w)
     for (int k = 0; k < T; k += 2) {
         const int pair = k >> 1;
         double* Pw = env.P2[pair & 1];                 // rows x 256, row 0 = first row of block k+1
@@ -277,6 +278,11 @@ static void factor_sweep_lookahead(SweepEnv& env, const FactorRef& f) {
         if (oz_la) {
             int8_t* S = (pair & 1) ? env.oz_S2 : env.oz_S;
             double* sc = (pair & 1) ? env.oz_scale2 : env.oz_scale;
+            if (f.Lsl_w != nullptr && slices_kept == pair) {     // kept for the solves that follow (predict_var, W = L^-T)
+                S = f.Lsl_w + f.Lsl_off_w[pair];
+                sc = f.Lsc_w + f.Lsc_off_w[pair];
+                ++slices_kept;
+            }
             const size_t rb = ozaki_slice_bytes(EGX_NB);        // bytes of the slices of one 128-row block
             cudaStreamWaitEvent(sq, env.ev_panel[pair], 0);
             if (pair > 0) cudaStreamWaitEvent(sq, env.ev_bulk[pair - 1], 0);
@@ -342,6 +348,7 @@ static void factor_sweep_lookahead(SweepEnv& env, const FactorRef& f) {
     cudaStreamWaitEvent(sb, env.ev_join, 0);
     cudaEventRecord(env.ev_join_q, sq);
     cudaStreamWaitEvent(sb, env.ev_join_q, 0);
+    if (f.Lsl_w_pairs != nullptr) *f.Lsl_w_pairs = slices_kept;
 }
 
 void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows, long ld_rows, int row_tiles_all,
@@ -350,6 +357,7 @@ void blocked_sweep(SweepEnv& env, const FactorRef& f, bool factor, double* rows,
     const long ld = f.ld;
     const long LDP = 2 * EGX_NB;
     const bool la = env.lookahead && factor && T > 4 && static_cast<int>(env.ev_panel.size()) >= (T + 1) / 2;
+    if (f.Lsl_w_pairs != nullptr) *f.Lsl_w_pairs = 0;
     if (la && env.lookahead_v != 1 && env.sq != nullptr && static_cast<int>(env.ev_colrest.size()) >= (T + 1) / 2) {
         factor_sweep_lookahead(env, f);
         return;

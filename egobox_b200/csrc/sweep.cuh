@@ -83,6 +83,15 @@ struct FactorRef {
     const double* Lsc = nullptr;
     const long* Lsl_off = nullptr;
     const long* Lsc_off = nullptr;
+    // optional (factor sweeps with the look-ahead schedule only): write the slices of the panel rows of pair p -- which ARE the
+    // slices of the block rows of L below that pair, the B operand of later solves -- at Lsl_w + Lsl_off_w[p] / Lsc_w + Lsc_off_w[p]
+    // instead of the two rotating buffers; *Lsl_w_pairs = number of leading pairs written (room per pair: T - 2p - 2 row blocks of
+    // L plus the qpad appended rows)
+    int8_t* Lsl_w = nullptr;
+    double* Lsc_w = nullptr;
+    const long* Lsl_off_w = nullptr;
+    const long* Lsc_off_w = nullptr;
+    int* Lsl_w_pairs = nullptr;
 };
 
 // factor = true : in-place Cholesky of f.M (+ appended rows become (L^-1 B)^T)
